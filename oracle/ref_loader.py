@@ -1,0 +1,75 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product package.
+
+Imports the *unmodified* reference (`/root/reference/ultralytics`) inside the dev
+container so that golden vectors can be generated from it (see `gen_golden.py`).
+The reference cannot travel to the GPU box, so nothing in `-m gpu` tests, `smoke()`
+or `bench.py` may call this module; they use the committed fixtures in
+`tests/golden/` instead.
+
+The reference needs three packages that are absent from this image
+(SURVEY.md section 8c): matplotlib (utils/__init__.py:23), pywt (nn/modules/block.py:12,
+conv.py:5) and thop (nn/tasks.py:10).  A meta-path finder hands out empty stub
+modules for them; `pywt.Wavelet("haar")` returns PyWavelets' published Haar taps
+(dec_lo=[s,s], dec_hi=[-s,s], s=1/sqrt(2)) because `_PywtDWT2D.__init__`
+(block.py:3597-3599) reads them.
+"""
+import importlib.abc
+import importlib.machinery
+import math
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("EDGELINE_REFERENCE_ROOT", "/root/reference")
+_STUBBED = ("matplotlib", "pywt", "thop", "seaborn")
+
+
+class _Wavelet:
+    def __init__(self, name):
+        if name != "haar":
+            raise ValueError("stub pywt only provides the Haar wavelet")
+        s = 1.0 / math.sqrt(2.0)
+        self.dec_lo, self.dec_hi = [s, s], [-s, s]
+        self.rec_lo, self.rec_hi = [s, s], [s, -s]
+
+
+class _StubLoader(importlib.abc.Loader):
+    def create_module(self, spec):
+        m = types.ModuleType(spec.name)
+        m.__path__ = []  # behave like a package so `import matplotlib.pyplot` resolves
+        if spec.name == "pywt":
+            m.Wavelet = _Wavelet
+        if spec.name == "thop":
+            m.profile = lambda *a, **k: (0.0, 0.0)
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+class _StubFinder(importlib.abc.MetaPathFinder):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] in _STUBBED:
+            return importlib.machinery.ModuleSpec(fullname, _StubLoader(), is_package=True)
+        return None
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "ultralytics"))
+
+
+def load():
+    """Return the imported reference `ultralytics` package (CPU)."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    os.environ.setdefault("YOLO_CONFIG_DIR", "/tmp/edgeline_yolo_cfg")
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))  # ultralytics/__init__.py:7-9 forces 1
+    os.makedirs(os.environ["YOLO_CONFIG_DIR"], exist_ok=True)
+    sys.dont_write_bytecode = True  # the reference mount is read-only
+    if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
+        sys.meta_path.append(_StubFinder())
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import ultralytics  # noqa: E402
+
+    return ultralytics
