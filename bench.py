@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""EdgeLine-YOLO hot-path benchmark (contract: see the task brief).
+
+  python bench.py [--gpus N --steps K --warmup W]      product arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference ...                 reference arm: the CPU oracle port on the host cores
+
+Workload (BASELINE.json configs[1]): EdgeLine-YOLO-n inference, synthetic 640x640, batch 64 per GPU, bf16,
+8400 anchors, 80 classes; one step = preprocess + model forward + decode + NMS (predict defaults:
+conf 0.25, iou 0.7, max_det 300) over one batch.  N > 1: one process per GPU (torchrun), each with its
+own replica and its own batch shard -- weak scaling, no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "images/sec (EdgeLine-YOLO-n, 640x640, bf16)", "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="edgeline", choices=["edgeline", "reference"])
+    ap.add_argument("--scale", default="n")
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--imgsz", type=int, default=640)
+    ap.add_argument("--nc", type=int, default=80)
+    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel roofline pass")
+    return ap.parse_args()
+
+
+def workload(a):
+    return {"workload": f"EdgeLine-YOLO-{a.scale} inference, synthetic {a.imgsz}x{a.imgsz}, batch {a.batch}/GPU, nc={a.nc}, "
+                        f"{(a.imgsz // 8) ** 2 + (a.imgsz // 16) ** 2 + (a.imgsz // 32) ** 2} anchors, predict defaults (conf .25, iou .7, max_det 300), "
+                        "random-init weights (wave.gamma=0.5, no bias_init)",
+            "batch_per_gpu": a.batch, "imgsz": a.imgsz, "scale": a.scale, "nc": a.nc, "parallelism": f"batch-sharded replicas x{a.gpus}",
+            "l2_policy": "inputs larger than L2 (157 MB bf16 batch; 126 MB L2); per-kernel pass flushes L2 with a 256 MB write"}
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_oracle_rate(a, steps, warmup):
+    """Images/s of the CPU oracle port (reference semantics on the host cores), all torch threads."""
+    import torch
+
+    from oracle import model_ref
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = model_ref.build(a.scale, a.nc, seed=0)
+    x = torch.rand(a.cpu_sample, 3, a.imgsz, a.imgsz, generator=torch.Generator().manual_seed(0))
+    for _ in range(warmup):
+        model_ref.predict(model, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model_ref.predict(model, x)
+    dt = time.perf_counter() - t0
+    return a.cpu_sample * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, ms, threads = cpu_oracle_rate(a, max(1, a.steps), max(1, min(a.warmup, 2)))
+    sample = f"{a.cpu_sample} images per step (bounded sample of the batch-{a.batch} workload), forward + decode + NMS, fp32"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload(a),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- kernel roofline
+def profile_kernels(pred, a, iters=10):
+    """Times every hot-path kernel call of one forward in isolation (CUDA events on the launching stream, L2
+    flushed before each timed launch, GPU kept busy so the events bracket only the kernel) and attaches the
+    algorithmic bytes of SURVEY.md section 8(d)."""
+    import torch
+
+    from edge_yolo_b200 import ops
+
+    calls = []
+    e = lambda t: t.element_size()
+
+    def record(name, fn, nbytes):
+        def wrapped(*args, **kw):
+            out = fn(*args, **kw)
+            calls.append((name, fn, args, kw, nbytes(out, *args, **kw)))
+            return out
+        return wrapped
+
+    shims = {
+        "dwt_haar": lambda out, x: 2 * x.numel() * e(x),
+        "wave_merge": lambda out, b, LLp, *r: int(4.5 * b.numel() * e(b)),
+        "gated_residual": lambda out, b, y, g, **k: 3 * b.numel() * e(b),
+        "linear_attention": lambda out, qkv, heads: (qkv.numel() + out.numel()) * e(qkv),
+        "gfl_decode": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss) + out.numel() * 4,
+        "nms_batched": lambda out, y, *r, **k: y.shape[0] * y.shape[2] * (y.shape[1] - 4) * 4 + out[0].numel() * 4,
+    }
+    saved = {k: getattr(ops, k) for k in shims}
+    try:
+        for k, nb in shims.items():
+            setattr(ops, k, record(k, saved[k], nb))
+        with torch.no_grad():
+            pred._forward(False)
+    finally:
+        for k, v in saved.items():
+            setattr(ops, k, v)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=pred.device)
+    per = {}
+    with torch.no_grad():
+        for name, fn, args, kw, nbytes in calls:
+            ts = []
+            for it in range(iters + 2):
+                flush.zero_()
+                torch.cuda._sleep(200_000)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(*args, **kw)
+                e1.record()
+                e1.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1) * 1e-3)
+            ts.sort()
+            t = ts[len(ts) // 2]
+            d = per.setdefault(name, {"launch_sites": 0, "bytes": 0, "seconds": 0.0})
+            d["launch_sites"] += 1
+            d["bytes"] += nbytes
+            d["seconds"] += t
+    for d in per.values():
+        d["gbs"] = d["bytes"] / d["seconds"] / 1e9
+        d["us"] = d["seconds"] * 1e6
+        del d["seconds"]
+    return per
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ product arm
+def product_arm(a):
+    import torch
+    import torch.distributed as dist
+
+    from edge_yolo_b200 import _lib
+    from edge_yolo_b200.engine import Predictor, build_model
+
+    _lib.lib()  # fail loudly if the extension is missing
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (product arm) needs a GPU; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+
+    model = build_model(a.scale, a.nc, seed=0, device=dev)
+    pred = Predictor(model, a.batch, a.imgsz)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host_u8 = torch.randint(0, 256, (a.batch, a.imgsz, a.imgsz, 3), dtype=torch.uint8, generator=gen).pin_memory()
+    pred.predict_u8(host_u8)  # also leaves a real batch in pred.x
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- leg 1: inputs resident in HBM, device-timed
+    for _ in range(a.warmup):
+        pred.step_device()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(a.steps):
+            pred.step_device()
+        e1.record()
+        e1.synchronize()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        # ---- leg 2: end to end through the public API: pinned host uint8 in, pinned host detections out
+        for _ in range(min(a.warmup, 3)):
+            pred.predict_u8(host_u8)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            rows, cnt = pred.predict_u8(host_u8)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = clk.summary()
+    kept = int(cnt.sum())
+
+    value = world * a.batch * a.steps / (ms_total * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload(a), "clocks": clocks,
+            "e2e": {"value": world * a.batch * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": host_u8.numel(),
+                    "d2h_bytes_per_step": pred.host_out.numel() * 4 + pred.host_cnt.numel() * 4, "ms_per_step": e2e_s / a.steps * 1e3,
+                    "detections_per_step": kept},
+            "gpu_launches": (pred.launches_per_step or 0) * a.steps, "gpu_launches_per_step": pred.launches_per_step}
+
+    if rank == 0 and not a.no_profile:
+        per = profile_kernels(pred, a)
+        peak, peak_src = measured_peak()
+        top = max(per, key=lambda k: per[k]["us"])
+        line["kernels"] = per
+        line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": per[top]["gbs"], "peak": peak, "unit": "GB/s",
+                            "frac": per[top]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                            "note": "achieved = algorithmic bytes of all launch sites of this kernel in one step / their summed CUDA-event time"}
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        rate, ms, threads = cpu_oracle_rate(a, steps=3, warmup=1)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"3 steps x {a.cpu_sample} images (bounded sample of the batch-{a.batch} workload), forward + decode + NMS, fp32"}
+    if world > 1:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        product_arm(args)

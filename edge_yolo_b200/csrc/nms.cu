@@ -1,0 +1,521 @@
+// Batched, sync-free GPU NMS.  Replaces non_max_suppression (utils/ops.py:167-316) and the
+// torchvision.ops.nms call inside it (ops.py:296) for detection outputs (nm=0, not rotated).
+//
+// Pipeline per call (all device-side, no host round trip, CUDA-graph capturable):
+//   1. emit      : conf filter + multi-label expansion / first-max class -> 64-bit keys
+//                  key = score_bits << 32 | ~(anchor*nc+cls)   (unique, so "descending key" ==
+//                  "stable descending score, ties by ascending candidate index" == torchvision order)
+//   2. select    : only if more than max_nms candidates are possible: exact radix select of the
+//                  max_nms-th largest key (8 x 8-bit passes) + compaction (ops.py:285-286)
+//   3. sort      : bitonic sort of the keys, descending (shared-memory for <= 16384 keys/image)
+//   4. sweep     : one CTA per image walks the sorted candidates in chunks of 256, keeps the list
+//                  of kept boxes in shared memory and stops at max_det keeps.  Work is
+//                  n x kept IoUs instead of the n^2/2 of a bitmask matrix, and there is no
+//                  n x n/64 mask in HBM.
+// IoU arithmetic replicates torchvision's fp32 sequence with round-to-nearest intrinsics (no FMA
+// contraction) so keep decisions are bit-exact against the CPU op.
+#include "el_common.cuh"
+
+namespace el {
+
+constexpr int kSortChunk = 16384;  // keys sorted per CTA in shared memory (128 KiB)
+constexpr int kSortThreads = 1024;
+constexpr int kSweepThreads = 256;
+constexpr int kMaxDetSmem = 4096;
+
+__host__ __device__ inline uint32_t pow2ceil(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ------------------------------------------------------------------------------- 1. emit
+template <bool MULTI>
+__global__ void __launch_bounds__(256) nms_emit(const float* __restrict__ pred, int nc, int A, float conf, const int32_t* __restrict__ class_keep,
+                                                unsigned long long* __restrict__ keys, int64_t key_stride, int* __restrict__ counts) {
+    const int b = blockIdx.y, a = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const float* p = pred + ((int64_t)b * (4 + nc) + 4) * A;
+    unsigned long long* kb = keys + (int64_t)b * key_stride;
+    const bool in = a < A;
+    if (MULTI) {
+        for (int c = 0; c < nc; ++c) {
+            float s = in ? __ldg(p + (int64_t)c * A + a) : 0.f;
+            bool pass = in && s > conf && (!class_keep || class_keep[c]);
+            unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(counts + b, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) {
+                    uint32_t idx = (uint32_t)a * (uint32_t)nc + (uint32_t)c;
+                    kb[base + __popc(m & ((1u << lane) - 1))] = ((unsigned long long)__float_as_uint(s) << 32) | (uint32_t)(~idx);
+                }
+            }
+        }
+    } else {
+        float best = -INFINITY;
+        int j = 0;
+        if (in)
+            for (int c = 0; c < nc; ++c) {  // first maximum, like cls.max(1) on the CPU (ops.py:274)
+                float s = __ldg(p + (int64_t)c * A + a);
+                if (s > best) { best = s; j = c; }
+            }
+        bool pass = in && best > conf && (!class_keep || class_keep[j]);
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(counts + b, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
+                uint32_t idx = (uint32_t)a * (uint32_t)nc + (uint32_t)j;
+                kb[base + __popc(m & ((1u << lane) - 1))] = ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)(~idx);
+            }
+        }
+    }
+}
+
+// keys for the plain nms(boxes, scores) entry: any float score, order-preserving bit map
+__global__ void __launch_bounds__(256) nms_box_keys(const float* __restrict__ scores, int n, unsigned long long* __restrict__ keys, int* __restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count = n;
+    if (i >= n) return;
+    uint32_t u = __float_as_uint(scores[i]);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone float -> uint
+    keys[i] = ((unsigned long long)u << 32) | (uint32_t)(~(uint32_t)i);
+}
+
+// ------------------------------------------------------------------------------- 2. select
+struct SelectState {            // per image
+    unsigned long long prefix;  // high bits of the k-th largest key found so far
+    int k_rem;                  // rank still to resolve inside the current prefix
+    int count2;                 // compacted count
+};
+
+__global__ void __launch_bounds__(256) select_hist(const unsigned long long* __restrict__ keys, int64_t key_stride, const int* __restrict__ counts,
+                                                   int max_nms, const SelectState* __restrict__ st, unsigned* __restrict__ hist, int shift) {
+    const int b = blockIdx.y, n = counts[b];
+    if (n <= max_nms) return;
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long pre = st[b].prefix;
+    const unsigned long long* kb = keys + (int64_t)b * key_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned long long k = kb[i];
+        bool match = shift >= 56 ? true : ((k >> (shift + 8)) == (pre >> (shift + 8)));
+        if (match) atomicAdd(&h[(unsigned)(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(hist + b * 256 + threadIdx.x, h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) select_pick(const int* __restrict__ counts, int max_nms, SelectState* __restrict__ st, unsigned* __restrict__ hist,
+                                                   int shift) {
+    const int b = blockIdx.x, d = threadIdx.x;
+    if (counts[b] <= max_nms) return;
+    __shared__ unsigned suf[257];
+    unsigned mine = hist[b * 256 + d];
+    hist[b * 256 + d] = 0;  // ready for the next pass
+    suf[d] = mine;
+    if (d == 0) suf[256] = 0;
+    __syncthreads();
+    // inclusive suffix sum (Hillis-Steele over 256 entries)
+    for (int o = 1; o < 256; o <<= 1) {
+        unsigned v = (d + o < 256) ? suf[d + o] : 0;
+        __syncthreads();
+        suf[d] += v;
+        __syncthreads();
+    }
+    const unsigned k = (unsigned)st[b].k_rem;
+    __syncthreads();
+    if (suf[d] >= k && suf[d + 1] < k) {  // exactly one digit satisfies this
+        st[b].prefix |= (unsigned long long)d << shift;
+        st[b].k_rem = (int)(k - suf[d + 1]);
+    }
+}
+
+__global__ void __launch_bounds__(256) select_compact(const unsigned long long* __restrict__ keys, int64_t key_stride, const int* __restrict__ counts,
+                                                      int max_nms, SelectState* __restrict__ st, unsigned long long* __restrict__ keys2,
+                                                      int64_t key2_stride) {
+    const int b = blockIdx.y, n = counts[b], lane = threadIdx.x & 31;
+    const unsigned long long thr = n > max_nms ? st[b].prefix : 0ull;  // keys are unique: exactly max_nms keys are >= thr
+    const unsigned long long* kb = keys + (int64_t)b * key_stride;
+    unsigned long long* ob = keys2 + (int64_t)b * key2_stride;
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        unsigned long long k = i < n ? kb[i] : 0ull;
+        bool pass = i < n && k >= thr;
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&st[b].count2, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) ob[base + __popc(m & ((1u << lane) - 1))] = k;
+        }
+    }
+}
+
+__global__ void init_select(SelectState* st, int B, int max_nms) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) { st[b].prefix = 0; st[b].k_rem = max_nms; st[b].count2 = 0; }
+}
+
+// ------------------------------------------------------------------------------- 3. sort
+// count source: plain int array or SelectState.count2
+__device__ __forceinline__ int seg_count(const int* counts, const SelectState* st, int b, int cap) {
+    int n = st ? st[b].count2 : counts[b];
+    return n < cap ? n : cap;
+}
+
+// compare-exchange network on shared memory; element i sorts descending iff (g & k) == 0, g = global index
+__device__ __forceinline__ void bitonic_smem(unsigned long long* s, int n_local, int g_base, int k_lo, int k_hi, int j_hi_first) {
+    for (int k = k_lo; k <= k_hi; k <<= 1) {
+        int j0 = (k == k_lo && j_hi_first) ? j_hi_first : (k >> 1);
+        if (j0 > (n_local >> 1)) j0 = n_local >> 1;
+        for (int j = j0; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n_local >> 1); t += blockDim.x) {
+                int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
+                int p = i | j;
+                bool desc = (((g_base + i) & k) == 0);
+                unsigned long long a = s[i], c = s[p];
+                if ((a < c) == desc) { s[i] = c; s[p] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// whole segment in one CTA (capacity <= kSortChunk)
+__global__ void __launch_bounds__(kSortThreads) sort_single(unsigned long long* __restrict__ keys, int64_t key_stride, const int* __restrict__ counts,
+                                                             const SelectState* __restrict__ st, int cap) {
+    extern __shared__ unsigned long long sk[];
+    const int b = blockIdx.x;
+    const int n = seg_count(counts, st, b, cap);
+    if (n <= 1) return;
+    const int m = (int)pow2ceil((uint32_t)n);
+    unsigned long long* kb = keys + (int64_t)b * key_stride;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) sk[i] = i < n ? kb[i] : 0ull;
+    __syncthreads();
+    bitonic_smem(sk, m, 0, 2, m, 0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) kb[i] = sk[i];
+}
+
+// multi-CTA path: (a) sort every chunk, (b) global exchange steps for j >= chunk, (c) finish inside chunks
+__global__ void __launch_bounds__(kSortThreads) sort_chunks(unsigned long long* __restrict__ keys, int64_t key_stride, const int* __restrict__ counts,
+                                                             const SelectState* __restrict__ st, int cap) {
+    extern __shared__ unsigned long long sk[];
+    const int b = blockIdx.y, base = blockIdx.x * kSortChunk;
+    const int n = seg_count(counts, st, b, cap);
+    if (base >= (int)pow2ceil((uint32_t)(n > 1 ? n : 1)) && base > 0) return;
+    unsigned long long* kb = keys + (int64_t)b * key_stride + base;
+    for (int i = threadIdx.x; i < kSortChunk; i += blockDim.x) sk[i] = (base + i) < n ? kb[i] : 0ull;
+    __syncthreads();
+    bitonic_smem(sk, kSortChunk, base, 2, kSortChunk, 0);
+    for (int i = threadIdx.x; i < kSortChunk; i += blockDim.x) kb[i] = sk[i];  // padded capacity is a chunk multiple
+}
+
+__global__ void __launch_bounds__(256) sort_global_step(unsigned long long* __restrict__ keys, int64_t key_stride, const int* __restrict__ counts,
+                                                        const SelectState* __restrict__ st, int cap, int cap_pow2, int k, int j) {
+    const int b = blockIdx.y;
+    const int n = seg_count(counts, st, b, cap);
+    const int m = (int)pow2ceil((uint32_t)(n > 1 ? n : 1));
+    if (k > m) return;  // stage not needed for this image
+    unsigned long long* kb = keys + (int64_t)b * key_stride;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < (m >> 1); t += gridDim.x * blockDim.x) {
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int p = i | j;
+        bool desc = ((i & k) == 0);
+        unsigned long long a = kb[i], c = kb[p];
+        if ((a < c) == desc) { kb[i] = c; kb[p] = a; }
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) sort_chunk_merge(unsigned long long* __restrict__ keys, int64_t key_stride, const int* __restrict__ counts,
+                                                                  const SelectState* __restrict__ st, int cap, int k) {
+    extern __shared__ unsigned long long sk[];
+    const int b = blockIdx.y, base = blockIdx.x * kSortChunk;
+    const int n = seg_count(counts, st, b, cap);
+    const int m = (int)pow2ceil((uint32_t)(n > 1 ? n : 1));
+    if (k > m || base >= m) return;
+    unsigned long long* kb = keys + (int64_t)b * key_stride + base;
+    for (int i = threadIdx.x; i < kSortChunk; i += blockDim.x) sk[i] = kb[i];
+    __syncthreads();
+    bitonic_smem(sk, kSortChunk, base, k, k, kSortChunk >> 1);
+    for (int i = threadIdx.x; i < kSortChunk; i += blockDim.x) kb[i] = sk[i];
+}
+
+// ------------------------------------------------------------------------------- 4. sweep
+// torchvision's IoU test with every fp32 rounding made explicit (no FMA contraction):
+//   inter/(Sa+Sb-inter) > thr ; thr is the double threshold rounded DOWN to float, which makes the
+//   float compare equivalent to torchvision's CPU compare of the float IoU against a double.
+__device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1, float bx2, float by2, float barea,
+                                       float thr) {
+    float left = fmaxf(ax1, bx1), right = fminf(ax2, bx2), top = fmaxf(ay1, by1), bottom = fminf(ay2, by2);
+    float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+    float inter = __fmul_rn(w, h);
+    float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
+    return __fdiv_rn(inter, uni) > thr;
+}
+
+struct SweepArgs {
+    const unsigned long long* keys; int64_t key_stride;
+    const int* counts; const SelectState* st; int cap;
+    // FROM_PRED: boxes decoded from pred (B,4+nc,A); else raw boxes (n,4)
+    const float* pred; int nc, A; float max_wh; int agnostic;
+    const float* boxes;
+    float thr; int max_det;
+    float* out; int32_t* out_count; int64_t* out_index;  // batched outputs
+    int64_t* keep;                                       // nms_boxes output
+    float* gkept;                                        // global kept list (5 x cap) when !SMEM_KEPT
+};
+
+template <bool SMEM_KEPT, bool FROM_PRED>
+__global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant__ SweepArgs P) {
+    extern __shared__ float s_kept[];  // [5][kcap] when SMEM_KEPT
+    __shared__ int s_nk[2];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = seg_count(P.counts, P.st, b, P.cap);
+    const int kcap = SMEM_KEPT ? P.max_det : P.cap;
+    float* kx1 = SMEM_KEPT ? s_kept : P.gkept;
+    float *ky1 = kx1 + kcap, *kx2 = ky1 + kcap, *ky2 = kx2 + kcap, *kar = ky2 + kcap;
+    const unsigned long long* kb = P.keys + (int64_t)b * P.key_stride;
+    if (tid == 0) { s_nk[0] = 0; s_nk[1] = 0; }
+    __syncthreads();
+    int step = 0;
+    bool done = false;
+    for (int c0 = 0; c0 < n && !done; c0 += kSweepThreads) {
+        const int i = c0 + tid;
+        const bool valid = i < n;
+        float rx1 = 0.f, ry1 = 0.f, rx2 = 0.f, ry2 = 0.f, score = 0.f, clsf = 0.f;
+        float ox1 = 0.f, oy1 = 0.f, ox2 = 0.f, oy2 = 0.f, area = 0.f;
+        uint32_t idx = 0;
+        if (valid) {
+            unsigned long long k = kb[i];
+            idx = ~(uint32_t)k;
+            if (FROM_PRED) {
+                score = __uint_as_float((uint32_t)(k >> 32));
+                uint32_t a = idx / (uint32_t)P.nc, c = idx - a * (uint32_t)P.nc;
+                const float* pb = P.pred + (int64_t)b * (4 + P.nc) * P.A + a;
+                float cx = __ldg(pb), cy = __ldg(pb + P.A), w = __ldg(pb + 2 * (int64_t)P.A), h = __ldg(pb + 3 * (int64_t)P.A);
+                float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);  // xywh2xyxy, ops.py:416-433
+                rx1 = __fsub_rn(cx, hw); ry1 = __fsub_rn(cy, hh); rx2 = __fadd_rn(cx, hw); ry2 = __fadd_rn(cy, hh);
+                clsf = (float)c;
+                float off = P.agnostic ? 0.f : __fmul_rn(clsf, P.max_wh);  // ops.py:289
+                ox1 = __fadd_rn(rx1, off); oy1 = __fadd_rn(ry1, off); ox2 = __fadd_rn(rx2, off); oy2 = __fadd_rn(ry2, off);
+            } else {
+                const float4 bx = __ldg(reinterpret_cast<const float4*>(P.boxes) + idx);
+                ox1 = bx.x; oy1 = bx.y; ox2 = bx.z; oy2 = bx.w;
+            }
+            area = __fmul_rn(__fsub_rn(ox2, ox1), __fsub_rn(oy2, oy1));
+        }
+        bool alive = valid;
+        int checked = 0;  // candidates of this chunk have not been tested against anything yet
+        for (int sub = 0; sub < kSweepThreads / 32; ++sub, ++step) {
+            if (c0 + sub * 32 >= n) break;  // no candidates left for the remaining warps (uniform)
+            const int nk = s_nk[step & 1];
+            if (warp >= sub && alive) {
+                for (int j = checked; j < nk; ++j) {
+                    if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
+                }
+            }
+            checked = nk;
+            if (warp == sub) {
+                // greedy resolution inside the warp: the lowest alive lane is kept, then kills its overlaps
+                unsigned m = __ballot_sync(0xffffffffu, alive), K = 0;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    K |= 1u << j;
+                    float jx1 = __shfl_sync(0xffffffffu, ox1, j), jy1 = __shfl_sync(0xffffffffu, oy1, j);
+                    float jx2 = __shfl_sync(0xffffffffu, ox2, j), jy2 = __shfl_sync(0xffffffffu, oy2, j);
+                    float jar = __shfl_sync(0xffffffffu, area, j);
+                    if (alive && lane > j && iou_gt(jx1, jy1, jx2, jy2, jar, ox1, oy1, ox2, oy2, area, P.thr)) alive = false;
+                    m = __ballot_sync(0xffffffffu, alive) & ~((2u << j) - 1u);
+                }
+                const int rank = nk + __popc(K & ((1u << lane) - 1u));
+                if (((K >> lane) & 1u) && rank < P.max_det) {
+                    kx1[rank] = ox1; ky1[rank] = oy1; kx2[rank] = ox2; ky2[rank] = oy2; kar[rank] = area;
+                    if (FROM_PRED) {
+                        float* o = P.out + ((int64_t)b * P.max_det + rank) * 6;
+                        o[0] = rx1; o[1] = ry1; o[2] = rx2; o[3] = ry2; o[4] = score; o[5] = clsf;
+                        if (P.out_index) P.out_index[(int64_t)b * P.max_det + rank] = (int64_t)idx;
+                    } else {
+                        P.keep[rank] = (int64_t)idx;
+                    }
+                }
+                if (lane == 0) {
+                    int nn = nk + __popc(K);
+                    s_nk[(step + 1) & 1] = nn < P.max_det ? nn : P.max_det;
+                }
+            }
+            __syncthreads();  // also publishes global-memory kept entries to the other warps of the CTA
+            if (s_nk[(step + 1) & 1] >= P.max_det) { done = true; ++step; break; }
+        }
+    }
+    if (tid == 0) P.out_count[b] = s_nk[step & 1];
+}
+
+struct NmsLayout {
+    size_t counts, state, hist, keys, keys2, total;
+    int64_t key_stride, key2_stride;
+    int cap, cap2;
+    bool select;
+};
+
+static NmsLayout nms_layout(int B, int nc, int A, int multi, int max_nms) {
+    NmsLayout L{};
+    const int64_t cand = multi ? (int64_t)A * nc : (int64_t)A;
+    L.select = cand > max_nms;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    L.counts = off; off = al(off + sizeof(int) * B);
+    L.state = off; off = al(off + sizeof(SelectState) * B);
+    L.hist = off; off = al(off + sizeof(unsigned) * 256 * B);
+    if (L.select) {
+        L.cap = (int)cand;
+        L.key_stride = cand;
+        L.cap2 = max_nms;
+        uint32_t p2 = pow2ceil((uint32_t)max_nms);
+        L.key2_stride = p2 <= (uint32_t)kSortChunk ? p2 : ceil_div(p2, kSortChunk) * kSortChunk;
+    } else {
+        L.cap = (int)cand;
+        uint32_t p2 = pow2ceil((uint32_t)cand);
+        L.key_stride = p2 <= (uint32_t)kSortChunk ? p2 : ceil_div(p2, kSortChunk) * kSortChunk;
+        L.cap2 = 0; L.key2_stride = 0;
+    }
+    L.keys = off; off = al(off + sizeof(unsigned long long) * L.key_stride * B);
+    L.keys2 = off; off = al(off + sizeof(unsigned long long) * L.key2_stride * B);
+    L.total = off;
+    return L;
+}
+
+// sort `B` segments of capacity `cap` (pow2-padded stride) in place
+static void launch_sort(unsigned long long* keys, int64_t stride, const int* counts, const SelectState* st, int cap, int B, cudaStream_t s) {
+    const uint32_t p2 = pow2ceil((uint32_t)(cap > 1 ? cap : 1));
+    if (p2 <= (uint32_t)kSortChunk) {
+        note_launches(1);
+        size_t sm = (size_t)p2 * sizeof(unsigned long long);
+        if (sm > 48 * 1024) cudaFuncSetAttribute(sort_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        sort_single<<<B, kSortThreads, sm, s>>>(keys, stride, counts, st, cap);
+        return;
+    }
+    const size_t sm = (size_t)kSortChunk * sizeof(unsigned long long);
+    cudaFuncSetAttribute(sort_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(sort_chunk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    const int chunks = (int)(p2 / kSortChunk);
+    sort_chunks<<<dim3(chunks, B), kSortThreads, sm, s>>>(keys, stride, counts, st, cap);
+    note_launches(1);
+    for (uint32_t k = 2u * kSortChunk; k <= p2; k <<= 1) {
+        for (uint32_t j = k >> 1; j >= (uint32_t)kSortChunk; j >>= 1) {
+            int blocks = (int)(p2 / 2 / 256);
+            if (blocks > kSMs * 8) blocks = kSMs * 8;
+            sort_global_step<<<dim3(blocks, B), 256, 0, s>>>(keys, stride, counts, st, cap, (int)p2, (int)k, (int)j);
+            note_launches(1);
+        }
+        sort_chunk_merge<<<dim3(chunks, B), kSortThreads, sm, s>>>(keys, stride, counts, st, cap, (int)k);
+        note_launches(1);
+    }
+}
+
+static float threshold_round_down(double thr) {
+    float f = (float)thr;
+    if ((double)f > thr) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+}  // namespace el
+
+using namespace el;
+
+extern "C" int el_nms_workspace_bytes(int B, int nc, int A, int multi_label, int max_nms, size_t* bytes) {
+    if (!bytes || B <= 0 || nc <= 0 || A <= 0 || max_nms <= 0) return EL_ERR_ARG;
+    if ((int64_t)A * nc >= (int64_t)1 << 31) return EL_ERR_UNSUPPORTED;
+    *bytes = nms_layout(B, nc, A, multi_label && nc > 1, max_nms).total;
+    return EL_OK;
+}
+
+extern "C" int el_nms_batched(const float* pred, int B, int nc, int A, float conf, double iou, int multi_label, int agnostic, const int32_t* class_keep,
+                              int max_det, int max_nms, float max_wh, void* workspace, size_t workspace_bytes, float* out, int32_t* out_count,
+                              int64_t* out_index, void* stream) {
+    if (!pred || !workspace || !out || !out_count || B <= 0 || nc <= 0 || A <= 0 || max_det <= 0 || max_nms <= 0) return EL_ERR_ARG;
+    if (conf < 0.f || conf > 1.f || iou < 0.0 || iou > 1.0) return EL_ERR_ARG;  // ops.py:217-218
+    if ((int64_t)A * nc >= (int64_t)1 << 31) return EL_ERR_UNSUPPORTED;
+    if (max_det > kMaxDetSmem) return EL_ERR_UNSUPPORTED;
+    const bool multi = multi_label && nc > 1;  // ops.py:239
+    const NmsLayout L = nms_layout(B, nc, A, multi, max_nms);
+    if (workspace_bytes < L.total) return EL_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    int* counts = (int*)(ws + L.counts);
+    SelectState* st = (SelectState*)(ws + L.state);
+    unsigned* hist = (unsigned*)(ws + L.hist);
+    unsigned long long* keys = (unsigned long long*)(ws + L.keys);
+    unsigned long long* keys2 = (unsigned long long*)(ws + L.keys2);
+
+    cudaMemsetAsync(ws, 0, L.keys, s);  // counts, select state, histograms
+    dim3 eg((A + 255) / 256, B);
+    if (multi)
+        nms_emit<true><<<eg, 256, 0, s>>>(pred, nc, A, conf, class_keep, keys, L.key_stride, counts);
+    else
+        nms_emit<false><<<eg, 256, 0, s>>>(pred, nc, A, conf, class_keep, keys, L.key_stride, counts);
+
+    SweepArgs P{};
+    if (L.select) {
+        init_select<<<(B + 127) / 128, 128, 0, s>>>(st, B, max_nms);
+        int hb = (int)ceil_div(L.cap, 256 * 16);
+        if (hb > 64) hb = 64;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            select_hist<<<dim3(hb, B), 256, 0, s>>>(keys, L.key_stride, counts, max_nms, st, hist, shift);
+            select_pick<<<B, 256, 0, s>>>(counts, max_nms, st, hist, shift);
+        }
+        select_compact<<<dim3(hb, B), 256, 0, s>>>(keys, L.key_stride, counts, max_nms, st, keys2, L.key2_stride);
+        note_launches(18);
+        launch_sort(keys2, L.key2_stride, nullptr, st, L.cap2, B, s);
+        P.keys = keys2; P.key_stride = L.key2_stride; P.counts = nullptr; P.st = st; P.cap = L.cap2;
+    } else {
+        launch_sort(keys, L.key_stride, counts, nullptr, L.cap, B, s);
+        P.keys = keys; P.key_stride = L.key_stride; P.counts = counts; P.st = nullptr; P.cap = L.cap;
+    }
+    P.pred = pred; P.nc = nc; P.A = A; P.max_wh = max_wh; P.agnostic = agnostic;
+    P.thr = threshold_round_down(iou); P.max_det = max_det;
+    P.out = out; P.out_count = out_count; P.out_index = out_index;
+    size_t sm = (size_t)5 * max_det * sizeof(float);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(nms_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    nms_sweep<true, true><<<B, kSweepThreads, sm, s>>>(P);
+    note_launches(2);  // emit + sweep
+    return check_launch();
+}
+
+extern "C" int el_nms_boxes_workspace_bytes(int n, size_t* bytes) {
+    if (!bytes || n < 0) return EL_ERR_ARG;
+    uint32_t p2 = pow2ceil((uint32_t)(n > 1 ? n : 1));
+    int64_t stride = p2 <= (uint32_t)kSortChunk ? p2 : ceil_div(p2, kSortChunk) * kSortChunk;
+    *bytes = 256 + sizeof(unsigned long long) * stride + sizeof(float) * 5 * (size_t)(n > 0 ? n : 1) + 256;
+    return EL_OK;
+}
+
+extern "C" int el_nms_boxes(const float* boxes, const float* scores, int n, double iou, void* workspace, size_t workspace_bytes, int64_t* keep,
+                            int32_t* keep_count, void* stream) {
+    if (!keep_count || n < 0 || iou < 0.0 || iou > 1.0) return EL_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(keep_count, 0, sizeof(int32_t), s); return check_launch(); }
+    if (!boxes || !scores || !workspace || !keep) return EL_ERR_ARG;
+    if (!aligned16(boxes)) return EL_ERR_ARG;
+    size_t need;
+    el_nms_boxes_workspace_bytes(n, &need);
+    if (workspace_bytes < need) return EL_ERR_WORKSPACE;
+    uint32_t p2 = pow2ceil((uint32_t)(n > 1 ? n : 1));
+    int64_t stride = p2 <= (uint32_t)kSortChunk ? p2 : ceil_div(p2, kSortChunk) * kSortChunk;
+    char* ws = (char*)workspace;
+    int* count = (int*)ws;
+    unsigned long long* keys = (unsigned long long*)(ws + 256);
+    float* gkept = (float*)(ws + 256 + sizeof(unsigned long long) * stride);
+    nms_box_keys<<<(n + 255) / 256, 256, 0, s>>>(scores, n, keys, count);
+    launch_sort(keys, stride, count, nullptr, n, 1, s);
+    SweepArgs P{};
+    P.keys = keys; P.key_stride = stride; P.counts = count; P.st = nullptr; P.cap = n;
+    P.boxes = boxes; P.thr = threshold_round_down(iou); P.max_det = n;
+    P.out_count = keep_count; P.keep = keep; P.gkept = gkept;
+    nms_sweep<false, false><<<1, kSweepThreads, 0, s>>>(P);
+    note_launches(2);  // keys + sweep
+    return check_launch();
+}

@@ -1,0 +1,536 @@
+// Haar DWT split / adjoint, sub-band merge (bilinear up * w + concat) and gated residual for the
+// DSC3K2_Wavelet neck.  Replaces _PywtDWT2D.forward (nn/modules/block.py:3619-3642) and the
+// elementwise tail of _WaveletEnhancer.forward (block.py:3696-3710) of the reference.
+//
+// All kernels are HBM-bound streaming kernels: the fast path walks channel-contiguous (NHWC or
+// NHWC channel-slice) views with 16-byte vectors, one vector per thread per tap; a generic
+// strided kernel (thread order follows the fastest-moving stride) covers NCHW and odd shapes.
+#include "el_common.cuh"
+
+namespace el {
+
+// float32(2^-1/2)^2 -- the value of every tap _PywtDWT2D builds (block.py:3597-3609), NOT 0.5.
+__device__ __constant__ float kHaar = 0.49999997f;
+
+// ------------------------------------------------------------------------------- DWT forward
+template <typename T>
+__global__ void __launch_bounds__(256) dwt_fwd_cvec(const T* __restrict__ x, Strides4 xs, T* __restrict__ o, int64_t ob, Strides4 os,
+                                                    int CV, int H2, int W2, int64_t total) {
+    constexpr int V = Vec16<T>::N;
+    const float k = kHaar;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(idx % CV);
+        int64_t t = idx / CV;
+        int j = (int)(t % W2); t /= W2;
+        int i = (int)(t % H2);
+        int64_t n = t / H2;
+        const T* p = x + n * xs.n + (int64_t)(2 * i) * xs.h + (int64_t)(2 * j) * xs.w + cv * V;
+        float a[V], b[V], c[V], d[V];
+        uint4 ra = ldg_stream(p), rb = ldg_stream(p + xs.w), rc = ldg_stream(p + xs.h), rd = ldg_stream(p + xs.h + xs.w);
+        unpack<T>(ra, a); unpack<T>(rb, b); unpack<T>(rc, c); unpack<T>(rd, d);
+        float ll[V], lh[V], hl[V], hh[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            float s0 = a[e] + b[e], s1 = c[e] + d[e], d0 = a[e] - b[e], d1 = c[e] - d[e];
+            ll[e] = k * (s0 + s1);
+            lh[e] = k * (d0 + d1);
+            hl[e] = k * (s0 - s1);
+            hh[e] = k * (d0 - d1);
+        }
+        T* q = o + n * os.n + (int64_t)i * os.h + (int64_t)j * os.w + cv * V;
+        *reinterpret_cast<uint4*>(q) = pack<T>(ll);
+        *reinterpret_cast<uint4*>(q + ob) = pack<T>(lh);
+        *reinterpret_cast<uint4*>(q + 2 * ob) = pack<T>(hl);
+        *reinterpret_cast<uint4*>(q + 3 * ob) = pack<T>(hh);
+    }
+}
+
+// decompose a flat index over (n, c, i, j) with either c or j moving fastest
+template <bool CH_FAST>
+__device__ __forceinline__ void split_ncij(int64_t idx, int C, int I, int J, int64_t& n, int& c, int& i, int& j) {
+    if (CH_FAST) {
+        c = (int)(idx % C); idx /= C;
+        j = (int)(idx % J); idx /= J;
+        i = (int)(idx % I); n = idx / I;
+    } else {
+        j = (int)(idx % J); idx /= J;
+        i = (int)(idx % I); idx /= I;
+        c = (int)(idx % C); n = idx / C;
+    }
+}
+
+template <typename T, bool CH_FAST>
+__global__ void __launch_bounds__(256) dwt_fwd_generic(const T* __restrict__ x, Strides4 xs, T* __restrict__ o, int64_t ob, Strides4 os,
+                                                       int C, int H2, int W2, int64_t total) {
+    const float k = kHaar;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n; int c, i, j;
+        split_ncij<CH_FAST>(idx, C, H2, W2, n, c, i, j);
+        const T* p = x + n * xs.n + (int64_t)c * xs.c + (int64_t)(2 * i) * xs.h + (int64_t)(2 * j) * xs.w;
+        float a = to_f(p[0]), b = to_f(p[xs.w]), cc = to_f(p[xs.h]), d = to_f(p[xs.h + xs.w]);
+        float s0 = a + b, s1 = cc + d, d0 = a - b, d1 = cc - d;
+        T* q = o + n * os.n + (int64_t)c * os.c + (int64_t)i * os.h + (int64_t)j * os.w;
+        q[0] = from_f<T>(k * (s0 + s1));
+        q[ob] = from_f<T>(k * (d0 + d1));
+        q[2 * ob] = from_f<T>(k * (s0 - s1));
+        q[3 * ob] = from_f<T>(k * (d0 - d1));
+    }
+}
+
+// ------------------------------------------------------------------------------- DWT adjoint
+// One thread per 2x2 output quad (ceil sizes so odd trailing rows/cols get their zeros).
+template <typename T, bool CH_FAST>
+__global__ void __launch_bounds__(256) dwt_bwd_generic(const T* __restrict__ g, int64_t gb, Strides4 gs, T* __restrict__ o, Strides4 os,
+                                                       int C, int H, int W, int64_t total) {
+    const float k = kHaar;
+    const int H2 = H / 2, W2 = W / 2, HQ = (H + 1) / 2, WQ = (W + 1) / 2;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n; int c, i, j;
+        split_ncij<CH_FAST>(idx, C, HQ, WQ, n, c, i, j);
+        T* q = o + n * os.n + (int64_t)c * os.c + (int64_t)(2 * i) * os.h + (int64_t)(2 * j) * os.w;
+        if (i < H2 && j < W2) {
+            const T* p = g + n * gs.n + (int64_t)c * gs.c + (int64_t)i * gs.h + (int64_t)j * gs.w;
+            float ll = to_f(p[0]), lh = to_f(p[gb]), hl = to_f(p[2 * gb]), hh = to_f(p[3 * gb]);
+            float s0 = ll + lh, s1 = hl + hh, d0 = ll - lh, d1 = hl - hh;
+            q[0] = from_f<T>(k * (s0 + s1));
+            q[os.w] = from_f<T>(k * (d0 + d1));
+            q[os.h] = from_f<T>(k * (s0 - s1));
+            q[os.h + os.w] = from_f<T>(k * (d0 - d1));
+        } else {  // pixels the floor()ed analysis never read
+            const T z = from_f<T>(0.f);
+            q[0] = z;
+            if (2 * j + 1 < W) q[os.w] = z;
+            if (2 * i + 1 < H) {
+                q[os.h] = z;
+                if (2 * j + 1 < W) q[os.h + os.w] = z;
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- merge forward
+struct BandPtrs {
+    const void* p[4];
+    Strides4 s[4];
+};
+struct BandPtrsMut {
+    void* p[4];
+    Strides4 s[4];
+};
+
+__device__ __forceinline__ void band_weights(const float* __restrict__ alpha, float (&w)[4]) {
+    // softplus(alpha) / (sum + 1e-6), block.py:3696-3697 (torch softplus: x > 20 -> x)
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float a = __ldg(alpha + i);
+        w[i] = a > 20.f ? a : log1pf(expf(a));
+        s += w[i];
+    }
+    s += 1e-6f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = w[i] / s;
+}
+
+// PyTorch upsample_bilinear2d source rule, align_corners=False
+__device__ __forceinline__ void bilin_src(int dst, float scale, int n_in, int& i0, int& i1, float& lam) {
+    float src = scale * (dst + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = (int)src;
+    if (i0 > n_in - 1) i0 = n_in - 1;
+    i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    lam = src - (float)i0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) merge_fwd_cvec(const T* __restrict__ b, Strides4 bs, BandPtrs bands, const float* __restrict__ alpha,
+                                                      T* __restrict__ out, Strides4 os, int c, int H, int W, int h, int w, int64_t total) {
+    constexpr int V = Vec16<T>::N;
+    __shared__ float sw[4];
+    if (threadIdx.x == 0) {
+        float wt[4];
+        band_weights(alpha, wt);
+        sw[0] = wt[0]; sw[1] = wt[1]; sw[2] = wt[2]; sw[3] = wt[3];
+    }
+    __syncthreads();
+    const int CV = 3 * c / V, half = c / 2;
+    const float sh = (float)h / (float)H, swd = (float)w / (float)W;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(idx % CV);
+        int64_t t = idx / CV;
+        int x = (int)(t % W); t /= W;
+        int y = (int)(t % H);
+        int64_t n = t / H;
+        int ch = cv * V;
+        T* q = out + n * os.n + (int64_t)y * os.h + (int64_t)x * os.w + ch;
+        if (ch < c) {  // pass-through copy of b
+            stg_stream(q, ldg_stream(b + n * bs.n + (int64_t)y * bs.h + (int64_t)x * bs.w + ch));
+            continue;
+        }
+        int seg = (ch - c) / half, cc = (ch - c) - seg * half;
+        int y0, y1, x0, x1; float ly, lx;
+        bilin_src(y, sh, h, y0, y1, ly);
+        bilin_src(x, swd, w, x0, x1, lx);
+        const Strides4 s = bands.s[seg];
+        const T* p = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + cc;
+        float v00[V], v01[V], v10[V], v11[V], r[V];
+        // band pixels are re-read by ~4 output pixels each: keep them in L1
+        unpack<T>(ldg_cached(p + (int64_t)y0 * s.h + (int64_t)x0 * s.w), v00);
+        unpack<T>(ldg_cached(p + (int64_t)y0 * s.h + (int64_t)x1 * s.w), v01);
+        unpack<T>(ldg_cached(p + (int64_t)y1 * s.h + (int64_t)x0 * s.w), v10);
+        unpack<T>(ldg_cached(p + (int64_t)y1 * s.h + (int64_t)x1 * s.w), v11);
+        const float wy0 = 1.f - ly, wx0 = 1.f - lx, wb = sw[seg];
+#pragma unroll
+        for (int e = 0; e < V; ++e) r[e] = (wy0 * (wx0 * v00[e] + lx * v01[e]) + ly * (wx0 * v10[e] + lx * v11[e])) * wb;
+        stg_stream(q, pack<T>(r));
+    }
+}
+
+template <typename T, bool CH_FAST>
+__global__ void __launch_bounds__(256) merge_fwd_generic(const T* __restrict__ b, Strides4 bs, BandPtrs bands, const float* __restrict__ alpha,
+                                                         T* __restrict__ out, Strides4 os, int c, int H, int W, int h, int w, int64_t total) {
+    __shared__ float sw[4];
+    if (threadIdx.x == 0) {
+        float wt[4];
+        band_weights(alpha, wt);
+        sw[0] = wt[0]; sw[1] = wt[1]; sw[2] = wt[2]; sw[3] = wt[3];
+    }
+    __syncthreads();
+    const int half = c / 2;
+    const float sh = (float)h / (float)H, swd = (float)w / (float)W;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n; int ch, y, x;
+        split_ncij<CH_FAST>(idx, 3 * c, H, W, n, ch, y, x);
+        T* q = out + n * os.n + (int64_t)ch * os.c + (int64_t)y * os.h + (int64_t)x * os.w;
+        if (ch < c) {
+            *q = b[n * bs.n + (int64_t)ch * bs.c + (int64_t)y * bs.h + (int64_t)x * bs.w];
+            continue;
+        }
+        int seg = (ch - c) / half, cc = (ch - c) - seg * half;
+        int y0, y1, x0, x1; float ly, lx;
+        bilin_src(y, sh, h, y0, y1, ly);
+        bilin_src(x, swd, w, x0, x1, lx);
+        const Strides4 s = bands.s[seg];
+        const T* p = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + (int64_t)cc * s.c;
+        float v00 = to_f(p[(int64_t)y0 * s.h + (int64_t)x0 * s.w]), v01 = to_f(p[(int64_t)y0 * s.h + (int64_t)x1 * s.w]);
+        float v10 = to_f(p[(int64_t)y1 * s.h + (int64_t)x0 * s.w]), v11 = to_f(p[(int64_t)y1 * s.h + (int64_t)x1 * s.w]);
+        float r = ((1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11)) * sw[seg];
+        *q = from_f<T>(r);
+    }
+}
+
+// ---------------------------------------------------------------------------- merge backward
+// (1) gb = gout[:, :c];  (2) gband_i = w_i * up^T(gout_i)  (gather form, no atomics);
+// (3) galpha_w[i] += <gout_i, up(band_i)>.
+template <typename T, bool CH_FAST>
+__global__ void __launch_bounds__(256) merge_bwd_gb(const T* __restrict__ go, Strides4 gos, T* __restrict__ gb, Strides4 gbs, int c, int H, int W,
+                                                    int64_t total) {
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n; int ch, y, x;
+        split_ncij<CH_FAST>(idx, c, H, W, n, ch, y, x);
+        gb[n * gbs.n + (int64_t)ch * gbs.c + (int64_t)y * gbs.h + (int64_t)x * gbs.w] =
+            go[n * gos.n + (int64_t)ch * gos.c + (int64_t)y * gos.h + (int64_t)x * gos.w];
+    }
+}
+
+// range of destination indices whose bilinear footprint can touch source index s
+__device__ __forceinline__ void dst_range(int s, float scale, int n_out, int& lo, int& hi) {
+    float inv = 1.f / scale;
+    lo = (int)floorf((s - 1 + 0.5f) * inv - 0.5f) - 1;
+    hi = (int)ceilf((s + 1 + 0.5f) * inv - 0.5f) + 1;
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > n_out - 1 ? n_out - 1 : hi;
+}
+
+template <typename T, bool CH_FAST>
+__global__ void __launch_bounds__(256) merge_bwd_bands(const T* __restrict__ go, Strides4 gos, const float* __restrict__ alpha, BandPtrsMut gband,
+                                                       int c, int H, int W, int h, int w, int64_t total) {
+    __shared__ float sw[4];
+    if (threadIdx.x == 0) {
+        float wt[4];
+        band_weights(alpha, wt);
+        sw[0] = wt[0]; sw[1] = wt[1]; sw[2] = wt[2]; sw[3] = wt[3];
+    }
+    __syncthreads();
+    const int half = c / 2;
+    const float sh = (float)h / (float)H, swd = (float)w / (float)W;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n; int ch, sy, sx;
+        split_ncij<CH_FAST>(idx, 2 * c, h, w, n, ch, sy, sx);  // 4 bands x c/2 channels
+        int seg = ch / half, cc = ch - seg * half;
+        int ylo, yhi, xlo, xhi;
+        dst_range(sy, sh, H, ylo, yhi);
+        dst_range(sx, swd, W, xlo, xhi);
+        const T* gp = go + n * gos.n + (int64_t)(c + ch) * gos.c;
+        float acc = 0.f;
+        for (int y = ylo; y <= yhi; ++y) {
+            int y0, y1; float ly;
+            bilin_src(y, sh, h, y0, y1, ly);
+            float wy = (y0 == sy ? 1.f - ly : 0.f) + (y1 == sy ? ly : 0.f);
+            if (wy == 0.f) continue;
+            for (int x = xlo; x <= xhi; ++x) {
+                int x0, x1; float lx;
+                bilin_src(x, swd, w, x0, x1, lx);
+                float wx = (x0 == sx ? 1.f - lx : 0.f) + (x1 == sx ? lx : 0.f);
+                if (wx == 0.f) continue;
+                acc += wy * wx * to_f(gp[(int64_t)y * gos.h + (int64_t)x * gos.w]);
+            }
+        }
+        const Strides4 s = gband.s[seg];
+        reinterpret_cast<T*>(gband.p[seg])[n * s.n + (int64_t)cc * s.c + (int64_t)sy * s.h + (int64_t)sx * s.w] = from_f<T>(acc * sw[seg]);
+    }
+}
+
+template <typename T, bool CH_FAST>
+__global__ void __launch_bounds__(256) merge_bwd_alpha(const T* __restrict__ go, Strides4 gos, BandPtrs bands, float* __restrict__ galpha_w, int c,
+                                                       int H, int W, int h, int w, int64_t total) {
+    const int half = c / 2;
+    const float sh = (float)h / (float)H, swd = (float)w / (float)W;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n; int ch, y, x;
+        split_ncij<CH_FAST>(idx, 2 * c, H, W, n, ch, y, x);
+        int seg = ch / half, cc = ch - seg * half;
+        int y0, y1, x0, x1; float ly, lx;
+        bilin_src(y, sh, h, y0, y1, ly);
+        bilin_src(x, swd, w, x0, x1, lx);
+        const Strides4 s = bands.s[seg];
+        const T* p = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + (int64_t)cc * s.c;
+        float v00 = to_f(p[(int64_t)y0 * s.h + (int64_t)x0 * s.w]), v01 = to_f(p[(int64_t)y0 * s.h + (int64_t)x1 * s.w]);
+        float v10 = to_f(p[(int64_t)y1 * s.h + (int64_t)x0 * s.w]), v11 = to_f(p[(int64_t)y1 * s.h + (int64_t)x1 * s.w]);
+        float up = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+        float g = to_f(go[n * gos.n + (int64_t)(c + ch) * gos.c + (int64_t)y * gos.h + (int64_t)x * gos.w]);
+        float pr = up * g;
+        acc[0] += seg == 0 ? pr : 0.f;
+        acc[1] += seg == 1 ? pr : 0.f;
+        acc[2] += seg == 2 ? pr : 0.f;
+        acc[3] += seg == 3 ? pr : 0.f;
+    }
+    __shared__ float red[4][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float v = warp_sum(acc[i]);
+        if (lane == 0) red[i][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float v = 0.f;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) v += red[threadIdx.x][k];
+        atomicAdd(galpha_w + threadIdx.x, v);
+    }
+}
+
+// --------------------------------------------------------------------------- gated residual
+template <typename T>
+__global__ void __launch_bounds__(256) gated_cvec(const T* b, Strides4 bs, const T* __restrict__ y, Strides4 ys, const float* __restrict__ gamma,
+                                                  T* o, Strides4 os, int CV, int H, int W, int64_t total) {
+    constexpr int V = Vec16<T>::N;
+    const float g = tanhf(__ldg(gamma));
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int cv = (int)(idx % CV);
+        int64_t t = idx / CV;
+        int x = (int)(t % W); t /= W;
+        int yy = (int)(t % H);
+        int64_t n = t / H;
+        float fb[V], fy[V], r[V];
+        // b may alias o: plain (coherent) load
+        unpack<T>(*reinterpret_cast<const uint4*>(b + n * bs.n + (int64_t)yy * bs.h + (int64_t)x * bs.w + cv * V), fb);
+        unpack<T>(ldg_stream(y + n * ys.n + (int64_t)yy * ys.h + (int64_t)x * ys.w + cv * V), fy);
+#pragma unroll
+        for (int e = 0; e < V; ++e) r[e] = fb[e] + g * fy[e];
+        *reinterpret_cast<uint4*>(o + n * os.n + (int64_t)yy * os.h + (int64_t)x * os.w + cv * V) = pack<T>(r);
+    }
+}
+
+template <typename T, bool CH_FAST>
+__global__ void __launch_bounds__(256) gated_generic(const T* b, Strides4 bs, const T* __restrict__ y, Strides4 ys, const float* __restrict__ gamma,
+                                                     T* o, Strides4 os, int C, int H, int W, int64_t total) {
+    const float g = tanhf(__ldg(gamma));
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n; int c, yy, x;
+        split_ncij<CH_FAST>(idx, C, H, W, n, c, yy, x);
+        float r = to_f(b[n * bs.n + (int64_t)c * bs.c + (int64_t)yy * bs.h + (int64_t)x * bs.w]) +
+                  g * to_f(y[n * ys.n + (int64_t)c * ys.c + (int64_t)yy * ys.h + (int64_t)x * ys.w]);
+        o[n * os.n + (int64_t)c * os.c + (int64_t)yy * os.h + (int64_t)x * os.w] = from_f<T>(r);
+    }
+}
+
+// uint8 HWC -> normalised activations (value / 255), any destination strides
+template <typename T>
+__global__ void __launch_bounds__(256) ingest_u8_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, Strides4 ds, int H, int W, int64_t total) {
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t t = idx;  // one thread per pixel: 3 bytes in, 3 elements out
+        int x = (int)(t % W); t /= W;
+        int y = (int)(t % H);
+        int64_t n = t / H;
+        const uint8_t* p = src + idx * 3;
+        T* q = dst + n * ds.n + (int64_t)y * ds.h + (int64_t)x * ds.w;
+        q[0] = from_f<T>((float)p[0] / 255.f);
+        q[ds.c] = from_f<T>((float)p[1] / 255.f);
+        q[2 * ds.c] = from_f<T>((float)p[2] / 255.f);
+    }
+}
+
+// grid for a streaming grid-stride kernel: enough CTAs to cover `total`, capped at a multiple
+// of the SM count so the tail wave is full (148 SMs x 8 resident 256-thread CTAs)
+static inline int stream_grid(int64_t total, int threads = 256) {
+    int64_t need = ceil_div(total, threads);
+    int64_t cap = (int64_t)kSMs * 16;
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+}  // namespace el
+
+using namespace el;
+
+extern "C" int el_dwt_haar_fwd(const void* x, const int64_t xs_[4], void* bands, const int64_t bs_[5], int B, int C, int H, int W, int dtype,
+                               void* stream) {
+    if (!x || !bands || !xs_ || !bs_ || B <= 0 || C <= 0 || H <= 0 || W <= 0) return EL_ERR_ARG;
+    const int H2 = H / 2, W2 = W / 2;
+    if (H2 == 0 || W2 == 0) return EL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    Strides4 xs = s4(xs_), os = s4(bs_ + 1);
+    const int64_t ob = bs_[0];
+    EL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        if (channel_vectorisable<T>(x, xs, C) && channel_vectorisable<T>(bands, os, C) && ob % V == 0) {
+            int64_t total = (int64_t)B * H2 * W2 * (C / V);
+            dwt_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C / V, H2, W2, total);
+        } else {
+            int64_t total = (int64_t)B * C * H2 * W2;
+            if (xs.c == 1)
+                dwt_fwd_generic<T, true><<<stream_grid(total), 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C, H2, W2, total);
+            else
+                dwt_fwd_generic<T, false><<<stream_grid(total), 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C, H2, W2, total);
+        }
+    });
+    note_launches(1);
+    return check_launch();
+}
+
+extern "C" int el_dwt_haar_bwd(const void* g, const int64_t gs_[5], void* gx, const int64_t gxs_[4], int B, int C, int H, int W, int dtype,
+                               void* stream) {
+    if (!g || !gx || !gs_ || !gxs_ || B <= 0 || C <= 0 || H <= 0 || W <= 0) return EL_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Strides4 gs = s4(gs_ + 1), os = s4(gxs_);
+    int64_t total = (int64_t)B * C * ((H + 1) / 2) * ((W + 1) / 2);
+    EL_DISPATCH_DTYPE(dtype, {
+        if (os.c == 1)
+            dwt_bwd_generic<T, true><<<stream_grid(total), 256, 0, st>>>((const T*)g, gs_[0], gs, (T*)gx, os, C, H, W, total);
+        else
+            dwt_bwd_generic<T, false><<<stream_grid(total), 256, 0, st>>>((const T*)g, gs_[0], gs, (T*)gx, os, C, H, W, total);
+    });
+    note_launches(1);
+    return check_launch();
+}
+
+extern "C" int el_wave_merge_fwd(const void* b, const int64_t bs_[4], const void* const band[4], const int64_t band_s[16], const float* alpha,
+                                 void* out, const int64_t os_[4], int B, int c, int H, int W, int h, int w, int dtype, void* stream) {
+    if (!b || !band || !band_s || !alpha || !out || B <= 0 || c <= 0 || (c & 1) || H <= 0 || W <= 0 || h <= 0 || w <= 0) return EL_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Strides4 bs = s4(bs_), os = s4(os_);
+    BandPtrs bp;
+    for (int i = 0; i < 4; ++i) {
+        if (!band[i]) return EL_ERR_ARG;
+        bp.p[i] = band[i];
+        bp.s[i] = s4(band_s + 4 * i);
+    }
+    EL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        bool vec = channel_vectorisable<T>(b, bs, c) && channel_vectorisable<T>(out, os, 3 * c) && (c / 2) % V == 0;
+        for (int i = 0; i < 4; ++i) vec = vec && channel_vectorisable<T>(bp.p[i], bp.s[i], c / 2);
+        if (vec) {
+            int64_t total = (int64_t)B * H * W * (3 * c / V);
+            merge_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, H, W, h, w, total);
+        } else {
+            int64_t total = (int64_t)B * 3 * c * H * W;
+            if (os.c == 1)
+                merge_fwd_generic<T, true><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, H, W, h, w, total);
+            else
+                merge_fwd_generic<T, false><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, H, W, h, w, total);
+        }
+    });
+    note_launches(1);
+    return check_launch();
+}
+
+extern "C" int el_wave_merge_bwd(const void* gout, const int64_t gos_[4], const void* const band[4], const int64_t band_s[16], const float* alpha,
+                                 void* gb, const int64_t gbs_[4], void* const gband[4], const int64_t gband_s[16], float* galpha_w, int B, int c,
+                                 int H, int W, int h, int w, int dtype, void* stream) {
+    if (!gout || !alpha || B <= 0 || c <= 0 || (c & 1) || H <= 0 || W <= 0 || h <= 0 || w <= 0) return EL_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Strides4 gos = s4(gos_);
+    EL_DISPATCH_DTYPE(dtype, {
+        if (gb) {
+            Strides4 gbs = s4(gbs_);
+            int64_t total = (int64_t)B * c * H * W;
+            if (gos.c == 1)
+                merge_bwd_gb<T, true><<<stream_grid(total), 256, 0, st>>>((const T*)gout, gos, (T*)gb, gbs, c, H, W, total);
+            else
+                merge_bwd_gb<T, false><<<stream_grid(total), 256, 0, st>>>((const T*)gout, gos, (T*)gb, gbs, c, H, W, total);
+        }
+        if (gband) {
+            BandPtrsMut gp;
+            for (int i = 0; i < 4; ++i) {
+                if (!gband[i]) return EL_ERR_ARG;
+                gp.p[i] = gband[i];
+                gp.s[i] = s4(gband_s + 4 * i);
+            }
+            int64_t total = (int64_t)B * 2 * c * h * w;
+            if (gp.s[0].c == 1)
+                merge_bwd_bands<T, true><<<stream_grid(total), 256, 0, st>>>((const T*)gout, gos, alpha, gp, c, H, W, h, w, total);
+            else
+                merge_bwd_bands<T, false><<<stream_grid(total), 256, 0, st>>>((const T*)gout, gos, alpha, gp, c, H, W, h, w, total);
+        }
+        if (galpha_w) {
+            if (!band) return EL_ERR_ARG;
+            BandPtrs bp;
+            for (int i = 0; i < 4; ++i) {
+                bp.p[i] = band[i];
+                bp.s[i] = s4(band_s + 4 * i);
+            }
+            int64_t total = (int64_t)B * 2 * c * H * W;
+            int grid = stream_grid(total);
+            if (grid > kSMs * 4) grid = kSMs * 4;  // fewer atomics
+            if (gos.c == 1)
+                merge_bwd_alpha<T, true><<<grid, 256, 0, st>>>((const T*)gout, gos, bp, galpha_w, c, H, W, h, w, total);
+            else
+                merge_bwd_alpha<T, false><<<grid, 256, 0, st>>>((const T*)gout, gos, bp, galpha_w, c, H, W, h, w, total);
+        }
+    });
+    note_launches((gb ? 1 : 0) + (gband ? 1 : 0) + (galpha_w ? 1 : 0));
+    return check_launch();
+}
+
+extern "C" int el_gated_residual_fwd(const void* b, const int64_t bs_[4], const void* y, const int64_t ys_[4], const float* gamma, void* out,
+                                     const int64_t os_[4], int B, int C, int H, int W, int dtype, void* stream) {
+    if (!b || !y || !gamma || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return EL_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Strides4 bs = s4(bs_), ys = s4(ys_), os = s4(os_);
+    EL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        if (channel_vectorisable<T>(b, bs, C) && channel_vectorisable<T>(y, ys, C) && channel_vectorisable<T>(out, os, C)) {
+            int64_t total = (int64_t)B * H * W * (C / V);
+            gated_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, C / V, H, W, total);
+        } else {
+            int64_t total = (int64_t)B * C * H * W;
+            if (os.c == 1)
+                gated_generic<T, true><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, C, H, W, total);
+            else
+                gated_generic<T, false><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, C, H, W, total);
+        }
+    });
+    note_launches(1);
+    return check_launch();
+}
+
+extern "C" int el_ingest_u8(const uint8_t* src, void* dst, const int64_t ds_[4], int B, int H, int W, int dtype, void* stream) {
+    if (!src || !dst || B <= 0 || H <= 0 || W <= 0) return EL_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Strides4 ds = s4(ds_);
+    int64_t total = (int64_t)B * H * W;
+    EL_DISPATCH_DTYPE(dtype, { ingest_u8_kernel<T><<<stream_grid(total), 256, 0, st>>>(src, (T*)dst, ds, H, W, total); });
+    note_launches(1);
+    return check_launch();
+}

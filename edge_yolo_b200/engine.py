@@ -1,0 +1,105 @@
+"""Batch predictor for EdgeLine-YOLO on one B200: uint8 images in, NMS-ed detections out.
+
+Mirrors what `YOLO.predict` does per batch in the reference (engine/predictor.py:220-266 +
+models/yolo/detect/predict.py:23-41): preprocess (/255, dtype), model forward, NMS -- but as one
+CUDA graph replay with static buffers: one H2D copy in, one D2H copy out, zero host syncs in
+between.  One process drives one GPU; multi-GPU inference is N independent replicas, each on its
+own shard of the image batch (replicas only, no collective).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import lib
+from .model import EdgeLineYOLO
+from .modules import GFLHeadv2_uniH, _WaveletEnhancer
+
+
+def build_model(scale="n", nc=80, seed=0, gamma=0.5, dtype=torch.bfloat16, device="cuda", fuse=True) -> EdgeLineYOLO:
+    """Seeded random-init EdgeLine-YOLO (no checkpoints offline).  gamma is set to 0.5 because the reference's
+    init (0.0) makes every wavelet branch an exact identity; the head keeps the raw init (no
+    `bias_init`), i.e. the regime `YOLO(cfg).predict` really runs in at random init."""
+    torch.manual_seed(seed)
+    model = EdgeLineYOLO(scale, nc).eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, _WaveletEnhancer):
+                m.gamma.fill_(gamma)
+    if fuse:
+        model.fuse(dsconv=True)
+    model = model.to(device=device, dtype=dtype).to(memory_format=torch.channels_last)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model
+
+
+class Predictor:
+    def __init__(self, model: EdgeLineYOLO, batch: int, imgsz: int = 640, conf=0.25, iou=0.7, max_det=300, multi_label=False,
+                 agnostic=False, max_nms=30000, use_graph=True):
+        self.model, self.batch, self.imgsz = model, batch, imgsz
+        self.nms_kw = dict(conf_thres=conf, iou_thres=iou, multi_label=multi_label, agnostic=agnostic, max_det=max_det, max_nms=max_nms)
+        p = next(model.parameters())
+        self.device, self.dtype = p.device, p.dtype
+        for m in model.modules():
+            if isinstance(m, GFLHeadv2_uniH):
+                m.el_skip_feats = True  # predict never reads the raw maps
+        self.u8 = torch.empty((batch, imgsz, imgsz, 3), device=self.device, dtype=torch.uint8)
+        self.x = torch.empty((batch, 3, imgsz, imgsz), device=self.device, dtype=self.dtype, memory_format=torch.channels_last)
+        self.host_out = torch.empty((batch, max_det, 6), dtype=torch.float32).pin_memory()
+        self.host_cnt = torch.empty((batch,), dtype=torch.int32).pin_memory()
+        self.graph_from_u8 = self.graph_from_x = None
+        self.launches_per_step = None
+        self.out = self.cnt = None
+        if use_graph:
+            self._capture()
+
+    @torch.no_grad()
+    def _forward(self, from_u8: bool):
+        if from_u8:
+            ops.ingest_u8(self.u8, out=self.x)
+        y, _ = self.model(self.x)
+        return ops.nms_batched(y, **self.nms_kw)
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):  # cuDNN autotune + allocator warm-up outside the capture
+                self._forward(True)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        n0 = lib().el_launch_count()
+        self.graph_from_u8 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_from_u8):
+            self.out, self.cnt = self._forward(True)
+        self.launches_per_step = int(lib().el_launch_count() - n0)
+        self.graph_from_x = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_from_x, pool=self.graph_from_u8.pool()):
+            self.out_x, self.cnt_x = self._forward(False)
+
+    def step_device(self):
+        """One pass with the input batch already resident in HBM (`self.x`); results stay on the device."""
+        if self.graph_from_x is not None:
+            self.graph_from_x.replay()
+            return self.out_x, self.cnt_x
+        return self._forward(False)
+
+    def predict_u8(self, host_u8: torch.Tensor):
+        """host_u8: pinned uint8 (B, H, W, 3).  H2D copy, one graph replay, D2H of rows + counts.
+        Returns (rows (B, max_det, 6) pinned fp32, counts (B) pinned int32); valid rows are rows[b, :counts[b]]."""
+        self.u8.copy_(host_u8, non_blocking=True)
+        if self.graph_from_u8 is not None:
+            self.graph_from_u8.replay()
+            out, cnt = self.out, self.cnt
+        else:
+            out, cnt = self._forward(True)
+        self.host_out.copy_(out, non_blocking=True)
+        self.host_cnt.copy_(cnt, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.host_out, self.host_cnt
+
+    def predict(self, host_u8: torch.Tensor):
+        """List of (k, 6) tensors [x1, y1, x2, y2, conf, cls] per image, like the reference's NMS output."""
+        rows, cnt = self.predict_u8(host_u8)
+        return [rows[i, : int(cnt[i])].clone() for i in range(self.batch)]

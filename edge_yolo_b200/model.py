@@ -1,0 +1,127 @@
+"""EdgeLine-YOLO graph builder (the `yolo11-test.yaml` topology) without ultralytics.
+
+Mirrors what `parse_model` (nn/tasks.py:958-1147) builds from
+`cfg/models/11/yolo11-test.yaml`: same layer indices, channel arithmetic and therefore the same
+`model.{i}.*` state-dict keys, so reference checkpoints load unchanged.  Used by bench / smoke /
+tests on machines where the reference package is absent; with ultralytics present use
+`edge_yolo_b200.install()` instead and keep `YOLO(cfg, task="detect")`.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from .modules import C2PSA_LinearAttention, Concat, Conv, DSC3K2_Wavelet, DSConv, GFLHeadv2_uniH, SPPF
+
+# [depth, width, max_channels]  (yolo11-test.yaml:9-15)
+SCALES = {"n": (0.50, 0.25, 1024), "s": (0.50, 0.50, 1024), "m": (0.50, 1.00, 512), "l": (1.00, 1.00, 512), "x": (1.00, 1.50, 512)}
+
+# (from, repeats, module, args)  (yolo11-test.yaml:18-50)
+_LAYERS = [
+    (-1, 1, "Conv", [64, 3, 2]),
+    (-1, 1, "Conv", [128, 3, 2]),
+    (-1, 2, "DSC3K2_Wavelet", [256, False, 0.25]),
+    (-1, 1, "Conv", [256, 3, 2]),
+    (-1, 2, "DSC3K2_Wavelet", [512, False, 0.25]),
+    (-1, 1, "Conv", [512, 3, 2]),
+    (-1, 2, "DSC3K2_Wavelet", [512, True]),
+    (-1, 1, "Conv", [1024, 3, 2]),
+    (-1, 2, "DSC3K2_Wavelet", [1024, True]),
+    (-1, 1, "SPPF", [1024, 5]),
+    (-1, 2, "C2PSA_LinearAttention", [1024]),
+    (-1, 1, "Upsample", [None, 2, "nearest"]),
+    ([-1, 6], 1, "Concat", [1]),
+    (-1, 2, "DSC3K2_Wavelet", [512, False]),
+    (-1, 1, "Upsample", [None, 2, "nearest"]),
+    ([-1, 4], 1, "Concat", [1]),
+    (-1, 2, "DSC3K2_Wavelet", [256, False]),
+    (-1, 1, "Conv", [256, 3, 2]),
+    ([-1, 13], 1, "Concat", [1]),
+    (-1, 2, "DSC3K2_Wavelet", [512, False]),
+    (-1, 1, "Conv", [512, 3, 2]),
+    ([-1, 10], 1, "Concat", [1]),
+    (-1, 2, "DSC3K2_Wavelet", [1024, True]),
+    ([16, 19, 22], 1, "GFLHeadv2_uniH", ["nc"]),
+]
+
+
+def make_divisible(x, divisor):
+    return math.ceil(x / divisor) * divisor
+
+
+class EdgeLineYOLO(nn.Module):
+    """Detection model: `forward(x)` -> list of raw maps (train) or `(y, maps)` (eval), like DetectionModel."""
+
+    def __init__(self, scale: str = "n", nc: int = 80, ch: int = 3):
+        super().__init__()
+        depth, width, max_ch = SCALES[scale]
+        self.scale, self.nc = scale, nc
+        chans, layers, self.save = [ch], [], set()
+        for i, (f, n, name, args) in enumerate(_LAYERS):
+            args = list(args)
+            n = max(round(n * depth), 1) if n > 1 else n
+            c1 = chans[f] if isinstance(f, int) else None
+            if name in ("Conv", "SPPF", "DSC3K2_Wavelet", "C2PSA_LinearAttention"):
+                c2 = make_divisible(min(args[0], max_ch) * width, 8)
+                args = [c1, c2, *args[1:]]
+                if name in ("DSC3K2_Wavelet", "C2PSA_LinearAttention"):
+                    args.insert(2, n)  # repeats become a constructor argument (tasks.py:1067-1068)
+                    if name == "DSC3K2_Wavelet" and scale in "lx":
+                        args[3] = True  # tasks.py:1069-1072
+                m = {"Conv": Conv, "SPPF": SPPF, "DSC3K2_Wavelet": DSC3K2_Wavelet, "C2PSA_LinearAttention": C2PSA_LinearAttention}[name](*args)
+            elif name == "Upsample":
+                m, c2 = nn.Upsample(*args), c1
+            elif name == "Concat":
+                m, c2 = Concat(*args), sum(chans[x] for x in f)
+            else:  # head
+                m, c2 = GFLHeadv2_uniH(nc, [chans[x] for x in f]), None
+            m.i, m.f = i, f
+            layers.append(m)
+            self.save.update(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
+            if i == 0:
+                chans = []
+            chans.append(c2)
+        self.model = nn.Sequential(*layers)
+        head = self.model[-1]
+        head.stride = torch.tensor([8.0, 16.0, 32.0])  # what the reference's 256x256 probe measures (tasks.py:361-363)
+        self.stride = head.stride
+        for m in self.modules():  # initialize_weights, utils/torch_utils.py:416-418
+            if isinstance(m, nn.BatchNorm2d):
+                m.eps, m.momentum = 1e-3, 0.03
+            elif isinstance(m, (nn.SiLU, nn.ReLU)):
+                m.inplace = True
+
+    def forward(self, x):
+        outs = []
+        for m in self.model:
+            if m.f != -1:
+                x = outs[m.f] if isinstance(m.f, int) else [x if j == -1 else outs[j] for j in m.f]
+            x = m(x)
+            outs.append(x if m.i in self.save else None)
+        return x
+
+    def fuse(self, dsconv: bool = False):
+        """Fold BatchNorm into the preceding conv.  Like BaseModel.fuse (tasks.py:214-242) only `Conv`
+        (incl. DWConv) is folded by default; `dsconv=True` additionally folds DSConv's BN into its
+        pointwise conv (identical maths in eval mode, one kernel less per DSConv)."""
+        for m in self.modules():
+            if isinstance(m, Conv) and hasattr(m, "bn"):
+                m.conv = _fold(m.conv, m.bn)
+                del m.bn
+                m.forward = m.forward_fuse
+            elif dsconv and isinstance(m, DSConv) and isinstance(m.bn, nn.BatchNorm2d):
+                m.pw = _fold(m.pw, m.bn)
+                m.bn = nn.Identity()
+        return self
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
+    fused = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups, bias=True)
+    fused = fused.to(conv.weight.device, conv.weight.dtype).requires_grad_(False)
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    fused.weight.copy_(conv.weight * scale.view(-1, 1, 1, 1))
+    bias = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+    fused.bias.copy_((bias - bn.running_mean) * scale + bn.bias)
+    return fused

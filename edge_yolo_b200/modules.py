@@ -1,0 +1,368 @@
+"""Host-side mirror of the reference's operator interface for the EdgeLine hot path.
+
+Two things live here:
+
+1. `*_forward` functions: the B200 bodies of the reference's module forwards.  They only rely on
+   attribute names the reference classes also have (`f_ll`, `f_h`, `fuse`, `alpha`, `gamma`, `qkv`,
+   `proj`, `cv2`, `cv3`, `reg_conf`, `stride`, ...), so `install.py` can bind them onto the
+   reference's own classes (drop-in behind the ultralytics API), and the standalone classes
+   below use the very same functions.
+2. Standalone `nn.Module`s with the reference's constructor signatures and state-dict keys
+    so that EdgeLine-YOLO can be built and benchmarked on a machine without
+   ultralytics.  Convolutions / BatchNorm / SiLU stay on PyTorch + cuDNN (north_star).
+
+Reference paths are relative to /root/reference/ultralytics/.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+# ------------------------------------------------------------------------------------------
+# shared forward bodies (bound onto reference classes by install.py)
+# ------------------------------------------------------------------------------------------
+
+
+def dwt_forward(self, x: torch.Tensor):
+    """`_PywtDWT2D.forward` (nn/modules/block.py:3619-3642): returns (LL, LH, HL, HH)."""
+    if getattr(self, "wave_name", "haar") != "haar":
+        raise NotImplementedError("edge_yolo_b200 implements the Haar wavelet only (the only one any EdgeLine yaml uses)")
+    buf = ops.dwt_haar(x)
+    B = x.shape[0]
+    return buf[:B], buf[B : 2 * B], buf[2 * B : 3 * B], buf[3 * B :]
+
+
+def wavelet_enhancer_forward(self, b: torch.Tensor) -> torch.Tensor:
+    """`_WaveletEnhancer.forward` (block.py:3685-3710).
+
+    DWT split -> f_ll / shared f_h convs (cuDNN) -> fused upsample*w+concat kernel -> fuse conv ->
+    gated residual kernel.  In eval mode the three high bands go through `f_h` as one 3B batch
+    (BatchNorm uses running statistics, so this is exactly three separate calls); in training
+    mode they are three calls like the reference, because batch statistics differ per call.
+    """
+    B = b.shape[0]
+    buf = ops.dwt_haar(b)
+    LLp = self.f_ll(buf[:B])
+    if self.training:
+        LHp, HLp, HHp = self.f_h(buf[B : 2 * B]), self.f_h(buf[2 * B : 3 * B]), self.f_h(buf[3 * B :])
+    else:
+        hp = self.f_h(buf[B:])
+        LHp, HLp, HHp = hp[:B], hp[B : 2 * B], hp[2 * B :]
+    cat = ops.wave_merge(b, LLp, LHp, HLp, HHp, self.alpha)
+    y = self.fuse(cat)
+    return ops.gated_residual(b, y, self.gamma)
+
+
+def linear_attention_forward(self, x: torch.Tensor) -> torch.Tensor:
+    """`LinearAttention.forward` (block.py:3360-3373): qkv conv -> fused attention core -> proj conv."""
+    return self.proj(ops.linear_attention(self.qkv(x), self.num_heads))
+
+
+def _dgqp_weights(self):
+    """fp32 views of the DGQP heads `reg_conf[i]` = Conv2d(20,64,1) ReLU Conv2d(64,1,1) Sigmoid (head.py:847-854)."""
+    key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for seq in self.reg_conf for p in seq.parameters())
+    cache = getattr(self, "_el_dgqp", None)
+    if cache is None or cache[0] != key:
+        ws = []
+        for seq in self.reg_conf:
+            c1, c2 = seq[0], seq[2]
+            if c1.weight.shape[1] != 20 or c1.weight.shape[0] != 64 or c2.weight.shape[:2] != (1, 64):
+                raise NotImplementedError("edge_yolo_b200 decode supports reg_topk=4, add_mean=True, reg_channels=64 (the yaml's values)")
+            ws.append(tuple(t.detach().float().reshape(-1).contiguous() for t in (c1.weight, c1.bias, c2.weight, c2.bias)))
+        cache = (key, ws)
+        self._el_dgqp = cache
+    return cache[1]
+
+
+def gfl_head_forward(self, x):
+    """`GFLHeadv2_uniH.forward` (nn/modules/head.py:880-908).
+
+    Training: returns the per-level cat(box, cls) list like the reference (whose quality maps are
+    computed and dropped on this path).  Eval: one fused decode kernel produces
+    y (B, 4+nc, A) in fp32; returns `y` when exporting, else `(y, x)`.
+    """
+    boxes, clss = [], []
+    for i in range(self.nl):
+        xi = x[i]
+        for name in ("stem", "dat", "pos_cls", "pos_reg", "cit_cls", "cit_reg"):  # Identity placeholders in the reference
+            mods = getattr(self, name, None)
+            if mods:
+                xi = mods[i](xi)
+        boxes.append(self.cv2[i](xi))
+        clss.append(self.cv3[i](xi))
+    if self.training:
+        for i in range(self.nl):
+            x[i] = torch.cat((boxes[i], clss[i]), 1)
+        return x
+    if getattr(self, "export", False) and getattr(self, "format", None) in {"tflite", "edgetpu", "imx", "saved_model", "pb", "tfjs"}:
+        raise NotImplementedError("edge_yolo_b200: export formats are out of scope (no multi-backend dispatch)")
+    y = ops.gfl_decode(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride])
+    if getattr(self, "export", False):
+        return y
+    if getattr(self, "el_skip_feats", False):  # fast predict path: nobody reads the raw maps
+        return y, None
+    for i in range(self.nl):
+        x[i] = torch.cat((boxes[i], clss[i]), 1)
+    return y, x
+
+
+# ------------------------------------------------------------------------------------------
+# standalone modules (same names, constructor signatures and state-dict keys as the reference)
+# ------------------------------------------------------------------------------------------
+
+
+def autopad(k, p=None, d=1):
+    if d > 1:
+        k = d * (k - 1) + 1
+    return k // 2 if p is None else p
+
+
+class Conv(nn.Module):
+    """conv + BatchNorm + SiLU (nn/modules/conv.py:41-60); keys `conv.weight`, `bn.*`."""
+
+    default_act = nn.SiLU()
+
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, d=1, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, s, autopad(k, p, d), groups=g, dilation=d, bias=False)
+        self.bn = nn.BatchNorm2d(c2)
+        self.act = self.default_act if act is True else act if isinstance(act, nn.Module) else nn.Identity()
+
+    def forward(self, x):
+        return self.act(self.bn(self.conv(x)))
+
+    def forward_fuse(self, x):
+        return self.act(self.conv(x))
+
+
+class DWConv(Conv):
+    """Depth-wise Conv (conv.py:124-129)."""
+
+    def __init__(self, c1, c2, k=1, s=1, d=1, act=True):
+        super().__init__(c1, c2, k, s, g=math.gcd(c1, c2), d=d, act=act)
+
+
+class DSConv(nn.Module):
+    """Depthwise-separable conv with its own BatchNorm (conv.py:87-104); keys `dw`, `pw`, `bn`."""
+
+    def __init__(self, c_in, c_out, k=3, s=1, p=None, d=1, bias=False):
+        super().__init__()
+        p = (d * (k - 1)) // 2 if p is None else p
+        self.dw = nn.Conv2d(c_in, c_in, k, s, p, dilation=d, groups=c_in, bias=bias)
+        self.pw = nn.Conv2d(c_in, c_out, 1, 1, 0, bias=bias)
+        self.bn = nn.BatchNorm2d(c_out)
+        self.act = nn.SiLU()
+
+    def forward(self, x):
+        return self.act(self.bn(self.pw(self.dw(x))))
+
+
+class Concat(nn.Module):
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+
+    def forward(self, x):
+        return torch.cat(x, self.d)
+
+
+class SPPF(nn.Module):
+    """nn/modules/block.py:204-223."""
+
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_ * 4, c2, 1, 1)
+        self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
+
+    def forward(self, x):
+        y = [self.cv1(x)]
+        for _ in range(3):
+            y.append(self.m(y[-1]))
+        return self.cv2(torch.cat(y, 1))
+
+
+class DSBottleneck(nn.Module):
+    """block.py:1467-1503."""
+
+    def __init__(self, c1, c2, shortcut=True, e=0.5, k1=3, k2=5, d2=1):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = DSConv(c1, c_, k1, s=1, p=None, d=1)
+        self.cv2 = DSConv(c_, c2, k2, s=1, p=None, d=d2)
+        self.add = shortcut and c1 == c2
+
+    def forward(self, x):
+        y = self.cv2(self.cv1(x))
+        return x + y if self.add else y
+
+
+class DSC3k(nn.Module):
+    """C3 shell around DSBottlenecks (block.py:1506-1562, parent C3 at :382-396)."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5, k1=3, k2=5, d2=1):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(DSBottleneck(c_, c_, shortcut=shortcut, e=1.0, k1=k1, k2=k2, d2=d2) for _ in range(n)))
+
+    def forward(self, x):
+        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+
+
+class _PywtDWT2D(nn.Module):
+    """Haar analysis; no parameters and no persistent buffers (block.py:3582-3642)."""
+
+    def __init__(self, wave: str = "haar", mode: str = "symmetric"):
+        super().__init__()
+        if wave != "haar":
+            raise NotImplementedError("edge_yolo_b200 implements the Haar wavelet only")
+        self.wave_name, self.mode = wave, mode
+
+    forward = dwt_forward
+
+
+class _WaveletEnhancer(nn.Module):
+    """block.py:3645-3710; keys `alpha`, `gamma`, `f_ll.*`, `f_h.*`, `fuse.*`."""
+
+    def __init__(self, c: int, use_ds: bool = False, alpha0=(0.5, 0.2, 0.2, 0.1), wave: str = "haar", mode: str = "symmetric"):
+        super().__init__()
+        self.c = c
+        self.dwt = _PywtDWT2D(wave=wave, mode=mode)
+        self.f_ll = Conv(c, c // 2, k=1, s=1)
+        self.f_h = (DSConv if use_ds else Conv)(c, c // 2, k=3, s=1)
+        self.fuse = Conv(3 * c, c, k=1, s=1)
+        self.alpha = nn.Parameter(torch.tensor(alpha0, dtype=torch.float32))
+        self.gamma = nn.Parameter(torch.tensor(0.0))
+
+    forward = wavelet_enhancer_forward
+
+
+class DSC3K2_Wavelet(nn.Module):
+    """C2f shell whose stacked branch is wavelet-enhanced (block.py:3749-3788)."""
+
+    def __init__(self, c1, c2, n=1, dsc3k=False, e=0.5, g=1, shortcut=True, k1=3, k2=7, d2=1, **kwargs):
+        super().__init__()
+        use_ds = bool(kwargs.get("use_ds", False))
+        self.c = int(c2 * e)
+        self.cv1 = Conv(c1, 2 * self.c, 1, 1)
+        self.cv2 = Conv((2 + n) * self.c, c2, 1, 1)
+        if dsc3k:
+            self.m = nn.ModuleList(DSC3k(self.c, self.c, n=2, shortcut=shortcut, g=g) for _ in range(n))
+        else:
+            self.m = nn.ModuleList(DSBottleneck(self.c, self.c, shortcut=shortcut, e=1.0, k1=k1, k2=k2, d2=d2) for _ in range(n))
+        self.wave = _WaveletEnhancer(self.c, use_ds=use_ds, wave=kwargs.get("wave", "haar"), mode=kwargs.get("mode", "symmetric"))
+
+    def forward(self, x):
+        y = list(self.cv1(x).chunk(2, 1))
+        y[1] = self.wave(y[1])
+        for m in self.m:
+            y.append(m(y[-1]))
+        return self.cv2(torch.cat(y, 1))
+
+
+class LinearAttention(nn.Module):
+    """block.py:3348-3373; keys `qkv.weight`, `qkv.bias`, `proj.weight`; extra kwargs are dropped."""
+
+    def __init__(self, dim, num_heads, attn_ratio=None, qkv_bias=False, proj_bias=True, **kwargs):
+        super().__init__()
+        assert dim % num_heads == 0, "LinearAttention: dim must be divisible by num_heads"
+        self.dim, self.num_heads, self.head_dim = dim, num_heads, dim // num_heads
+        self.qkv = nn.Conv2d(dim, 3 * dim, kernel_size=1, bias=qkv_bias)
+        self.proj = nn.Conv2d(dim, dim, kernel_size=1, bias=proj_bias)
+
+    forward = linear_attention_forward
+
+
+class PSABlock_LinearAttention(nn.Module):
+    """block.py:3412-3449."""
+
+    def __init__(self, dim, attn_ratio=0.5, num_heads=None, mlp_ratio=2.0, qkv_bias=True, proj_bias=False, fmap="elu", eps=1e-6):
+        super().__init__()
+        self.attn = LinearAttention(dim=dim, num_heads=num_heads, attn_ratio=attn_ratio, qkv_bias=qkv_bias, proj_bias=proj_bias, fmap=fmap, eps=eps)
+        hidden = int(dim * mlp_ratio)
+        self.ffn = nn.Sequential(Conv(dim, hidden, k=1, s=1, act=True), Conv(hidden, dim, k=1, s=1, act=False))
+
+    def forward(self, x):
+        x = x + self.attn(x)
+        return x + self.ffn(x)
+
+
+class C2PSA_LinearAttention(nn.Module):
+    """block.py:3452-3497."""
+
+    def __init__(self, c1, c2, n=1, e=0.5, attn_ratio=0.5, num_heads=None, mlp_ratio=2.0, fmap="elu"):
+        super().__init__()
+        assert c1 == c2, "C2PSA_LinearAttention requires c1 == c2"
+        self.c = int(c1 * e)
+        heads = max(1, (self.c // 64) if num_heads is None else num_heads)
+        assert self.c % heads == 0, f"branch channels {self.c} must be divisible by num_heads {heads}"
+        self.cv1 = Conv(c1, 2 * self.c, k=1, s=1)
+        self.m = nn.Sequential(*[PSABlock_LinearAttention(dim=self.c, attn_ratio=attn_ratio, num_heads=heads, mlp_ratio=mlp_ratio, fmap=fmap)
+                                 for _ in range(n)])
+        self.cv2 = Conv(2 * self.c, c1, k=1, s=1)
+
+    def forward(self, x):
+        a, b = torch.split(self.cv1(x), (self.c, self.c), dim=1)
+        return self.cv2(torch.cat((a, self.m(b)), dim=1))
+
+
+class DFL(nn.Module):
+    """Frozen arange 1x1 conv (block.py:72-91).  Kept for the `dfl.conv.weight` state-dict key; the
+    integral itself runs inside the fused decode kernel."""
+
+    def __init__(self, c1=16):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, 1, 1, bias=False).requires_grad_(False)
+        self.conv.weight.data[:] = torch.arange(c1, dtype=torch.float).view(1, c1, 1, 1)
+        self.c1 = c1
+
+
+class GFLHeadv2_uniH(nn.Module):
+    """Detect towers + DGQP quality heads (head.py:38-189, 194-345, 827-908)."""
+
+    dynamic = False
+    export = False
+    format = None
+    end2end = False
+    max_det = 300
+    shape = None
+    anchors = torch.empty(0)
+    strides = torch.empty(0)
+    legacy = False
+
+    def __init__(self, nc=80, ch=(), reg_topk=4, add_mean=True, reg_channels=64, use_dat=False, use_cit=False, use_poscnn=False):
+        super().__init__()
+        self.nc, self.nl, self.reg_max = nc, len(ch), 16
+        self.no = nc + self.reg_max * 4
+        self.stride = torch.zeros(self.nl)
+        c2, c3 = max((16, ch[0] // 4, self.reg_max * 4)), max(ch[0], min(self.nc, 100))
+        self.cv2 = nn.ModuleList(nn.Sequential(Conv(x, c2, 3), Conv(c2, c2, 3), nn.Conv2d(c2, 4 * self.reg_max, 1)) for x in ch)
+        self.cv3 = nn.ModuleList(
+            nn.Sequential(nn.Sequential(DWConv(x, x, 3), Conv(x, c3, 1)), nn.Sequential(DWConv(c3, c3, 3), Conv(c3, c3, 1)), nn.Conv2d(c3, self.nc, 1))
+            for x in ch)
+        self.dfl = DFL(self.reg_max)
+        self.reg_topk, self.add_mean, self.reg_channels = reg_topk, add_mean, reg_channels
+        self.apply_quality_in_inference = True
+        in_stat = 4 * (reg_topk + (1 if add_mean else 0))
+        self.reg_conf = nn.ModuleList(
+            nn.Sequential(nn.Conv2d(in_stat, reg_channels, 1, bias=True), nn.ReLU(inplace=True), nn.Conv2d(reg_channels, 1, 1, bias=True), nn.Sigmoid())
+            for _ in ch)
+        self.stem = nn.ModuleList(nn.Identity() for _ in ch)
+        self.dat = self.pos_cls = self.pos_reg = self.cit_cls = self.cit_reg = None
+        self._qualities = None
+
+    forward = gfl_head_forward
+
+    def bias_init(self):
+        """head.py:150-161 (not called by the reference's DetectionModel; used for the 'trained-like' regime)."""
+        for a, b, s in zip(self.cv2, self.cv3, self.stride):
+            a[-1].bias.data[:] = 1.0
+            b[-1].bias.data[: self.nc] = math.log(5 / self.nc / (640 / float(s)) ** 2)

@@ -1,0 +1,389 @@
+"""Tensor-level entry points of the EdgeLine hot path: torch tensors in, CUDA kernels (through the
+C ABI of libedgeline_b200.so) out.  PyTorch only provides device memory, streams and autograd
+plumbing here; there is no CPU or eager-PyTorch fallback -- non-CUDA tensors are a hard error.
+
+Reference functions replaced (paths under /root/reference/ultralytics/):
+  dwt_haar            _PywtDWT2D.forward                        nn/modules/block.py:3619-3642
+  wave_merge          _WaveletEnhancer.forward (tail)           nn/modules/block.py:3696-3708
+  gated_residual      _WaveletEnhancer.forward (last line)      nn/modules/block.py:3710
+  linear_attention    LinearAttention.forward (core)            nn/modules/block.py:3364-3372
+  gfl_decode          GF2Detect._compute_quality_from_logits +  nn/modules/head.py:227-243, 301-345
+                      _inference_with_quality
+  nms_batched / nms   non_max_suppression / torchvision nms     utils/ops.py:167-316 / :296
+  qfl / dfl           quality_focal_loss / DFLoss               utils/loss.py:22-70 / :209-224
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import EdgelineError, check
+
+_DTYPES = {torch.float32: _lib.EL_F32, torch.float16: _lib.EL_F16, torch.bfloat16: _lib.EL_BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise EdgelineError(f"unsupported dtype {t.dtype}") from None
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if not t.is_cuda:
+            raise EdgelineError("edge_yolo_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _i64(vals):
+    return (c_int64 * len(vals))(*vals)
+
+
+def _ptrs(ts):
+    return (c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def _channels_last(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.stride(1) == 1 and t.shape[1] > 1
+
+
+def _empty_like_layout(ref: torch.Tensor, shape, dtype=None) -> torch.Tensor:
+    fmt = torch.channels_last if _channels_last(ref) else torch.contiguous_format
+    return torch.empty(shape, device=ref.device, dtype=dtype or ref.dtype, memory_format=fmt)
+
+
+# ------------------------------------------------------------------------------------ DWT
+def _dwt_fwd(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    B, C, H, W = x.shape
+    H2, W2 = H // 2, W // 2
+    buf = _empty_like_layout(x, (4 * B, C, H2, W2))  # band-major: LL | LH | HL | HH, each (B,C,H2,W2)
+    if buf.numel():
+        sn, sc, sh, sw = buf.stride()
+        check(_lib.lib().el_dwt_haar_fwd(x.data_ptr(), _i64(x.stride()), buf.data_ptr(), _i64((B * sn, sn, sc, sh, sw)),
+                                         B, C, H, W, _dt(x), _stream()), "el_dwt_haar_fwd")
+    return buf
+
+
+def _dwt_bwd(gbuf: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    B, C, H, W = like.shape
+    gbuf = gbuf if gbuf.dtype == like.dtype else gbuf.to(like.dtype)
+    gx = _empty_like_layout(like, (B, C, H, W))
+    sn, sc, sh, sw = gbuf.stride()
+    check(_lib.lib().el_dwt_haar_bwd(gbuf.data_ptr(), _i64((B * sn, sn, sc, sh, sw)), gx.data_ptr(), _i64(gx.stride()),
+                                     B, C, H, W, _dt(like), _stream()), "el_dwt_haar_bwd")
+    return gx
+
+
+class _DWT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape, ctx.cl, ctx.dtype = x.shape, _channels_last(x), x.dtype
+        return _dwt_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        fmt = torch.channels_last if ctx.cl else torch.contiguous_format
+        like = torch.empty(ctx.shape, device=g.device, dtype=ctx.dtype, memory_format=fmt)
+        g = g.contiguous(memory_format=fmt)
+        return _dwt_bwd(g, like)
+
+
+def dwt_haar(x: torch.Tensor) -> torch.Tensor:
+    """Single-level Haar analysis.  Returns one buffer (4*B, C, H//2, W//2): rows [0,B) = LL, [B,2B) = LH,
+    [2B,3B) = HL, [3B,4B) = HH (so `buf[B:]` feeds the shared high-band conv in one call)."""
+    if x.requires_grad and torch.is_grad_enabled():
+        return _DWT.apply(x)
+    return _dwt_fwd(x)
+
+
+def idwt_haar(bands: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """Haar synthesis (adjoint of `dwt_haar`), the single-level case of inverse_2d_wavelet_transform
+    (nn/modules/conv.py:438-443).  `bands` is the (4*B, C, H//2, W//2) buffer `dwt_haar` returns."""
+    _need_cuda(bands)
+    B = bands.shape[0] // 4
+    like = _empty_like_layout(bands, (B, bands.shape[1], H, W))
+    return _dwt_bwd(bands, like)
+
+
+# ---------------------------------------------------------------------------------- merge
+def _merge_fwd(b, bands, alpha):
+    _need_cuda(b, alpha, *bands)
+    B, c, H, W = b.shape
+    h, w = bands[0].shape[-2:]
+    for t in bands:
+        if t.shape != (B, c // 2, h, w) or t.dtype != b.dtype:
+            raise EdgelineError(f"wave_merge: band shape/dtype {tuple(t.shape)}/{t.dtype} does not match b {tuple(b.shape)}/{b.dtype}")
+    out = _empty_like_layout(b, (B, 3 * c, H, W))
+    a = alpha if alpha.dtype == torch.float32 else alpha.float()
+    bs = [s for t in bands for s in t.stride()]
+    check(_lib.lib().el_wave_merge_fwd(b.data_ptr(), _i64(b.stride()), _ptrs(bands), _i64(bs), a.data_ptr(), out.data_ptr(),
+                                       _i64(out.stride()), B, c, H, W, h, w, _dt(b), _stream()), "el_wave_merge_fwd")
+    return out
+
+
+class _Merge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, b, LLp, LHp, HLp, HHp, alpha):
+        ctx.save_for_backward(LLp, LHp, HLp, HHp, alpha)
+        ctx.b_meta = (b.shape, _channels_last(b))
+        return _merge_fwd(b, (LLp, LHp, HLp, HHp), alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        LLp, LHp, HLp, HHp, alpha = ctx.saved_tensors
+        bands = (LLp, LHp, HLp, HHp)
+        (B, c, H, W), cl = ctx.b_meta
+        h, w = LLp.shape[-2:]
+        fmt = torch.channels_last if cl else torch.contiguous_format
+        g = g.contiguous(memory_format=fmt)
+        gb = torch.empty((B, c, H, W), device=g.device, dtype=g.dtype, memory_format=fmt)
+        gbands = [torch.empty_like(t, memory_format=torch.contiguous_format if not _channels_last(t) else torch.channels_last) for t in bands]
+        gw = torch.zeros(4, device=g.device, dtype=torch.float32)
+        a = alpha.detach().float()
+        bs = [s for t in bands for s in t.stride()]
+        gs = [s for t in gbands for s in t.stride()]
+        check(_lib.lib().el_wave_merge_bwd(g.data_ptr(), _i64(g.stride()), _ptrs(bands), _i64(bs), a.data_ptr(), gb.data_ptr(),
+                                           _i64(gb.stride()), _ptrs(gbands), _i64(gs), gw.data_ptr(), B, c, H, W, h, w, _dt(g),
+                                           _stream()), "el_wave_merge_bwd")
+        # chain d loss / d w (4 numbers, from the kernel) through w = softplus(alpha) / (sum + 1e-6)
+        with torch.enable_grad():
+            al = alpha.detach().float().requires_grad_()
+            sp = torch.nn.functional.softplus(al)
+            wv = sp / (sp.sum() + 1e-6)
+            (galpha,) = torch.autograd.grad(wv, al, gw)
+        return gb, gbands[0], gbands[1], gbands[2], gbands[3], galpha.to(alpha.dtype)
+
+
+def wave_merge(b, LLp, LHp, HLp, HHp, alpha) -> torch.Tensor:
+    """cat[b, up(LLp)*w0, up(LHp)*w1, up(HLp)*w2, up(HHp)*w3] -> (B, 3c, H, W); w from `alpha` on the device."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (b, LLp, LHp, HLp, HHp, alpha)):
+        return _Merge.apply(b, LLp, LHp, HLp, HHp, alpha)
+    return _merge_fwd(b, (LLp, LHp, HLp, HHp), alpha)
+
+
+# ------------------------------------------------------------------------- gated residual
+def _gated_fwd(b, y, gamma, out=None):
+    _need_cuda(b, y, gamma)
+    if y.shape != b.shape or y.dtype != b.dtype:
+        raise EdgelineError("gated_residual: b and y must have the same shape and dtype")
+    B, C, H, W = b.shape
+    out = _empty_like_layout(b, b.shape) if out is None else out
+    g = gamma if gamma.dtype == torch.float32 else gamma.float()
+    check(_lib.lib().el_gated_residual_fwd(b.data_ptr(), _i64(b.stride()), y.data_ptr(), _i64(y.stride()), g.data_ptr(),
+                                           out.data_ptr(), _i64(out.stride()), B, C, H, W, _dt(b), _stream()), "el_gated_residual_fwd")
+    return out
+
+
+class _Gated(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, b, y, gamma):
+        ctx.save_for_backward(y, gamma)
+        return _gated_fwd(b, y, gamma)
+
+    @staticmethod
+    def backward(ctx, g):
+        y, gamma = ctx.saved_tensors
+        t = torch.tanh(gamma.float())
+        # d/db = g ; d/dy = tanh(gamma) g ; d/dgamma = (1 - tanh^2) <g, y>   (three tiny reductions / scalings)
+        ggamma = ((g.float() * y.float()).sum() * (1 - t * t)).to(gamma.dtype)
+        return g, (g.float() * t).to(g.dtype), ggamma
+
+
+def gated_residual(b, y, gamma, inplace: bool = False) -> torch.Tensor:
+    """b + tanh(gamma) * y.  `inplace=True` writes the result over `b` (inference only)."""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (b, y, gamma)):
+        return _Gated.apply(b, y, gamma)
+    return _gated_fwd(b, y, gamma, out=b if inplace else None)
+
+
+# ------------------------------------------------------------------------------ attention
+def linear_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    """qkv (B, 3C, H, W) -> y (B, C, H, W); head_dim must be 64 (the only value the reference model produces)."""
+    _need_cuda(qkv)
+    B, C3, H, W = qkv.shape
+    C, N = C3 // 3, H * W
+    if C3 != 3 * C or C != heads * 64:
+        raise EdgelineError(f"linear_attention: need 3*heads*64 channels, got {C3} with heads={heads}")
+    if torch.is_grad_enabled() and qkv.requires_grad:
+        raise EdgelineError("linear_attention: backward kernel not available yet (inference only)")
+    y = _empty_like_layout(qkv, (B, C, H, W))
+    if _channels_last(qkv):
+        qs = (qkv.stride(0), 1, qkv.stride(3))  # token stride = W stride (H stride = W * that)
+        ys = (y.stride(0), 1, y.stride(3))
+        if qkv.stride(2) != W * qkv.stride(3):
+            raise EdgelineError("linear_attention: token axis must be uniformly strided")
+    else:
+        if qkv.stride(3) != 1 or qkv.stride(2) != W:
+            qkv = qkv.contiguous()
+        qs = (qkv.stride(0), qkv.stride(1), 1)
+        ys = (y.stride(0), y.stride(1), 1)
+    check(_lib.lib().el_linattn_fwd(qkv.data_ptr(), _i64(qs), y.data_ptr(), _i64(ys), B, heads, N, _dt(qkv), _stream()), "el_linattn_fwd")
+    return y
+
+
+# --------------------------------------------------------------------------------- decode
+def gfl_decode(boxes, clss, dgqp, strides, want_quality: bool = False):
+    """boxes[l] (B,64,Hl,Wl), clss[l] (B,nc,Hl,Wl), dgqp[l] = (w1 (64,20), b1 (64), w2 (64), b2 (1)) fp32,
+    strides[l] float -> y (B, 4+nc, A) fp32 [, q (B, A) fp32]."""
+    nl = len(boxes)
+    _need_cuda(*boxes, *clss)
+    B, nc = boxes[0].shape[0], clss[0].shape[1]
+    dt = _dt(boxes[0])
+    hw, bs, cs = [], [], []
+    for bx, cl in zip(boxes, clss):
+        if bx.shape[1] != 64 or cl.shape[1] != nc or bx.shape[-2:] != cl.shape[-2:] or bx.dtype != boxes[0].dtype or cl.dtype != boxes[0].dtype:
+            raise EdgelineError("gfl_decode: inconsistent level shapes / dtypes")
+        hw += [bx.shape[2], bx.shape[3]]
+        bs += list(bx.stride())
+        cs += list(cl.stride())
+    A = sum(hw[2 * i] * hw[2 * i + 1] for i in range(nl))
+    for w in dgqp:
+        for t in w:
+            if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                raise EdgelineError("gfl_decode: DGQP weights must be contiguous fp32 CUDA tensors")
+    y = torch.empty((B, 4 + nc, A), device=boxes[0].device, dtype=torch.float32)
+    q = torch.empty((B, A), device=boxes[0].device, dtype=torch.float32) if want_quality else None
+    cols = [_ptrs([w[k] for w in dgqp]) for k in range(4)]
+    check(_lib.lib().el_gfl_decode_fwd(nl, _ptrs(boxes), _i64(bs), _ptrs(clss), _i64(cs), (c_int32 * len(hw))(*hw),
+                                       (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3],
+                                       y.data_ptr(), q.data_ptr() if q is not None else None, B, nc, dt, _stream()), "el_gfl_decode_fwd")
+    return (y, q) if want_quality else y
+
+
+# ------------------------------------------------------------------------------------ NMS
+def nms_batched(pred: torch.Tensor, conf_thres=0.25, iou_thres=0.45, multi_label=False, agnostic=False, classes=None,
+                max_det=300, max_nms=30000, max_wh=7680.0, want_index=False):
+    """pred (B, 4+nc, A) fp32 -> (out (B, max_det, 6), count (B) int32 [, index (B, max_det) int64]); rows past
+    count[b] are undefined.  No host synchronisation."""
+    _need_cuda(pred)
+    if pred.dtype != torch.float32:
+        pred = pred.float()
+    pred = pred.contiguous()
+    B, no, A = pred.shape
+    nc = no - 4
+    L = _lib.lib()
+    need = c_size_t()
+    check(L.el_nms_workspace_bytes(B, nc, A, int(bool(multi_label)), int(max_nms), ctypes.byref(need)), "el_nms_workspace_bytes")
+    ws = torch.empty(need.value, device=pred.device, dtype=torch.uint8)
+    out = torch.empty((B, max_det, 6), device=pred.device, dtype=torch.float32)
+    cnt = torch.empty((B,), device=pred.device, dtype=torch.int32)
+    idx = torch.empty((B, max_det), device=pred.device, dtype=torch.int64) if want_index else None
+    keep = None
+    if classes is not None:
+        keep = torch.zeros(nc, dtype=torch.int32)
+        keep[torch.as_tensor(classes, dtype=torch.long)] = 1
+        keep = keep.to(pred.device)
+    check(L.el_nms_batched(pred.data_ptr(), B, nc, A, float(conf_thres), float(iou_thres), int(bool(multi_label)), int(bool(agnostic)),
+                           keep.data_ptr() if keep is not None else None, int(max_det), int(max_nms), float(max_wh), ws.data_ptr(),
+                           need.value, out.data_ptr(), cnt.data_ptr(), idx.data_ptr() if idx is not None else None, _stream()),
+          "el_nms_batched")
+    return (out, cnt, idx) if want_index else (out, cnt)
+
+
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float) -> torch.Tensor:
+    """Same contract as torchvision.ops.nms: int64 keep indices, descending score (one host sync for the count)."""
+    _need_cuda(boxes, scores)
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=boxes.device)
+    boxes = boxes.float().contiguous()
+    scores = scores.float().contiguous()
+    L = _lib.lib()
+    need = c_size_t()
+    check(L.el_nms_boxes_workspace_bytes(n, ctypes.byref(need)), "el_nms_boxes_workspace_bytes")
+    ws = torch.empty(need.value, device=boxes.device, dtype=torch.uint8)
+    keep = torch.empty(n, device=boxes.device, dtype=torch.int64)
+    cnt = torch.empty(1, device=boxes.device, dtype=torch.int32)
+    check(L.el_nms_boxes(boxes.data_ptr(), scores.data_ptr(), n, float(iou_threshold), ws.data_ptr(), need.value, keep.data_ptr(),
+                         cnt.data_ptr(), _stream()), "el_nms_boxes")
+    return keep[: int(cnt.item())]
+
+
+# --------------------------------------------------------------------------------- losses
+class _QFL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, beta, reduce_sum):
+        _need_cuda(pred, target)
+        p = pred.contiguous()
+        t = target.expand_as(pred).float().contiguous()
+        ctx.save_for_backward(p, t)
+        ctx.beta, ctx.reduce_sum = float(beta), reduce_sum
+        L, n = _lib.lib(), p.numel()
+        if reduce_sum:
+            total = torch.empty((), device=p.device, dtype=torch.float32)
+            part = torch.empty(L.el_qfl_partials(n), device=p.device, dtype=torch.float32)
+            check(L.el_qfl_fwd(p.data_ptr(), t.data_ptr(), n, ctx.beta, _dt(p), None, total.data_ptr(), part.data_ptr(), _stream()), "el_qfl_fwd")
+            return total
+        loss = torch.empty(p.shape, device=p.device, dtype=torch.float32)
+        check(L.el_qfl_fwd(p.data_ptr(), t.data_ptr(), n, ctx.beta, _dt(p), loss.data_ptr(), None, None, _stream()), "el_qfl_fwd")
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t = ctx.saved_tensors
+        gp = torch.empty_like(p)
+        g = g.float().contiguous()
+        args = (None, g.data_ptr()) if ctx.reduce_sum else (g.data_ptr(), None)
+        check(_lib.lib().el_qfl_bwd(p.data_ptr(), t.data_ptr(), p.numel(), ctx.beta, _dt(p), args[0], args[1], gp.data_ptr(), _stream()),
+              "el_qfl_bwd")
+        return gp, None, None, None
+
+
+def quality_focal_loss(pred, target, beta: float = 2.0, reduction: str = "none"):
+    """Same signature as utils/loss.py:22 `quality_focal_loss`; the result is fp32."""
+    if reduction == "none":
+        return _QFL.apply(pred, target, beta, False)
+    total = _QFL.apply(pred, target, beta, True)
+    return total / pred.numel() if reduction == "mean" else total
+
+
+class _DFL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_dist, target):
+        _need_cuda(pred_dist, target)
+        p = pred_dist.contiguous()
+        t = target.float().contiguous()
+        rows = t.shape[0]
+        if p.shape != (rows * 4, 16) or t.shape != (rows, 4):
+            raise EdgelineError(f"dfl: expected pred (4n,16) and target (n,4), got {tuple(p.shape)} / {tuple(t.shape)}")
+        ctx.save_for_backward(p, t)
+        loss = torch.empty((rows, 1), device=p.device, dtype=torch.float32)
+        if rows:
+            check(_lib.lib().el_dfl_fwd(p.data_ptr(), t.data_ptr(), rows, _dt(p), loss.data_ptr(), _stream()), "el_dfl_fwd")
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t = ctx.saved_tensors
+        gp = torch.empty_like(p)
+        if t.shape[0]:
+            g = g.float().contiguous()
+            check(_lib.lib().el_dfl_bwd(p.data_ptr(), t.data_ptr(), t.shape[0], _dt(p), g.data_ptr(), gp.data_ptr(), _stream()), "el_dfl_bwd")
+        return gp, None
+
+
+def dfl_loss(pred_dist: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """DFLoss.__call__ (utils/loss.py:209-224): pred (4n,16) logits, target (n,4) -> (n,1) fp32."""
+    return _DFL.apply(pred_dist, target)
+
+
+# --------------------------------------------------------------------------------- ingest
+def ingest_u8(src: torch.Tensor, dtype=torch.bfloat16, channels_last: bool = True, out: torch.Tensor | None = None) -> torch.Tensor:
+    """uint8 (B,H,W,3) images -> (B,3,H,W) activations / 255 (the predictor's preprocess, engine/predictor.py:117-135)."""
+    _need_cuda(src)
+    if src.dtype != torch.uint8 or src.dim() != 4 or src.shape[-1] != 3 or not src.is_contiguous():
+        raise EdgelineError("ingest_u8: need a contiguous uint8 (B,H,W,3) tensor")
+    B, H, W, _ = src.shape
+    if out is None:
+        out = torch.empty((B, 3, H, W), device=src.device, dtype=dtype,
+                          memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    check(_lib.lib().el_ingest_u8(src.data_ptr(), out.data_ptr(), _i64(out.stride()), B, H, W, _dt(out), _stream()), "el_ingest_u8")
+    return out

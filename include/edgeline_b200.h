@@ -1,0 +1,151 @@
+/*
+ * edgeline_b200.h -- C ABI of libedgeline_b200.so: hand-written sm_100a kernels for the
+ * custom-operator path of EdgeLine-YOLO (OneWalkman/EDGE-YOLO, a fork of ultralytics 8.3.63).
+ *
+ * The reference is pure Python; its "plugin API" for this path is a set of nn.Module classes
+ * and functions looked up by name.  Each entry point below replaces the
+ * body of one of them; the citation names the reference code it stands in for, paths relative
+ * to /root/reference/ultralytics/.  A reference-side binding is a ctypes call, see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer named `x`, `y`, `out`, ... is a DEVICE pointer unless the comment says
+ *     "host"; stride arrays, level tables and pointer tables are HOST arrays read during the call;
+ *   - strides are in ELEMENTS, logical order (n, c, h, w); any memory format (NCHW, NHWC,
+ *     channel-slice views) is expressed through them; 16-byte aligned, channel-contiguous views
+ *     take the vectorised kernels, everything else a generic strided kernel;
+ *   - `dtype` is an el_dtype and is the storage type of activations; arithmetic is fp32;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work: they never
+ *     allocate, never synchronise, and may be captured in a CUDA graph;
+ *   - return value: EL_OK (0) or an el_status error; there is no CPU fallback.
+ */
+#ifndef EDGELINE_B200_H
+#define EDGELINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { EL_F32 = 0, EL_F16 = 1, EL_BF16 = 2 } el_dtype;
+
+typedef enum {
+    EL_OK = 0,
+    EL_ERR_ARG = 1,         /* null pointer, non-positive size, bad enum */
+    EL_ERR_UNSUPPORTED = 2, /* shape outside the kernel's compiled envelope */
+    EL_ERR_WORKSPACE = 3,   /* workspace smaller than el_*_workspace_bytes says */
+    EL_ERR_CUDA = 4         /* launch failed; see el_last_cuda_error() */
+} el_status;
+
+const char* el_version(void);
+const char* el_status_string(int status);
+/* cudaError_t of the most recent failed launch on this thread (0 if none). */
+int el_last_cuda_error(void);
+/* Number of kernels this library has enqueued so far in the process (measurement aid: bench.py
+ * reports the per-step delta as `gpu_launches`). */
+unsigned long long el_launch_count(void);
+
+/* ---- a1. Haar analysis: _PywtDWT2D.forward, nn/modules/block.py:3619-3642 -------------------
+ * x (B,C,H,W) -> bands (4,B,C,H/2,W/2) in the order LL,LH,HL,HH; xs = {sn,sc,sh,sw},
+ * bs = {sband,sn,sc,sh,sw}.  Odd trailing row/column is dropped (floor), taps are
+ * float32(2^-1/2)^2 = 0.49999997 (block.py:3597-3609). */
+int el_dwt_haar_fwd(const void* x, const int64_t xs[4], void* bands, const int64_t bs[5],
+                    int B, int C, int H, int W, int dtype, void* stream);
+/* Adjoint (== the exact inverse up to the tap rounding): gradient of the above, and the Haar
+ * synthesis that inverse_2d_wavelet_transform (nn/modules/conv.py:438-443) performs.
+ * gbands (4,B,C,H/2,W/2) -> gx (B,C,H,W), every element of gx written. */
+int el_dwt_haar_bwd(const void* gbands, const int64_t gs[5], void* gx, const int64_t gxs[4],
+                    int B, int C, int H, int W, int dtype, void* stream);
+
+/* ---- a2. sub-band merge: _WaveletEnhancer.forward, block.py:3696-3708 -----------------------
+ * out (B,3c,H,W) = cat[b, up(LLp)*w0, up(LHp)*w1, up(HLp)*w2, up(HHp)*w3], up = bilinear
+ * align_corners=False (h,w)->(H,W), w = softplus(alpha)/(sum+1e-6) computed on the device from
+ * `alpha` (4 floats).  band[i] (B,c/2,h,w) with strides band_s[4*i..4*i+3]. */
+int el_wave_merge_fwd(const void* b, const int64_t bs[4], const void* const band[4],
+                      const int64_t band_s[16], const float* alpha, void* out,
+                      const int64_t os[4], int B, int c, int H, int W, int h, int w, int dtype,
+                      void* stream);
+/* Gradient of the merge: gout (B,3c,H,W) -> gb (B,c,H,W) (= gout[:, :c], written, not
+ * accumulated), gband[i] (B,c/2,h,w) (adjoint of the scaled upsample) and galpha_w (4 floats,
+ * d loss / d w[i] = <gout_i, up(band_i)>, accumulated with atomics -- zero it first). */
+int el_wave_merge_bwd(const void* gout, const int64_t gos[4], const void* const band[4],
+                      const int64_t band_s[16], const float* alpha, void* gb,
+                      const int64_t gbs[4], void* const gband[4], const int64_t gband_s[16],
+                      float* galpha_w, int B, int c, int H, int W, int h, int w, int dtype,
+                      void* stream);
+/* Gated residual, block.py:3710: out = b + tanh(gamma) * y; gamma is one device float.
+ * out may alias b. */
+int el_gated_residual_fwd(const void* b, const int64_t bs[4], const void* y, const int64_t ys[4],
+                          const float* gamma, void* out, const int64_t os[4], int B, int C,
+                          int H, int W, int dtype, void* stream);
+
+/* ---- a4. linear-attention core: LinearAttention.forward, block.py:3364-3372 -----------------
+ * qkv (B,3C,N) with strides qs = {sb, sc, sn} (channel = t*C + head*64 + j, t in q,k,v);
+ * y (B,C,N), ys likewise.  softmax_d(K), softmax_N(Q), ctx = K^T V, y = Q ctx.  head_dim is 64
+ * (heads = C/64, block.py:3474).  EL_BF16/EL_F16 inputs run the contraction on tcgen05 tensor
+ * cores with the accumulator in TMEM; EL_F32 runs an fp32 CUDA-core kernel (1e-5 contract). */
+int el_linattn_fwd(const void* qkv, const int64_t qs[3], void* y, const int64_t ys[3], int B,
+                   int heads, int N, int dtype, void* stream);
+
+/* ---- a6+a7. GFLv2 x UniHead decode: head.py:227-243 + 301-345, block.py:87-90, tal.py:333-357 --
+ * Per level l < nl: box[l] (B,64,Hl,Wl) DFL logits, cls[l] (B,nc,Hl,Wl) class logits (host
+ * tables of device pointers, strides box_s/cls_s[4*l..]), hw[2*l..] = {Hl,Wl}, stride[l].
+ * DGQP head weights (fp32, device): w1[l] (64,20), b1[l] (64), w2[l] (64), b2[l] (1).
+ * Writes y (B,4+nc,A) fp32 contiguous: rows 0-3 = (cx,cy,w,h)*stride, rows 4.. =
+ * sigmoid(cls)*clamp(q,1e-6,1-1e-6); optional q_out (B,A) fp32 (may be NULL). */
+int el_gfl_decode_fwd(int nl, const void* const* box, const int64_t* box_s, const void* const* cls,
+                      const int64_t* cls_s, const int32_t* hw, const float* stride,
+                      const float* const* w1, const float* const* b1, const float* const* w2,
+                      const float* const* b2, float* y, float* q_out, int B, int nc, int dtype,
+                      void* stream);
+
+/* ---- a9. batched NMS: non_max_suppression, utils/ops.py:167-316 (detection, nm=0) ------------
+ * pred (B,4+nc,A) fp32 contiguous, xywh + scores (the tensor el_gfl_decode_fwd writes).
+ * Candidate build (conf filter, multi-label expansion or first-max class, optional class
+ * filter), top-max_nms cut, class-offset (cls*max_wh), stable descending sort and greedy IoU
+ * suppression (torchvision.ops.nms semantics: strict `>`, IoU in fp32 compared with the
+ * threshold as a double, no epsilon) all run on the device with no host synchronisation.
+ * out (B,max_det,6) rows [x1,y1,x2,y2,score,cls]; out_count (B); out_index (B,max_det) int64 =
+ * anchor*nc+cls of each kept row (may be NULL).  class_keep: nc int32 flags or NULL. */
+int el_nms_workspace_bytes(int B, int nc, int A, int multi_label, int max_nms, size_t* bytes);
+int el_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, double iou_thres,
+                   int multi_label, int agnostic, const int32_t* class_keep, int max_det,
+                   int max_nms, float max_wh, void* workspace, size_t workspace_bytes, float* out,
+                   int32_t* out_count, int64_t* out_index, void* stream);
+/* torchvision.ops.nms(boxes, scores, iou) itself (call site utils/ops.py:296): boxes (n,4) xyxy
+ * fp32, scores (n) fp32 -> keep (n) int64 indices in descending-score order, keep_count (1). */
+int el_nms_boxes_workspace_bytes(int n, size_t* bytes);
+int el_nms_boxes(const float* boxes, const float* scores, int n, double iou_thres, void* workspace,
+                 size_t workspace_bytes, int64_t* keep, int32_t* keep_count, void* stream);
+
+/* ---- a10. Quality Focal Loss: quality_focal_loss, utils/loss.py:22-70 ------------------------
+ * pred (n) logits in `dtype`, target (n) fp32.  fwd: loss (n) fp32 elementwise (may be NULL)
+ * and/or loss_sum (1 float, deterministic two-stage reduction; may be NULL; needs `partials`
+ * of el_qfl_partials() floats).  bwd: gpred = g * dloss/dpred with g = gout[i] (elementwise,
+ * fp32) or *gscalar (one device float) -- exactly one of the two non-NULL. */
+int el_qfl_partials(int64_t n);
+int el_qfl_fwd(const void* pred, const float* target, int64_t n, float beta, int dtype, float* loss,
+               float* loss_sum, float* partials, void* stream);
+int el_qfl_bwd(const void* pred, const float* target, int64_t n, float beta, int dtype,
+               const float* gout, const float* gscalar, void* gpred, void* stream);
+
+/* ---- a11. Distribution Focal Loss: DFLoss.__call__, utils/loss.py:209-224 -------------------
+ * pred (rows*4, 16) logits in `dtype` contiguous, target (rows,4) fp32 (NOT modified; the
+ * reference clamps in place, the clamp is applied on the fly here).  fwd: loss (rows) fp32 =
+ * mean over the 4 sides.  bwd: gpred (rows*4,16) = gout[row] * (softmax - wl*d_tl - wr*d_tr)/4. */
+int el_dfl_fwd(const void* pred, const float* target, int64_t rows, int dtype, float* loss,
+               void* stream);
+int el_dfl_bwd(const void* pred, const float* target, int64_t rows, int dtype, const float* gout,
+               void* gpred, void* stream);
+
+/* ---- ingest: uint8 HWC images -> normalised NHWC activations (engine/predictor.py:117-135) ----
+ * src (B,H,W,3) uint8 -> dst (B,3,H,W) logical with strides ds, value/255 in `dtype`. */
+int el_ingest_u8(const uint8_t* src, void* dst, const int64_t ds[4], int B, int H, int W, int dtype,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDGELINE_B200_H */

@@ -1,0 +1,98 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports exactly what
+include/edgeline_b200.h declares; argument validation happens before any CUDA work; the Python
+host layer refuses CPU tensors (there is no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from edge_yolo_b200 import _lib, build
+
+    build.build()
+    return _lib.lib()
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "edgeline_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(el_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound(lib):
+    from edge_yolo_b200 import _lib
+
+    declared = _declared()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_lib.EXPORTED) == declared
+
+
+def test_version_and_status_strings(lib):
+    assert b"sm_100a" in lib.el_version()
+    assert lib.el_status_string(0) == b"ok"
+    assert lib.el_status_string(2) == b"unsupported shape"
+
+
+def test_argument_validation_without_gpu(lib):
+    z = (ctypes.c_int64 * 5)()
+    assert lib.el_dwt_haar_fwd(None, z, None, z, 1, 1, 2, 2, 0, None) == 1
+    assert lib.el_linattn_fwd(None, z, None, z, 1, 1, 4, 0, None) == 1
+    n = ctypes.c_size_t()
+    assert lib.el_nms_workspace_bytes(64, 80, 8400, 0, 30000, ctypes.byref(n)) == 0 and n.value > 64 * 8400 * 8
+    assert lib.el_nms_workspace_bytes(64, 80, 8400, 1, 30000, ctypes.byref(n)) == 0 and n.value > 64 * 8400 * 80 * 8
+    assert lib.el_nms_workspace_bytes(0, 80, 8400, 1, 30000, ctypes.byref(n)) == 1
+    assert lib.el_nms_batched(None, 1, 1, 1, 0.5, 0.5, 0, 0, None, 300, 30000, 7680.0, None, 0, None, None, None, None) == 1
+    assert lib.el_qfl_partials(64 * 8400 * 80) >= 148
+
+
+def test_no_cpu_fallback():
+    from edge_yolo_b200 import EdgelineError, ops
+
+    x = torch.randn(1, 4, 8, 8)
+    with pytest.raises(EdgelineError):
+        ops.dwt_haar(x)
+    with pytest.raises(EdgelineError):
+        ops.linear_attention(torch.randn(1, 192, 4, 4), 1)
+    with pytest.raises(EdgelineError):
+        ops.nms_batched(torch.rand(1, 6, 10))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "edge_yolo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, f"{f} mentions the oracle: the product path must not depend on it"
+
+
+def test_standalone_graph_matches_reference_parameter_counts():
+    from edge_yolo_b200.model import EdgeLineYOLO
+
+    # SURVEY.md appendix A (counted on the reference): n 2,678,699  s 9,617,483
+    assert sum(p.numel() for p in EdgeLineYOLO("n", 80).parameters()) == 2678699
+    assert sum(p.numel() for p in EdgeLineYOLO("s", 80).parameters()) == 9617483
+    assert sum(p.numel() for p in EdgeLineYOLO("s", 10).parameters()) == 9590393
+
+
+def test_nms_signature_matches_reference():
+    import inspect
+
+    from edge_yolo_b200.nms import non_max_suppression
+
+    names = list(inspect.signature(non_max_suppression).parameters)
+    assert names == ["prediction", "conf_thres", "iou_thres", "classes", "agnostic", "multi_label", "labels", "max_det", "nc",
+                     "max_time_img", "max_nms", "max_wh", "in_place", "rotated"]
+    with pytest.raises(AssertionError):
+        non_max_suppression(torch.zeros(1, 6, 4), conf_thres=1.5)
+    # end-to-end shaped input never touches a kernel (ops.py:224-228)
+    out = non_max_suppression(torch.tensor([[[0, 0, 1, 1, 0.9, 1.0], [0, 0, 1, 1, 0.1, 2.0]]]), conf_thres=0.25)
+    assert out[0].shape == (1, 6)

@@ -1,0 +1,67 @@
+"""Dev-container-only checks against the unmodified reference (skipped where /root/reference is absent):
+state-dict compatibility of the standalone graph, and the whole-model CPU oracle vs the reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader
+
+pytestmark = [pytest.mark.reference, pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")]
+
+
+@pytest.fixture(scope="module")
+def ref_model():
+    ref_loader.load()
+    from ultralytics.nn.tasks import DetectionModel
+
+    torch.manual_seed(0)
+    m = DetectionModel(ref_loader.REFERENCE_ROOT + "/ultralytics/cfg/models/11/yolo11n-test.yaml", ch=3, nc=80, verbose=False).eval()
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if k.endswith("wave.gamma"):
+                p.fill_(0.5)
+    return m
+
+
+def test_state_dict_keys_and_shapes_match(ref_model):
+    from edge_yolo_b200.model import EdgeLineYOLO
+
+    mine = EdgeLineYOLO("n", 80).state_dict()
+    ref = ref_model.state_dict()
+    assert list(mine.keys()) == list(ref.keys())
+    assert all(mine[k].shape == ref[k].shape for k in ref)
+
+
+def test_whole_model_oracle_matches_reference(ref_model):
+    from edge_yolo_b200.model import EdgeLineYOLO
+    from oracle import model_ref
+
+    mine = EdgeLineYOLO("n", 80).float().eval()
+    mine.load_state_dict(ref_model.state_dict(), strict=True)
+    model_ref.to_oracle(mine)
+    x = torch.rand(2, 3, 192, 256, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        y_ref, feats_ref = ref_model(x)
+        y, feats = mine(x)
+    for a, b in zip(feats, feats_ref):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(y[:, :4].numpy(), y_ref[:, :4].numpy(), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(y[:, 4:].numpy(), y_ref[:, 4:].numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_nms_oracle_matches_reference_on_model_output(ref_model):
+    from ultralytics.utils import ops as rops
+
+    from oracle import hotpath as O
+
+    x = torch.rand(2, 3, 160, 160, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        y_ref, _ = ref_model(x)
+    # no max_nms cut here: random-init scores are heavily tied and the reference's pre-cut argsort
+    # (ops.py:286) orders ties in an implementation-defined way, which is outside the parity contract
+    for kw in (dict(conf_thres=0.25, iou_thres=0.7), dict(conf_thres=0.262, iou_thres=0.7, multi_label=True)):
+        want = rops.non_max_suppression(y_ref.clone(), max_time_img=1e9, **kw)
+        got, _ = O.non_max_suppression(y_ref.numpy(), **kw)
+        assert [g.shape[0] for g in got] == [w.shape[0] for w in want]
+        for g, w in zip(got, want):
+            assert g.tobytes() == w.numpy().astype(np.float32).tobytes()
