@@ -189,7 +189,7 @@ def test_decode_vs_oracle(dtype, tol, cl, nc, sizes):
     B = 2
     boxes = [(torch.randn(B, 64, h, w, generator=gen) * 2).to(dtype) for h, w in sizes]
     clss = [(torch.randn(B, nc, h, w, generator=gen) * 2).to(dtype) for h, w in sizes]
-    ws = [(torch.randn(64, 20, generator=gen) * 2, torch.randn(64, generator=gen), torch.randn(64, generator=gen) * 0.3, torch.randn(1, generator=gen)) for _ in sizes]
+    ws = [(torch.randn(64, 20, generator=gen) * 2, torch.randn(64, generator=gen), torch.randn(1, 64, generator=gen) * 0.3, torch.randn(1, generator=gen)) for _ in sizes]
     quals = [O.dgqp_quality(b.float(), *w) for b, w in zip(boxes, ws)]
     ref = O.gfl_decode([b.float() for b in boxes], [c.float() for c in clss], quals, [8.0, 16.0, 32.0])
     fmt = torch.channels_last if cl else torch.contiguous_format
@@ -203,7 +203,7 @@ def test_decode_cat_views():
     """box / cls passed as channel-slice views of one cat tensor, like the reference's x[i] (head.py:903)."""
     gen = torch.Generator().manual_seed(7)
     x = torch.randn(2, 64 + 5, 6, 7, generator=gen)
-    w = (torch.randn(64, 20, generator=gen), torch.randn(64, generator=gen), torch.randn(64, generator=gen), torch.randn(1, generator=gen))
+    w = (torch.randn(64, 20, generator=gen), torch.randn(64, generator=gen), torch.randn(1, 64, generator=gen), torch.randn(1, generator=gen))
     q = O.dgqp_quality(x[:, :64], *w)
     ref = O.gfl_decode([x[:, :64]], [x[:, 64:]], [q], [8.0])
     xd = x.to(DEV)
