@@ -372,6 +372,127 @@ __global__ void __launch_bounds__(256) ingest_u8_kernel(const uint8_t* __restric
     }
 }
 
+
+// =============================================================================================
+// Tiled fast paths.  Thread <-> (channel vector cv, column) is fixed for the whole kernel, so every
+// division, bilinear column weight and band pointer is computed once; the thread then walks kRows
+// rows with pointer increments only.  grid = (column tiles, row chunks, images).
+// =============================================================================================
+constexpr int kRows = 8;
+
+struct TileMap {
+    int cv, col;      // this thread's channel vector and column
+    bool active;
+};
+__device__ __forceinline__ TileMap tile_map(int CV, int cols_per_block, int n_cols) {
+    TileMap m;
+    const int xi = (int)threadIdx.x / CV;
+    m.cv = (int)threadIdx.x - xi * CV;
+    m.col = (int)blockIdx.x * cols_per_block + xi;
+    m.active = xi < cols_per_block && m.col < n_cols;
+    return m;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dwt_fwd_tiled(const T* __restrict__ x, Strides4 xs, T* __restrict__ o, int64_t ob, Strides4 os, int CV,
+                                                     int cols_per_block, int H2, int W2) {
+    constexpr int V = Vec16<T>::N;
+    const TileMap m = tile_map(CV, cols_per_block, W2);
+    if (!m.active) return;
+    const float k = kHaar;
+    const int i0 = (int)blockIdx.y * kRows, i1 = min(i0 + kRows, H2);
+    const int64_t n = blockIdx.z;
+    const T* p = x + n * xs.n + (int64_t)(2 * i0) * xs.h + (int64_t)(2 * m.col) * xs.w + m.cv * V;
+    T* q = o + n * os.n + (int64_t)i0 * os.h + (int64_t)m.col * os.w + m.cv * V;
+#pragma unroll 2
+    for (int i = i0; i < i1; ++i, p += 2 * xs.h, q += os.h) {
+        float a[V], b[V], c[V], d[V];
+        uint4 ra = ldg_stream(p), rb = ldg_stream(p + xs.w), rc = ldg_stream(p + xs.h), rd = ldg_stream(p + xs.h + xs.w);
+        unpack<T>(ra, a); unpack<T>(rb, b); unpack<T>(rc, c); unpack<T>(rd, d);
+        float ll[V], lh[V], hl[V], hh[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            float s0 = a[e] + b[e], s1 = c[e] + d[e], d0 = a[e] - b[e], d1 = c[e] - d[e];
+            ll[e] = k * (s0 + s1); lh[e] = k * (d0 + d1); hl[e] = k * (s0 - s1); hh[e] = k * (d0 - d1);
+        }
+        *reinterpret_cast<uint4*>(q) = pack<T>(ll);
+        *reinterpret_cast<uint4*>(q + ob) = pack<T>(lh);
+        *reinterpret_cast<uint4*>(q + 2 * ob) = pack<T>(hl);
+        *reinterpret_cast<uint4*>(q + 3 * ob) = pack<T>(hh);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) merge_fwd_tiled(const T* __restrict__ b, Strides4 bs, BandPtrs bands, const float* __restrict__ alpha,
+                                                       T* __restrict__ out, Strides4 os, int c, int CV, int cols_per_block, int H, int W, int h, int w) {
+    constexpr int V = Vec16<T>::N;
+    const TileMap m = tile_map(CV, cols_per_block, W);
+    if (!m.active) return;
+    const int y0b = (int)blockIdx.y * kRows, y1b = min(y0b + kRows, H);
+    const int64_t n = blockIdx.z;
+    const int ch = m.cv * V;
+    T* q = out + n * os.n + (int64_t)y0b * os.h + (int64_t)m.col * os.w + ch;
+    if (ch < c) {  // pass-through copy of b
+        const T* p = b + n * bs.n + (int64_t)y0b * bs.h + (int64_t)m.col * bs.w + ch;
+#pragma unroll 4
+        for (int y = y0b; y < y1b; ++y, p += bs.h, q += os.h) stg_stream(q, ldg_stream(p));
+        return;
+    }
+    const int half = c / 2, seg = (ch - c) / half, cc = (ch - c) - seg * half;
+    float wt[4];
+    band_weights(alpha, wt);
+    const float wb = seg == 0 ? wt[0] : seg == 1 ? wt[1] : seg == 2 ? wt[2] : wt[3];
+    const float sh = (float)h / (float)H, swd = (float)w / (float)W;
+    int x0, x1; float lx;
+    bilin_src(m.col, swd, w, x0, x1, lx);
+    const Strides4 s = bands.s[seg];
+    const T* p0 = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + cc + (int64_t)x0 * s.w;
+    const T* p1 = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + cc + (int64_t)x1 * s.w;
+    const float wx0 = 1.f - lx;
+    for (int y = y0b; y < y1b; ++y, q += os.h) {
+        int ya, yb; float ly;
+        bilin_src(y, sh, h, ya, yb, ly);
+        float v00[V], v01[V], v10[V], v11[V], r[V];
+        // each band pixel feeds ~4 output pixels: keep it in L1
+        unpack<T>(ldg_cached(p0 + (int64_t)ya * s.h), v00);
+        unpack<T>(ldg_cached(p1 + (int64_t)ya * s.h), v01);
+        unpack<T>(ldg_cached(p0 + (int64_t)yb * s.h), v10);
+        unpack<T>(ldg_cached(p1 + (int64_t)yb * s.h), v11);
+        const float wy0 = 1.f - ly;
+#pragma unroll
+        for (int e = 0; e < V; ++e) r[e] = (wy0 * (wx0 * v00[e] + lx * v01[e]) + ly * (wx0 * v10[e] + lx * v11[e])) * wb;
+        stg_stream(q, pack<T>(r));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gated_tiled(const T* b, Strides4 bs, const T* __restrict__ y, Strides4 ys, const float* __restrict__ gamma, T* o,
+                                                   Strides4 os, int CV, int cols_per_block, int H, int W) {
+    constexpr int V = Vec16<T>::N;
+    const TileMap m = tile_map(CV, cols_per_block, W);
+    if (!m.active) return;
+    const float g = tanhf(__ldg(gamma));
+    const int r0 = (int)blockIdx.y * kRows, r1 = min(r0 + kRows, H);
+    const int64_t n = blockIdx.z;
+    const T* pb = b + n * bs.n + (int64_t)r0 * bs.h + (int64_t)m.col * bs.w + m.cv * V;
+    const T* py = y + n * ys.n + (int64_t)r0 * ys.h + (int64_t)m.col * ys.w + m.cv * V;
+    T* po = o + n * os.n + (int64_t)r0 * os.h + (int64_t)m.col * os.w + m.cv * V;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r, pb += bs.h, py += ys.h, po += os.h) {
+        float fb[V], fy[V], res[V];
+        unpack<T>(*reinterpret_cast<const uint4*>(pb), fb);  // b may alias o: coherent load
+        unpack<T>(ldg_stream(py), fy);
+#pragma unroll
+        for (int e = 0; e < V; ++e) res[e] = fb[e] + g * fy[e];
+        *reinterpret_cast<uint4*>(po) = pack<T>(res);
+    }
+}
+
+static inline dim3 tile_grid(int CV, int n_cols, int n_rows, int B, int& cols_per_block) {
+    cols_per_block = 256 / CV;
+    return dim3((unsigned)ceil_div(n_cols, cols_per_block), (unsigned)ceil_div(n_rows, kRows), (unsigned)B);
+}
+
 // grid for a streaming grid-stride kernel: enough CTAs to cover `total`, capped at a multiple
 // of the SM count so the tail wave is full (148 SMs x 8 resident 256-thread CTAs)
 static inline int stream_grid(int64_t total, int threads = 256) {
@@ -395,8 +516,14 @@ extern "C" int el_dwt_haar_fwd(const void* x, const int64_t xs_[4], void* bands,
     EL_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec16<T>::N;
         if (channel_vectorisable<T>(x, xs, C) && channel_vectorisable<T>(bands, os, C) && ob % V == 0) {
-            int64_t total = (int64_t)B * H2 * W2 * (C / V);
-            dwt_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C / V, H2, W2, total);
+            if (C / V <= 256 && B <= 65535) {
+                int cpb;
+                dim3 g = tile_grid(C / V, W2, H2, B, cpb);
+                dwt_fwd_tiled<T><<<g, 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C / V, cpb, H2, W2);
+            } else {
+                int64_t total = (int64_t)B * H2 * W2 * (C / V);
+                dwt_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C / V, H2, W2, total);
+            }
         } else {
             int64_t total = (int64_t)B * C * H2 * W2;
             if (xs.c == 1)
@@ -441,8 +568,14 @@ extern "C" int el_wave_merge_fwd(const void* b, const int64_t bs_[4], const void
         bool vec = channel_vectorisable<T>(b, bs, c) && channel_vectorisable<T>(out, os, 3 * c) && (c / 2) % V == 0;
         for (int i = 0; i < 4; ++i) vec = vec && channel_vectorisable<T>(bp.p[i], bp.s[i], c / 2);
         if (vec) {
-            int64_t total = (int64_t)B * H * W * (3 * c / V);
-            merge_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, H, W, h, w, total);
+            if (3 * c / V <= 256 && B <= 65535) {
+                int cpb;
+                dim3 g = tile_grid(3 * c / V, W, H, B, cpb);
+                merge_fwd_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, 3 * c / V, cpb, H, W, h, w);
+            } else {
+                int64_t total = (int64_t)B * H * W * (3 * c / V);
+                merge_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, H, W, h, w, total);
+            }
         } else {
             int64_t total = (int64_t)B * 3 * c * H * W;
             if (os.c == 1)
@@ -511,8 +644,14 @@ extern "C" int el_gated_residual_fwd(const void* b, const int64_t bs_[4], const 
     EL_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec16<T>::N;
         if (channel_vectorisable<T>(b, bs, C) && channel_vectorisable<T>(y, ys, C) && channel_vectorisable<T>(out, os, C)) {
-            int64_t total = (int64_t)B * H * W * (C / V);
-            gated_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, C / V, H, W, total);
+            if (C / V <= 256 && B <= 65535) {
+                int cpb;
+                dim3 g = tile_grid(C / V, W, H, B, cpb);
+                gated_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, C / V, cpb, H, W);
+            } else {
+                int64_t total = (int64_t)B * H * W * (C / V);
+                gated_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, C / V, H, W, total);
+            }
         } else {
             int64_t total = (int64_t)B * C * H * W;
             if (os.c == 1)

@@ -102,6 +102,7 @@ class EdgeLineYOLO(nn.Module):
             outs.append(x if m.i in self.save else None)
         return x
 
+    @torch.no_grad()
     def fuse(self, dsconv: bool = False):
         """Fold BatchNorm into the preceding conv.  Like BaseModel.fuse (tasks.py:214-242) only `Conv`
         (incl. DWConv) is folded by default; `dsconv=True` additionally folds DSConv's BN into its
