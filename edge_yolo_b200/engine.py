@@ -27,7 +27,7 @@ def build_model(scale="n", nc=80, seed=0, gamma=0.5, dtype=torch.bfloat16, devic
             if isinstance(m, _WaveletEnhancer):
                 m.gamma.fill_(gamma)
     if fuse:
-        model.fuse(dsconv=True)
+        model.fuse(engine=True)
     model = model.to(device=device, dtype=dtype).to(memory_format=torch.channels_last)
     for p in model.parameters():
         p.requires_grad_(False)

@@ -9,10 +9,12 @@ tests on machines where the reference package is absent; with ultralytics presen
 from __future__ import annotations
 
 import math
+import types
 
 import torch
 import torch.nn as nn
 
+from . import modules as M
 from .modules import C2PSA_LinearAttention, Concat, Conv, DSC3K2_Wavelet, DSConv, GFLHeadv2_uniH, SPPF
 
 # [depth, width, max_channels]  (yolo11-test.yaml:9-15)
@@ -98,23 +100,53 @@ class EdgeLineYOLO(nn.Module):
         for m in self.model:
             if m.f != -1:
                 x = outs[m.f] if isinstance(m.f, int) else [x if j == -1 else outs[j] for j in m.f]
+            if getattr(m, "el_fused_into_next", False):  # nn.Upsample folded into the following Concat (engine mode)
+                outs.append(None)
+                continue
             x = m(x)
             outs.append(x if m.i in self.save else None)
         return x
 
     @torch.no_grad()
-    def fuse(self, dsconv: bool = False):
+    def fuse(self, dsconv: bool = False, engine: bool = False):
         """Fold BatchNorm into the preceding conv.  Like BaseModel.fuse (tasks.py:214-242) only `Conv`
         (incl. DWConv) is folded by default; `dsconv=True` additionally folds DSConv's BN into its
-        pointwise conv (identical maths in eval mode, one kernel less per DSConv)."""
+        pointwise conv (identical maths in eval mode, one kernel less per DSConv).
+
+        `engine=True` (implies dsconv; eval / NHWC only) additionally moves every folded bias + activation
+        (+ shortcut add) into one `el_bias_act` epilogue kernel, removes the torch.cat / split copies of the
+        C2f-style blocks and fuses nn.Upsample + Concat pairs (see modules.*_engine_forward)."""
+        dsconv = dsconv or engine
+        acts = {nn.SiLU: M.ops.ACT_SILU, nn.Identity: M.ops.ACT_NONE, nn.ReLU: M.ops.ACT_RELU}
         for m in self.modules():
             if isinstance(m, Conv) and hasattr(m, "bn"):
                 m.conv = _fold(m.conv, m.bn)
                 del m.bn
                 m.forward = m.forward_fuse
+                if engine and type(m.act) in acts:
+                    m.el_bias, m.el_act = m.conv.bias.detach().float().clone(), acts[type(m.act)]
+                    m.conv.bias = None
+                    m.forward = types.MethodType(M.conv_engine_forward, m)
             elif dsconv and isinstance(m, DSConv) and isinstance(m.bn, nn.BatchNorm2d):
                 m.pw = _fold(m.pw, m.bn)
                 m.bn = nn.Identity()
+                if engine:
+                    m.el_bias = m.pw.bias.detach().float().clone()
+                    m.pw.bias = None
+                    m.forward = types.MethodType(M.dsconv_engine_forward, m)
+        if engine:
+            binds = {M.DSBottleneck: M.dsbottleneck_engine_forward, M.DSC3k: M.dsc3k_engine_forward,
+                     M.DSC3K2_Wavelet: M.dsc3k2_wavelet_engine_forward, M.PSABlock_LinearAttention: M.psablock_engine_forward,
+                     M.C2PSA_LinearAttention: M.c2psa_engine_forward}
+            for m in self.modules():
+                if type(m) in binds:
+                    m.forward = types.MethodType(binds[type(m)], m)
+            layers = list(self.model)
+            for up, cat in zip(layers, layers[1:]):
+                if (isinstance(up, nn.Upsample) and isinstance(cat, Concat) and up.scale_factor == 2 and up.mode == "nearest"
+                        and isinstance(cat.f, list) and cat.f[0] == -1 and cat.d == 1 and up.i not in self.save):
+                    up.el_fused_into_next, cat.el_upsample_first = True, True
+                    cat.forward = types.MethodType(M.concat_engine_forward, cat)
         return self
 
 

@@ -36,7 +36,7 @@ def dwt_forward(self, x: torch.Tensor):
     return buf[:B], buf[B : 2 * B], buf[2 * B : 3 * B], buf[3 * B :]
 
 
-def wavelet_enhancer_forward(self, b: torch.Tensor) -> torch.Tensor:
+def wavelet_enhancer_forward(self, b: torch.Tensor, inplace: bool = False) -> torch.Tensor:
     """`_WaveletEnhancer.forward` (block.py:3685-3710).
 
     DWT split -> f_ll / shared f_h convs (cuDNN) -> fused upsample*w+concat kernel -> fuse conv ->
@@ -54,7 +54,7 @@ def wavelet_enhancer_forward(self, b: torch.Tensor) -> torch.Tensor:
         LHp, HLp, HHp = hp[:B], hp[B : 2 * B], hp[2 * B :]
     cat = ops.wave_merge(b, LLp, LHp, HLp, HHp, self.alpha)
     y = self.fuse(cat)
-    return ops.gated_residual(b, y, self.gamma)
+    return ops.gated_residual(b, y, self.gamma, inplace=inplace and not torch.is_grad_enabled())
 
 
 def linear_attention_forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -108,6 +108,93 @@ def gfl_head_forward(self, x):
     for i in range(self.nl):
         x[i] = torch.cat((boxes[i], clss[i]), 1)
     return y, x
+
+
+# ------------------------------------------------------------------------------------------
+# inference-engine forwards (bound by EdgeLineYOLO.fuse(engine=True); eval only, NHWC activations)
+#
+# Same maths as the reference modules after BaseModel.fuse() (nn/tasks.py:214-242), but every conv
+# epilogue (folded-BN bias + SiLU, shortcut add) is one el_bias_act kernel that can write straight into
+# a channel slice of the block's concat buffer, so torch.cat / broadcast-add / SiLU launches vanish.
+# ------------------------------------------------------------------------------------------
+
+
+def _bias_on(self, x):
+    b = self.el_bias
+    if b is not None and b.device != x.device:
+        b = self.el_bias = b.to(x.device)
+    return b
+
+
+def conv_engine_forward(self, x, out=None, residual=None):
+    """Conv.forward_fuse (conv.py:58-60): conv (cuDNN, no bias) -> fused bias + activation [+ residual]."""
+    return ops.bias_act(self.conv(x), _bias_on(self, x), self.el_act, residual=residual, out=out)
+
+
+def dsconv_engine_forward(self, x, out=None, residual=None):
+    """DSConv.forward (conv.py:100-104) with its BatchNorm folded into the pointwise conv."""
+    return ops.bias_act(self.pw(self.dw(x)), _bias_on(self, x), ops.ACT_SILU, residual=residual, out=out)
+
+
+def dsbottleneck_engine_forward(self, x, out=None):
+    """DSBottleneck.forward (block.py:1500-1503): the shortcut add rides in cv2's epilogue."""
+    return self.cv2(self.cv1(x), out=out, residual=x if self.add else None)
+
+
+def dsc3k_engine_forward(self, x, out=None):
+    """C3.forward (block.py:394-396) for DSC3k: both branches land in one buffer, no torch.cat."""
+    B, _, H, W = x.shape
+    c_ = self.cv1.conv.out_channels
+    buf = torch.empty((B, 2 * c_, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    cur = self.cv1(x)
+    last = len(self.m) - 1
+    for k, blk in enumerate(self.m):
+        cur = blk(cur, out=buf[:, :c_] if k == last else None)
+    if last < 0:
+        buf[:, :c_].copy_(cur)
+    self.cv2(x, out=buf[:, c_:])
+    return self.cv3(buf, out=out)
+
+
+def dsc3k2_wavelet_engine_forward(self, x):
+    """DSC3K2_Wavelet.forward (block.py:3783-3788): cv1 writes [a | b] into the concat buffer, the enhancer
+    updates b in place, each stacked block appends its output slice, cv2 reads the buffer."""
+    B, _, H, W = x.shape
+    c, n = self.c, len(self.m)
+    buf = torch.empty((B, (2 + n) * c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    self.cv1(x, out=buf[:, : 2 * c])
+    cur = wavelet_enhancer_forward(self.wave, buf[:, c : 2 * c], inplace=True)
+    for k, blk in enumerate(self.m):
+        cur = blk(cur, out=buf[:, (2 + k) * c : (3 + k) * c])
+    return self.cv2(buf)
+
+
+def psablock_engine_forward(self, x, out=None):
+    """PSABlock_LinearAttention.forward (block.py:3446-3449) with both residual adds fused into epilogues."""
+    att = self.attn
+    y = ops.linear_attention(att.qkv(x), att.num_heads)
+    x = ops.bias_act(att.proj(y), att.proj.bias.float() if att.proj.bias is not None else None, ops.ACT_NONE, residual=x)
+    return self.ffn[1](self.ffn[0](x), out=out, residual=x)
+
+
+def c2psa_engine_forward(self, x):
+    """C2PSA_LinearAttention.forward (block.py:3489-3497) without split / cat copies."""
+    B, _, H, W = x.shape
+    c = self.c
+    buf = torch.empty((B, 2 * c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    self.cv1(x, out=buf)
+    cur = buf[:, c:]
+    last = len(self.m) - 1
+    for k, blk in enumerate(self.m):
+        cur = blk(cur, out=buf[:, c:] if k == last else None)
+    return self.cv2(buf)
+
+
+def concat_engine_forward(self, x):
+    """Concat (conv.py Concat) whose first input is the low-resolution map of the preceding nn.Upsample."""
+    if getattr(self, "el_upsample_first", False):
+        return ops.upsample2x_cat(x[0], x[1])
+    return torch.cat(x, self.d)
 
 
 # ------------------------------------------------------------------------------------------

@@ -387,3 +387,38 @@ def ingest_u8(src: torch.Tensor, dtype=torch.bfloat16, channels_last: bool = Tru
                           memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     check(_lib.lib().el_ingest_u8(src.data_ptr(), out.data_ptr(), _i64(out.stride()), B, H, W, _dt(out), _stream()), "el_ingest_u8")
     return out
+
+
+# ------------------------------------------------------------------------------ epilogues
+ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
+
+
+def bias_act(x: torch.Tensor, bias: torch.Tensor | None, act: int = ACT_SILU, residual: torch.Tensor | None = None,
+             out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = act(x + bias[c]) (+ residual).  Inference-engine epilogue of a cuDNN conv; `out` defaults to `x` (in place)
+    and may be a channel slice of a wider concat buffer."""
+    _need_cuda(x)
+    B, C, H, W = x.shape
+    out = x if out is None else out
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != C or not bias.is_contiguous()):
+        raise EdgelineError("bias_act: bias must be a contiguous fp32 vector of C elements")
+    if residual is not None and (residual.shape != x.shape or residual.dtype != x.dtype):
+        raise EdgelineError("bias_act: residual must match x")
+    check(_lib.lib().el_bias_act_fwd(x.data_ptr(), _i64(x.stride()), bias.data_ptr() if bias is not None else None,
+                                     residual.data_ptr() if residual is not None else None,
+                                     _i64(residual.stride()) if residual is not None else None, out.data_ptr(), _i64(out.stride()),
+                                     B, C, H, W, int(act), _dt(x), _stream()), "el_bias_act_fwd")
+    return out
+
+
+def upsample2x_cat(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+    """cat[nearest-2x(x), skip] along channels in one pass (NHWC activations)."""
+    _need_cuda(x, skip)
+    B, C1, h, w = x.shape
+    C2, H, W = skip.shape[1:]
+    if (H, W) != (2 * h, 2 * w) or skip.shape[0] != B or skip.dtype != x.dtype:
+        raise EdgelineError("upsample2x_cat: skip must be (B, C2, 2h, 2w) of the same dtype")
+    out = torch.empty((B, C1 + C2, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    check(_lib.lib().el_upsample2x_cat_fwd(x.data_ptr(), _i64(x.stride()), skip.data_ptr(), _i64(skip.stride()), out.data_ptr(),
+                                           _i64(out.stride()), B, C1, C2, H, W, _dt(x), _stream()), "el_upsample2x_cat_fwd")
+    return out

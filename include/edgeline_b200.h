@@ -145,6 +145,20 @@ int el_dfl_bwd(const void* pred, const float* target, int64_t rows, int dtype, c
 int el_ingest_u8(const uint8_t* src, void* dst, const int64_t ds[4], int B, int H, int W, int dtype,
                  void* stream);
 
+/* ---- conv epilogues of the inference engine (the convolutions themselves stay on cuDNN) ---------
+ * el_bias_act_fwd: out = act(x + bias[c]) (+ residual): the BatchNorm-folded bias and SiLU of Conv /
+ * DSConv (nn/modules/conv.py:41-60, 87-104) and the shortcut add of DSBottleneck (block.py:1500-1503)
+ * in one pass.  act: 0 none, 1 SiLU, 2 ReLU; bias (C) fp32 or NULL; residual (same shape) or NULL;
+ * out may alias x and may be a channel slice of a wider (concat) buffer.
+ * el_upsample2x_cat_fwd: out (B,C1+C2,H,W) = cat[nearest2x(x (B,C1,H/2,W/2)), skip (B,C2,H,W)], the
+ * nn.Upsample + Concat pairs of the neck (cfg/models/11/yolo11-test.yaml:34-39); NHWC views only. */
+int el_bias_act_fwd(const void* x, const int64_t xs[4], const float* bias, const void* residual,
+                    const int64_t rs[4], void* out, const int64_t os[4], int B, int C, int H, int W,
+                    int act, int dtype, void* stream);
+int el_upsample2x_cat_fwd(const void* x, const int64_t xs[4], const void* skip, const int64_t ss[4],
+                          void* out, const int64_t os[4], int B, int C1, int C2, int H, int W,
+                          int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

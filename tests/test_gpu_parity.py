@@ -408,3 +408,76 @@ def test_whole_model_vs_cpu_oracle(dtype, cl, tol):
     got = non_max_suppression(y, conf_thres=0.25, iou_thres=0.7)
     for g, w in zip(got, want):
         assert g.cpu().numpy().tobytes() == w.tobytes()
+
+
+# ----------------------------------------------------------------------------- engine path
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-4), (torch.bfloat16, None)])
+def test_engine_fused_graph_matches_module_graph(dtype, tol):
+    """fuse(engine=True) (folded BN, el_bias_act epilogues, concat buffers, fused upsample+cat) is the same function
+    as the plain module graph."""
+    import copy
+
+    from edge_yolo_b200.engine import build_model
+
+    plain = build_model("n", 80, seed=3, dtype=torch.float32, device=DEV, fuse=False)
+    with torch.no_grad():
+        for m in plain.modules():  # non-trivial BatchNorm statistics so that folding is exercised
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.8, 1.2)
+                m.bias.normal_(0, 0.1)
+    fused = copy.deepcopy(plain).fuse(engine=True)
+    plain, fused = plain.to(dtype), fused.to(dtype)
+    x = torch.rand(2, 3, 256, 320, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y0, f0 = plain(x)
+        y1, f1 = fused(x)
+    if tol is None:
+        assert float((y1[:, 4:] - y0[:, 4:]).abs().max()) < 3e-2
+        err = (y1[:, :4] - y0[:, :4]).abs() / (y0[:, :4].abs() + 1.0)
+        assert float(err.median()) < 2e-2
+    else:
+        for a, b in zip(f1, f0):
+            close(a, b, tol, tol)
+        close(y1[:, 4:], y0[:, 4:], tol, 1e-5)
+        close(y1[:, :4], y0[:, :4], tol, 2e-2)
+
+
+def test_epilogue_kernels_vs_torch():
+    gen = torch.Generator().manual_seed(20)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 1e-2)):
+        for shape in ((2, 32, 40, 40), (3, 8, 17, 19), (2, 256, 5, 5)):
+            x = torch.randn(*shape, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+            r = torch.randn(*shape, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+            bias = torch.randn(shape[1], generator=gen).to(DEV)
+            want = torch.nn.functional.silu(x.float() + bias.view(1, -1, 1, 1)) + r.float()
+            wide = torch.zeros(shape[0], shape[1] + 16, *shape[2:], device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
+            got = ops().bias_act(x.clone(), bias, ops().ACT_SILU, residual=r, out=wide[:, 8 : 8 + shape[1]])
+            close(got, want, tol, tol)
+            assert float(wide[:, :8].abs().max()) == 0 and float(wide[:, 8 + shape[1] :].abs().max()) == 0
+            close(ops().bias_act(x.clone(), bias, ops().ACT_NONE), x.float() + bias.view(1, -1, 1, 1), tol, tol)
+            close(ops().bias_act(x.clone(), None, ops().ACT_RELU), x.float().clamp_min(0), tol, tol)
+        lo = torch.randn(2, 16, 6, 7, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+        sk = torch.randn(2, 24, 12, 14, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+        want = torch.cat((torch.nn.functional.interpolate(lo.float(), scale_factor=2, mode="nearest"), sk.float()), 1)
+        close(ops().upsample2x_cat(lo, sk), want, 0, 0)
+
+
+def test_predictor_matches_api_path():
+    """Predictor (graph replay, uint8 ingest) returns exactly what model + non_max_suppression return."""
+    from edge_yolo_b200.engine import Predictor, build_model
+    from edge_yolo_b200.nms import non_max_suppression
+
+    model = build_model("n", 80, seed=0, device=DEV)
+    pred = Predictor(model, batch=2, imgsz=320)
+    host = torch.randint(0, 256, (2, 320, 320, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).pin_memory()
+    dets = pred.predict(host)
+    with torch.no_grad():
+        x = ops().ingest_u8(host.to(DEV))
+        close(x.float(), host.to(DEV).permute(0, 3, 1, 2).float() / 255, 1e-2, 1e-2)
+        y, _ = model(x)
+        want = non_max_suppression(y, conf_thres=0.25, iou_thres=0.7, max_det=300)
+    assert [d.shape[0] for d in dets] == [w.shape[0] for w in want]
+    for d, w in zip(dets, want):
+        assert d.numpy().tobytes() == w.cpu().numpy().tobytes()
