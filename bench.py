@@ -149,6 +149,9 @@ def profile_kernels(pred, a, iters=10):
         "linear_attention": lambda out, qkv, heads: (qkv.numel() + out.numel()) * e(qkv),
         "gfl_decode": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss) + out.numel() * 4,
         "nms_batched": lambda out, y, *r, **k: y.shape[0] * y.shape[2] * (y.shape[1] - 4) * 4 + out[0].numel() * 4,
+        # fused decode + NMS: head maps in, xywh boxes (16 B / anchor) out, rows out
+        "gfl_detect": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss)
+        + sum(t.shape[0] * t.shape[2] * t.shape[3] for t in boxes) * 16 + out[0].numel() * 4,
     }
     saved = {k: getattr(ops, k) for k in shims}
     try:
@@ -182,7 +185,7 @@ def profile_kernels(pred, a, iters=10):
             ts = []
             for it in range(iters // 2 + 1):
                 flush.zero_()
-                torch.cuda._sleep(2_000_000)
+                torch.cuda._sleep(6_000_000)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for aa, kk in sets:

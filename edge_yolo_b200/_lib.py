@@ -36,6 +36,11 @@ _SIGNATURES = {
     "el_gfl_decode_fwd": (c_int, [c_int, POINTER(c_void_p), I64P, POINTER(c_void_p), I64P, POINTER(c_int32), POINTER(c_float),
                                   POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p,
                                   c_int, c_int, c_int, c_void_p]),
+    "el_gfl_detect_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "el_gfl_detect_fwd": (c_int, [c_int, POINTER(c_void_p), I64P, POINTER(c_void_p), I64P, POINTER(c_int32), POINTER(c_float),
+                                  POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int,
+                                  c_float, c_double, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_size_t,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "el_nms_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "el_nms_batched": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_double, c_int, c_int, c_void_p, c_int, c_int, c_float,
                                c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),

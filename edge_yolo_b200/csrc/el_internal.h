@@ -1,0 +1,32 @@
+// Internal (non-ABI) interfaces shared between translation units of libedgeline_b200.so.
+#pragma once
+#include "el_common.cuh"
+
+namespace el {
+
+struct SelectState {            // per image, radix-select state of the max_nms cut
+    unsigned long long prefix;  // high bits of the k-th largest key found so far
+    int k_rem;                  // rank still to resolve inside the current prefix
+    int count2;                 // compacted count
+};
+
+struct NmsLayout {  // offsets into the caller's workspace
+    size_t counts, state, hist, keys, keys2, total;
+    int64_t key_stride, key2_stride;
+    int cap, cap2;
+    bool select;
+};
+NmsLayout nms_layout(int B, int nc, int A, int multi, int max_nms);
+
+// where the sweep reads xywh boxes: component k of anchor a of image b at base[b*sb + a*sa + k*sk]
+struct BoxSource { const float* base; int64_t sb, sa, sk; };
+
+// zero counters / select state (call before emitting keys)
+void nms_prepare(const NmsLayout& L, void* ws, cudaStream_t s);
+// keys + counts are in the workspace: max_nms cut, sort, greedy sweep
+int nms_finish(const NmsLayout& L, void* ws, BoxSource src, int B, int nc, double iou, int agnostic, int max_det, int max_nms, float max_wh,
+               float* out, int32_t* out_count, int64_t* out_index, cudaStream_t s);
+
+constexpr int kMaxDetSmem = 4096;
+
+}  // namespace el

@@ -14,14 +14,13 @@
 //                  n x n/64 mask in HBM.
 // IoU arithmetic replicates torchvision's fp32 sequence with round-to-nearest intrinsics (no FMA
 // contraction) so keep decisions are bit-exact against the CPU op.
-#include "el_common.cuh"
+#include "el_internal.h"
 
 namespace el {
 
 constexpr int kSortChunk = 16384;  // keys sorted per CTA in shared memory (128 KiB)
 constexpr int kSortThreads = 1024;
-constexpr int kSweepThreads = 256;
-constexpr int kMaxDetSmem = 4096;
+constexpr int kSweepThreads = 1024;
 
 __host__ __device__ inline uint32_t pow2ceil(uint32_t v) {
     uint32_t p = 1;
@@ -85,11 +84,6 @@ __global__ void __launch_bounds__(256) nms_box_keys(const float* __restrict__ sc
 }
 
 // ------------------------------------------------------------------------------- 2. select
-struct SelectState {            // per image
-    unsigned long long prefix;  // high bits of the k-th largest key found so far
-    int k_rem;                  // rank still to resolve inside the current prefix
-    int count2;                 // compacted count
-};
 
 __global__ void __launch_bounds__(256) select_hist(const unsigned long long* __restrict__ keys, int64_t key_stride, const int* __restrict__ counts,
                                                    int max_nms, const SelectState* __restrict__ st, unsigned* __restrict__ hist, int shift) {
@@ -248,10 +242,12 @@ __global__ void __launch_bounds__(kSortThreads) sort_chunk_merge(unsigned long l
 // torchvision's IoU test with every fp32 rounding made explicit (no FMA contraction):
 //   inter/(Sa+Sb-inter) > thr ; thr is the double threshold rounded DOWN to float, which makes the
 //   float compare equivalent to torchvision's CPU compare of the float IoU against a double.
+// Disjoint boxes (the common case, also every cross-class pair thanks to the class offset) leave
+// before the division: inter == 0 gives 0/uni = 0 or 0/0 = NaN, neither of which is > thr >= 0.
 __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1, float bx2, float by2, float barea,
                                        float thr) {
-    float left = fmaxf(ax1, bx1), right = fminf(ax2, bx2), top = fmaxf(ay1, by1), bottom = fminf(ay2, by2);
-    float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+    float w = __fsub_rn(fminf(ax2, bx2), fmaxf(ax1, bx1)), h = __fsub_rn(fminf(ay2, by2), fmaxf(ay1, by1));
+    if (!(w > 0.f) || !(h > 0.f)) return false;
     float inter = __fmul_rn(w, h);
     float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
     return __fdiv_rn(inter, uni) > thr;
@@ -260,9 +256,9 @@ __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay
 struct SweepArgs {
     const unsigned long long* keys; int64_t key_stride;
     const int* counts; const SelectState* st; int cap;
-    // FROM_PRED: boxes decoded from pred (B,4+nc,A); else raw boxes (n,4)
-    const float* pred; int nc, A; float max_wh; int agnostic;
-    const float* boxes;
+    // FROM_PRED: component k of anchor a of image b lives at box[b*sb + a*sa + k*sk] (xywh); else raw xyxy boxes (n,4)
+    const float* box; int64_t sb, sa, sk;
+    int nc; float max_wh; int agnostic;
     float thr; int max_det;
     float* out; int32_t* out_count; int64_t* out_index;  // batched outputs
     int64_t* keep;                                       // nms_boxes output
@@ -295,15 +291,15 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
             if (FROM_PRED) {
                 score = __uint_as_float((uint32_t)(k >> 32));
                 uint32_t a = idx / (uint32_t)P.nc, c = idx - a * (uint32_t)P.nc;
-                const float* pb = P.pred + (int64_t)b * (4 + P.nc) * P.A + a;
-                float cx = __ldg(pb), cy = __ldg(pb + P.A), w = __ldg(pb + 2 * (int64_t)P.A), h = __ldg(pb + 3 * (int64_t)P.A);
+                const float* pb = P.box + (int64_t)b * P.sb + (int64_t)a * P.sa;
+                float cx = __ldg(pb), cy = __ldg(pb + P.sk), w = __ldg(pb + 2 * P.sk), h = __ldg(pb + 3 * P.sk);
                 float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);  // xywh2xyxy, ops.py:416-433
                 rx1 = __fsub_rn(cx, hw); ry1 = __fsub_rn(cy, hh); rx2 = __fadd_rn(cx, hw); ry2 = __fadd_rn(cy, hh);
                 clsf = (float)c;
                 float off = P.agnostic ? 0.f : __fmul_rn(clsf, P.max_wh);  // ops.py:289
                 ox1 = __fadd_rn(rx1, off); oy1 = __fadd_rn(ry1, off); ox2 = __fadd_rn(rx2, off); oy2 = __fadd_rn(ry2, off);
             } else {
-                const float4 bx = __ldg(reinterpret_cast<const float4*>(P.boxes) + idx);
+                const float4 bx = __ldg(reinterpret_cast<const float4*>(P.box) + idx);
                 ox1 = bx.x; oy1 = bx.y; ox2 = bx.z; oy2 = bx.w;
             }
             area = __fmul_rn(__fsub_rn(ox2, ox1), __fsub_rn(oy2, oy1));
@@ -354,14 +350,8 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
     if (tid == 0) P.out_count[b] = s_nk[step & 1];
 }
 
-struct NmsLayout {
-    size_t counts, state, hist, keys, keys2, total;
-    int64_t key_stride, key2_stride;
-    int cap, cap2;
-    bool select;
-};
 
-static NmsLayout nms_layout(int B, int nc, int A, int multi, int max_nms) {
+NmsLayout nms_layout(int B, int nc, int A, int multi, int max_nms) {
     NmsLayout L{};
     const int64_t cand = multi ? (int64_t)A * nc : (int64_t)A;
     L.select = cand > max_nms;
@@ -433,31 +423,18 @@ extern "C" int el_nms_workspace_bytes(int B, int nc, int A, int multi_label, int
     return EL_OK;
 }
 
-extern "C" int el_nms_batched(const float* pred, int B, int nc, int A, float conf, double iou, int multi_label, int agnostic, const int32_t* class_keep,
-                              int max_det, int max_nms, float max_wh, void* workspace, size_t workspace_bytes, float* out, int32_t* out_count,
-                              int64_t* out_index, void* stream) {
-    if (!pred || !workspace || !out || !out_count || B <= 0 || nc <= 0 || A <= 0 || max_det <= 0 || max_nms <= 0) return EL_ERR_ARG;
-    if (conf < 0.f || conf > 1.f || iou < 0.0 || iou > 1.0) return EL_ERR_ARG;  // ops.py:217-218
-    if ((int64_t)A * nc >= (int64_t)1 << 31) return EL_ERR_UNSUPPORTED;
-    if (max_det > kMaxDetSmem) return EL_ERR_UNSUPPORTED;
-    const bool multi = multi_label && nc > 1;  // ops.py:239
-    const NmsLayout L = nms_layout(B, nc, A, multi, max_nms);
-    if (workspace_bytes < L.total) return EL_ERR_WORKSPACE;
-    cudaStream_t s = (cudaStream_t)stream;
+namespace el {
+
+void nms_prepare(const NmsLayout& L, void* ws, cudaStream_t s) { cudaMemsetAsync(ws, 0, L.keys, s); }  // counts, select state, histograms
+
+int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc, double iou, int agnostic, int max_det, int max_nms, float max_wh,
+               float* out, int32_t* out_count, int64_t* out_index, cudaStream_t s) {
     char* ws = (char*)workspace;
     int* counts = (int*)(ws + L.counts);
     SelectState* st = (SelectState*)(ws + L.state);
     unsigned* hist = (unsigned*)(ws + L.hist);
     unsigned long long* keys = (unsigned long long*)(ws + L.keys);
     unsigned long long* keys2 = (unsigned long long*)(ws + L.keys2);
-
-    cudaMemsetAsync(ws, 0, L.keys, s);  // counts, select state, histograms
-    dim3 eg((A + 255) / 256, B);
-    if (multi)
-        nms_emit<true><<<eg, 256, 0, s>>>(pred, nc, A, conf, class_keep, keys, L.key_stride, counts);
-    else
-        nms_emit<false><<<eg, 256, 0, s>>>(pred, nc, A, conf, class_keep, keys, L.key_stride, counts);
-
     SweepArgs P{};
     if (L.select) {
         init_select<<<(B + 127) / 128, 128, 0, s>>>(st, B, max_nms);
@@ -475,14 +452,39 @@ extern "C" int el_nms_batched(const float* pred, int B, int nc, int A, float con
         launch_sort(keys, L.key_stride, counts, nullptr, L.cap, B, s);
         P.keys = keys; P.key_stride = L.key_stride; P.counts = counts; P.st = nullptr; P.cap = L.cap;
     }
-    P.pred = pred; P.nc = nc; P.A = A; P.max_wh = max_wh; P.agnostic = agnostic;
+    P.box = src.base; P.sb = src.sb; P.sa = src.sa; P.sk = src.sk;
+    P.nc = nc; P.max_wh = max_wh; P.agnostic = agnostic;
     P.thr = threshold_round_down(iou); P.max_det = max_det;
     P.out = out; P.out_count = out_count; P.out_index = out_index;
     size_t sm = (size_t)5 * max_det * sizeof(float);
     if (sm > 48 * 1024) cudaFuncSetAttribute(nms_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     nms_sweep<true, true><<<B, kSweepThreads, sm, s>>>(P);
-    note_launches(2);  // emit + sweep
+    note_launches(1);
     return check_launch();
+}
+
+}  // namespace el
+
+extern "C" int el_nms_batched(const float* pred, int B, int nc, int A, float conf, double iou, int multi_label, int agnostic, const int32_t* class_keep,
+                              int max_det, int max_nms, float max_wh, void* workspace, size_t workspace_bytes, float* out, int32_t* out_count,
+                              int64_t* out_index, void* stream) {
+    if (!pred || !workspace || !out || !out_count || B <= 0 || nc <= 0 || A <= 0 || max_det <= 0 || max_nms <= 0) return EL_ERR_ARG;
+    if (conf < 0.f || conf > 1.f || iou < 0.0 || iou > 1.0) return EL_ERR_ARG;  // ops.py:217-218
+    if ((int64_t)A * nc >= (int64_t)1 << 31) return EL_ERR_UNSUPPORTED;
+    if (max_det > kMaxDetSmem) return EL_ERR_UNSUPPORTED;
+    const bool multi = multi_label && nc > 1;  // ops.py:239
+    const NmsLayout L = nms_layout(B, nc, A, multi, max_nms);
+    if (workspace_bytes < L.total) return EL_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = (char*)workspace;
+    nms_prepare(L, ws, s);
+    dim3 eg((A + 255) / 256, B);
+    if (multi)
+        nms_emit<true><<<eg, 256, 0, s>>>(pred, nc, A, conf, class_keep, (unsigned long long*)(ws + L.keys), L.key_stride, (int*)(ws + L.counts));
+    else
+        nms_emit<false><<<eg, 256, 0, s>>>(pred, nc, A, conf, class_keep, (unsigned long long*)(ws + L.keys), L.key_stride, (int*)(ws + L.counts));
+    note_launches(1);
+    return nms_finish(L, ws, BoxSource{pred, (int64_t)(4 + nc) * A, 1, A}, B, nc, iou, agnostic, max_det, max_nms, max_wh, out, out_count, out_index, s);
 }
 
 extern "C" int el_nms_boxes_workspace_bytes(int n, size_t* bytes) {
@@ -513,7 +515,7 @@ extern "C" int el_nms_boxes(const float* boxes, const float* scores, int n, doub
     launch_sort(keys, stride, count, nullptr, n, 1, s);
     SweepArgs P{};
     P.keys = keys; P.key_stride = stride; P.counts = count; P.st = nullptr; P.cap = n;
-    P.boxes = boxes; P.thr = threshold_round_down(iou); P.max_det = n;
+    P.box = boxes; P.thr = threshold_round_down(iou); P.max_det = n;
     P.out_count = keep_count; P.keep = keep; P.gkept = gkept;
     nms_sweep<false, false><<<1, kSweepThreads, 0, s>>>(P);
     note_launches(2);  // keys + sweep

@@ -43,7 +43,7 @@ class Predictor:
         self.device, self.dtype = p.device, p.dtype
         for m in model.modules():
             if isinstance(m, GFLHeadv2_uniH):
-                m.el_skip_feats = True  # predict never reads the raw maps
+                m.el_detect = dict(self.nms_kw)  # the head runs the fused decode + NMS kernel chain
         self.u8 = torch.empty((batch, imgsz, imgsz, 3), device=self.device, dtype=torch.uint8)
         self.x = torch.empty((batch, 3, imgsz, imgsz), device=self.device, dtype=self.dtype, memory_format=torch.channels_last)
         self.host_out = torch.empty((batch, max_det, 6), dtype=torch.float32).pin_memory()
@@ -58,8 +58,7 @@ class Predictor:
     def _forward(self, from_u8: bool):
         if from_u8:
             ops.ingest_u8(self.u8, out=self.x)
-        y, _ = self.model(self.x)
-        return ops.nms_batched(y, **self.nms_kw)
+        return self.model(self.x)  # (rows, counts) from the fused detect head
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)

@@ -100,6 +100,9 @@ def gfl_head_forward(self, x):
         return x
     if getattr(self, "export", False) and getattr(self, "format", None) in {"tflite", "edgetpu", "imx", "saved_model", "pb", "tfjs"}:
         raise NotImplementedError("edge_yolo_b200: export formats are out of scope (no multi-backend dispatch)")
+    det = getattr(self, "el_detect", None)
+    if det is not None:  # engine path (Predictor): fused decode + NMS, returns (rows (B, max_det, 6), counts (B))
+        return ops.gfl_detect(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride], **det)
     y = ops.gfl_decode(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride])
     if getattr(self, "export", False):
         return y

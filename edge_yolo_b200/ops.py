@@ -258,6 +258,46 @@ def gfl_decode(boxes, clss, dgqp, strides, want_quality: bool = False):
     return (y, q) if want_quality else y
 
 
+def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, multi_label=False, agnostic=False, classes=None,
+               max_det=300, max_nms=30000, max_wh=7680.0):
+    """Fused decode + NMS of the engine path: same inputs as `gfl_decode`, same outputs as `nms_batched`
+    (out (B, max_det, 6), count (B) int32); the dense (B, 4+nc, A) tensor is never written.  Falls back to
+    `gfl_decode` + `nms_batched` (identical results) when the head maps are not dense NHWC."""
+    nl = len(boxes)
+    _need_cuda(*boxes, *clss)
+    B, nc = boxes[0].shape[0], clss[0].shape[1]
+    hw, bs, cs = [], [], []
+    for bx, cl in zip(boxes, clss):
+        hw += [bx.shape[2], bx.shape[3]]
+        bs += list(bx.stride())
+        cs += list(cl.stride())
+    A = sum(hw[2 * i] * hw[2 * i + 1] for i in range(nl))
+    L = _lib.lib()
+    need = c_size_t()
+    check(L.el_gfl_detect_workspace_bytes(B, nc, A, int(bool(multi_label)), int(max_nms), ctypes.byref(need)), "el_gfl_detect_workspace_bytes")
+    dev = boxes[0].device
+    ws = torch.empty(need.value, device=dev, dtype=torch.uint8)
+    out = torch.empty((B, max_det, 6), device=dev, dtype=torch.float32)
+    cnt = torch.empty((B,), device=dev, dtype=torch.int32)
+    keep = None
+    if classes is not None:
+        keep = torch.zeros(nc, dtype=torch.int32)
+        keep[torch.as_tensor(classes, dtype=torch.long)] = 1
+        keep = keep.to(dev)
+    cols = [_ptrs([w[k] for w in dgqp]) for k in range(4)]
+    st = L.el_gfl_detect_fwd(nl, _ptrs(boxes), _i64(bs), _ptrs(clss), _i64(cs), (c_int32 * len(hw))(*hw),
+                             (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3], B, nc, _dt(boxes[0]),
+                             float(conf_thres), float(iou_thres), int(bool(multi_label)), int(bool(agnostic)),
+                             keep.data_ptr() if keep is not None else None, int(max_det), int(max_nms), float(max_wh), ws.data_ptr(),
+                             need.value, out.data_ptr(), cnt.data_ptr(), None, _stream())
+    if st == 2:  # EL_ERR_UNSUPPORTED: strided / NCHW maps -> two-call path with the same kernels downstream
+        y = gfl_decode(boxes, clss, dgqp, strides)
+        return nms_batched(y, conf_thres, iou_thres, multi_label=multi_label, agnostic=agnostic, classes=classes, max_det=max_det,
+                           max_nms=max_nms, max_wh=max_wh)
+    check(st, "el_gfl_detect_fwd")
+    return out, cnt
+
+
 # ------------------------------------------------------------------------------------ NMS
 def nms_batched(pred: torch.Tensor, conf_thres=0.25, iou_thres=0.45, multi_label=False, agnostic=False, classes=None,
                 max_det=300, max_nms=30000, max_wh=7680.0, want_index=False):

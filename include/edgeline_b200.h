@@ -101,6 +101,21 @@ int el_gfl_decode_fwd(int nl, const void* const* box, const int64_t* box_s, cons
                       const float* const* b2, float* y, float* q_out, int B, int nc, int dtype,
                       void* stream);
 
+/* ---- a6+a7+a9 fused (engine path): decode -> NMS candidates -> sort -> sweep, no dense score tensor --
+ * Same inputs as el_gfl_decode_fwd plus the NMS arguments of el_nms_batched.  Persistent CTAs stage
+ * 64-anchor tiles of the NHWC head outputs with bulk TMA copies, decode them in shared memory and write
+ * only the xywh boxes (B,A,4) and the candidate keys; results are bit-identical to
+ * el_gfl_decode_fwd + el_nms_batched.  Returns EL_ERR_UNSUPPORTED when the maps are not dense NHWC with
+ * 16-byte-aligned tile rows (callers then use the two-call path). */
+int el_gfl_detect_workspace_bytes(int B, int nc, int A, int multi_label, int max_nms, size_t* bytes);
+int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* box_s, const void* const* cls,
+                      const int64_t* cls_s, const int32_t* hw, const float* stride,
+                      const float* const* w1, const float* const* b1, const float* const* w2,
+                      const float* const* b2, int B, int nc, int dtype, float conf_thres,
+                      double iou_thres, int multi_label, int agnostic, const int32_t* class_keep,
+                      int max_det, int max_nms, float max_wh, void* workspace, size_t workspace_bytes,
+                      float* out, int32_t* out_count, int64_t* out_index, void* stream);
+
 /* ---- a9. batched NMS: non_max_suppression, utils/ops.py:167-316 (detection, nm=0) ------------
  * pred (B,4+nc,A) fp32 contiguous, xywh + scores (the tensor el_gfl_decode_fwd writes).
  * Candidate build (conf filter, multi-label expansion or first-max class, optional class

@@ -473,6 +473,9 @@ def test_predictor_matches_api_path():
     pred = Predictor(model, batch=2, imgsz=320)
     host = torch.randint(0, 256, (2, 320, 320, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).pin_memory()
     dets = pred.predict(host)
+    for m in model.modules():  # back to the API behaviour of the head: dense y
+        if hasattr(m, "el_detect"):
+            m.el_detect = None
     with torch.no_grad():
         x = ops().ingest_u8(host.to(DEV))
         close(x.float(), host.to(DEV).permute(0, 3, 1, 2).float() / 255, 1e-2, 1e-2)
@@ -481,3 +484,35 @@ def test_predictor_matches_api_path():
     assert [d.shape[0] for d in dets] == [w.shape[0] for w in want]
     for d, w in zip(dets, want):
         assert d.numpy().tobytes() == w.cpu().numpy().tobytes()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("nc,sizes,kw", [
+    (80, ((80, 80), (40, 40), (20, 20)), dict(conf_thres=0.25, iou_thres=0.7)),
+    (80, ((80, 80), (40, 40), (20, 20)), dict(conf_thres=0.6, iou_thres=0.7, multi_label=True)),
+    (10, ((160, 160), (80, 80), (40, 40)), dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)),   # BASELINE config 3 shape: max_nms cut
+    (80, ((80, 80), (40, 40), (20, 20)), dict(conf_thres=0.25, iou_thres=0.5, classes=[3, 17, 60], agnostic=True)),
+    (12, ((24, 40), (12, 20), (6, 10)), dict(conf_thres=0.3, iou_thres=0.6)),                            # ragged last tiles
+])
+def test_fused_detect_equals_decode_then_nms(dtype, nc, sizes, kw):
+    """Engine path (bulk-TMA staged decode that emits NMS candidates directly) == API path (dense y, then NMS), bit for bit."""
+    gen = torch.Generator().manual_seed(30)
+    B = 3
+    cl = torch.channels_last
+    boxes = [(torch.randn(B, 64, h, w, generator=gen) * 2).to(DEV).to(dtype).contiguous(memory_format=cl) for h, w in sizes]
+    clss = [(torch.randn(B, nc, h, w, generator=gen) * 2).to(DEV).to(dtype).contiguous(memory_format=cl) for h, w in sizes]
+    ws = [tuple(t.to(DEV) for t in (torch.randn(64 * 20, generator=gen), torch.randn(64, generator=gen), torch.randn(64, generator=gen) * 0.3,
+                                    torch.randn(1, generator=gen))) for _ in sizes]
+    st = [8.0, 16.0, 32.0]
+    o = ops()
+    y = o.gfl_decode(boxes, clss, ws, st)
+    want, wcnt = o.nms_batched(y, **kw)
+    got, gcnt = o.gfl_detect(boxes, clss, ws, st, **kw)
+    assert gcnt.cpu().tolist() == wcnt.cpu().tolist()
+    for b in range(B):
+        n = int(wcnt[b])
+        assert got[b, :n].cpu().numpy().tobytes() == want[b, :n].cpu().numpy().tobytes()
+    # and the API path itself against the CPU oracle on the same dense tensor
+    ref, _ = O.non_max_suppression(y.cpu().numpy(), **kw)
+    for b in range(B):
+        assert want[b, : int(wcnt[b])].cpu().numpy().tobytes() == ref[b].tobytes()
