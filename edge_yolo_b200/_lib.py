@@ -31,15 +31,16 @@ _SIGNATURES = {
     "el_wave_merge_fwd": (c_int, [c_void_p, I64P, POINTER(c_void_p), I64P, c_void_p, c_void_p, I64P] + [c_int] * 7 + [c_void_p]),
     "el_wave_merge_bwd": (c_int, [c_void_p, I64P, POINTER(c_void_p), I64P, c_void_p, c_void_p, I64P, POINTER(c_void_p), I64P, c_void_p]
                           + [c_int] * 7 + [c_void_p]),
-    "el_gated_residual_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "el_gated_residual_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_void_p, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p]),
     "el_linattn_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_void_p]),
     "el_gfl_decode_fwd": (c_int, [c_int, POINTER(c_void_p), I64P, POINTER(c_void_p), I64P, POINTER(c_int32), POINTER(c_float),
-                                  POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p,
-                                  c_int, c_int, c_int, c_void_p]),
+                                  POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                  POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "el_gfl_detect_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "el_gfl_detect_fwd": (c_int, [c_int, POINTER(c_void_p), I64P, POINTER(c_void_p), I64P, POINTER(c_int32), POINTER(c_float),
-                                  POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int,
-                                  c_float, c_double, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_size_t,
+                                  POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                  POINTER(c_void_p), c_int, c_int, c_int, c_float, c_double, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_size_t,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "el_nms_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "el_nms_batched": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_double, c_int, c_int, c_void_p, c_int, c_int, c_float,
@@ -52,7 +53,8 @@ _SIGNATURES = {
     "el_dfl_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "el_dfl_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "el_ingest_u8": (c_int, [c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_void_p]),
-    "el_bias_act_fwd": (c_int, [c_void_p, I64P, c_void_p, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "el_bias_act_fwd": (c_int, [c_void_p, I64P, c_void_p, c_void_p, I64P, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_void_p]),
     "el_upsample2x_cat_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -29,6 +29,7 @@ struct DecodeLevel {
     const void* box; Strides4 bs;
     const void* cls; Strides4 cs;
     const float *w1, *b1, *w2, *b2;
+    const float *bb, *cb;  // optional biases of the final 1x1 convs of the box / class towers (folded in here), may be NULL
     int H, W, a_off, tile_off;
     float stride;
 };
@@ -159,6 +160,10 @@ __global__ void __launch_bounds__(256) gfl_decode_kernel(const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < kRegMax; ++k) lg[k] = to_f(p[(int64_t)(side * kRegMax + k) * L.bs.c]);
             }
+            if (L.bb) {
+#pragma unroll
+                for (int k = 0; k < kRegMax; ++k) lg[k] += __ldg(L.bb + side * kRegMax + k);
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < kRegMax; ++k) lg[k] = 0.f;
@@ -210,6 +215,7 @@ __global__ void __launch_bounds__(256) gfl_decode_kernel(const __grid_constant__
                 int py = pix / L.W, px = pix - py * L.W;
                 v = to_f(reinterpret_cast<const T*>(L.cls)[(int64_t)b * L.cs.n + (int64_t)c * L.cs.c + (int64_t)py * L.cs.h + (int64_t)px * L.cs.w]);
             }
+            if (L.cb) v += __ldg(L.cb + c);
             o[(int64_t)c * P.A + a] = sigmoidf_(v) * s_q[a];
         }
     }
@@ -282,9 +288,15 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
     float (*s_dist)[kTile] = (float (*)[kTile])cur; cur += 4 * kTile * 4;
     float (*s_part)[kTile] = (float (*)[kTile])cur; cur += 8 * kTile * 4;
     float* s_q = (float*)cur; cur += kTile * 4;
+    const int bias_ld = (4 * kRegMax + nc + 3) & ~3;
+    float* s_bias = (float*)cur; cur += kMaxLevels * bias_ld * 4;  // per level: box bias (64) | class bias (nc)
     uint64_t* bar = (uint64_t*)cur;
 
-    for (int l = 0; l < P.nl; ++l) load_level_weights(s_w + l * kWStride, P.lv[l]);
+    for (int l = 0; l < P.nl; ++l) {
+        load_level_weights(s_w + l * kWStride, P.lv[l]);
+        for (int i = tid; i < 4 * kRegMax + nc; i += 256)
+            s_bias[l * bias_ld + i] = i < 4 * kRegMax ? (P.lv[l].bb ? __ldg(P.lv[l].bb + i) : 0.f) : (P.lv[l].cb ? __ldg(P.lv[l].cb + i - 4 * kRegMax) : 0.f);
+    }
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -315,6 +327,8 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
         const TileInfo ti = tile_info(P, t);
         const DecodeLevel& L = P.lv[ti.l];
         const float* w = s_w + ti.l * kWStride;
+        const float* bias_b = s_bias + ti.l * bias_ld;
+        const float* bias_c = bias_b + 4 * kRegMax;
         mbar_wait(&bar[stage], (it >> 1) & 1);
 
         {   // phase 1: thread = (anchor a, side): 16 logits from the staged tile
@@ -337,10 +351,8 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                     for (int k = 0; k < 4; ++k) lg[4 * v + k] = f[k];
                 }
             }
-            if (a >= ti.nvalid) {
 #pragma unroll
-                for (int k = 0; k < kRegMax; ++k) lg[k] = 0.f;
-            }
+            for (int k = 0; k < kRegMax; ++k) lg[k] = a < ti.nvalid ? lg[k] + bias_b[side * kRegMax + k] : 0.f;
             float dist;
             side_stats(lg, dist, &s_stat[a][side * 5]);
             s_dist[side][a] = dist;
@@ -370,7 +382,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                     float sc = 0.f;
                     bool pass = false;
                     if (av && c < nc) {
-                        sc = sigmoidf_(to_f(pc[c])) * q;
+                        sc = sigmoidf_(to_f(pc[c]) + bias_c[c]) * q;
                         pass = sc > E.conf && (!E.class_keep || E.class_keep[c]);
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -390,7 +402,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                 if (av) {
                     const int c1 = min(nc, (qd + 1) * cq);
                     for (int c = qd * cq; c < c1; ++c) {  // first maximum inside the quarter
-                        const float sc = sigmoidf_(to_f(pc[c])) * q;
+                        const float sc = sigmoidf_(to_f(pc[c]) + bias_c[c]) * q;
                         if (sc > best) { best = sc; bc = c; }
                     }
                 }
@@ -424,11 +436,14 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
 static size_t emit_smem_bytes(int nc, size_t esz) {
     const size_t box_bytes = (size_t)kTile * 4 * kRegMax * esz;
     const size_t cls_bytes = ((size_t)kTile * nc * esz + 127) & ~(size_t)127;
-    return 2 * box_bytes + 2 * cls_bytes + (size_t)kMaxLevels * kWStride * 4 + kTile * kStatLd * 4 + 4 * kTile * 4 + 8 * kTile * 4 + kTile * 4 + 16;
+    const size_t bias_ld = (4 * kRegMax + nc + 3) & ~3;
+    return 2 * box_bytes + 2 * cls_bytes + (size_t)kMaxLevels * kWStride * 4 + kTile * kStatLd * 4 + 4 * kTile * 4 + 8 * kTile * 4 + kTile * 4 +
+           kMaxLevels * bias_ld * 4 + 16;
 }
 
 static int fill_params(DecodeParams& P, int nl, const void* const* box, const int64_t* box_s, const void* const* cls, const int64_t* cls_s, const int32_t* hw,
-                       const float* stride, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2, int nc) {
+                       const float* stride, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2,
+                       const float* const* box_bias, const float* const* cls_bias, int nc) {
     P.nl = nl; P.nc = nc;
     int a_off = 0, tile_off = 0;
     for (int l = 0; l < nl; ++l) {
@@ -437,6 +452,8 @@ static int fill_params(DecodeParams& P, int nl, const void* const* box, const in
         L.box = box[l]; L.bs = s4(box_s + 4 * l);
         L.cls = cls[l]; L.cs = s4(cls_s + 4 * l);
         L.w1 = w1[l]; L.b1 = b1[l]; L.w2 = w2[l]; L.b2 = b2[l];
+        L.bb = box_bias ? box_bias[l] : nullptr;
+        L.cb = cls_bias ? cls_bias[l] : nullptr;
         L.H = hw[2 * l]; L.W = hw[2 * l + 1];
         L.stride = stride[l];
         L.a_off = a_off; L.tile_off = tile_off;
@@ -470,11 +487,12 @@ using namespace el;
 
 extern "C" int el_gfl_decode_fwd(int nl, const void* const* box, const int64_t* box_s, const void* const* cls, const int64_t* cls_s,
                                  const int32_t* hw, const float* stride, const float* const* w1, const float* const* b1, const float* const* w2,
-                                 const float* const* b2, float* y, float* q_out, int B, int nc, int dtype, void* stream) {
+                                 const float* const* b2, const float* const* box_bias, const float* const* cls_bias, float* y, float* q_out, int B,
+                                 int nc, int dtype, void* stream) {
     if (nl <= 0 || nl > kMaxLevels || !box || !cls || !box_s || !cls_s || !hw || !stride || !w1 || !b1 || !w2 || !b2 || !y || B <= 0 || nc <= 0)
         return EL_ERR_ARG;
     DecodeParams P;
-    if (int e = fill_params(P, nl, box, box_s, cls, cls_s, hw, stride, w1, b1, w2, b2, nc)) return e;
+    if (int e = fill_params(P, nl, box, box_s, cls, cls_s, hw, stride, w1, b1, w2, b2, box_bias, cls_bias, nc)) return e;
     bool box_fast = true, cls_fast = true;
     for (int l = 0; l < nl; ++l) {
         const DecodeLevel& L = P.lv[l];
@@ -515,7 +533,7 @@ extern "C" int el_gfl_detect_workspace_bytes(int B, int nc, int A, int multi_lab
 
 extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* box_s, const void* const* cls, const int64_t* cls_s, const int32_t* hw,
                                  const float* stride, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2,
-                                 int B, int nc, int dtype, float conf, double iou, int multi_label, int agnostic, const int32_t* class_keep,
+                                 const float* const* box_bias, const float* const* cls_bias, int B, int nc, int dtype, float conf, double iou, int multi_label, int agnostic, const int32_t* class_keep,
                                  int max_det, int max_nms, float max_wh, void* workspace, size_t workspace_bytes, float* out, int32_t* out_count,
                                  int64_t* out_index, void* stream) {
     if (nl <= 0 || nl > kMaxLevels || !box || !cls || !box_s || !cls_s || !hw || !stride || !w1 || !b1 || !w2 || !b2 || B <= 0 || nc <= 0 ||
@@ -524,7 +542,7 @@ extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* 
     if (conf < 0.f || conf > 1.f || iou < 0.0 || iou > 1.0) return EL_ERR_ARG;
     if (max_det > kMaxDetSmem) return EL_ERR_UNSUPPORTED;
     DecodeParams P;
-    if (int e = fill_params(P, nl, box, box_s, cls, cls_s, hw, stride, w1, b1, w2, b2, nc)) return e;
+    if (int e = fill_params(P, nl, box, box_s, cls, cls_s, hw, stride, w1, b1, w2, b2, box_bias, cls_bias, nc)) return e;
     if ((int64_t)P.A * nc >= (int64_t)1 << 31) return EL_ERR_UNSUPPORTED;
     const size_t esz = dtype == EL_F32 ? 4 : 2;
     if (!emit_supported(P, esz)) return EL_ERR_UNSUPPORTED;  // caller falls back to el_gfl_decode_fwd + el_nms_batched

@@ -20,7 +20,7 @@ constexpr int kEpRows = 4;
 // thread <-> (channel vector, column) fixed; walks kEpRows rows.  grid = (col tiles, row chunks, images)
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bias_act_tiled(const T* x, Strides4 xs, const float* __restrict__ bias, const T* res, Strides4 rs, T* o,
-                                                      Strides4 os, int CV, int cols_per_block, int H, int W) {
+                                                      Strides4 os, T* o2, Strides4 os2, int split_cv, int CV, int cols_per_block, int H, int W) {
     constexpr int V = Vec16<T>::N;
     const int xi = (int)threadIdx.x / CV, cv = (int)threadIdx.x - xi * CV, col = (int)blockIdx.x * cols_per_block + xi;
     if (xi >= cols_per_block || col >= W) return;
@@ -31,6 +31,11 @@ __global__ void __launch_bounds__(256) bias_act_tiled(const T* x, Strides4 xs, c
     const int64_t n = blockIdx.z;
     const T* p = x + n * xs.n + (int64_t)r0 * xs.h + (int64_t)col * xs.w + cv * V;
     T* q = o + n * os.n + (int64_t)r0 * os.h + (int64_t)col * os.w + cv * V;
+    int64_t qh = os.h;
+    if (o2 && cv >= split_cv) {  // channels >= split go to the second destination (e.g. a dense tensor next to a concat slice)
+        q = o2 + n * os2.n + (int64_t)r0 * os2.h + (int64_t)col * os2.w + (cv - split_cv) * V;
+        qh = os2.h;
+    }
     const T* pr = res ? res + n * rs.n + (int64_t)r0 * rs.h + (int64_t)col * rs.w + cv * V : nullptr;
 #pragma unroll
     for (int r = 0; r < kEpRows; ++r) {
@@ -48,14 +53,14 @@ __global__ void __launch_bounds__(256) bias_act_tiled(const T* x, Strides4 xs, c
 #pragma unroll
             for (int e = 0; e < V; ++e) f[e] += g[e];
         }
-        *reinterpret_cast<uint4*>(q + (int64_t)r * os.h) = pack<T>(f);
+        *reinterpret_cast<uint4*>(q + (int64_t)r * qh) = pack<T>(f);
     }
 }
 
 // flat variant for small feature maps / very wide channel counts: one vector per thread, grid-stride
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bias_act_flat(const T* x, Strides4 xs, const float* __restrict__ bias, const T* res, Strides4 rs, T* o, Strides4 os,
-                                                     int CV, int H, int W, uint32_t total) {
+                                                     T* o2, Strides4 os2, int split_cv, int CV, int H, int W, uint32_t total) {
     constexpr int V = Vec16<T>::N;
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         uint32_t cv = idx % (uint32_t)CV, t = idx / (uint32_t)CV;
@@ -74,13 +79,16 @@ __global__ void __launch_bounds__(256) bias_act_flat(const T* x, Strides4 xs, co
 #pragma unroll
             for (int e = 0; e < V; ++e) f[e] += g[e];
         }
-        *reinterpret_cast<uint4*>(o + (int64_t)n * os.n + (int64_t)row * os.h + (int64_t)col * os.w + cv * V) = pack<T>(f);
+        if (o2 && (int)cv >= split_cv)
+            *reinterpret_cast<uint4*>(o2 + (int64_t)n * os2.n + (int64_t)row * os2.h + (int64_t)col * os2.w + ((int)cv - split_cv) * V) = pack<T>(f);
+        else
+            *reinterpret_cast<uint4*>(o + (int64_t)n * os.n + (int64_t)row * os.h + (int64_t)col * os.w + cv * V) = pack<T>(f);
     }
 }
 
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bias_act_generic(const T* x, Strides4 xs, const float* __restrict__ bias, const T* res, Strides4 rs, T* o, Strides4 os,
-                                                        int C, int H, int W, int64_t total, bool ch_fast) {
+                                                        T* o2, Strides4 os2, int split, int C, int H, int W, int64_t total, bool ch_fast) {
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         int64_t t = idx, n; int c, row, col;
         if (ch_fast) { c = (int)(t % C); t /= C; col = (int)(t % W); t /= W; row = (int)(t % H); n = t / H; }
@@ -88,7 +96,8 @@ __global__ void __launch_bounds__(256) bias_act_generic(const T* x, Strides4 xs,
         float v = to_f(x[n * xs.n + (int64_t)c * xs.c + (int64_t)row * xs.h + (int64_t)col * xs.w]) + (bias ? __ldg(bias + c) : 0.f);
         v = ACT == 1 ? silu_f<T>(v) : (ACT == 2 ? fmaxf(v, 0.f) : v);
         if (res) v += to_f(res[n * rs.n + (int64_t)c * rs.c + (int64_t)row * rs.h + (int64_t)col * rs.w]);
-        o[n * os.n + (int64_t)c * os.c + (int64_t)row * os.h + (int64_t)col * os.w] = from_f<T>(v);
+        if (o2 && c >= split) o2[n * os2.n + (int64_t)(c - split) * os2.c + (int64_t)row * os2.h + (int64_t)col * os2.w] = from_f<T>(v);
+        else o[n * os.n + (int64_t)c * os.c + (int64_t)row * os.h + (int64_t)col * os.w] = from_f<T>(v);
     }
 }
 
@@ -111,15 +120,90 @@ __global__ void __launch_bounds__(256) upsample2x_cat_tiled(const T* __restrict_
     }
 }
 
+
+// SPPF pooling pyramid (nn/modules/block.py:204-223): out = cat[x, m(x), m(m(x)), m(m(m(x)))] with m = MaxPool2d(5, 1, 2).
+// Chained 5x5 max-pools with -inf padding are exactly the clipped 5x5 / 9x9 / 13x13 window maxima, and max is separable,
+// so one CTA per (image, channel vector) stages the map in shared memory, does the three row passes, then the three column
+// passes, and writes all four concat slices.
+template <typename T> __device__ __forceinline__ uint4 vmax16(uint4 a, uint4 b);
+template <> __device__ __forceinline__ uint4 vmax16<float>(uint4 a, uint4 b) {
+    return make_uint4(__float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x))), __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y))),
+                      __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z))), __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w))));
+}
+template <> __device__ __forceinline__ uint4 vmax16<__nv_bfloat16>(uint4 a, uint4 b) {
+    uint4 r;
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+    return r;
+}
+template <> __device__ __forceinline__ uint4 vmax16<__half>(uint4 a, uint4 b) {
+    uint4 r;
+    const __half2* pa = reinterpret_cast<const __half2*>(&a);
+    const __half2* pb = reinterpret_cast<const __half2*>(&b);
+    __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sppf_pool_kernel(const T* __restrict__ x, Strides4 xs, T* __restrict__ o, Strides4 os, int C, int H, int W) {
+    constexpr int V = Vec16<T>::N;
+    extern __shared__ uint4 s_tiles[];  // [4][H*W]: input, row-max r=2, r=4, r=6
+    const int HW = H * W, cv = blockIdx.x;
+    const int64_t n = blockIdx.y;
+    uint4* s_in = s_tiles;
+    uint4* s_h[3] = {s_tiles + HW, s_tiles + 2 * HW, s_tiles + 3 * HW};
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+        const int yy = p / W, xx = p - yy * W;
+        s_in[p] = ldg_stream(x + n * xs.n + (int64_t)yy * xs.h + (int64_t)xx * xs.w + cv * V);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {  // row pass: windows |dx| <= 2, 4, 6 (nested)
+        const int yy = p / W, xx = p - yy * W;
+        uint4 m = s_in[p];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int d = 2 * r + 1; d <= 2 * r + 2; ++d) {
+                if (xx - d >= 0) m = vmax16<T>(m, s_in[p - d]);
+                if (xx + d < W) m = vmax16<T>(m, s_in[p + d]);
+            }
+            s_h[r][p] = m;
+        }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {  // column pass on the matching row-max tile
+        const int yy = p / W, xx = p - yy * W;
+        T* q = o + n * os.n + (int64_t)yy * os.h + (int64_t)xx * os.w + cv * V;
+        *reinterpret_cast<uint4*>(q) = s_in[p];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            uint4 m = s_h[r][p];
+            for (int d = 1; d <= 2 * r + 2; ++d) {
+                if (yy - d >= 0) m = vmax16<T>(m, s_h[r][p - d * W]);
+                if (yy + d < H) m = vmax16<T>(m, s_h[r][p + d * W]);
+            }
+            *reinterpret_cast<uint4*>(q + (int64_t)(r + 1) * C) = m;
+        }
+    }
+}
+
 }  // namespace el
 
 using namespace el;
 
 extern "C" int el_bias_act_fwd(const void* x, const int64_t xs_[4], const float* bias, const void* residual, const int64_t rs_[4], void* out,
-                               const int64_t os_[4], int B, int C, int H, int W, int act, int dtype, void* stream) {
+                               const int64_t os_[4], void* out2, const int64_t os2_[4], int split, int B, int C, int H, int W, int act, int dtype,
+                               void* stream) {
     if (!x || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0 || act < 0 || act > 2 || (residual && !rs_)) return EL_ERR_ARG;
+    if (out2 && (!os2_ || split <= 0 || split >= C)) return EL_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    Strides4 xs = s4(xs_), os = s4(os_), rs = residual ? s4(rs_) : Strides4{0, 0, 0, 0};
+    Strides4 xs = s4(xs_), os = s4(os_), rs = residual ? s4(rs_) : Strides4{0, 0, 0, 0}, os2 = out2 ? s4(os2_) : Strides4{0, 0, 0, 0};
+    const int C1 = out2 ? split : C;  // channels landing in `out`
 #define EL_BIAS_ACT(KERNEL, ...)                                                           \
     do {                                                                                   \
         if (act == 1) KERNEL<T, 1> __VA_ARGS__;                                            \
@@ -128,23 +212,24 @@ extern "C" int el_bias_act_fwd(const void* x, const int64_t xs_[4], const float*
     } while (0)
     EL_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec16<T>::N;
-        if (channel_vectorisable<T>(x, xs, C) && channel_vectorisable<T>(out, os, C) && (!residual || channel_vectorisable<T>(residual, rs, C))) {
+        if (channel_vectorisable<T>(x, xs, C) && channel_vectorisable<T>(out, os, C1) && (!residual || channel_vectorisable<T>(residual, rs, C)) &&
+            (!out2 || channel_vectorisable<T>(out2, os2, C - split))) {
             const int CV = C / V;
             const int64_t total = (int64_t)B * H * W * CV;
-            if (CV <= 256 && W >= 2 * (256 / CV) && B <= 65535) {
-                const int cpb = 256 / CV;
+            if (CV <= 256 && B <= 65535) {
+                    const int cpb = 256 / CV < W ? 256 / CV : W;
                 dim3 g((unsigned)ceil_div(W, cpb), (unsigned)ceil_div(H, kEpRows), (unsigned)B);
-                EL_BIAS_ACT(bias_act_tiled, <<<g, 256, 0, st>>>((const T*)x, xs, bias, (const T*)residual, rs, (T*)out, os, CV, cpb, H, W));
+                EL_BIAS_ACT(bias_act_tiled, <<<g, 256, 0, st>>>((const T*)x, xs, bias, (const T*)residual, rs, (T*)out, os, (T*)out2, os2, split / V, CV, cpb, H, W));
             } else if (total < ((int64_t)1 << 32)) {
                 int grid = (int)(ceil_div(total, 256) < (int64_t)kSMs * 16 ? ceil_div(total, 256) : (int64_t)kSMs * 16);
-                EL_BIAS_ACT(bias_act_flat, <<<grid, 256, 0, st>>>((const T*)x, xs, bias, (const T*)residual, rs, (T*)out, os, CV, H, W, (uint32_t)total));
+                EL_BIAS_ACT(bias_act_flat, <<<grid, 256, 0, st>>>((const T*)x, xs, bias, (const T*)residual, rs, (T*)out, os, (T*)out2, os2, split / V, CV, H, W, (uint32_t)total));
             } else {
                 return EL_ERR_UNSUPPORTED;
             }
         } else {
             const int64_t total = (int64_t)B * C * H * W;
             int grid = (int)(ceil_div(total, 256) < (int64_t)kSMs * 16 ? ceil_div(total, 256) : (int64_t)kSMs * 16);
-            EL_BIAS_ACT(bias_act_generic, <<<grid, 256, 0, st>>>((const T*)x, xs, bias, (const T*)residual, rs, (T*)out, os, C, H, W, total, os.c == 1));
+            EL_BIAS_ACT(bias_act_generic, <<<grid, 256, 0, st>>>((const T*)x, xs, bias, (const T*)residual, rs, (T*)out, os, (T*)out2, os2, split, C, H, W, total, os.c == 1));
         }
     });
 #undef EL_BIAS_ACT
@@ -165,6 +250,22 @@ extern "C" int el_upsample2x_cat_fwd(const void* x, const int64_t xs_[4], const 
         const int CV = (C1 + C2) / V, cpb = 256 / CV;
         dim3 g((unsigned)ceil_div(W, cpb), (unsigned)ceil_div(H, kEpRows), (unsigned)B);
         upsample2x_cat_tiled<T><<<g, 256, 0, st>>>((const T*)x, xs, (const T*)skip, ss, (T*)out, os, C1 / V, CV, cpb, H, W);
+    });
+    note_launches(1);
+    return check_launch();
+}
+
+extern "C" int el_sppf_pool_fwd(const void* x, const int64_t xs_[4], void* out, const int64_t os_[4], int B, int C, int H, int W, int dtype, void* stream) {
+    if (!x || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return EL_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Strides4 xs = s4(xs_), os = s4(os_);
+    const size_t sm = (size_t)4 * H * W * sizeof(uint4);
+    if (sm > 200 * 1024 || B > 65535) return EL_ERR_UNSUPPORTED;  // maps above ~56x56: callers keep nn.MaxPool2d
+    EL_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec16<T>::N;
+        if (!(channel_vectorisable<T>(x, xs, C) && channel_vectorisable<T>(out, os, 4 * C))) return EL_ERR_UNSUPPORTED;
+        if (sm > 48 * 1024) cudaFuncSetAttribute(sppf_pool_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        sppf_pool_kernel<T><<<dim3(C / V, B), 256, sm, st>>>((const T*)x, xs, (T*)out, os, C, H, W);
     });
     note_launches(1);
     return check_launch();

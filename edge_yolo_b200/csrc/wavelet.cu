@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256) merge_fwd_tiled(const T* __restrict__ b, 
 
 template <typename T>
 __global__ void __launch_bounds__(256) gated_tiled(const T* b, Strides4 bs, const T* __restrict__ y, Strides4 ys, const float* __restrict__ gamma, T* o,
-                                                   Strides4 os, int CV, int cols_per_block, int H, int W) {
+                                                   Strides4 os, T* o2, Strides4 os2, int CV, int cols_per_block, int H, int W) {
     constexpr int V = Vec16<T>::N;
     const TileMap m = tile_map(CV, cols_per_block, W);
     if (!m.active) return;
@@ -477,6 +477,7 @@ __global__ void __launch_bounds__(256) gated_tiled(const T* b, Strides4 bs, cons
     const T* pb = b + n * bs.n + (int64_t)r0 * bs.h + (int64_t)m.col * bs.w + m.cv * V;
     const T* py = y + n * ys.n + (int64_t)r0 * ys.h + (int64_t)m.col * ys.w + m.cv * V;
     T* po = o + n * os.n + (int64_t)r0 * os.h + (int64_t)m.col * os.w + m.cv * V;
+    T* po2 = o2 ? o2 + n * os2.n + (int64_t)r0 * os2.h + (int64_t)m.col * os2.w + m.cv * V : nullptr;
 #pragma unroll 4
     for (int r = r0; r < r1; ++r, pb += bs.h, py += ys.h, po += os.h) {
         float fb[V], fy[V], res[V];
@@ -484,7 +485,9 @@ __global__ void __launch_bounds__(256) gated_tiled(const T* b, Strides4 bs, cons
         unpack<T>(ldg_stream(py), fy);
 #pragma unroll
         for (int e = 0; e < V; ++e) res[e] = fb[e] + g * fy[e];
-        *reinterpret_cast<uint4*>(po) = pack<T>(res);
+        const uint4 pk = pack<T>(res);
+        *reinterpret_cast<uint4*>(po) = pk;
+        if (po2) { *reinterpret_cast<uint4*>(po2) = pk; po2 += os2.h; }  // second copy, e.g. the block's concat slice
     }
 }
 
@@ -637,17 +640,20 @@ extern "C" int el_wave_merge_bwd(const void* gout, const int64_t gos_[4], const 
 }
 
 extern "C" int el_gated_residual_fwd(const void* b, const int64_t bs_[4], const void* y, const int64_t ys_[4], const float* gamma, void* out,
-                                     const int64_t os_[4], int B, int C, int H, int W, int dtype, void* stream) {
-    if (!b || !y || !gamma || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return EL_ERR_ARG;
+                                     const int64_t os_[4], void* out2, const int64_t os2_[4], int B, int C, int H, int W, int dtype, void* stream) {
+    if (!b || !y || !gamma || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0 || (out2 && !os2_)) return EL_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    Strides4 bs = s4(bs_), ys = s4(ys_), os = s4(os_);
+    Strides4 bs = s4(bs_), ys = s4(ys_), os = s4(os_), os2 = out2 ? s4(os2_) : Strides4{0, 0, 0, 0};
     EL_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec16<T>::N;
+        if (out2 && !(channel_vectorisable<T>(b, bs, C) && channel_vectorisable<T>(y, ys, C) && channel_vectorisable<T>(out, os, C) &&
+                      channel_vectorisable<T>(out2, os2, C) && C / V <= 256 && B <= 65535))
+            return EL_ERR_UNSUPPORTED;  // the second destination is an engine-only (NHWC) feature
         if (channel_vectorisable<T>(b, bs, C) && channel_vectorisable<T>(y, ys, C) && channel_vectorisable<T>(out, os, C)) {
             if (C / V <= 256 && B <= 65535) {
                 int cpb;
                 dim3 g = tile_grid(C / V, W, H, B, cpb);
-                gated_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, C / V, cpb, H, W);
+                gated_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, (T*)out2, os2, C / V, cpb, H, W);
             } else {
                 int64_t total = (int64_t)B * H * W * (C / V);
                 gated_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, C / V, H, W, total);

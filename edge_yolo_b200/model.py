@@ -141,6 +141,14 @@ class EdgeLineYOLO(nn.Module):
             for m in self.modules():
                 if type(m) in binds:
                     m.forward = types.MethodType(binds[type(m)], m)
+            head = self.model[-1]
+            if isinstance(head, GFLHeadv2_uniH):  # the last 1x1 convs of both towers lose their bias; the decode kernels add it
+                box_b, cls_b = [], []
+                for seq, dst in ((head.cv2, box_b), (head.cv3, cls_b)):
+                    for tower in seq:
+                        dst.append(tower[-1].bias.detach().float().clone())
+                        tower[-1].bias = None
+                head.el_head_bias = (box_b, cls_b)
             layers = list(self.model)
             for up, cat in zip(layers, layers[1:]):
                 if (isinstance(up, nn.Upsample) and isinstance(cat, Concat) and up.scale_factor == 2 and up.mode == "nearest"

@@ -36,7 +36,7 @@ def dwt_forward(self, x: torch.Tensor):
     return buf[:B], buf[B : 2 * B], buf[2 * B : 3 * B], buf[3 * B :]
 
 
-def wavelet_enhancer_forward(self, b: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+def wavelet_enhancer_forward(self, b: torch.Tensor, inplace: bool = False, out2: torch.Tensor | None = None) -> torch.Tensor:
     """`_WaveletEnhancer.forward` (block.py:3685-3710).
 
     DWT split -> f_ll / shared f_h convs (cuDNN) -> fused upsample*w+concat kernel -> fuse conv ->
@@ -54,7 +54,7 @@ def wavelet_enhancer_forward(self, b: torch.Tensor, inplace: bool = False) -> to
         LHp, HLp, HHp = hp[:B], hp[B : 2 * B], hp[2 * B :]
     cat = ops.wave_merge(b, LLp, LHp, HLp, HHp, self.alpha)
     y = self.fuse(cat)
-    return ops.gated_residual(b, y, self.gamma, inplace=inplace and not torch.is_grad_enabled())
+    return ops.gated_residual(b, y, self.gamma, inplace=inplace and not torch.is_grad_enabled(), out2=out2)
 
 
 def linear_attention_forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -100,10 +100,13 @@ def gfl_head_forward(self, x):
         return x
     if getattr(self, "export", False) and getattr(self, "format", None) in {"tflite", "edgetpu", "imx", "saved_model", "pb", "tfjs"}:
         raise NotImplementedError("edge_yolo_b200: export formats are out of scope (no multi-backend dispatch)")
+    bias = getattr(self, "el_head_bias", None)  # engine fuse: biases of the towers' last convs, added inside the decode kernels
+    if bias is not None and bias[0][0].device != boxes[0].device:
+        bias = self.el_head_bias = tuple([t.to(boxes[0].device) for t in side] for side in bias)
     det = getattr(self, "el_detect", None)
     if det is not None:  # engine path (Predictor): fused decode + NMS, returns (rows (B, max_det, 6), counts (B))
-        return ops.gfl_detect(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride], **det)
-    y = ops.gfl_decode(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride])
+        return ops.gfl_detect(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride], bias=bias, **det)
+    y = ops.gfl_decode(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride], bias=bias)
     if getattr(self, "export", False):
         return y
     if getattr(self, "el_skip_feats", False):  # fast predict path: nobody reads the raw maps
@@ -129,14 +132,14 @@ def _bias_on(self, x):
     return b
 
 
-def conv_engine_forward(self, x, out=None, residual=None):
+def conv_engine_forward(self, x, out=None, residual=None, out2=None):
     """Conv.forward_fuse (conv.py:58-60): conv (cuDNN, no bias) -> fused bias + activation [+ residual]."""
-    return ops.bias_act(self.conv(x), _bias_on(self, x), self.el_act, residual=residual, out=out)
+    return ops.bias_act(self.conv(x), _bias_on(self, x), self.el_act, residual=residual, out=out, out2=out2)
 
 
-def dsconv_engine_forward(self, x, out=None, residual=None):
+def dsconv_engine_forward(self, x, out=None, residual=None, out2=None):
     """DSConv.forward (conv.py:100-104) with its BatchNorm folded into the pointwise conv."""
-    return ops.bias_act(self.pw(self.dw(x)), _bias_on(self, x), ops.ACT_SILU, residual=residual, out=out)
+    return ops.bias_act(self.pw(self.dw(x)), _bias_on(self, x), ops.ACT_SILU, residual=residual, out=out, out2=out2)
 
 
 def dsbottleneck_engine_forward(self, x, out=None):
@@ -165,10 +168,18 @@ def dsc3k2_wavelet_engine_forward(self, x):
     B, _, H, W = x.shape
     c, n = self.c, len(self.m)
     buf = torch.empty((B, (2 + n) * c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
-    self.cv1(x, out=buf[:, : 2 * c])
-    cur = wavelet_enhancer_forward(self.wave, buf[:, c : 2 * c], inplace=True)
+    # the processed half b is kept as a dense tensor as well: every consumer (DWT, merge, the stacked convs) then reads
+    # whole DRAM bursts instead of c of every (2+n)c interleaved channels, and cuDNN needs no hidden .contiguous() copy
+    b = torch.empty((B, c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    self.cv1(x, out=buf[:, :c], out2=b)
+    cur = wavelet_enhancer_forward(self.wave, b, inplace=True, out2=buf[:, c : 2 * c])
     for k, blk in enumerate(self.m):
-        cur = blk(cur, out=buf[:, (2 + k) * c : (3 + k) * c])
+        dst = buf[:, (2 + k) * c : (3 + k) * c]
+        if k == n - 1:
+            blk(cur, out=dst)
+        else:
+            cur = blk(cur)
+            dst.copy_(cur)
     return self.cv2(buf)
 
 
@@ -185,8 +196,8 @@ def c2psa_engine_forward(self, x):
     B, _, H, W = x.shape
     c = self.c
     buf = torch.empty((B, 2 * c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
-    self.cv1(x, out=buf)
-    cur = buf[:, c:]
+    cur = torch.empty((B, c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    self.cv1(x, out=buf[:, :c], out2=cur)  # attention branch as a dense tensor, pass-through half straight into the concat buffer
     last = len(self.m) - 1
     for k, blk in enumerate(self.m):
         cur = blk(cur, out=buf[:, c:] if k == last else None)

@@ -170,7 +170,7 @@ def wave_merge(b, LLp, LHp, HLp, HHp, alpha) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------- gated residual
-def _gated_fwd(b, y, gamma, out=None):
+def _gated_fwd(b, y, gamma, out=None, out2=None):
     _need_cuda(b, y, gamma)
     if y.shape != b.shape or y.dtype != b.dtype:
         raise EdgelineError("gated_residual: b and y must have the same shape and dtype")
@@ -178,7 +178,9 @@ def _gated_fwd(b, y, gamma, out=None):
     out = _empty_like_layout(b, b.shape) if out is None else out
     g = gamma if gamma.dtype == torch.float32 else gamma.float()
     check(_lib.lib().el_gated_residual_fwd(b.data_ptr(), _i64(b.stride()), y.data_ptr(), _i64(y.stride()), g.data_ptr(),
-                                           out.data_ptr(), _i64(out.stride()), B, C, H, W, _dt(b), _stream()), "el_gated_residual_fwd")
+                                           out.data_ptr(), _i64(out.stride()), out2.data_ptr() if out2 is not None else None,
+                                           _i64(out2.stride()) if out2 is not None else None, B, C, H, W, _dt(b), _stream()),
+          "el_gated_residual_fwd")
     return out
 
 
@@ -197,11 +199,11 @@ class _Gated(torch.autograd.Function):
         return g, (g.float() * t).to(g.dtype), ggamma
 
 
-def gated_residual(b, y, gamma, inplace: bool = False) -> torch.Tensor:
-    """b + tanh(gamma) * y.  `inplace=True` writes the result over `b` (inference only)."""
+def gated_residual(b, y, gamma, inplace: bool = False, out2: torch.Tensor | None = None) -> torch.Tensor:
+    """b + tanh(gamma) * y.  `inplace=True` writes the result over `b`, `out2` receives a second copy (inference only)."""
     if torch.is_grad_enabled() and any(t.requires_grad for t in (b, y, gamma)):
         return _Gated.apply(b, y, gamma)
-    return _gated_fwd(b, y, gamma, out=b if inplace else None)
+    return _gated_fwd(b, y, gamma, out=b if inplace else None, out2=out2)
 
 
 # ------------------------------------------------------------------------------ attention
@@ -230,7 +232,18 @@ def linear_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------- decode
-def gfl_decode(boxes, clss, dgqp, strides, want_quality: bool = False):
+def _bias_tables(bias, nl):
+    if bias is None:
+        return None, None
+    box_b, cls_b = bias
+    for t in list(box_b) + list(cls_b):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda):
+            raise EdgelineError("decode bias vectors must be contiguous fp32 CUDA tensors")
+    tab = lambda ts: (c_void_p * nl)(*[t.data_ptr() if t is not None else None for t in ts])
+    return tab(box_b), tab(cls_b)
+
+
+def gfl_decode(boxes, clss, dgqp, strides, want_quality: bool = False, bias=None):
     """boxes[l] (B,64,Hl,Wl), clss[l] (B,nc,Hl,Wl), dgqp[l] = (w1 (64,20), b1 (64), w2 (64), b2 (1)) fp32,
     strides[l] float -> y (B, 4+nc, A) fp32 [, q (B, A) fp32]."""
     nl = len(boxes)
@@ -252,14 +265,15 @@ def gfl_decode(boxes, clss, dgqp, strides, want_quality: bool = False):
     y = torch.empty((B, 4 + nc, A), device=boxes[0].device, dtype=torch.float32)
     q = torch.empty((B, A), device=boxes[0].device, dtype=torch.float32) if want_quality else None
     cols = [_ptrs([w[k] for w in dgqp]) for k in range(4)]
+    bb, cb = _bias_tables(bias, nl)
     check(_lib.lib().el_gfl_decode_fwd(nl, _ptrs(boxes), _i64(bs), _ptrs(clss), _i64(cs), (c_int32 * len(hw))(*hw),
-                                       (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3],
+                                       (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3], bb, cb,
                                        y.data_ptr(), q.data_ptr() if q is not None else None, B, nc, dt, _stream()), "el_gfl_decode_fwd")
     return (y, q) if want_quality else y
 
 
 def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, multi_label=False, agnostic=False, classes=None,
-               max_det=300, max_nms=30000, max_wh=7680.0):
+               max_det=300, max_nms=30000, max_wh=7680.0, bias=None):
     """Fused decode + NMS of the engine path: same inputs as `gfl_decode`, same outputs as `nms_batched`
     (out (B, max_det, 6), count (B) int32); the dense (B, 4+nc, A) tensor is never written.  Falls back to
     `gfl_decode` + `nms_batched` (identical results) when the head maps are not dense NHWC."""
@@ -285,13 +299,14 @@ def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, mult
         keep[torch.as_tensor(classes, dtype=torch.long)] = 1
         keep = keep.to(dev)
     cols = [_ptrs([w[k] for w in dgqp]) for k in range(4)]
+    bb, cb = _bias_tables(bias, nl)
     st = L.el_gfl_detect_fwd(nl, _ptrs(boxes), _i64(bs), _ptrs(clss), _i64(cs), (c_int32 * len(hw))(*hw),
-                             (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3], B, nc, _dt(boxes[0]),
+                             (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3], bb, cb, B, nc, _dt(boxes[0]),
                              float(conf_thres), float(iou_thres), int(bool(multi_label)), int(bool(agnostic)),
                              keep.data_ptr() if keep is not None else None, int(max_det), int(max_nms), float(max_wh), ws.data_ptr(),
                              need.value, out.data_ptr(), cnt.data_ptr(), None, _stream())
     if st == 2:  # EL_ERR_UNSUPPORTED: strided / NCHW maps -> two-call path with the same kernels downstream
-        y = gfl_decode(boxes, clss, dgqp, strides)
+        y = gfl_decode(boxes, clss, dgqp, strides, bias=bias)
         return nms_batched(y, conf_thres, iou_thres, multi_label=multi_label, agnostic=agnostic, classes=classes, max_det=max_det,
                            max_nms=max_nms, max_wh=max_wh)
     check(st, "el_gfl_detect_fwd")
@@ -434,9 +449,10 @@ ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 
 
 def bias_act(x: torch.Tensor, bias: torch.Tensor | None, act: int = ACT_SILU, residual: torch.Tensor | None = None,
-             out: torch.Tensor | None = None) -> torch.Tensor:
+             out: torch.Tensor | None = None, out2: torch.Tensor | None = None) -> torch.Tensor:
     """out = act(x + bias[c]) (+ residual).  Inference-engine epilogue of a cuDNN conv; `out` defaults to `x` (in place)
-    and may be a channel slice of a wider concat buffer."""
+    and may be a channel slice of a wider concat buffer.  With `out2`, the first out.shape[1] channels go to `out` and
+    the remaining ones to `out2`."""
     _need_cuda(x)
     B, C, H, W = x.shape
     out = x if out is None else out
@@ -447,7 +463,8 @@ def bias_act(x: torch.Tensor, bias: torch.Tensor | None, act: int = ACT_SILU, re
     check(_lib.lib().el_bias_act_fwd(x.data_ptr(), _i64(x.stride()), bias.data_ptr() if bias is not None else None,
                                      residual.data_ptr() if residual is not None else None,
                                      _i64(residual.stride()) if residual is not None else None, out.data_ptr(), _i64(out.stride()),
-                                     B, C, H, W, int(act), _dt(x), _stream()), "el_bias_act_fwd")
+                                     out2.data_ptr() if out2 is not None else None, _i64(out2.stride()) if out2 is not None else None,
+                                     out.shape[1] if out2 is not None else 0, B, C, H, W, int(act), _dt(x), _stream()), "el_bias_act_fwd")
     return out
 
 

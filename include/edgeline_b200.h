@@ -76,10 +76,11 @@ int el_wave_merge_bwd(const void* gout, const int64_t gos[4], const void* const 
                       float* galpha_w, int B, int c, int H, int W, int h, int w, int dtype,
                       void* stream);
 /* Gated residual, block.py:3710: out = b + tanh(gamma) * y; gamma is one device float.
- * out may alias b. */
+ * out may alias b.  out2 (optional, NHWC engine path only) receives a second copy of the result,
+ * e.g. the block's slice of the concat buffer. */
 int el_gated_residual_fwd(const void* b, const int64_t bs[4], const void* y, const int64_t ys[4],
-                          const float* gamma, void* out, const int64_t os[4], int B, int C,
-                          int H, int W, int dtype, void* stream);
+                          const float* gamma, void* out, const int64_t os[4], void* out2,
+                          const int64_t os2[4], int B, int C, int H, int W, int dtype, void* stream);
 
 /* ---- a4. linear-attention core: LinearAttention.forward, block.py:3364-3372 -----------------
  * qkv (B,3C,N) with strides qs = {sb, sc, sn} (channel = t*C + head*64 + j, t in q,k,v);
@@ -93,12 +94,15 @@ int el_linattn_fwd(const void* qkv, const int64_t qs[3], void* y, const int64_t 
  * Per level l < nl: box[l] (B,64,Hl,Wl) DFL logits, cls[l] (B,nc,Hl,Wl) class logits (host
  * tables of device pointers, strides box_s/cls_s[4*l..]), hw[2*l..] = {Hl,Wl}, stride[l].
  * DGQP head weights (fp32, device): w1[l] (64,20), b1[l] (64), w2[l] (64), b2[l] (1).
+ * box_bias / cls_bias: NULL, or per-level fp32 device vectors (64) / (nc) added to the logits first
+ * (the engine strips the bias of the towers' last 1x1 convs and folds it in here); entries may be NULL.
  * Writes y (B,4+nc,A) fp32 contiguous: rows 0-3 = (cx,cy,w,h)*stride, rows 4.. =
  * sigmoid(cls)*clamp(q,1e-6,1-1e-6); optional q_out (B,A) fp32 (may be NULL). */
 int el_gfl_decode_fwd(int nl, const void* const* box, const int64_t* box_s, const void* const* cls,
                       const int64_t* cls_s, const int32_t* hw, const float* stride,
                       const float* const* w1, const float* const* b1, const float* const* w2,
-                      const float* const* b2, float* y, float* q_out, int B, int nc, int dtype,
+                      const float* const* b2, const float* const* box_bias,
+                      const float* const* cls_bias, float* y, float* q_out, int B, int nc, int dtype,
                       void* stream);
 
 /* ---- a6+a7+a9 fused (engine path): decode -> NMS candidates -> sort -> sweep, no dense score tensor --
@@ -111,7 +115,8 @@ int el_gfl_detect_workspace_bytes(int B, int nc, int A, int multi_label, int max
 int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* box_s, const void* const* cls,
                       const int64_t* cls_s, const int32_t* hw, const float* stride,
                       const float* const* w1, const float* const* b1, const float* const* w2,
-                      const float* const* b2, int B, int nc, int dtype, float conf_thres,
+                      const float* const* b2, const float* const* box_bias,
+                      const float* const* cls_bias, int B, int nc, int dtype, float conf_thres,
                       double iou_thres, int multi_label, int agnostic, const int32_t* class_keep,
                       int max_det, int max_nms, float max_wh, void* workspace, size_t workspace_bytes,
                       float* out, int32_t* out_count, int64_t* out_index, void* stream);
@@ -164,12 +169,15 @@ int el_ingest_u8(const uint8_t* src, void* dst, const int64_t ds[4], int B, int 
  * el_bias_act_fwd: out = act(x + bias[c]) (+ residual): the BatchNorm-folded bias and SiLU of Conv /
  * DSConv (nn/modules/conv.py:41-60, 87-104) and the shortcut add of DSBottleneck (block.py:1500-1503)
  * in one pass.  act: 0 none, 1 SiLU, 2 ReLU; bias (C) fp32 or NULL; residual (same shape) or NULL;
- * out may alias x and may be a channel slice of a wider (concat) buffer.
+ * out may alias x and may be a channel slice of a wider (concat) buffer.  With out2 != NULL channels
+ * [0, split) go to out and [split, C) to out2 (a C2f block's pass-through half into the concat buffer,
+ * the processed half into a dense tensor).
  * el_upsample2x_cat_fwd: out (B,C1+C2,H,W) = cat[nearest2x(x (B,C1,H/2,W/2)), skip (B,C2,H,W)], the
  * nn.Upsample + Concat pairs of the neck (cfg/models/11/yolo11-test.yaml:34-39); NHWC views only. */
 int el_bias_act_fwd(const void* x, const int64_t xs[4], const float* bias, const void* residual,
-                    const int64_t rs[4], void* out, const int64_t os[4], int B, int C, int H, int W,
-                    int act, int dtype, void* stream);
+                    const int64_t rs[4], void* out, const int64_t os[4], void* out2,
+                    const int64_t os2[4], int split, int B, int C, int H, int W, int act, int dtype,
+                    void* stream);
 int el_upsample2x_cat_fwd(const void* x, const int64_t xs[4], const void* skip, const int64_t ss[4],
                           void* out, const int64_t os[4], int B, int C1, int C2, int H, int W,
                           int dtype, void* stream);
