@@ -55,6 +55,7 @@ _SIGNATURES = {
     "el_ingest_u8": (c_int, [c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_void_p]),
     "el_bias_act_fwd": (c_int, [c_void_p, I64P, c_void_p, c_void_p, I64P, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_void_p]),
+    "el_sppf_pool_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_upsample2x_cat_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

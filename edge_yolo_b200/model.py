@@ -137,7 +137,7 @@ class EdgeLineYOLO(nn.Module):
         if engine:
             binds = {M.DSBottleneck: M.dsbottleneck_engine_forward, M.DSC3k: M.dsc3k_engine_forward,
                      M.DSC3K2_Wavelet: M.dsc3k2_wavelet_engine_forward, M.PSABlock_LinearAttention: M.psablock_engine_forward,
-                     M.C2PSA_LinearAttention: M.c2psa_engine_forward}
+                     M.C2PSA_LinearAttention: M.c2psa_engine_forward, M.SPPF: M.sppf_engine_forward}
             for m in self.modules():
                 if type(m) in binds:
                     m.forward = types.MethodType(binds[type(m)], m)

@@ -112,7 +112,10 @@ def gfl_head_forward(self, x):
     if getattr(self, "el_skip_feats", False):  # fast predict path: nobody reads the raw maps
         return y, None
     for i in range(self.nl):
-        x[i] = torch.cat((boxes[i], clss[i]), 1)
+        if bias is not None:  # engine-fused towers: put the stripped biases back into the maps handed to the caller
+            x[i] = torch.cat((boxes[i] + bias[0][i].view(1, -1, 1, 1).to(boxes[i].dtype), clss[i] + bias[1][i].view(1, -1, 1, 1).to(clss[i].dtype)), 1)
+        else:
+            x[i] = torch.cat((boxes[i], clss[i]), 1)
     return y, x
 
 
@@ -202,6 +205,17 @@ def c2psa_engine_forward(self, x):
     for k, blk in enumerate(self.m):
         cur = blk(cur, out=buf[:, c:] if k == last else None)
     return self.cv2(buf)
+
+
+def sppf_engine_forward(self, x):
+    """SPPF.forward (block.py:219-223): the three chained max-pools and the concat are one kernel."""
+    y = self.cv1(x)
+    if y.shape[2] * y.shape[3] * 64 > 200 * 1024 or self.m.kernel_size != 5:  # large maps keep the PyTorch pooling
+        ys = [y]
+        for _ in range(3):
+            ys.append(self.m(ys[-1]))
+        return self.cv2(torch.cat(ys, 1))
+    return self.cv2(ops.sppf_pool(y))
 
 
 def concat_engine_forward(self, x):

@@ -479,3 +479,13 @@ def upsample2x_cat(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
     check(_lib.lib().el_upsample2x_cat_fwd(x.data_ptr(), _i64(x.stride()), skip.data_ptr(), _i64(skip.stride()), out.data_ptr(),
                                            _i64(out.stride()), B, C1, C2, H, W, _dt(x), _stream()), "el_upsample2x_cat_fwd")
     return out
+
+
+def sppf_pool(x: torch.Tensor) -> torch.Tensor:
+    """cat[x, m(x), m(m(x)), m(m(m(x)))] with m = MaxPool2d(5, 1, 2), in one kernel (NHWC, maps up to ~56x56)."""
+    _need_cuda(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, 4 * C, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    check(_lib.lib().el_sppf_pool_fwd(x.data_ptr(), _i64(x.stride()), out.data_ptr(), _i64(out.stride()), B, C, H, W, _dt(x), _stream()),
+          "el_sppf_pool_fwd")
+    return out

@@ -181,6 +181,11 @@ int el_bias_act_fwd(const void* x, const int64_t xs[4], const float* bias, const
 int el_upsample2x_cat_fwd(const void* x, const int64_t xs[4], const void* skip, const int64_t ss[4],
                           void* out, const int64_t os[4], int B, int C1, int C2, int H, int W,
                           int dtype, void* stream);
+/* el_sppf_pool_fwd: out (B,4C,H,W) = cat[x, m(x), m(m(x)), m(m(m(x)))], m = MaxPool2d(5,1,2): the pooling
+ * pyramid of SPPF (nn/modules/block.py:204-223) as separable 5/9/13 window maxima in shared memory.
+ * NHWC views, H*W*64 B of shared memory (maps up to ~56x56), else EL_ERR_UNSUPPORTED. */
+int el_sppf_pool_fwd(const void* x, const int64_t xs[4], void* out, const int64_t os[4], int B, int C,
+                     int H, int W, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

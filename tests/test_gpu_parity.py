@@ -462,6 +462,13 @@ def test_epilogue_kernels_vs_torch():
         sk = torch.randn(2, 24, 12, 14, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
         want = torch.cat((torch.nn.functional.interpolate(lo.float(), scale_factor=2, mode="nearest"), sk.float()), 1)
         close(ops().upsample2x_cat(lo, sk), want, 0, 0)
+        for hw in ((20, 20), (7, 9), (40, 40)):
+            z = torch.randn(2, 32, *hw, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+            mp = torch.nn.MaxPool2d(5, 1, 2)
+            ys = [z]
+            for _ in range(3):
+                ys.append(mp(ys[-1]))
+            close(ops().sppf_pool(z), torch.cat(ys, 1), 0, 0)
 
 
 def test_predictor_matches_api_path():
@@ -516,3 +523,26 @@ def test_fused_detect_equals_decode_then_nms(dtype, nc, sizes, kw):
     ref, _ = O.non_max_suppression(y.cpu().numpy(), **kw)
     for b in range(B):
         assert want[b, : int(wcnt[b])].cpu().numpy().tobytes() == ref[b].tobytes()
+
+
+def test_decode_bias_folding():
+    """bias vectors of the towers' last convs added inside the decode kernels == adding them to the maps first."""
+    gen = torch.Generator().manual_seed(31)
+    B, nc, sizes = 2, 80, ((16, 16), (8, 8), (4, 4))
+    cl = torch.channels_last
+    boxes = [(torch.randn(B, 64, h, w, generator=gen) * 2).to(DEV).contiguous(memory_format=cl) for h, w in sizes]
+    clss = [(torch.randn(B, nc, h, w, generator=gen) * 2).to(DEV).contiguous(memory_format=cl) for h, w in sizes]
+    ws = [tuple(t.to(DEV) for t in (torch.randn(64 * 20, generator=gen), torch.randn(64, generator=gen), torch.randn(64, generator=gen) * 0.3,
+                                    torch.randn(1, generator=gen))) for _ in sizes]
+    bb = [torch.randn(64, generator=gen).to(DEV) for _ in sizes]
+    cb = [torch.randn(nc, generator=gen).to(DEV) for _ in sizes]
+    o, st = ops(), [8.0, 16.0, 32.0]
+    want = o.gfl_decode([b + v.view(1, -1, 1, 1) for b, v in zip(boxes, bb)], [c + v.view(1, -1, 1, 1) for c, v in zip(clss, cb)], ws, st)
+    got = o.gfl_decode(boxes, clss, ws, st, bias=(bb, cb))
+    assert torch.equal(got, want)
+    kw = dict(conf_thres=0.25, iou_thres=0.7)
+    r0, c0 = o.nms_batched(want, **kw)
+    r1, c1 = o.gfl_detect(boxes, clss, ws, st, bias=(bb, cb), **kw)
+    assert c0.tolist() == c1.tolist()
+    for b in range(B):
+        assert torch.equal(r0[b, : int(c0[b])], r1[b, : int(c0[b])])
