@@ -7,6 +7,8 @@
 // This file holds the fp32 CUDA-core kernel (1e-5 contract; also the fallback for odd shapes).
 // One CTA per (image, head); K/V/Q token tiles are staged through shared memory with a
 // layout-aware coalesced loader, so NCHW and NHWC inputs run the same math.
+#include <cstdlib>
+
 #include "el_common.cuh"
 
 namespace el {
@@ -160,7 +162,8 @@ extern "C" int el_linattn_fwd(const void* qkv, const int64_t qs[3], void* y, con
     if (!qkv || !y || !qs || !ys || B <= 0 || heads <= 0 || N <= 0) return EL_ERR_ARG;
     AttnArgs A{qkv, qs[0], qs[1], qs[2], y, ys[0], ys[1], ys[2], heads, N};
     cudaStream_t s = (cudaStream_t)stream;
-    if (linattn_tc_supported(A, dtype)) return linattn_tc_launch(A, B, dtype, s);
+    static const bool force_simt = getenv("EL_LINATTN_SIMT") != nullptr;  // A/B switch for tests and profiling
+    if (!force_simt && linattn_tc_supported(A, dtype)) return linattn_tc_launch(A, B, dtype, s);
     const bool ch_fast = A.qc == 1 && A.yc == 1;
     EL_DISPATCH_DTYPE(dtype, {
         if (ch_fast) {

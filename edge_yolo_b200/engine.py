@@ -98,6 +98,57 @@ class Predictor:
         torch.cuda.current_stream(self.device).synchronize()
         return self.host_out, self.host_cnt
 
+    def predict_many(self, host_batches, consume=None):
+        """Software-pipelined `predict_u8` over a sequence of pinned uint8 batches: the H2D copy of batch i+1 runs on a copy
+        stream while batch i computes, and the D2H of batch i's rows overlaps batch i+1.  `consume(i, rows, counts)` is called
+        once per batch with pinned host tensors that stay valid until the next-but-one call; returns the number of batches."""
+        dev = self.device
+        if not hasattr(self, "_pipe"):
+            self._pipe = dict(copy=torch.cuda.Stream(device=dev), stage=[torch.empty_like(self.u8) for _ in range(2)],
+                              out=[torch.empty_like(self.host_out).pin_memory() for _ in range(2)],
+                              cnt=[torch.empty_like(self.host_cnt).pin_memory() for _ in range(2)])
+        P = self._pipe
+        main = torch.cuda.current_stream(dev)
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+        stage_free = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        for e in stage_free:
+            e.record(main)
+        batches = list(host_batches)
+
+        def submit(i):
+            with torch.cuda.stream(P["copy"]):
+                P["copy"].wait_event(stage_free[i & 1])
+                P["stage"][i & 1].copy_(batches[i], non_blocking=True)
+                h2d_done[i & 1].record(P["copy"])
+
+        if batches:
+            submit(0)
+        for i in range(len(batches)):
+            if i + 1 < len(batches):
+                submit(i + 1)
+            main.wait_event(h2d_done[i & 1])
+            self.u8.copy_(P["stage"][i & 1], non_blocking=True)  # device-to-device: frees the stage for the next H2D
+            stage_free[i & 1].record(main)
+            if self.graph_from_u8 is not None:
+                self.graph_from_u8.replay()
+                out, cnt = self.out, self.cnt
+            else:
+                out, cnt = self._forward(True)
+            if i >= 2:
+                done[i & 1].synchronize()  # the host buffers of batch i-2 are about to be overwritten
+            P["out"][i & 1].copy_(out, non_blocking=True)
+            P["cnt"][i & 1].copy_(cnt, non_blocking=True)
+            done[i & 1].record(main)
+            if i >= 1 and consume is not None:
+                done[(i - 1) & 1].synchronize()
+                consume(i - 1, P["out"][(i - 1) & 1], P["cnt"][(i - 1) & 1])
+        if batches:
+            done[(len(batches) - 1) & 1].synchronize()
+            if consume is not None:
+                consume(len(batches) - 1, P["out"][(len(batches) - 1) & 1], P["cnt"][(len(batches) - 1) & 1])
+        return len(batches)
+
     def predict(self, host_u8: torch.Tensor):
         """List of (k, 6) tensors [x1, y1, x2, y2, conf, cls] per image, like the reference's NMS output."""
         rows, cnt = self.predict_u8(host_u8)

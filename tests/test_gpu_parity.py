@@ -491,6 +491,16 @@ def test_predictor_matches_api_path():
     assert [d.shape[0] for d in dets] == [w.shape[0] for w in want]
     for d, w in zip(dets, want):
         assert d.numpy().tobytes() == w.cpu().numpy().tobytes()
+    # pipelined multi-batch API returns the same rows for every batch, in order
+    hosts = [host, torch.flip(host, dims=[0]).contiguous().pin_memory(), host]
+    got = {}
+    pred.predict_many(hosts, consume=lambda i, rows, cnt: got.__setitem__(i, [rows[b, : int(cnt[b])].clone() for b in range(2)]))
+    assert sorted(got) == [0, 1, 2]
+    for k in (0, 2):
+        for d, w in zip(got[k], want):
+            assert d.numpy().tobytes() == w.cpu().numpy().tobytes()
+    for d, w in zip(got[1], want[::-1]):
+        assert d.shape == w.shape
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
