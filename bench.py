@@ -221,19 +221,18 @@ def measured_peak():
 # ------------------------------------------------------------------------------ product arm
 def product_arm(a):
     import torch
-    import torch.distributed as dist
 
     from edge_yolo_b200 import _lib
+    from edge_yolo_b200 import dist as eld
     from edge_yolo_b200.engine import Predictor, build_model
 
     _lib.lib()  # fail loudly if the extension is missing
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = eld.env_rank()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (product arm) needs a GPU; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    eld.init(dev)
     torch.backends.cudnn.benchmark = not a.no_cudnn_benchmark
 
     model = build_model(a.scale, a.nc, seed=0, device=dev)
@@ -243,16 +242,10 @@ def product_arm(a):
     pred.predict_u8(host_u8)  # also leaves a real batch in pred.x
 
     def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize(dev)
+        eld.barrier(dev)
 
     def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return eld.max_over_ranks(v, dev)
 
     # ---- leg 1: inputs resident in HBM, device-timed
     for _ in range(a.warmup):
@@ -308,9 +301,7 @@ def product_arm(a):
         rate, ms, threads = cpu_oracle_rate(a, steps=3, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"3 steps x {a.cpu_sample} images (bounded sample of the batch-{a.batch} workload), forward + decode + NMS, fp32"}
-    if world > 1:
-        dist.barrier(device_ids=[local])
-        dist.destroy_process_group()
+    eld.shutdown()
     if rank == 0:
         print(json.dumps(line), flush=True)
 

@@ -1,0 +1,69 @@
+"""Drop-in installation behind the unchanged ultralytics API (the reference fork).
+
+`install()` rebinds the *bodies* of the reference's hot-path functions to the CUDA implementations; class
+identities, constructor signatures, parameter names and therefore state-dict / pickle compatibility are
+untouched, so `YOLO(cfg, task="detect").predict / val`, `ultralytics.nn.modules.*` and
+`ultralytics.utils.ops.non_max_suppression` keep working as before:
+
+    import edge_yolo_b200.install as el; el.install()
+    model = YOLO("yolo11n-test.yaml", task="detect")      # reference quirk Q1: task must be given
+
+What is replaced (reference path -> ours):
+    nn/modules/block.py  _PywtDWT2D.forward          -> modules.dwt_forward
+                         _WaveletEnhancer.forward    -> modules.wavelet_enhancer_forward
+                         LinearAttention.forward     -> modules.linear_attention_forward
+    nn/modules/head.py   GFLHeadv2_uniH.forward      -> modules.gfl_head_forward
+    utils/ops.py         non_max_suppression         -> nms.non_max_suppression
+    utils/loss.py        quality_focal_loss, QualityFocalLoss.forward, distribution_focal_loss, DFLoss.__call__
+                                                      -> loss.*
+There is no CPU fallback: after install() these functions need CUDA tensors.
+"""
+from __future__ import annotations
+
+import importlib
+
+_ORIGINALS: dict = {}
+
+
+def _swap(obj, name, new):
+    key = (obj, name)
+    if key not in _ORIGINALS:
+        _ORIGINALS[key] = getattr(obj, name)
+    setattr(obj, name, new)
+
+
+def install(nms: bool = True, modules: bool = True, losses: bool = True):
+    """Patch the imported `ultralytics` package in place.  Returns the list of patched names."""
+    from . import _lib, loss as el_loss, modules as M, nms as el_nms
+
+    _lib.lib()  # fail now, loudly, if the CUDA library has not been built
+    block = importlib.import_module("ultralytics.nn.modules.block")
+    head = importlib.import_module("ultralytics.nn.modules.head")
+    uops = importlib.import_module("ultralytics.utils.ops")
+    uloss = importlib.import_module("ultralytics.utils.loss")
+    done = []
+    if modules:
+        _swap(block._PywtDWT2D, "forward", M.dwt_forward)
+        _swap(block._WaveletEnhancer, "forward", M.wavelet_enhancer_forward)
+        _swap(block.LinearAttention, "forward", M.linear_attention_forward)
+        _swap(head.GFLHeadv2_uniH, "forward", M.gfl_head_forward)
+        done += ["block._PywtDWT2D.forward", "block._WaveletEnhancer.forward", "block.LinearAttention.forward", "head.GFLHeadv2_uniH.forward"]
+    if nms:
+        _swap(uops, "non_max_suppression", el_nms.non_max_suppression)
+        done.append("utils.ops.non_max_suppression")
+    if losses:
+        _swap(uloss, "quality_focal_loss", el_loss.quality_focal_loss)
+        _swap(uloss, "distribution_focal_loss", el_loss.distribution_focal_loss)
+        _swap(uloss.QualityFocalLoss, "forward", el_loss.QualityFocalLoss.forward)
+        _swap(uloss.DistributionFocalLoss, "forward", el_loss.DistributionFocalLoss.forward)
+        _swap(uloss.DFLoss, "__call__", el_loss.DFLoss.__call__)
+        done += ["utils.loss.quality_focal_loss", "utils.loss.distribution_focal_loss", "utils.loss.QualityFocalLoss.forward",
+                 "utils.loss.DistributionFocalLoss.forward", "utils.loss.DFLoss.__call__"]
+    return done
+
+
+def uninstall():
+    """Restore everything `install()` replaced."""
+    for (obj, name), orig in list(_ORIGINALS.items()):
+        setattr(obj, name, orig)
+    _ORIGINALS.clear()
