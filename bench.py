@@ -120,7 +120,7 @@ def reference_arm(a):
             "config": workload(a),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------- kernel roofline
@@ -303,11 +303,19 @@ def product_arm(a):
                                 "sample": f"3 steps x {a.cpu_sample} images (bounded sample of the batch-{a.batch} workload), forward + decode + NMS, fp32"}
     eld.shutdown()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        _emit(line)
+
+
+def _emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
     args = parse()
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner to stdout) are sent to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         reference_arm(args)
     else:
