@@ -38,18 +38,24 @@ struct DecodeParams {
     int nl, nc, A, tiles_per_image;
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Transcendentals: fp32 maps keep IEEE expf / division (1e-5 contract against the fp32 reference); 16-bit maps use the SFU
+// intrinsics (relative error ~1e-6, two orders below the bf16 / fp16 input rounding).  The policy is a template parameter of
+// every helper so the dense and the fused kernel stay bit-identical for a given dtype.
+template <bool FAST> __device__ __forceinline__ float exp_(float x) { return FAST ? __expf(x) : expf(x); }
+template <bool FAST> __device__ __forceinline__ float rcp_(float x) { return FAST ? __frcp_rn(x) : 1.f / x; }
+template <bool FAST> __device__ __forceinline__ float sigmoidf_(float x) { return rcp_<FAST>(1.f + exp_<FAST>(-x)); }
 
 // ---- shared arithmetic ------------------------------------------------------------------------
 // softmax over the 16 bins of one side: DFL integral, sorted top-4 probabilities and their mean
+template <bool FAST>
 __device__ __forceinline__ void side_stats(float (&lg)[kRegMax], float& dist, float* __restrict__ stat5) {
     float m = lg[0];
 #pragma unroll
     for (int k = 1; k < kRegMax; ++k) m = fmaxf(m, lg[k]);
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kRegMax; ++k) { lg[k] = expf(lg[k] - m); s += lg[k]; }
-    const float inv = 1.f / s;
+    for (int k = 0; k < kRegMax; ++k) { lg[k] = exp_<FAST>(lg[k] - m); s += lg[k]; }
+    const float inv = rcp_<FAST>(s);
     float d = 0.f, psum = 0.f;
     float t0 = -1.f, t1 = -1.f, t2 = -1.f, t3 = -1.f;  // running top-4, descending
 #pragma unroll
@@ -98,10 +104,11 @@ __device__ __forceinline__ void dgqp_hidden(const float* __restrict__ w, const f
     s_part[hg][ap + 32] = z1;
 }
 
+template <bool FAST>
 __device__ __forceinline__ float dgqp_quality(const float* __restrict__ w, const float (*s_part)[kTile], int a) {
     float z = w[kHidden * kStat + 2 * kHidden];  // b2
     z += ((s_part[0][a] + s_part[1][a]) + (s_part[2][a] + s_part[3][a])) + ((s_part[4][a] + s_part[5][a]) + (s_part[6][a] + s_part[7][a]));
-    const float q = sigmoidf_(z);
+    const float q = sigmoidf_<FAST>(z);
     return fminf(fmaxf(q, 1e-6f), 1.f - 1e-6f);  // clamp(1e-6, 1 - 1e-6), head.py:343
 }
 
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(256) gfl_decode_kernel(const __grid_constant__
             for (int k = 0; k < kRegMax; ++k) lg[k] = 0.f;
         }
         float dist;
-        side_stats(lg, dist, &s_stat[a][side * 5]);
+        side_stats<sizeof(T) == 2>(lg, dist, &s_stat[a][side * 5]);
         s_dist[side][a] = dist;
     }
     if (CLS_STAGE) {  // channel-contiguous class maps: coalesced read now, transposed use in phase 3
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(256) gfl_decode_kernel(const __grid_constant__
     __syncthreads();
     if (tid < kTile) {
         const int a = tid, pix = pix0 + a;
-        const float q = dgqp_quality(s_w, s_part, a);
+        const float q = dgqp_quality<sizeof(T) == 2>(s_w, s_part, a);
         s_q[a] = q;
         if (pix < HW) {
             const int py = pix / L.W, px = pix - py * L.W;
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(256) gfl_decode_kernel(const __grid_constant__
                 v = to_f(reinterpret_cast<const T*>(L.cls)[(int64_t)b * L.cs.n + (int64_t)c * L.cs.c + (int64_t)py * L.cs.h + (int64_t)px * L.cs.w]);
             }
             if (L.cb) v += __ldg(L.cb + c);
-            o[(int64_t)c * P.A + a] = sigmoidf_(v) * s_q[a];
+            o[(int64_t)c * P.A + a] = sigmoidf_<sizeof(T) == 2>(v) * s_q[a];
         }
     }
 }
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < kRegMax; ++k) lg[k] = a < ti.nvalid ? lg[k] + bias_b[side * kRegMax + k] : 0.f;
             float dist;
-            side_stats(lg, dist, &s_stat[a][side * 5]);
+            side_stats<sizeof(T) == 2>(lg, dist, &s_stat[a][side * 5]);
             s_dist[side][a] = dist;
         }
         __syncthreads();
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
         __syncthreads();
         if (tid < kTile) {
             const int a = tid;
-            s_q[a] = dgqp_quality(w, s_part, a);
+            s_q[a] = dgqp_quality<sizeof(T) == 2>(w, s_part, a);
             if (a < ti.nvalid) {
                 const int pix = ti.pix0 + a, py = pix / L.W, px = pix - py * L.W;
                 E.boxes[(int64_t)ti.b * P.A + L.a_off + pix] = decode_box(px, py, s_dist[0][a], s_dist[1][a], s_dist[2][a], s_dist[3][a], L.stride);
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                     float sc = 0.f;
                     bool pass = false;
                     if (av && c < nc) {
-                        sc = sigmoidf_(to_f(pc[c]) + bias_c[c]) * q;
+                        sc = sigmoidf_<sizeof(T) == 2>(to_f(pc[c]) + bias_c[c]) * q;
                         pass = sc > E.conf && (!E.class_keep || E.class_keep[c]);
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -402,7 +409,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                 if (av) {
                     const int c1 = min(nc, (qd + 1) * cq);
                     for (int c = qd * cq; c < c1; ++c) {  // first maximum inside the quarter
-                        const float sc = sigmoidf_(to_f(pc[c]) + bias_c[c]) * q;
+                        const float sc = sigmoidf_<sizeof(T) == 2>(to_f(pc[c]) + bias_c[c]) * q;
                         if (sc > best) { best = sc; bc = c; }
                     }
                 }

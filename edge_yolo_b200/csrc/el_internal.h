@@ -11,7 +11,7 @@ struct SelectState {            // per image, radix-select state of the max_nms 
 };
 
 struct NmsLayout {  // offsets into the caller's workspace
-    size_t counts, state, hist, keys, keys2, total;
+    size_t counts, state, hist, keys, keys2, handled, gkept, total;
     int64_t key_stride, key2_stride;
     int cap, cap2;
     bool select;

@@ -15,19 +15,19 @@ template <typename T> __device__ __forceinline__ float silu_f(float v) {
     else return v / (1.f + expf(-v));
 }
 
-constexpr int kEpRows = 4;
+constexpr int kEpRowsMax = 4;
 
 // thread <-> (channel vector, column) fixed; walks kEpRows rows.  grid = (col tiles, row chunks, images)
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bias_act_tiled(const T* x, Strides4 xs, const float* __restrict__ bias, const T* res, Strides4 rs, T* o,
-                                                      Strides4 os, T* o2, Strides4 os2, int split_cv, int CV, int cols_per_block, int H, int W) {
+                                                      Strides4 os, T* o2, Strides4 os2, int split_cv, int CV, int cols_per_block, int rows, int H, int W) {
     constexpr int V = Vec16<T>::N;
     const int xi = (int)threadIdx.x / CV, cv = (int)threadIdx.x - xi * CV, col = (int)blockIdx.x * cols_per_block + xi;
     if (xi >= cols_per_block || col >= W) return;
     float bv[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) bv[e] = bias ? __ldg(bias + cv * V + e) : 0.f;
-    const int r0 = (int)blockIdx.y * kEpRows, r1 = min(r0 + kEpRows, H);
+    const int r0 = (int)blockIdx.y * rows, r1 = min(r0 + rows, H);
     const int64_t n = blockIdx.z;
     const T* p = x + n * xs.n + (int64_t)r0 * xs.h + (int64_t)col * xs.w + cv * V;
     T* q = o + n * os.n + (int64_t)r0 * os.h + (int64_t)col * os.w + cv * V;
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) bias_act_tiled(const T* x, Strides4 xs, c
     }
     const T* pr = res ? res + n * rs.n + (int64_t)r0 * rs.h + (int64_t)col * rs.w + cv * V : nullptr;
 #pragma unroll
-    for (int r = 0; r < kEpRows; ++r) {
+    for (int r = 0; r < kEpRowsMax; ++r) {
         if (r0 + r >= r1) break;
         float f[V];
         unpack<T>(*reinterpret_cast<const uint4*>(p + (int64_t)r * xs.h), f);  // x may alias o
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) upsample2x_cat_tiled(const T* __restrict_
     constexpr int V = Vec16<T>::N;
     const int xi = (int)threadIdx.x / CV, cv = (int)threadIdx.x - xi * CV, col = (int)blockIdx.x * cols_per_block + xi;
     if (xi >= cols_per_block || col >= W) return;
-    const int r0 = (int)blockIdx.y * kEpRows, r1 = min(r0 + kEpRows, H);
+    const int r0 = (int)blockIdx.y * kEpRowsMax, r1 = min(r0 + kEpRowsMax, H);
     const int64_t n = blockIdx.z;
     T* q = o + n * os.n + (int64_t)col * os.w + cv * V;
     if (cv < CV1) {
@@ -218,8 +218,10 @@ extern "C" int el_bias_act_fwd(const void* x, const int64_t xs_[4], const float*
             const int64_t total = (int64_t)B * H * W * CV;
             if (CV <= 256 && B <= 65535) {
                     const int cpb = 256 / CV < W ? 256 / CV : W;
-                dim3 g((unsigned)ceil_div(W, cpb), (unsigned)ceil_div(H, kEpRows), (unsigned)B);
-                EL_BIAS_ACT(bias_act_tiled, <<<g, 256, 0, st>>>((const T*)x, xs, bias, (const T*)residual, rs, (T*)out, os, (T*)out2, os2, split / V, CV, cpb, H, W));
+                int rows = kEpRowsMax;
+                while (rows > 1 && ceil_div(W, cpb) * ceil_div(H, rows) * B < (int64_t)kSMs * 16) rows >>= 1;
+                dim3 g((unsigned)ceil_div(W, cpb), (unsigned)ceil_div(H, rows), (unsigned)B);
+                EL_BIAS_ACT(bias_act_tiled, <<<g, 256, 0, st>>>((const T*)x, xs, bias, (const T*)residual, rs, (T*)out, os, (T*)out2, os2, split / V, CV, cpb, rows, H, W));
             } else if (total < ((int64_t)1 << 32)) {
                 int grid = (int)(ceil_div(total, 256) < (int64_t)kSMs * 16 ? ceil_div(total, 256) : (int64_t)kSMs * 16);
                 EL_BIAS_ACT(bias_act_flat, <<<grid, 256, 0, st>>>((const T*)x, xs, bias, (const T*)residual, rs, (T*)out, os, (T*)out2, os2, split / V, CV, H, W, (uint32_t)total));
@@ -248,7 +250,7 @@ extern "C" int el_upsample2x_cat_fwd(const void* x, const int64_t xs_[4], const 
             (C1 + C2) / V > 256 || B > 65535)
             return EL_ERR_UNSUPPORTED;  // the engine only uses this on NHWC activations
         const int CV = (C1 + C2) / V, cpb = 256 / CV;
-        dim3 g((unsigned)ceil_div(W, cpb), (unsigned)ceil_div(H, kEpRows), (unsigned)B);
+        dim3 g((unsigned)ceil_div(W, cpb), (unsigned)ceil_div(H, kEpRowsMax), (unsigned)B);
         upsample2x_cat_tiled<T><<<g, 256, 0, st>>>((const T*)x, xs, (const T*)skip, ss, (T*)out, os, C1 / V, CV, cpb, H, W);
     });
     note_launches(1);

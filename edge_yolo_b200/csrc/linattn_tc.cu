@@ -34,7 +34,7 @@ constexpr uint32_t kOffA0 = 0, kOffB0 = kTileBytes, kOffA1 = 2 * kTileBytes, kOf
 constexpr uint32_t kOffQ = 4 * kTileBytes;            // raw q tile for the column statistics (128 rows x 128 B, chunk-swizzled)
 constexpr uint32_t kOffCtx = kOffQ + kTileBytes;      // ctx' bf16, 8 KiB
 constexpr uint32_t kOffStat = kOffCtx + kD * kD * 2;  // max[64], sum[64] fp32
-constexpr uint32_t kOffBar = kOffStat + 2 * kD * 4;   // 3 mbarriers + tmem address
+constexpr uint32_t kOffBar = kOffStat + 6 * kD * 4;   // (max, sum, 4 x 64 partials) then 3 mbarriers + tmem address
 constexpr uint32_t kSmemBytes = kOffBar + 64;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,6 +147,14 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
     const uint32_t idesc2 = umma_idesc(kFmt, 0, 0, 128, 64);   // both operands K-major
 
     // ------------------------------------------------------------------ pass 1: ctx = softmax_d(K)^T V, q column statistics
+    // The three token rows (K, V, Q: 24 x 16 B per thread) of chunk c+1 are requested while chunk c is being processed.
+    uint4 rk[8], rv[8], rq[8];
+    {
+        const bool v0 = tid < N;
+        load_row<T>(gk + (int64_t)tid * A.qn, v0, rk);
+        load_row<T>(gv + (int64_t)tid * A.qn, v0, rv);
+        load_row<T>(gq + (int64_t)tid * A.qn, v0, rq);
+    }
     for (int c = 0; c < n_chunks; ++c) {
         const int buf = c & 1;
         unsigned char* sA = sm + (buf ? kOffA1 : kOffA0);
@@ -154,14 +162,12 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
         const int n = c * kChunk + tid;
         const bool valid = n < N;
         if (c >= 2) mbar_wait(bar_g1[buf], ((c >> 1) - 1) & 1);  // the MMAs that read this buffer two chunks ago are done
-        uint4 r[8];
         float f[kD];
         // K: softmax over the 64 channels of this token, entirely in registers
-        load_row<T>(gk + (int64_t)n * A.qn, valid, r);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             float t8[8];
-            unpack<T>(r[g], t8);
+            unpack<T>(rk[g], t8);
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[8 * g + e] = t8[e];
         }
@@ -179,14 +185,19 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
             o.z = pack2<T>(f[8 * g + 4] * inv, f[8 * g + 5] * inv); o.w = pack2<T>(f[8 * g + 6] * inv, f[8 * g + 7] * inv);
             *reinterpret_cast<uint4*>(sA + g * 2048 + tid * 16) = o;
         }
-        // V: straight copy into the same layout
-        load_row<T>(gv + (int64_t)n * A.qn, valid, r);
+        // V: straight copy into the same layout; Q: raw tile for the per-channel max / sum over tokens (chunk index
+        // XOR-swizzled by the row: conflict-free for the row writes here and the column reads below)
 #pragma unroll
-        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(sB + g * 2048 + tid * 16) = r[g];
-        // Q: raw tile for the per-channel max / sum over tokens (chunk index XOR-swizzled by the row: conflict-free both ways)
-        load_row<T>(gq + (int64_t)n * A.qn, valid, r);
+        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(sB + g * 2048 + tid * 16) = rv[g];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(sm + kOffQ + tid * 128 + ((g ^ (tid & 7)) << 4)) = r[g];
+        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(sm + kOffQ + tid * 128 + ((g ^ (tid & 7)) << 4)) = rq[g];
+        if (c + 1 < n_chunks) {  // prefetch the next chunk's rows; they land while the MMAs and the statistics run
+            const int nn = n + kChunk;
+            const bool vn = nn < N;
+            load_row<T>(gk + (int64_t)nn * A.qn, vn, rk);
+            load_row<T>(gv + (int64_t)nn * A.qn, vn, rv);
+            load_row<T>(gq + (int64_t)nn * A.qn, vn, rq);
+        }
         proxy_fence();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
         if (tid == 0) {
@@ -200,18 +211,28 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
             }
             umma_commit(bar_g1[buf]);
         }
-        if (tid < kD) {  // online max / sum of exp over the tokens of this tile for channel `tid` (overlaps the MMAs)
+        {   // online max / sum of exp over this tile's tokens: thread = (channel, half of the tokens), halves merged through smem
             const int nvalid = min(kChunk, N - c * kChunk);
             const T* col = reinterpret_cast<const T*>(sm + kOffQ);
-            const int g = tid >> 3, e = tid & 7;
-            float m_old = s_max[tid], mx = m_old;
-            for (int t = 0; t < nvalid; ++t) mx = fmaxf(mx, to_f(col[t * 64 + ((g ^ (t & 7)) << 3) + e]));
+            const int ch = tid & 63, hf = tid >> 6, g = ch >> 3, e = ch & 7;
+            const int t0 = hf * 64, t1 = min(nvalid, t0 + 64);
+            float mx = -INFINITY;
+            for (int t = t0; t < t1; ++t) mx = fmaxf(mx, to_f(col[t * 64 + ((g ^ (t & 7)) << 3) + e]));
+            float* s_pm = reinterpret_cast<float*>(sm + kOffStat) + 2 * kD;  // [2][64] partial max, [2][64] partial sum
+            s_pm[hf * 64 + ch] = mx;
+            __syncthreads();
+            const float mt = fmaxf(fmaxf(s_pm[ch], s_pm[64 + ch]), s_max[ch]);
             float acc = 0.f;
-            for (int t = 0; t < nvalid; ++t) acc += __expf(to_f(col[t * 64 + ((g ^ (t & 7)) << 3) + e]) - mx);
-            s_sum[tid] = s_sum[tid] * (m_old == -INFINITY ? 0.f : __expf(m_old - mx)) + acc;
-            s_max[tid] = mx;
+            for (int t = t0; t < t1; ++t) acc += __expf(to_f(col[t * 64 + ((g ^ (t & 7)) << 3) + e]) - mt);
+            s_pm[128 + hf * 64 + ch] = acc;
+            __syncthreads();
+            if (tid < kD) {
+                const float m_old = s_max[tid];
+                s_sum[tid] = s_sum[tid] * (m_old == -INFINITY ? 0.f : __expf(m_old - mt)) + s_pm[128 + tid] + s_pm[192 + tid];
+                s_max[tid] = mt;
+            }
         }
-        __syncthreads();  // the q tile is reused by the next chunk
+        __syncthreads();  // the q tile and the partials are reused by the next chunk
     }
     // all of GEMM1 has landed in TMEM once the last commit fires (commits complete in order)
     {
@@ -242,22 +263,22 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
 
     // ------------------------------------------------------------------ pass 2: y = exp(q - max) ctx'
     T* gy = reinterpret_cast<T*>(A.y) + (int64_t)b * A.yb + head * kD;
+    load_row<T>(gq + (int64_t)tid * A.qn, tid < N, rq);
     for (int c = 0; c < n_chunks; ++c) {
         unsigned char* sP = sm + ((c & 1) ? kOffA1 : kOffA0);
         const int n = c * kChunk + tid;
         const bool valid = n < N;
-        uint4 r[8];
-        load_row<T>(gq + (int64_t)n * A.qn, valid, r);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             float t8[8];
-            unpack<T>(r[g], t8);
+            unpack<T>(rq[g], t8);
 #pragma unroll
             for (int e = 0; e < 8; ++e) t8[e] = valid ? __expf(t8[e] - s_max[8 * g + e]) : 0.f;
             uint4 o;
             o.x = pack2<T>(t8[0], t8[1]); o.y = pack2<T>(t8[2], t8[3]); o.z = pack2<T>(t8[4], t8[5]); o.w = pack2<T>(t8[6], t8[7]);
             *reinterpret_cast<uint4*>(sP + g * 2048 + tid * 16) = o;  // row = token, 16 B chunk g of the K dim
         }
+        if (c + 1 < n_chunks) load_row<T>(gq + (int64_t)(n + kChunk) * A.qn, n + kChunk < N, rq);  // next chunk's q rows (L2 hits)
         proxy_fence();
         __syncthreads();
         if (tid == 0) {

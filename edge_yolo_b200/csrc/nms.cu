@@ -263,43 +263,86 @@ struct SweepArgs {
     float* out; int32_t* out_count; int64_t* out_index;  // batched outputs
     int64_t* keep;                                       // nms_boxes output
     float* gkept;                                        // global kept list (5 x cap) when !SMEM_KEPT
+    const int* handled;                                  // per image: 1 = already done by nms_sweep_classes (may be NULL)
 };
+
+constexpr int kMaxBucketClasses = 2048;  // per-class kept lists are used up to this many classes
+
+// raw (un-offset) xyxy box + class of sorted candidate i; shared by the bounds pre-pass and the sweep
+struct Cand { float rx1, ry1, rx2, ry2, score, clsf; uint32_t idx; int cls; };
+__device__ __forceinline__ Cand load_cand(const SweepArgs& P, const unsigned long long* kb, int b, int i) {
+    Cand c;
+    const unsigned long long k = kb[i];
+    c.idx = ~(uint32_t)k;
+    c.score = __uint_as_float((uint32_t)(k >> 32));
+    const uint32_t a = c.idx / (uint32_t)P.nc;
+    c.cls = (int)(c.idx - a * (uint32_t)P.nc);
+    c.clsf = (float)c.cls;
+    const float* pb = P.box + (int64_t)b * P.sb + (int64_t)a * P.sa;
+    const float cx = __ldg(pb), cy = __ldg(pb + P.sk), w = __ldg(pb + 2 * P.sk), h = __ldg(pb + 3 * P.sk);
+    const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);  // xywh2xyxy, ops.py:416-433
+    c.rx1 = __fsub_rn(cx, hw); c.ry1 = __fsub_rn(cy, hh); c.rx2 = __fadd_rn(cx, hw); c.ry2 = __fadd_rn(cy, hh);
+    return c;
+}
 
 template <bool SMEM_KEPT, bool FROM_PRED>
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant__ SweepArgs P) {
-    extern __shared__ float s_kept[];  // [5][kcap] when SMEM_KEPT
+    extern __shared__ float s_kept[];  // [5][kcap] floats, then (FROM_PRED) next[kcap] and head[nb] ints
     __shared__ int s_nk[2];
+    __shared__ float s_red[2][kSweepThreads / 32];
+    __shared__ int s_bucketed;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (P.handled && P.handled[b]) return;
     const int n = seg_count(P.counts, P.st, b, P.cap);
     const int kcap = SMEM_KEPT ? P.max_det : P.cap;
     float* kx1 = SMEM_KEPT ? s_kept : P.gkept;
     float *ky1 = kx1 + kcap, *kx2 = ky1 + kcap, *ky2 = kx2 + kcap, *kar = ky2 + kcap;
     const unsigned long long* kb = P.keys + (int64_t)b * P.key_stride;
+    // Per-class kept lists (FROM_PRED only).  The reference separates classes by adding cls*max_wh to the coordinates
+    // (ops.py:289-295); when every candidate coordinate of this image lies in an interval narrower than max_wh, boxes of
+    // different classes are disjoint after the offset, so a candidate only has to be tested against kept boxes of its own
+    // class -- same result, ~nc times fewer IoU tests.  Otherwise (or class-agnostic) everything goes into one list.
+    int* s_next = reinterpret_cast<int*>(s_kept + 5 * (SMEM_KEPT ? kcap : 0));
+    int* s_head = s_next + kcap;
+    const int nb = (FROM_PRED && !P.agnostic && P.nc <= kMaxBucketClasses) ? P.nc : 1;
+    if (FROM_PRED) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (int i = tid; i < n; i += kSweepThreads) {
+            const Cand c = load_cand(P, kb, b, i);
+            lo = fminf(lo, fminf(fminf(c.rx1, c.ry1), fminf(c.rx2, c.ry2)));
+            hi = fmaxf(hi, fmaxf(fmaxf(c.rx1, c.ry1), fmaxf(c.rx2, c.ry2)));
+        }
+        lo = -warp_max(-lo); hi = warp_max(hi);
+        if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
+        for (int i = tid; i < nb; i += kSweepThreads) s_head[i] = -1;
+    }
     if (tid == 0) { s_nk[0] = 0; s_nk[1] = 0; }
     __syncthreads();
+    if (FROM_PRED && tid == 0) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (int w = 0; w < kSweepThreads / 32; ++w) { lo = fminf(lo, s_red[0][w]); hi = fmaxf(hi, s_red[1][w]); }
+        // strict: NaN / inf coordinates fall back to the single list
+        s_bucketed = (nb > 1 && (hi - lo) < P.max_wh && P.max_wh > 0.f) ? 1 : 0;
+    }
+    __syncthreads();
+    const bool bucketed = FROM_PRED && s_bucketed;
     int step = 0;
     bool done = false;
     for (int c0 = 0; c0 < n && !done; c0 += kSweepThreads) {
         const int i = c0 + tid;
         const bool valid = i < n;
-        float rx1 = 0.f, ry1 = 0.f, rx2 = 0.f, ry2 = 0.f, score = 0.f, clsf = 0.f;
+        Cand cd{};
         float ox1 = 0.f, oy1 = 0.f, ox2 = 0.f, oy2 = 0.f, area = 0.f;
-        uint32_t idx = 0;
+        int bucket = 0;
         if (valid) {
-            unsigned long long k = kb[i];
-            idx = ~(uint32_t)k;
             if (FROM_PRED) {
-                score = __uint_as_float((uint32_t)(k >> 32));
-                uint32_t a = idx / (uint32_t)P.nc, c = idx - a * (uint32_t)P.nc;
-                const float* pb = P.box + (int64_t)b * P.sb + (int64_t)a * P.sa;
-                float cx = __ldg(pb), cy = __ldg(pb + P.sk), w = __ldg(pb + 2 * P.sk), h = __ldg(pb + 3 * P.sk);
-                float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);  // xywh2xyxy, ops.py:416-433
-                rx1 = __fsub_rn(cx, hw); ry1 = __fsub_rn(cy, hh); rx2 = __fadd_rn(cx, hw); ry2 = __fadd_rn(cy, hh);
-                clsf = (float)c;
-                float off = P.agnostic ? 0.f : __fmul_rn(clsf, P.max_wh);  // ops.py:289
-                ox1 = __fadd_rn(rx1, off); oy1 = __fadd_rn(ry1, off); ox2 = __fadd_rn(rx2, off); oy2 = __fadd_rn(ry2, off);
+                cd = load_cand(P, kb, b, i);
+                const float off = P.agnostic ? 0.f : __fmul_rn(cd.clsf, P.max_wh);  // ops.py:289
+                ox1 = __fadd_rn(cd.rx1, off); oy1 = __fadd_rn(cd.ry1, off); ox2 = __fadd_rn(cd.rx2, off); oy2 = __fadd_rn(cd.ry2, off);
+                bucket = bucketed ? cd.cls : 0;
             } else {
-                const float4 bx = __ldg(reinterpret_cast<const float4*>(P.box) + idx);
+                cd.idx = ~(uint32_t)kb[i];
+                const float4 bx = __ldg(reinterpret_cast<const float4*>(P.box) + cd.idx);
                 ox1 = bx.x; oy1 = bx.y; ox2 = bx.z; oy2 = bx.w;
             }
             area = __fmul_rn(__fsub_rn(ox2, ox1), __fsub_rn(oy2, oy1));
@@ -310,8 +353,14 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
             if (c0 + sub * 32 >= n) break;  // no candidates left for the remaining warps (uniform)
             const int nk = s_nk[step & 1];
             if (warp >= sub && alive) {
-                for (int j = checked; j < nk; ++j) {
-                    if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
+                if (FROM_PRED) {  // newest-first list of this candidate's class; entries below `checked` were tested earlier
+                    for (int j = s_head[bucket]; j >= checked; j = s_next[j]) {
+                        if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
+                    }
+                } else {
+                    for (int j = checked; j < nk; ++j) {
+                        if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
+                    }
                 }
             }
             checked = nk;
@@ -328,14 +377,25 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
                     m = __ballot_sync(0xffffffffu, alive) & ~((2u << j) - 1u);
                 }
                 const int rank = nk + __popc(K & ((1u << lane) - 1u));
-                if (((K >> lane) & 1u) && rank < P.max_det) {
+                const bool keep = ((K >> lane) & 1u) && rank < P.max_det;
+                if (keep) {
                     kx1[rank] = ox1; ky1[rank] = oy1; kx2[rank] = ox2; ky2[rank] = oy2; kar[rank] = area;
                     if (FROM_PRED) {
                         float* o = P.out + ((int64_t)b * P.max_det + rank) * 6;
-                        o[0] = rx1; o[1] = ry1; o[2] = rx2; o[3] = ry2; o[4] = score; o[5] = clsf;
-                        if (P.out_index) P.out_index[(int64_t)b * P.max_det + rank] = (int64_t)idx;
+                        o[0] = cd.rx1; o[1] = cd.ry1; o[2] = cd.rx2; o[3] = cd.ry2; o[4] = cd.score; o[5] = cd.clsf;
+                        if (P.out_index) P.out_index[(int64_t)b * P.max_det + rank] = (int64_t)cd.idx;
                     } else {
-                        P.keep[rank] = (int64_t)idx;
+                        P.keep[rank] = (int64_t)cd.idx;
+                    }
+                }
+                if (FROM_PRED) {  // link the new keeps into their class lists in rank order (lists stay sorted newest-first)
+                    unsigned km = __ballot_sync(0xffffffffu, keep);
+                    while (km) {
+                        const int j = __ffs(km) - 1;
+                        km &= km - 1;
+                        // box data and next pointer are published before the head: warps still in their test loop may already see the entry
+                        if (lane == j) { s_next[rank] = s_head[bucket]; __threadfence_block(); s_head[bucket] = rank; }
+                        __syncwarp();
                     }
                 }
                 if (lane == 0) {
@@ -350,6 +410,167 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
     if (tid == 0) P.out_count[b] = s_nk[step & 1];
 }
 
+// ---- class-parallel sweep ---------------------------------------------------------------------------
+// When the class offset makes boxes of different classes disjoint (see nms_sweep), NMS decomposes into independent
+// per-class problems; only the final "first max_det in global score order" couples them.  One CTA per image:
+//   1. classes of the sorted candidates -> stable counting sort by class in shared memory (per-class lists in score order)
+//   2. each warp runs the greedy sweep of whole classes (32 candidates per step, kept boxes of the class in an L1-resident
+//      scratch), a class stops after max_det keeps (later ones can never reach the global top max_det)
+//   3. ordered block scan over the keep flags picks the first max_det survivors in global score order.
+// The serial chain is the longest class instead of the whole image.  Images that fail the disjointness test (or
+// class-agnostic calls) are left to nms_sweep, flagged through `handled`.
+constexpr int kClsThreads = 1024;
+constexpr int kClsMaxList = 512;  // longest per-class list one warp is allowed to walk
+
+__global__ void __launch_bounds__(kClsThreads) nms_sweep_classes(const __grid_constant__ SweepArgs P, float* __restrict__ gkept_all,
+                                                                 int* __restrict__ handled) {
+    extern __shared__ unsigned char s_raw[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = seg_count(P.counts, P.st, b, P.cap);
+    const int nb = P.nc;
+    uint16_t* s_cls = reinterpret_cast<uint16_t*>(s_raw);
+    uint16_t* s_list = s_cls + P.cap;
+    int* s_segcnt = reinterpret_cast<int*>(s_raw + (((size_t)4 * P.cap + 15) & ~(size_t)15));
+    int* s_off = s_segcnt + kClsThreads;  // nb + 1
+    uint8_t* s_keep = reinterpret_cast<uint8_t*>(s_off + nb + 1);
+    __shared__ float s_red[2][kClsThreads / 32];
+    __shared__ int s_wsum[kClsThreads / 32];
+    __shared__ int s_flag, s_running;
+    const unsigned long long* kb = P.keys + (int64_t)b * P.key_stride;
+
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = tid; i < n; i += kClsThreads) {
+        const Cand c = load_cand(P, kb, b, i);
+        lo = fminf(lo, fminf(fminf(c.rx1, c.ry1), fminf(c.rx2, c.ry2)));
+        hi = fmaxf(hi, fmaxf(fmaxf(c.rx1, c.ry1), fmaxf(c.rx2, c.ry2)));
+        s_cls[i] = (uint16_t)c.cls;
+        s_keep[i] = 0;
+    }
+    lo = -warp_max(-lo); hi = warp_max(hi);
+    if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
+    __syncthreads();
+    if (tid == 0) {
+        float l2 = INFINITY, h2 = -INFINITY;
+        for (int w = 0; w < kClsThreads / 32; ++w) { l2 = fminf(l2, s_red[0][w]); h2 = fmaxf(h2, s_red[1][w]); }
+        s_flag = (n == 0 || ((h2 - l2) < P.max_wh)) ? 1 : 0;  // NaN / inf coordinates fail the test -> serial kernel
+        handled[b] = s_flag;
+        s_running = 0;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    if (n == 0) { if (tid == 0) P.out_count[b] = 0; return; }
+
+    // ---- 1. stable counting sort by class: thread = (class c, segment of the candidate list)
+    const int S = kClsThreads / nb, seglen = (n + S - 1) / S;
+    const int c_t = tid % nb, seg_t = tid / nb;
+    const bool worker = tid < nb * S;
+    const int i0 = seg_t * seglen, i1 = min(n, i0 + seglen);
+    if (worker) {
+        int cnt = 0;
+        for (int i = i0; i < i1; ++i) cnt += (s_cls[i] == c_t);  // all lanes read the same element: broadcast
+        s_segcnt[seg_t * nb + c_t] = cnt;
+    }
+    __syncthreads();
+    if (tid < nb) {  // per class: exclusive prefix over the segments, total into s_off[c + 1]
+        int run = 0;
+        for (int sg = 0; sg < S; ++sg) { const int t = s_segcnt[sg * nb + tid]; s_segcnt[sg * nb + tid] = run; run += t; }
+        s_off[tid + 1] = run;
+        if (run > kClsMaxList) s_flag = 0;  // a long single-class chain is better served by the whole CTA (nms_sweep)
+    }
+    __syncthreads();
+    if (!s_flag) {
+        if (tid == 0) handled[b] = 0;
+        return;
+    }
+    if (warp == 0) {  // exclusive scan of the class totals (nb <= 1024): 32 classes per step
+        int carry = 0;
+        for (int base = 0; base < nb; base += 32) {
+            int v = base + lane < nb ? s_off[base + lane + 1] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (base + lane < nb) s_off[base + lane + 1] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_off[0] = 0;
+    }
+    __syncthreads();
+    if (worker) {
+        int pos = s_off[c_t] + s_segcnt[seg_t * nb + c_t];
+        for (int i = i0; i < i1; ++i)
+            if (s_cls[i] == c_t) s_list[pos++] = (uint16_t)i;
+    }
+    __syncthreads();
+
+    // ---- 2. per-class greedy sweeps, one warp per class
+    for (int c = warp; c < nb; c += kClsThreads / 32) {
+        const int base = s_off[c], cnt = s_off[c + 1] - base;
+        if (cnt == 0) continue;
+        float* gk = gkept_all + ((int64_t)b * P.cap + base) * 5;  // this class's kept boxes: [k][x1,y1,x2,y2,area]
+        const float off = __fmul_rn((float)c, P.max_wh);            // ops.py:289
+        int kc = 0;
+        for (int g0 = 0; g0 < cnt && kc < P.max_det; g0 += 32) {
+            const int li = g0 + lane;
+            const bool valid = li < cnt;
+            int i = 0;
+            float ox1 = 0.f, oy1 = 0.f, ox2 = 0.f, oy2 = 0.f, area = 0.f;
+            if (valid) {
+                i = s_list[base + li];
+                const Cand cd = load_cand(P, kb, b, i);
+                ox1 = __fadd_rn(cd.rx1, off); oy1 = __fadd_rn(cd.ry1, off); ox2 = __fadd_rn(cd.rx2, off); oy2 = __fadd_rn(cd.ry2, off);
+                area = __fmul_rn(__fsub_rn(ox2, ox1), __fsub_rn(oy2, oy1));
+            }
+            bool alive = valid;
+            for (int j = 0; j < kc; ++j) {  // kept boxes of this class (written by this warp, warp-uniform address)
+                if (!__any_sync(0xffffffffu, alive)) break;
+                const float* kj = gk + j * 5;
+                if (alive && iou_gt(kj[0], kj[1], kj[2], kj[3], kj[4], ox1, oy1, ox2, oy2, area, P.thr)) alive = false;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, alive), K = 0;
+            while (m) {  // greedy resolution inside the group
+                const int j = __ffs(m) - 1;
+                K |= 1u << j;
+                float jx1 = __shfl_sync(0xffffffffu, ox1, j), jy1 = __shfl_sync(0xffffffffu, oy1, j);
+                float jx2 = __shfl_sync(0xffffffffu, ox2, j), jy2 = __shfl_sync(0xffffffffu, oy2, j);
+                float jar = __shfl_sync(0xffffffffu, area, j);
+                if (alive && lane > j && iou_gt(jx1, jy1, jx2, jy2, jar, ox1, oy1, ox2, oy2, area, P.thr)) alive = false;
+                m = __ballot_sync(0xffffffffu, alive) & ~((2u << j) - 1u);
+            }
+            const int rank = kc + __popc(K & ((1u << lane) - 1u));
+            if (((K >> lane) & 1u) && rank < P.max_det) {
+                float* kj = gk + rank * 5;
+                kj[0] = ox1; kj[1] = oy1; kj[2] = ox2; kj[3] = oy2; kj[4] = area;
+                s_keep[i] = 1;
+            }
+            kc += __popc(K);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. first max_det survivors in global (sorted) order
+    for (int c0 = 0; c0 < n; c0 += kClsThreads) {
+        const int i = c0 + tid;
+        const bool k = i < n && s_keep[i];
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) s_wsum[warp] = __popc(m);
+        __syncthreads();
+        int pre = s_running, tot = 0;
+        for (int w = 0; w < kClsThreads / 32; ++w) { const int v = s_wsum[w]; if (w < warp) pre += v; tot += v; }
+        const int rank = pre + __popc(m & ((1u << lane) - 1u));
+        if (k && rank < P.max_det) {
+            const Cand cd = load_cand(P, kb, b, i);
+            float* o = P.out + ((int64_t)b * P.max_det + rank) * 6;
+            o[0] = cd.rx1; o[1] = cd.ry1; o[2] = cd.rx2; o[3] = cd.ry2; o[4] = cd.score; o[5] = cd.clsf;
+            if (P.out_index) P.out_index[(int64_t)b * P.max_det + rank] = (int64_t)cd.idx;
+        }
+        __syncthreads();
+        if (tid == 0) s_running += tot;
+        __syncthreads();
+        if (s_running >= P.max_det) break;
+    }
+    if (tid == 0) P.out_count[b] = s_running < P.max_det ? s_running : P.max_det;
+}
 
 NmsLayout nms_layout(int B, int nc, int A, int multi, int max_nms) {
     NmsLayout L{};
@@ -374,6 +595,9 @@ NmsLayout nms_layout(int B, int nc, int A, int multi, int max_nms) {
     }
     L.keys = off; off = al(off + sizeof(unsigned long long) * L.key_stride * B);
     L.keys2 = off; off = al(off + sizeof(unsigned long long) * L.key2_stride * B);
+    const int sweep_cap = L.select ? L.cap2 : L.cap;  // candidates the sweep can see per image
+    L.handled = off; off = al(off + sizeof(int) * B);
+    L.gkept = off; off = al(off + sizeof(float) * 5 * (size_t)sweep_cap * B);  // kept boxes of the class-parallel sweep
     L.total = off;
     return L;
 }
@@ -456,9 +680,20 @@ int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc
     P.nc = nc; P.max_wh = max_wh; P.agnostic = agnostic;
     P.thr = threshold_round_down(iou); P.max_det = max_det;
     P.out = out; P.out_count = out_count; P.out_index = out_index;
-    size_t sm = (size_t)5 * max_det * sizeof(float);
+    // class-parallel sweep first (per-class independence needs class offsets and a class count that fits the CTA)
+    const size_t sm_cls = (((size_t)4 * P.cap + 15) & ~(size_t)15) + sizeof(int) * (kClsThreads + nc + 1) + (size_t)P.cap + 16;
+    const bool try_classes = !agnostic && nc > 1 && nc <= kClsThreads && P.cap <= 65535 && sm_cls <= 200 * 1024;
+    int* handled = (int*)(ws + L.handled);
+    if (try_classes) {
+        if (sm_cls > 48 * 1024) cudaFuncSetAttribute(nms_sweep_classes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cls);
+        nms_sweep_classes<<<B, kClsThreads, sm_cls, s>>>(P, (float*)(ws + L.gkept), handled);
+        note_launches(1);
+        P.handled = handled;
+    }
+    const int nb = (!agnostic && nc <= kMaxBucketClasses) ? nc : 1;
+    size_t sm = (size_t)6 * max_det * sizeof(float) + (size_t)nb * sizeof(int);
     if (sm > 48 * 1024) cudaFuncSetAttribute(nms_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    nms_sweep<true, true><<<B, kSweepThreads, sm, s>>>(P);
+    nms_sweep<true, true><<<B, kSweepThreads, sm, s>>>(P);  // images the class-parallel kernel declined (or all of them)
     note_launches(1);
     return check_launch();
 }

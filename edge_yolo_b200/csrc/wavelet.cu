@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) ingest_u8_kernel(const uint8_t* __restric
 // division, bilinear column weight and band pointer is computed once; the thread then walks kRows
 // rows with pointer increments only.  grid = (column tiles, row chunks, images).
 // =============================================================================================
-constexpr int kRows = 8;
+constexpr int kRowsMax = 8;  // rows walked per thread; the host shrinks it until the grid fills the 148 SMs several times over
 
 struct TileMap {
     int cv, col;      // this thread's channel vector and column
@@ -395,12 +395,12 @@ __device__ __forceinline__ TileMap tile_map(int CV, int cols_per_block, int n_co
 
 template <typename T>
 __global__ void __launch_bounds__(256) dwt_fwd_tiled(const T* __restrict__ x, Strides4 xs, T* __restrict__ o, int64_t ob, Strides4 os, int CV,
-                                                     int cols_per_block, int H2, int W2) {
+                                                     int cols_per_block, int rows, int H2, int W2) {
     constexpr int V = Vec16<T>::N;
     const TileMap m = tile_map(CV, cols_per_block, W2);
     if (!m.active) return;
     const float k = kHaar;
-    const int i0 = (int)blockIdx.y * kRows, i1 = min(i0 + kRows, H2);
+    const int i0 = (int)blockIdx.y * rows, i1 = min(i0 + rows, H2);
     const int64_t n = blockIdx.z;
     const T* p = x + n * xs.n + (int64_t)(2 * i0) * xs.h + (int64_t)(2 * m.col) * xs.w + m.cv * V;
     T* q = o + n * os.n + (int64_t)i0 * os.h + (int64_t)m.col * os.w + m.cv * V;
@@ -422,13 +422,31 @@ __global__ void __launch_bounds__(256) dwt_fwd_tiled(const T* __restrict__ x, St
     }
 }
 
+constexpr int kMergeRows = 16;
+
 template <typename T>
 __global__ void __launch_bounds__(256) merge_fwd_tiled(const T* __restrict__ b, Strides4 bs, BandPtrs bands, const float* __restrict__ alpha,
-                                                       T* __restrict__ out, Strides4 os, int c, int CV, int cols_per_block, int H, int W, int h, int w) {
+                                                       T* __restrict__ out, Strides4 os, int c, int CV, int cols_per_block, int rows, int H, int W,
+                                                       int h, int w) {
     constexpr int V = Vec16<T>::N;
+    // per-block tables: the four band weights and the vertical taps of this block's rows (both uniform over the block)
+    __shared__ float s_w[4];
+    __shared__ int s_ya[kMergeRows], s_yb[kMergeRows];
+    __shared__ float s_ly[kMergeRows];
+    const int y0b = (int)blockIdx.y * rows, y1b = min(y0b + rows, H);
+    if (threadIdx.x == 0) {
+        float wt[4];
+        band_weights(alpha, wt);
+        s_w[0] = wt[0]; s_w[1] = wt[1]; s_w[2] = wt[2]; s_w[3] = wt[3];
+    }
+    if ((int)threadIdx.x < y1b - y0b) {
+        int ya, yb; float ly;
+        bilin_src(y0b + threadIdx.x, (float)h / (float)H, h, ya, yb, ly);
+        s_ya[threadIdx.x] = ya; s_yb[threadIdx.x] = yb; s_ly[threadIdx.x] = ly;
+    }
+    __syncthreads();
     const TileMap m = tile_map(CV, cols_per_block, W);
     if (!m.active) return;
-    const int y0b = (int)blockIdx.y * kRows, y1b = min(y0b + kRows, H);
     const int64_t n = blockIdx.z;
     const int ch = m.cv * V;
     T* q = out + n * os.n + (int64_t)y0b * os.h + (int64_t)m.col * os.w + ch;
@@ -439,40 +457,62 @@ __global__ void __launch_bounds__(256) merge_fwd_tiled(const T* __restrict__ b, 
         return;
     }
     const int half = c / 2, seg = (ch - c) / half, cc = (ch - c) - seg * half;
-    float wt[4];
-    band_weights(alpha, wt);
-    const float wb = seg == 0 ? wt[0] : seg == 1 ? wt[1] : seg == 2 ? wt[2] : wt[3];
-    const float sh = (float)h / (float)H, swd = (float)w / (float)W;
     int x0, x1; float lx;
-    bilin_src(m.col, swd, w, x0, x1, lx);
+    bilin_src(m.col, (float)w / (float)W, w, x0, x1, lx);
     const Strides4 s = bands.s[seg];
     const T* p0 = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + cc + (int64_t)x0 * s.w;
     const T* p1 = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + cc + (int64_t)x1 * s.w;
     const float wx0 = 1.f - lx;
-    for (int y = y0b; y < y1b; ++y, q += os.h) {
-        int ya, yb; float ly;
-        bilin_src(y, sh, h, ya, yb, ly);
-        float v00[V], v01[V], v10[V], v11[V], r[V];
-        // each band pixel feeds ~4 output pixels: keep it in L1
-        unpack<T>(ldg_cached(p0 + (int64_t)ya * s.h), v00);
-        unpack<T>(ldg_cached(p1 + (int64_t)ya * s.h), v01);
-        unpack<T>(ldg_cached(p0 + (int64_t)yb * s.h), v10);
-        unpack<T>(ldg_cached(p1 + (int64_t)yb * s.h), v11);
-        const float wy0 = 1.f - ly;
+    // Horizontally blended source rows are cached in registers: consecutive output rows share their two source rows
+    // (for the exact 2x case each source row pair serves two output rows), so a row costs one pair of 16 B loads
+    // instead of four and half the unpack work.  The row index is block-uniform: no divergence.
+    int ca = -1, cb = -1;
+    float ha[V], hb[V];
+    auto hrow = [&](int yy, float (&dst)[V]) {
+        float v0[V], v1[V];
+        unpack<T>(ldg_cached(p0 + (int64_t)yy * s.h), v0);  // each band pixel feeds ~4 output pixels: keep it in L1
+        unpack<T>(ldg_cached(p1 + (int64_t)yy * s.h), v1);
 #pragma unroll
-        for (int e = 0; e < V; ++e) r[e] = (wy0 * (wx0 * v00[e] + lx * v01[e]) + ly * (wx0 * v10[e] + lx * v11[e])) * wb;
+        for (int e = 0; e < V; ++e) dst[e] = wx0 * v0[e] + lx * v1[e];
+    };
+    const float wb = s_w[seg];
+    for (int y = y0b; y < y1b; ++y, q += os.h) {
+        const int ya = s_ya[y - y0b], yb = s_yb[y - y0b];
+        const float ly = s_ly[y - y0b];
+        if (ya != ca) {
+            if (ya == cb) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) ha[e] = hb[e];
+            } else {
+                hrow(ya, ha);
+            }
+            ca = ya;
+        }
+        if (yb != cb) {
+            if (yb == ca) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) hb[e] = ha[e];
+            } else {
+                hrow(yb, hb);
+            }
+            cb = yb;
+        }
+        const float wy0 = 1.f - ly;
+        float r[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) r[e] = (wy0 * ha[e] + ly * hb[e]) * wb;
         stg_stream(q, pack<T>(r));
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) gated_tiled(const T* b, Strides4 bs, const T* __restrict__ y, Strides4 ys, const float* __restrict__ gamma, T* o,
-                                                   Strides4 os, T* o2, Strides4 os2, int CV, int cols_per_block, int H, int W) {
+                                                   Strides4 os, T* o2, Strides4 os2, int CV, int cols_per_block, int rows, int H, int W) {
     constexpr int V = Vec16<T>::N;
     const TileMap m = tile_map(CV, cols_per_block, W);
     if (!m.active) return;
     const float g = tanhf(__ldg(gamma));
-    const int r0 = (int)blockIdx.y * kRows, r1 = min(r0 + kRows, H);
+    const int r0 = (int)blockIdx.y * rows, r1 = min(r0 + rows, H);
     const int64_t n = blockIdx.z;
     const T* pb = b + n * bs.n + (int64_t)r0 * bs.h + (int64_t)m.col * bs.w + m.cv * V;
     const T* py = y + n * ys.n + (int64_t)r0 * ys.h + (int64_t)m.col * ys.w + m.cv * V;
@@ -491,9 +531,12 @@ __global__ void __launch_bounds__(256) gated_tiled(const T* b, Strides4 bs, cons
     }
 }
 
-static inline dim3 tile_grid(int CV, int n_cols, int n_rows, int B, int& cols_per_block) {
-    cols_per_block = 256 / CV;
-    return dim3((unsigned)ceil_div(n_cols, cols_per_block), (unsigned)ceil_div(n_rows, kRows), (unsigned)B);
+static inline dim3 tile_grid(int CV, int n_cols, int n_rows, int B, int& cols_per_block, int& rows, int rows_max = kRowsMax, int rows_min = 1) {
+    cols_per_block = 256 / CV < n_cols ? 256 / CV : n_cols;
+    const int64_t col_tiles = ceil_div(n_cols, cols_per_block);
+    rows = rows_max;
+    while (rows > rows_min && col_tiles * ceil_div(n_rows, rows) * B < (int64_t)kSMs * 16) rows >>= 1;  // small maps: more, shorter threads
+    return dim3((unsigned)col_tiles, (unsigned)ceil_div(n_rows, rows), (unsigned)B);
 }
 
 // grid for a streaming grid-stride kernel: enough CTAs to cover `total`, capped at a multiple
@@ -520,9 +563,9 @@ extern "C" int el_dwt_haar_fwd(const void* x, const int64_t xs_[4], void* bands,
         constexpr int V = Vec16<T>::N;
         if (channel_vectorisable<T>(x, xs, C) && channel_vectorisable<T>(bands, os, C) && ob % V == 0) {
             if (C / V <= 256 && B <= 65535) {
-                int cpb;
-                dim3 g = tile_grid(C / V, W2, H2, B, cpb);
-                dwt_fwd_tiled<T><<<g, 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C / V, cpb, H2, W2);
+                int cpb, rows;
+                dim3 g = tile_grid(C / V, W2, H2, B, cpb, rows);
+                dwt_fwd_tiled<T><<<g, 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C / V, cpb, rows, H2, W2);
             } else {
                 int64_t total = (int64_t)B * H2 * W2 * (C / V);
                 dwt_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C / V, H2, W2, total);
@@ -572,9 +615,9 @@ extern "C" int el_wave_merge_fwd(const void* b, const int64_t bs_[4], const void
         for (int i = 0; i < 4; ++i) vec = vec && channel_vectorisable<T>(bp.p[i], bp.s[i], c / 2);
         if (vec) {
             if (3 * c / V <= 256 && B <= 65535) {
-                int cpb;
-                dim3 g = tile_grid(3 * c / V, W, H, B, cpb);
-                merge_fwd_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, 3 * c / V, cpb, H, W, h, w);
+                int cpb, rows;
+                dim3 g = tile_grid(3 * c / V, W, H, B, cpb, rows, kMergeRows, 4);
+                merge_fwd_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, 3 * c / V, cpb, rows, H, W, h, w);
             } else {
                 int64_t total = (int64_t)B * H * W * (3 * c / V);
                 merge_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, H, W, h, w, total);
@@ -651,9 +694,9 @@ extern "C" int el_gated_residual_fwd(const void* b, const int64_t bs_[4], const 
             return EL_ERR_UNSUPPORTED;  // the second destination is an engine-only (NHWC) feature
         if (channel_vectorisable<T>(b, bs, C) && channel_vectorisable<T>(y, ys, C) && channel_vectorisable<T>(out, os, C)) {
             if (C / V <= 256 && B <= 65535) {
-                int cpb;
-                dim3 g = tile_grid(C / V, W, H, B, cpb);
-                gated_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, (T*)out2, os2, C / V, cpb, H, W);
+                int cpb, rows;
+                dim3 g = tile_grid(C / V, W, H, B, cpb, rows);
+                gated_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, (T*)out2, os2, C / V, cpb, rows, H, W);
             } else {
                 int64_t total = (int64_t)B * H * W * (C / V);
                 gated_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, (const T*)y, ys, gamma, (T*)out, os, C / V, H, W, total);
