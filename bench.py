@@ -175,13 +175,32 @@ def profile_kernels(pred, a, iters=10):
             return type(v)(clone_arg(t) for t in v)
         return v
 
+    from edge_yolo_b200 import _lib
+
+    # the fused detect call is a chain of three kernels groups; time them separately (emit is HBM-bound, sort / sweep latency-bound)
+    staged = []
+    for name, fn, args, kw, nbytes in calls:
+        if name != "gfl_detect":
+            staged.append((name, fn, args, kw, nbytes, 7))
+            continue
+        boxes, clss = args[0], args[1]
+        nA = sum(t.shape[0] * t.shape[2] * t.shape[3] for t in boxes)
+        kw = dict(kw, workspace=torch.empty(1 << 30, dtype=torch.uint8, device=pred.device))  # persistent across the staged calls
+        staged.append(("gfl_decode_emit", fn, args, kw, sum(t.numel() * e(t) for t in boxes + clss) + nA * 16, 1))
+        staged.append(("nms_sort", fn, args, kw, 0, 2))
+        staged.append(("nms_sweep", fn, args, kw, 0, 4))
+
     per = {}
     with torch.no_grad():
-        for name, fn, args, kw, nbytes in calls:
+        for name, fn, args, kw, nbytes, stages in staged:
+            _lib.lib().el_debug_set_detect_stages(7)
+            if stages != 7:
+                fn(*args, **kw)  # leaves emitted + sorted keys in place for the partial runs
             # R rotating copies of the inputs (>= 512 MB in total) so no launch finds its operands in L2; all R launches are
             # enqueued behind a ~1 ms spin so that they run back to back, bracketed by ONE event pair on the launching stream
-            R = int(min(48, max(2, (512 << 20) // max(nbytes, 1))))
-            sets = [(args, kw)] + [(tuple(clone_arg(v) for v in args), kw) for _ in range(R - 1)]
+            R = int(min(48, max(2, (512 << 20) // max(nbytes, 1)))) if stages in (7, 1) else 4
+            sets = [(args, kw)] + ([(tuple(clone_arg(v) for v in args), kw) for _ in range(R - 1)] if stages in (7, 1) else [(args, kw)] * (R - 1))
+            _lib.lib().el_debug_set_detect_stages(stages)
             ts = []
             for it in range(iters // 2 + 1):
                 flush.zero_()
@@ -203,6 +222,7 @@ def profile_kernels(pred, a, iters=10):
             d["seconds"] += t
             first = args[0][0] if isinstance(args[0], (list, tuple)) else args[0]
             d["sites"].append({"shape": list(first.shape), "MB": round(nbytes / 1e6, 2), "us": round(t * 1e6, 2), "gbs": round(nbytes / t / 1e9, 1)})
+        _lib.lib().el_debug_set_detect_stages(7)
     for d in per.values():
         d["gbs"] = d["bytes"] / d["seconds"] / 1e9
         d["us"] = d["seconds"] * 1e6

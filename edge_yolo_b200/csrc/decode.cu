@@ -559,7 +559,8 @@ extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* 
     if (workspace_bytes < box_off + (size_t)B * P.A * sizeof(float4)) return EL_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
-    nms_prepare(L, ws, st);
+    const bool do_emit = g_detect_stages & 1;
+    if (do_emit) nms_prepare(L, ws, st);
     EmitArgs E{conf, class_keep, (unsigned long long*)(ws + L.keys), L.key_stride, (int*)(ws + L.counts), (float4*)(ws + box_off), B};
     const size_t sm = emit_smem_bytes(nc, esz);
     const int total = B * P.tiles_per_image;
@@ -570,12 +571,14 @@ extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* 
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);               \
         kern<<<grid, 256, sm, st>>>(P, E);                                                              \
     } while (0)
-    EL_DISPATCH_DTYPE(dtype, {
-        if (multi) EL_LAUNCH_EMIT(true);
-        else EL_LAUNCH_EMIT(false);
-    });
+    if (do_emit) {
+        EL_DISPATCH_DTYPE(dtype, {
+            if (multi) EL_LAUNCH_EMIT(true);
+            else EL_LAUNCH_EMIT(false);
+        });
+        note_launches(1);
+    }
 #undef EL_LAUNCH_EMIT
-    note_launches(1);
     if (int e = check_launch()) return e;
     return nms_finish(L, ws, BoxSource{(const float*)(ws + box_off), (int64_t)P.A * 4, 4, 1}, B, nc, iou, agnostic, max_det, max_nms, max_wh, out,
                       out_count, out_index, st);

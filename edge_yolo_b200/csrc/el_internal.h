@@ -29,4 +29,7 @@ int nms_finish(const NmsLayout& L, void* ws, BoxSource src, int B, int nc, doubl
 
 constexpr int kMaxDetSmem = 4096;
 
+// measurement aid (el_debug_set_detect_stages): bit0 = candidate emit, bit1 = select + sort, bit2 = sweep
+extern int g_detect_stages;
+
 }  // namespace el

@@ -438,13 +438,27 @@ __global__ void __launch_bounds__(kClsThreads) nms_sweep_classes(const __grid_co
     __shared__ int s_flag, s_running;
     const unsigned long long* kb = P.keys + (int64_t)b * P.key_stride;
 
+    // cheap test first: class histogram from the keys alone; a dominant class (long chain) is left to nms_sweep
+    for (int i = tid; i <= nb; i += kClsThreads) s_off[i] = 0;
+    if (tid == 0) { s_flag = 1; s_running = 0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += kClsThreads) {
+        const uint32_t idx = ~(uint32_t)kb[i];
+        const int c = (int)(idx % (uint32_t)P.nc);
+        s_cls[i] = (uint16_t)c;
+        s_keep[i] = 0;
+        if (atomicAdd(&s_off[c + 1], 1) + 1 > kClsMaxList) s_flag = 0;
+    }
+    __syncthreads();
+    if (!s_flag) {
+        if (tid == 0) handled[b] = 0;
+        return;
+    }
     float lo = INFINITY, hi = -INFINITY;
     for (int i = tid; i < n; i += kClsThreads) {
         const Cand c = load_cand(P, kb, b, i);
         lo = fminf(lo, fminf(fminf(c.rx1, c.ry1), fminf(c.rx2, c.ry2)));
         hi = fmaxf(hi, fmaxf(fmaxf(c.rx1, c.ry1), fmaxf(c.rx2, c.ry2)));
-        s_cls[i] = (uint16_t)c.cls;
-        s_keep[i] = 0;
     }
     lo = -warp_max(-lo); hi = warp_max(hi);
     if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
@@ -454,7 +468,6 @@ __global__ void __launch_bounds__(kClsThreads) nms_sweep_classes(const __grid_co
         for (int w = 0; w < kClsThreads / 32; ++w) { l2 = fminf(l2, s_red[0][w]); h2 = fmaxf(h2, s_red[1][w]); }
         s_flag = (n == 0 || ((h2 - l2) < P.max_wh)) ? 1 : 0;  // NaN / inf coordinates fail the test -> serial kernel
         handled[b] = s_flag;
-        s_running = 0;
     }
     __syncthreads();
     if (!s_flag) return;
@@ -475,13 +488,8 @@ __global__ void __launch_bounds__(kClsThreads) nms_sweep_classes(const __grid_co
         int run = 0;
         for (int sg = 0; sg < S; ++sg) { const int t = s_segcnt[sg * nb + tid]; s_segcnt[sg * nb + tid] = run; run += t; }
         s_off[tid + 1] = run;
-        if (run > kClsMaxList) s_flag = 0;  // a long single-class chain is better served by the whole CTA (nms_sweep)
     }
     __syncthreads();
-    if (!s_flag) {
-        if (tid == 0) handled[b] = 0;
-        return;
-    }
     if (warp == 0) {  // exclusive scan of the class totals (nb <= 1024): 32 classes per step
         int carry = 0;
         for (int base = 0; base < nb; base += 32) {
@@ -649,6 +657,8 @@ extern "C" int el_nms_workspace_bytes(int B, int nc, int A, int multi_label, int
 
 namespace el {
 
+int g_detect_stages = 7;
+
 void nms_prepare(const NmsLayout& L, void* ws, cudaStream_t s) { cudaMemsetAsync(ws, 0, L.keys, s); }  // counts, select state, histograms
 
 int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc, double iou, int agnostic, int max_det, int max_nms, float max_wh,
@@ -660,7 +670,12 @@ int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc
     unsigned long long* keys = (unsigned long long*)(ws + L.keys);
     unsigned long long* keys2 = (unsigned long long*)(ws + L.keys2);
     SweepArgs P{};
-    if (L.select) {
+    const bool do_sort = g_detect_stages & 2, do_sweep = g_detect_stages & 4;
+    if (L.select && !do_sort) {
+        P.keys = keys2; P.key_stride = L.key2_stride; P.counts = nullptr; P.st = st; P.cap = L.cap2;
+    } else if (!do_sort) {
+        P.keys = keys; P.key_stride = L.key_stride; P.counts = counts; P.st = nullptr; P.cap = L.cap;
+    } else if (L.select) {
         init_select<<<(B + 127) / 128, 128, 0, s>>>(st, B, max_nms);
         int hb = (int)ceil_div(L.cap, 256 * 16);
         if (hb > 64) hb = 64;
@@ -680,6 +695,7 @@ int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc
     P.nc = nc; P.max_wh = max_wh; P.agnostic = agnostic;
     P.thr = threshold_round_down(iou); P.max_det = max_det;
     P.out = out; P.out_count = out_count; P.out_index = out_index;
+    if (!do_sweep) return check_launch();
     // class-parallel sweep first (per-class independence needs class offsets and a class count that fits the CTA)
     const size_t sm_cls = (((size_t)4 * P.cap + 15) & ~(size_t)15) + sizeof(int) * (kClsThreads + nc + 1) + (size_t)P.cap + 16;
     const bool try_classes = !agnostic && nc > 1 && nc <= kClsThreads && P.cap <= 65535 && sm_cls <= 200 * 1024;
@@ -756,3 +772,5 @@ extern "C" int el_nms_boxes(const float* boxes, const float* scores, int n, doub
     note_launches(2);  // keys + sweep
     return check_launch();
 }
+
+extern "C" void el_debug_set_detect_stages(int mask) { el::g_detect_stages = mask & 7; }

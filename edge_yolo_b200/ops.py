@@ -273,7 +273,7 @@ def gfl_decode(boxes, clss, dgqp, strides, want_quality: bool = False, bias=None
 
 
 def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, multi_label=False, agnostic=False, classes=None,
-               max_det=300, max_nms=30000, max_wh=7680.0, bias=None):
+               max_det=300, max_nms=30000, max_wh=7680.0, bias=None, workspace=None):
     """Fused decode + NMS of the engine path: same inputs as `gfl_decode`, same outputs as `nms_batched`
     (out (B, max_det, 6), count (B) int32); the dense (B, 4+nc, A) tensor is never written.  Falls back to
     `gfl_decode` + `nms_batched` (identical results) when the head maps are not dense NHWC."""
@@ -290,7 +290,7 @@ def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, mult
     need = c_size_t()
     check(L.el_gfl_detect_workspace_bytes(B, nc, A, int(bool(multi_label)), int(max_nms), ctypes.byref(need)), "el_gfl_detect_workspace_bytes")
     dev = boxes[0].device
-    ws = torch.empty(need.value, device=dev, dtype=torch.uint8)
+    ws = workspace if workspace is not None and workspace.numel() >= need.value else torch.empty(need.value, device=dev, dtype=torch.uint8)
     out = torch.empty((B, max_det, 6), device=dev, dtype=torch.float32)
     cnt = torch.empty((B,), device=dev, dtype=torch.int32)
     keep = None

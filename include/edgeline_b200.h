@@ -46,6 +46,9 @@ int el_last_cuda_error(void);
 /* Number of kernels this library has enqueued so far in the process (measurement aid: bench.py
  * reports the per-step delta as `gpu_launches`). */
 unsigned long long el_launch_count(void);
+/* Measurement aid for bench.py: run only some stages of el_gfl_detect_fwd / el_nms_batched's tail so that they can be
+ * timed separately (bit0 candidate emit, bit1 select + sort, bit2 sweep; default 7 = everything).  Process-global. */
+void el_debug_set_detect_stages(int mask);
 
 /* ---- a1. Haar analysis: _PywtDWT2D.forward, nn/modules/block.py:3619-3642 -------------------
  * x (B,C,H,W) -> bands (4,B,C,H/2,W/2) in the order LL,LH,HL,HH; xs = {sn,sc,sh,sw},
