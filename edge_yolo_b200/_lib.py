@@ -34,6 +34,9 @@ _SIGNATURES = {
                           + [c_int] * 7 + [c_void_p]),
     "el_gated_residual_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_void_p, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int,
                                       c_void_p]),
+    "el_linattn_bwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_void_p]),
+    "el_gated_residual_bwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_void_p, c_void_p, I64P, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p]),
     "el_linattn_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_void_p]),
     "el_gfl_decode_fwd": (c_int, [c_int, POINTER(c_void_p), I64P, POINTER(c_void_p), I64P, POINTER(c_int32), POINTER(c_float),
                                   POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),

@@ -356,6 +356,31 @@ __global__ void __launch_bounds__(256) gated_generic(const T* b, Strides4 bs, co
     }
 }
 
+// backward of the gated residual: d/dy = tanh(gamma) g, d/dgamma = (1 - tanh^2) <g, y> (d/db = g is the caller's pass-through)
+template <typename T, bool CH_FAST>
+__global__ void __launch_bounds__(256) gated_bwd_generic(const T* __restrict__ g, Strides4 gs, const T* __restrict__ y, Strides4 ys,
+                                                         const float* __restrict__ gamma, T* __restrict__ gy, Strides4 os, float* __restrict__ ggamma,
+                                                         int C, int H, int W, int64_t total) {
+    const float t = tanhf(__ldg(gamma));
+    float acc = 0.f;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n; int c, yy, x;
+        split_ncij<CH_FAST>(idx, C, H, W, n, c, yy, x);
+        const float gv = to_f(g[n * gs.n + (int64_t)c * gs.c + (int64_t)yy * gs.h + (int64_t)x * gs.w]);
+        acc += gv * to_f(y[n * ys.n + (int64_t)c * ys.c + (int64_t)yy * ys.h + (int64_t)x * ys.w]);
+        gy[n * os.n + (int64_t)c * os.c + (int64_t)yy * os.h + (int64_t)x * os.w] = from_f<T>(gv * t);
+    }
+    __shared__ float red[8];
+    float v = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) s += red[k];
+        atomicAdd(ggamma, s * (1.f - t * t));
+    }
+}
+
 // uint8 HWC -> normalised activations (value / 255), any destination strides
 template <typename T>
 __global__ void __launch_bounds__(256) ingest_u8_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, Strides4 ds, int H, int W, int64_t total) {
@@ -793,6 +818,24 @@ extern "C" int el_ingest_u8(const uint8_t* src, void* dst, const int64_t ds_[4],
     Strides4 ds = s4(ds_);
     int64_t total = (int64_t)B * H * W;
     EL_DISPATCH_DTYPE(dtype, { ingest_u8_kernel<T><<<stream_grid(total), 256, 0, st>>>(src, (T*)dst, ds, H, W, total); });
+    note_launches(1);
+    return check_launch();
+}
+
+extern "C" int el_gated_residual_bwd(const void* g, const int64_t gs_[4], const void* y, const int64_t ys_[4], const float* gamma, void* gy,
+                                     const int64_t os_[4], float* ggamma, int B, int C, int H, int W, int dtype, void* stream) {
+    if (!g || !y || !gamma || !gy || !ggamma || B <= 0 || C <= 0 || H <= 0 || W <= 0) return EL_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Strides4 gs = s4(gs_), ys = s4(ys_), os = s4(os_);
+    const int64_t total = (int64_t)B * C * H * W;
+    int grid = stream_grid(total);
+    if (grid > kSMs * 4) grid = kSMs * 4;  // fewer atomics on the scalar
+    EL_DISPATCH_DTYPE(dtype, {
+        if (os.c == 1)
+            gated_bwd_generic<T, true><<<grid, 256, 0, st>>>((const T*)g, gs, (const T*)y, ys, gamma, (T*)gy, os, ggamma, C, H, W, total);
+        else
+            gated_bwd_generic<T, false><<<grid, 256, 0, st>>>((const T*)g, gs, (const T*)y, ys, gamma, (T*)gy, os, ggamma, C, H, W, total);
+    });
     note_launches(1);
     return check_launch();
 }

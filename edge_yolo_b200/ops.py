@@ -193,10 +193,15 @@ class _Gated(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         y, gamma = ctx.saved_tensors
-        t = torch.tanh(gamma.float())
-        # d/db = g ; d/dy = tanh(gamma) g ; d/dgamma = (1 - tanh^2) <g, y>   (three tiny reductions / scalings)
-        ggamma = ((g.float() * y.float()).sum() * (1 - t * t)).to(gamma.dtype)
-        return g, (g.float() * t).to(g.dtype), ggamma
+        g = g if g.dtype == y.dtype else g.to(y.dtype)
+        B, C, H, W = y.shape
+        gy = _empty_like_layout(y, y.shape)
+        ggamma = torch.zeros((), device=y.device, dtype=torch.float32)
+        gm = gamma if gamma.dtype == torch.float32 else gamma.float()
+        # d/db = g ; d/dy = tanh(gamma) g ; d/dgamma = (1 - tanh^2) <g, y>
+        check(_lib.lib().el_gated_residual_bwd(g.data_ptr(), _i64(g.stride()), y.data_ptr(), _i64(y.stride()), gm.data_ptr(), gy.data_ptr(),
+                                               _i64(gy.stride()), ggamma.data_ptr(), B, C, H, W, _dt(y), _stream()), "el_gated_residual_bwd")
+        return g, gy, ggamma.to(gamma.dtype)
 
 
 def gated_residual(b, y, gamma, inplace: bool = False, out2: torch.Tensor | None = None) -> torch.Tensor:
@@ -207,28 +212,54 @@ def gated_residual(b, y, gamma, inplace: bool = False, out2: torch.Tensor | None
 
 
 # ------------------------------------------------------------------------------ attention
+def _attn_strides(t: torch.Tensor):
+    """(batch, channel, token) element strides of a (B, C, H, W) map whose token axis (h*W + w) is uniformly strided."""
+    W = t.shape[3]
+    if t.stride(2) != W * t.stride(3):
+        raise EdgelineError("linear_attention: token axis must be uniformly strided")
+    return (t.stride(0), t.stride(1), t.stride(3))
+
+
+def _linattn_fwd(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    B, C3, H, W = qkv.shape
+    C, N = C3 // 3, H * W
+    if not _channels_last(qkv) and (qkv.stride(3) != 1 or qkv.stride(2) != W):
+        qkv = qkv.contiguous()
+    y = _empty_like_layout(qkv, (B, C, H, W))
+    check(_lib.lib().el_linattn_fwd(qkv.data_ptr(), _i64(_attn_strides(qkv)), y.data_ptr(), _i64(_attn_strides(y)), B, heads, N, _dt(qkv),
+                                    _stream()), "el_linattn_fwd")
+    return y
+
+
+class _LinAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, heads):
+        ctx.save_for_backward(qkv)
+        ctx.heads = heads
+        return _linattn_fwd(qkv, heads)
+
+    @staticmethod
+    def backward(ctx, g):
+        (qkv,) = ctx.saved_tensors
+        B, C3, H, W = qkv.shape
+        fmt = torch.channels_last if _channels_last(qkv) else torch.contiguous_format
+        q = qkv.contiguous(memory_format=fmt)
+        g = g.to(qkv.dtype).contiguous(memory_format=fmt)
+        out = torch.empty_like(q, memory_format=fmt)
+        check(_lib.lib().el_linattn_bwd(q.data_ptr(), _i64(_attn_strides(q)), g.data_ptr(), _i64(_attn_strides(g)), out.data_ptr(),
+                                        _i64(_attn_strides(out)), B, ctx.heads, H * W, _dt(q), _stream()), "el_linattn_bwd")
+        return out, None
+
+
 def linear_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     """qkv (B, 3C, H, W) -> y (B, C, H, W); head_dim must be 64 (the only value the reference model produces)."""
     _need_cuda(qkv)
-    B, C3, H, W = qkv.shape
-    C, N = C3 // 3, H * W
-    if C3 != 3 * C or C != heads * 64:
+    C3 = qkv.shape[1]
+    if C3 != 3 * heads * 64:
         raise EdgelineError(f"linear_attention: need 3*heads*64 channels, got {C3} with heads={heads}")
     if torch.is_grad_enabled() and qkv.requires_grad:
-        raise EdgelineError("linear_attention: backward kernel not available yet (inference only)")
-    y = _empty_like_layout(qkv, (B, C, H, W))
-    if _channels_last(qkv):
-        qs = (qkv.stride(0), 1, qkv.stride(3))  # token stride = W stride (H stride = W * that)
-        ys = (y.stride(0), 1, y.stride(3))
-        if qkv.stride(2) != W * qkv.stride(3):
-            raise EdgelineError("linear_attention: token axis must be uniformly strided")
-    else:
-        if qkv.stride(3) != 1 or qkv.stride(2) != W:
-            qkv = qkv.contiguous()
-        qs = (qkv.stride(0), qkv.stride(1), 1)
-        ys = (y.stride(0), y.stride(1), 1)
-    check(_lib.lib().el_linattn_fwd(qkv.data_ptr(), _i64(qs), y.data_ptr(), _i64(ys), B, heads, N, _dt(qkv), _stream()), "el_linattn_fwd")
-    return y
+        return _LinAttn.apply(qkv, heads)
+    return _linattn_fwd(qkv, heads)
 
 
 # --------------------------------------------------------------------------------- decode

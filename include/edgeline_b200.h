@@ -85,6 +85,12 @@ int el_gated_residual_fwd(const void* b, const int64_t bs[4], const void* y, con
                           const float* gamma, void* out, const int64_t os[4], void* out2,
                           const int64_t os2[4], int B, int C, int H, int W, int dtype, void* stream);
 
+/* Backward of the gated residual: gy = tanh(gamma) * g, *ggamma += (1 - tanh^2(gamma)) * <g, y> (zero it first);
+ * the gradient with respect to b is g itself. */
+int el_gated_residual_bwd(const void* g, const int64_t gs[4], const void* y, const int64_t ys[4],
+                          const float* gamma, void* gy, const int64_t os[4], float* ggamma, int B, int C,
+                          int H, int W, int dtype, void* stream);
+
 /* ---- a4. linear-attention core: LinearAttention.forward, block.py:3364-3372 -----------------
  * qkv (B,3C,N) with strides qs = {sb, sc, sn} (channel = t*C + head*64 + j, t in q,k,v);
  * y (B,C,N), ys likewise.  softmax_d(K), softmax_N(Q), ctx = K^T V, y = Q ctx.  head_dim is 64
@@ -92,6 +98,9 @@ int el_gated_residual_fwd(const void* b, const int64_t bs[4], const void* y, con
  * cores with the accumulator in TMEM; EL_F32 runs an fp32 CUDA-core kernel (1e-5 contract). */
 int el_linattn_fwd(const void* qkv, const int64_t qs[3], void* y, const int64_t ys[3], int B,
                    int heads, int N, int dtype, void* stream);
+/* Backward: gy (B,C,N) -> gqkv (B,3C,N) through both softmaxes and both contractions (fp32 arithmetic). */
+int el_linattn_bwd(const void* qkv, const int64_t qs[3], const void* gy, const int64_t gs[3], void* gqkv,
+                   const int64_t os[3], int B, int heads, int N, int dtype, void* stream);
 
 /* ---- a6+a7. GFLv2 x UniHead decode: head.py:227-243 + 301-345, block.py:87-90, tal.py:333-357 --
  * Per level l < nl: box[l] (B,64,Hl,Wl) DFL logits, cls[l] (B,nc,Hl,Wl) class logits (host
