@@ -148,6 +148,9 @@ def profile_kernels(pred, a, iters=10):
         "gated_residual": lambda out, b, y, g, **k: 3 * b.numel() * e(b),
         "linear_attention": lambda out, qkv, heads: (qkv.numel() + out.numel()) * e(qkv),
         "gfl_decode": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss) + out.numel() * 4,
+        "bias_act": lambda out, x, bias, act=1, residual=None, **k: (2 + (residual is not None)) * x.numel() * e(x),
+        "upsample2x_cat": lambda out, x, skip: (x.numel() + skip.numel() + out.numel()) * e(x),
+        "sppf_pool": lambda out, x: 5 * x.numel() * e(x),
         "nms_batched": lambda out, y, *r, **k: y.shape[0] * y.shape[2] * (y.shape[1] - 4) * 4 + out[0].numel() * 4,
         # fused decode + NMS: head maps in, xywh boxes (16 B / anchor) out, rows out
         "gfl_detect": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss)
@@ -221,7 +224,13 @@ def profile_kernels(pred, a, iters=10):
             d["bytes"] += nbytes
             d["seconds"] += t
             first = args[0][0] if isinstance(args[0], (list, tuple)) else args[0]
-            d["sites"].append({"shape": list(first.shape), "MB": round(nbytes / 1e6, 2), "us": round(t * 1e6, 2), "gbs": round(nbytes / t / 1e9, 1)})
+            site = {"shape": list(first.shape), "MB": round(nbytes / 1e6, 2), "us": round(t * 1e6, 2), "gbs": round(nbytes / t / 1e9, 1)}
+            same = [x for x in d["sites"] if x["shape"] == site["shape"] and x["MB"] == site["MB"]]
+            if same:
+                same[0]["count"] = same[0].get("count", 1) + 1
+                same[0]["us"] = round((same[0]["us"] * (same[0]["count"] - 1) + site["us"]) / same[0]["count"], 2)
+            else:
+                d["sites"].append(site)
         _lib.lib().el_debug_set_detect_stages(7)
     for d in per.values():
         d["gbs"] = d["bytes"] / d["seconds"] / 1e9
