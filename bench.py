@@ -148,9 +148,9 @@ def profile_kernels(pred, a, iters=10):
         "gated_residual": lambda out, b, y, g, **k: 3 * b.numel() * e(b),
         "linear_attention": lambda out, qkv, heads: (qkv.numel() + out.numel()) * e(qkv),
         "gfl_decode": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss) + out.numel() * 4,
-        "bias_act": lambda out, x, bias, act=1, residual=None, **k: (2 + (residual is not None)) * x.numel() * e(x),
-        "upsample2x_cat": lambda out, x, skip: (x.numel() + skip.numel() + out.numel()) * e(x),
-        "sppf_pool": lambda out, x: 5 * x.numel() * e(x),
+        "bias_act": lambda _o, x, bias, act=1, residual=None, **k: (2 + (residual is not None)) * x.numel() * e(x),
+        "upsample2x_cat": lambda _o, x, skip: (x.numel() + skip.numel() + _o.numel()) * e(x),
+        "sppf_pool": lambda _o, x: 5 * x.numel() * e(x),
         "nms_batched": lambda out, y, *r, **k: y.shape[0] * y.shape[2] * (y.shape[1] - 4) * 4 + out[0].numel() * 4,
         # fused decode + NMS: head maps in, xywh boxes (16 B / anchor) out, rows out
         "gfl_detect": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss)

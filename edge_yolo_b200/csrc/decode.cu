@@ -13,6 +13,8 @@
 //                            shared memory, and instead of the dense score matrix only the xywh boxes
 //                            (B, A, 4) and the NMS candidate keys are written (warp-ballot compaction)
 //                            -- 45 % of the dense kernel's HBM traffic.
+#include <climits>
+
 #include "el_internal.h"
 
 namespace el {
@@ -279,6 +281,7 @@ __device__ __forceinline__ TileInfo tile_info(const DecodeParams& P, int t) {
 }
 
 constexpr int kWStride = ((kWFloats * 4 + 15) & ~15) / 4;
+constexpr int kStageCap = 1024;  // staged candidate keys per tile (8 KiB per stage); the rare overflow goes straight to global memory
 
 template <typename T, bool MULTI>
 __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_constant__ DecodeParams P, const __grid_constant__ EmitArgs E) {
@@ -297,7 +300,17 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
     float* s_q = (float*)cur; cur += kTile * 4;
     const int bias_ld = (4 * kRegMax + nc + 3) & ~3;
     float* s_bias = (float*)cur; cur += kMaxLevels * bias_ld * 4;  // per level: box bias (64) | class bias (nc)
-    uint64_t* bar = (uint64_t*)cur;
+    uint64_t* bar = (uint64_t*)cur; cur += 16;
+    // candidate keys are staged per tile in shared memory and flushed to the image's key list one tile later, so the global
+    // atomic that reserves the slots (one per tile instead of one per warp) has a whole tile of work to hide behind
+    unsigned long long* s_stage[2];
+    s_stage[0] = (unsigned long long*)cur; cur += kStageCap * 8; s_stage[1] = (unsigned long long*)cur; cur += kStageCap * 8;
+    int* s_scnt = (int*)cur;      // [2] staged count (may overshoot the capacity)
+    int* s_slimit = s_scnt + 2;   // [2] first position that did not fit (INT_MAX if none)
+    int* s_fcnt = s_scnt + 4;     // [2] number of staged keys to flush
+    int* s_fbase = s_scnt + 6;    // [2] reserved base slot in the image's key list
+    int* s_fimg = s_scnt + 8;     // [2] image of the staged tile
+    if (tid < 2) { s_scnt[tid] = 0; s_slimit[tid] = INT_MAX; s_fcnt[tid] = 0; }
 
     for (int l = 0; l < P.nl; ++l) {
         load_level_weights(s_w + l * kWStride, P.lv[l]);
@@ -329,6 +342,24 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
 
     const int cq = (nc + 3) >> 2;  // classes per quarter-thread in phase 3
     int it = 0;
+    int pending_base = 0;  // thread 0: slot reserved (atomicAdd issued at the end of the previous tile, consumed one tile later)
+    // append one warp's candidates (ballot-compacted) to the tile's staging buffer; spill to global memory when it is full
+    auto append = [&](bool pass, unsigned long long key, int stage, int img) {
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (!m) return;
+        const int nn = __popc(m), rank = __popc(m & ((1u << lane) - 1));
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&s_scnt[stage], nn);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (pos + nn <= kStageCap) {
+            if (pass) s_stage[stage][pos + rank] = key;
+        } else {
+            int gb = 0;
+            if (lane == 0) { atomicMin(&s_slimit[stage], pos); gb = atomicAdd(E.counts + img, nn); }
+            gb = __shfl_sync(0xffffffffu, gb, 0);
+            if (pass) E.keys[(int64_t)img * E.key_stride + gb + rank] = key;
+        }
+    };
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int stage = it & 1;
         const TileInfo ti = tile_info(P, t);
@@ -365,6 +396,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
             s_dist[side][a] = dist;
         }
         __syncthreads();
+        if (tid == 0 && it > 0) s_fbase[stage ^ 1] = pending_base;  // the previous tile's atomic has had a whole phase to return
         dgqp_hidden(w, s_stat, s_part);
         __syncthreads();
         if (tid < kTile) {
@@ -375,6 +407,11 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                 E.boxes[(int64_t)ti.b * P.A + L.a_off + pix] = decode_box(px, py, s_dist[0][a], s_dist[1][a], s_dist[2][a], s_dist[3][a], L.stride);
             }
         }
+        if (it > 0) {  // flush the previous tile's staged keys (coalesced 8-byte stores)
+            const int ps = stage ^ 1, fc = s_fcnt[ps];
+            unsigned long long* dst = E.keys + (int64_t)s_fimg[ps] * E.key_stride + s_fbase[ps];
+            for (int i = tid; i < fc; i += 256) dst[i] = s_stage[ps][i];
+        }
         __syncthreads();
         {   // phase 3: thread = (anchor a, quarter qd of the classes); scores never leave the SM unless they are candidates
             const int a = tid >> 2, qd = tid & 3;
@@ -382,7 +419,6 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
             const float q = s_q[a];
             const T* pc = s_clsT[stage] + a * nc;
             const uint32_t anchor = (uint32_t)(L.a_off + ti.pix0 + a);
-            unsigned long long* kb = E.keys + (int64_t)ti.b * E.key_stride;
             if (MULTI) {
                 for (int j = 0; j < cq; ++j) {
                     const int c = qd * cq + j;
@@ -392,16 +428,8 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                         sc = sigmoidf_<sizeof(T) == 2>(to_f(pc[c]) + bias_c[c]) * q;
                         pass = sc > E.conf && (!E.class_keep || E.class_keep[c]);
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, pass);
-                    if (m) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(E.counts + ti.b, __popc(m));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (pass) {
-                            const uint32_t idx = anchor * (uint32_t)nc + (uint32_t)c;
-                            kb[base + __popc(m & ((1u << lane) - 1))] = ((unsigned long long)__float_as_uint(sc) << 32) | (uint32_t)(~idx);
-                        }
-                    }
+                    const uint32_t idx = anchor * (uint32_t)nc + (uint32_t)c;
+                    append(pass, ((unsigned long long)__float_as_uint(sc) << 32) | (uint32_t)(~idx), stage, ti.b);
                 }
             } else {
                 float best = -INFINITY;
@@ -420,23 +448,28 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                     if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
                 }
                 const bool pass = av && qd == 0 && best > E.conf && (!E.class_keep || E.class_keep[bc]);
-                const unsigned m = __ballot_sync(0xffffffffu, pass);
-                if (m) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(E.counts + ti.b, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (pass) {
-                        const uint32_t idx = anchor * (uint32_t)nc + (uint32_t)bc;
-                        kb[base + __popc(m & ((1u << lane) - 1))] = ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)(~idx);
-                    }
-                }
+                const uint32_t idx = anchor * (uint32_t)nc + (uint32_t)bc;
+                append(pass, ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)(~idx), stage, ti.b);
             }
         }
         __syncthreads();  // every read of this stage is done: refill it with the tile two rounds ahead
         if (tid == 0) {
             const int tn = t + 2 * gridDim.x;
             if (tn < total) issue(tn, stage);
+            // close this tile's staging buffer and reserve its slots; the result is only needed during the next tile
+            const int cnt = min(s_scnt[stage], s_slimit[stage]);
+            s_fcnt[stage] = cnt; s_fimg[stage] = ti.b;
+            s_scnt[stage] = 0; s_slimit[stage] = INT_MAX;
+            pending_base = cnt ? atomicAdd(E.counts + ti.b, cnt) : 0;
         }
+    }
+    if (it > 0) {  // flush the last tile
+        const int ps = (it - 1) & 1;
+        if (tid == 0) s_fbase[ps] = pending_base;
+        __syncthreads();
+        const int fc = s_fcnt[ps];
+        unsigned long long* dst = E.keys + (int64_t)s_fimg[ps] * E.key_stride + s_fbase[ps];
+        for (int i = tid; i < fc; i += 256) dst[i] = s_stage[ps][i];
     }
 }
 
@@ -445,7 +478,7 @@ static size_t emit_smem_bytes(int nc, size_t esz) {
     const size_t cls_bytes = ((size_t)kTile * nc * esz + 127) & ~(size_t)127;
     const size_t bias_ld = (4 * kRegMax + nc + 3) & ~3;
     return 2 * box_bytes + 2 * cls_bytes + (size_t)kMaxLevels * kWStride * 4 + kTile * kStatLd * 4 + 4 * kTile * 4 + 8 * kTile * 4 + kTile * 4 +
-           kMaxLevels * bias_ld * 4 + 16;
+           kMaxLevels * bias_ld * 4 + 16 + 2 * kStageCap * 8 + 64;
 }
 
 static int fill_params(DecodeParams& P, int nl, const void* const* box, const int64_t* box_s, const void* const* cls, const int64_t* cls_s, const int32_t* hw,

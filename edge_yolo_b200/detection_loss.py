@@ -1,0 +1,205 @@
+"""`v8DetectionLoss` with the reference's signature (utils/loss.py:293-420) on top of the CUDA loss kernels.
+
+What runs where:
+  * DFL term            -> `el_dfl_fwd/bwd`   (loss.DFLoss)
+  * class term          -> BCE-with-logits, the branch the reference really takes with GFLHeadv2_uniH (`head._qualities`
+                           stays None in training); `use_qfl=True` switches to `el_qfl_fwd/bwd`, the one-line
+                           change the reference documents at loss.py:404-407
+  * target assignment   -> `TaskAlignedAssigner` below: a vectorised torch restatement of utils/tal.py:14-295.  It is the
+                           rank-1 "next" row of SURVEY section 8(f); it has no kernel of its own yet, so it runs as device-side torch
+                           ops (no host synchronisation except the data-dependent `fg_mask.sum()` the reference also has)
+  * CIoU                -> `bbox_ciou` (utils/metrics.py:74-134 with xywh=False, CIoU=True)
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn.functional as F
+
+from .loss import DFLoss, quality_focal_loss
+
+
+def make_anchors(feats, strides, offset: float = 0.5):
+    """Cell centres and strides, level-major then row-major (utils/tal.py:333-345)."""
+    pts, st = [], []
+    dtype, device = feats[0].dtype, feats[0].device
+    for f, s in zip(feats, strides):
+        h, w = f.shape[2:]
+        gy, gx = torch.meshgrid(torch.arange(h, device=device, dtype=dtype) + offset, torch.arange(w, device=device, dtype=dtype) + offset, indexing="ij")
+        pts.append(torch.stack((gx, gy), -1).reshape(-1, 2))
+        st.append(torch.full((h * w, 1), float(s), dtype=dtype, device=device))
+    return torch.cat(pts), torch.cat(st)
+
+
+def dist2bbox(dist, anchors):
+    """ltrb distances -> xyxy (utils/tal.py:348-357 with xywh=False)."""
+    lt, rb = dist.chunk(2, -1)
+    return torch.cat((anchors - lt, anchors + rb), -1)
+
+
+def bbox2dist(anchors, bbox, reg_max):
+    """xyxy -> ltrb distances clamped to [0, reg_max - 0.01] (utils/tal.py:360-363)."""
+    x1y1, x2y2 = bbox.chunk(2, -1)
+    return torch.cat((anchors - x1y1, x2y2 - anchors), -1).clamp_(0, reg_max - 0.01)
+
+
+def bbox_ciou(a, b, eps: float = 1e-7):
+    """Complete IoU of xyxy boxes with a trailing dim of 4 -> (..., 1) (utils/metrics.py:74-134)."""
+    ax1, ay1, ax2, ay2 = a.chunk(4, -1)
+    bx1, by1, bx2, by2 = b.chunk(4, -1)
+    aw, ah = ax2 - ax1, ay2 - ay1 + eps
+    bw, bh = bx2 - bx1, by2 - by1 + eps
+    inter = (torch.minimum(ax2, bx2) - torch.maximum(ax1, bx1)).clamp_(0) * (torch.minimum(ay2, by2) - torch.maximum(ay1, by1)).clamp_(0)
+    union = aw * ah + bw * bh - inter + eps
+    iou = inter / union
+    cw = torch.maximum(ax2, bx2) - torch.minimum(ax1, bx1)
+    chh = torch.maximum(ay2, by2) - torch.minimum(ay1, by1)
+    c2 = cw.pow(2) + chh.pow(2) + eps
+    rho2 = ((bx1 + bx2 - ax1 - ax2).pow(2) + (by1 + by2 - ay1 - ay2).pow(2)) / 4
+    v = (4 / math.pi ** 2) * ((bw / bh).atan() - (aw / ah).atan()).pow(2)
+    with torch.no_grad():
+        alpha = v / (v - iou + (1 + eps))
+    return iou - (rho2 / c2 + v * alpha)
+
+
+class TaskAlignedAssigner:
+    """Task-aligned target assignment (utils/tal.py:14-295): metric = score^alpha * CIoU^beta, top-k anchors per ground truth
+    among those whose centre lies inside it, ties between ground truths resolved by the larger overlap."""
+
+    def __init__(self, topk=13, num_classes=80, alpha=1.0, beta=6.0, eps=1e-9):
+        self.topk, self.num_classes, self.alpha, self.beta, self.eps = topk, num_classes, alpha, beta, eps
+
+    @torch.no_grad()
+    def __call__(self, scores, boxes, anchors, gt_labels, gt_boxes, gt_valid):
+        """scores (B,A,nc) probabilities, boxes (B,A,4) xyxy px, anchors (A,2) px, gt_labels (B,M,1), gt_boxes (B,M,4),
+        gt_valid (B,M,1) -> (labels (B,A), boxes (B,A,4), scores (B,A,nc), fg (B,A) bool, gt index (B,A))."""
+        B, A, nc = scores.shape
+        M = gt_boxes.shape[1]
+        if M == 0:
+            z = torch.zeros_like(scores[..., 0])
+            return torch.full_like(z, self.num_classes), torch.zeros_like(boxes), torch.zeros_like(scores), z, z
+        valid = gt_valid.bool()                                                   # (B,M,1)
+        # anchor centre strictly inside the ground-truth box (tal.py:254-261)
+        lt = anchors.view(1, 1, A, 2) - gt_boxes[..., None, :2]
+        rb = gt_boxes[..., None, 2:] - anchors.view(1, 1, A, 2)
+        inside = torch.cat((lt, rb), -1).amin(-1) > 1e-9                          # (B,M,A)
+        cand = inside & valid
+        # per (gt, anchor): class probability of the gt's class and CIoU, only where the anchor is a candidate (tal.py:149-166)
+        lab = gt_labels.squeeze(-1).long().clamp(0, nc - 1)                       # (B,M)
+        cls_score = scores.gather(2, lab.unsqueeze(1).expand(B, A, M)).permute(0, 2, 1)   # (B,M,A)
+        iou = bbox_ciou(gt_boxes.unsqueeze(2), boxes.unsqueeze(1)).squeeze(-1).clamp_(0)
+        zero = torch.zeros((), dtype=iou.dtype, device=iou.device)
+        iou = torch.where(cand, iou, zero)
+        cls_score = torch.where(cand, cls_score, zero.to(cls_score.dtype))
+        metric = cls_score.pow(self.alpha) * iou.pow(self.beta)
+        # top-k anchors per ground truth; padded ground truths select nothing (tal.py:172-199)
+        top = metric.topk(self.topk, dim=-1).indices                              # (B,M,k)
+        in_top = torch.zeros_like(metric, dtype=torch.bool).scatter_(2, top, True) & valid
+        pos = in_top & inside                                                     # (B,M,A)
+        # an anchor claimed by several ground truths goes to the one it overlaps most (tal.py:282-295)
+        n_claims = pos.sum(1)                                                     # (B,A)
+        best = F.one_hot(iou.argmax(1), M).permute(0, 2, 1).bool()                # (B,M,A)
+        pos = torch.where((n_claims > 1).unsqueeze(1), best, pos)
+        fg = pos.any(1)
+        gt_idx = pos.float().argmax(1)                                            # (B,A); 0 where background
+        # targets (tal.py:201-241)
+        labels = lab.gather(1, gt_idx)
+        tboxes = gt_boxes.gather(1, gt_idx.unsqueeze(-1).expand(B, A, 4))
+        tscores = F.one_hot(labels, nc).to(scores.dtype) * fg.unsqueeze(-1)
+        # soft labels: metric normalised per ground truth to its best overlap (tal.py:96-101)
+        posf = pos.to(metric.dtype)
+        metric = metric * posf
+        best_metric = metric.amax(-1, keepdim=True)
+        best_iou = (iou * posf).amax(-1, keepdim=True)
+        norm = (metric * best_iou / (best_metric + self.eps)).amax(1).unsqueeze(-1)
+        return labels, tboxes, tscores * norm, fg, gt_idx
+
+
+class BboxLoss:
+    """CIoU + DFL terms over the foreground anchors (utils/loss.py:227-249)."""
+
+    def __init__(self, reg_max=16):
+        self.reg_max = reg_max
+        self.dfl = DFLoss(reg_max) if reg_max > 1 else None
+
+    def __call__(self, pred_dist, pred_boxes, anchors, target_boxes, target_scores, target_scores_sum, fg):
+        weight = target_scores.sum(-1)[fg].unsqueeze(-1)
+        iou = bbox_ciou(pred_boxes[fg], target_boxes[fg])
+        loss_iou = ((1.0 - iou) * weight).sum() / target_scores_sum
+        if self.dfl is None:
+            return loss_iou, pred_dist.new_zeros(())
+        ltrb = bbox2dist(anchors, target_boxes, self.reg_max - 1)
+        loss_dfl = self.dfl(pred_dist[fg].view(-1, self.reg_max), ltrb[fg]) * weight
+        return loss_iou, loss_dfl.sum() / target_scores_sum
+
+
+class v8DetectionLoss:
+    """Drop-in for `ultralytics.utils.loss.v8DetectionLoss`: `criterion(preds, batch) -> (loss.sum() * B, loss.detach())`
+    with loss = (box, cls, dfl) scaled by the hyper-parameter gains."""
+
+    def __init__(self, model, tal_topk=10, use_qfl: bool = False):
+        head = model.model[-1]
+        self.head = head
+        self.hyp = getattr(model, "args", None) or SimpleNamespace(box=7.5, cls=0.5, dfl=1.5)  # cfg/default.yaml
+        if isinstance(self.hyp, dict):
+            self.hyp = SimpleNamespace(**self.hyp)
+        self.stride, self.nc, self.reg_max = head.stride, head.nc, head.reg_max
+        self.no = head.nc + head.reg_max * 4
+        self.device = next(model.parameters()).device
+        self.use_dfl, self.use_qfl = head.reg_max > 1, use_qfl
+        self.assigner = TaskAlignedAssigner(topk=tal_topk, num_classes=self.nc, alpha=0.5, beta=6.0)
+        self.bbox_loss = BboxLoss(head.reg_max)
+        self.proj = torch.arange(head.reg_max, dtype=torch.float, device=self.device)
+
+    def preprocess(self, targets, batch_size, scale):
+        """(n, 6) rows [image, cls, cx, cy, w, h] (normalised) -> (B, M, 5) [cls, x1, y1, x2, y2] px, zero padded (loss.py:321-336)."""
+        if targets.shape[0] == 0:
+            return torch.zeros(batch_size, 0, 5, device=self.device)
+        img = targets[:, 0].long()
+        counts = torch.bincount(img, minlength=batch_size)
+        M = int(counts.max())
+        order = torch.argsort(img, stable=True)
+        start = torch.cumsum(counts, 0) - counts
+        slot = torch.arange(targets.shape[0], device=targets.device) - start[img[order]]
+        out = torch.zeros(batch_size, M, 5, device=self.device, dtype=targets.dtype)
+        out[img[order], slot] = targets[order, 1:]
+        xy, half = out[..., 1:3] * scale[:2], out[..., 3:5] * scale[2:] / 2
+        out[..., 1:5] = torch.cat((xy - half, xy + half), -1)
+        return out
+
+    def bbox_decode(self, anchors, pred_dist):
+        if self.use_dfl:
+            b, a, c = pred_dist.shape
+            pred_dist = pred_dist.view(b, a, 4, c // 4).softmax(3).matmul(self.proj.to(pred_dist.dtype))
+        return dist2bbox(pred_dist, anchors)
+
+    def __call__(self, preds, batch):
+        feats = preds[1] if isinstance(preds, tuple) else preds
+        B = feats[0].shape[0]
+        cat = torch.cat([f.reshape(B, self.no, -1) for f in feats], 2)
+        pred_dist = cat[:, : self.reg_max * 4].permute(0, 2, 1).contiguous()
+        pred_scores = cat[:, self.reg_max * 4 :].permute(0, 2, 1).contiguous()
+        dtype = pred_scores.dtype
+        imgsz = torch.tensor(feats[0].shape[2:], device=self.device, dtype=dtype) * float(self.stride[0])  # (h, w)
+        anchors, stride_t = make_anchors(feats, self.stride, 0.5)
+
+        targets = torch.cat((batch["batch_idx"].view(-1, 1), batch["cls"].view(-1, 1), batch["bboxes"]), 1).to(self.device)
+        targets = self.preprocess(targets, B, imgsz[[1, 0, 1, 0]])
+        gt_labels, gt_boxes = targets.split((1, 4), 2)
+        gt_valid = gt_boxes.sum(2, keepdim=True) > 0
+
+        pred_boxes = self.bbox_decode(anchors, pred_dist)
+        _, t_boxes, t_scores, fg, _ = self.assigner(pred_scores.detach().sigmoid(), (pred_boxes.detach() * stride_t).to(gt_boxes.dtype),
+                                                    anchors * stride_t, gt_labels, gt_boxes, gt_valid)
+        t_sum = t_scores.sum().clamp_min(1)
+        loss = torch.zeros(3, device=self.device)
+        if self.use_qfl:
+            loss[1] = quality_focal_loss(pred_scores, t_scores.to(dtype), beta=2.0, reduction="sum") / t_sum
+        else:
+            loss[1] = F.binary_cross_entropy_with_logits(pred_scores, t_scores.to(dtype), reduction="none").sum() / t_sum
+        if fg.any():
+            loss[0], loss[2] = self.bbox_loss(pred_dist, pred_boxes, anchors, t_boxes / stride_t, t_scores, t_sum, fg)
+        loss = loss * torch.tensor([self.hyp.box, self.hyp.cls, self.hyp.dfl], device=self.device)
+        return loss.sum() * B, loss.detach()

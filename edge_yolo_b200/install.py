@@ -16,6 +16,7 @@ What is replaced (reference path -> ours):
     utils/ops.py         non_max_suppression         -> nms.non_max_suppression
     utils/loss.py        quality_focal_loss, QualityFocalLoss.forward, distribution_focal_loss, DFLoss.__call__
                                                       -> loss.*
+                         v8DetectionLoss (also the name bound in nn/tasks.py) -> detection_loss.v8DetectionLoss
 There is no CPU fallback: after install() these functions need CUDA tensors.
 """
 from __future__ import annotations
@@ -32,9 +33,9 @@ def _swap(obj, name, new):
     setattr(obj, name, new)
 
 
-def install(nms: bool = True, modules: bool = True, losses: bool = True):
+def install(nms: bool = True, modules: bool = True, losses: bool = True, criterion: bool = True):
     """Patch the imported `ultralytics` package in place.  Returns the list of patched names."""
-    from . import _lib, loss as el_loss, modules as M, nms as el_nms
+    from . import _lib, detection_loss as el_det, loss as el_loss, modules as M, nms as el_nms
 
     _lib.lib()  # fail now, loudly, if the CUDA library has not been built
     block = importlib.import_module("ultralytics.nn.modules.block")
@@ -59,6 +60,11 @@ def install(nms: bool = True, modules: bool = True, losses: bool = True):
         _swap(uloss.DFLoss, "__call__", el_loss.DFLoss.__call__)
         done += ["utils.loss.quality_focal_loss", "utils.loss.distribution_focal_loss", "utils.loss.QualityFocalLoss.forward",
                  "utils.loss.DistributionFocalLoss.forward", "utils.loss.DFLoss.__call__"]
+    if criterion:  # DetectionModel.init_criterion resolves the name in nn/tasks.py at call time (tasks.py:411-413)
+        tasks = importlib.import_module("ultralytics.nn.tasks")
+        _swap(uloss, "v8DetectionLoss", el_det.v8DetectionLoss)
+        _swap(tasks, "v8DetectionLoss", el_det.v8DetectionLoss)
+        done += ["utils.loss.v8DetectionLoss", "nn.tasks.v8DetectionLoss"]
     return done
 
 

@@ -215,6 +215,43 @@ def gen_losses(loss_mod):
     _save("losses", **out)
 
 
+def gen_detection_loss(loss_mod, head_mod):
+    """`v8DetectionLoss.__call__`, utils/loss.py:345-420 (BCE branch: the uniH head leaves `_qualities` None),
+    including TaskAlignedAssigner (utils/tal.py:14-295) and BboxLoss (loss.py:227-249)."""
+    from types import SimpleNamespace
+
+    torch.manual_seed(7)
+    g = torch.Generator().manual_seed(7)
+    nc = 5
+    head = head_mod.GFLHeadv2_uniH(nc=nc, ch=(16, 32, 64))
+    head.stride = torch.tensor([8.0, 16.0, 32.0])
+
+    class Wrapper(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.ModuleList([head])
+            self.args = SimpleNamespace(box=7.5, cls=0.5, dfl=1.5)
+
+    crit = loss_mod.v8DetectionLoss(Wrapper())
+    out = {"nc": np.int64(nc)}
+    for tag, B, sizes, boxes in (
+        ("a", 2, (8, 4, 2), [[0, 1, .30, .35, .30, .40], [0, 3, .70, .60, .40, .50], [0, 1, .50, .50, .90, .90], [1, 0, .25, .75, .35, .30], [1, 4, .60, .30, .50, .45]]),
+        ("b", 3, (6, 3, 2), [[0, 2, .5, .5, .6, .6], [2, 2, .4, .4, .5, .3], [2, 0, .45, .42, .5, .35], [2, 1, .8, .8, .3, .3]]),  # image 1 has no target
+    ):
+        feats = [(torch.randn(B, 64 + nc, s, s, generator=g) * 1.5).requires_grad_() for s in sizes]
+        t = torch.tensor(boxes, dtype=torch.float32)
+        batch = {"batch_idx": t[:, 0], "cls": t[:, 1], "bboxes": t[:, 2:]}
+        total, items = crit([f for f in feats], batch)
+        grads = torch.autograd.grad(total, feats)
+        out[f"{tag}_targets"] = _np(t)
+        out[f"{tag}_total"] = _np(total)
+        out[f"{tag}_items"] = _np(items)
+        for i, (f, gr) in enumerate(zip(feats, grads)):
+            out[f"{tag}_feat{i}"] = _np(f)
+            out[f"{tag}_grad{i}"] = _np(gr)
+    _save("detection_loss", **out)
+
+
 def main():
     ref_loader.load()
     from ultralytics.nn.modules import block, head
@@ -227,6 +264,7 @@ def main():
     gen_head(head)
     gen_nms(ops)
     gen_losses(loss)
+    gen_detection_loss(loss, head)
 
 
 if __name__ == "__main__":

@@ -27,7 +27,8 @@ def test_install_and_uninstall_round_trip():
     ref_sig = inspect.signature(uops.non_max_suppression)
     names = el.install()
     try:
-        assert len(names) == 10
+        assert len(names) == 12
+        assert tasks.v8DetectionLoss.__module__ == "edge_yolo_b200.detection_loss"
         assert block._WaveletEnhancer.forward is M.wavelet_enhancer_forward
         assert block.LinearAttention.forward is M.linear_attention_forward
         assert head.GFLHeadv2_uniH.forward is M.gfl_head_forward
