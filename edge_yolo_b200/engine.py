@@ -48,6 +48,12 @@ class Predictor:
         self.x = torch.empty((batch, 3, imgsz, imgsz), device=self.device, dtype=self.dtype, memory_format=torch.channels_last)
         self.host_out = torch.empty((batch, max_det, 6), dtype=torch.float32).pin_memory()
         self.host_cnt = torch.empty((batch,), dtype=torch.int32).pin_memory()
+        # layer 0 (Conv 3->C0, k3 s2) reads the uint8 batch directly: folded weights / 255 in fp32 (ops.stem_conv_u8)
+        stem = model.model[0]
+        self.stem = None
+        if getattr(stem, "el_bias", None) is not None and stem.conv.weight.shape[1:] == (3, 3, 3) and stem.conv.stride == (2, 2) \
+                and stem.conv.weight.shape[0] in (16, 32, 64) and stem.el_act == ops.ACT_SILU and imgsz % 2 == 0:
+            self.stem = ((stem.conv.weight.detach().float() / 255.0).contiguous(), stem.el_bias.to(self.device).contiguous())
         self.graph_from_u8 = self.graph_from_x = None
         self.launches_per_step = None
         self.out = self.cnt = None
@@ -56,6 +62,8 @@ class Predictor:
 
     @torch.no_grad()
     def _forward(self, from_u8: bool):
+        if from_u8 and self.stem is not None:
+            return self.model(None, stem_out=ops.stem_conv_u8(self.u8, *self.stem, dtype=self.dtype))
         if from_u8:
             ops.ingest_u8(self.u8, out=self.x)
         return self.model(self.x)  # (rows, counts) from the fused detect head

@@ -95,9 +95,14 @@ class EdgeLineYOLO(nn.Module):
             elif isinstance(m, (nn.SiLU, nn.ReLU)):
                 m.inplace = True
 
-    def forward(self, x):
+    def forward(self, x, stem_out=None):
+        """`stem_out`: precomputed output of layer 0 (the engine's fused uint8 stem, ops.stem_conv_u8); `x` is then unused."""
         outs = []
         for m in self.model:
+            if stem_out is not None and m.i == 0:
+                x = stem_out
+                outs.append(x if 0 in self.save else None)
+                continue
             if m.f != -1:
                 x = outs[m.f] if isinstance(m.f, int) else [x if j == -1 else outs[j] for j in m.f]
             if getattr(m, "el_fused_into_next", False):  # nn.Upsample folded into the following Concat (engine mode)

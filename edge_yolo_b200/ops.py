@@ -475,6 +475,25 @@ def ingest_u8(src: torch.Tensor, dtype=torch.bfloat16, channels_last: bool = Tru
     return out
 
 
+def stem_conv_u8(src: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, dtype=torch.bfloat16, out: torch.Tensor | None = None) -> torch.Tensor:
+    """uint8 (B,H,W,3) images -> SiLU(conv3x3/s2(img/255) + bias) as (B,C0,H/2,W/2) NHWC activations: the predictor's
+    preprocess (engine/predictor.py:117-135) fused with layer 0 of the yaml.  weight (C0,3,3,3) fp32 must already carry
+    the folded BatchNorm scale and the 1/255."""
+    _need_cuda(src, weight, bias)
+    if src.dtype != torch.uint8 or src.dim() != 4 or src.shape[-1] != 3 or not src.is_contiguous():
+        raise EdgelineError("stem_conv_u8: need a contiguous uint8 (B,H,W,3) tensor")
+    B, H, W, _ = src.shape
+    C0 = weight.shape[0]
+    if weight.dtype != torch.float32 or bias.dtype != torch.float32 or tuple(weight.shape) != (C0, 3, 3, 3) or bias.numel() != C0 \
+            or not weight.is_contiguous() or not bias.is_contiguous():
+        raise EdgelineError("stem_conv_u8: weight must be contiguous fp32 (C0,3,3,3) and bias fp32 (C0)")
+    if out is None:
+        out = torch.empty((B, C0, H // 2, W // 2), device=src.device, dtype=dtype, memory_format=torch.channels_last)
+    check(_lib.lib().el_stem_conv_u8(src.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(), _i64(out.stride()), B, C0, H, W,
+                                     _dt(out), _stream()), "el_stem_conv_u8")
+    return out
+
+
 # ------------------------------------------------------------------------------ epilogues
 ACT_NONE, ACT_SILU, ACT_RELU = 0, 1, 2
 

@@ -176,6 +176,12 @@ int el_dfl_bwd(const void* pred, const float* target, int64_t rows, int dtype, c
  * src (B,H,W,3) uint8 -> dst (B,3,H,W) logical with strides ds, value/255 in `dtype`. */
 int el_ingest_u8(const uint8_t* src, void* dst, const int64_t ds[4], int B, int H, int W, int dtype,
                  void* stream);
+/* el_stem_conv_u8: the same preprocess fused with layer 0 of the yaml (cfg/models/11/yolo11-test.yaml:21,
+ * Conv(3, C0, k=3, s=2, p=1) + BatchNorm + SiLU, nn/modules/conv.py:41-60): src (B,H,W,3) uint8 ->
+ * dst (B,C0,H/2,W/2) logical with strides ds (channel-contiguous).  w (C0,3,3,3) fp32 = BN-folded weights
+ * already divided by 255, bias (C0) fp32 = folded BN bias.  C0 in {16,32,64}, H and W even. */
+int el_stem_conv_u8(const uint8_t* src, const float* w, const float* bias, void* dst,
+                    const int64_t ds[4], int B, int C0, int H, int W, int dtype, void* stream);
 
 /* ---- conv epilogues of the inference engine (the convolutions themselves stay on cuDNN) ---------
  * el_bias_act_fwd: out = act(x + bias[c]) (+ residual): the BatchNorm-folded bias and SiLU of Conv /

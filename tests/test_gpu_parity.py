@@ -471,6 +471,20 @@ def test_epilogue_kernels_vs_torch():
             close(ops().sppf_pool(z), torch.cat(ys, 1), 0, 0)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("c0,hw", [(16, (64, 96)), (32, (34, 70)), (64, (16, 130))])
+def test_stem_conv_u8(dtype, tol, c0, hw):
+    """Fused uint8 preprocess + Conv(3,C0,3,2,1) + bias + SiLU (engine/predictor.py:117-135 + conv.py:58-60) vs torch fp32."""
+    gen = torch.Generator().manual_seed(c0)
+    img = torch.randint(0, 256, (3, *hw, 3), dtype=torch.uint8, generator=gen)
+    w = torch.randn(c0, 3, 3, 3, generator=gen) * 0.3
+    b = torch.randn(c0, generator=gen)
+    want = torch.nn.functional.silu(torch.nn.functional.conv2d(img.permute(0, 3, 1, 2).double() / 255, w.double(), b.double(), stride=2, padding=1))
+    got = ops().stem_conv_u8(img.to(DEV), (w / 255).to(DEV), b.to(DEV), dtype=dtype)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    close(got, want.float(), tol, tol)
+
+
 def test_predictor_matches_api_path():
     """Predictor (graph replay, uint8 ingest) returns exactly what model + non_max_suppression return."""
     from edge_yolo_b200.engine import Predictor, build_model
@@ -486,8 +500,12 @@ def test_predictor_matches_api_path():
     with torch.no_grad():
         x = ops().ingest_u8(host.to(DEV))
         close(x.float(), host.to(DEV).permute(0, 3, 1, 2).float() / 255, 1e-2, 1e-2)
-        y, _ = model(x)
+        assert pred.stem is not None
+        y, _ = model(None, stem_out=ops().stem_conv_u8(host.to(DEV), *pred.stem))
         want = non_max_suppression(y, conf_thres=0.25, iou_thres=0.7, max_det=300)
+        # the fused uint8 stem agrees with ingest -> layer 0 of the graph within the bf16 contract
+        y_ingest, _ = model(x)
+        assert float((y[:, 4:] - y_ingest[:, 4:]).abs().max()) < 2e-2
     assert [d.shape[0] for d in dets] == [w.shape[0] for w in want]
     for d, w in zip(dets, want):
         assert d.numpy().tobytes() == w.cpu().numpy().tobytes()
