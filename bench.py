@@ -149,6 +149,9 @@ def profile_kernels(pred, a, iters=10):
         "linear_attention": lambda out, qkv, heads: (qkv.numel() + out.numel()) * e(qkv),
         "gfl_decode": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss) + out.numel() * 4,
         "bias_act": lambda _o, x, bias, act=1, residual=None, **k: (2 + (residual is not None)) * x.numel() * e(x),
+        "pwconv": lambda _o, srcs, wpk, N, bias=None, act=0, residual=None, out=None, out2=None: (
+            sum(t.numel() for t in srcs) + srcs[0].numel() // srcs[0].shape[1] * N * (1 + (residual is not None))) * e(srcs[0]),
+        "dwconv": lambda _o, x, *r, **k: 2 * x.numel() * e(x),
         "upsample2x_cat": lambda _o, x, skip: (x.numel() + skip.numel() + _o.numel()) * e(x),
         "sppf_pool": lambda _o, x: 5 * x.numel() * e(x),
         "nms_batched": lambda out, y, *r, **k: y.shape[0] * y.shape[2] * (y.shape[1] - 4) * 4 + out[0].numel() * 4,
@@ -232,6 +235,27 @@ def profile_kernels(pred, a, iters=10):
             else:
                 d["sites"].append(site)
         _lib.lib().el_debug_set_detect_stages(7)
+        if pred.stem is not None:  # the fused uint8 stem runs only on the from-uint8 path: timed here with rotating inputs
+            R = 4
+            srcs = [pred.u8.clone() for _ in range(R)]
+            out0 = ops.stem_conv_u8(srcs[0], *pred.stem, dtype=pred.dtype)
+            nbytes = srcs[0].numel() + out0.numel() * out0.element_size()
+            ts = []
+            for it in range(iters // 2 + 1):
+                flush.zero_()
+                torch.cuda._sleep(6_000_000)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for sx in srcs:
+                    ops.stem_conv_u8(sx, *pred.stem, dtype=pred.dtype, out=out0)
+                e1.record()
+                e1.synchronize()
+                if it >= 1:
+                    ts.append(e0.elapsed_time(e1) * 1e-3 / R)
+            ts.sort()
+            t = ts[len(ts) // 2]
+            per["stem_conv_u8"] = {"launch_sites": 1, "bytes": nbytes, "seconds": t,
+                                   "sites": [{"shape": list(out0.shape), "MB": round(nbytes / 1e6, 2), "us": round(t * 1e6, 2), "gbs": round(nbytes / t / 1e9, 1)}]}
     for d in per.values():
         d["gbs"] = d["bytes"] / d["seconds"] / 1e9
         d["us"] = d["seconds"] * 1e6

@@ -48,6 +48,10 @@ class Predictor:
         self.x = torch.empty((batch, 3, imgsz, imgsz), device=self.device, dtype=self.dtype, memory_format=torch.channels_last)
         self.host_out = torch.empty((batch, max_det, 6), dtype=torch.float32).pin_memory()
         self.host_cnt = torch.empty((batch,), dtype=torch.int32).pin_memory()
+        for m in model.modules():  # folded-BN biases live on the device before any graph capture (no lazy H2D inside a capture)
+            for k, v in list(vars(m).items()):
+                if k.startswith("el_") and isinstance(v, torch.Tensor):
+                    setattr(m, k, v.to(self.device))
         # layer 0 (Conv 3->C0, k3 s2) reads the uint8 batch directly: folded weights / 255 in fp32 (ops.stem_conv_u8)
         stem = model.model[0]
         self.stem = None
@@ -72,8 +76,9 @@ class Predictor:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            for _ in range(3):  # cuDNN autotune + allocator warm-up outside the capture
+            for _ in range(3):  # cuDNN autotune + allocator warm-up outside the capture (both entry points: layer 0 differs)
                 self._forward(True)
+                self._forward(False)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         n0 = lib().el_launch_count()

@@ -132,6 +132,9 @@ class EdgeLineYOLO(nn.Module):
                     m.el_bias, m.el_act = m.conv.bias.detach().float().clone(), acts[type(m.act)]
                     m.conv.bias = None
                     m.forward = types.MethodType(M.conv_engine_forward, m)
+                    if _dw_eligible(m.conv):  # DWConv: depthwise + bias + activation in one kernel
+                        m.el_dw, m.el_k = M.ops.pack_dw_weight(m.conv.weight), m.conv.kernel_size[0]
+                        m.forward = types.MethodType(M.dwconv_engine_forward, m)
             elif dsconv and isinstance(m, DSConv) and isinstance(m.bn, nn.BatchNorm2d):
                 m.pw = _fold(m.pw, m.bn)
                 m.bn = nn.Identity()
@@ -139,6 +142,8 @@ class EdgeLineYOLO(nn.Module):
                     m.el_bias = m.pw.bias.detach().float().clone()
                     m.pw.bias = None
                     m.forward = types.MethodType(M.dsconv_engine_forward, m)
+                    if _dw_eligible(m.dw) and m.dw.bias is None:
+                        m.el_dw, m.el_k = M.ops.pack_dw_weight(m.dw.weight), m.dw.kernel_size[0]
         if engine:
             binds = {M.DSBottleneck: M.dsbottleneck_engine_forward, M.DSC3k: M.dsc3k_engine_forward,
                      M.DSC3K2_Wavelet: M.dsc3k2_wavelet_engine_forward, M.PSABlock_LinearAttention: M.psablock_engine_forward,
@@ -153,6 +158,8 @@ class EdgeLineYOLO(nn.Module):
                     for tower in seq:
                         dst.append(tower[-1].bias.detach().float().clone())
                         tower[-1].bias = None
+                        if tower[-1].kernel_size == (1, 1):
+                            tower[-1].forward = types.MethodType(M.conv2d_pw_forward, tower[-1])
                 head.el_head_bias = (box_b, cls_b)
             layers = list(self.model)
             for up, cat in zip(layers, layers[1:]):
@@ -160,7 +167,22 @@ class EdgeLineYOLO(nn.Module):
                         and isinstance(cat.f, list) and cat.f[0] == -1 and cat.d == 1 and up.i not in self.save):
                     up.el_fused_into_next, cat.el_upsample_first = True, True
                     cat.forward = types.MethodType(M.concat_engine_forward, cat)
+            for cat, nxt in zip(layers, layers[1:]):  # Concat -> DSC3K2_Wavelet: cv1 reads the parts in place
+                if (isinstance(cat, Concat) and not getattr(cat, "el_upsample_first", False) and cat.d == 1 and cat.i not in self.save
+                        and isinstance(nxt, M.DSC3K2_Wavelet) and nxt.f == -1 and isinstance(cat.f, list) and len(cat.f) <= 4):
+                    cat.el_lazy = True
+                    cat.forward = types.MethodType(M.concat_engine_forward, cat)
         return self
+
+
+def _dw_eligible(conv: nn.Conv2d) -> bool:
+    """Depthwise, stride 1, 'same' padding, k in {3,5,7}: what el_dwconv_fwd implements."""
+    k = conv.kernel_size[0]
+    C = conv.in_channels
+    if not M.USE_DWCONV:
+        return False
+    return (conv.groups == C == conv.out_channels and C > 1 and conv.kernel_size == (k, k) and k in (3, 5, 7) and conv.stride == (1, 1)
+            and conv.dilation == (1, 1) and conv.padding == (k // 2, k // 2) and C % 8 == 0 and (C <= 64 or C % 64 == 0))
 
 
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:

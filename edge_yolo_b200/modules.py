@@ -19,6 +19,7 @@ import math
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 
@@ -128,6 +129,9 @@ def gfl_head_forward(self, x):
 # ------------------------------------------------------------------------------------------
 
 
+USE_DWCONV = False  # el_dwconv_fwd in the engine graph (off while PyTorch's depthwise kernel is faster at the small-C sites)
+
+
 def _bias_on(self, x):
     b = self.el_bias
     if b is not None and b.device != x.device:
@@ -135,14 +139,76 @@ def _bias_on(self, x):
     return b
 
 
+def _dw_on(self, x):
+    w = getattr(self, "el_dw", None)
+    if w is not None and w.device != x.device:
+        w = self.el_dw = w.to(x.device)
+    return w
+
+
+def _pixel_linear(t: torch.Tensor) -> bool:
+    B, C, H, W = t.shape
+    sn, sc, sh, sw = t.stride()
+    return sc == 1 and C % 8 == 0 and sw % 8 == 0 and (W == 1 or sh == W * sw) and (B == 1 or H * W == 1 or sn == H * W * sw) \
+        and t.data_ptr() % 16 == 0
+
+
+def _pw_ok(conv: nn.Conv2d, srcs, *others) -> bool:
+    """el_pwconv_fwd applies: 1x1 / stride 1 / dense conv, 16-bit NHWC (or channel-slice) operands, <= 4 sources, no autograd."""
+    return (conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.groups == 1 and conv.padding in ((0, 0), 0) and conv.out_channels % 8 == 0
+            and len(srcs) <= 4 and srcs[0].is_cuda and srcs[0].dtype in (torch.bfloat16, torch.float16) and not torch.is_grad_enabled()
+            and all(_pixel_linear(t) for t in srcs) and all(t is None or _pixel_linear(t) for t in others))
+
+
+def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=None):
+    """1x1 conv over the channel concatenation of `srcs` + bias + activation (+ residual) as one tcgen05 GEMM (ops.pwconv).
+    Weight tiles are packed once per (conv, source split) and cached on the conv module."""
+    cache = conv.__dict__.setdefault("el_wpk", {})
+    key = (tuple(t.shape[1] for t in srcs), srcs[0].dtype, srcs[0].device)
+    wpk = cache.get(key)
+    if wpk is None:
+        wpk = cache[key] = ops.pack_pw_weight(conv.weight, key[0], key[1]).to(key[2])
+    return ops.pwconv(srcs, wpk, conv.out_channels, bias=bias, act=act, residual=residual, out=out, out2=out2)
+
+
+def conv2d_pw_forward(self, x):
+    """Bare nn.Conv2d 1x1 (the last conv of the Detect towers, head.py:59-74; its bias lives in the decode kernel)."""
+    if _pw_ok(self, [x]):
+        b = self.__dict__.get("el_bias32")
+        if b is None and self.bias is not None:
+            b = self.el_bias32 = self.bias.detach().float().contiguous()
+        return pw_apply(self, [x], b, ops.ACT_NONE)
+    return F.conv2d(x, self.weight, self.bias)
+
+
+def _as_list(x):
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
 def conv_engine_forward(self, x, out=None, residual=None, out2=None):
-    """Conv.forward_fuse (conv.py:58-60): conv (cuDNN, no bias) -> fused bias + activation [+ residual]."""
+    """Conv.forward_fuse (conv.py:58-60).  1x1 convs: one tcgen05 GEMM with the bias + activation [+ residual] epilogue and,
+    for a list input, the concat folded into the K loop; other convs: cuDNN (no bias) -> el_bias_act epilogue."""
+    srcs = _as_list(x)
+    if _pw_ok(self.conv, srcs, out, residual, out2):
+        return pw_apply(self.conv, srcs, _bias_on(self, srcs[0]), self.el_act, out=out, residual=residual, out2=out2)
+    x = srcs[0] if len(srcs) == 1 else torch.cat(srcs, 1)
     return ops.bias_act(self.conv(x), _bias_on(self, x), self.el_act, residual=residual, out=out, out2=out2)
+
+
+def dwconv_engine_forward(self, x, out=None, residual=None, out2=None):
+    """DWConv.forward_fuse (conv.py:107-112): depthwise conv + folded-BN bias + activation in one kernel."""
+    if residual is not None or out2 is not None:
+        return conv_engine_forward(self, x, out=out, residual=residual, out2=out2)
+    return ops.dwconv(x, _dw_on(self, x), self.el_k, bias=_bias_on(self, x), act=self.el_act, out=out)
 
 
 def dsconv_engine_forward(self, x, out=None, residual=None, out2=None):
     """DSConv.forward (conv.py:100-104) with its BatchNorm folded into the pointwise conv."""
-    return ops.bias_act(self.pw(self.dw(x)), _bias_on(self, x), ops.ACT_SILU, residual=residual, out=out, out2=out2)
+    w = _dw_on(self, x)
+    d = ops.dwconv(x, w, self.el_k) if w is not None else self.dw(x)
+    if _pw_ok(self.pw, [d], out, residual, out2):
+        return pw_apply(self.pw, [d], _bias_on(self, x), ops.ACT_SILU, out=out, residual=residual, out2=out2)
+    return ops.bias_act(self.pw(d), _bias_on(self, x), ops.ACT_SILU, residual=residual, out=out, out2=out2)
 
 
 def dsbottleneck_engine_forward(self, x, out=None):
@@ -151,46 +217,43 @@ def dsbottleneck_engine_forward(self, x, out=None):
 
 
 def dsc3k_engine_forward(self, x, out=None):
-    """C3.forward (block.py:394-396) for DSC3k: both branches land in one buffer, no torch.cat."""
-    B, _, H, W = x.shape
-    c_ = self.cv1.conv.out_channels
-    buf = torch.empty((B, 2 * c_, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    """C3.forward (block.py:394-396) for DSC3k: cv3 reads both branches in place (concat folded into its K loop)."""
     cur = self.cv1(x)
-    last = len(self.m) - 1
-    for k, blk in enumerate(self.m):
-        cur = blk(cur, out=buf[:, :c_] if k == last else None)
-    if last < 0:
-        buf[:, :c_].copy_(cur)
-    self.cv2(x, out=buf[:, c_:])
-    return self.cv3(buf, out=out)
+    for blk in self.m:
+        cur = blk(cur)
+    return self.cv3([cur, self.cv2(x)], out=out)
 
 
 def dsc3k2_wavelet_engine_forward(self, x):
-    """DSC3K2_Wavelet.forward (block.py:3783-3788): cv1 writes [a | b] into the concat buffer, the enhancer
-    updates b in place, each stacked block appends its output slice, cv2 reads the buffer."""
-    B, _, H, W = x.shape
-    c, n = self.c, len(self.m)
-    buf = torch.empty((B, (2 + n) * c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
-    # the processed half b is kept as a dense tensor as well: every consumer (DWT, merge, the stacked convs) then reads
-    # whole DRAM bursts instead of c of every (2+n)c interleaved channels, and cuDNN needs no hidden .contiguous() copy
-    b = torch.empty((B, c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
-    self.cv1(x, out=buf[:, :c], out2=b)
-    cur = wavelet_enhancer_forward(self.wave, b, inplace=True, out2=buf[:, c : 2 * c])
-    for k, blk in enumerate(self.m):
-        dst = buf[:, (2 + k) * c : (3 + k) * c]
-        if k == n - 1:
-            blk(cur, out=dst)
-        else:
-            cur = blk(cur)
-            dst.copy_(cur)
-    return self.cv2(buf)
+    """DSC3K2_Wavelet.forward (block.py:3783-3788): cv1 writes its two halves a | b as dense tensors (chunk(2, 1) is the
+    epilogue's split), the enhancer updates b in place, and cv2 reads a, b', m1(b'), ... in place: no concat buffer.
+    `x` may be the list of a lazily concatenated input (Concat in engine mode)."""
+    x0 = _as_list(x)[0]
+    B, _, H, W = x0.shape
+    c = self.c
+    a = torch.empty((B, c, H, W), device=x0.device, dtype=x0.dtype, memory_format=torch.channels_last)
+    b = torch.empty_like(a)
+    self.cv1(x, out=a, out2=b)
+    cur = wavelet_enhancer_forward(self.wave, b, inplace=True)
+    ys = [a, cur]
+    for blk in self.m:
+        cur = blk(cur)
+        ys.append(cur)
+    return self.cv2(ys)
 
 
 def psablock_engine_forward(self, x, out=None):
-    """PSABlock_LinearAttention.forward (block.py:3446-3449) with both residual adds fused into epilogues."""
+    """PSABlock_LinearAttention.forward (block.py:3446-3449) with both residual adds fused into GEMM epilogues."""
     att = self.attn
-    y = ops.linear_attention(att.qkv(x), att.num_heads)
-    x = ops.bias_act(att.proj(y), att.proj.bias.float() if att.proj.bias is not None else None, ops.ACT_NONE, residual=x)
+    if "el_bias32" not in att.qkv.__dict__:
+        att.qkv.el_bias32 = att.qkv.bias.detach().float().contiguous() if att.qkv.bias is not None else None
+        att.proj.el_bias32 = att.proj.bias.detach().float().contiguous() if att.proj.bias is not None else None
+    if _pw_ok(att.qkv, [x]) and _pw_ok(att.proj, [x]):
+        y = ops.linear_attention(pw_apply(att.qkv, [x], att.qkv.el_bias32, ops.ACT_NONE), att.num_heads)
+        x = pw_apply(att.proj, [y], att.proj.el_bias32, ops.ACT_NONE, residual=x)
+    else:
+        y = ops.linear_attention(att.qkv(x), att.num_heads)
+        x = ops.bias_act(F.conv2d(y, att.proj.weight), att.proj.el_bias32, ops.ACT_NONE, residual=x)
     return self.ffn[1](self.ffn[0](x), out=out, residual=x)
 
 
@@ -198,13 +261,12 @@ def c2psa_engine_forward(self, x):
     """C2PSA_LinearAttention.forward (block.py:3489-3497) without split / cat copies."""
     B, _, H, W = x.shape
     c = self.c
-    buf = torch.empty((B, 2 * c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
-    cur = torch.empty((B, c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
-    self.cv1(x, out=buf[:, :c], out2=cur)  # attention branch as a dense tensor, pass-through half straight into the concat buffer
-    last = len(self.m) - 1
-    for k, blk in enumerate(self.m):
-        cur = blk(cur, out=buf[:, c:] if k == last else None)
-    return self.cv2(buf)
+    a = torch.empty((B, c, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    cur = torch.empty_like(a)
+    self.cv1(x, out=a, out2=cur)  # pass-through half and attention branch as two dense tensors
+    for blk in self.m:
+        cur = blk(cur)
+    return self.cv2([a, cur])
 
 
 def sppf_engine_forward(self, x):
@@ -222,6 +284,8 @@ def concat_engine_forward(self, x):
     """Concat (conv.py Concat) whose first input is the low-resolution map of the preceding nn.Upsample."""
     if getattr(self, "el_upsample_first", False):
         return ops.upsample2x_cat(x[0], x[1])
+    if getattr(self, "el_lazy", False):  # the only consumer is a block whose cv1 folds the concat into its K loop
+        return list(x)
     return torch.cat(x, self.d)
 
 

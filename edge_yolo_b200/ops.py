@@ -518,6 +518,99 @@ def bias_act(x: torch.Tensor, bias: torch.Tensor | None, act: int = ACT_SILU, re
     return out
 
 
+def pack_dw_weight(weight: torch.Tensor) -> torch.Tensor:
+    """Depthwise Conv2d weight (C,1,k,k) -> fp32 (k*k, C) tap-major, the layout el_dwconv_fwd reads."""
+    C, one, k, k2 = weight.shape
+    if one != 1 or k != k2:
+        raise EdgelineError("pack_dw_weight: need a depthwise (C,1,k,k) weight")
+    return weight.detach().float().reshape(C, k * k).t().contiguous()
+
+
+def dwconv(x: torch.Tensor, w_packed: torch.Tensor, k: int, bias: torch.Tensor | None = None, act: int = 0,
+           out: torch.Tensor | None = None) -> torch.Tensor:
+    """Depthwise k x k conv, stride 1, padding k//2, NHWC activations; optional fused bias + activation (DSConv.dw /
+    DWConv of the reference, nn/modules/conv.py:87-112).  `w_packed` from pack_dw_weight."""
+    _need_cuda(x, w_packed)
+    B, C, H, W = x.shape
+    if w_packed.dtype != torch.float32 or tuple(w_packed.shape) != (k * k, C) or not w_packed.is_contiguous():
+        raise EdgelineError("dwconv: w_packed must be contiguous fp32 (k*k, C)")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != C or not bias.is_contiguous()):
+        raise EdgelineError("dwconv: bias must be a contiguous fp32 vector of C elements")
+    if out is None:
+        out = torch.empty((B, C, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    check(_lib.lib().el_dwconv_fwd(x.data_ptr(), _i64(x.stride()), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                   out.data_ptr(), _i64(out.stride()), B, C, H, W, int(k), int(act), _dt(x), _stream()), "el_dwconv_fwd")
+    return out
+
+
+def _pw_k_order(src_c):
+    """K order of el_pwconv_fwd's packed weights: per source, 64-channel chunks of 8-channel groups, each chunk padded to an
+    even number of groups.  Returns the source-concat channel index of every packed k (or -1 for padding)."""
+    idx, base = [], 0
+    for c in src_c:
+        if c % 8:
+            raise EdgelineError("pwconv: every source needs a multiple of 8 channels")
+        kg = c // 8
+        for g0 in range(0, kg, 8):
+            ng = min(8, kg - g0)
+            idx += list(range(base + g0 * 8, base + (g0 + ng) * 8))
+            if ng & 1:
+                idx += [-1] * 8
+        base += c
+    return idx
+
+
+def pack_pw_weight(weight: torch.Tensor, src_c, dtype=torch.bfloat16) -> torch.Tensor:
+    """1x1 conv weight (N, K[,1,1]) with K = sum(src_c) -> the UMMA operand tiles el_pwconv_fwd keeps resident in shared
+    memory: [n_tiles][k-group][n_tile][8] in `dtype` (K-major canonical no-swizzle layout, zero padded)."""
+    w = weight.detach().reshape(weight.shape[0], -1).float()
+    N, K = w.shape
+    if K != sum(src_c):
+        raise EdgelineError("pack_pw_weight: weight K does not match the sources")
+    order = _pw_k_order(src_c)
+    n_tile = _lib.lib().el_pwconv_tile(N, len(order) // 8)
+    if n_tile <= 0:
+        raise EdgelineError("pack_pw_weight: K too large for a resident weight tile")
+    n_tiles = -(-N // n_tile)
+    idx = torch.tensor(order, dtype=torch.long, device=w.device)
+    wk = torch.cat([w, torch.zeros(N, 1, device=w.device)], 1)[:, idx]          # (N, Kp); -1 picks the zero column
+    wk = torch.cat([wk, torch.zeros(n_tiles * n_tile - N, wk.shape[1], device=w.device)], 0)
+    wk = wk.view(n_tiles, n_tile, -1, 8).permute(0, 2, 1, 3).contiguous()        # [tile][k-group][row][8]
+    return wk.to(dtype)
+
+
+def pwconv(srcs, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
+           out: torch.Tensor | None = None, out2: torch.Tensor | None = None) -> torch.Tensor:
+    """1x1 conv over the channel-concatenation of `srcs` (NHWC 16-bit tensors or channel-slice views of the same B,H,W)
+    + bias + activation (+ residual) in one tcgen05 GEMM kernel.  With `out2`, channels [0, out.shape[1]) go to `out`
+    and the rest to `out2`."""
+    x0 = srcs[0]
+    _need_cuda(*srcs, wpk)
+    B, _, H, W = x0.shape
+    M = B * H * W
+
+    def pitch(t, what):
+        if t.shape[0] != B or t.shape[2] != H or t.shape[3] != W or t.dtype != x0.dtype:
+            raise EdgelineError(f"pwconv: {what} must share batch, size and dtype with the first source")
+        sn, sc, sh, sw = t.stride()
+        if sc != 1 or (W > 1 and sh != W * sw) or (H * W > 1 and B > 1 and sn != H * W * sw):
+            raise EdgelineError(f"pwconv: {what} must be an NHWC tensor or a channel slice of one")
+        return sw
+
+    if out is None:
+        out = torch.empty((B, N, H, W), device=x0.device, dtype=x0.dtype, memory_format=torch.channels_last)
+    split = out.shape[1] if out2 is not None else 0
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise EdgelineError("pwconv: bias must be a contiguous fp32 vector of N elements")
+    n = len(srcs)
+    check(_lib.lib().el_pwconv_fwd(n, _ptrs(srcs), _i64([pitch(t, "source") for t in srcs]), (c_int32 * n)(*[t.shape[1] for t in srcs]),
+                                   wpk.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                   residual.data_ptr() if residual is not None else None, pitch(residual, "residual") if residual is not None else 0,
+                                   out.data_ptr(), pitch(out, "out"), out2.data_ptr() if out2 is not None else None,
+                                   pitch(out2, "out2") if out2 is not None else 0, split, M, N, int(act), _dt(x0), _stream()), "el_pwconv_fwd")
+    return out
+
+
 def upsample2x_cat(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
     """cat[nearest-2x(x), skip] along channels in one pass (NHWC activations)."""
     _need_cuda(x, skip)

@@ -199,6 +199,26 @@ int el_bias_act_fwd(const void* x, const int64_t xs[4], const float* bias, const
 int el_upsample2x_cat_fwd(const void* x, const int64_t xs[4], const void* skip, const int64_t ss[4],
                           void* out, const int64_t os[4], int B, int C1, int C2, int H, int W,
                           int dtype, void* stream);
+/* el_dwconv_fwd: depthwise k x k convolution, stride 1, padding k/2 (k in {3,5,7}), NHWC views, optional fused
+ * bias + activation: DSConv.dw (nn/modules/conv.py:87-104, no epilogue) and DWConv + folded BatchNorm + SiLU
+ * (conv.py:107-112; Detect cls tower head.py:66-71).  w: fp32 (k*k, C) tap-major; bias fp32 (C) or NULL;
+ * act as el_bias_act_fwd.  C must be a multiple of the 16-byte channel vector and <= 64 or a multiple of 64. */
+int el_dwconv_fwd(const void* x, const int64_t xs[4], const float* w, const float* bias, void* out,
+                  const int64_t os[4], int B, int C, int H, int W, int k, int act, int dtype, void* stream);
+/* el_pwconv_fwd: pointwise (1x1) convolution + folded-BatchNorm bias + activation (+ shortcut) as one streaming
+ * tcgen05 GEMM over NHWC pixels (Conv(k=1).forward_fuse nn/modules/conv.py:58-60; DSConv.pw + bn + act conv.py:100-104;
+ * LinearAttention.qkv / proj block.py:3353-3373).  out[p, n] = act(sum_k X[p,k] W[n,k] + bias[n]) (+ res[p,n]).
+ * The K dimension is the concatenation of `nsrc` (<= 4) source tensors (src[i]: 16-bit, src_c[i] channels, multiple
+ * of 8, pixel pitch src_pitch[i] elements) -- the torch.cat of the C2f-style blocks (block.py:3783-3788) is never
+ * materialised.  Channels >= split go to out2 when out2 != NULL (chunk(2,1) of cv1).  M = B*H*W pixels; every view
+ * must be pixel-linear (address = base + p * pitch).  wpk: weights packed by the host into UMMA tiles
+ * [n_tiles][k-groups (padded per 64-channel chunk to even)][n_tile = el_pwconv_tile(N, k-groups)][8]; see ops.pack_pw_weight.
+ * bf16 / fp16 only (EL_ERR_UNSUPPORTED otherwise: the fp32 API path keeps cuDNN). */
+int el_pwconv_tile(int N, int k_groups);
+int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], const int32_t src_c[],
+                  const void* wpk, const float* bias, const void* res, int64_t res_pitch, void* out,
+                  int64_t out_pitch, void* out2, int64_t out2_pitch, int split, int64_t M, int N, int act,
+                  int dtype, void* stream);
 /* el_sppf_pool_fwd: out (B,4C,H,W) = cat[x, m(x), m(m(x)), m(m(m(x)))], m = MaxPool2d(5,1,2): the pooling
  * pyramid of SPPF (nn/modules/block.py:204-223) as separable 5/9/13 window maxima in shared memory.
  * NHWC views, H*W*64 B of shared memory (maps up to ~56x56), else EL_ERR_UNSUPPORTED. */

@@ -485,6 +485,77 @@ def test_stem_conv_u8(dtype, tol, c0, hw):
     close(got, want.float(), tol, tol)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("k", [3, 5, 7])
+@pytest.mark.parametrize("shape,epi", [((2, 16, 40, 52), False), ((3, 8, 9, 7), True), ((2, 64, 20, 20), True), ((1, 128, 11, 13), False)])
+def test_dwconv(dtype, tol, k, shape, epi):
+    """Depthwise k x k conv (+ bias + SiLU) over NHWC views (DSConv.dw / DWConv, nn/modules/conv.py:87-112) vs torch fp64."""
+    gen = torch.Generator().manual_seed(k * 100 + shape[1])
+    B, C, H, W = shape
+    full = torch.randn(B, 2 * C, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    x = full[:, C:]  # channel-slice view of a wider concat buffer
+    w = (torch.randn(C, 1, k, k, generator=gen) * 0.3).to(DEV)
+    b = torch.randn(C, generator=gen).to(DEV) if epi else None
+    want = torch.nn.functional.conv2d(x.double(), w.double(), b.double() if epi else None, padding=k // 2, groups=C)
+    if epi:
+        want = torch.nn.functional.silu(want)
+    got = ops().dwconv(x, ops().pack_dw_weight(w), k, bias=b, act=ops().ACT_SILU if epi else ops().ACT_NONE)
+    assert got.shape == want.shape
+    close(got, want.float(), tol, tol * 4)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("src_c,N,hw,opts", [
+    ([64], 64, (16, 16), {}),                                   # one full 64-channel chunk, one tile
+    ([16], 8, (9, 7), dict(act=1)),                             # N below one UMMA N step, ragged pixel tile
+    ([8], 16, (9, 15), dict(act=1, res=True)),                  # one channel group: K padded to 16
+    ([32, 32, 32], 64, (20, 20), dict(act=1)),                  # concat-free cv2 of a C2f block: three sources
+    ([16, 24, 8], 40, (13, 11), dict(act=2, res=True)),         # odd group counts per source
+    ([128], 256, (20, 20), dict(act=1, split=128)),             # cv1 with chunk(2, 1) destinations
+    ([128], 384, (10, 10), dict(bias=False)),                   # qkv: two output-channel tiles
+    ([512], 256, (20, 20), dict(act=1)),                        # SPPF cv2: 8 chunks through the ring
+    ([192, 192], 128, (40, 40), dict(act=1, slices=True)),      # sources are channel slices of wider buffers
+])
+def test_pwconv(dtype, src_c, N, hw, opts):
+    """1x1 conv (+ bias + act + residual, concat-free K, split destinations) on tcgen05 vs torch fp32 on the same 16-bit inputs
+    (Conv(k=1).forward_fuse nn/modules/conv.py:58-60; DSConv.pw conv.py:100-104).  16-bit contract: 2e-2."""
+    o = ops()
+    gen = torch.Generator().manual_seed(sum(src_c) + N)
+    B, (H, W) = 3, hw
+    cl = torch.channels_last
+    srcs = []
+    for c in src_c:
+        if opts.get("slices"):
+            full = torch.randn(B, c + 16, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl)
+            srcs.append(full[:, 8 : 8 + c])
+        else:
+            srcs.append(torch.randn(B, c, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl))
+    K = sum(src_c)
+    w = (torch.randn(N, K, generator=gen) * K ** -0.5).to(DEV)
+    bias = torch.randn(N, generator=gen).to(DEV) if opts.get("bias", True) else None
+    res = torch.randn(B, N, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl) if opts.get("res") else None
+    act = opts.get("act", 0)
+    x = torch.cat([t.float() for t in srcs], 1)
+    want = torch.einsum("bkhw,nk->bnhw", x, w.to(dtype).float())
+    if bias is not None:
+        want = want + bias.view(1, -1, 1, 1)
+    want = torch.nn.functional.silu(want) if act == 1 else (want.relu() if act == 2 else want)
+    if res is not None:
+        want = want + res.float()
+    wpk = o.pack_pw_weight(w, src_c, dtype)
+    if opts.get("split"):
+        sp = opts["split"]
+        big = torch.zeros(B, sp + 32, H, W, device=DEV, dtype=dtype).contiguous(memory_format=cl)
+        out, out2 = big[:, :sp], torch.empty(B, N - sp, H, W, device=DEV, dtype=dtype).contiguous(memory_format=cl)
+        o.pwconv(srcs, wpk, N, bias=bias, act=act, residual=res, out=out, out2=out2)
+        got = torch.cat([out, out2], 1)
+        assert float(big[:, sp:].abs().max()) == 0.0  # nothing written past the slice
+    else:
+        got = o.pwconv(srcs, wpk, N, bias=bias, act=act, residual=res)
+    assert got.shape == want.shape
+    close(got, want, 2e-2, 2e-2)
+
+
 def test_predictor_matches_api_path():
     """Predictor (graph replay, uint8 ingest) returns exactly what model + non_max_suppression return."""
     from edge_yolo_b200.engine import Predictor, build_model
