@@ -1,4 +1,4 @@
-// Pointwise (1 x 1) convolution of the inference engine as a streaming tcgen05 GEMM with a fused epilogue:
+// Pointwise (1 x 1) convolution of the inference engine as a streaming TMA + tcgen05 GEMM with a fused epilogue:
 //     out[p, n] = act( sum_k X[p, k] * W[n, k] + bias[n] ) (+ res[p, n])          p = pixel (B*H*W rows), NHWC activations
 // Replaces, for 16-bit activations, cuDNN / cuBLAS 1x1 convs followed by el_bias_act_fwd:
 //   Conv(k=1).forward_fuse      nn/modules/conv.py:58-60   (cv1 / cv2 / fuse / f_ll of DSC3K2_Wavelet block.py:3757-3788, C2PSA cv1/cv2/ffn
@@ -10,16 +10,19 @@
 // destinations (chunk(2, 1) of cv1's output).
 //
 // Roofline: HBM.  AI = 2*K*N / (2*(K+N)) flop/B <= 128 for every EdgeLine site, far below the bf16 ridge (~213 flop/B),
-// so the design goal is bytes in flight, not tensor-pipe occupancy:
-//   * A (activations): 128-pixel x 64-channel chunks stream through a ring of shared-memory stages with 16-byte
-//     cp.async (LDGSTS, L2-only), written directly in the canonical no-swizzle K-major UMMA layout
-//     [k-group of 8 channels][pixel row][16 B]; the k-group pitch is padded by 16 B so that the scattered 16 B
-//     writes of a warp spread over all banks.  S-2 stages (>= 33 KB per CTA) are in flight while one is consumed.
-//   * B (weights): pre-packed on the host into the same layout, loaded ONCE per CTA with 1-D bulk TMA copies and
-//     kept resident; CTAs are persistent over pixel tiles.
-//   * D: fp32 accumulators in TMEM, double buffered (2 x N columns); tcgen05.mma M128 x N x K16 issued by one
-//     thread, completion via tcgen05.commit -> mbarrier; epilogue reads with tcgen05.ld (thread <-> pixel row),
-//     adds the folded-BatchNorm bias, applies SiLU / ReLU, adds the shortcut, and writes 16-byte vectors.
+// so the design goal is bytes in flight and few LSU wavefronts, not tensor-pipe occupancy.  Warp-specialised, persistent:
+//   warp 0 (one lane)  TMA producer: 128-pixel x <=64-channel boxes of the activations (2-D tensor maps, 32/64/128-byte
+//                      swizzle = row bytes, out-of-range pixels / channels zero-filled by the hardware) into a ring of
+//                      shared-memory stages; full/empty mbarriers.
+//   warp 1 (one lane)  tcgen05.mma M128 x N x K16, A and B from shared memory (K-major swizzled tiles), fp32 accumulators
+//                      in TMEM, double buffered (2 x N columns); tcgen05.commit frees the stage / publishes the tile.
+//   warps 2-5          epilogue: tcgen05.ld (thread <-> pixel row), + folded-BatchNorm bias, SiLU / ReLU, + shortcut,
+//                      16-bit pack into a swizzled staging tile, TMA store (clips the ragged last pixel tile and channel
+//                      tails); overlaps the loads and MMAs of the next tile.
+// Weights are pre-packed on the host into the same swizzled tiles and stay resident in shared memory (1-D bulk copies,
+// once per CTA).
+#include <cuda.h>
+
 #include <type_traits>
 
 #include "el_common.cuh"
@@ -27,37 +30,32 @@
 namespace el {
 namespace pw {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 192;
 constexpr int kTileM = 128;
-constexpr uint32_t kLboA = 128 * 16 + 16;    // padded k-group pitch of the A stages (bytes)
 constexpr int kMaxChunks = 28;
 constexpr int kMaxSrc = 4;
+constexpr int kMaxStages = 8;
 
 struct Chunk {
-    uint16_t g0;    // first channel group (of 8) inside the source
-    uint16_t wg0;   // first k-group of this chunk in the packed weight tile
-    uint8_t src;    // source tensor
-    uint8_t ng;     // real channel groups in this chunk (1..8)
-    uint8_t ngp;    // padded to even (k-groups fed to the MMAs)
-    uint8_t pad_;
+    uint32_t w_off;   // byte offset of this chunk's weight tile in the resident weight block
+    uint16_t c0;      // first channel inside the source
+    uint8_t src;      // source tensor
+    uint8_t rb;       // row bytes of the box = swizzle span: 32, 64 or 128 (16, 32 or 64 channels)
 };
 
 struct Args {
-    const void* src[kMaxSrc];
-    int64_t pitch[kMaxSrc];  // elements between consecutive pixels
+    CUtensorMap src_map[kMaxSrc];
+    CUtensorMap out_map, out2_map;
     Chunk chunk[kMaxChunks];
     int nchunks;
-    const void* wpk;         // [n_tiles][KGp][n_tile][8] 16-bit
+    const void* wpk;         // [n_tiles][w_bytes] swizzled weight tiles
     const float* bias;       // [N] or null
     const void* res; int64_t res_pitch;
-    void* out; int64_t out_pitch;
-    void* out2; int64_t out2_pitch;
-    int split;               // channels >= split go to out2 (when out2 != null)
+    int has_out2, split;     // channels >= split go to out2
     int64_t M;
-    int N, n_tile, kgp;      // kgp = padded k-groups in total
+    int N, n_tile, ob;       // ob: channels per staging / store box (16, 32 or 64)
     int act, stages;
-    uint32_t stage_bytes;    // widest chunk's k-groups x kLboA
-    uint32_t tmem_cols;
+    uint32_t w_bytes, stage_bytes, tmem_cols;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,6 +63,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm vo
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -80,15 +79,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// 16-byte LDGSTS, L2 only; src_bytes = 0 zero-fills (rows past M, padded k-groups)
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+// 2-D tiled TMA load: box at (c0 = channel, c1 = pixel) -> shared, completion in bytes on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar),
+                 "r"(c0), "r"(c1)
+                 : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// 2-D tiled TMA store shared -> global (SASS: UTMASTG); out-of-range rows / channels are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30) (unused: one swizzle
+// atom along K), SBO>>4 [32,46) = 8 rows x row bytes, version=1 [46,48), layout [61,64): 2 = 128B, 4 = 64B, 6 = 32B swizzle
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((8 * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ uint32_t umma_idesc(int fmt, int M, int N) {  // D = f32, A/B = fmt (0 f16, 1 bf16), both K-major
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -107,6 +115,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the four epilogue warps
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {  // 32 lanes x 32 bit x 16 columns
     asm volatile(
@@ -126,40 +135,51 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
     __half2 t = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
-template <typename T>
+template <typename T, int ACT, bool RES>
 __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_constant__ Args A) {
-    extern __shared__ __align__(128) unsigned char sm[];
+    extern __shared__ __align__(1024) unsigned char sm_raw[];
+    // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the 128-byte swizzle atoms need
+    const uint32_t sbase = (smem_addr(sm_raw) + 1023u) & ~1023u;
+    unsigned char* sm = sm_raw + (sbase - smem_addr(sm_raw));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = A.stages, n_tile = A.n_tile;
-    const uint32_t w_bytes = (uint32_t)A.kgp * n_tile * 16;
-    // shared memory map: [weights][A ring][bias][barriers]
-    const uint32_t sbase = smem_addr(sm);
-    const uint32_t off_ring = (w_bytes + 127) & ~127u;
-    const uint32_t off_bias = off_ring + (uint32_t)S * A.stage_bytes;
-    const uint32_t off_bar = off_bias + (((uint32_t)n_tile * 4 + 127) & ~127u);
+    // shared memory map: [weights][stage ring][2 staging tiles 128 x ob][bias][barriers]
+    const uint32_t off_ring = (A.w_bytes + 1023u) & ~1023u;
+    const uint32_t off_stage = off_ring + (uint32_t)S * A.stage_bytes;
+    const uint32_t staging_bytes = (uint32_t)kTileM * A.ob * 2;
+    const uint32_t off_bias = off_stage + 2 * staging_bytes;
+    const uint32_t off_bar = off_bias + (((uint32_t)(n_tile + 64) * 4 + 127) & ~127u);  // + 64: the last store box may overhang n_tile
     float* s_bias = reinterpret_cast<float*>(sm + off_bias);
-    const uint32_t bar_w = sbase + off_bar;             // weights landed
-    const uint32_t bar_acc = sbase + off_bar + 8;       // [2] accumulator buffer complete
-    const uint32_t bar_free = sbase + off_bar + 24;     // [S] MMAs that read the stage are done
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + off_bar + 24 + 8 * 8);
+    const uint32_t bar_w = sbase + off_bar;                  // weights landed
+    const uint32_t bar_acc_full = sbase + off_bar + 8;       // [2] accumulator buffer complete
+    const uint32_t bar_acc_empty = sbase + off_bar + 24;     // [2] accumulator buffer drained by the epilogue
+    const uint32_t bar_full = sbase + off_bar + 40;          // [S] stage filled by TMA
+    const uint32_t bar_empty = bar_full + 8 * kMaxStages;    // [S] stage consumed by the MMAs
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + off_bar + 40 + 16 * kMaxStages);
 
     const int nt = blockIdx.y, n0 = nt * n_tile;
     const int64_t m_tiles = (A.M + kTileM - 1) / kTileM;
+    const int64_t first = blockIdx.x;
+    const int my_tiles = first < m_tiles ? (int)((m_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
+    const int nch = A.nchunks;
     constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
 
     if (tid == 0) {
         mbar_init(bar_w, 1);
-        mbar_init(bar_acc, 1);
-        mbar_init(bar_acc + 8, 1);
-        for (int s = 0; s < S; ++s) mbar_init(bar_free + 8 * s, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, 128); }
+        for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // resident weight tile of this CTA's output-channel block: bulk TMA copies, <= 32 KB each
-        mbar_expect_tx(bar_w, w_bytes);
-        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(A.wpk) + (size_t)nt * w_bytes;
-        for (uint32_t o = 0; o < w_bytes; o += 32768) bulk_g2s(sbase + o, wsrc + o, min(32768u, w_bytes - o), bar_w);
+        mbar_expect_tx(bar_w, A.w_bytes);
+        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(A.wpk) + (size_t)nt * A.w_bytes;
+        for (uint32_t o = 0; o < A.w_bytes; o += 32768) bulk_g2s(sbase + o, wsrc + o, min(32768u, A.w_bytes - o), bar_w);
     }
-    for (int i = tid; i < n_tile; i += kThreads) s_bias[i] = (A.bias && n0 + i < A.N) ? __ldg(A.bias + n0 + i) : 0.f;
+    for (int i = tid; i < n_tile + 64; i += kThreads) s_bias[i] = (A.bias && n0 + i < A.N) ? __ldg(A.bias + n0 + i) : 0.f;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(A.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -168,121 +188,167 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t idesc = umma_idesc(kFmt, kTileM, n_tile);
-    const uint32_t lbo_b = (uint32_t)n_tile * 16;
 
-    // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int64_t first = blockIdx.x;
-    const int my_tiles = first < m_tiles ? (int)((m_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
-    const int nch = A.nchunks;
-    const int total = my_tiles * nch;
-
-    // producer: item j = (tile j / nch, chunk j % nch) -> stage j % S
-    auto produce = [&](int j) {
-        const int slot = j % S, use = j / S;
-        if (use > 0) mbar_wait(bar_free + 8 * slot, (uint32_t)(use - 1) & 1);
-        const int tl = j / nch, c = j - tl * nch;
-        const Chunk ck = A.chunk[c];
-        const int64_t m0 = (first + (int64_t)tl * gridDim.x) * kTileM;
-        const T* base = reinterpret_cast<const T*>(A.src[ck.src]);
-        const int64_t pitch = A.pitch[ck.src];
-        const uint32_t stage = sbase + off_ring + (uint32_t)slot * A.stage_bytes;
-        const int ngp = ck.ngp;
-        int row = tid / ngp, g = tid - row * ngp;
-        const int pieces = kTileM * ngp;
-        const bool regular = (kThreads % ngp) == 0;  // 2, 4, 8 k-groups: (row, g) advance by a fixed row step
-        const int rstep = kThreads / ngp;
-        for (int p = tid; p < pieces; p += kThreads) {
-            if (!regular) { row = p / ngp; g = p - row * ngp; }
-            const int64_t m = m0 + row;
-            const bool valid = m < A.M && g < ck.ng;
-            const T* src = valid ? base + m * pitch + (int64_t)(ck.g0 + g) * 8 : base;
-            cp_async16(stage + (uint32_t)g * kLboA + (uint32_t)row * 16, src, valid ? 16u : 0u);
-            row += rstep;
-        }
-    };
-
-    const int dist = S - 2;  // stages in flight ahead of the consumer
-    for (int j = 0; j < dist; ++j) {
-        if (j < total) produce(j);
-        cp_async_commit();
-    }
-    if (tid == 0) mbar_wait(bar_w, 0);
-
-    for (int j = 0; j < total; ++j) {
-        if (j + dist < total) produce(j + dist);
-        cp_async_commit();
-        // groups are committed once per loop trip (empty ones included), so "all but the newest `dist`" = item j has landed
-        switch (dist) {
-            case 1: cp_async_wait<1>(); break;
-            case 2: cp_async_wait<2>(); break;
-            case 3: cp_async_wait<3>(); break;
-            case 4: cp_async_wait<4>(); break;
-            case 5: cp_async_wait<5>(); break;
-            default: cp_async_wait<6>(); break;
-        }
-        proxy_fence();  // LDGSTS writes (generic proxy) -> visible to the tensor core (async proxy)
-        __syncthreads();
-        const int tl = j / nch, c = j - tl * nch;
-        const int buf = tl & 1;
-        const bool last = c == nch - 1;
-        if (tid == 0) {
-            tc_fence_after();
-            const Chunk ck = A.chunk[c];
-            const uint32_t stage = sbase + off_ring + (uint32_t)(j % S) * A.stage_bytes;
-            const uint32_t d = tmem + (uint32_t)buf * n_tile;
-            for (int ks = 0; ks < ck.ngp / 2; ++ks) {
-                const uint64_t da = umma_desc(stage + (uint32_t)(2 * ks) * kLboA, kLboA, 128);
-                const uint64_t db = umma_desc(sbase + (uint32_t)(ck.wg0 + 2 * ks) * lbo_b, lbo_b, 128);
-                umma(d, da, db, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-            }
-            umma_commit(bar_free + 8 * (j % S));
-            if (last) umma_commit(bar_acc + 8 * buf);
-        }
-        if (last) {
-            // ---------------------------------------------------------------- epilogue of tile tl (thread <-> pixel row)
-            mbar_wait(bar_acc + 8 * buf, (uint32_t)(tl >> 1) & 1);
-            tc_fence_after();
-            const int64_t m = (first + (int64_t)tl * gridDim.x) * kTileM + tid;
-            const bool valid = m < A.M;
-            const uint32_t taddr = tmem + (uint32_t)buf * n_tile + ((uint32_t)(warp * 32) << 16);
-            const T* rrow = A.res ? reinterpret_cast<const T*>(A.res) + m * A.res_pitch + n0 : nullptr;
-            T* orow = reinterpret_cast<T*>(A.out) + m * A.out_pitch;
-            T* orow2 = A.out2 ? reinterpret_cast<T*>(A.out2) + m * A.out2_pitch : nullptr;
-            for (int c0 = 0; c0 < n_tile; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);  // warp-collective: executed by all lanes, stores predicated below
-                if (!valid || n0 + c0 >= A.N) continue;
-                float f[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float t = __uint_as_float(v[e]) + s_bias[c0 + e];
-                    f[e] = A.act == 1 ? __fdividef(t, 1.f + __expf(-t)) : (A.act == 2 ? fmaxf(t, 0.f) : t);
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int m0 = (int)((first + (int64_t)tl * gridDim.x) * kTileM);
+                for (int c = 0; c < nch; ++c, ++it) {
+                    const int s = it % S, use = it / S;
+                    if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)(use - 1) & 1);
+                    const Chunk ck = A.chunk[c];
+                    mbar_expect_tx(bar_full + 8 * s, (uint32_t)kTileM * ck.rb);
+                    tma_load_2d(sbase + off_ring + (uint32_t)s * A.stage_bytes, &A.src_map[ck.src], ck.c0, m0, bar_full + 8 * s);
                 }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(kFmt, kTileM, n_tile);
+            mbar_wait(bar_w, 0);
+            int it = 0;
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int b = tl & 1, ub = tl >> 1;
+                if (ub > 0) mbar_wait(bar_acc_empty + 8 * b, (uint32_t)(ub - 1) & 1);
+                tc_fence_after();
+                const uint32_t d = tmem + (uint32_t)b * n_tile;
+                for (int c = 0; c < nch; ++c, ++it) {
+                    const int s = it % S;
+                    mbar_wait(bar_full + 8 * s, (uint32_t)(it / S) & 1);
+                    tc_fence_after();
+                    const Chunk ck = A.chunk[c];
+                    const uint32_t a_base = sbase + off_ring + (uint32_t)s * A.stage_bytes, b_base = sbase + ck.w_off;
+                    for (int ks = 0; ks < ck.rb / 32; ++ks)  // one MMA per 16 channels = 32 bytes along K inside the swizzle atom
+                        umma(d, umma_desc_sw(a_base + 32 * ks, ck.rb), umma_desc_sw(b_base + 32 * ks, ck.rb), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                    umma_commit(bar_empty + 8 * s);
+                }
+                umma_commit(bar_acc_full + 8 * b);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------ epilogue warps
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;          // pixel row inside the tile
+        const int et = tid - 64;                // 0..127
+        const int ob = A.ob, rbo = ob * 2;      // staging row bytes = swizzle span of the store box
+        const uint32_t swz = ((uint32_t)(row * rbo) >> 7) & (uint32_t)(rbo / 16 - 1);
+        const int n_real = min(n_tile, A.N - n0);
+        int sub = 0;  // staging buffer use counter
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int b = tl & 1;
+            const int64_t m0 = (first + (int64_t)tl * gridDim.x) * kTileM;
+            mbar_wait(bar_acc_full + 8 * b, (uint32_t)(tl >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem + (uint32_t)b * n_tile + ((uint32_t)(q * 32) << 16);
+            const T* rrow = RES ? reinterpret_cast<const T*>(A.res) + (m0 + row) * A.res_pitch + n0 : nullptr;
+            const bool rvalid = m0 + row < A.M;
+            for (int c0 = 0; c0 < n_real; c0 += ob, ++sub) {
+                const uint32_t stg = sbase + off_stage + (uint32_t)(sub & 1) * staging_bytes;
+                if (et == 0) bulk_wait_read<1>();  // the store that last read this staging buffer (two uses ago) is done with it
+                epi_barrier();
+                for (int j = 0; j < ob; j += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c0 + j, v);
+                    float f[16];
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0 + j);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int n = n0 + c0 + 8 * h;
-                    if (n >= A.N) break;
-                    if (rrow) {
-                        float r8[8];
-                        unpack<T>(ldg_stream(rrow + c0 + 8 * h), r8);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[8 * h + e] += r8[e];
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const float4 bb = b4[e4];
+                        f[4 * e4] = __uint_as_float(v[4 * e4]) + bb.x; f[4 * e4 + 1] = __uint_as_float(v[4 * e4 + 1]) + bb.y;
+                        f[4 * e4 + 2] = __uint_as_float(v[4 * e4 + 2]) + bb.z; f[4 * e4 + 3] = __uint_as_float(v[4 * e4 + 3]) + bb.w;
                     }
-                    uint4 o;
-                    o.x = pack2<T>(f[8 * h], f[8 * h + 1]); o.y = pack2<T>(f[8 * h + 2], f[8 * h + 3]);
-                    o.z = pack2<T>(f[8 * h + 4], f[8 * h + 5]); o.w = pack2<T>(f[8 * h + 6], f[8 * h + 7]);
-                    T* dst = (orow2 && n >= A.split) ? orow2 + (n - A.split) : orow + n;
-                    *reinterpret_cast<uint4*>(dst) = o;
+                    if (ACT == 1) {  // SiLU: x * sigmoid(x) = h + h * tanh(h), h = x / 2 (one MUFU per element; 16-bit outputs)
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) { const float h = 0.5f * f[e]; f[e] = fmaf(h, tanh_fast(h), h); }
+                    } else if (ACT == 2) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (RES) {
+                            if (rvalid && n0 + c0 + j + 8 * h < A.N) {
+                                float r8[8];
+                                unpack<T>(ldg_stream(rrow + c0 + j + 8 * h), r8);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[8 * h + e] += r8[e];
+                            }
+                        }
+                        uint4 o;
+                        o.x = pack2<T>(f[8 * h], f[8 * h + 1]); o.y = pack2<T>(f[8 * h + 2], f[8 * h + 3]);
+                        o.z = pack2<T>(f[8 * h + 4], f[8 * h + 5]); o.w = pack2<T>(f[8 * h + 6], f[8 * h + 7]);
+                        const uint32_t chunk = (uint32_t)(j / 8 + h) ^ swz;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)row * rbo + chunk * 16), "r"(o.x), "r"(o.y), "r"(o.z),
+                                     "r"(o.w)
+                                     : "memory");
+                    }
+                }
+                proxy_fence();  // generic-proxy writes of the staging tile -> visible to the TMA store (async proxy)
+                epi_barrier();
+                if (et == 0) {
+                    const int n = n0 + c0;
+                    if (A.has_out2 && n >= A.split) tma_store_2d(&A.out2_map, n - A.split, (int)m0, stg);
+                    else tma_store_2d(&A.out_map, n, (int)m0, stg);
+                    bulk_commit();
                 }
             }
-            tc_fence_before();  // TMEM reads of this buffer are ordered before the MMAs that reuse it (two tiles later)
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty + 8 * b);
         }
+        if (et == 0) bulk_wait_read<0>();
     }
-    cp_async_wait<0>();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(A.tmem_cols));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// (channels, pixels) view with `pitch` elements between pixels; box = (row_bytes / 2 channels, 128 pixels), swizzle span = row bytes
+static bool make_map(CUtensorMap* map, const void* base, int channels, int64_t M, int64_t pitch, int row_bytes, int dtype) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)channels, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)(row_bytes / 2), (cuuint32_t)kTileM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    return fn(map, dtype == EL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static inline int box_bytes_for(int channels) { return channels <= 16 ? 32 : (channels <= 32 ? 64 : 128); }
+
+template <typename T>
+static cudaError_t launch(const Args& A, dim3 grid, size_t smem, bool res, cudaStream_t st) {
+#define EL_PW_LAUNCH(ACT, RES)                                                                                                          \
+    {                                                                                                                                   \
+        cudaError_t e = cudaFuncSetAttribute(pwconv_tc_kernel<T, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
+        if (e != cudaSuccess) return e;                                                                                                 \
+        pwconv_tc_kernel<T, ACT, RES><<<grid, kThreads, smem, st>>>(A);                                                                 \
+        return cudaSuccess;                                                                                                             \
+    }
+    if (res) {
+        if (A.act == 0) EL_PW_LAUNCH(0, true) else if (A.act == 1) EL_PW_LAUNCH(1, true) else EL_PW_LAUNCH(2, true)
+    } else {
+        if (A.act == 0) EL_PW_LAUNCH(0, false) else if (A.act == 1) EL_PW_LAUNCH(1, false) else EL_PW_LAUNCH(2, false)
+    }
+#undef EL_PW_LAUNCH
 }
 
 }  // namespace pw
@@ -290,11 +356,12 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
 
 using namespace el;
 
-extern "C" int el_pwconv_tile(int N, int k_groups) {
-    // output channels per CTA: multiple of 16, <= 256, resident weight tile (k_groups * 16 B per row) <= 144 KB, as even a split as possible
-    if (N <= 0 || k_groups <= 0) return 0;
+extern "C" int el_pwconv_tile(int N, int w_row_bytes) {
+    // output channels per CTA: multiple of 16, <= 256, resident weight block (w_row_bytes per output channel) <= 128 KB, as even a split
+    // as possible
+    if (N <= 0 || w_row_bytes <= 0) return 0;
     const int n16 = (int)ceil_div(N, 16) * 16;
-    int max_rows = (int)((144 * 1024) / ((int64_t)k_groups * 16)) & ~15;
+    int max_rows = (int)((128 * 1024) / (int64_t)w_row_bytes) & ~15;
     if (max_rows > 256) max_rows = 256;
     if (max_rows < 16) return 0;
     const int tiles = (int)ceil_div(n16, max_rows);
@@ -306,51 +373,60 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
                              int N, int act, int dtype, void* stream) {
     if (nsrc < 1 || nsrc > pw::kMaxSrc || !src || !src_pitch || !src_c || !wpk || !out || M <= 0 || N <= 0 || act < 0 || act > 2) return EL_ERR_ARG;
     if (dtype != EL_BF16 && dtype != EL_F16) return EL_ERR_UNSUPPORTED;
-    if (N % 8 || (out2 && (split % 8 || split <= 0 || split >= N))) return EL_ERR_UNSUPPORTED;
-    pw::Args A{};
-    int nch = 0, wg = 0;
-    for (int i = 0; i < nsrc; ++i) {
-        if (!src[i] || src_c[i] <= 0 || src_c[i] % 8 || src_pitch[i] % 8 || !aligned16(src[i])) return EL_ERR_UNSUPPORTED;
-        A.src[i] = src[i];
-        A.pitch[i] = src_pitch[i];
-        const int kg = src_c[i] / 8;
-        for (int g0 = 0; g0 < kg; g0 += 8) {
-            if (nch >= pw::kMaxChunks) return EL_ERR_UNSUPPORTED;
-            const int ng = kg - g0 < 8 ? kg - g0 : 8;
-            pw::Chunk& c = A.chunk[nch++];
-            c.g0 = (uint16_t)g0; c.wg0 = (uint16_t)wg; c.src = (uint8_t)i; c.ng = (uint8_t)ng; c.ngp = (uint8_t)((ng + 1) & ~1);
-            wg += c.ngp;
-        }
-    }
+    if (N % 8 || M >= (1ll << 31) - 256 || (out2 && (split % 16 || split <= 0 || split >= N))) return EL_ERR_UNSUPPORTED;
     if (!aligned16(out) || out_pitch % 8 || (out2 && (!aligned16(out2) || out2_pitch % 8)) || (res && (!aligned16(res) || res_pitch % 8)))
         return EL_ERR_UNSUPPORTED;
+    for (int i = 0; i < nsrc; ++i)
+        if (!src[i] || src_c[i] <= 0 || src_c[i] % 8 || src_pitch[i] % 8 || !aligned16(src[i])) return EL_ERR_UNSUPPORTED;
+    pw::Args A{};
+    // K chunks: per source, boxes of 64 channels (16 / 32 when the whole source is that narrow); tails are zero-filled by TMA
+    int nch = 0, w_row_bytes = 0, max_rb = 32;
+    for (int i = 0; i < nsrc; ++i) {
+        const int rb = pw::box_bytes_for(src_c[i]);
+        for (int c0 = 0; c0 < src_c[i]; c0 += rb / 2) {
+            if (nch >= pw::kMaxChunks) return EL_ERR_UNSUPPORTED;
+            pw::Chunk& c = A.chunk[nch++];
+            c.c0 = (uint16_t)c0; c.src = (uint8_t)i; c.rb = (uint8_t)rb;
+            w_row_bytes += rb;
+        }
+        max_rb = rb > max_rb ? rb : max_rb;
+    }
     A.nchunks = nch;
-    A.kgp = wg;
-    A.wpk = wpk; A.bias = bias; A.res = res; A.res_pitch = res_pitch;
-    A.out = out; A.out_pitch = out_pitch; A.out2 = out2; A.out2_pitch = out2_pitch; A.split = out2 ? split : N;
-    A.M = M; A.N = N; A.act = act;
-    A.n_tile = el_pwconv_tile(N, wg);
+    A.n_tile = el_pwconv_tile(N, w_row_bytes);
     if (A.n_tile <= 0) return EL_ERR_UNSUPPORTED;
+    uint32_t w_off = 0;
+    for (int i = 0; i < nch; ++i) {  // every weight tile starts on a 1024 B boundary (swizzle atom alignment)
+        A.chunk[i].w_off = w_off;
+        w_off += ((uint32_t)A.n_tile * A.chunk[i].rb + 1023u) & ~1023u;
+    }
+    A.w_bytes = w_off;
+    A.stage_bytes = (uint32_t)pw::kTileM * max_rb;
     const int n_tiles = (int)ceil_div(N, A.n_tile);
+    // store box: up to 64 channels; with two destinations it must not straddle the split
+    int ob = 64;
+    if (out2) while (split % ob) ob >>= 1;
+    while (ob > 16 && ob / 2 >= A.n_tile) ob >>= 1;
+    if (ob < 16) return EL_ERR_UNSUPPORTED;
+    A.ob = ob;
+    A.wpk = wpk; A.bias = bias; A.res = res; A.res_pitch = res_pitch;
+    A.has_out2 = out2 != nullptr; A.split = out2 ? split : N;
+    A.M = M; A.N = N; A.act = act;
     uint32_t cols = 32;
     while (cols < 2u * A.n_tile) cols <<= 1;
     if (cols > 512) return EL_ERR_UNSUPPORTED;
     A.tmem_cols = cols;
-    const size_t w_bytes = (size_t)A.kgp * A.n_tile * 16;
-    const size_t fixed = ((w_bytes + 127) & ~(size_t)127) + (((size_t)A.n_tile * 4 + 127) & ~(size_t)127) + 24 + 8 * 8 + 16;
-    int max_ngp = 2;
-    for (int i = 0; i < nch; ++i) max_ngp = A.chunk[i].ngp > max_ngp ? A.chunk[i].ngp : max_ngp;
-    A.stage_bytes = (uint32_t)max_ngp * pw::kLboA;
-    // shared memory per CTA: the smallest of 56 / 100 / 220 KB (4 / 2 / 1 CTAs per SM) that still holds a ring of >= 5 stages
-    // (>= 3 in flight); with resident weights too large for that, whatever ring fits in 220 KB (>= 3 stages)
+    const size_t fixed = 1024 /* alignment slack */ + ((A.w_bytes + 1023u) & ~1023u) + 2 * (size_t)pw::kTileM * ob * 2 +
+                         (((size_t)(A.n_tile + 64) * 4 + 127) & ~(size_t)127) + 40 + 16 * pw::kMaxStages + 16;
+    // shared memory per CTA: the smallest of 56 / 100 / 220 KB (4 / 2 / 1 CTAs per SM) that holds a ring of >= 4 stages; with
+    // resident weights too large for that, whatever ring fits in 220 KB (>= 2 stages)
     int S = 0;
     for (size_t budget : {(size_t)56 * 1024, (size_t)100 * 1024, (size_t)220 * 1024}) {
         if (budget <= fixed) continue;
         S = (int)((budget - fixed) / A.stage_bytes);
-        if (S >= 5) break;
+        if (S >= 4) break;
     }
-    if (S < 3) return EL_ERR_UNSUPPORTED;
-    if (S > 8) S = 8;
+    if (S < 2) return EL_ERR_UNSUPPORTED;
+    if (S > pw::kMaxStages) S = pw::kMaxStages;
     A.stages = S;
     const size_t smem = fixed + (size_t)S * A.stage_bytes;
     int per_sm = (int)(227 * 1024 / (smem + 1024));
@@ -361,18 +437,14 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     int64_t gx = (int64_t)kSMs * per_sm / n_tiles;
     if (gx < 1) gx = 1;
     if (gx > m_tiles) gx = m_tiles;
+    for (int i = 0; i < nsrc; ++i)
+        if (!pw::make_map(&A.src_map[i], src[i], src_c[i], M, src_pitch[i], pw::box_bytes_for(src_c[i]), dtype)) return EL_ERR_CUDA;
+    if (!pw::make_map(&A.out_map, out, out2 ? split : N, M, out_pitch, ob * 2, dtype)) return EL_ERR_CUDA;
+    if (out2 && !pw::make_map(&A.out2_map, out2, N - split, M, out2_pitch, ob * 2, dtype)) return EL_ERR_CUDA;
     dim3 grid((unsigned)gx, (unsigned)n_tiles);
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e;
-    if (dtype == EL_BF16) {
-        e = cudaFuncSetAttribute(pw::pwconv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
-        pw::pwconv_tc_kernel<__nv_bfloat16><<<grid, pw::kThreads, smem, st>>>(A);
-    } else {
-        e = cudaFuncSetAttribute(pw::pwconv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
-        pw::pwconv_tc_kernel<__half><<<grid, pw::kThreads, smem, st>>>(A);
-    }
+    const cudaError_t e = dtype == EL_BF16 ? pw::launch<__nv_bfloat16>(A, grid, smem, res != nullptr, st) : pw::launch<__half>(A, grid, smem, res != nullptr, st);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
     note_launches(1);
     return check_launch();
 }

@@ -543,40 +543,48 @@ def dwconv(x: torch.Tensor, w_packed: torch.Tensor, k: int, bias: torch.Tensor |
     return out
 
 
-def _pw_k_order(src_c):
-    """K order of el_pwconv_fwd's packed weights: per source, 64-channel chunks of 8-channel groups, each chunk padded to an
-    even number of groups.  Returns the source-concat channel index of every packed k (or -1 for padding)."""
-    idx, base = [], 0
+def _pw_chunks(src_c):
+    """K chunks of el_pwconv_fwd: per source, TMA boxes of 64 channels (16 / 32 when the whole source is that narrow).
+    Returns [(first channel in the concatenated K, real channels, box channels)]."""
+    chunks, base = [], 0
     for c in src_c:
         if c % 8:
             raise EdgelineError("pwconv: every source needs a multiple of 8 channels")
-        kg = c // 8
-        for g0 in range(0, kg, 8):
-            ng = min(8, kg - g0)
-            idx += list(range(base + g0 * 8, base + (g0 + ng) * 8))
-            if ng & 1:
-                idx += [-1] * 8
+        bw = 16 if c <= 16 else (32 if c <= 32 else 64)
+        for c0 in range(0, c, bw):
+            chunks.append((base + c0, min(bw, c - c0), bw))
         base += c
-    return idx
+    return chunks
 
 
 def pack_pw_weight(weight: torch.Tensor, src_c, dtype=torch.bfloat16) -> torch.Tensor:
-    """1x1 conv weight (N, K[,1,1]) with K = sum(src_c) -> the UMMA operand tiles el_pwconv_fwd keeps resident in shared
-    memory: [n_tiles][k-group][n_tile][8] in `dtype` (K-major canonical no-swizzle layout, zero padded)."""
+    """1x1 conv weight (N, K[,1,1]) with K = sum(src_c) -> the resident UMMA B operand of el_pwconv_fwd: per output-channel
+    tile, one K-major tile [n_tile][box channels] per K chunk, stored with the 32/64/128-byte swizzle of its row width
+    (16-byte chunk j of row r lands at chunk j ^ ((r * row_bytes >> 7) & (row_bytes / 16 - 1))), each tile padded to 1024 B."""
     w = weight.detach().reshape(weight.shape[0], -1).float()
     N, K = w.shape
     if K != sum(src_c):
         raise EdgelineError("pack_pw_weight: weight K does not match the sources")
-    order = _pw_k_order(src_c)
-    n_tile = _lib.lib().el_pwconv_tile(N, len(order) // 8)
+    chunks = _pw_chunks(src_c)
+    n_tile = _lib.lib().el_pwconv_tile(N, sum(2 * bw for _, _, bw in chunks))
     if n_tile <= 0:
         raise EdgelineError("pack_pw_weight: K too large for a resident weight tile")
     n_tiles = -(-N // n_tile)
-    idx = torch.tensor(order, dtype=torch.long, device=w.device)
-    wk = torch.cat([w, torch.zeros(N, 1, device=w.device)], 1)[:, idx]          # (N, Kp); -1 picks the zero column
-    wk = torch.cat([wk, torch.zeros(n_tiles * n_tile - N, wk.shape[1], device=w.device)], 0)
-    wk = wk.view(n_tiles, n_tile, -1, 8).permute(0, 2, 1, 3).contiguous()        # [tile][k-group][row][8]
-    return wk.to(dtype)
+    wp = torch.zeros(n_tiles * n_tile, K, device=w.device)
+    wp[:N] = w
+    rows = torch.arange(n_tile, device=w.device)
+    out = []
+    for t in range(n_tiles):
+        for k0, creal, bw in chunks:
+            tile = torch.zeros(n_tile, bw, device=w.device)
+            tile[:, :creal] = wp[t * n_tile : (t + 1) * n_tile, k0 : k0 + creal]
+            rb = 2 * bw
+            f = ((rows * rb) >> 7) & (rb // 16 - 1)
+            idx = torch.arange(bw // 8, device=w.device).view(1, -1) ^ f.view(-1, 1)       # dest[r, p] = tile[r, p ^ f(r)]
+            sw = tile.view(n_tile, bw // 8, 8).gather(1, idx.view(n_tile, -1, 1).expand(-1, -1, 8)).reshape(-1).to(dtype)
+            pad = (-sw.numel() * 2) % 1024 // 2
+            out.append(torch.cat([sw, torch.zeros(pad, device=w.device, dtype=dtype)]) if pad else sw)
+    return torch.cat(out).contiguous()
 
 
 def pwconv(srcs, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
