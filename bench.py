@@ -145,11 +145,12 @@ def profile_kernels(pred, a, iters=10):
     shims = {
         "dwt_haar": lambda out, x: 2 * x.numel() * e(x),
         "wave_merge": lambda out, b, LLp, *r: int(4.5 * b.numel() * e(b)),
+        "wave_merge_bands": lambda out, LLp, *r: int(2.5 * out.numel() // 2 * e(out)),
         "gated_residual": lambda out, b, y, g, **k: 3 * b.numel() * e(b),
         "linear_attention": lambda out, qkv, heads: (qkv.numel() + out.numel()) * e(qkv),
         "gfl_decode": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss) + out.numel() * 4,
         "bias_act": lambda _o, x, bias, act=1, residual=None, **k: (2 + (residual is not None)) * x.numel() * e(x),
-        "pwconv": lambda _o, srcs, wpk, N, bias=None, act=0, residual=None, out=None, out2=None: (
+        "pwconv": lambda _o, srcs, wpk, N, bias=None, act=0, residual=None, out=None, out2=None, res_scale=1.0: (
             sum(t.numel() for t in srcs) + srcs[0].numel() // srcs[0].shape[1] * N * (1 + (residual is not None))) * e(srcs[0]),
         "dwconv": lambda _o, x, *r, **k: 2 * x.numel() * e(x),
         "upsample2x_cat": lambda _o, x, skip: (x.numel() + skip.numel() + _o.numel()) * e(x),
@@ -316,6 +317,7 @@ def product_arm(a):
         # ---- leg 2: end to end through the public API: pinned host uint8 in, pinned host detections out
         for _ in range(min(a.warmup, 3)):
             pred.predict_u8(host_u8)
+        pred.predict_many([host_u8] * 3)  # allocates the pipeline's pinned / staging buffers outside the timed region
         barrier()
         kept_per_step = []
         t0 = time.perf_counter()

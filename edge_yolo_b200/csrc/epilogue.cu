@@ -196,57 +196,84 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(const T* __restrict__ x,
 // Stem: uint8 HWC image -> Conv(3, C0, k=3, s=2, p=1) + folded BatchNorm + SiLU -> NHWC activations, in one pass.
 // Replaces, for the inference engine, the uint8->float preprocess (engine/predictor.py:117-135), layer 0 of the yaml
 // (cfg/models/11/yolo11-test.yaml:21, a cuDNN conv that PyTorch runs through an fp32 NHWC round trip for 3 input channels)
-// and its bias + SiLU epilogue.  The 1/255 scale is folded into the weights by the caller.  One thread = one output pixel,
-// all C0 output channels in registers; the 17 x 65 pixel input patch of a 8 x 32 output tile is staged in shared memory.
+// and its bias + SiLU epilogue.  The 1/255 scale is folded into the weights by the caller.
+// CUDA-core FMA kernel balanced against the shared-memory pipe: a thread computes 4 adjacent output pixels x 16 output
+// channels, so every 16-byte weight broadcast (LDS.128 = 4 LSU cycles per warp) feeds 16 FMAs per lane; the 17 x 129 pixel
+// input patch of an 8 x 64 output tile is staged once per CTA as fp32 (uint8 -> float without the conversion pipe: 0x4B000000 | b).
+constexpr int kStemTW = 64, kStemTH = 8, kStemIW = 2 * kStemTW + 1, kStemIH = 2 * kStemTH + 1, kStemRow = kStemIW * 3 + 1;  // 388 floats per patch row
+
 template <typename T, int C0>
-__global__ void __launch_bounds__(256) stem_conv_u8_kernel(const uint8_t* __restrict__ src, const float* __restrict__ w, const float* __restrict__ bias,
+__global__ void __launch_bounds__(128) stem_conv_u8_kernel(const uint8_t* __restrict__ src, const float* __restrict__ w, const float* __restrict__ bias,
                                                            T* __restrict__ dst, Strides4 ds, int H, int W) {
-    constexpr int TW = 32, TH = 8, IW = 2 * TW + 1, IH = 2 * TH + 1, IROW = IW * 3;
-    __shared__ __align__(16) float s_w[27 * C0];  // [tap = (ky*3+kx)*3+ci][co]
-    __shared__ float s_b[C0];
-    __shared__ uint8_t s_in[IH][IROW + 1];
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
+    extern __shared__ __align__(16) float s_stem[];
+    float* s_w = s_stem;                       // [tap = (ky*3+kx)*3+ci][co]
+    float* s_b = s_w + 27 * C0;                // [co]
+    float* s_in = s_b + C0;                    // [kStemIH][kStemRow]
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * kStemTW, oy0 = blockIdx.y * kStemTH;
     const int64_t n = blockIdx.z;
-    for (int i = tid; i < 27 * C0; i += 256) {  // caller layout (C0, 3, 3, 3) = [co][ci][ky][kx] -> [tap][co]
+    for (int i = tid; i < 27 * C0; i += 128) {  // caller layout (C0, 3, 3, 3) = [co][ci][ky][kx] -> [tap][co]
         const int co = i / 27, r = i - co * 27, ci = r / 9, k = r - ci * 9;
         s_w[(k * 3 + ci) * C0 + co] = __ldg(w + i);
     }
     if (tid < C0) s_b[tid] = __ldg(bias + tid);
     const uint8_t* img = src + n * (int64_t)H * W * 3;
     const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
-    for (int i = tid; i < IH * IROW; i += 256) {
-        const int r = i / IROW, cb = i - r * IROW, px = cb / 3, ch = cb - px * 3;
+    for (int i = tid; i < kStemIH * (kStemIW * 3); i += 128) {
+        const int r = i / (kStemIW * 3), cb = i - r * (kStemIW * 3), px = cb / 3;
         const int iy = iy0 + r, ix = ix0 + px;
-        s_in[r][cb] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + ((int64_t)iy * W + ix) * 3 + ch) : (uint8_t)0;
+        const uint32_t b = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + ((int64_t)iy * W + ix0) * 3 + cb) : 0u;
+        s_in[r * kStemRow + cb] = __uint_as_float(0x4B000000u | b) - 8388608.f;
     }
     __syncthreads();
-    const int ox = ox0 + tx, oy = oy0 + ty;
+    const int cg = tid & 15, ty = tid >> 4;  // 16 column groups of 4 pixels x 8 rows
+    const int ox = ox0 + 4 * cg, oy = oy0 + ty;
     if (ox >= W / 2 || oy >= H / 2) return;
-    float acc[C0];
+    constexpr int V = Vec16<T>::N;
+#pragma unroll 1
+    for (int cb = 0; cb < C0; cb += 16) {
+        float acc[4][16];
 #pragma unroll
-    for (int c = 0; c < C0; ++c) acc[c] = s_b[c];
+        for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
+            for (int c = 0; c < 16; ++c) acc[p][c] = s_b[cb + c];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {  // t = kx*3 + ci: 9 consecutive bytes of the patch row
-            const float v = (float)s_in[2 * ty + ky][6 * tx + t];
-            const float4* wp = reinterpret_cast<const float4*>(s_w + (ky * 9 + t) * C0);
+        for (int ky = 0; ky < 3; ++ky) {
+            float v[27];  // 9 input pixels x 3 channels of patch row 2*ty + ky, starting at pixel 8*cg
+            const float* row = s_in + (2 * ty + ky) * kStemRow + 24 * cg;
 #pragma unroll
-            for (int c4 = 0; c4 < C0 / 4; ++c4) {
-                const float4 w4 = wp[c4];  // same address for the whole warp: broadcast
-                acc[4 * c4] += v * w4.x; acc[4 * c4 + 1] += v * w4.y; acc[4 * c4 + 2] += v * w4.z; acc[4 * c4 + 3] += v * w4.w;
+            for (int t = 0; t < 24; t += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(row + t);
+                v[t] = q.x; v[t + 1] = q.y; v[t + 2] = q.z; v[t + 3] = q.w;
+            }
+            v[24] = row[24]; v[25] = row[25]; v[26] = row[26];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {  // t = kx*3 + ci
+                const float4* wp = reinterpret_cast<const float4*>(s_w + (ky * 9 + t) * C0 + cb);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const float4 w4 = wp[c4];  // same address for the whole warp: broadcast
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float x = v[6 * p + t];
+                        acc[p][4 * c4] = fmaf(x, w4.x, acc[p][4 * c4]); acc[p][4 * c4 + 1] = fmaf(x, w4.y, acc[p][4 * c4 + 1]);
+                        acc[p][4 * c4 + 2] = fmaf(x, w4.z, acc[p][4 * c4 + 2]); acc[p][4 * c4 + 3] = fmaf(x, w4.w, acc[p][4 * c4 + 3]);
+                    }
+                }
             }
         }
-    }
-    constexpr int V = Vec16<T>::N;
-    T* q = dst + n * ds.n + (int64_t)oy * ds.h + (int64_t)ox * ds.w;
 #pragma unroll
-    for (int g = 0; g < C0 / V; ++g) {
-        float f[V];
+        for (int p = 0; p < 4; ++p) {
+            if (ox + p >= W / 2) break;
+            T* q = dst + n * ds.n + (int64_t)oy * ds.h + (int64_t)(ox + p) * ds.w + cb;
 #pragma unroll
-        for (int e = 0; e < V; ++e) f[e] = silu_f<T>(acc[g * V + e]);
-        *reinterpret_cast<uint4*>(q + g * V) = pack<T>(f);
+            for (int g = 0; g < 16 / V; ++g) {
+                float f[V];
+#pragma unroll
+                for (int e = 0; e < V; ++e) f[e] = silu_f<T>(acc[p][g * V + e]);
+                *reinterpret_cast<uint4*>(q + g * V) = pack<T>(f);
+            }
+        }
     }
 }
 
@@ -337,12 +364,13 @@ extern "C" int el_stem_conv_u8(const uint8_t* src, const float* w, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     Strides4 ds = s4(ds_);
     if (B > 65535) return EL_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)ceil_div(W / 2, 32), (unsigned)ceil_div(H / 2, 8), (unsigned)B);
+    dim3 grid((unsigned)ceil_div(W / 2, kStemTW), (unsigned)ceil_div(H / 2, kStemTH), (unsigned)B);
+    const size_t smem = (size_t)(28 * C0 + kStemIH * kStemRow) * sizeof(float);
     EL_DISPATCH_DTYPE(dtype, {
         if (!channel_vectorisable<T>(dst, ds, C0)) return EL_ERR_UNSUPPORTED;
-        if (C0 == 16) stem_conv_u8_kernel<T, 16><<<grid, 256, 0, st>>>(src, w, bias, (T*)dst, ds, H, W);
-        else if (C0 == 32) stem_conv_u8_kernel<T, 32><<<grid, 256, 0, st>>>(src, w, bias, (T*)dst, ds, H, W);
-        else if (C0 == 64) stem_conv_u8_kernel<T, 64><<<grid, 256, 0, st>>>(src, w, bias, (T*)dst, ds, H, W);
+        if (C0 == 16) stem_conv_u8_kernel<T, 16><<<grid, 128, smem, st>>>(src, w, bias, (T*)dst, ds, H, W);
+        else if (C0 == 32) stem_conv_u8_kernel<T, 32><<<grid, 128, smem, st>>>(src, w, bias, (T*)dst, ds, H, W);
+        else if (C0 == 64) stem_conv_u8_kernel<T, 64><<<grid, 128, smem, st>>>(src, w, bias, (T*)dst, ds, H, W);
         else return EL_ERR_UNSUPPORTED;
     });
     note_launches(1);

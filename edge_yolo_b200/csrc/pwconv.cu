@@ -50,7 +50,7 @@ struct Args {
     int nchunks;
     const void* wpk;         // [n_tiles][w_bytes] swizzled weight tiles
     const float* bias;       // [N] or null
-    const void* res; int64_t res_pitch;
+    const void* res; int64_t res_pitch; float res_scale;  // out = res + res_scale * act(...)
     int has_out2, split;     // channels >= split go to out2
     int64_t M;
     int N, n_tile, ob;       // ob: channels per staging / store box (16, 32 or 64)
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                                 float r8[8];
                                 unpack<T>(ldg_stream(rrow + c0 + j + 8 * h), r8);
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) f[8 * h + e] += r8[e];
+                                for (int e = 0; e < 8; ++e) f[8 * h + e] = fmaf(A.res_scale, f[8 * h + e], r8[e]);
                             }
                         }
                         uint4 o;
@@ -369,8 +369,8 @@ extern "C" int el_pwconv_tile(int N, int w_row_bytes) {
 }
 
 extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], const int32_t src_c[], const void* wpk, const float* bias,
-                             const void* res, int64_t res_pitch, void* out, int64_t out_pitch, void* out2, int64_t out2_pitch, int split, int64_t M,
-                             int N, int act, int dtype, void* stream) {
+                             const void* res, int64_t res_pitch, float res_scale, void* out, int64_t out_pitch, void* out2, int64_t out2_pitch,
+                             int split, int64_t M, int N, int act, int dtype, void* stream) {
     if (nsrc < 1 || nsrc > pw::kMaxSrc || !src || !src_pitch || !src_c || !wpk || !out || M <= 0 || N <= 0 || act < 0 || act > 2) return EL_ERR_ARG;
     if (dtype != EL_BF16 && dtype != EL_F16) return EL_ERR_UNSUPPORTED;
     if (N % 8 || M >= (1ll << 31) - 256 || (out2 && (split % 16 || split <= 0 || split >= N))) return EL_ERR_UNSUPPORTED;
@@ -408,7 +408,7 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     while (ob > 16 && ob / 2 >= A.n_tile) ob >>= 1;
     if (ob < 16) return EL_ERR_UNSUPPORTED;
     A.ob = ob;
-    A.wpk = wpk; A.bias = bias; A.res = res; A.res_pitch = res_pitch;
+    A.wpk = wpk; A.bias = bias; A.res = res; A.res_pitch = res_pitch; A.res_scale = res_scale;
     A.has_out2 = out2 != nullptr; A.split = out2 ? split : N;
     A.M = M; A.N = N; A.act = act;
     uint32_t cols = 32;

@@ -452,7 +452,7 @@ constexpr int kMergeRows = 16;
 template <typename T>
 __global__ void __launch_bounds__(256) merge_fwd_tiled(const T* __restrict__ b, Strides4 bs, BandPtrs bands, const float* __restrict__ alpha,
                                                        T* __restrict__ out, Strides4 os, int c, int CV, int cols_per_block, int rows, int H, int W,
-                                                       int h, int w) {
+                                                       int h, int w, int c_off) {
     constexpr int V = Vec16<T>::N;
     // per-block tables: the four band weights and the vertical taps of this block's rows (both uniform over the block)
     __shared__ float s_w[4];
@@ -473,8 +473,8 @@ __global__ void __launch_bounds__(256) merge_fwd_tiled(const T* __restrict__ b, 
     const TileMap m = tile_map(CV, cols_per_block, W);
     if (!m.active) return;
     const int64_t n = blockIdx.z;
-    const int ch = m.cv * V;
-    T* q = out + n * os.n + (int64_t)y0b * os.h + (int64_t)m.col * os.w + ch;
+    const int ch = m.cv * V + c_off;  // c_off = c: bands-only output (the pass-through copy of b is skipped)
+    T* q = out + n * os.n + (int64_t)y0b * os.h + (int64_t)m.col * os.w + (ch - c_off);
     if (ch < c) {  // pass-through copy of b
         const T* p = b + n * bs.n + (int64_t)y0b * bs.h + (int64_t)m.col * bs.w + ch;
 #pragma unroll 4
@@ -536,7 +536,8 @@ __global__ void __launch_bounds__(256) merge_fwd_tiled(const T* __restrict__ b, 
 // of output instead of ~120 for the general kernel.
 template <typename T>
 __global__ void __launch_bounds__(256) merge_fwd_x2(const T* __restrict__ b, Strides4 bs, BandPtrs bands, const float* __restrict__ alpha,
-                                                    T* __restrict__ out, Strides4 os, int c, int CV, int cols_per_block, int srows, int h, int w) {
+                                                    T* __restrict__ out, Strides4 os, int c, int CV, int cols_per_block, int srows, int h, int w,
+                                                    int c_off) {
     constexpr int V = Vec16<T>::N;
     __shared__ float s_w[4];
     if (threadIdx.x == 0) {
@@ -550,12 +551,12 @@ __global__ void __launch_bounds__(256) merge_fwd_x2(const T* __restrict__ b, Str
     if (!m.active) return;
     const int k0 = (int)blockIdx.y * srows, k1 = min(k0 + srows, h);
     const int64_t n = blockIdx.z;
-    const int ch = m.cv * V;
+    const int ch = m.cv * V + c_off;  // c_off = c: bands-only output (the pass-through copy of b is skipped)
     // this block writes output rows 2*k0+1 .. 2*k1 (clipped to H-1), plus row 0 when k0 == 0
     const int y_first = k0 == 0 ? 0 : 2 * k0 + 1, y_last = min(2 * k1, H - 1);
     if (ch < c) {  // pass-through copy of b
         const T* p = b + n * bs.n + (int64_t)y_first * bs.h + (int64_t)m.col * bs.w + ch;
-        T* q = out + n * os.n + (int64_t)y_first * os.h + (int64_t)m.col * os.w + ch;
+        T* q = out + n * os.n + (int64_t)y_first * os.h + (int64_t)m.col * os.w + (ch - c_off);
 #pragma unroll 4
         for (int y = y_first; y <= y_last; ++y, p += bs.h, q += os.h) stg_stream(q, ldg_stream(p));
         return;
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(256) merge_fwd_x2(const T* __restrict__ b, Str
     const Strides4 s = bands.s[seg];
     const T* p0 = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + cc + (int64_t)x0 * s.w + (int64_t)k0 * s.h;
     const int64_t dx = (int64_t)(x1 - x0) * s.w, sh = s.h;
-    T* q = out + n * os.n + (int64_t)y_first * os.h + (int64_t)m.col * os.w + ch;
+    T* q = out + n * os.n + (int64_t)y_first * os.h + (int64_t)m.col * os.w + (ch - c_off);
     const int64_t oh = os.h;
     float prev[V], cur[V], r[V];
     auto hrow = [&](const T* p, float (&dst)[V]) {
@@ -695,9 +696,11 @@ extern "C" int el_dwt_haar_bwd(const void* g, const int64_t gs_[5], void* gx, co
 
 extern "C" int el_wave_merge_fwd(const void* b, const int64_t bs_[4], const void* const band[4], const int64_t band_s[16], const float* alpha,
                                  void* out, const int64_t os_[4], int B, int c, int H, int W, int h, int w, int dtype, void* stream) {
-    if (!b || !band || !band_s || !alpha || !out || B <= 0 || c <= 0 || (c & 1) || H <= 0 || W <= 0 || h <= 0 || w <= 0) return EL_ERR_ARG;
+    if (!band || !band_s || !alpha || !out || (b && !bs_) || B <= 0 || c <= 0 || (c & 1) || H <= 0 || W <= 0 || h <= 0 || w <= 0) return EL_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    Strides4 bs = s4(bs_), os = s4(os_);
+    // b == NULL: bands-only mode, out has 2c channels [LLu | LHu | HLu | HHu] (the consumer reads b in place)
+    const int c_off = b ? 0 : c, co = b ? 3 * c : 2 * c;
+    Strides4 bs = b ? s4(bs_) : Strides4{0, 1, 0, 0}, os = s4(os_);
     BandPtrs bp;
     for (int i = 0; i < 4; ++i) {
         if (!band[i]) return EL_ERR_ARG;
@@ -706,17 +709,18 @@ extern "C" int el_wave_merge_fwd(const void* b, const int64_t bs_[4], const void
     }
     EL_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec16<T>::N;
-        bool vec = channel_vectorisable<T>(b, bs, c) && channel_vectorisable<T>(out, os, 3 * c) && (c / 2) % V == 0;
+        bool vec = (!b || channel_vectorisable<T>(b, bs, c)) && channel_vectorisable<T>(out, os, co) && (c / 2) % V == 0;
         for (int i = 0; i < 4; ++i) vec = vec && channel_vectorisable<T>(bp.p[i], bp.s[i], c / 2);
+        if (!b && !(vec && co / V <= 256 && B <= 65535)) return EL_ERR_UNSUPPORTED;
         if (vec) {
-            if (3 * c / V <= 256 && B <= 65535 && H == 2 * h && W == 2 * w) {
+            if (co / V <= 256 && B <= 65535 && H == 2 * h && W == 2 * w) {
                 int cpb, srows;
-                dim3 g = tile_grid(3 * c / V, W, h, B, cpb, srows, 8, 2);  // rows here = SOURCE rows per thread
-                merge_fwd_x2<T><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, 3 * c / V, cpb, srows, h, w);
-            } else if (3 * c / V <= 256 && B <= 65535) {
+                dim3 g = tile_grid(co / V, W, h, B, cpb, srows, 8, 2);  // rows here = SOURCE rows per thread
+                merge_fwd_x2<T><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, co / V, cpb, srows, h, w, c_off);
+            } else if (co / V <= 256 && B <= 65535) {
                 int cpb, rows;
-                dim3 g = tile_grid(3 * c / V, W, H, B, cpb, rows, kMergeRows, 4);
-                merge_fwd_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, 3 * c / V, cpb, rows, H, W, h, w);
+                dim3 g = tile_grid(co / V, W, H, B, cpb, rows, kMergeRows, 4);
+                merge_fwd_tiled<T><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, co / V, cpb, rows, H, W, h, w, c_off);
             } else {
                 int64_t total = (int64_t)B * H * W * (3 * c / V);
                 merge_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, H, W, h, w, total);

@@ -90,8 +90,14 @@ class Predictor:
         with torch.cuda.graph(self.graph_from_x, pool=self.graph_from_u8.pool()):
             self.out_x, self.cnt_x = self._forward(False)
 
-    def step_device(self):
-        """One pass with the input batch already resident in HBM (`self.x`); results stay on the device."""
+    def step_device(self, from_u8: bool = True):
+        """One pass with the input batch already resident in HBM; results stay on the device.  `from_u8` (default): the uint8
+        HWC batch in `self.u8`, i.e. the product path incl. preprocess; else the preprocessed activations in `self.x`."""
+        if from_u8:
+            if self.graph_from_u8 is not None:
+                self.graph_from_u8.replay()
+                return self.out, self.cnt
+            return self._forward(True)
         if self.graph_from_x is not None:
             self.graph_from_x.replay()
             return self.out_x, self.cnt_x

@@ -58,6 +58,25 @@ def wavelet_enhancer_forward(self, b: torch.Tensor, inplace: bool = False, out2:
     return ops.gated_residual(b, y, self.gamma, inplace=inplace and not torch.is_grad_enabled(), out2=out2)
 
 
+def wavelet_enhancer_engine_forward(self, b: torch.Tensor) -> torch.Tensor:
+    """`_WaveletEnhancer.forward` (block.py:3685-3710) for the inference engine, in place on b: DWT split -> f_ll (tcgen05 1x1) /
+    shared f_h (cuDNN 3x3) -> bands-only upsample*w kernel -> ONE GEMM for `fuse` that reads [b | upsampled bands] in place
+    (no concat of b) and applies bias + SiLU + the gated residual b + tanh(gamma) * y in its epilogue."""
+    fuse = self.fuse
+    if not (hasattr(fuse, "el_bias") and b.dtype in (torch.bfloat16, torch.float16) and _pixel_linear(b) and b.shape[1] % 16 == 0
+            and b.shape[2] % 2 == 0 and b.shape[3] % 2 == 0 and _pw_ok(fuse.conv, [b])):
+        return wavelet_enhancer_forward(self, b, inplace=True)
+    B, _, H, W = b.shape
+    buf = ops.dwt_haar(b)
+    LLp = self.f_ll(buf[:B])
+    hp = self.f_h(buf[B:])
+    U = ops.wave_merge_bands(LLp, hp[:B], hp[B : 2 * B], hp[2 * B :], self.alpha, H, W)
+    gate = self.__dict__.get("el_gate")
+    if gate is None or gate[0] != self.gamma._version:  # tanh(gamma) as a host scalar, cached until gamma is modified
+        gate = self.el_gate = (self.gamma._version, float(torch.tanh(self.gamma.detach().float())))
+    return pw_apply(fuse.conv, [b, U], _bias_on(fuse, b), fuse.el_act, out=b, residual=b, res_scale=gate[1])
+
+
 def linear_attention_forward(self, x: torch.Tensor) -> torch.Tensor:
     """`LinearAttention.forward` (block.py:3360-3373): qkv conv -> fused attention core -> proj conv."""
     return self.proj(ops.linear_attention(self.qkv(x), self.num_heads))
@@ -160,7 +179,7 @@ def _pw_ok(conv: nn.Conv2d, srcs, *others) -> bool:
             and all(_pixel_linear(t) for t in srcs) and all(t is None or _pixel_linear(t) for t in others))
 
 
-def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=None):
+def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=None, res_scale=1.0):
     """1x1 conv over the channel concatenation of `srcs` + bias + activation (+ residual) as one tcgen05 GEMM (ops.pwconv).
     Weight tiles are packed once per (conv, source split) and cached on the conv module."""
     cache = conv.__dict__.setdefault("el_wpk", {})
@@ -168,7 +187,7 @@ def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=Non
     wpk = cache.get(key)
     if wpk is None:
         wpk = cache[key] = ops.pack_pw_weight(conv.weight, key[0], key[1]).to(key[2])
-    return ops.pwconv(srcs, wpk, conv.out_channels, bias=bias, act=act, residual=residual, out=out, out2=out2)
+    return ops.pwconv(srcs, wpk, conv.out_channels, bias=bias, act=act, residual=residual, out=out, out2=out2, res_scale=res_scale)
 
 
 def conv2d_pw_forward(self, x):
@@ -234,7 +253,7 @@ def dsc3k2_wavelet_engine_forward(self, x):
     a = torch.empty((B, c, H, W), device=x0.device, dtype=x0.dtype, memory_format=torch.channels_last)
     b = torch.empty_like(a)
     self.cv1(x, out=a, out2=b)
-    cur = wavelet_enhancer_forward(self.wave, b, inplace=True)
+    cur = wavelet_enhancer_engine_forward(self.wave, b)
     ys = [a, cur]
     for blk in self.m:
         cur = blk(cur)

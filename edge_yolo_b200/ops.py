@@ -162,6 +162,23 @@ class _Merge(torch.autograd.Function):
         return gb, gbands[0], gbands[1], gbands[2], gbands[3], galpha.to(alpha.dtype)
 
 
+def wave_merge_bands(LLp, LHp, HLp, HHp, alpha, H: int, W: int) -> torch.Tensor:
+    """Inference-engine variant of `wave_merge` without the pass-through copy of b: (B, 2c, H, W) = cat of the four upsampled,
+    weighted sub-bands (block.py:3696-3707); the consumer (the `fuse` conv) reads b in place.  No autograd."""
+    bands = (LLp, LHp, HLp, HHp)
+    _need_cuda(alpha, *bands)
+    B, half, h, w = LLp.shape
+    for t in bands:
+        if t.shape != LLp.shape or t.dtype != LLp.dtype:
+            raise EdgelineError("wave_merge_bands: the four bands must share shape and dtype")
+    out = torch.empty((B, 4 * half, H, W), device=LLp.device, dtype=LLp.dtype, memory_format=torch.channels_last)
+    a = alpha if alpha.dtype == torch.float32 else alpha.float()
+    bs = [s for t in bands for s in t.stride()]
+    check(_lib.lib().el_wave_merge_fwd(None, None, _ptrs(bands), _i64(bs), a.data_ptr(), out.data_ptr(), _i64(out.stride()), B, 2 * half, H, W,
+                                       h, w, _dt(LLp), _stream()), "el_wave_merge_fwd")
+    return out
+
+
 def wave_merge(b, LLp, LHp, HLp, HHp, alpha) -> torch.Tensor:
     """cat[b, up(LLp)*w0, up(LHp)*w1, up(HLp)*w2, up(HHp)*w3] -> (B, 3c, H, W); w from `alpha` on the device."""
     if torch.is_grad_enabled() and any(t.requires_grad for t in (b, LLp, LHp, HLp, HHp, alpha)):
@@ -588,10 +605,10 @@ def pack_pw_weight(weight: torch.Tensor, src_c, dtype=torch.bfloat16) -> torch.T
 
 
 def pwconv(srcs, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
-           out: torch.Tensor | None = None, out2: torch.Tensor | None = None) -> torch.Tensor:
+           out: torch.Tensor | None = None, out2: torch.Tensor | None = None, res_scale: float = 1.0) -> torch.Tensor:
     """1x1 conv over the channel-concatenation of `srcs` (NHWC 16-bit tensors or channel-slice views of the same B,H,W)
     + bias + activation (+ residual) in one tcgen05 GEMM kernel.  With `out2`, channels [0, out.shape[1]) go to `out`
-    and the rest to `out2`."""
+    and the rest to `out2`.  With `residual`, out = residual + res_scale * act(conv + bias) (`out` may be `residual` itself)."""
     x0 = srcs[0]
     _need_cuda(*srcs, wpk)
     B, _, H, W = x0.shape
@@ -614,7 +631,7 @@ def pwconv(srcs, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, ac
     check(_lib.lib().el_pwconv_fwd(n, _ptrs(srcs), _i64([pitch(t, "source") for t in srcs]), (c_int32 * n)(*[t.shape[1] for t in srcs]),
                                    wpk.data_ptr(), bias.data_ptr() if bias is not None else None,
                                    residual.data_ptr() if residual is not None else None, pitch(residual, "residual") if residual is not None else 0,
-                                   out.data_ptr(), pitch(out, "out"), out2.data_ptr() if out2 is not None else None,
+                                   float(res_scale), out.data_ptr(), pitch(out, "out"), out2.data_ptr() if out2 is not None else None,
                                    pitch(out2, "out2") if out2 is not None else 0, split, M, N, int(act), _dt(x0), _stream()), "el_pwconv_fwd")
     return out
 

@@ -65,7 +65,9 @@ int el_dwt_haar_bwd(const void* gbands, const int64_t gs[5], void* gx, const int
 /* ---- a2. sub-band merge: _WaveletEnhancer.forward, block.py:3696-3708 -----------------------
  * out (B,3c,H,W) = cat[b, up(LLp)*w0, up(LHp)*w1, up(HLp)*w2, up(HHp)*w3], up = bilinear
  * align_corners=False (h,w)->(H,W), w = softplus(alpha)/(sum+1e-6) computed on the device from
- * `alpha` (4 floats).  band[i] (B,c/2,h,w) with strides band_s[4*i..4*i+3]. */
+ * `alpha` (4 floats).  band[i] (B,c/2,h,w) with strides band_s[4*i..4*i+3].
+ * b == NULL (inference engine, NHWC 16-byte-vector views only): bands-only output (B,2c,H,W) without
+ * the pass-through copy of b -- the consumer (`fuse`, el_pwconv_fwd) reads b in place. */
 int el_wave_merge_fwd(const void* b, const int64_t bs[4], const void* const band[4],
                       const int64_t band_s[16], const float* alpha, void* out,
                       const int64_t os[4], int B, int c, int H, int W, int h, int w, int dtype,
@@ -207,7 +209,8 @@ int el_dwconv_fwd(const void* x, const int64_t xs[4], const float* w, const floa
                   const int64_t os[4], int B, int C, int H, int W, int k, int act, int dtype, void* stream);
 /* el_pwconv_fwd: pointwise (1x1) convolution + folded-BatchNorm bias + activation (+ shortcut) as one streaming
  * tcgen05 GEMM over NHWC pixels (Conv(k=1).forward_fuse nn/modules/conv.py:58-60; DSConv.pw + bn + act conv.py:100-104;
- * LinearAttention.qkv / proj block.py:3353-3373).  out[p, n] = act(sum_k X[p,k] W[n,k] + bias[n]) (+ res[p,n]).
+ * LinearAttention.qkv / proj block.py:3353-3373).  out[p, n] = res_scale * act(sum_k X[p,k] W[n,k] + bias[n]) (+ res[p,n]);
+ * res_scale = tanh(gamma) with res = b is the gated residual of _WaveletEnhancer (block.py:3708-3710), else 1.
  * The K dimension is the concatenation of `nsrc` (<= 4) source tensors (src[i]: 16-bit, src_c[i] channels, multiple
  * of 8, pixel pitch src_pitch[i] elements) -- the torch.cat of the C2f-style blocks (block.py:3783-3788) is never
  * materialised.  Channels >= split go to out2 when out2 != NULL (chunk(2,1) of cv1).  M = B*H*W pixels; every view
@@ -216,9 +219,9 @@ int el_dwconv_fwd(const void* x, const int64_t xs[4], const float* w, const floa
  * bf16 / fp16 only (EL_ERR_UNSUPPORTED otherwise: the fp32 API path keeps cuDNN). */
 int el_pwconv_tile(int N, int k_groups);
 int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], const int32_t src_c[],
-                  const void* wpk, const float* bias, const void* res, int64_t res_pitch, void* out,
-                  int64_t out_pitch, void* out2, int64_t out2_pitch, int split, int64_t M, int N, int act,
-                  int dtype, void* stream);
+                  const void* wpk, const float* bias, const void* res, int64_t res_pitch, float res_scale,
+                  void* out, int64_t out_pitch, void* out2, int64_t out2_pitch, int split, int64_t M, int N,
+                  int act, int dtype, void* stream);
 /* el_sppf_pool_fwd: out (B,4C,H,W) = cat[x, m(x), m(m(x)), m(m(m(x)))], m = MaxPool2d(5,1,2): the pooling
  * pyramid of SPPF (nn/modules/block.py:204-223) as separable 5/9/13 window maxima in shared memory.
  * NHWC views, H*W*64 B of shared memory (maps up to ~56x56), else EL_ERR_UNSUPPORTED. */

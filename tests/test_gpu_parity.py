@@ -505,10 +505,27 @@ def test_dwconv(dtype, tol, k, shape, epi):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("c,hw", [(16, (16, 24)), (64, (10, 6)), (128, (4, 4))])
+def test_wave_merge_bands_only(dtype, c, hw):
+    """Engine variant of the merge without the pass-through copy of b == channels [c, 3c) of the full merge, bit for bit."""
+    gen = torch.Generator().manual_seed(c)
+    B, (H, W) = 2, hw
+    cl = torch.channels_last
+    b = torch.randn(B, c, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl)
+    bands = [torch.randn(B, c // 2, H // 2, W // 2, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl) for _ in range(4)]
+    alpha = torch.tensor([0.5, 0.2, 0.2, 0.1], device=DEV)
+    full = ops().wave_merge(b, *bands, alpha)
+    got = ops().wave_merge_bands(*bands, alpha, H, W)
+    assert got.shape == (B, 2 * c, H, W)
+    assert torch.equal(got, full[:, c:])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("src_c,N,hw,opts", [
     ([64], 64, (16, 16), {}),                                   # one full 64-channel chunk, one tile
     ([16], 8, (9, 7), dict(act=1)),                             # N below one UMMA N step, ragged pixel tile
     ([8], 16, (9, 15), dict(act=1, res=True)),                  # one channel group: K padded to 16
+    ([32, 64], 32, (12, 12), dict(act=1, res=True, res_scale=0.4621, inplace=True)),  # enhancer tail: fuse + gated residual, in place on b
     ([32, 32, 32], 64, (20, 20), dict(act=1)),                  # concat-free cv2 of a C2f block: three sources
     ([16, 24, 8], 40, (13, 11), dict(act=2, res=True)),         # odd group counts per source
     ([128], 256, (20, 20), dict(act=1, split=128)),             # cv1 with chunk(2, 1) destinations
@@ -540,8 +557,11 @@ def test_pwconv(dtype, src_c, N, hw, opts):
     if bias is not None:
         want = want + bias.view(1, -1, 1, 1)
     want = torch.nn.functional.silu(want) if act == 1 else (want.relu() if act == 2 else want)
+    rs = opts.get("res_scale", 1.0)
+    if opts.get("inplace"):
+        res = srcs[0]
     if res is not None:
-        want = want + res.float()
+        want = res.float() + rs * want
     wpk = o.pack_pw_weight(w, src_c, dtype)
     if opts.get("split"):
         sp = opts["split"]
@@ -551,7 +571,7 @@ def test_pwconv(dtype, src_c, N, hw, opts):
         got = torch.cat([out, out2], 1)
         assert float(big[:, sp:].abs().max()) == 0.0  # nothing written past the slice
     else:
-        got = o.pwconv(srcs, wpk, N, bias=bias, act=act, residual=res)
+        got = o.pwconv(srcs, wpk, N, bias=bias, act=act, residual=res, res_scale=rs, out=srcs[0] if opts.get("inplace") else None)
     assert got.shape == want.shape
     close(got, want, 2e-2, 2e-2)
 
