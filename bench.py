@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel roofline pass")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay (for ncu)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run warm-ups, then ONE eager step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="skip cuDNN autotuning (keeps ncu launch lists short)")
     return ap.parse_args()
 
@@ -294,6 +296,17 @@ def product_arm(a):
     gen = torch.Generator().manual_seed(1234 + rank)
     host_u8 = torch.randint(0, 256, (a.batch, a.imgsz, a.imgsz, 3), dtype=torch.uint8, generator=gen).pin_memory()
     pred.predict_u8(host_u8)  # also leaves a real batch in pred.x
+
+    if a.profile_step:
+        for _ in range(max(a.warmup, 2)):
+            pred.step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        pred.step_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        eld.shutdown()
+        return
 
     def barrier():
         eld.barrier(dev)

@@ -1,9 +1,19 @@
 // Library-level entry points of libedgeline_b200.so.
+#include <stdlib.h>
+
 #include "el_common.cuh"
 
 namespace el {
 thread_local int g_last_cuda_error = 0;
 unsigned long long g_launches = 0;
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("EL_PDL");
+        on = !(e && e[0] == '0');
+    }
+    return on != 0;
+}
 }
 
 extern "C" const char* el_version(void) { return "edgeline_b200 0.1.0 (sm_100a)"; }

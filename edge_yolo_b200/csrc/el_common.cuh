@@ -118,6 +118,28 @@ template <typename T> inline bool channel_vectorisable(const void* p, const Stri
     return s.c == 1 && (C % V) == 0 && aligned16(p) && (s.n % V) == 0 && (s.h % V) == 0 && (s.w % V) == 0;
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------
+// Kernels of this library that follow one another in a stream are launched with programmatic stream serialization: a kernel
+// calls pdl_launch_dependents() at entry, so the NEXT kernel's CTAs may become resident and run their prologue (barrier init,
+// TMEM allocation, weight staging) while this one is still computing; the next kernel calls pdl_wait() before it touches any
+// activation memory, which blocks until this grid has completed and flushed.  A kernel that follows a non-PDL kernel (cuDNN,
+// PyTorch) simply starts after it, as usual.  Captured by CUDA graphs as programmatic edges.  EL_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 #define EL_DISPATCH_DTYPE(dtype, ...)                                              \
     switch (dtype) {                                                               \
         case EL_F32: { using T = float; __VA_ARGS__; } break;                      \

@@ -22,6 +22,7 @@ template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bias_act_tiled(const T* x, Strides4 xs, const float* __restrict__ bias, const T* res, Strides4 rs, T* o,
                                                       Strides4 os, T* o2, Strides4 os2, int split_cv, int CV, int cols_per_block, int rows, int H, int W) {
     constexpr int V = Vec16<T>::N;
+    pdl_launch_dependents();
     const int xi = (int)threadIdx.x / CV, cv = (int)threadIdx.x - xi * CV, col = (int)blockIdx.x * cols_per_block + xi;
     if (xi >= cols_per_block || col >= W) return;
     float bv[V];
@@ -62,6 +63,7 @@ template <typename T, int ACT>
 __global__ void __launch_bounds__(256) bias_act_flat(const T* x, Strides4 xs, const float* __restrict__ bias, const T* res, Strides4 rs, T* o, Strides4 os,
                                                      T* o2, Strides4 os2, int split_cv, int CV, int H, int W, uint32_t total) {
     constexpr int V = Vec16<T>::N;
+    pdl_launch_dependents();
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         uint32_t cv = idx % (uint32_t)CV, t = idx / (uint32_t)CV;
         uint32_t col = t % (uint32_t)W; t /= (uint32_t)W;
@@ -106,6 +108,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_cat_tiled(const T* __restrict__ x, Strides4 xs, const T* __restrict__ skip, Strides4 ss, T* __restrict__ o,
                                                             Strides4 os, int CV1, int CV, int cols_per_block, int H, int W) {
     constexpr int V = Vec16<T>::N;
+    pdl_launch_dependents();
+    pdl_wait();
     const int xi = (int)threadIdx.x / CV, cv = (int)threadIdx.x - xi * CV, col = (int)blockIdx.x * cols_per_block + xi;
     if (xi >= cols_per_block || col >= W) return;
     const int r0 = (int)blockIdx.y * kEpRowsMax, r1 = min(r0 + kEpRowsMax, H);
@@ -218,12 +222,22 @@ __global__ void __launch_bounds__(128) stem_conv_u8_kernel(const uint8_t* __rest
     }
     if (tid < C0) s_b[tid] = __ldg(bias + tid);
     const uint8_t* img = src + n * (int64_t)H * W * 3;
-    const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
-    for (int i = tid; i < kStemIH * (kStemIW * 3); i += 128) {
-        const int r = i / (kStemIW * 3), cb = i - r * (kStemIW * 3), px = cb / 3;
-        const int iy = iy0 + r, ix = ix0 + px;
-        const uint32_t b = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + ((int64_t)iy * W + ix0) * 3 + cb) : 0u;
-        s_in[r * kStemRow + cb] = __uint_as_float(0x4B000000u | b) - 8388608.f;
+    const int iy0 = 2 * oy0 - 1;
+    // patch rows are staged with aligned 32-bit loads (coalesced; W % 4 == 0 so a word never straddles an image row):
+    // byte range [seg0, seg0 + 387) of each image row, seg0 = (2*ox0 - 1) * 3 (negative at the left edge = zero padding)
+    const int seg0 = (2 * ox0 - 1) * 3, row_bytes = W * 3;
+    const int w_lo = (seg0 - (seg0 & 3)) >> 2;  // floor(seg0 / 4), also for seg0 = -3
+    constexpr int NW = (kStemIW * 3 + 3) / 4 + 1;  // words that cover 387 bytes at any alignment
+    for (int i = tid; i < kStemIH * NW; i += 128) {
+        const int r = i / NW, wi = i - r * NW;
+        const int iy = iy0 + r, byte0 = 4 * (w_lo + wi);
+        uint32_t u = 0;
+        if (iy >= 0 && iy < H && byte0 >= 0 && byte0 < row_bytes) u = __ldg(reinterpret_cast<const uint32_t*>(img + (int64_t)iy * row_bytes + byte0));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cb = byte0 + k - seg0;
+            if (cb >= 0 && cb < kStemIW * 3) s_in[r * kStemRow + cb] = __uint_as_float(0x4B000000u | ((u >> (8 * k)) & 0xffu)) - 8388608.f;
+        }
     }
     __syncthreads();
     const int cg = tid & 15, ty = tid >> 4;  // 16 column groups of 4 pixels x 8 rows
@@ -336,7 +350,7 @@ extern "C" int el_upsample2x_cat_fwd(const void* x, const int64_t xs_[4], const 
             return EL_ERR_UNSUPPORTED;  // the engine only uses this on NHWC activations
         const int CV = (C1 + C2) / V, cpb = 256 / CV;
         dim3 g((unsigned)ceil_div(W, cpb), (unsigned)ceil_div(H, kEpRowsMax), (unsigned)B);
-        upsample2x_cat_tiled<T><<<g, 256, 0, st>>>((const T*)x, xs, (const T*)skip, ss, (T*)out, os, C1 / V, CV, cpb, H, W);
+        launch_pdl(upsample2x_cat_tiled<T>, g, dim3(256), 0, st, (const T*)x, xs, (const T*)skip, ss, (T*)out, os, C1 / V, CV, cpb, H, W);
     });
     note_launches(1);
     return check_launch();
@@ -360,7 +374,7 @@ extern "C" int el_sppf_pool_fwd(const void* x, const int64_t xs_[4], void* out, 
 
 extern "C" int el_stem_conv_u8(const uint8_t* src, const float* w, const float* bias, void* dst, const int64_t ds_[4], int B, int C0, int H, int W, int dtype,
                                void* stream) {
-    if (!src || !w || !bias || !dst || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return EL_ERR_ARG;
+    if (!src || !w || !bias || !dst || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 3) || (reinterpret_cast<uintptr_t>(src) & 3)) return EL_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     Strides4 ds = s4(ds_);
     if (B > 65535) return EL_ERR_UNSUPPORTED;

@@ -170,7 +170,11 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
     const int nch = A.nchunks;
     constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
 
+    pdl_launch_dependents();  // the next kernel may start its prologue; it waits for this grid before touching activations
     if (tid == 0) {
+        for (int i = 0; i < kMaxSrc; ++i)
+            if (i == 0 || A.chunk[nch - 1].src >= i) asm volatile("prefetch.tensormap [%0];" ::"l"(&A.src_map[i]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&A.out_map) : "memory");
         mbar_init(bar_w, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, 128); }
         for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -188,6 +192,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
+    pdl_wait();  // everything above touched only weights / bias; activations of the previous kernel are complete from here on
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------ TMA producer
@@ -340,8 +345,8 @@ static cudaError_t launch(const Args& A, dim3 grid, size_t smem, bool res, cudaS
     {                                                                                                                                   \
         cudaError_t e = cudaFuncSetAttribute(pwconv_tc_kernel<T, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
         if (e != cudaSuccess) return e;                                                                                                 \
-        pwconv_tc_kernel<T, ACT, RES><<<grid, kThreads, smem, st>>>(A);                                                                 \
-        return cudaSuccess;                                                                                                             \
+        return launch_pdl(pwconv_tc_kernel<T, ACT, RES>, grid, dim3(kThreads), smem, st, A);                                            \
+                                                                                                                   \
     }
     if (res) {
         if (A.act == 0) EL_PW_LAUNCH(0, true) else if (A.act == 1) EL_PW_LAUNCH(1, true) else EL_PW_LAUNCH(2, true)
@@ -356,15 +361,17 @@ static cudaError_t launch(const Args& A, dim3 grid, size_t smem, bool res, cudaS
 
 using namespace el;
 
-extern "C" int el_pwconv_tile(int N, int w_row_bytes) {
+extern "C" int el_pwconv_tile(int N, int w_row_bytes, int64_t M) {
     // output channels per CTA: multiple of 16, <= 256, resident weight block (w_row_bytes per output channel) <= 128 KB, as even a split
-    // as possible
-    if (N <= 0 || w_row_bytes <= 0) return 0;
+    // as possible; few pixel tiles (small maps) split N further, down to 64 channels, until ~2 CTAs per SM exist
+    if (N <= 0 || w_row_bytes <= 0 || M <= 0) return 0;
     const int n16 = (int)ceil_div(N, 16) * 16;
     int max_rows = (int)((128 * 1024) / (int64_t)w_row_bytes) & ~15;
     if (max_rows > 256) max_rows = 256;
     if (max_rows < 16) return 0;
-    const int tiles = (int)ceil_div(n16, max_rows);
+    int tiles = (int)ceil_div(n16, max_rows);
+    const int64_t m_tiles = ceil_div(M, pw::kTileM);
+    while (m_tiles * tiles < 2 * kSMs && ceil_div(n16, tiles + 1) >= 64) ++tiles;
     return (int)ceil_div(ceil_div(n16, tiles), 16) * 16;
 }
 
@@ -392,7 +399,7 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
         max_rb = rb > max_rb ? rb : max_rb;
     }
     A.nchunks = nch;
-    A.n_tile = el_pwconv_tile(N, w_row_bytes);
+    A.n_tile = el_pwconv_tile(N, w_row_bytes, M);
     if (A.n_tile <= 0) return EL_ERR_UNSUPPORTED;
     uint32_t w_off = 0;
     for (int i = 0; i < nch; ++i) {  // every weight tile starts on a 1024 B boundary (swizzle atom alignment)

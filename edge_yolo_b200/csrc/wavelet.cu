@@ -422,6 +422,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) dwt_fwd_tiled(const T* __restrict__ x, Strides4 xs, T* __restrict__ o, int64_t ob, Strides4 os, int CV,
                                                      int cols_per_block, int rows, int H2, int W2) {
     constexpr int V = Vec16<T>::N;
+    pdl_launch_dependents();
+    pdl_wait();
     const TileMap m = tile_map(CV, cols_per_block, W2);
     if (!m.active) return;
     const float k = kHaar;
@@ -540,6 +542,7 @@ __global__ void __launch_bounds__(256) merge_fwd_x2(const T* __restrict__ b, Str
                                                     int c_off) {
     constexpr int V = Vec16<T>::N;
     __shared__ float s_w[4];
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         float wt[4];
         band_weights(alpha, wt);
@@ -661,7 +664,7 @@ extern "C" int el_dwt_haar_fwd(const void* x, const int64_t xs_[4], void* bands,
             if (C / V <= 256 && B <= 65535) {
                 int cpb, rows;
                 dim3 g = tile_grid(C / V, W2, H2, B, cpb, rows);
-                dwt_fwd_tiled<T><<<g, 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C / V, cpb, rows, H2, W2);
+                launch_pdl(dwt_fwd_tiled<T>, g, dim3(256), 0, st, (const T*)x, xs, (T*)bands, ob, os, C / V, cpb, rows, H2, W2);
             } else {
                 int64_t total = (int64_t)B * H2 * W2 * (C / V);
                 dwt_fwd_cvec<T><<<stream_grid(total), 256, 0, st>>>((const T*)x, xs, (T*)bands, ob, os, C / V, H2, W2, total);

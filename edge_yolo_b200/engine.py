@@ -56,7 +56,7 @@ class Predictor:
         stem = model.model[0]
         self.stem = None
         if getattr(stem, "el_bias", None) is not None and stem.conv.weight.shape[1:] == (3, 3, 3) and stem.conv.stride == (2, 2) \
-                and stem.conv.weight.shape[0] in (16, 32, 64) and stem.el_act == ops.ACT_SILU and imgsz % 2 == 0:
+                and stem.conv.weight.shape[0] in (16, 32, 64) and stem.el_act == ops.ACT_SILU and imgsz % 4 == 0:
             self.stem = ((stem.conv.weight.detach().float() / 255.0).contiguous(), stem.el_bias.to(self.device).contiguous())
         self.graph_from_u8 = self.graph_from_x = None
         self.launches_per_step = None

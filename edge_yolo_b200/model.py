@@ -132,7 +132,7 @@ class EdgeLineYOLO(nn.Module):
                     m.el_bias, m.el_act = m.conv.bias.detach().float().clone(), acts[type(m.act)]
                     m.conv.bias = None
                     m.forward = types.MethodType(M.conv_engine_forward, m)
-                    if _dw_eligible(m.conv):  # DWConv: depthwise + bias + activation in one kernel
+                    if _dw_eligible(m.conv, epilogue=True):  # DWConv: depthwise + bias + activation in one kernel
                         m.el_dw, m.el_k = M.ops.pack_dw_weight(m.conv.weight), m.conv.kernel_size[0]
                         m.forward = types.MethodType(M.dwconv_engine_forward, m)
             elif dsconv and isinstance(m, DSConv) and isinstance(m.bn, nn.BatchNorm2d):
@@ -175,13 +175,16 @@ class EdgeLineYOLO(nn.Module):
         return self
 
 
-def _dw_eligible(conv: nn.Conv2d) -> bool:
-    """Depthwise, stride 1, 'same' padding, k in {3,5,7}: what el_dwconv_fwd implements."""
+def _dw_eligible(conv: nn.Conv2d, epilogue: bool = False) -> bool:
+    """Depthwise, stride 1, 'same' padding, k in {3,5,7}: what el_dwconv_fwd implements.  Measured on B200 (tools/prof_conv.py):
+    it beats PyTorch's depthwise kernel for k = 7 and whenever the bias + activation epilogue rides along (DWConv); the bare
+    k = 3 depthwise of DSConv stays on PyTorch's kernel, which is on par."""
     k = conv.kernel_size[0]
     C = conv.in_channels
-    if not M.USE_DWCONV:
+    if not M.USE_DWCONV or not (epilogue or k >= 5):
         return False
-    return (conv.groups == C == conv.out_channels and C > 1 and conv.kernel_size == (k, k) and k in (3, 5, 7) and conv.stride == (1, 1)
+    C8 = C // 8
+    return (C % 8 == 0 and (C8 & (C8 - 1) == 0 or C % 64 == 0) and conv.groups == C == conv.out_channels and C > 1 and conv.kernel_size == (k, k) and k in (3, 5, 7) and conv.stride == (1, 1)
             and conv.dilation == (1, 1) and conv.padding == (k // 2, k // 2) and C % 8 == 0 and (C <= 64 or C % 64 == 0))
 
 

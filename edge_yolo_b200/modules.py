@@ -148,7 +148,7 @@ def gfl_head_forward(self, x):
 # ------------------------------------------------------------------------------------------
 
 
-USE_DWCONV = False  # el_dwconv_fwd in the engine graph (off while PyTorch's depthwise kernel is faster at the small-C sites)
+USE_DWCONV = True  # el_dwconv_fwd in the engine graph (model._dw_eligible picks the sites where it wins)
 
 
 def _bias_on(self, x):
@@ -183,10 +183,12 @@ def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=Non
     """1x1 conv over the channel concatenation of `srcs` + bias + activation (+ residual) as one tcgen05 GEMM (ops.pwconv).
     Weight tiles are packed once per (conv, source split) and cached on the conv module."""
     cache = conv.__dict__.setdefault("el_wpk", {})
-    key = (tuple(t.shape[1] for t in srcs), srcs[0].dtype, srcs[0].device)
+    x0 = srcs[0]
+    M = x0.shape[0] * x0.shape[2] * x0.shape[3]
+    key = (tuple(t.shape[1] for t in srcs), x0.dtype, x0.device, M if M < (1 << 16) else 0)  # the tile split depends on M only for small maps
     wpk = cache.get(key)
     if wpk is None:
-        wpk = cache[key] = ops.pack_pw_weight(conv.weight, key[0], key[1]).to(key[2])
+        wpk = cache[key] = ops.pack_pw_weight(conv.weight, key[0], key[1], M).to(key[2])
     return ops.pwconv(srcs, wpk, conv.out_channels, bias=bias, act=act, residual=residual, out=out, out2=out2, res_scale=res_scale)
 
 

@@ -574,16 +574,17 @@ def _pw_chunks(src_c):
     return chunks
 
 
-def pack_pw_weight(weight: torch.Tensor, src_c, dtype=torch.bfloat16) -> torch.Tensor:
+def pack_pw_weight(weight: torch.Tensor, src_c, dtype=torch.bfloat16, M: int = 1 << 30) -> torch.Tensor:
     """1x1 conv weight (N, K[,1,1]) with K = sum(src_c) -> the resident UMMA B operand of el_pwconv_fwd: per output-channel
     tile, one K-major tile [n_tile][box channels] per K chunk, stored with the 32/64/128-byte swizzle of its row width
-    (16-byte chunk j of row r lands at chunk j ^ ((r * row_bytes >> 7) & (row_bytes / 16 - 1))), each tile padded to 1024 B."""
+    (16-byte chunk j of row r lands at chunk j ^ ((r * row_bytes >> 7) & (row_bytes / 16 - 1))), each tile padded to 1024 B.
+    `M` = pixels of the call site: small maps use narrower output-channel tiles (el_pwconv_tile), so the packing depends on it."""
     w = weight.detach().reshape(weight.shape[0], -1).float()
     N, K = w.shape
     if K != sum(src_c):
         raise EdgelineError("pack_pw_weight: weight K does not match the sources")
     chunks = _pw_chunks(src_c)
-    n_tile = _lib.lib().el_pwconv_tile(N, sum(2 * bw for _, _, bw in chunks))
+    n_tile = _lib.lib().el_pwconv_tile(N, sum(2 * bw for _, _, bw in chunks), M)
     if n_tile <= 0:
         raise EdgelineError("pack_pw_weight: K too large for a resident weight tile")
     n_tiles = -(-N // n_tile)

@@ -181,7 +181,7 @@ int el_ingest_u8(const uint8_t* src, void* dst, const int64_t ds[4], int B, int 
 /* el_stem_conv_u8: the same preprocess fused with layer 0 of the yaml (cfg/models/11/yolo11-test.yaml:21,
  * Conv(3, C0, k=3, s=2, p=1) + BatchNorm + SiLU, nn/modules/conv.py:41-60): src (B,H,W,3) uint8 ->
  * dst (B,C0,H/2,W/2) logical with strides ds (channel-contiguous).  w (C0,3,3,3) fp32 = BN-folded weights
- * already divided by 255, bias (C0) fp32 = folded BN bias.  C0 in {16,32,64}, H and W even. */
+ * already divided by 255, bias (C0) fp32 = folded BN bias.  C0 in {16,32,64}, H even, W a multiple of 4. */
 int el_stem_conv_u8(const uint8_t* src, const float* w, const float* bias, void* dst,
                     const int64_t ds[4], int B, int C0, int H, int W, int dtype, void* stream);
 
@@ -215,9 +215,9 @@ int el_dwconv_fwd(const void* x, const int64_t xs[4], const float* w, const floa
  * of 8, pixel pitch src_pitch[i] elements) -- the torch.cat of the C2f-style blocks (block.py:3783-3788) is never
  * materialised.  Channels >= split go to out2 when out2 != NULL (chunk(2,1) of cv1).  M = B*H*W pixels; every view
  * must be pixel-linear (address = base + p * pitch).  wpk: weights packed by the host into UMMA tiles
- * [n_tiles][k-groups (padded per 64-channel chunk to even)][n_tile = el_pwconv_tile(N, k-groups)][8]; see ops.pack_pw_weight.
+ * [n_tiles][k-groups (padded per 64-channel chunk to even)][n_tile = el_pwconv_tile(N, weight row bytes, M)][8]; see ops.pack_pw_weight.
  * bf16 / fp16 only (EL_ERR_UNSUPPORTED otherwise: the fp32 API path keeps cuDNN). */
-int el_pwconv_tile(int N, int k_groups);
+int el_pwconv_tile(int N, int w_row_bytes, int64_t M);
 int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], const int32_t src_c[],
                   const void* wpk, const float* bias, const void* res, int64_t res_pitch, float res_scale,
                   void* out, int64_t out_pitch, void* out2, int64_t out2_pitch, int split, int64_t M, int N,

@@ -56,7 +56,7 @@ if "pw" in which:
         xs = [rn(B, K, hw, hw) for _ in range(R)]
         w = torch.randn(N, K, device=dev, generator=g) * (K ** -0.5)
         bias = torch.randn(N, device=dev, generator=g)
-        wpk = ops.pack_pw_weight(w, [K], dt)
+        wpk = ops.pack_pw_weight(w, [K], dt, B * hw * hw)
         wb = w.view(N, K, 1, 1).to(dt).contiguous(memory_format=cl)
         out = torch.empty(B, N, hw, hw, device=dev, dtype=dt).contiguous(memory_format=cl)
         t_ours = timeit(lambda x: ops.pwconv([x], wpk, N, bias=bias, act=ops.ACT_SILU, out=out), [(x,) for x in xs])

@@ -15,7 +15,7 @@ for K, N, hw in ((64, 64, 160), (128, 128, 80), (16, 8, 160), (32, 32, 160)):
     x = torch.randn(B, K, hw, hw, device=dev, generator=g).to(dt).contiguous(memory_format=cl)
     w = torch.randn(N, K, device=dev, generator=g) * (K ** -0.5)
     bias = torch.randn(N, device=dev, generator=g)
-    wpk = ops.pack_pw_weight(w, [K], dt)
+    wpk = ops.pack_pw_weight(w, [K], dt, B * hw * hw)
     out = torch.empty(B, N, hw, hw, device=dev, dtype=dt).contiguous(memory_format=cl)
     flush.zero_()
     ops.pwconv([x], wpk, N, bias=bias, act=ops.ACT_SILU, out=out)
