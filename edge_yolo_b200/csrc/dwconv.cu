@@ -17,8 +17,14 @@
 namespace el {
 
 template <typename T> __device__ __forceinline__ float dw_silu(float v) {
-    if constexpr (sizeof(T) == 2) return __fdividef(v, 1.f + __expf(-v));
-    else return v / (1.f + expf(-v));
+    if constexpr (sizeof(T) == 2) {  // x * sigmoid(x) = h + h * tanh(h), h = x / 2 (one MUFU; error below 16-bit rounding)
+        const float h = 0.5f * v;
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        return fmaf(h, t, h);
+    } else {
+        return v / (1.f + expf(-v));
+    }
 }
 
 constexpr int kDwRT = 4;          // output rows per strip = vertical register tile

@@ -126,6 +126,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {  
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -254,16 +262,22 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                 const uint32_t stg = sbase + off_stage + (uint32_t)(sub & 1) * staging_bytes;
                 if (et == 0) bulk_wait_read<1>();  // the store that last read this staging buffer (two uses ago) is done with it
                 epi_barrier();
-                for (int j = 0; j < ob; j += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + c0 + j, v);
+                for (int j0 = 0; j0 < ob; j0 += 32) {  // two 16-column TMEM loads in flight per wait
+                uint32_t v[2][16];
+                tmem_ld16_nowait(taddr + c0 + j0, v[0]);
+                if (j0 + 16 < ob) tmem_ld16_nowait(taddr + c0 + j0 + 16, v[1]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    if (j0 + jj * 16 >= ob) break;
+                    const int j = j0 + jj * 16;
                     float f[16];
                     const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0 + j);
 #pragma unroll
                     for (int e4 = 0; e4 < 4; ++e4) {
                         const float4 bb = b4[e4];
-                        f[4 * e4] = __uint_as_float(v[4 * e4]) + bb.x; f[4 * e4 + 1] = __uint_as_float(v[4 * e4 + 1]) + bb.y;
-                        f[4 * e4 + 2] = __uint_as_float(v[4 * e4 + 2]) + bb.z; f[4 * e4 + 3] = __uint_as_float(v[4 * e4 + 3]) + bb.w;
+                        f[4 * e4] = __uint_as_float(v[jj][4 * e4]) + bb.x; f[4 * e4 + 1] = __uint_as_float(v[jj][4 * e4 + 1]) + bb.y;
+                        f[4 * e4 + 2] = __uint_as_float(v[jj][4 * e4 + 2]) + bb.z; f[4 * e4 + 3] = __uint_as_float(v[jj][4 * e4 + 3]) + bb.w;
                     }
                     if (ACT == 1) {  // SiLU: x * sigmoid(x) = h + h * tanh(h), h = x / 2 (one MUFU per element; 16-bit outputs)
 #pragma unroll
@@ -290,6 +304,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                                      "r"(o.w)
                                      : "memory");
                     }
+                }
                 }
                 proxy_fence();  // generic-proxy writes of the staging tile -> visible to the TMA store (async proxy)
                 epi_barrier();
@@ -424,22 +439,21 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     A.tmem_cols = cols;
     const size_t fixed = 1024 /* alignment slack */ + ((A.w_bytes + 1023u) & ~1023u) + 2 * (size_t)pw::kTileM * ob * 2 +
                          (((size_t)(A.n_tile + 64) * 4 + 127) & ~(size_t)127) + 40 + 16 * pw::kMaxStages + 16;
-    // shared memory per CTA: the smallest of 56 / 100 / 220 KB (4 / 2 / 1 CTAs per SM) that holds a ring of >= 4 stages; with
-    // resident weights too large for that, whatever ring fits in 220 KB (>= 2 stages)
-    int S = 0;
-    for (size_t budget : {(size_t)56 * 1024, (size_t)100 * 1024, (size_t)220 * 1024}) {
+    // CTAs per SM: the most (<= 4, limited by TMEM columns) whose share of shared memory still holds a ring of >= 3 stages (one being
+    // consumed, two in flight per CTA); with resident weights too large for that, whatever ring fits one CTA (>= 2 stages).
+    // Two or more co-resident CTAs are what overlaps one tile's epilogue with the other's loads and MMAs.
+    int S = 0, per_sm = 1;
+    for (int ps = 4; ps >= 1; --ps) {
+        if (ps > (int)(512 / cols)) continue;
+        const size_t budget = (size_t)227 * 1024 / ps - 1024;
         if (budget <= fixed) continue;
-        S = (int)((budget - fixed) / A.stage_bytes);
-        if (S >= 4) break;
+        const int s_fit = (int)((budget - fixed) / A.stage_bytes);
+        if (s_fit >= 3 || (ps == 1 && s_fit >= 2)) { S = s_fit; per_sm = ps; break; }
     }
     if (S < 2) return EL_ERR_UNSUPPORTED;
     if (S > pw::kMaxStages) S = pw::kMaxStages;
     A.stages = S;
     const size_t smem = fixed + (size_t)S * A.stage_bytes;
-    int per_sm = (int)(227 * 1024 / (smem + 1024));
-    if (per_sm > (int)(512 / cols)) per_sm = (int)(512 / cols);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
     const int64_t m_tiles = ceil_div(M, pw::kTileM);
     int64_t gx = (int64_t)kSMs * per_sm / n_tiles;
     if (gx < 1) gx = 1;

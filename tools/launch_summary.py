@@ -44,8 +44,8 @@ def main():
             f.write("id,kernel,grid,block,us\n")
             for i, name, g, b, us in step:
                 f.write(f"{i},\"{name[:160]}\",\"{g}\",\"{b}\",{us:.2f}\n")
-    ours = sum(us for k, (n, us) in by.items() if "el::" in k)
-    print(f"# el:: kernels {ours:.1f} us = {ours / total:.3f} of the step")
+    ours = sum(us for k, (n, us) in by.items() if any(ns in k for ns in ("el::", "pw::", "tc::")))
+    print(f"# libedgeline_b200 kernels (el:: / pw:: / tc::) {ours:.1f} us = {ours / total:.3f} of the step")
 
 
 if __name__ == "__main__":
