@@ -32,14 +32,14 @@ namespace pw {
 
 constexpr int kThreads = 192;
 constexpr int kTileM = 128;
-constexpr int kMaxChunks = 28;
+constexpr int kMaxChunks = 40;
 constexpr int kMaxSrc = 4;
 constexpr int kMaxStages = 8;
 
 struct Chunk {
     uint32_t w_off;   // byte offset of this chunk's weight tile in the resident weight block
     uint16_t c0;      // first channel inside the source
-    uint8_t src;      // source tensor
+    uint8_t src;      // source tensor (1x1) or filter tap ky * 3 + kx (3x3)
     uint8_t rb;       // row bytes of the box = swizzle span: 32, 64 or 128 (16, 32 or 64 channels)
 };
 
@@ -56,6 +56,10 @@ struct Args {
     int N, n_tile, ob;       // ob: channels per staging / store box (16, 32 or 64)
     int act, stages;
     uint32_t w_bytes, stage_bytes, tmem_cols;
+    // 3x3 mode (el_conv3x3_fwd): a pixel tile is a tw x th patch of one image (tw * th = 128), src_map[0] / out_map are 4-D
+    // (channel, x, y, image) maps, chunk.src is the filter tap and the box of tap (ky, kx) starts at (x0 * stride + kx - 1, y0 * stride + ky - 1)
+    int spatial, tw, th, tiles_x, tiles_y, stride;
+    int64_t n_tiles_m;
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,6 +92,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // 2-D tiled TMA store shared -> global (SASS: UTMASTG); out-of-range rows / channels are clipped
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(map),
+                 "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(c3)
+                 : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -172,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + off_bar + 40 + 16 * kMaxStages);
 
     const int nt = blockIdx.y, n0 = nt * n_tile;
-    const int64_t m_tiles = (A.M + kTileM - 1) / kTileM;
+    const int64_t m_tiles = A.spatial ? A.n_tiles_m : (A.M + kTileM - 1) / kTileM;
     const int64_t first = blockIdx.x;
     const int my_tiles = first < m_tiles ? (int)((m_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
     const int nch = A.nchunks;
@@ -181,7 +195,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
     pdl_launch_dependents();  // the next kernel may start its prologue; it waits for this grid before touching activations
     if (tid == 0) {
         for (int i = 0; i < kMaxSrc; ++i)
-            if (i == 0 || A.chunk[nch - 1].src >= i) asm volatile("prefetch.tensormap [%0];" ::"l"(&A.src_map[i]) : "memory");
+            if (i == 0 || (!A.spatial && A.chunk[nch - 1].src >= i)) asm volatile("prefetch.tensormap [%0];" ::"l"(&A.src_map[i]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&A.out_map) : "memory");
         mbar_init(bar_w, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, 128); }
@@ -207,13 +221,23 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
         if (lane == 0) {
             int it = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
-                const int m0 = (int)((first + (int64_t)tl * gridDim.x) * kTileM);
+                const int64_t tile = first + (int64_t)tl * gridDim.x;
+                const int m0 = (int)(tile * kTileM);
+                int img = 0, x0 = 0, y0 = 0;
+                if (A.spatial) {
+                    const int per_img = A.tiles_x * A.tiles_y, r = (int)(tile % per_img);
+                    img = (int)(tile / per_img);
+                    y0 = (r / A.tiles_x) * A.th * A.stride - 1;
+                    x0 = (r % A.tiles_x) * A.tw * A.stride - 1;
+                }
                 for (int c = 0; c < nch; ++c, ++it) {
                     const int s = it % S, use = it / S;
                     if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)(use - 1) & 1);
                     const Chunk ck = A.chunk[c];
+                    const uint32_t dst = sbase + off_ring + (uint32_t)s * A.stage_bytes;
                     mbar_expect_tx(bar_full + 8 * s, (uint32_t)kTileM * ck.rb);
-                    tma_load_2d(sbase + off_ring + (uint32_t)s * A.stage_bytes, &A.src_map[ck.src], ck.c0, m0, bar_full + 8 * s);
+                    if (A.spatial) tma_load_4d(dst, &A.src_map[0], ck.c0, x0 + ck.src % 3, y0 + ck.src / 3, img, bar_full + 8 * s);
+                    else tma_load_2d(dst, &A.src_map[ck.src], ck.c0, m0, bar_full + 8 * s);
                 }
             }
         }
@@ -310,8 +334,15 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                 epi_barrier();
                 if (et == 0) {
                     const int n = n0 + c0;
-                    if (A.has_out2 && n >= A.split) tma_store_2d(&A.out2_map, n - A.split, (int)m0, stg);
-                    else tma_store_2d(&A.out_map, n, (int)m0, stg);
+                    if (A.spatial) {
+                        const int64_t tile = first + (int64_t)tl * gridDim.x;
+                        const int per_img = A.tiles_x * A.tiles_y, r = (int)(tile % per_img);
+                        tma_store_4d(&A.out_map, n, (r % A.tiles_x) * A.tw, (r / A.tiles_x) * A.th, (int)(tile / per_img), stg);
+                    } else if (A.has_out2 && n >= A.split) {
+                        tma_store_2d(&A.out2_map, n - A.split, (int)m0, stg);
+                    } else {
+                        tma_store_2d(&A.out_map, n, (int)m0, stg);
+                    }
                     bulk_commit();
                 }
             }
@@ -349,6 +380,21 @@ static bool make_map(CUtensorMap* map, const void* base, int channels, int64_t M
     const cuuint32_t estr[2] = {1, 1};
     const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     return fn(map, dtype == EL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// (channels, x, y, image) view of an NHWC activation; box = (row_bytes / 2 channels, tw pixels, th rows, 1 image) traversed with
+// `stride` along x and y (a stride-2 convolution reads every second pixel of the tap-shifted window)
+static bool make_map4(CUtensorMap* map, const void* base, int channels, int W, int H, int B, const int64_t st[4] /* n, c, h, w elements */, int row_bytes,
+                      int tw, int th, int stride, int dtype) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)channels, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)st[3] * 2, (cuuint64_t)st[2] * 2, (cuuint64_t)st[0] * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)(row_bytes / 2), (cuuint32_t)(tw * stride), (cuuint32_t)(th * stride), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    return fn(map, dtype == EL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box,
               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -428,6 +474,7 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     int ob = 64;
     if (out2) while (split % ob) ob >>= 1;
     while (ob > 16 && ob / 2 >= A.n_tile) ob >>= 1;
+    if (n_tiles > 1) while (A.n_tile % ob) ob >>= 1;  // an overhanging last box is only harmless past N (clipped), not into the next tile
     if (ob < 16) return EL_ERR_UNSUPPORTED;
     A.ob = ob;
     A.wpk = wpk; A.bias = bias; A.res = res; A.res_pitch = res_pitch; A.res_scale = res_scale;
@@ -465,6 +512,90 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     dim3 grid((unsigned)gx, (unsigned)n_tiles);
     cudaStream_t st = (cudaStream_t)stream;
     const cudaError_t e = dtype == EL_BF16 ? pw::launch<__nv_bfloat16>(A, grid, smem, res != nullptr, st) : pw::launch<__half>(A, grid, smem, res != nullptr, st);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
+    note_launches(1);
+    return check_launch();
+}
+
+// Dense 3 x 3 convolution (padding 1, stride 1 or 2) + bias + activation as an implicit GEMM on the same kernel: the nine filter
+// taps are nine K-chunk groups whose TMA boxes are the tap-shifted windows of the input (zero padding = TMA out-of-bounds fill).
+extern "C" int el_conv3x3_fwd(const void* x, const int64_t xs_[4], int C, const void* wpk, const float* bias, void* out, const int64_t os_[4], int B,
+                              int H, int W, int N, int stride, int act, int dtype, void* stream) {
+    if (!x || !xs_ || !wpk || !out || !os_ || B <= 0 || C <= 0 || H <= 0 || W <= 0 || N <= 0 || act < 0 || act > 2) return EL_ERR_ARG;
+    if (dtype != EL_BF16 && dtype != EL_F16) return EL_ERR_UNSUPPORTED;
+    if ((stride != 1 && stride != 2) || C % 8 || N % 8 || xs_[1] != 1 || os_[1] != 1 || !aligned16(x) || !aligned16(out)) return EL_ERR_UNSUPPORTED;
+    for (int i = 0; i < 4; ++i)
+        if (i != 1 && (xs_[i] % 8 || os_[i] % 8)) return EL_ERR_UNSUPPORTED;
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    pw::Args A{};
+    const int rb = pw::box_bytes_for(C);
+    int nch = 0, w_row_bytes = 0;
+    for (int tap = 0; tap < 9; ++tap)
+        for (int c0 = 0; c0 < C; c0 += rb / 2) {
+            if (nch >= pw::kMaxChunks) return EL_ERR_UNSUPPORTED;
+            pw::Chunk& c = A.chunk[nch++];
+            c.c0 = (uint16_t)c0; c.src = (uint8_t)tap; c.rb = (uint8_t)rb;
+            w_row_bytes += rb;
+        }
+    A.nchunks = nch;
+    // pixel tile = tw x th patch with tw * th = 128: the widest power of two that wastes the least of the last column tile
+    int tw = 128;
+    {
+        int best = -1;
+        for (int t = 4; t <= 128; t <<= 1) {
+            if (t * stride > 256 || (128 / t) * stride > 256) continue;
+            const int64_t covered = ceil_div(Wo, t) * t * (ceil_div(Ho, 128 / t) * (128 / t));
+            if (best < 0 || covered < best || (covered == best && t > tw)) { best = (int)covered; tw = t; }
+        }
+    }
+    A.spatial = 1; A.tw = tw; A.th = 128 / tw; A.stride = stride;
+    A.tiles_x = (int)ceil_div(Wo, A.tw); A.tiles_y = (int)ceil_div(Ho, A.th);
+    A.n_tiles_m = (int64_t)B * A.tiles_x * A.tiles_y;
+    const int64_t M = A.n_tiles_m * pw::kTileM;
+    A.n_tile = el_pwconv_tile(N, w_row_bytes, M);
+    if (A.n_tile <= 0) return EL_ERR_UNSUPPORTED;
+    uint32_t w_off = 0;
+    for (int i = 0; i < nch; ++i) {
+        A.chunk[i].w_off = w_off;
+        w_off += ((uint32_t)A.n_tile * A.chunk[i].rb + 1023u) & ~1023u;
+    }
+    A.w_bytes = w_off;
+    A.stage_bytes = (uint32_t)pw::kTileM * rb;
+    const int n_tiles = (int)ceil_div(N, A.n_tile);
+    int ob = 64;
+    while (ob > 16 && ob / 2 >= A.n_tile) ob >>= 1;
+    if (n_tiles > 1) while (A.n_tile % ob) ob >>= 1;
+    if (ob < 16) return EL_ERR_UNSUPPORTED;
+    A.ob = ob;
+    A.wpk = wpk; A.bias = bias; A.res = nullptr; A.res_pitch = 0; A.res_scale = 1.f;
+    A.has_out2 = 0; A.split = N;
+    A.M = M; A.N = N; A.act = act;
+    uint32_t cols = 32;
+    while (cols < 2u * A.n_tile) cols <<= 1;
+    if (cols > 512) return EL_ERR_UNSUPPORTED;
+    A.tmem_cols = cols;
+    const size_t fixed = 1024 + ((A.w_bytes + 1023u) & ~1023u) + 2 * (size_t)pw::kTileM * ob * 2 + (((size_t)(A.n_tile + 64) * 4 + 127) & ~(size_t)127) + 40 +
+                         16 * pw::kMaxStages + 16;
+    int S = 0, per_sm = 1;
+    for (int ps = 4; ps >= 1; --ps) {
+        if (ps > (int)(512 / cols)) continue;
+        const size_t budget = (size_t)227 * 1024 / ps - 1024;
+        if (budget <= fixed) continue;
+        const int s_fit = (int)((budget - fixed) / A.stage_bytes);
+        if (s_fit >= 4 || (ps == 1 && s_fit >= 2)) { S = s_fit; per_sm = ps; break; }
+    }
+    if (S < 2) return EL_ERR_UNSUPPORTED;
+    if (S > pw::kMaxStages) S = pw::kMaxStages;
+    A.stages = S;
+    const size_t smem = fixed + (size_t)S * A.stage_bytes;
+    int64_t gx = (int64_t)kSMs * per_sm / n_tiles;
+    if (gx < 1) gx = 1;
+    if (gx > A.n_tiles_m) gx = A.n_tiles_m;
+    if (!pw::make_map4(&A.src_map[0], x, C, W, H, B, xs_, rb, A.tw, A.th, stride, dtype)) return EL_ERR_CUDA;
+    if (!pw::make_map4(&A.out_map, out, N, Wo, Ho, B, os_, ob * 2, A.tw, A.th, 1, dtype)) return EL_ERR_CUDA;
+    dim3 grid((unsigned)gx, (unsigned)n_tiles);
+    cudaStream_t st = (cudaStream_t)stream;
+    const cudaError_t e = dtype == EL_BF16 ? pw::launch<__nv_bfloat16>(A, grid, smem, false, st) : pw::launch<__half>(A, grid, smem, false, st);
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
     note_launches(1);
     return check_launch();

@@ -179,6 +179,27 @@ def _pw_ok(conv: nn.Conv2d, srcs, *others) -> bool:
             and all(_pixel_linear(t) for t in srcs) and all(t is None or _pixel_linear(t) for t in others))
 
 
+USE_CONV3X3 = True  # el_conv3x3_fwd for the dense 3x3 convs of the engine graph
+
+
+def _conv3_ok(conv: nn.Conv2d, x: torch.Tensor, out=None) -> bool:
+    """el_conv3x3_fwd applies: dense 3x3, padding 1, stride 1 / 2, 16-bit NHWC, channel counts in 8s -- and pays off: measured on B200
+    (tools/prof_conv.py c3) the nine tap-shifted TMA boxes re-read the input 9x from L2, which beats cuDNN + el_bias_act for
+    C_in <= 32 (HBM-bound sites: 16->32 s2 @320^2 89 vs 185 us, 32->64 s2 @160^2 50 vs 70 us) and loses to cuDNN's smem-reusing
+    implicit GEMM from C_in = 64 up, so wider convs stay on cuDNN."""
+    if not (USE_CONV3X3 and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (1, 1)
+            and conv.groups == 1 and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and not torch.is_grad_enabled()):
+        return False
+    B, C, H, W = x.shape
+    N = conv.out_channels
+    if C % 8 or N % 8 or C > 32 or x.stride(1) != 1 or any(s % 8 for i, s in enumerate(x.stride()) if i != 1) or x.data_ptr() % 16:
+        return False
+    if out is not None and (out.stride(1) != 1 or any(s % 8 for i, s in enumerate(out.stride()) if i != 1) or out.data_ptr() % 16):
+        return False
+    n_tile, n_tiles = ops.conv3x3_tiles(N, C, B, H, W, conv.stride[0])
+    return 0 < n_tiles <= 3
+
+
 def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=None, res_scale=1.0):
     """1x1 conv over the channel concatenation of `srcs` + bias + activation (+ residual) as one tcgen05 GEMM (ops.pwconv).
     Weight tiles are packed once per (conv, source split) and cached on the conv module."""
@@ -213,6 +234,16 @@ def conv_engine_forward(self, x, out=None, residual=None, out2=None):
     if _pw_ok(self.conv, srcs, out, residual, out2):
         return pw_apply(self.conv, srcs, _bias_on(self, srcs[0]), self.el_act, out=out, residual=residual, out2=out2)
     x = srcs[0] if len(srcs) == 1 else torch.cat(srcs, 1)
+    if residual is None and out2 is None and _conv3_ok(self.conv, x, out):
+        cache = self.conv.__dict__.setdefault("el_wpk", {})
+        B, C, H, W = x.shape
+        s = self.conv.stride[0]
+        M = B * ((H - 1) // s + 1) * ((W - 1) // s + 1)
+        key = ("3x3", x.dtype, x.device, M if M < (1 << 16) else 0)
+        wpk = cache.get(key)
+        if wpk is None:
+            wpk = cache[key] = ops.pack_conv3x3_weight(self.conv.weight, x.dtype, M).to(x.device)
+        return ops.conv3x3(x, wpk, self.conv.out_channels, bias=_bias_on(self, x), act=self.el_act, stride=s, out=out)
     return ops.bias_act(self.conv(x), _bias_on(self, x), self.el_act, residual=residual, out=out, out2=out2)
 
 

@@ -637,6 +637,39 @@ def pwconv(srcs, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, ac
     return out
 
 
+def conv3x3_tiles(N: int, C: int, B: int, H: int, W: int, stride: int = 1):
+    """(n_tile, n_tiles) el_conv3x3_fwd would use: callers fall back to cuDNN when the weight block splits N too finely."""
+    rb = 32 if C <= 16 else (64 if C <= 32 else 128)
+    row_bytes = 9 * rb * -(-C // (rb // 2))
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    n_tile = _lib.lib().el_pwconv_tile(N, row_bytes, B * Ho * Wo)
+    return n_tile, (-(-N // n_tile) if n_tile > 0 else 0)
+
+
+def pack_conv3x3_weight(weight: torch.Tensor, dtype=torch.bfloat16, M: int = 1 << 30) -> torch.Tensor:
+    """Conv2d weight (N, C, 3, 3) -> resident UMMA tiles of el_conv3x3_fwd: the (N, 9*C) matrix in (ky, kx, c) order, packed like a
+    1x1 conv over nine C-channel sources (one per filter tap)."""
+    N, C, kh, kw = weight.shape
+    if (kh, kw) != (3, 3):
+        raise EdgelineError("pack_conv3x3_weight: need a (N, C, 3, 3) weight")
+    return pack_pw_weight(weight.detach().permute(0, 2, 3, 1).reshape(N, 9 * C), [C] * 9, dtype, M)
+
+
+def conv3x3(x: torch.Tensor, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, act: int = ACT_NONE, stride: int = 1,
+            out: torch.Tensor | None = None) -> torch.Tensor:
+    """Dense 3x3 conv (padding 1, stride 1 / 2) + bias + activation as a TMA + tcgen05 implicit GEMM (NHWC 16-bit activations)."""
+    _need_cuda(x, wpk)
+    B, C, H, W = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty((B, N, Ho, Wo), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise EdgelineError("conv3x3: bias must be a contiguous fp32 vector of N elements")
+    check(_lib.lib().el_conv3x3_fwd(x.data_ptr(), _i64(x.stride()), C, wpk.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                                    _i64(out.stride()), B, H, W, N, int(stride), int(act), _dt(x), _stream()), "el_conv3x3_fwd")
+    return out
+
+
 def upsample2x_cat(x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
     """cat[nearest-2x(x), skip] along channels in one pass (NHWC activations)."""
     _need_cuda(x, skip)

@@ -222,6 +222,13 @@ int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], 
                   const void* wpk, const float* bias, const void* res, int64_t res_pitch, float res_scale,
                   void* out, int64_t out_pitch, void* out2, int64_t out2_pitch, int split, int64_t M, int N,
                   int act, int dtype, void* stream);
+/* el_conv3x3_fwd: dense 3x3 convolution, padding 1, stride 1 or 2, + folded-BatchNorm bias + activation as an implicit GEMM on
+ * the el_pwconv_fwd kernel (Conv(k=3).forward_fuse nn/modules/conv.py:58-60: the stride-2 downsampling convs of the yaml,
+ * _WaveletEnhancer.f_h block.py:3657-3679, the Detect box tower head.py:59-63).  x (B,C,H,W) / out (B,N,Ho,Wo) NHWC views with
+ * element strides xs / os = {n,c,h,w}; wpk = ops.pack_pw_weight of the (N, 9*C) matrix in (ky, kx, c) order with nine
+ * "sources" of C channels.  bf16 / fp16 only. */
+int el_conv3x3_fwd(const void* x, const int64_t xs[4], int C, const void* wpk, const float* bias, void* out,
+                   const int64_t os[4], int B, int H, int W, int N, int stride, int act, int dtype, void* stream);
 /* el_sppf_pool_fwd: out (B,4C,H,W) = cat[x, m(x), m(m(x)), m(m(m(x)))], m = MaxPool2d(5,1,2): the pooling
  * pyramid of SPPF (nn/modules/block.py:204-223) as separable 5/9/13 window maxima in shared memory.
  * NHWC views, H*W*64 B of shared memory (maps up to ~56x56), else EL_ERR_UNSUPPORTED. */

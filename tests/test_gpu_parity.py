@@ -576,6 +576,32 @@ def test_pwconv(dtype, src_c, N, hw, opts):
     close(got, want, 2e-2, 2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C,N,hw,stride,act", [
+    (16, 32, (20, 24), 1, 1),      # one 32-byte box per tap
+    (16, 8, (40, 40), 1, 1),       # f_h of the enhancer: N below one UMMA N step
+    (64, 64, (17, 13), 1, 1),      # ragged patches on both axes
+    (32, 64, (32, 48), 2, 1),      # stride-2 downsampling conv
+    (64, 128, (21, 19), 2, 0),     # stride 2, odd sizes, no activation
+    (128, 128, (12, 12), 1, 2),    # K = 1152: the weight block splits N
+])
+def test_conv3x3(dtype, C, N, hw, stride, act):
+    """Dense 3x3 conv (padding 1, stride 1 / 2) + bias + act as a TMA + tcgen05 implicit GEMM vs torch fp32 on the same 16-bit inputs
+    (Conv(k=3).forward_fuse nn/modules/conv.py:58-60).  16-bit contract: 2e-2."""
+    o = ops()
+    gen = torch.Generator().manual_seed(C + N + stride)
+    B, (H, W) = 3, hw
+    x = torch.randn(B, C, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(N, C, 3, 3, generator=gen) * (9 * C) ** -0.5).to(DEV)
+    bias = torch.randn(N, generator=gen).to(DEV)
+    want = torch.nn.functional.conv2d(x.float(), w.to(dtype).float(), bias, stride=stride, padding=1)
+    want = torch.nn.functional.silu(want) if act == 1 else (want.relu() if act == 2 else want)
+    Ho, Wo = want.shape[2:]
+    got = o.conv3x3(x, o.pack_conv3x3_weight(w, dtype, B * Ho * Wo), N, bias=bias, act=act, stride=stride)
+    assert got.shape == want.shape
+    close(got, want, 2e-2, 2e-2)
+
+
 def test_predictor_matches_api_path():
     """Predictor (graph replay, uint8 ingest) returns exactly what model + non_max_suppression return."""
     from edge_yolo_b200.engine import Predictor, build_model

@@ -62,3 +62,23 @@ if "pw" in which:
         t_ours = timeit(lambda x: ops.pwconv([x], wpk, N, bias=bias, act=ops.ACT_SILU, out=out), [(x,) for x in xs])
         t_ref = timeit(lambda x: ops.bias_act(F.conv2d(x, wb), bias, ops.ACT_SILU), [(x,) for x in xs])
         print(f"  {K:4d}->{N:<4d} {hw:3d}x{hw:<3d} | {t_ours:8.1f} us ({nbytes / t_ours / 1e3:7.1f}) | {t_ref:8.1f} us")
+if "c3" in which:
+    print("3x3 conv: B C -> N HxW s | ours us | torch conv + bias_act us")
+    for Bc, C, N, hw, s in ((64, 16, 32, 320, 2), (64, 32, 64, 160, 2), (64, 64, 128, 80, 2), (64, 128, 256, 40, 2), (192, 16, 8, 80, 1), (192, 32, 16, 40, 1),
+                            (192, 64, 32, 20, 1), (192, 128, 64, 10, 1), (64, 64, 64, 80, 1), (64, 128, 64, 40, 1), (64, 256, 64, 20, 1), (64, 64, 64, 40, 1),
+                            (64, 64, 64, 20, 1)):
+        nb_in = Bc * C * hw * hw * 2
+        R = max(2, min(8, (300 << 20) // nb_in))
+        xs = [rn(Bc, C, hw, hw) for _ in range(R)]
+        w = torch.randn(N, C, 3, 3, device=dev, generator=g) * (9 * C) ** -0.5
+        bias = torch.randn(N, device=dev, generator=g)
+        ho = (hw - 1) // s + 1
+        wb = w.to(dt).contiguous(memory_format=cl)
+        tiles = ops.conv3x3_tiles(N, C, Bc, hw, hw, s)
+        try:
+            wpk = ops.pack_conv3x3_weight(w, dt, Bc * ho * ho)
+            t_ours = timeit(lambda x: ops.conv3x3(x, wpk, N, bias=bias, act=ops.ACT_SILU, stride=s), [(x,) for x in xs])
+        except Exception as e:  # noqa: BLE001
+            t_ours = float("nan")
+        t_ref = timeit(lambda x: ops.bias_act(F.conv2d(x, wb, None, s, 1), bias, ops.ACT_SILU), [(x,) for x in xs])
+        print(f"  B={Bc:3d} {C:4d}->{N:<4d} {hw:3d}x{hw:<3d} s{s} tiles{tiles} | {t_ours:8.1f} us | {t_ref:8.1f} us")
