@@ -6,7 +6,7 @@
 //                                                        (cfg/models/11/yolo11-test.yaml:34-39) in one pass
 // Both are pure HBM-bound elementwise kernels over channel-contiguous (NHWC) views with arbitrary pitches, so the
 // result can be written straight into a slice of a pre-allocated concat buffer.
-#include "el_common.cuh"
+#include "el_internal.h"
 
 namespace el {
 
@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(const T* __restrict__ x,
 // Replaces, for the inference engine, the uint8->float preprocess (engine/predictor.py:117-135), layer 0 of the yaml
 // (cfg/models/11/yolo11-test.yaml:21, a cuDNN conv that PyTorch runs through an fp32 NHWC round trip for 3 input channels)
 // and its bias + SiLU epilogue.  The 1/255 scale is folded into the weights by the caller.
-// CUDA-core FMA kernel balanced against the shared-memory pipe: a thread computes 4 adjacent output pixels x 16 output
-// channels, so every 16-byte weight broadcast (LDS.128 = 4 LSU cycles per warp) feeds 16 FMAs per lane; the 17 x 129 pixel
+// CUDA-core FMA kernel balanced against the shared-memory pipe: a thread computes 8 adjacent output pixels x 8 output
+// channels, so every 16-byte weight broadcast (LDS.128 = 4 LSU cycles per warp) feeds 32 FMAs per lane; the 17 x 129 pixel
 // input patch of an 8 x 64 output tile is staged once per CTA as fp32 (uint8 -> float without the conversion pipe: 0x4B000000 | b).
 constexpr int kStemTW = 64, kStemTH = 8, kStemIW = 2 * kStemTW + 1, kStemIH = 2 * kStemTH + 1, kStemRow = kStemIW * 3 + 1;  // 388 floats per patch row
 
@@ -246,48 +246,50 @@ __global__ void __launch_bounds__(128) stem_conv_u8_kernel(const uint8_t* __rest
         }
     }
     __syncthreads();
-    const int cg = tid & 15, ty = tid >> 4;  // 16 column groups of 4 pixels x 8 rows
-    const int ox = ox0 + 4 * cg, oy = oy0 + ty;
+    // thread <-> (half of a 16-channel block, group of 8 adjacent output pixels, row): 64 fp32 accumulators; every 16-byte weight
+    // broadcast feeds 8 pixels x 4 channels = 32 FMAs and every input float 8 channels, which keeps the shared-memory pipe
+    // (LDS.128 = 4 cycles per warp) below the FMA pipe
+    const int half = tid & 1, cg = (tid >> 1) & 7, ty = tid >> 4;
+    const int ox = ox0 + 8 * cg, oy = oy0 + ty;
     if (ox >= W / 2 || oy >= H / 2) return;
     constexpr int V = Vec16<T>::N;
 #pragma unroll 1
-    for (int cb = 0; cb < C0; cb += 16) {
-        float acc[4][16];
+    for (int cb = 8 * half; cb < C0; cb += 16) {
+        float acc[8][8];
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int p = 0; p < 8; ++p)
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[p][c] = s_b[cb + c];
-#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[p][c] = s_b[cb + c];
+#pragma unroll 1
         for (int ky = 0; ky < 3; ++ky) {
-            float v[27];  // 9 input pixels x 3 channels of patch row 2*ty + ky, starting at pixel 8*cg
-            const float* row = s_in + (2 * ty + ky) * kStemRow + 24 * cg;
+            float v[51];  // 17 input pixels x 3 channels of patch row 2*ty + ky, starting at pixel 16*cg
+            const float* row = s_in + (2 * ty + ky) * kStemRow + 48 * cg;
 #pragma unroll
-            for (int t = 0; t < 24; t += 4) {
+            for (int t = 0; t < 48; t += 4) {
                 const float4 q = *reinterpret_cast<const float4*>(row + t);
                 v[t] = q.x; v[t + 1] = q.y; v[t + 2] = q.z; v[t + 3] = q.w;
             }
-            v[24] = row[24]; v[25] = row[25]; v[26] = row[26];
+            v[48] = row[48]; v[49] = row[49]; v[50] = row[50];
 #pragma unroll
             for (int t = 0; t < 9; ++t) {  // t = kx*3 + ci
                 const float4* wp = reinterpret_cast<const float4*>(s_w + (ky * 9 + t) * C0 + cb);
+                const float4 wa = wp[0], wb = wp[1];  // two addresses per warp (the channel halves): broadcast
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const float4 w4 = wp[c4];  // same address for the whole warp: broadcast
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const float x = v[6 * p + t];
-                        acc[p][4 * c4] = fmaf(x, w4.x, acc[p][4 * c4]); acc[p][4 * c4 + 1] = fmaf(x, w4.y, acc[p][4 * c4 + 1]);
-                        acc[p][4 * c4 + 2] = fmaf(x, w4.z, acc[p][4 * c4 + 2]); acc[p][4 * c4 + 3] = fmaf(x, w4.w, acc[p][4 * c4 + 3]);
-                    }
+                for (int p = 0; p < 8; ++p) {
+                    const float x = v[6 * p + t];
+                    acc[p][0] = fmaf(x, wa.x, acc[p][0]); acc[p][1] = fmaf(x, wa.y, acc[p][1]);
+                    acc[p][2] = fmaf(x, wa.z, acc[p][2]); acc[p][3] = fmaf(x, wa.w, acc[p][3]);
+                    acc[p][4] = fmaf(x, wb.x, acc[p][4]); acc[p][5] = fmaf(x, wb.y, acc[p][5]);
+                    acc[p][6] = fmaf(x, wb.z, acc[p][6]); acc[p][7] = fmaf(x, wb.w, acc[p][7]);
                 }
             }
         }
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
+        for (int p = 0; p < 8; ++p) {
             if (ox + p >= W / 2) break;
             T* q = dst + n * ds.n + (int64_t)oy * ds.h + (int64_t)(ox + p) * ds.w + cb;
 #pragma unroll
-            for (int g = 0; g < 16 / V; ++g) {
+            for (int g = 0; g < 8 / V; ++g) {
                 float f[V];
 #pragma unroll
                 for (int e = 0; e < V; ++e) f[e] = silu_f<T>(acc[p][g * V + e]);
@@ -384,6 +386,13 @@ extern "C" int el_stem_conv_u8(const uint8_t* src, const float* w, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     Strides4 ds = s4(ds_);
     if (B > 65535) return EL_ERR_UNSUPPORTED;
+    if (dtype == EL_BF16 || dtype == EL_F16) {  // 16-bit activations: im2col GEMM on the tensor cores (stem_tc.cu)
+        if (ds.c != 1 || ds.n % 8 || ds.h % 8 || ds.w % 8 || !aligned16(dst) || (C0 != 16 && C0 != 32 && C0 != 64)) return EL_ERR_UNSUPPORTED;
+        const int rc = stem_tc_launch(src, w, bias, dst, ds, B, C0, H, W, dtype, st);
+        if (rc != EL_OK) return rc;
+        note_launches(1);
+        return check_launch();
+    }
     dim3 grid((unsigned)ceil_div(W / 2, kStemTW), (unsigned)ceil_div(H / 2, kStemTH), (unsigned)B);
     const size_t smem = (size_t)(28 * C0 + kStemIH * kStemRow) * sizeof(float);
     EL_DISPATCH_DTYPE(dtype, {
