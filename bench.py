@@ -51,7 +51,9 @@ def workload(a):
                         f"{(a.imgsz // 8) ** 2 + (a.imgsz // 16) ** 2 + (a.imgsz // 32) ** 2} anchors, predict defaults (conf .25, iou .7, max_det 300), "
                         "random-init weights (wave.gamma=0.5, no bias_init)",
             "batch_per_gpu": a.batch, "imgsz": a.imgsz, "scale": a.scale, "nc": a.nc, "parallelism": f"batch-sharded replicas x{a.gpus}",
-            "l2_policy": "inputs larger than L2 (157 MB bf16 batch; 126 MB L2); per-kernel pass flushes L2 with a 256 MB write"}
+            "input": "uint8 HWC batch (what the predictor's preprocess consumes); `value`: resident in HBM, `e2e`: pinned host memory",
+            "l2_policy": "every step streams ~8 GB of activations through the 126 MB L2, so nothing of the 78.6 MB input batch or of one step's "
+                         "intermediates survives to the next step; the per-kernel pass rotates input copies totalling more than L2"}
 
 
 # ----------------------------------------------------------------------------------- clocks
@@ -267,6 +269,20 @@ def profile_kernels(pred, a, iters=10):
     return per
 
 
+def step_traffic(kernel):
+    """DRAM bytes (read + write) of all launches of `kernel` in one step, from the committed ncu capture of the default workload."""
+    names = {"pwconv": ["pw::pwconv_tc_kernel"], "dwconv": ["el::dwconv_tile_kernel"], "bias_act": ["el::bias_act_tiled", "el::bias_act_flat"],
+             "stem_conv_u8": ["stemtc::stem_tc_kernel"], "wave_merge_bands": ["el::merge_fwd_x2"], "dwt_haar": ["el::dwt_fwd_tiled"],
+             "gfl_decode_emit": ["el::gfl_decode_emit_kernel"], "nms_sweep": ["el::nms_sweep"], "upsample2x_cat": ["el::upsample2x_cat_tiled"]}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01e_step_b64_time_dram.json")) as f:
+            prof = json.load(f)
+        # pwconv_tc_kernel also runs the narrow 3x3 convs (el_conv3x3_fwd); the capture cannot tell the two apart
+        return sum(prof[n]["dram_bytes"] for n in names.get(kernel, []) if n in prof) or None
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -363,9 +379,15 @@ def product_arm(a):
         peak, peak_src = measured_peak()
         top = max(per, key=lambda k: per[k]["us"])
         line["kernels"] = per
+        best = max(per[top]["sites"], key=lambda s_: s_["MB"])
         line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": per[top]["gbs"], "peak": peak, "unit": "GB/s",
-                            "frac": per[top]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                            "note": "achieved = algorithmic bytes of all launch sites of this kernel in one step / their summed CUDA-event time"}
+                            "frac": per[top]["gbs"] / peak,
+                            "traffic": step_traffic(top) if (a.scale, a.batch, a.imgsz, a.nc) == ("n", 64, 640, 80) else None, "peak_source": peak_src,
+                            "launch_sites": per[top]["launch_sites"], "algorithmic_bytes": per[top]["bytes"],
+                            "largest_site": {"shape": best["shape"], "MB": best["MB"], "us": best["us"], "achieved": best["gbs"], "frac": best["gbs"] / peak},
+                            "note": "achieved = algorithmic bytes of ALL launch sites of this kernel in one step / their summed CUDA-event time "
+                                    "(each site timed alone, inputs rotated through > L2); traffic = DRAM bytes of the same launches in one step "
+                                    "from the committed ncu capture (profiles/r01e_step_b64_time_dram.json), null for other configs"}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         rate, ms, threads = cpu_oracle_rate(a, steps=3, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
