@@ -44,6 +44,7 @@ class Predictor:
         for m in model.modules():
             if isinstance(m, GFLHeadv2_uniH):
                 m.el_detect = dict(self.nms_kw)  # the head runs the fused decode + NMS kernel chain
+                m.el_level_streams = True         # ... and its three pyramid levels as parallel graph branches
         self.u8 = torch.empty((batch, imgsz, imgsz, 3), device=self.device, dtype=torch.uint8)
         self.x = torch.empty((batch, 3, imgsz, imgsz), device=self.device, dtype=self.dtype, memory_format=torch.channels_last)
         self.host_out = torch.empty((batch, max_det, 6), dtype=torch.float32).pin_memory()

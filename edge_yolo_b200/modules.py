@@ -105,15 +105,48 @@ def gfl_head_forward(self, x):
     computed and dropped on this path).  Eval: one fused decode kernel produces
     y (B, 4+nc, A) in fp32; returns `y` when exporting, else `(y, x)`.
     """
-    boxes, clss = [], []
-    for i in range(self.nl):
+    def tower_in(i):
         xi = x[i]
         for name in ("stem", "dat", "pos_cls", "pos_reg", "cit_cls", "cit_reg"):  # Identity placeholders in the reference
             mods = getattr(self, name, None)
             if mods:
                 xi = mods[i](xi)
-        boxes.append(self.cv2[i](xi))
-        clss.append(self.cv3[i](xi))
+        return xi
+
+    def towers(i):
+        xi = tower_in(i)
+        return self.cv2[i](xi), self.cv3[i](xi)
+
+    if getattr(self, "el_level_streams", False) and x[0].is_cuda and not self.training:
+        # engine: the box and class towers of the three pyramid levels are six independent chains until the decode, and the
+        # 40x40 / 20x20 ones are short kernels that cannot fill the GPU -- run them as parallel branches (fork / join on side
+        # streams; captured into the CUDA graph as a fork-join)
+        main = torch.cuda.current_stream(x[0].device)
+        side = self.__dict__.setdefault("_el_streams", [torch.cuda.Stream(device=x[0].device) for _ in range(2 * self.nl - 1)])
+        fork = torch.cuda.Event()
+        fork.record(main)
+        boxes, clss = [None] * self.nl, [None] * self.nl
+        joins = []
+        jobs = [(i, t) for i in range(self.nl) for t in (0, 1)][1:]  # (level, tower); job (0, box tower) stays on the main stream
+        for st, (i, t) in zip(side, jobs):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                if t == 0:
+                    boxes[i] = self.cv2[i](tower_in(i))
+                else:
+                    clss[i] = self.cv3[i](tower_in(i))
+                ev = torch.cuda.Event()
+                ev.record(st)
+                joins.append(ev)
+        boxes[0] = self.cv2[0](tower_in(0))
+        for ev in joins:
+            main.wait_event(ev)
+    else:
+        boxes, clss = [], []
+        for i in range(self.nl):
+            bi, ci = towers(i)
+            boxes.append(bi)
+            clss.append(ci)
     if self.training:
         for i in range(self.nl):
             x[i] = torch.cat((boxes[i], clss[i]), 1)
