@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from ._lib import lib
+from ._lib import check as _check, lib
 from .model import EdgeLineYOLO
 from .modules import GFLHeadv2_uniH, _WaveletEnhancer
 
@@ -36,8 +36,13 @@ def build_model(scale="n", nc=80, seed=0, gamma=0.5, dtype=torch.bfloat16, devic
 
 class Predictor:
     def __init__(self, model: EdgeLineYOLO, batch: int, imgsz: int = 640, conf=0.25, iou=0.7, max_det=300, multi_label=False,
-                 agnostic=False, max_nms=30000, use_graph=True):
+                 agnostic=False, max_nms=30000, use_graph=True, pipeline_nms=True):
+        """`pipeline_nms` (with `use_graph`): the step is captured as TWO graphs, A = stem .. decode + candidate emit and
+        B = NMS sort + sweep, on two alternating buffer sets; B runs on a side stream, so the latency-bound NMS tail of batch i
+        (one CTA per image) overlaps the forward of batch i+1.  Results of a step are valid once its B graph has finished
+        (`drain()` / the events handled inside `predict_u8` / `predict_many`)."""
         self.model, self.batch, self.imgsz = model, batch, imgsz
+        self.pipelined = bool(use_graph and pipeline_nms)
         self.nms_kw = dict(conf_thres=conf, iou_thres=iou, multi_label=multi_label, agnostic=agnostic, max_det=max_det, max_nms=max_nms)
         p = next(model.parameters())
         self.device, self.dtype = p.device, p.dtype
@@ -83,18 +88,76 @@ class Predictor:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         n0 = lib().el_launch_count()
-        self.graph_from_u8 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_from_u8):
-            self.out, self.cnt = self._forward(True)
-        self.launches_per_step = int(lib().el_launch_count() - n0)
+        if self.pipelined:
+            self._capture_pipelined()
+        else:
+            self.graph_from_u8 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_from_u8):
+                self.out, self.cnt = self._forward(True)
+        self.launches_per_step = int(lib().el_launch_count() - n0) // (2 if self.pipelined else 1)
         self.graph_from_x = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_from_x, pool=self.graph_from_u8.pool()):
+        with torch.cuda.graph(self.graph_from_x, pool=(self.sets[0]["A"] if self.pipelined else self.graph_from_u8).pool()):
             self.out_x, self.cnt_x = self._forward(False)
+
+    def _capture_pipelined(self):
+        import ctypes
+
+        head = self.model.model[-1]
+        nc = head.nc
+        A = sum((self.imgsz // int(s)) ** 2 for s in head.stride)
+        need = ctypes.c_size_t()
+        _check(lib().el_gfl_detect_workspace_bytes(self.batch, nc, A, int(bool(self.nms_kw["multi_label"])), int(self.nms_kw["max_nms"]),
+                                                      ctypes.byref(need)), "el_gfl_detect_workspace_bytes")
+        self.sets, pool = [], None
+        for _ in range(2):
+            split = dict(workspace=torch.empty(need.value, device=self.device, dtype=torch.uint8),
+                         out=torch.zeros((self.batch, self.nms_kw["max_det"], 6), device=self.device, dtype=torch.float32),
+                         cnt=torch.zeros((self.batch,), device=self.device, dtype=torch.int32))
+            head.el_detect_split = split
+            gA = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gA, pool=pool):
+                self._forward(True)  # stem .. decode + candidate emit into split["workspace"]
+            pool = gA.pool()
+            gB = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gB, pool=pool):
+                split["finish"]()     # sort + sweep on the same buffers -> split["out"], split["cnt"]
+            self.sets.append(dict(A=gA, B=gB, out=split["out"], cnt=split["cnt"], split=split))  # `split` keeps the head maps alive
+        head.el_detect_split = None
+        self.side = torch.cuda.Stream(device=self.device)
+        self.ev_a = [torch.cuda.Event() for _ in range(2)]
+        self.b_done = [torch.cuda.Event() for _ in range(2)]
+        for e in self.b_done:
+            e.record(torch.cuda.current_stream(self.device))
+        self._k = 0
+        self.out, self.cnt = self.sets[0]["out"], self.sets[0]["cnt"]
+
+    def drain(self):
+        """Make the current stream wait for every NMS graph still running on the side stream (no-op when not pipelined)."""
+        if self.pipelined:
+            main = torch.cuda.current_stream(self.device)
+            for e in self.b_done:
+                main.wait_event(e)
 
     def step_device(self, from_u8: bool = True):
         """One pass with the input batch already resident in HBM; results stay on the device.  `from_u8` (default): the uint8
-        HWC batch in `self.u8`, i.e. the product path incl. preprocess; else the preprocessed activations in `self.x`."""
+        HWC batch in `self.u8`, i.e. the product path incl. preprocess; else the preprocessed activations in `self.x`.
+        Pipelined mode: the forward is enqueued on the current stream, the NMS graph on the side stream; the returned tensors
+        belong to one of two alternating buffer sets and are valid after `self.b_done[k]` / `drain()`."""
         if from_u8:
+            if self.pipelined:
+                k = self._k
+                self._k ^= 1
+                S = self.sets[k]
+                main = torch.cuda.current_stream(self.device)
+                main.wait_event(self.b_done[k])  # the NMS graph that last used this buffer set (two steps ago) is done
+                S["A"].replay()
+                self.ev_a[k].record(main)
+                self.side.wait_event(self.ev_a[k])
+                with torch.cuda.stream(self.side):
+                    S["B"].replay()
+                    self.b_done[k].record(self.side)
+                self.out, self.cnt, self._last = S["out"], S["cnt"], k
+                return S["out"], S["cnt"]
             if self.graph_from_u8 is not None:
                 self.graph_from_u8.replay()
                 return self.out, self.cnt
@@ -105,14 +168,11 @@ class Predictor:
         return self._forward(False)
 
     def predict_u8(self, host_u8: torch.Tensor):
-        """host_u8: pinned uint8 (B, H, W, 3).  H2D copy, one graph replay, D2H of rows + counts.
+        """host_u8: pinned uint8 (B, H, W, 3).  H2D copy, one step, D2H of rows + counts.
         Returns (rows (B, max_det, 6) pinned fp32, counts (B) pinned int32); valid rows are rows[b, :counts[b]]."""
         self.u8.copy_(host_u8, non_blocking=True)
-        if self.graph_from_u8 is not None:
-            self.graph_from_u8.replay()
-            out, cnt = self.out, self.cnt
-        else:
-            out, cnt = self._forward(True)
+        out, cnt = self.step_device()
+        self.drain()
         self.host_out.copy_(out, non_blocking=True)
         self.host_cnt.copy_(cnt, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
@@ -150,16 +210,14 @@ class Predictor:
             main.wait_event(h2d_done[i & 1])
             self.u8.copy_(P["stage"][i & 1], non_blocking=True)  # device-to-device: frees the stage for the next H2D
             stage_free[i & 1].record(main)
-            if self.graph_from_u8 is not None:
-                self.graph_from_u8.replay()
-                out, cnt = self.out, self.cnt
-            else:
-                out, cnt = self._forward(True)
+            out, cnt = self.step_device()
             if i >= 2:
                 done[i & 1].synchronize()  # the host buffers of batch i-2 are about to be overwritten
-            P["out"][i & 1].copy_(out, non_blocking=True)
-            P["cnt"][i & 1].copy_(cnt, non_blocking=True)
-            done[i & 1].record(main)
+            res_stream = self.side if self.pipelined else main  # the rows come out of the NMS graph: copy them in its stream order
+            with torch.cuda.stream(res_stream):
+                P["out"][i & 1].copy_(out, non_blocking=True)
+                P["cnt"][i & 1].copy_(cnt, non_blocking=True)
+                done[i & 1].record(res_stream)
             if i >= 1 and consume is not None:
                 done[(i - 1) & 1].synchronize()
                 consume(i - 1, P["out"][(i - 1) & 1], P["cnt"][(i - 1) & 1])

@@ -158,7 +158,15 @@ def gfl_head_forward(self, x):
         bias = self.el_head_bias = tuple([t.to(boxes[0].device) for t in side] for side in bias)
     det = getattr(self, "el_detect", None)
     if det is not None:  # engine path (Predictor): fused decode + NMS, returns (rows (B, max_det, 6), counts (B))
-        return ops.gfl_detect(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride], bias=bias, **det)
+        split = getattr(self, "el_detect_split", None)
+        if split is None:
+            return ops.gfl_detect(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride], bias=bias, **det)
+        # pipelined engine: this call only decodes + emits candidate keys into the caller's workspace; `split["finish"]()` runs the
+        # sort + sweep on the same buffers (captured as a second CUDA graph that overlaps the next batch's forward)
+        args = (boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride])
+        kw = dict(det, bias=bias, workspace=split["workspace"], out=split["out"], cnt=split["cnt"])
+        split["finish"] = lambda: ops.gfl_detect(*args, stages=6, **kw)
+        return ops.gfl_detect(*args, stages=1, **kw)
     y = ops.gfl_decode(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride], bias=bias)
     if getattr(self, "export", False):
         return y

@@ -321,10 +321,14 @@ def gfl_decode(boxes, clss, dgqp, strides, want_quality: bool = False, bias=None
 
 
 def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, multi_label=False, agnostic=False, classes=None,
-               max_det=300, max_nms=30000, max_wh=7680.0, bias=None, workspace=None):
+               max_det=300, max_nms=30000, max_wh=7680.0, bias=None, workspace=None, stages=7, out=None, cnt=None):
     """Fused decode + NMS of the engine path: same inputs as `gfl_decode`, same outputs as `nms_batched`
     (out (B, max_det, 6), count (B) int32); the dense (B, 4+nc, A) tensor is never written.  Falls back to
-    `gfl_decode` + `nms_batched` (identical results) when the head maps are not dense NHWC."""
+    `gfl_decode` + `nms_batched` (identical results) when the head maps are not dense NHWC.
+
+    `stages` (bit 0 decode + candidate emit, bit 1 select + sort, bit 2 sweep) runs part of the chain on the caller's
+    `workspace` / `out` / `cnt`: the engine captures stage 1 and stages 6 as two CUDA graphs so that the latency-bound NMS tail
+    of batch i overlaps the backbone of batch i+1 (engine.Predictor)."""
     nl = len(boxes)
     _need_cuda(*boxes, *clss)
     B, nc = boxes[0].shape[0], clss[0].shape[1]
@@ -339,8 +343,10 @@ def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, mult
     check(L.el_gfl_detect_workspace_bytes(B, nc, A, int(bool(multi_label)), int(max_nms), ctypes.byref(need)), "el_gfl_detect_workspace_bytes")
     dev = boxes[0].device
     ws = workspace if workspace is not None and workspace.numel() >= need.value else torch.empty(need.value, device=dev, dtype=torch.uint8)
-    out = torch.empty((B, max_det, 6), device=dev, dtype=torch.float32)
-    cnt = torch.empty((B,), device=dev, dtype=torch.int32)
+    if stages != 7 and (workspace is None or ws is not workspace):
+        raise EdgelineError("gfl_detect: staged execution needs a caller-owned workspace of el_gfl_detect_workspace_bytes")
+    out = torch.empty((B, max_det, 6), device=dev, dtype=torch.float32) if out is None else out
+    cnt = torch.empty((B,), device=dev, dtype=torch.int32) if cnt is None else cnt
     keep = None
     if classes is not None:
         keep = torch.zeros(nc, dtype=torch.int32)
@@ -348,11 +354,19 @@ def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, mult
         keep = keep.to(dev)
     cols = [_ptrs([w[k] for w in dgqp]) for k in range(4)]
     bb, cb = _bias_tables(bias, nl)
-    st = L.el_gfl_detect_fwd(nl, _ptrs(boxes), _i64(bs), _ptrs(clss), _i64(cs), (c_int32 * len(hw))(*hw),
-                             (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3], bb, cb, B, nc, _dt(boxes[0]),
-                             float(conf_thres), float(iou_thres), int(bool(multi_label)), int(bool(agnostic)),
-                             keep.data_ptr() if keep is not None else None, int(max_det), int(max_nms), float(max_wh), ws.data_ptr(),
-                             need.value, out.data_ptr(), cnt.data_ptr(), None, _stream())
+    if stages != 7:
+        L.el_debug_set_detect_stages(int(stages))
+    try:
+        st = L.el_gfl_detect_fwd(nl, _ptrs(boxes), _i64(bs), _ptrs(clss), _i64(cs), (c_int32 * len(hw))(*hw),
+                                 (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3], bb, cb, B, nc, _dt(boxes[0]),
+                                 float(conf_thres), float(iou_thres), int(bool(multi_label)), int(bool(agnostic)),
+                                 keep.data_ptr() if keep is not None else None, int(max_det), int(max_nms), float(max_wh), ws.data_ptr(),
+                                 need.value, out.data_ptr(), cnt.data_ptr(), None, _stream())
+    finally:
+        if stages != 7:
+            L.el_debug_set_detect_stages(7)
+    if st == 2 and stages != 7:
+        raise EdgelineError("gfl_detect: staged execution needs dense NHWC head maps")
     if st == 2:  # EL_ERR_UNSUPPORTED: strided / NCHW maps -> two-call path with the same kernels downstream
         y = gfl_decode(boxes, clss, dgqp, strides, bias=bias)
         return nms_batched(y, conf_thres, iou_thres, multi_label=multi_label, agnostic=agnostic, classes=classes, max_det=max_det,

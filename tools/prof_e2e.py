@@ -34,7 +34,8 @@ def timed(fn, n=10):
 
 
 print("H2D 78.6 MB            : %.3f ms (wall %.3f)" % timed(lambda: pred.u8.copy_(host, non_blocking=True)))
-print("graph from u8          : %.3f ms (wall %.3f)" % timed(lambda: pred.graph_from_u8.replay()))
+print("step from u8 (drained) : %.3f ms (wall %.3f)" % timed(lambda: (pred.step_device(), pred.drain())))
+print("step from u8 (pipelined): %.3f ms (wall %.3f)" % timed(lambda: pred.step_device(), 20))
 print("graph from x           : %.3f ms (wall %.3f)" % timed(lambda: pred.graph_from_x.replay()))
 print("D2H rows               : %.3f ms (wall %.3f)" % timed(lambda: pred.host_out.copy_(pred.out, non_blocking=True)))
 print("predict_u8 (serial)    : %.3f ms (wall %.3f)" % timed(lambda: pred.predict_u8(host)))
@@ -52,6 +53,6 @@ t0 = time.perf_counter()
 for _ in range(16):
     with torch.cuda.stream(side):
         stage.copy_(host, non_blocking=True)
-    pred.graph_from_u8.replay()
+    pred.step_device()
 torch.cuda.synchronize()
 print("independent copy||graph: %.3f ms / iter" % ((time.perf_counter() - t0) * 1e3 / 16))
