@@ -43,6 +43,7 @@ class Predictor:
         (`drain()` / the events handled inside `predict_u8` / `predict_many`)."""
         self.model, self.batch, self.imgsz = model, batch, imgsz
         self.pipelined = bool(use_graph and pipeline_nms)
+        self.defer_decode = True
         self.nms_kw = dict(conf_thres=conf, iou_thres=iou, multi_label=multi_label, agnostic=agnostic, max_det=max_det, max_nms=max_nms)
         p = next(model.parameters())
         self.device, self.dtype = p.device, p.dtype
@@ -112,7 +113,7 @@ class Predictor:
         for _ in range(2):
             split = dict(workspace=torch.empty(need.value, device=self.device, dtype=torch.uint8),
                          out=torch.zeros((self.batch, self.nms_kw["max_det"], 6), device=self.device, dtype=torch.float32),
-                         cnt=torch.zeros((self.batch,), device=self.device, dtype=torch.int32))
+                         cnt=torch.zeros((self.batch,), device=self.device, dtype=torch.int32), defer_decode=self.defer_decode)
             head.el_detect_split = split
             gA = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gA, pool=pool):

@@ -165,6 +165,9 @@ def gfl_head_forward(self, x):
         # sort + sweep on the same buffers (captured as a second CUDA graph that overlaps the next batch's forward)
         args = (boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride])
         kw = dict(det, bias=bias, workspace=split["workspace"], out=split["out"], cnt=split["cnt"])
+        if split.get("defer_decode"):  # the decode + emit kernel moves into the second graph as well
+            split["finish"] = lambda: ops.gfl_detect(*args, stages=7, **kw)
+            return split["out"], split["cnt"]
         split["finish"] = lambda: ops.gfl_detect(*args, stages=6, **kw)
         return ops.gfl_detect(*args, stages=1, **kw)
     y = ops.gfl_decode(boxes, clss, _dgqp_weights(self), [float(s) for s in self.stride], bias=bias)
