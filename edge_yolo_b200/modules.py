@@ -218,9 +218,21 @@ def _pixel_linear(t: torch.Tensor) -> bool:
 
 def _pw_ok(conv: nn.Conv2d, srcs, *others) -> bool:
     """el_pwconv_fwd applies: 1x1 / stride 1 / dense conv, 16-bit NHWC (or channel-slice) operands, <= 4 sources, no autograd."""
-    return (conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.groups == 1 and conv.padding in ((0, 0), 0) and conv.out_channels % 8 == 0
+    if not (conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.groups == 1 and conv.padding in ((0, 0), 0) and conv.out_channels % 8 == 0
             and len(srcs) <= 4 and srcs[0].is_cuda and srcs[0].dtype in (torch.bfloat16, torch.float16) and not torch.is_grad_enabled()
-            and all(_pixel_linear(t) for t in srcs) and all(t is None or _pixel_linear(t) for t in others))
+            and all(_pixel_linear(t) for t in srcs) and all(t is None or _pixel_linear(t) for t in others)):
+        return False
+    # the weight block of one output-channel tile stays resident in shared memory (<= 128 KB): very wide K splits N into many tiles,
+    # each of which re-reads the activations -- beyond 4 tiles cuDNN is the better choice
+    x0 = srcs[0]
+    key = (tuple(t.shape[1] for t in srcs), x0.shape[0] * x0.shape[2] * x0.shape[3])
+    cache = conv.__dict__.setdefault("el_pw_tiles", {})
+    n_tiles = cache.get(key)
+    if n_tiles is None:
+        row_bytes = sum(2 * bw for _, _, bw in ops._pw_chunks(key[0]))
+        n_tile = ops._lib.lib().el_pwconv_tile(conv.out_channels, row_bytes, key[1])
+        n_tiles = cache[key] = (-(-conv.out_channels // n_tile) if n_tile > 0 else 99)
+    return n_tiles <= 4
 
 
 USE_CONV3X3 = True  # el_conv3x3_fwd for the dense 3x3 convs of the engine graph

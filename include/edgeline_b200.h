@@ -46,8 +46,10 @@ int el_last_cuda_error(void);
 /* Number of kernels this library has enqueued so far in the process (measurement aid: bench.py
  * reports the per-step delta as `gpu_launches`). */
 unsigned long long el_launch_count(void);
-/* Measurement aid for bench.py: run only some stages of el_gfl_detect_fwd / el_nms_batched's tail so that they can be
- * timed separately (bit0 candidate emit, bit1 select + sort, bit2 sweep; default 7 = everything).  Process-global. */
+/* Stage mask of el_gfl_detect_fwd / el_nms_batched's tail (bit0 decode + candidate emit, bit1 select + sort, bit2 sweep;
+ * default 7 = everything): the following calls launch only the selected stages on the caller's workspace.  Used by bench.py to
+ * time the stages separately and by the inference engine to capture the chain as separate CUDA graphs (the NMS of batch i
+ * overlaps the forward of batch i+1).  Process-global: set, call, restore from one thread. */
 void el_debug_set_detect_stages(int mask);
 
 /* ---- a1. Haar analysis: _PywtDWT2D.forward, nn/modules/block.py:3619-3642 -------------------
