@@ -50,7 +50,8 @@ struct Args {
     int nchunks;
     const void* wpk;         // [n_tiles][w_bytes] swizzled weight tiles
     const float* bias;       // [N] or null
-    const void* res; int64_t res_pitch; float res_scale;  // out = res + res_scale * act(...)
+    const void* res; int64_t res_pitch; float res_scale;  // RES 1: out = res + res_scale * act(...);  RES 2: addend z (B, N, H/2, W/2), pitch = its pixel pitch
+    int up_H, up_W;          // RES 2: output map height / width (the flat pixel index is decoded to find the low-resolution addend row)
     int has_out2, split;     // channels >= split go to out2
     int64_t M;
     int N, n_tile, ob;       // ob: channels per staging / store box (16, 32 or 64)
@@ -163,7 +164,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 
-template <typename T, int ACT, bool RES>
+template <typename T, int ACT, int RES>  // RES: 0 none, 1 out = res + res_scale * act(.), 2 out = act(. + nearest-2x-upsampled addend)
 __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_constant__ Args A) {
     extern __shared__ __align__(1024) unsigned char sm_raw[];
     // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the 128-byte swizzle atoms need
@@ -280,8 +281,16 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
             mbar_wait(bar_acc_full + 8 * b, (uint32_t)(tl >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + (uint32_t)b * n_tile + ((uint32_t)(q * 32) << 16);
-            const T* rrow = RES ? reinterpret_cast<const T*>(A.res) + (m0 + row) * A.res_pitch + n0 : nullptr;
             const bool rvalid = m0 + row < A.M;
+            const T* rrow = nullptr;
+            if (RES == 1) rrow = reinterpret_cast<const T*>(A.res) + (m0 + row) * A.res_pitch + n0;
+            if (RES == 2 && rvalid) {  // pixel (b, y, x) of the output reads pixel (b, y / 2, x / 2) of the low-resolution addend
+                const int64_t m = m0 + row;
+                const int hw = A.up_H * A.up_W;
+                const int64_t bimg = m / hw;
+                const int r = (int)(m - bimg * hw), y = r / A.up_W, x = r - y * A.up_W;
+                rrow = reinterpret_cast<const T*>(A.res) + ((bimg * (A.up_H / 2) + y / 2) * (A.up_W / 2) + x / 2) * A.res_pitch + n0;
+            }
             for (int c0 = 0; c0 < n_real; c0 += ob, ++sub) {
                 const uint32_t stg = sbase + off_stage + (uint32_t)(sub & 1) * staging_bytes;
                 if (et == 0) bulk_wait_read<1>();  // the store that last read this staging buffer (two uses ago) is done with it
@@ -303,6 +312,17 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                         f[4 * e4] = __uint_as_float(v[jj][4 * e4]) + bb.x; f[4 * e4 + 1] = __uint_as_float(v[jj][4 * e4 + 1]) + bb.y;
                         f[4 * e4 + 2] = __uint_as_float(v[jj][4 * e4 + 2]) + bb.z; f[4 * e4 + 3] = __uint_as_float(v[jj][4 * e4 + 3]) + bb.w;
                     }
+                    if (RES == 2) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (rvalid && n0 + c0 + j + 8 * h < A.N) {
+                                float r8[8];
+                                unpack<T>(ldg_cached(rrow + c0 + j + 8 * h), r8);  // each low-resolution pixel is read by 4 output pixels: keep it in L1
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[8 * h + e] += r8[e];
+                            }
+                        }
+                    }
                     if (ACT == 1) {  // SiLU: x * sigmoid(x) = h + h * tanh(h), h = x / 2 (one MUFU per element; 16-bit outputs)
 #pragma unroll
                         for (int e = 0; e < 16; ++e) { const float h = 0.5f * f[e]; f[e] = fmaf(h, tanh_fast(h), h); }
@@ -312,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                     }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        if (RES) {
+                        if (RES == 1) {
                             if (rvalid && n0 + c0 + j + 8 * h < A.N) {
                                 float r8[8];
                                 unpack<T>(ldg_stream(rrow + c0 + j + 8 * h), r8);
@@ -401,19 +421,19 @@ static bool make_map4(CUtensorMap* map, const void* base, int channels, int W, i
 static inline int box_bytes_for(int channels) { return channels <= 16 ? 32 : (channels <= 32 ? 64 : 128); }
 
 template <typename T>
-static cudaError_t launch(const Args& A, dim3 grid, size_t smem, bool res, cudaStream_t st) {
+static cudaError_t launch(const Args& A, dim3 grid, size_t smem, int res_mode, cudaStream_t st) {
 #define EL_PW_LAUNCH(ACT, RES)                                                                                                          \
     {                                                                                                                                   \
         cudaError_t e = cudaFuncSetAttribute(pwconv_tc_kernel<T, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
         if (e != cudaSuccess) return e;                                                                                                 \
         return launch_pdl(pwconv_tc_kernel<T, ACT, RES>, grid, dim3(kThreads), smem, st, A);                                            \
-                                                                                                                   \
     }
-    if (res) {
-        if (A.act == 0) EL_PW_LAUNCH(0, true) else if (A.act == 1) EL_PW_LAUNCH(1, true) else EL_PW_LAUNCH(2, true)
-    } else {
-        if (A.act == 0) EL_PW_LAUNCH(0, false) else if (A.act == 1) EL_PW_LAUNCH(1, false) else EL_PW_LAUNCH(2, false)
+#define EL_PW_BY_ACT(RES)                                                                                                               \
+    {                                                                                                                                   \
+        if (A.act == 0) EL_PW_LAUNCH(0, RES) else if (A.act == 1) EL_PW_LAUNCH(1, RES) else EL_PW_LAUNCH(2, RES)                        \
     }
+    if (res_mode == 1) EL_PW_BY_ACT(1) else if (res_mode == 2) EL_PW_BY_ACT(2) else EL_PW_BY_ACT(0)
+#undef EL_PW_BY_ACT
 #undef EL_PW_LAUNCH
 }
 
@@ -437,8 +457,8 @@ extern "C" int el_pwconv_tile(int N, int w_row_bytes, int64_t M) {
 }
 
 extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], const int32_t src_c[], const void* wpk, const float* bias,
-                             const void* res, int64_t res_pitch, float res_scale, void* out, int64_t out_pitch, void* out2, int64_t out2_pitch,
-                             int split, int64_t M, int N, int act, int dtype, void* stream) {
+                             const void* res, int64_t res_pitch, float res_scale, int up_H, int up_W, void* out, int64_t out_pitch, void* out2,
+                             int64_t out2_pitch, int split, int64_t M, int N, int act, int dtype, void* stream) {
     if (nsrc < 1 || nsrc > pw::kMaxSrc || !src || !src_pitch || !src_c || !wpk || !out || M <= 0 || N <= 0 || act < 0 || act > 2) return EL_ERR_ARG;
     if (dtype != EL_BF16 && dtype != EL_F16) return EL_ERR_UNSUPPORTED;
     if (N % 8 || M >= (1ll << 31) - 256 || (out2 && (split % 16 || split <= 0 || split >= N))) return EL_ERR_UNSUPPORTED;
@@ -477,7 +497,7 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     if (n_tiles > 1) while (A.n_tile % ob) ob >>= 1;  // an overhanging last box is only harmless past N (clipped), not into the next tile
     if (ob < 16) return EL_ERR_UNSUPPORTED;
     A.ob = ob;
-    A.wpk = wpk; A.bias = bias; A.res = res; A.res_pitch = res_pitch; A.res_scale = res_scale;
+    A.wpk = wpk; A.bias = bias; A.res = res; A.res_pitch = res_pitch; A.res_scale = res_scale; A.up_H = up_H; A.up_W = up_W;
     A.has_out2 = out2 != nullptr; A.split = out2 ? split : N;
     A.M = M; A.N = N; A.act = act;
     uint32_t cols = 32;
@@ -511,7 +531,9 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     if (out2 && !pw::make_map(&A.out2_map, out2, N - split, M, out2_pitch, ob * 2, dtype)) return EL_ERR_CUDA;
     dim3 grid((unsigned)gx, (unsigned)n_tiles);
     cudaStream_t st = (cudaStream_t)stream;
-    const cudaError_t e = dtype == EL_BF16 ? pw::launch<__nv_bfloat16>(A, grid, smem, res != nullptr, st) : pw::launch<__half>(A, grid, smem, res != nullptr, st);
+    const int res_mode = !res ? 0 : (up_H > 0 ? 2 : 1);
+    if (res_mode == 2 && ((up_H & 1) || (up_W & 1) || up_W <= 0 || M % ((int64_t)up_H * up_W))) return EL_ERR_ARG;
+    const cudaError_t e = dtype == EL_BF16 ? pw::launch<__nv_bfloat16>(A, grid, smem, res_mode, st) : pw::launch<__half>(A, grid, smem, res_mode, st);
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
     note_launches(1);
     return check_launch();
@@ -595,7 +617,7 @@ extern "C" int el_conv3x3_fwd(const void* x, const int64_t xs_[4], int C, const 
     if (!pw::make_map4(&A.out_map, out, N, Wo, Ho, B, os_, ob * 2, A.tw, A.th, 1, dtype)) return EL_ERR_CUDA;
     dim3 grid((unsigned)gx, (unsigned)n_tiles);
     cudaStream_t st = (cudaStream_t)stream;
-    const cudaError_t e = dtype == EL_BF16 ? pw::launch<__nv_bfloat16>(A, grid, smem, false, st) : pw::launch<__half>(A, grid, smem, false, st);
+    const cudaError_t e = dtype == EL_BF16 ? pw::launch<__nv_bfloat16>(A, grid, smem, 0, st) : pw::launch<__half>(A, grid, smem, 0, st);
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
     note_launches(1);
     return check_launch();

@@ -167,6 +167,10 @@ class EdgeLineYOLO(nn.Module):
                         and isinstance(cat.f, list) and cat.f[0] == -1 and cat.d == 1 and up.i not in self.save):
                     up.el_fused_into_next, cat.el_upsample_first = True, True
                     cat.forward = types.MethodType(M.concat_engine_forward, cat)
+                    nxt = layers[cat.i + 1] if cat.i + 1 < len(layers) else None
+                    if (isinstance(nxt, M.DSC3K2_Wavelet) and nxt.f == -1 and cat.i not in self.save and hasattr(nxt.cv1, "el_bias")
+                            and nxt.cv1.conv.kernel_size == (1, 1) and nxt.c % 16 == 0 and len(cat.f) == 2):
+                        cat.el_up_lazy = True  # Upsample + Concat + cv1 collapse into a low-resolution GEMM + an addend epilogue
             for cat, nxt in zip(layers, layers[1:]):  # Concat -> DSC3K2_Wavelet: cv1 reads the parts in place
                 if (isinstance(cat, Concat) and not getattr(cat, "el_upsample_first", False) and cat.d == 1 and cat.i not in self.save
                         and isinstance(nxt, M.DSC3K2_Wavelet) and nxt.f == -1 and isinstance(cat.f, list) and len(cat.f) <= 4):

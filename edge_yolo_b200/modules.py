@@ -256,7 +256,7 @@ def _conv3_ok(conv: nn.Conv2d, x: torch.Tensor, out=None) -> bool:
     return 0 < n_tiles <= 3
 
 
-def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=None, res_scale=1.0):
+def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=None, res_scale=1.0, up_addend=None):
     """1x1 conv over the channel concatenation of `srcs` + bias + activation (+ residual) as one tcgen05 GEMM (ops.pwconv).
     Weight tiles are packed once per (conv, source split) and cached on the conv module."""
     cache = conv.__dict__.setdefault("el_wpk", {})
@@ -266,7 +266,8 @@ def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=Non
     wpk = cache.get(key)
     if wpk is None:
         wpk = cache[key] = ops.pack_pw_weight(conv.weight, key[0], key[1], M).to(key[2])
-    return ops.pwconv(srcs, wpk, conv.out_channels, bias=bias, act=act, residual=residual, out=out, out2=out2, res_scale=res_scale)
+    return ops.pwconv(srcs, wpk, conv.out_channels, bias=bias, act=act, residual=residual, out=out, out2=out2, res_scale=res_scale,
+                      up_addend=up_addend)
 
 
 def conv2d_pw_forward(self, x):
@@ -277,6 +278,26 @@ def conv2d_pw_forward(self, x):
             b = self.el_bias32 = self.bias.detach().float().contiguous()
         return pw_apply(self, [x], b, ops.ACT_NONE)
     return F.conv2d(x, self.weight, self.bias)
+
+
+class UpCat(tuple):
+    """(x_low, skip): lazy cat[nearest-2x(x_low), skip] handed from an engine-mode Concat to the cv1 of the following block."""
+
+
+def upcat_cv1(cv1, uc: UpCat, out, out2):
+    """cv1(cat[Upsample(x_low), skip]) for a fused 1x1 Conv: a 1x1 conv commutes with nearest upsampling, so the x_low part of the
+    weights is applied at LOW resolution (a quarter of the pixels) and its result enters the skip part's GEMM as a pre-activation
+    addend that the epilogue reads at (y/2, x/2).  Neither the upsampled nor the concatenated tensor exists."""
+    x_low, skip = uc
+    conv = cv1.conv
+    C1 = x_low.shape[1]
+    halves = conv.__dict__.get("el_up_halves")
+    if halves is None:
+        lo, sk = nn.Conv2d(C1, conv.out_channels, 1, bias=False), nn.Conv2d(skip.shape[1], conv.out_channels, 1, bias=False)
+        lo.weight, sk.weight = nn.Parameter(conv.weight[:, :C1].detach().clone(), False), nn.Parameter(conv.weight[:, C1:].detach().clone(), False)
+        halves = conv.el_up_halves = (lo, sk)
+    z = pw_apply(halves[0], [x_low], None, ops.ACT_NONE)
+    return pw_apply(halves[1], [skip], _bias_on(cv1, skip), cv1.el_act, out=out, out2=out2, up_addend=z)
 
 
 def _as_list(x):
@@ -336,12 +357,15 @@ def dsc3k2_wavelet_engine_forward(self, x):
     """DSC3K2_Wavelet.forward (block.py:3783-3788): cv1 writes its two halves a | b as dense tensors (chunk(2, 1) is the
     epilogue's split), the enhancer updates b in place, and cv2 reads a, b', m1(b'), ... in place: no concat buffer.
     `x` may be the list of a lazily concatenated input (Concat in engine mode)."""
-    x0 = _as_list(x)[0]
+    x0 = x[1] if isinstance(x, UpCat) else _as_list(x)[0]
     B, _, H, W = x0.shape
     c = self.c
     a = torch.empty((B, c, H, W), device=x0.device, dtype=x0.dtype, memory_format=torch.channels_last)
     b = torch.empty_like(a)
-    self.cv1(x, out=a, out2=b)
+    if isinstance(x, UpCat):
+        upcat_cv1(self.cv1, x, a, b)
+    else:
+        self.cv1(x, out=a, out2=b)
     cur = wavelet_enhancer_engine_forward(self.wave, b)
     ys = [a, cur]
     for blk in self.m:
@@ -391,6 +415,9 @@ def sppf_engine_forward(self, x):
 def concat_engine_forward(self, x):
     """Concat (conv.py Concat) whose first input is the low-resolution map of the preceding nn.Upsample."""
     if getattr(self, "el_upsample_first", False):
+        if getattr(self, "el_up_lazy", False) and x[0].dtype in (torch.bfloat16, torch.float16) and _pixel_linear(x[0]) and _pixel_linear(x[1]) \
+                and x[1].shape[2] % 2 == 0 and x[1].shape[3] % 2 == 0:
+            return UpCat((x[0], x[1]))  # consumed by the next block's cv1: the upsampled / concatenated tensor is never built
         return ops.upsample2x_cat(x[0], x[1])
     if getattr(self, "el_lazy", False):  # the only consumer is a block whose cv1 folds the concat into its K loop
         return list(x)

@@ -620,10 +620,12 @@ def pack_pw_weight(weight: torch.Tensor, src_c, dtype=torch.bfloat16, M: int = 1
 
 
 def pwconv(srcs, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, act: int = ACT_NONE, residual: torch.Tensor | None = None,
-           out: torch.Tensor | None = None, out2: torch.Tensor | None = None, res_scale: float = 1.0) -> torch.Tensor:
+           out: torch.Tensor | None = None, out2: torch.Tensor | None = None, res_scale: float = 1.0, up_addend: torch.Tensor | None = None) -> torch.Tensor:
     """1x1 conv over the channel-concatenation of `srcs` (NHWC 16-bit tensors or channel-slice views of the same B,H,W)
     + bias + activation (+ residual) in one tcgen05 GEMM kernel.  With `out2`, channels [0, out.shape[1]) go to `out`
-    and the rest to `out2`.  With `residual`, out = residual + res_scale * act(conv + bias) (`out` may be `residual` itself)."""
+    and the rest to `out2`.  With `residual`, out = residual + res_scale * act(conv + bias) (`out` may be `residual` itself).
+    With `up_addend` (B, N, H/2, W/2), out = act(conv + bias + nearest-2x-upsample(up_addend)): the 1x1 conv over
+    cat[Upsample(x_low), skip] with the x_low part of the weights applied at low resolution."""
     x0 = srcs[0]
     _need_cuda(*srcs, wpk)
     B, _, H, W = x0.shape
@@ -642,11 +644,18 @@ def pwconv(srcs, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, ac
     split = out.shape[1] if out2 is not None else 0
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise EdgelineError("pwconv: bias must be a contiguous fp32 vector of N elements")
+    up_H = up_W = 0
+    if up_addend is not None:
+        if residual is not None or H % 2 or W % 2 or tuple(up_addend.shape) != (B, N, H // 2, W // 2) or up_addend.dtype != x0.dtype \
+                or not up_addend.is_contiguous(memory_format=torch.channels_last):
+            raise EdgelineError("pwconv: up_addend must be a dense NHWC (B, N, H/2, W/2) tensor and excludes `residual`")
+        residual, up_H, up_W = up_addend, H, W
     n = len(srcs)
     check(_lib.lib().el_pwconv_fwd(n, _ptrs(srcs), _i64([pitch(t, "source") for t in srcs]), (c_int32 * n)(*[t.shape[1] for t in srcs]),
                                    wpk.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                   residual.data_ptr() if residual is not None else None, pitch(residual, "residual") if residual is not None else 0,
-                                   float(res_scale), out.data_ptr(), pitch(out, "out"), out2.data_ptr() if out2 is not None else None,
+                                   residual.data_ptr() if residual is not None else None,
+                                   (residual.stride(3) if up_H else pitch(residual, "residual")) if residual is not None else 0,
+                                   float(res_scale), up_H, up_W, out.data_ptr(), pitch(out, "out"), out2.data_ptr() if out2 is not None else None,
                                    pitch(out2, "out2") if out2 is not None else 0, split, M, N, int(act), _dt(x0), _stream()), "el_pwconv_fwd")
     return out
 

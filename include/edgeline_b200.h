@@ -213,6 +213,9 @@ int el_dwconv_fwd(const void* x, const int64_t xs[4], const float* w, const floa
  * tcgen05 GEMM over NHWC pixels (Conv(k=1).forward_fuse nn/modules/conv.py:58-60; DSConv.pw + bn + act conv.py:100-104;
  * LinearAttention.qkv / proj block.py:3353-3373).  out[p, n] = res_scale * act(sum_k X[p,k] W[n,k] + bias[n]) (+ res[p,n]);
  * res_scale = tanh(gamma) with res = b is the gated residual of _WaveletEnhancer (block.py:3708-3710), else 1.
+ * up_H > 0 switches `res` to a PRE-activation addend at half resolution: out[b,y,x] = act(conv + bias + res[b, y/2, x/2]) with
+ * (up_H, up_W) the output map size -- nn.Upsample(2, nearest) + Concat + 1x1 conv of the neck (yolo11-test.yaml:34-39) without
+ * ever materialising the upsampled / concatenated tensor: res = W[:, :C1] . x_low computed at low resolution.
  * The K dimension is the concatenation of `nsrc` (<= 4) source tensors (src[i]: 16-bit, src_c[i] channels, multiple
  * of 8, pixel pitch src_pitch[i] elements) -- the torch.cat of the C2f-style blocks (block.py:3783-3788) is never
  * materialised.  Channels >= split go to out2 when out2 != NULL (chunk(2,1) of cv1).  M = B*H*W pixels; every view
@@ -222,8 +225,8 @@ int el_dwconv_fwd(const void* x, const int64_t xs[4], const float* w, const floa
 int el_pwconv_tile(int N, int w_row_bytes, int64_t M);
 int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], const int32_t src_c[],
                   const void* wpk, const float* bias, const void* res, int64_t res_pitch, float res_scale,
-                  void* out, int64_t out_pitch, void* out2, int64_t out2_pitch, int split, int64_t M, int N,
-                  int act, int dtype, void* stream);
+                  int up_H, int up_W, void* out, int64_t out_pitch, void* out2, int64_t out2_pitch, int split,
+                  int64_t M, int N, int act, int dtype, void* stream);
 /* el_conv3x3_fwd: dense 3x3 convolution, padding 1, stride 1 or 2, + folded-BatchNorm bias + activation as an implicit GEMM on
  * the el_pwconv_fwd kernel (Conv(k=3).forward_fuse nn/modules/conv.py:58-60: the stride-2 downsampling convs of the yaml,
  * _WaveletEnhancer.f_h block.py:3657-3679, the Detect box tower head.py:59-63).  x (B,C,H,W) / out (B,N,Ho,Wo) NHWC views with

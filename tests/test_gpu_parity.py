@@ -602,6 +602,33 @@ def test_conv3x3(dtype, C, N, hw, stride, act):
     close(got, want, 2e-2, 2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C1,C2,N,hw,split", [(256, 128, 128, (20, 20), 64), (128, 128, 64, (16, 24), 32), (64, 32, 48, (6, 10), 0)])
+def test_pwconv_upsample_concat(dtype, C1, C2, N, hw, split):
+    """nn.Upsample(2, nearest) + Concat + 1x1 Conv + SiLU of the neck (yolo11-test.yaml:34-39, conv.py:58-60) as a low-resolution
+    GEMM whose result enters the skip GEMM's epilogue as a pre-activation addend == the reference composition, 16-bit contract."""
+    o = ops()
+    gen = torch.Generator().manual_seed(C1 + N)
+    B, (H, W) = 2, hw
+    cl = torch.channels_last
+    x_low = torch.randn(B, C1, H // 2, W // 2, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl)
+    skip = torch.randn(B, C2, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl)
+    w = (torch.randn(N, C1 + C2, generator=gen) * (C1 + C2) ** -0.5).to(DEV)
+    bias = torch.randn(N, generator=gen).to(DEV)
+    cat = torch.cat([torch.nn.functional.interpolate(x_low.float(), scale_factor=2, mode="nearest"), skip.float()], 1)
+    want = torch.nn.functional.silu(torch.einsum("bkhw,nk->bnhw", cat, w.to(dtype).float()) + bias.view(1, -1, 1, 1))
+    z = o.pwconv([x_low], o.pack_pw_weight(w[:, :C1], [C1], dtype, B * H * W // 4), N)
+    wsk = o.pack_pw_weight(w[:, C1:], [C2], dtype, B * H * W)
+    if split:
+        a = torch.empty(B, split, H, W, device=DEV, dtype=dtype).contiguous(memory_format=cl)
+        b = torch.empty(B, N - split, H, W, device=DEV, dtype=dtype).contiguous(memory_format=cl)
+        o.pwconv([skip], wsk, N, bias=bias, act=o.ACT_SILU, out=a, out2=b, up_addend=z)
+        got = torch.cat([a, b], 1)
+    else:
+        got = o.pwconv([skip], wsk, N, bias=bias, act=o.ACT_SILU, up_addend=z)
+    close(got, want, 2e-2, 2e-2)
+
+
 def test_predictor_matches_api_path():
     """Predictor (graph replay, uint8 ingest) returns exactly what model + non_max_suppression return."""
     from edge_yolo_b200.engine import Predictor, build_model
