@@ -154,7 +154,7 @@ def profile_kernels(pred, a, iters=10):
         "linear_attention": lambda out, qkv, heads: (qkv.numel() + out.numel()) * e(qkv),
         "gfl_decode": lambda out, boxes, clss, *r, **k: sum(t.numel() * e(t) for t in boxes + clss) + out.numel() * 4,
         "bias_act": lambda _o, x, bias, act=1, residual=None, **k: (2 + (residual is not None)) * x.numel() * e(x),
-        "pwconv": lambda _o, srcs, wpk, N, bias=None, act=0, residual=None, out=None, out2=None, res_scale=1.0, up_addend=None: (
+        "pwconv": lambda _o, srcs, wpk, N, bias=None, act=0, residual=None, up_addend=None, **k: (
             sum(t.numel() for t in srcs) + srcs[0].numel() // srcs[0].shape[1] * N * (1 + (residual is not None))
             + (up_addend.numel() if up_addend is not None else 0)) * e(srcs[0]),
         "dwconv": lambda _o, x, *r, **k: 2 * x.numel() * e(x),
