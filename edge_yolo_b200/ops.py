@@ -345,6 +345,7 @@ def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, mult
     ws = workspace if workspace is not None and workspace.numel() >= need.value else torch.empty(need.value, device=dev, dtype=torch.uint8)
     if stages != 7 and (workspace is None or ws is not workspace):
         raise EdgelineError("gfl_detect: staged execution needs a caller-owned workspace of el_gfl_detect_workspace_bytes")
+    caller_out, caller_cnt = out, cnt
     out = torch.empty((B, max_det, 6), device=dev, dtype=torch.float32) if out is None else out
     cnt = torch.empty((B,), device=dev, dtype=torch.int32) if cnt is None else cnt
     keep = None
@@ -367,10 +368,15 @@ def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, mult
             L.el_debug_set_detect_stages(7)
     if st == 2 and stages != 7:
         raise EdgelineError("gfl_detect: staged execution needs dense NHWC head maps")
-    if st == 2:  # EL_ERR_UNSUPPORTED: strided / NCHW maps -> two-call path with the same kernels downstream
+    if st == 2:  # EL_ERR_UNSUPPORTED: strided / NCHW / unaligned maps -> two-call path with the same kernels downstream
         y = gfl_decode(boxes, clss, dgqp, strides, bias=bias)
-        return nms_batched(y, conf_thres, iou_thres, multi_label=multi_label, agnostic=agnostic, classes=classes, max_det=max_det,
-                           max_nms=max_nms, max_wh=max_wh)
+        res = nms_batched(y, conf_thres, iou_thres, multi_label=multi_label, agnostic=agnostic, classes=classes, max_det=max_det,
+                          max_nms=max_nms, max_wh=max_wh)
+        if caller_out is not None:  # the engine's graphs read the results from its own buffers
+            caller_out.copy_(res[0])
+            caller_cnt.copy_(res[1])
+            return caller_out, caller_cnt
+        return res
     check(st, "el_gfl_detect_fwd")
     return out, cnt
 

@@ -665,6 +665,33 @@ def test_predictor_matches_api_path():
         assert d.shape == w.shape
 
 
+@pytest.mark.parametrize("scale,nc,batch,imgsz,kw", [
+    ("n", 80, 3, 352, {}),                                             # ragged 128-pixel tiles at every level, odd batch
+    ("n", 10, 1, 224, dict(conf=0.001, multi_label=True)),             # nc not a multiple of 8: the class towers' last conv falls back to cuDNN
+    ("s", 80, 2, 256, {}),                                             # wider channels: other tile / chunk shapes of the GEMM
+])
+def test_predictor_shapes(scale, nc, batch, imgsz, kw):
+    """The engine (two CUDA graphs, TMA/tcgen05 convs, fused neck and enhancer tails) returns bit-identical detections to the same model
+    run eagerly layer by layer + non_max_suppression, at image sizes / batch sizes / scales other than the benchmark's."""
+    from edge_yolo_b200.engine import Predictor, build_model
+    from edge_yolo_b200.nms import non_max_suppression
+
+    model = build_model(scale, nc, seed=1, device=DEV)
+    pred = Predictor(model, batch=batch, imgsz=imgsz, **kw)
+    host = torch.randint(0, 256, (batch, imgsz, imgsz, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(imgsz)).pin_memory()
+    dets = pred.predict(host)
+    dets2 = pred.predict(host)  # second step uses the other buffer set
+    for m in model.modules():
+        if hasattr(m, "el_detect"):
+            m.el_detect = None
+    with torch.no_grad():
+        y, _ = model(None, stem_out=ops().stem_conv_u8(host.to(DEV), *pred.stem))
+        want = non_max_suppression(y, conf_thres=kw.get("conf", 0.25), iou_thres=0.7, max_det=300, multi_label=kw.get("multi_label", False))
+    for d, d2, w in zip(dets, dets2, want):
+        assert d.shape == w.shape and d.numpy().tobytes() == w.cpu().numpy().tobytes()
+        assert d2.numpy().tobytes() == d.numpy().tobytes()
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("nc,sizes,kw", [
     (80, ((80, 80), (40, 40), (20, 20)), dict(conf_thres=0.25, iou_thres=0.7)),
