@@ -669,6 +669,7 @@ def test_predictor_matches_api_path():
     ("n", 80, 3, 352, {}),                                             # ragged 128-pixel tiles at every level, odd batch
     ("n", 10, 1, 224, dict(conf=0.001, multi_label=True)),             # nc not a multiple of 8: the class towers' last conv falls back to cuDNN
     ("s", 80, 2, 256, {}),                                             # wider channels: other tile / chunk shapes of the GEMM
+    ("l", 80, 1, 256, {}),                                             # dsc3k=True blocks (DSC3k, two repeats): four-source cv2, wide K
 ])
 def test_predictor_shapes(scale, nc, batch, imgsz, kw):
     """The engine (two CUDA graphs, TMA/tcgen05 convs, fused neck and enhancer tails) returns bit-identical detections to the same model
