@@ -504,18 +504,31 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     while (cols < 2u * A.n_tile) cols <<= 1;
     if (cols > 512) return EL_ERR_UNSUPPORTED;
     A.tmem_cols = cols;
-    const size_t fixed = 1024 /* alignment slack */ + ((A.w_bytes + 1023u) & ~1023u) + 2 * (size_t)pw::kTileM * ob * 2 +
-                         (((size_t)(A.n_tile + 64) * 4 + 127) & ~(size_t)127) + 40 + 16 * pw::kMaxStages + 16;
     // CTAs per SM: the most (<= 4, limited by TMEM columns) whose share of shared memory still holds a ring of >= 3 stages (one being
     // consumed, two in flight per CTA); with resident weights too large for that, whatever ring fits one CTA (>= 2 stages).
-    // Two or more co-resident CTAs are what overlaps one tile's epilogue with the other's loads and MMAs.
+    // Two or more co-resident CTAs are what overlaps one tile's epilogue with the other's loads and MMAs -- so when 64-channel
+    // store boxes (2 x 16 KB of staging) leave room for a single CTA only, 32-channel boxes are used if they make room for two
+    // with a ring that still covers a whole tile (measured: 128 -> 128 @ 80^2 51.7 -> 42.5 us).
+    size_t fixed = 0;
     int S = 0, per_sm = 1;
-    for (int ps = 4; ps >= 1; --ps) {
-        if (ps > (int)(512 / cols)) continue;
-        const size_t budget = (size_t)227 * 1024 / ps - 1024;
-        if (budget <= fixed) continue;
-        const int s_fit = (int)((budget - fixed) / A.stage_bytes);
-        if (s_fit >= 3 || (ps == 1 && s_fit >= 2)) { S = s_fit; per_sm = ps; break; }
+    auto plan = [&](int box) {
+        fixed = 1024 /* alignment slack */ + ((A.w_bytes + 1023u) & ~1023u) + 2 * (size_t)pw::kTileM * box * 2 +
+                (((size_t)(A.n_tile + 64) * 4 + 127) & ~(size_t)127) + 40 + 16 * pw::kMaxStages + 16;
+        S = 0; per_sm = 1;
+        for (int ps = 4; ps >= 1; --ps) {
+            if (ps > (int)(512 / cols)) continue;
+            const size_t budget = (size_t)227 * 1024 / ps - 1024;
+            if (budget <= fixed) continue;
+            const int s_fit = (int)((budget - fixed) / A.stage_bytes);
+            if (s_fit >= 3 || (ps == 1 && s_fit >= 2)) { S = s_fit; per_sm = ps; break; }
+        }
+    };
+    plan(ob);
+    if (per_sm == 1 && ob == 64) {
+        const size_t fixed0 = fixed; const int S0 = S;
+        plan(32);
+        if (per_sm >= 2 && S >= nch + 1 && S >= 3) { ob = 32; A.ob = 32; }
+        else { fixed = fixed0; S = S0; per_sm = 1; }
     }
     if (S < 2) return EL_ERR_UNSUPPORTED;
     if (S > pw::kMaxStages) S = pw::kMaxStages;
