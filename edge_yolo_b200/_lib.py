@@ -64,6 +64,7 @@ _SIGNATURES = {
     "el_pwconv_tile": (c_int, [c_int, c_int, c_int64]),
     "el_pwconv_fwd": (c_int, [c_int, POINTER(c_void_p), I64P, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_int, c_void_p, c_int64, c_void_p,
                               c_int64, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
+    "el_conv3x3_tile": (c_int, [c_int, c_int, c_int64]),
     "el_conv3x3_fwd": (c_int, [c_void_p, I64P, c_int, c_void_p, c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_sppf_pool_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_upsample2x_cat_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -57,6 +57,8 @@ struct Args {
     int N, n_tile, ob;       // ob: channels per staging / store box (16, 32 or 64)
     int act, stages;
     uint32_t w_bytes, stage_bytes, tmem_cols;
+    int stream_w;            // 1: weight tiles are not resident: each ring stage holds [A box | weight tile of the chunk] (wide K)
+    uint32_t a_stage_bytes;  // stream_w: offset of the weight tile inside a stage
     // 3x3 mode (el_conv3x3_fwd): a pixel tile is a tw x th patch of one image (tw * th = 128), src_map[0] / out_map are 4-D
     // (channel, x, y, image) maps, chunk.src is the filter tap and the box of tap (ky, kx) starts at (x0 * stride + kx - 1, y0 * stride + ky - 1)
     int spatial, tw, th, tiles_x, tiles_y, stride;
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = A.stages, n_tile = A.n_tile;
     // shared memory map: [weights][stage ring][2 staging tiles 128 x ob][bias][barriers]
-    const uint32_t off_ring = (A.w_bytes + 1023u) & ~1023u;
+    const uint32_t off_ring = A.stream_w ? 0u : ((A.w_bytes + 1023u) & ~1023u);
     const uint32_t off_stage = off_ring + (uint32_t)S * A.stage_bytes;
     const uint32_t staging_bytes = (uint32_t)kTileM * A.ob * 2;
     const uint32_t off_bias = off_stage + 2 * staging_bytes;
@@ -202,9 +204,11 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
         for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, 128); }
         for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_w, A.w_bytes);
-        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(A.wpk) + (size_t)nt * A.w_bytes;
-        for (uint32_t o = 0; o < A.w_bytes; o += 32768) bulk_g2s(sbase + o, wsrc + o, min(32768u, A.w_bytes - o), bar_w);
+        if (!A.stream_w) {
+            mbar_expect_tx(bar_w, A.w_bytes);
+            const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(A.wpk) + (size_t)nt * A.w_bytes;
+            for (uint32_t o = 0; o < A.w_bytes; o += 32768) bulk_g2s(sbase + o, wsrc + o, min(32768u, A.w_bytes - o), bar_w);
+        }
     }
     for (int i = tid; i < n_tile + 64; i += kThreads) s_bias[i] = (A.bias && n0 + i < A.N) ? __ldg(A.bias + n0 + i) : 0.f;
     if (warp == 0) {
@@ -236,7 +240,11 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                     if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)(use - 1) & 1);
                     const Chunk ck = A.chunk[c];
                     const uint32_t dst = sbase + off_ring + (uint32_t)s * A.stage_bytes;
-                    mbar_expect_tx(bar_full + 8 * s, (uint32_t)kTileM * ck.rb);
+                    const uint32_t wt_bytes = A.stream_w ? (uint32_t)n_tile * ck.rb : 0u;
+                    mbar_expect_tx(bar_full + 8 * s, (uint32_t)kTileM * ck.rb + wt_bytes);
+                    if (A.stream_w)  // this chunk's weight tile rides in the same stage (L2-resident after the first tile)
+                        bulk_g2s(dst + A.a_stage_bytes, reinterpret_cast<const unsigned char*>(A.wpk) + (size_t)nt * A.w_bytes + ck.w_off, wt_bytes,
+                                 bar_full + 8 * s);
                     if (A.spatial) tma_load_4d(dst, &A.src_map[0], ck.c0, x0 + ck.src % 3, y0 + ck.src / 3, img, bar_full + 8 * s);
                     else tma_load_2d(dst, &A.src_map[ck.src], ck.c0, m0, bar_full + 8 * s);
                 }
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
         // ------------------------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(kFmt, kTileM, n_tile);
-            mbar_wait(bar_w, 0);
+            if (!A.stream_w) mbar_wait(bar_w, 0);
             int it = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const int b = tl & 1, ub = tl >> 1;
@@ -258,7 +266,8 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                     mbar_wait(bar_full + 8 * s, (uint32_t)(it / S) & 1);
                     tc_fence_after();
                     const Chunk ck = A.chunk[c];
-                    const uint32_t a_base = sbase + off_ring + (uint32_t)s * A.stage_bytes, b_base = sbase + ck.w_off;
+                    const uint32_t a_base = sbase + off_ring + (uint32_t)s * A.stage_bytes;
+                    const uint32_t b_base = A.stream_w ? a_base + A.a_stage_bytes : sbase + ck.w_off;
                     for (int ks = 0; ks < ck.rb / 32; ++ks)  // one MMA per 16 channels = 32 bytes along K inside the swizzle atom
                         umma(d, umma_desc_sw(a_base + 32 * ks, ck.rb), umma_desc_sw(b_base + 32 * ks, ck.rb), idesc, (c > 0 || ks > 0) ? 1u : 0u);
                     umma_commit(bar_empty + 8 * s);
@@ -456,6 +465,20 @@ extern "C" int el_pwconv_tile(int N, int w_row_bytes, int64_t M) {
     return (int)ceil_div(ceil_div(n16, tiles), 16) * 16;
 }
 
+extern "C" int el_conv3x3_tile(int N, int C, int64_t M) {
+    // C <= 32: the nine weight tiles stay resident (el_pwconv_tile rule).  Wider inputs stream each chunk's weight tile through the
+    // ring next to its activation box, so N is only split by the UMMA limit (256) and, on small maps, to get ~2 CTAs per SM.
+    if (N <= 0 || C <= 0 || M <= 0) return 0;
+    const int rb = C <= 16 ? 32 : (C <= 32 ? 64 : 128);
+    const int chunks = 9 * (int)ceil_div(C, rb / 2);
+    if (C <= 32) return el_pwconv_tile(N, chunks * rb, M);
+    const int n16 = (int)ceil_div(N, 16) * 16;
+    int tiles = (int)ceil_div(n16, 256);
+    const int64_t m_tiles = ceil_div(M, pw::kTileM);
+    while (m_tiles * tiles < 2 * kSMs && ceil_div(n16, tiles + 1) >= 64) ++tiles;
+    return (int)ceil_div(ceil_div(n16, tiles), 16) * 16;
+}
+
 extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], const int32_t src_c[], const void* wpk, const float* bias,
                              const void* res, int64_t res_pitch, float res_scale, int up_H, int up_W, void* out, int64_t out_pitch, void* out2,
                              int64_t out2_pitch, int split, int64_t M, int N, int act, int dtype, void* stream) {
@@ -489,6 +512,7 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     }
     A.w_bytes = w_off;
     A.stage_bytes = (uint32_t)pw::kTileM * max_rb;
+    A.a_stage_bytes = A.stage_bytes;
     const int n_tiles = (int)ceil_div(N, A.n_tile);
     // store box: up to 64 channels; with two destinations it must not straddle the split
     int ob = 64;
@@ -587,15 +611,17 @@ extern "C" int el_conv3x3_fwd(const void* x, const int64_t xs_[4], int C, const 
     A.tiles_x = (int)ceil_div(Wo, A.tw); A.tiles_y = (int)ceil_div(Ho, A.th);
     A.n_tiles_m = (int64_t)B * A.tiles_x * A.tiles_y;
     const int64_t M = A.n_tiles_m * pw::kTileM;
-    A.n_tile = el_pwconv_tile(N, w_row_bytes, M);
+    A.n_tile = el_conv3x3_tile(N, C, M);
     if (A.n_tile <= 0) return EL_ERR_UNSUPPORTED;
+    A.stream_w = C > 32;
     uint32_t w_off = 0;
     for (int i = 0; i < nch; ++i) {
         A.chunk[i].w_off = w_off;
         w_off += ((uint32_t)A.n_tile * A.chunk[i].rb + 1023u) & ~1023u;
     }
     A.w_bytes = w_off;
-    A.stage_bytes = (uint32_t)pw::kTileM * rb;
+    A.a_stage_bytes = (uint32_t)pw::kTileM * rb;
+    A.stage_bytes = A.a_stage_bytes + (A.stream_w ? (((uint32_t)A.n_tile * rb + 1023u) & ~1023u) : 0u);
     const int n_tiles = (int)ceil_div(N, A.n_tile);
     int ob = 64;
     while (ob > 16 && ob / 2 >= A.n_tile) ob >>= 1;
@@ -609,7 +635,7 @@ extern "C" int el_conv3x3_fwd(const void* x, const int64_t xs_[4], int C, const 
     while (cols < 2u * A.n_tile) cols <<= 1;
     if (cols > 512) return EL_ERR_UNSUPPORTED;
     A.tmem_cols = cols;
-    const size_t fixed = 1024 + ((A.w_bytes + 1023u) & ~1023u) + 2 * (size_t)pw::kTileM * ob * 2 + (((size_t)(A.n_tile + 64) * 4 + 127) & ~(size_t)127) + 40 +
+    const size_t fixed = 1024 + (A.stream_w ? 0 : ((A.w_bytes + 1023u) & ~1023u)) + 2 * (size_t)pw::kTileM * ob * 2 + (((size_t)(A.n_tile + 64) * 4 + 127) & ~(size_t)127) + 40 +
                          16 * pw::kMaxStages + 16;
     int S = 0, per_sm = 1;
     for (int ps = 4; ps >= 1; --ps) {

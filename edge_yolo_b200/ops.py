@@ -594,7 +594,7 @@ def _pw_chunks(src_c):
     return chunks
 
 
-def pack_pw_weight(weight: torch.Tensor, src_c, dtype=torch.bfloat16, M: int = 1 << 30) -> torch.Tensor:
+def pack_pw_weight(weight: torch.Tensor, src_c, dtype=torch.bfloat16, M: int = 1 << 30, n_tile: int | None = None) -> torch.Tensor:
     """1x1 conv weight (N, K[,1,1]) with K = sum(src_c) -> the resident UMMA B operand of el_pwconv_fwd: per output-channel
     tile, one K-major tile [n_tile][box channels] per K chunk, stored with the 32/64/128-byte swizzle of its row width
     (16-byte chunk j of row r lands at chunk j ^ ((r * row_bytes >> 7) & (row_bytes / 16 - 1))), each tile padded to 1024 B.
@@ -604,7 +604,8 @@ def pack_pw_weight(weight: torch.Tensor, src_c, dtype=torch.bfloat16, M: int = 1
     if K != sum(src_c):
         raise EdgelineError("pack_pw_weight: weight K does not match the sources")
     chunks = _pw_chunks(src_c)
-    n_tile = _lib.lib().el_pwconv_tile(N, sum(2 * bw for _, _, bw in chunks), M)
+    if n_tile is None:
+        n_tile = _lib.lib().el_pwconv_tile(N, sum(2 * bw for _, _, bw in chunks), M)
     if n_tile <= 0:
         raise EdgelineError("pack_pw_weight: K too large for a resident weight tile")
     n_tiles = -(-N // n_tile)
@@ -667,11 +668,9 @@ def pwconv(srcs, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, ac
 
 
 def conv3x3_tiles(N: int, C: int, B: int, H: int, W: int, stride: int = 1):
-    """(n_tile, n_tiles) el_conv3x3_fwd would use: callers fall back to cuDNN when the weight block splits N too finely."""
-    rb = 32 if C <= 16 else (64 if C <= 32 else 128)
-    row_bytes = 9 * rb * -(-C // (rb // 2))
+    """(n_tile, n_tiles) el_conv3x3_fwd uses for this site."""
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
-    n_tile = _lib.lib().el_pwconv_tile(N, row_bytes, B * Ho * Wo)
+    n_tile = _lib.lib().el_conv3x3_tile(N, C, B * Ho * Wo)
     return n_tile, (-(-N // n_tile) if n_tile > 0 else 0)
 
 
@@ -681,7 +680,7 @@ def pack_conv3x3_weight(weight: torch.Tensor, dtype=torch.bfloat16, M: int = 1 <
     N, C, kh, kw = weight.shape
     if (kh, kw) != (3, 3):
         raise EdgelineError("pack_conv3x3_weight: need a (N, C, 3, 3) weight")
-    return pack_pw_weight(weight.detach().permute(0, 2, 3, 1).reshape(N, 9 * C), [C] * 9, dtype, M)
+    return pack_pw_weight(weight.detach().permute(0, 2, 3, 1).reshape(N, 9 * C), [C] * 9, dtype, M, n_tile=_lib.lib().el_conv3x3_tile(N, C, M))
 
 
 def conv3x3(x: torch.Tensor, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, act: int = ACT_NONE, stride: int = 1,

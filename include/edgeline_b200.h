@@ -231,7 +231,9 @@ int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], 
  * the el_pwconv_fwd kernel (Conv(k=3).forward_fuse nn/modules/conv.py:58-60: the stride-2 downsampling convs of the yaml,
  * _WaveletEnhancer.f_h block.py:3657-3679, the Detect box tower head.py:59-63).  x (B,C,H,W) / out (B,N,Ho,Wo) NHWC views with
  * element strides xs / os = {n,c,h,w}; wpk = ops.pack_pw_weight of the (N, 9*C) matrix in (ky, kx, c) order with nine
- * "sources" of C channels.  bf16 / fp16 only. */
+ * "sources" of C channels and n_tile = el_conv3x3_tile(N, C, B*Ho*Wo) (C <= 32: weight tiles resident in shared memory;
+ * wider: streamed through the ring with the activation boxes).  bf16 / fp16 only. */
+int el_conv3x3_tile(int N, int C, int64_t M);
 int el_conv3x3_fwd(const void* x, const int64_t xs[4], int C, const void* wpk, const float* bias, void* out,
                    const int64_t os[4], int B, int H, int W, int N, int stride, int act, int dtype, void* stream);
 /* el_sppf_pool_fwd: out (B,4C,H,W) = cat[x, m(x), m(m(x)), m(m(m(x)))], m = MaxPool2d(5,1,2): the pooling
