@@ -93,35 +93,44 @@ __global__ void __launch_bounds__(kDwMaxThreads) dwconv_tile_kernel(const T* __r
     const float4* sw4 = reinterpret_cast<const float4*>(s_w);
     const int row_stride = PWf << G.cvl_shift;  // uint4 units
     for (int ly0 = strip0 * kDwRT; ly0 < TH; ly0 += G.NS * kDwRT) {
-        float acc[kDwRT][V];
+        // accumulators, inputs and taps are kept as fp32 pairs of adjacent channels: one FFMA2 per pair
+        f32x2 acc2[kDwRT][V / 2];
 #pragma unroll
         for (int r = 0; r < kDwRT; ++r)
 #pragma unroll
-            for (int e = 0; e < V; ++e) acc[r][e] = bv[e];
+            for (int e = 0; e < V / 2; ++e) acc2[r][e] = pack_f32x2(bv[2 * e], bv[2 * e + 1]);
 #pragma unroll 1
         for (int kx = 0; kx < K; ++kx) {
             const uint4* scol = s_in + (size_t)ly0 * row_stride + ((xl + kx) << G.cvl_shift) + cvl;
-            float v[NIN][V];
+            f32x2 v2[NIN][V / 2];
 #pragma unroll
             for (int j = 0; j < NIN; ++j) {
                 // rows below the tile's last output row + halo are not staged: clamp (their products land in rows that are never stored)
                 const int rr = min(ly0 + j, rows_in - 1) - ly0;
-                unpack<T>(scol[(size_t)rr * row_stride], v[j]);
+                float f[V];
+                unpack<T>(scol[(size_t)rr * row_stride], f);
+#pragma unroll
+                for (int e = 0; e < V / 2; ++e) v2[j][e] = pack_f32x2(f[2 * e], f[2 * e + 1]);
             }
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
-                float wv[V];
+                f32x2 w2[V / 2];
 #pragma unroll
                 for (int h = 0; h < HV; ++h) {
                     const float4 w4 = sw4[((ky * K + kx) * HV + h) * CVL + cvl];
-                    wv[4 * h] = w4.x; wv[4 * h + 1] = w4.y; wv[4 * h + 2] = w4.z; wv[4 * h + 3] = w4.w;
+                    w2[2 * h] = pack_f32x2(w4.x, w4.y); w2[2 * h + 1] = pack_f32x2(w4.z, w4.w);
                 }
 #pragma unroll
                 for (int r = 0; r < kDwRT; ++r)
 #pragma unroll
-                    for (int e = 0; e < V; ++e) acc[r][e] = fmaf(v[r + ky][e], wv[e], acc[r][e]);
+                    for (int e = 0; e < V / 2; ++e) acc2[r][e] = fma_f32x2(v2[r + ky][e], w2[e], acc2[r][e]);
             }
         }
+        float acc[kDwRT][V];
+#pragma unroll
+        for (int r = 0; r < kDwRT; ++r)
+#pragma unroll
+            for (int e = 0; e < V / 2; ++e) unpack_f32x2(acc2[r][e], acc[r][2 * e], acc[r][2 * e + 1]);
         T* q = o + n * os.n + (int64_t)(ty0 + ly0) * os.h + (int64_t)ox * os.w + ch;
 #pragma unroll
         for (int r = 0; r < kDwRT; ++r) {

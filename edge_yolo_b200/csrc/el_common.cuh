@@ -97,6 +97,22 @@ template <> __device__ __forceinline__ uint4 pack<__half>(const float (&f)[8]) {
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// ---- packed fp32x2 FMA (Blackwell FFMA2): two IEEE fp32 FMAs per instruction on a 64-bit register pair.  The 3-register scalar
+// FFMA issues every second cycle per scheduler, so FMA-bound CUDA-core kernels (depthwise 7x7, decode MLP) double their
+// arithmetic rate by keeping adjacent channels as pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack_f32x2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma_f32x2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // ---- warp helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
