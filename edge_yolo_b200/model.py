@@ -181,11 +181,12 @@ class EdgeLineYOLO(nn.Module):
 
 def _dw_eligible(conv: nn.Conv2d, epilogue: bool = False) -> bool:
     """Depthwise, stride 1, 'same' padding, k in {3,5,7}: what el_dwconv_fwd implements.  Measured on B200 (tools/prof_conv.py):
-    it beats PyTorch's depthwise kernel for k = 7 and whenever the bias + activation epilogue rides along (DWConv); the bare
-    k = 3 depthwise of DSConv stays on PyTorch's kernel, which is on par."""
+    it beats PyTorch's depthwise kernel for k = 7 and whenever the bias + activation epilogue rides along (DWConv); for the bare
+    k = 3 depthwise of DSConv the two are on par in isolation (modules.DWCONV_K3 picks ours: it chains with the neighbouring
+    GEMMs through programmatic dependent launch)."""
     k = conv.kernel_size[0]
     C = conv.in_channels
-    if not M.USE_DWCONV or not (epilogue or k >= 5):
+    if not M.USE_DWCONV or not (epilogue or k >= 5 or M.DWCONV_K3):
         return False
     C8 = C // 8
     return (C % 8 == 0 and (C8 & (C8 - 1) == 0 or C % 64 == 0) and conv.groups == C == conv.out_channels and C > 1 and conv.kernel_size == (k, k) and k in (3, 5, 7) and conv.stride == (1, 1)

@@ -193,6 +193,7 @@ def gfl_head_forward(self, x):
 
 
 USE_DWCONV = True  # el_dwconv_fwd in the engine graph (model._dw_eligible picks the sites where it wins)
+DWCONV_K3 = True   # also the bare k = 3 depthwise of DSConv (on par with PyTorch in isolation; ours chains with PDL)
 
 
 def _bias_on(self, x):
