@@ -23,9 +23,19 @@ constexpr int kMaxLevels = 4;
 constexpr int kTile = 64;        // anchors per tile
 constexpr int kRegMax = 16;
 constexpr int kStat = 20;        // 4 sides x (top-4 + mean)
-constexpr int kStatLd = kStat + 1;
 constexpr int kHidden = 64;
-constexpr int kWFloats = kHidden * kStat + kHidden + kHidden + 4;  // w1 | b1 | w2 | b2 (+pad) per level = 1412
+// The DGQP hidden layer (64 anchors x 20 statistics -> 64 units per tile) has two implementations, selected by the activation type:
+//   fp32 maps   : CUDA-core FMAs in IEEE fp32 (1e-5 contract against the fp32 reference)
+//   16-bit maps : mma.sync m16n8k8 TF32 tensor-core tiles (K = 20 padded to 24), fp32 accumulation; the TF32 rounding of the statistics
+//                 and weights (2^-11) sits two octaves below the 2^-9 rounding the 16-bit box logits already carry.  The FMA version
+//                 was 1/3 of the fused kernel's issue slots (ncu: issue-bound at 4 warps per scheduler).
+// Per level the weights live in shared memory as  w1 | b1 | w2 | b2 (+pad):
+//   FMA: w1 row-major (64 x 20);  MMA: w1 as TF32 B fragments [n-tile 8][k-step 3][lane 32][2] (one 8-byte load per lane and MMA).
+template <bool MMA> struct WL {
+    static constexpr int w1n = MMA ? 8 * 3 * 32 * 2 : kHidden * kStat;
+    static constexpr int b1 = w1n, w2 = b1 + kHidden, b2 = w2 + kHidden, total = b2 + 4;  // multiple of 4 floats: 16 B aligned levels
+    static constexpr int stat_ld = MMA ? 28 : kStat + 1;  // 28 = 4 x odd: conflict-free A-fragment loads; 21: conflict-free row reads
+};
 
 struct DecodeLevel {
     const void* box; Strides4 bs;
@@ -49,42 +59,76 @@ template <bool FAST> __device__ __forceinline__ float sigmoidf_(float x) { retur
 
 // ---- shared arithmetic ------------------------------------------------------------------------
 // softmax over the 16 bins of one side: DFL integral, sorted top-4 probabilities and their mean
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 template <bool FAST>
 __device__ __forceinline__ void side_stats(float (&lg)[kRegMax], float& dist, float* __restrict__ stat5) {
     float m = lg[0];
 #pragma unroll
     for (int k = 1; k < kRegMax; ++k) m = fmaxf(m, lg[k]);
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < kRegMax; ++k) { lg[k] = exp_<FAST>(lg[k] - m); s += lg[k]; }
-    const float inv = rcp_<FAST>(s);
-    float d = 0.f, psum = 0.f;
     float t0 = -1.f, t1 = -1.f, t2 = -1.f, t3 = -1.f;  // running top-4, descending
+    if constexpr (FAST) {
+        // 16-bit maps: exp as one FFMA + MUFU.EX2 per bin; the integral, the top-4 and the mean are taken on the unnormalised
+        // exponentials and scaled once (same values up to fp32 rounding, ~45 fewer instructions per side)
+        constexpr float kLog2e = 1.4426950408889634f;
+        const float ml = m * kLog2e;
+        float s = 0.f, d = 0.f;
 #pragma unroll
-    for (int k = 0; k < kRegMax; ++k) {
-        float p = lg[k] * inv;
-        d += (float)k * p;
-        psum += p;
-        float v = p;
-        float n0 = fmaxf(t0, v); v = fminf(t0, v); t0 = n0;
-        float n1 = fmaxf(t1, v); v = fminf(t1, v); t1 = n1;
-        float n2 = fmaxf(t2, v); v = fminf(t2, v); t2 = n2;
-        t3 = fmaxf(t3, v);
+        for (int k = 0; k < kRegMax; ++k) {
+            const float e = ex2_approx(fmaf(lg[k], kLog2e, -ml));
+            s += e;
+            d = fmaf((float)k, e, d);
+            float v = e;
+            float n0 = fmaxf(t0, v); v = fminf(t0, v); t0 = n0;
+            float n1 = fmaxf(t1, v); v = fminf(t1, v); t1 = n1;
+            float n2 = fmaxf(t2, v); v = fminf(t2, v); t2 = n2;
+            t3 = fmaxf(t3, v);
+        }
+        const float inv = __frcp_rn(s);
+        dist = d * inv;
+        stat5[0] = to_tf32(t0 * inv); stat5[1] = to_tf32(t1 * inv); stat5[2] = to_tf32(t2 * inv); stat5[3] = to_tf32(t3 * inv);
+        stat5[4] = to_tf32((s * inv) * (1.f / kRegMax));
+    } else {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRegMax; ++k) { lg[k] = exp_<FAST>(lg[k] - m); s += lg[k]; }
+        const float inv = rcp_<FAST>(s);
+        float d = 0.f, psum = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRegMax; ++k) {
+            float p = lg[k] * inv;
+            d += (float)k * p;
+            psum += p;
+            float v = p;
+            float n0 = fmaxf(t0, v); v = fminf(t0, v); t0 = n0;
+            float n1 = fmaxf(t1, v); v = fminf(t1, v); t1 = n1;
+            float n2 = fmaxf(t2, v); v = fminf(t2, v); t2 = n2;
+            t3 = fmaxf(t3, v);
+        }
+        dist = d;
+        stat5[0] = t0; stat5[1] = t1; stat5[2] = t2; stat5[3] = t3;
+        stat5[4] = psum * (1.f / kRegMax);  // prob.mean(dim=2): == 1/16, carries no information but is reproduced
     }
-    dist = d;
-    stat5[0] = t0; stat5[1] = t1; stat5[2] = t2; stat5[3] = t3;
-    stat5[4] = psum * (1.f / kRegMax);  // prob.mean(dim=2): == 1/16, carries no information but is reproduced
 }
 
-// DGQP hidden layer for one 64-anchor tile with 256 threads: thread = (anchor pair ap, ap+32 ; 8 hidden units).
-// w = [w1 (64x20) | b1 (64) | w2 (64) | b2] in shared memory; partial z sums go to s_part[8][kTile].
-__device__ __forceinline__ void dgqp_hidden(const float* __restrict__ w, const float (*s_stat)[kStatLd], float (*s_part)[kTile]) {
+// DGQP hidden layer for one 64-anchor tile with 256 threads, FMA version: thread = (anchor pair ap, ap+32 ; 8 hidden units).
+// partial z sums go to s_part[8][kTile].
+__device__ __forceinline__ void dgqp_hidden_fma(const float* __restrict__ w, const float* __restrict__ s_stat, float (*s_part)[kTile]) {
+    constexpr int LD = WL<false>::stat_ld;
     const int ap = threadIdx.x & 31, hg = threadIdx.x >> 5;
     float st0[kStat], st1[kStat];
 #pragma unroll
-    for (int c = 0; c < kStat; ++c) { st0[c] = s_stat[ap][c]; st1[c] = s_stat[ap + 32][c]; }
-    const float* b1 = w + kHidden * kStat;
-    const float* w2 = b1 + kHidden;
+    for (int c = 0; c < kStat; ++c) { st0[c] = s_stat[ap * LD + c]; st1[c] = s_stat[(ap + 32) * LD + c]; }
+    const float* b1 = w + WL<false>::b1;
+    const float* w2 = w + WL<false>::w2;
     float z0 = 0.f, z1 = 0.f;
 #pragma unroll 2
     for (int o = hg * 8; o < hg * 8 + 8; ++o) {
@@ -106,10 +150,60 @@ __device__ __forceinline__ void dgqp_hidden(const float* __restrict__ w, const f
     s_part[hg][ap + 32] = z1;
 }
 
+// D (16x8, fp32) += A (16x8, tf32, row) * B (8x8, tf32, col)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Tensor-core version: warp = (16-anchor m-tile mt, half nh of the hidden units = 4 n-tiles of 8); 12 MMAs per warp.
+// Fragment coordinates (g = lane / 4, t = lane % 4): A a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4); B b0 (k = t, n = g) b1 (k = t+4, n = g);
+// D d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1).  Epilogue in registers: z += w2[o] * relu(h[o] + b1[o]), reduced over the
+// four lanes of a group; the two halves meet in s_part[0..1][anchor].
+__device__ __forceinline__ void dgqp_hidden_mma(const float* __restrict__ w, const float* __restrict__ s_stat, float (*s_part)[kTile]) {
+    constexpr int LD = WL<true>::stat_ld;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3, mt = warp & 3, nh = warp >> 2;
+    const uint32_t* S = reinterpret_cast<const uint32_t*>(s_stat) + (16 * mt + g) * LD + t;
+    uint32_t a[3][4];
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+        a[ks][0] = S[8 * ks]; a[ks][1] = S[8 * LD + 8 * ks]; a[ks][2] = S[8 * ks + 4]; a[ks][3] = S[8 * LD + 8 * ks + 4];
+    }
+    const uint2* Wf = reinterpret_cast<const uint2*>(w) + lane;
+    const float2* b1 = reinterpret_cast<const float2*>(w + WL<true>::b1);
+    const float2* w2 = reinterpret_cast<const float2*>(w + WL<true>::w2);
+    float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int nt = 4 * nh + j;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            const uint2 b = Wf[(nt * 3 + ks) * 32];
+            mma_tf32(d, a[ks], b.x, b.y);
+        }
+        const float2 bb = b1[4 * nt + t], ww = w2[4 * nt + t];  // hidden units 8 nt + 2 t, + 1
+        z0 = fmaf(ww.x, fmaxf(d[0] + bb.x, 0.f), z0); z0 = fmaf(ww.y, fmaxf(d[1] + bb.y, 0.f), z0);
+        z1 = fmaf(ww.x, fmaxf(d[2] + bb.x, 0.f), z1); z1 = fmaf(ww.y, fmaxf(d[3] + bb.y, 0.f), z1);
+    }
+    z0 += __shfl_xor_sync(0xffffffffu, z0, 1); z0 += __shfl_xor_sync(0xffffffffu, z0, 2);
+    z1 += __shfl_xor_sync(0xffffffffu, z1, 1); z1 += __shfl_xor_sync(0xffffffffu, z1, 2);
+    if (t == 0) { s_part[nh][16 * mt + g] = z0; s_part[nh][16 * mt + g + 8] = z1; }
+}
+
+template <bool MMA>
+__device__ __forceinline__ void dgqp_hidden(const float* __restrict__ w, const float* __restrict__ s_stat, float (*s_part)[kTile]) {
+    if constexpr (MMA) dgqp_hidden_mma(w, s_stat, s_part);
+    else dgqp_hidden_fma(w, s_stat, s_part);
+}
+
 template <bool FAST>
 __device__ __forceinline__ float dgqp_quality(const float* __restrict__ w, const float (*s_part)[kTile], int a) {
-    float z = w[kHidden * kStat + 2 * kHidden];  // b2
-    z += ((s_part[0][a] + s_part[1][a]) + (s_part[2][a] + s_part[3][a])) + ((s_part[4][a] + s_part[5][a]) + (s_part[6][a] + s_part[7][a]));
+    float z = w[WL<FAST>::b2];
+    if constexpr (FAST) z += s_part[0][a] + s_part[1][a];
+    else z += ((s_part[0][a] + s_part[1][a]) + (s_part[2][a] + s_part[3][a])) + ((s_part[4][a] + s_part[5][a]) + (s_part[6][a] + s_part[7][a]));
     const float q = sigmoidf_<FAST>(z);
     return fminf(fmaxf(q, 1e-6f), 1.f - 1e-6f);  // clamp(1e-6, 1 - 1e-6), head.py:343
 }
@@ -121,21 +215,32 @@ __device__ __forceinline__ float4 decode_box(int px, int py, float l, float t, f
     return make_float4(((x1 + x2) / 2.f) * stride, ((y1 + y2) / 2.f) * stride, (x2 - x1) * stride, (y2 - y1) * stride);
 }
 
+template <bool MMA>
 __device__ __forceinline__ void load_level_weights(float* __restrict__ dst, const DecodeLevel& L) {
-    for (int i = threadIdx.x; i < kHidden * kStat; i += blockDim.x) dst[i] = __ldg(L.w1 + i);
-    if (threadIdx.x < kHidden) {
-        dst[kHidden * kStat + threadIdx.x] = __ldg(L.b1 + threadIdx.x);
-        dst[kHidden * kStat + kHidden + threadIdx.x] = __ldg(L.w2 + threadIdx.x);
+    if constexpr (MMA) {
+        for (int i = threadIdx.x; i < WL<true>::w1n; i += blockDim.x) {  // i = ((nt * 3 + ks) * 32 + lane) * 2 + j
+            const int j = i & 1, lane = (i >> 1) & 31, f = i >> 6, nt = f / 3, ks = f - 3 * nt;
+            const int k = 8 * ks + (lane & 3) + 4 * j, n = 8 * nt + (lane >> 2);
+            dst[i] = k < kStat ? to_tf32(__ldg(L.w1 + n * kStat + k)) : 0.f;
+        }
+    } else {
+        for (int i = threadIdx.x; i < kHidden * kStat; i += blockDim.x) dst[i] = __ldg(L.w1 + i);
     }
-    if (threadIdx.x == 0) dst[kHidden * kStat + 2 * kHidden] = __ldg(L.b2);
+    if (threadIdx.x < kHidden) {
+        dst[WL<MMA>::b1 + threadIdx.x] = __ldg(L.b1 + threadIdx.x);
+        dst[WL<MMA>::w2 + threadIdx.x] = __ldg(L.w2 + threadIdx.x);
+    }
+    if (threadIdx.x == 0) dst[WL<MMA>::b2] = __ldg(L.b2);
 }
 
 // ---------------------------------------------------------------------------------- dense kernel
 template <typename T, bool BOX_CH_FAST, bool CLS_STAGE>
 __global__ void __launch_bounds__(256) gfl_decode_kernel(const __grid_constant__ DecodeParams P, float* __restrict__ y, float* __restrict__ q_out) {
+    constexpr bool kFast = sizeof(T) == 2;  // 16-bit maps: SFU transcendentals + tensor-core DGQP layer
+    constexpr int LD = WL<kFast>::stat_ld;
     extern __shared__ float s_cls[];  // [kTile][nc+1] when CLS_STAGE
-    __shared__ __align__(16) float s_w[kWFloats];
-    __shared__ float s_stat[kTile][kStatLd];
+    __shared__ __align__(16) float s_w[WL<kFast>::total];
+    __shared__ __align__(16) float s_stat[kTile * LD];
     __shared__ float s_dist[4][kTile];
     __shared__ float s_part[8][kTile];
     __shared__ float s_q[kTile];
@@ -149,7 +254,7 @@ __global__ void __launch_bounds__(256) gfl_decode_kernel(const __grid_constant__
     const int HW = L.H * L.W;
     const int pix0 = ((int)blockIdx.x - L.tile_off) * kTile;
     const int nc = P.nc;
-    load_level_weights(s_w, L);
+    load_level_weights<kFast>(s_w, L);
 
     {   // phase 1: one thread per (anchor, side)
         const int side = tid & 3, a = tid >> 2;
@@ -178,8 +283,9 @@ __global__ void __launch_bounds__(256) gfl_decode_kernel(const __grid_constant__
             for (int k = 0; k < kRegMax; ++k) lg[k] = 0.f;
         }
         float dist;
-        side_stats<sizeof(T) == 2>(lg, dist, &s_stat[a][side * 5]);
+        side_stats<kFast>(lg, dist, &s_stat[a * LD + side * 5]);
         s_dist[side][a] = dist;
+        if (kFast && side == 0) *reinterpret_cast<float4*>(&s_stat[a * LD + kStat]) = make_float4(0.f, 0.f, 0.f, 0.f);  // K padding 20 -> 24
     }
     if (CLS_STAGE) {  // channel-contiguous class maps: coalesced read now, transposed use in phase 3
         const int n_el = kTile * nc;
@@ -195,11 +301,11 @@ __global__ void __launch_bounds__(256) gfl_decode_kernel(const __grid_constant__
         }
     }
     __syncthreads();
-    dgqp_hidden(s_w, s_stat, s_part);
+    dgqp_hidden<kFast>(s_w, s_stat, s_part);
     __syncthreads();
     if (tid < kTile) {
         const int a = tid, pix = pix0 + a;
-        const float q = dgqp_quality<sizeof(T) == 2>(s_w, s_part, a);
+        const float q = dgqp_quality<kFast>(s_w, s_part, a);
         s_q[a] = q;
         if (pix < HW) {
             const int py = pix / L.W, px = pix - py * L.W;
@@ -280,32 +386,66 @@ __device__ __forceinline__ TileInfo tile_info(const DecodeParams& P, int t) {
     return ti;
 }
 
-constexpr int kWStride = ((kWFloats * 4 + 15) & ~15) / 4;
 constexpr int kStageCap = 1024;  // staged candidate keys per tile (8 KiB per stage); the rare overflow goes straight to global memory
+
+// shared-memory map of the fused kernel (byte offsets), one definition for the host (size) and the device (carve-up)
+struct EmitLayout {
+    uint32_t box[2], cls[2], w, stat, dist, part, bias, bar, stage[2], ctl, total;
+    int bias_ld, w_stride;
+};
+template <bool MMA>
+__host__ __device__ inline EmitLayout emit_layout(int nc, uint32_t esz, int nl) {
+    EmitLayout L;
+    const uint32_t box_bytes = kTile * 4 * kRegMax * esz;
+    const uint32_t cls_bytes = (uint32_t)((kTile * nc * esz + 127) & ~127u);
+    uint32_t cur = 0;
+    L.box[0] = cur; cur += box_bytes; L.box[1] = cur; cur += box_bytes;
+    L.cls[0] = cur; cur += cls_bytes; L.cls[1] = cur; cur += cls_bytes;
+    L.w_stride = WL<MMA>::total;
+    L.w = cur; cur += (uint32_t)nl * L.w_stride * 4;
+    L.stat = cur; cur += kTile * WL<MMA>::stat_ld * 4;
+    L.dist = cur; cur += 4 * kTile * 4;
+    L.part = cur; cur += 8 * kTile * 4;
+    L.bias_ld = (4 * kRegMax + nc + 3) & ~3;
+    L.bias = cur; cur += (uint32_t)nl * L.bias_ld * 4;  // per level: box bias (64) | class bias (nc)
+    L.bar = cur; cur += 16;
+    L.stage[0] = cur; cur += kStageCap * 8; L.stage[1] = cur; cur += kStageCap * 8;
+    L.ctl = cur; cur += 64;
+    L.total = cur;
+    return L;
+}
+
+template <typename T> __device__ __forceinline__ void unpack2(uint32_t w, float& lo, float& hi);
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t w, float& lo, float& hi) {
+    lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack2<__half>(uint32_t w, float& lo, float& hi) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = t.x; hi = t.y;
+}
+template <> __device__ __forceinline__ void unpack2<float>(uint32_t w, float& lo, float& hi) { lo = hi = __uint_as_float(w); }  // never used
 
 template <typename T, bool MULTI>
 __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_constant__ DecodeParams P, const __grid_constant__ EmitArgs E) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool kFast = sizeof(T) == 2;
+    constexpr int LD = WL<kFast>::stat_ld;
     const int nc = P.nc, tid = threadIdx.x, lane = tid & 31;
-    const uint32_t box_bytes = kTile * 4 * kRegMax * sizeof(T);
-    const uint32_t cls_bytes = (uint32_t)((kTile * nc * sizeof(T) + 127) & ~127u);
-    T* s_box[2]; T* s_clsT[2];
-    unsigned char* cur = smem_raw;
-    s_box[0] = (T*)cur; cur += box_bytes; s_box[1] = (T*)cur; cur += box_bytes;
-    s_clsT[0] = (T*)cur; cur += cls_bytes; s_clsT[1] = (T*)cur; cur += cls_bytes;
-    float* s_w = (float*)cur; cur += kMaxLevels * kWStride * 4;
-    float (*s_stat)[kStatLd] = (float (*)[kStatLd])cur; cur += kTile * kStatLd * 4;
-    float (*s_dist)[kTile] = (float (*)[kTile])cur; cur += 4 * kTile * 4;
-    float (*s_part)[kTile] = (float (*)[kTile])cur; cur += 8 * kTile * 4;
-    float* s_q = (float*)cur; cur += kTile * 4;
-    const int bias_ld = (4 * kRegMax + nc + 3) & ~3;
-    float* s_bias = (float*)cur; cur += kMaxLevels * bias_ld * 4;  // per level: box bias (64) | class bias (nc)
-    uint64_t* bar = (uint64_t*)cur; cur += 16;
+    const EmitLayout ML = emit_layout<kFast>(nc, sizeof(T), P.nl);
+    // stage-indexed buffers as arithmetic on the stage bit (pointer arrays indexed at run time would live in local memory)
+    auto s_box = [&](int st) { return (T*)(smem_raw + ML.box[0] + st * (ML.box[1] - ML.box[0])); };
+    auto s_clsT = [&](int st) { return (T*)(smem_raw + ML.cls[0] + st * (ML.cls[1] - ML.cls[0])); };
+    float* s_w = (float*)(smem_raw + ML.w);
+    float* s_stat = (float*)(smem_raw + ML.stat);
+    float (*s_dist)[kTile] = (float (*)[kTile])(smem_raw + ML.dist);
+    float (*s_part)[kTile] = (float (*)[kTile])(smem_raw + ML.part);
+    float* s_bias = (float*)(smem_raw + ML.bias);
+    const int bias_ld = ML.bias_ld;
+    uint64_t* bar = (uint64_t*)(smem_raw + ML.bar);
     // candidate keys are staged per tile in shared memory and flushed to the image's key list one tile later, so the global
     // atomic that reserves the slots (one per tile instead of one per warp) has a whole tile of work to hide behind
-    unsigned long long* s_stage[2];
-    s_stage[0] = (unsigned long long*)cur; cur += kStageCap * 8; s_stage[1] = (unsigned long long*)cur; cur += kStageCap * 8;
-    int* s_scnt = (int*)cur;      // [2] staged count (may overshoot the capacity)
+    auto s_stage = [&](int st) { return (unsigned long long*)(smem_raw + ML.stage[0] + st * (kStageCap * 8)); };
+    int* s_scnt = (int*)(smem_raw + ML.ctl);  // [2] staged count (may overshoot the capacity)
     int* s_slimit = s_scnt + 2;   // [2] first position that did not fit (INT_MAX if none)
     int* s_fcnt = s_scnt + 4;     // [2] number of staged keys to flush
     int* s_fbase = s_scnt + 6;    // [2] reserved base slot in the image's key list
@@ -313,10 +453,11 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
     if (tid < 2) { s_scnt[tid] = 0; s_slimit[tid] = INT_MAX; s_fcnt[tid] = 0; }
 
     for (int l = 0; l < P.nl; ++l) {
-        load_level_weights(s_w + l * kWStride, P.lv[l]);
+        load_level_weights<kFast>(s_w + l * ML.w_stride, P.lv[l]);
         for (int i = tid; i < 4 * kRegMax + nc; i += 256)
             s_bias[l * bias_ld + i] = i < 4 * kRegMax ? (P.lv[l].bb ? __ldg(P.lv[l].bb + i) : 0.f) : (P.lv[l].cb ? __ldg(P.lv[l].cb + i - 4 * kRegMax) : 0.f);
     }
+    if (kFast && tid < kTile) *reinterpret_cast<float4*>(&s_stat[tid * LD + kStat]) = make_float4(0.f, 0.f, 0.f, 0.f);  // K padding 20 -> 24, written once
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -332,8 +473,8 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
         const T* gb = reinterpret_cast<const T*>(L.box) + (int64_t)ti.b * L.bs.n + (int64_t)ti.pix0 * (4 * kRegMax);
         const T* gc = reinterpret_cast<const T*>(L.cls) + (int64_t)ti.b * L.cs.n + (int64_t)ti.pix0 * nc;
         mbar_expect_tx(&bar[stage], nb + ncb);
-        bulk_g2s(s_box[stage], gb, nb, &bar[stage]);
-        bulk_g2s(s_clsT[stage], gc, ncb, &bar[stage]);
+        bulk_g2s(s_box(stage), gb, nb, &bar[stage]);
+        bulk_g2s(s_clsT(stage), gc, ncb, &bar[stage]);
     };
     if (tid == 0) {
         if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
@@ -352,7 +493,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
         if (lane == 0) pos = atomicAdd(&s_scnt[stage], nn);
         pos = __shfl_sync(0xffffffffu, pos, 0);
         if (pos + nn <= kStageCap) {
-            if (pass) s_stage[stage][pos + rank] = key;
+            if (pass) s_stage(stage)[pos + rank] = key;
         } else {
             int gb = 0;
             if (lane == 0) { atomicMin(&s_slimit[stage], pos); gb = atomicAdd(E.counts + img, nn); }
@@ -364,7 +505,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
         const int stage = it & 1;
         const TileInfo ti = tile_info(P, t);
         const DecodeLevel& L = P.lv[ti.l];
-        const float* w = s_w + ti.l * kWStride;
+        const float* w = s_w + ti.l * ML.w_stride;
         const float* bias_b = s_bias + ti.l * bias_ld;
         const float* bias_c = bias_b + 4 * kRegMax;
         mbar_wait(&bar[stage], (it >> 1) & 1);
@@ -372,7 +513,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
         {   // phase 1: thread = (anchor a, side): 16 logits from the staged tile
             const int side = tid & 3, a = tid >> 2;
             float lg[kRegMax];
-            const T* pv = s_box[stage] + a * (4 * kRegMax) + side * kRegMax;
+            const T* pv = s_box(stage) + a * (4 * kRegMax) + side * kRegMax;
             if constexpr (sizeof(T) == 2) {
                 const int h = (lane >> 2) & 1;  // alternate the half read first: conflict-free 16 B shared loads
                 float f0[8], f1[8];
@@ -389,35 +530,39 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                     for (int k = 0; k < 4; ++k) lg[4 * v + k] = f[k];
                 }
             }
+            // rows past nvalid hold a previous tile's (finite) logits: their results are never stored and MMA rows are independent
+            const float4* bb4 = reinterpret_cast<const float4*>(bias_b + side * kRegMax);
 #pragma unroll
-            for (int k = 0; k < kRegMax; ++k) lg[k] = a < ti.nvalid ? lg[k] + bias_b[side * kRegMax + k] : 0.f;
+            for (int v = 0; v < 4; ++v) {
+                const float4 bv = bb4[v];
+                lg[4 * v] += bv.x; lg[4 * v + 1] += bv.y; lg[4 * v + 2] += bv.z; lg[4 * v + 3] += bv.w;
+            }
+            if (a >= ti.nvalid) {
+#pragma unroll
+                for (int k = 0; k < kRegMax; ++k) lg[k] = 0.f;
+            }
             float dist;
-            side_stats<sizeof(T) == 2>(lg, dist, &s_stat[a][side * 5]);
+            side_stats<kFast>(lg, dist, &s_stat[a * LD + side * 5]);
             s_dist[side][a] = dist;
         }
         __syncthreads();
         if (tid == 0 && it > 0) s_fbase[stage ^ 1] = pending_base;  // the previous tile's atomic has had a whole phase to return
-        dgqp_hidden(w, s_stat, s_part);
+        dgqp_hidden<kFast>(w, s_stat, s_part);
         __syncthreads();
-        if (tid < kTile) {
-            const int a = tid;
-            s_q[a] = dgqp_quality<sizeof(T) == 2>(w, s_part, a);
-            if (a < ti.nvalid) {
-                const int pix = ti.pix0 + a, py = pix / L.W, px = pix - py * L.W;
-                E.boxes[(int64_t)ti.b * P.A + L.a_off + pix] = decode_box(px, py, s_dist[0][a], s_dist[1][a], s_dist[2][a], s_dist[3][a], L.stride);
-            }
-        }
         if (it > 0) {  // flush the previous tile's staged keys (coalesced 8-byte stores)
             const int ps = stage ^ 1, fc = s_fcnt[ps];
             unsigned long long* dst = E.keys + (int64_t)s_fimg[ps] * E.key_stride + s_fbase[ps];
-            for (int i = tid; i < fc; i += 256) dst[i] = s_stage[ps][i];
+            for (int i = tid; i < fc; i += 256) dst[i] = s_stage(ps)[i];
         }
-        __syncthreads();
         {   // phase 3: thread = (anchor a, quarter qd of the classes); scores never leave the SM unless they are candidates
             const int a = tid >> 2, qd = tid & 3;
             const bool av = a < ti.nvalid;
-            const float q = s_q[a];
-            const T* pc = s_clsT[stage] + a * nc;
+            const float q = dgqp_quality<kFast>(w, s_part, a);  // 4 lanes per anchor evaluate it redundantly: no extra barrier
+            if (av && qd == 0) {
+                const int pix = ti.pix0 + a, py = pix / L.W, px = pix - py * L.W;
+                E.boxes[(int64_t)ti.b * P.A + L.a_off + pix] = decode_box(px, py, s_dist[0][a], s_dist[1][a], s_dist[2][a], s_dist[3][a], L.stride);
+            }
+            const T* pc = s_clsT(stage) + a * nc;
             const uint32_t anchor = (uint32_t)(L.a_off + ti.pix0 + a);
             if (MULTI) {
                 for (int j = 0; j < cq; ++j) {
@@ -425,7 +570,7 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
                     float sc = 0.f;
                     bool pass = false;
                     if (av && c < nc) {
-                        sc = sigmoidf_<sizeof(T) == 2>(to_f(pc[c]) + bias_c[c]) * q;
+                        sc = sigmoidf_<kFast>(to_f(pc[c]) + bias_c[c]) * q;
                         pass = sc > E.conf && (!E.class_keep || E.class_keep[c]);
                     }
                     const uint32_t idx = anchor * (uint32_t)nc + (uint32_t)c;
@@ -434,10 +579,44 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
             } else {
                 float best = -INFINITY;
                 int bc = 0;
-                if (av) {
+                if (kFast && nc == 80) {
+                    // COCO-sized head, 16-bit maps: sigma(x) * q is monotone in the logit, so the class maximum is found on the logits
+                    // (one max per class instead of a sigmoid) and only logits within 1/64 of the maximum are scored -- the window keeps the
+                    // result identical to scoring every class even if the SFU exp is not monotone to the last ulp (a 1/64 step moves the
+                    // score by >= 87 ulp for logits <= 8; above 8 every class is scored).  Anchors whose best possible score is clearly
+                    // below conf skip the scoring altogether.
+                    constexpr int CQ = 20;
+                    float xs[CQ];
+                    const uint2* pcv = reinterpret_cast<const uint2*>(pc + qd * CQ);       // (160 a + 40 qd) bytes: 8 B aligned
+                    const float4* bv4 = reinterpret_cast<const float4*>(bias_c + qd * CQ);  // 16 B aligned
+#pragma unroll
+                    for (int v = 0; v < CQ / 4; ++v) {
+                        const uint2 r = pcv[v];
+                        const float4 bb = bv4[v];
+                        unpack2<T>(r.x, xs[4 * v], xs[4 * v + 1]);
+                        unpack2<T>(r.y, xs[4 * v + 2], xs[4 * v + 3]);
+                        xs[4 * v] += bb.x; xs[4 * v + 1] += bb.y; xs[4 * v + 2] += bb.z; xs[4 * v + 3] += bb.w;
+                    }
+                    float mx = xs[0];
+#pragma unroll
+                    for (int j = 1; j < CQ; ++j) mx = fmaxf(mx, xs[j]);
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    const float bound = sigmoidf_<kFast>(mx) * q;
+                    if (av && bound * 1.0001f > E.conf) {
+                        const float thr = mx > 8.f ? -INFINITY : mx - 0.015625f;
+#pragma unroll
+                        for (int j = 0; j < CQ; ++j) {
+                            if (xs[j] >= thr) {
+                                const float sc = sigmoidf_<kFast>(xs[j]) * q;
+                                if (sc > best) { best = sc; bc = qd * CQ + j; }
+                            }
+                        }
+                    }
+                } else if (av) {
                     const int c1 = min(nc, (qd + 1) * cq);
                     for (int c = qd * cq; c < c1; ++c) {  // first maximum inside the quarter
-                        const float sc = sigmoidf_<sizeof(T) == 2>(to_f(pc[c]) + bias_c[c]) * q;
+                        const float sc = sigmoidf_<kFast>(to_f(pc[c]) + bias_c[c]) * q;
                         if (sc > best) { best = sc; bc = c; }
                     }
                 }
@@ -469,16 +648,12 @@ __global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_co
         __syncthreads();
         const int fc = s_fcnt[ps];
         unsigned long long* dst = E.keys + (int64_t)s_fimg[ps] * E.key_stride + s_fbase[ps];
-        for (int i = tid; i < fc; i += 256) dst[i] = s_stage[ps][i];
+        for (int i = tid; i < fc; i += 256) dst[i] = s_stage(ps)[i];
     }
 }
 
-static size_t emit_smem_bytes(int nc, size_t esz) {
-    const size_t box_bytes = (size_t)kTile * 4 * kRegMax * esz;
-    const size_t cls_bytes = ((size_t)kTile * nc * esz + 127) & ~(size_t)127;
-    const size_t bias_ld = (4 * kRegMax + nc + 3) & ~3;
-    return 2 * box_bytes + 2 * cls_bytes + (size_t)kMaxLevels * kWStride * 4 + kTile * kStatLd * 4 + 4 * kTile * 4 + 8 * kTile * 4 + kTile * 4 +
-           kMaxLevels * bias_ld * 4 + 16 + 2 * kStageCap * 8 + 64;
+static size_t emit_smem_bytes(int nc, size_t esz, int nl) {
+    return (esz == 2 ? emit_layout<true>(nc, (uint32_t)esz, nl).total : emit_layout<false>(nc, (uint32_t)esz, nl).total) + 64;
 }
 
 static int fill_params(DecodeParams& P, int nl, const void* const* box, const int64_t* box_s, const void* const* cls, const int64_t* cls_s, const int32_t* hw,
@@ -595,7 +770,7 @@ extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* 
     const bool do_emit = g_detect_stages & 1;
     if (do_emit) nms_prepare(L, ws, st);
     EmitArgs E{conf, class_keep, (unsigned long long*)(ws + L.keys), L.key_stride, (int*)(ws + L.counts), (float4*)(ws + box_off), B};
-    const size_t sm = emit_smem_bytes(nc, esz);
+    const size_t sm = emit_smem_bytes(nc, esz, nl);
     const int total = B * P.tiles_per_image;
     const int grid = total < 2 * kSMs ? total : 2 * kSMs;  // persistent: two CTAs per SM
 #define EL_LAUNCH_EMIT(M)                                                                               \

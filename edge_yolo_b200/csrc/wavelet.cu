@@ -534,27 +534,33 @@ __global__ void __launch_bounds__(256) merge_fwd_tiled(const T* __restrict__ b, 
 
 // Exact 2x case (H = 2h, W = 2w: every EdgeLine site at 640^2 / 1280^2).  Output rows 2k+1 and 2k+2 both blend source rows
 // k and k+1 (weights .75/.25 and .25/.75), so a thread walks SOURCE rows: one pair of 16 B loads and one horizontal blend
-// per source row feed two output rows; the band weight is folded into the horizontal taps.  ~45 instructions per 16 B
-// of output instead of ~120 for the general kernel.
-template <typename T>
+// per source row feed two output rows; the band weight is folded into the horizontal taps.
+// The kernel was load-latency bound (ncu: long_scoreboard 11-19 of ~20 stall cycles per issue, one dependent L2 round trip per
+// source row): all 2*(SR+1) loads of a thread are now issued before the first use, and the band weights are evaluated per warp
+// (softplus in lanes, shuffles) instead of thread 0 + a block barrier.
+template <typename T, int SR>
 __global__ void __launch_bounds__(256) merge_fwd_x2(const T* __restrict__ b, Strides4 bs, BandPtrs bands, const float* __restrict__ alpha,
-                                                    T* __restrict__ out, Strides4 os, int c, int CV, int cols_per_block, int srows, int h, int w,
-                                                    int c_off) {
+                                                    T* __restrict__ out, Strides4 os, int c, int CV, int cols_per_block, int h, int w, int c_off) {
     constexpr int V = Vec16<T>::N;
-    __shared__ float s_w[4];
     pdl_launch_dependents();
-    if (threadIdx.x == 0) {
-        float wt[4];
-        band_weights(alpha, wt);
-        s_w[0] = wt[0]; s_w[1] = wt[1]; s_w[2] = wt[2]; s_w[3] = wt[3];
-    }
-    __syncthreads();
     const int H = 2 * h, W = 2 * w;
     const TileMap m = tile_map(CV, cols_per_block, W);
-    if (!m.active) return;
-    const int k0 = (int)blockIdx.y * srows, k1 = min(k0 + srows, h);
-    const int64_t n = blockIdx.z;
     const int ch = m.cv * V + c_off;  // c_off = c: bands-only output (the pass-through copy of b is skipped)
+    const int half = c / 2;
+    const int seg = ch >= c ? min((ch - c) / half, 3) : 0, cc = (ch - c) - seg * half;
+    float wb;
+    {   // softplus(alpha) / (sum + 1e-6), same operation order as band_weights()
+        const float a = __ldg(alpha + (threadIdx.x & 3));
+        const float sp = a > 20.f ? a : log1pf(expf(a));
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s += __shfl_sync(0xffffffffu, sp, i);
+        s += 1e-6f;
+        wb = __shfl_sync(0xffffffffu, sp, seg) / s;
+    }
+    if (!m.active) return;
+    const int k0 = (int)blockIdx.y * SR, k1 = min(k0 + SR, h);
+    const int64_t n = blockIdx.z;
     // this block writes output rows 2*k0+1 .. 2*k1 (clipped to H-1), plus row 0 when k0 == 0
     const int y_first = k0 == 0 ? 0 : 2 * k0 + 1, y_last = min(2 * k1, H - 1);
     if (ch < c) {  // pass-through copy of b
@@ -564,43 +570,52 @@ __global__ void __launch_bounds__(256) merge_fwd_x2(const T* __restrict__ b, Str
         for (int y = y_first; y <= y_last; ++y, p += bs.h, q += os.h) stg_stream(q, ldg_stream(p));
         return;
     }
-    const int half = c / 2, seg = (ch - c) / half, cc = (ch - c) - seg * half;
     int x0, x1; float lx;
     bilin_src(m.col, 0.5f, w, x0, x1, lx);
-    const float wb = s_w[seg], ax = (1.f - lx) * wb, bx = lx * wb;
+    const float ax = (1.f - lx) * wb, bx = lx * wb;
     const Strides4 s = bands.s[seg];
-    const T* p0 = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + cc + (int64_t)x0 * s.w + (int64_t)k0 * s.h;
-    const int64_t dx = (int64_t)(x1 - x0) * s.w, sh = s.h;
+    const T* pb = reinterpret_cast<const T*>(bands.p[seg]) + n * s.n + cc + (int64_t)x0 * s.w;
+    const int64_t dx = (int64_t)(x1 - x0) * s.w;
+    uint4 ra[SR + 1], rb[SR + 1];  // source rows k0 .. k0+SR (clamped at the bottom edge): every load in flight at once
+#pragma unroll
+    for (int i = 0; i <= SR; ++i) {
+        const T* p = pb + (int64_t)min(k0 + i, h - 1) * s.h;
+        ra[i] = ldg_cached(p);       // each band pixel feeds ~4 output pixels: keep it in L1
+        rb[i] = ldg_cached(p + dx);
+    }
     T* q = out + n * os.n + (int64_t)y_first * os.h + (int64_t)m.col * os.w + (ch - c_off);
     const int64_t oh = os.h;
     float prev[V], cur[V], r[V];
-    auto hrow = [&](const T* p, float (&dst)[V]) {
+    auto hrow = [&](uint4 a0, uint4 a1, float (&dst)[V]) {
         float v0[V], v1[V];
-        unpack<T>(ldg_cached(p), v0);       // each band pixel feeds ~4 output pixels: keep it in L1
-        unpack<T>(ldg_cached(p + dx), v1);
+        unpack<T>(a0, v0);
+        unpack<T>(a1, v1);
 #pragma unroll
         for (int e = 0; e < V; ++e) dst[e] = ax * v0[e] + bx * v1[e];
     };
-    hrow(p0, prev);
+    hrow(ra[0], rb[0], prev);
     if (k0 == 0) {  // output row 0 = source row 0
         stg_stream(q, pack<T>(prev));
         q += oh;
     }
-    for (int k = k0; k < k1; ++k) {
-        if (k + 1 < h) p0 += sh;  // source row k+1 (clamped at the bottom edge)
-        hrow(p0, cur);
 #pragma unroll
-        for (int e = 0; e < V; ++e) r[e] = 0.75f * prev[e] + 0.25f * cur[e];
-        stg_stream(q, pack<T>(r));
-        q += oh;
-        if (2 * k + 2 < H) {
+    for (int i = 0; i < SR; ++i) {
+        const int k = k0 + i;
+        if (k < k1) {
+            hrow(ra[i + 1], rb[i + 1], cur);
 #pragma unroll
-            for (int e = 0; e < V; ++e) r[e] = 0.25f * prev[e] + 0.75f * cur[e];
+            for (int e = 0; e < V; ++e) r[e] = 0.75f * prev[e] + 0.25f * cur[e];
             stg_stream(q, pack<T>(r));
             q += oh;
-        }
+            if (2 * k + 2 < H) {
 #pragma unroll
-        for (int e = 0; e < V; ++e) prev[e] = cur[e];
+                for (int e = 0; e < V; ++e) r[e] = 0.25f * prev[e] + 0.75f * cur[e];
+                stg_stream(q, pack<T>(r));
+                q += oh;
+            }
+#pragma unroll
+            for (int e = 0; e < V; ++e) prev[e] = cur[e];
+        }
     }
 }
 
@@ -718,8 +733,9 @@ extern "C" int el_wave_merge_fwd(const void* b, const int64_t bs_[4], const void
         if (vec) {
             if (co / V <= 256 && B <= 65535 && H == 2 * h && W == 2 * w) {
                 int cpb, srows;
-                dim3 g = tile_grid(co / V, W, h, B, cpb, srows, 8, 2);  // rows here = SOURCE rows per thread
-                merge_fwd_x2<T><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, co / V, cpb, srows, h, w, c_off);
+                dim3 g = tile_grid(co / V, W, h, B, cpb, srows, 4, 2);  // rows here = SOURCE rows per thread
+                if (srows == 4) merge_fwd_x2<T, 4><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, co / V, cpb, h, w, c_off);
+                else merge_fwd_x2<T, 2><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, co / V, cpb, h, w, c_off);
             } else if (co / V <= 256 && B <= 65535) {
                 int cpb, rows;
                 dim3 g = tile_grid(co / V, W, H, B, cpb, rows, kMergeRows, 4);

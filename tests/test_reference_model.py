@@ -65,3 +65,32 @@ def test_nms_oracle_matches_reference_on_model_output(ref_model):
         assert [g.shape[0] for g in got] == [w.shape[0] for w in want]
         for g, w in zip(got, want):
             assert g.tobytes() == w.numpy().astype(np.float32).tobytes()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_metric_oracle_matches_reference(seed):
+    """oracle/metrics_ref.py == the reference's box_iou + match_predictions + ap_per_class on the same detections."""
+    ref_loader.load()
+    from ultralytics.models.yolo.detect.val import DetectionValidator
+    from ultralytics.utils.metrics import ap_per_class, box_iou
+
+    from oracle import metrics_ref
+
+    dets, labs = metrics_ref.synthetic_case(seed)
+    v = DetectionValidator.__new__(DetectionValidator)
+    v.iouv = torch.linspace(0.5, 0.95, 10)
+    tps, confs, pcls, tcls = [], [], [], []
+    for det, lab in zip(dets, labs):
+        tcls.append(lab[:, 0])
+        if det.shape[0] == 0:
+            continue
+        d, l_ = torch.from_numpy(det), torch.from_numpy(lab)
+        if lab.shape[0]:
+            tp = v.match_predictions(d[:, 5], l_[:, 0], box_iou(l_[:, 1:], d[:, :4])).numpy()
+        else:
+            tp = np.zeros((det.shape[0], 10), dtype=bool)
+        tps.append(tp); confs.append(det[:, 4]); pcls.append(det[:, 5])
+    ap = ap_per_class(np.concatenate(tps), np.concatenate(confs), np.concatenate(pcls), np.concatenate(tcls))[5]
+    want = (float(ap.mean()), float(ap[:, 0].mean()))
+    got = metrics_ref.evaluate(dets, labs)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
