@@ -49,6 +49,13 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     return r;
 }
 __device__ __forceinline__ uint4 ldg_cached(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+// coherent 128-bit load served by L2 (never L1): for activations read right after griddepcontrol.wait by a kernel whose CTAs became
+// resident while the producer was still running (programmatic dependent launch)
+__device__ __forceinline__ uint4 ldg_l2(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
 __device__ __forceinline__ void stg_stream(void* p, uint4 v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
