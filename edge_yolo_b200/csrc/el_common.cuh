@@ -42,20 +42,23 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
 // ---- 16-byte vectors of T <-> float registers -------------------------------------------------
 template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
 
-// streaming (read-once) 128-bit load: keep it out of L1 so re-used tiles stay resident
+// Activation loads.  Neither uses the non-coherent path (ld.global.nc / __ldg): a kernel launched with programmatic dependent launch
+// becomes resident while its producer is still WRITING the tensors it will read after griddepcontrol.wait, which breaks the
+// "read-only for the lifetime of the kernel" contract of .nc -- measured: the engine graph and the eager path disagreed in the last bits
+// of a few pixels until the loads were made coherent (EL_PDL=0 also cured it).
+// streaming (read-once) 128-bit load, L2 only: re-used tiles of other tensors stay resident in L1
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ uint4 ldg_cached(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-// coherent 128-bit load served by L2 (never L1): for activations read right after griddepcontrol.wait by a kernel whose CTAs became
-// resident while the producer was still running (programmatic dependent launch)
-__device__ __forceinline__ uint4 ldg_l2(const void* p) {
+// 128-bit load of data that neighbouring threads / CTAs of the same SM read again (bilinear taps, 2x upsampling): allocate in L1
+__device__ __forceinline__ uint4 ldg_cached(const void* p) {
     uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    asm volatile("ld.global.ca.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint4 ldg_l2(const void* p) { return ldg_stream(p); }
 __device__ __forceinline__ void stg_stream(void* p, uint4 v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
