@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kDwMaxThreads) dwconv_tile_kernel(const T* __r
 }
 
 // =====================================================================================================================
-// k = 7 on the tensor cores (16-bit activations).  The CUDA-core kernel above is bounded by FMA issue (49 taps per output:
+// k x k on the tensor cores (16-bit activations; written for k = 7, also used for 3 and 5).  The CUDA-core kernel above is bounded by FMA issue (49 taps per output:
 // 0.15 - 0.4 of the HBM roofline, ncu: fma pipe 43 %, issue 72 %).  A depthwise row filter is a banded (Toeplitz) matrix:
 //     out_c[y][x] = sum_dy  sum_x'  in_c[y + dy][x'] * T_dy[x'][x],     T_dy[x'][x] = w_c[dy][x' - x]  (0 <= x' - x < 7)
 // so one channel's 16 (rows) x 8 (columns) output block is 7 mma.sync m16n8k16 (one per filter row dy) with the data as the
@@ -159,16 +159,24 @@ __global__ void __launch_bounds__(kDwMaxThreads) dwconv_tile_kernel(const T* __r
 //   stage : patch (38 rows x 22 columns x 16 channels) -> 16 channel planes [row][24] (2-byte scatter; zero fill = padding)
 //   MMA   : warp w owns channels 2w, 2w+1; per channel and 16-row block: 7 x (ldmatrix.x4 + ldmatrix.x2 + 2 MMA)
 //   out   : bias + activation on the accumulators -> channel planes of the output tile -> 16-byte NHWC vectors -> global
+// Measured and not kept: (a) pixel pairs per thread with 32-bit plane stores / loads (128 registers: 66 vs 56 us at 160^2); (b) splitting
+// the rows of small maps over more CTAs (41 vs 36.5 us at 80^2); (c) a second generation with cp.async into a raw NHWC buffer and
+// ldmatrix.trans for both transpositions (no prefetch registers, a third barrier per tile: 60.8 vs 57.0 us at 160^2, 50 vs 42 us for k = 3).
+// Of the 56 us at 160^2 about 25 us scale with the filter rows (ldmatrix + MMA); the rest is staging, write-out and barriers at 16 warps / SM.
 namespace dwtc {
 
-constexpr int TX = 16, TY = 32, CH = 16, KS = 7, PAD = 3;
-constexpr int PR = TY + KS - 1;   // 38 patch rows
-constexpr int PCU = TX + KS - 1;  // 22 patch columns in use
+constexpr int TX = 16, TY = 32, CH = 16;
 constexpr int PC = 24;            // patch row pitch (elements): 48 B -> the 8 row addresses of an ldmatrix hit 8 distinct 16 B slots
 constexpr int OC = 24;            // output tile row pitch: 12 words -> conflict-free accumulator stores
-constexpr int PLANE_IN = PR * PC, PLANE_OUT = TY * OC;
+constexpr int PLANE_OUT = TY * OC;
 constexpr int kThreads = 256;
-constexpr size_t kSmem = (size_t)CH * PLANE_IN * 2 + (size_t)CH * PLANE_OUT * 2 + (size_t)CH * KS * KS * 4;
+template <int KS> struct Geo {    // filter size 3 / 5 / 7 (the same kernel: KS Toeplitz blocks per channel, KS MMAs per output block)
+    static constexpr int PAD = KS / 2;
+    static constexpr int PR = TY + KS - 1;   // patch rows (38 for k = 7)
+    static constexpr int PCU = TX + KS - 1;  // patch columns in use (22 for k = 7); columns PCU..23 stay zero
+    static constexpr int PLANE_IN = PR * PC;
+    static constexpr size_t kSmem = (size_t)CH * PLANE_IN * 2 + (size_t)CH * PLANE_OUT * 2 + (size_t)CH * KS * KS * 4;
+};
 
 template <typename T> __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1);
 template <> __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -189,10 +197,11 @@ template <> __device__ __forceinline__ uint32_t pack2h<__half>(float a, float b)
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 2) dwconv7_tc_kernel(const T* __restrict__ x, Strides4 xs, const float* __restrict__ w,
+template <typename T, int KS>
+__global__ void __launch_bounds__(kThreads, 2) dwconv_tc_kernel(const T* __restrict__ x, Strides4 xs, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, T* __restrict__ o, Strides4 os, int C, int H, int W, int act,
                                                                  int n_cb, int rows_per_cta) {
+    constexpr int PAD = Geo<KS>::PAD, PR = Geo<KS>::PR, PCU = Geo<KS>::PCU, PLANE_IN = Geo<KS>::PLANE_IN;
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint16_t* s_in = reinterpret_cast<uint16_t*>(s_raw);                                    // [16 channels][38 rows][24]
     uint16_t* s_out = s_in + CH * PLANE_IN;                                                  // [16 channels][32 rows][24]
@@ -206,7 +215,10 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv7_tc_kernel(const T* __rest
         const int c = i / (KS * KS), tap = i - c * (KS * KS);
         s_wt[i] = __ldg(w + (int64_t)tap * C + c0 + c);
     }
-    for (int i = tid; i < CH * PR; i += kThreads) *reinterpret_cast<uint32_t*>(s_in + i * PC + PCU) = 0u;  // (plane, row) i: columns 22, 23
+    for (int i = tid; i < CH * PR * ((PC - PCU) / 2); i += kThreads) {  // (plane, row): columns PCU .. 23 (22, 23 for k = 7), one word per two columns
+        const int row = i / ((PC - PCU) / 2), wd = i - row * ((PC - PCU) / 2);
+        *reinterpret_cast<uint32_t*>(s_in + row * PC + PCU + 2 * wd) = 0u;
+    }
     __syncthreads();
     // Toeplitz B fragments of this warp's two channels: element (k, n) = w[dy][k - n]; b0 = rows k = 2t, 2t+1, b1 = rows 2t+8, 2t+9, column n = g
     uint32_t bf[2][KS][2];
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 2) dwconv7_tc_kernel(const T* __rest
     }
 }
 
-template <typename T>
+template <typename T, int KS>
 static int launch(const void* x, Strides4 xs, const float* w, const float* bias, void* out, Strides4 os, int B, int C, int H, int W, int act,
                   cudaStream_t st) {
     // a CTA walks down its rows in 32-row tiles (Toeplitz fragments built once, next tile prefetched).  Splitting the rows of small maps
@@ -340,9 +352,9 @@ static int launch(const void* x, Strides4 xs, const float* w, const float* bias,
     chunks = (int)ceil_div(H, rows_per_cta);
     if ((int64_t)n_cb * chunks > 65535) return EL_ERR_UNSUPPORTED;
     dim3 grid((unsigned)ceil_div(W, TX), (unsigned)(n_cb * chunks), (unsigned)B);
-    cudaError_t e = cudaFuncSetAttribute(dwconv7_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tc_kernel<T, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<KS>::kSmem);
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
-    e = launch_pdl(dwconv7_tc_kernel<T>, grid, dim3(kThreads), kSmem, st, (const T*)x, xs, w, bias, (T*)out, os, C, H, W, act, n_cb, rows_per_cta);
+    e = launch_pdl(dwconv_tc_kernel<T, KS>, grid, dim3(kThreads), Geo<KS>::kSmem, st, (const T*)x, xs, w, bias, (T*)out, os, C, H, W, act, n_cb, rows_per_cta);
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
     return EL_OK;
 }
@@ -400,10 +412,15 @@ extern "C" int el_dwconv_fwd(const void* x, const int64_t xs_[4], const float* w
     EL_DISPATCH_DTYPE(dtype, {
         if (!channel_vectorisable<T>(x, xs, C) || !channel_vectorisable<T>(out, os, C)) return EL_ERR_UNSUPPORTED;
         if constexpr (sizeof(T) == 2) {
-            // k = 7, 16-bit: Toeplitz MMA kernel (maps of at least 32 x 32: smaller ones do not fill its 32 x 16 tiles); EL_DW_TC=0/2 = never / always
+            // k = 7, 16-bit maps of at least 32 x 32 with C % 16 == 0: Toeplitz MMA kernel (smaller maps do not fill its 32 x 16 tiles; for
+            // k = 3 it was measured equal or slower than the CUDA-core kernel: 41.7 vs 41.3 us at 160^2, 60 vs 44 us at 80^2 -- its staging
+            // and write-out cost what the 9 taps cost).  EL_DW_TC = 0: never, 2: every map size, 3: every map size and k = 3 / 5 too
             static const int tc_mode = [] { const char* v = getenv("EL_DW_TC"); return v ? atoi(v) : 1; }();
-            if (k == 7 && C % dwtc::CH == 0 && B <= 65535 && C / dwtc::CH <= 65535 && tc_mode && (tc_mode == 2 || (H >= 32 && W >= 32))) {
-                rc = dwtc::launch<T>(x, xs, w, bias, out, os, B, C, H, W, act, st);
+            const bool k_ok = k == 7 || tc_mode == 3;
+            if (k_ok && C % dwtc::CH == 0 && B <= 65535 && C / dwtc::CH <= 65535 && tc_mode && (tc_mode >= 2 || (H >= 32 && W >= 32))) {
+                rc = k == 7 ? dwtc::launch<T, 7>(x, xs, w, bias, out, os, B, C, H, W, act, st)
+                   : k == 5 ? dwtc::launch<T, 5>(x, xs, w, bias, out, os, B, C, H, W, act, st)
+                            : dwtc::launch<T, 3>(x, xs, w, bias, out, os, B, C, H, W, act, st);
                 if (rc != EL_OK) return rc;
                 note_launches(1);
                 return check_launch();

@@ -505,22 +505,23 @@ def test_dwconv(dtype, tol, k, shape, epi):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("k", [7])
 @pytest.mark.parametrize("shape,epi", [((2, 32, 33, 47), True), ((1, 64, 80, 80), False), ((2, 16, 160, 160), True), ((3, 48, 32, 32), True)])
-def test_dwconv7_tensor_core(dtype, shape, epi):
-    """k = 7 depthwise conv on the Toeplitz-MMA kernel (maps >= 32 x 32, C % 16 == 0, 16-bit): ragged row / column tiles, channel-slice
+def test_dwconv_tensor_core(dtype, shape, epi, k):
+    """k x k depthwise conv on the Toeplitz-MMA kernel (maps >= 32 x 32, C % 16 == 0, 16-bit): ragged row / column tiles, channel-slice
     views, bias + SiLU.  The kernel rounds the taps to the activation type (what a 16-bit model holds anyway), so the reference uses the
     rounded taps and the check is tight: fp32 accumulation, one output rounding."""
     gen = torch.Generator().manual_seed(shape[1] * 7 + shape[2])
     B, C, H, W = shape
     full = torch.randn(B, C + 16, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
     x = full[:, 16:]  # channel-slice view: pixel pitch != C
-    w = (torch.randn(C, 1, 7, 7, generator=gen) * 0.3).to(DEV).to(dtype).float()
+    w = (torch.randn(C, 1, k, k, generator=gen) * 0.3).to(DEV).to(dtype).float()
     b = torch.randn(C, generator=gen).to(DEV) if epi else None
-    want = torch.nn.functional.conv2d(x.double(), w.double(), b.double() if epi else None, padding=3, groups=C)
+    want = torch.nn.functional.conv2d(x.double(), w.double(), b.double() if epi else None, padding=k // 2, groups=C)
     if epi:
         want = torch.nn.functional.silu(want)
     out = torch.full((B, C + 8, H, W), 7.0, device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
-    got = ops().dwconv(x, ops().pack_dw_weight(w), 7, bias=b, act=ops().ACT_SILU if epi else ops().ACT_NONE, out=out[:, :C])
+    got = ops().dwconv(x, ops().pack_dw_weight(w), k, bias=b, act=ops().ACT_SILU if epi else ops().ACT_NONE, out=out[:, :C])
     tol = 1e-2 if dtype == torch.bfloat16 else 2e-3
     close(got, want.float(), tol, tol)
     assert float((out[:, C:] - 7.0).abs().max()) == 0.0  # nothing written outside the destination view

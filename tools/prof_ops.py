@@ -46,7 +46,7 @@ if "pw" in which:  # the engine's 1x1 convs: cv1 with split outputs, concat-free
         flush.zero_()
         ops.pwconv(xs, wpk, N, bias=bias, act=ops.ACT_SILU, residual=res, out=out)
 if "dw" in which:
-    for C, hw, k, epi in ((8, 160, 7, False), (16, 80, 7, False), (64, 80, 3, True), (128, 40, 3, True)):
+    for C, hw, k, epi in ((16, 160, 7, False), (32, 80, 7, False), (64, 40, 7, False), (64, 80, 3, True), (128, 40, 3, True)):  # the engine's sites
         x = rn(B, C, hw, hw)
         wp = ops.pack_dw_weight(torch.randn(C, 1, k, k, device=dev, generator=g) * 0.2)
         bias = torch.randn(C, device=dev, generator=g) if epi else None
