@@ -272,11 +272,11 @@ def profile_kernels(pred, a, iters=10):
 
 def step_traffic(kernel):
     """DRAM bytes (read + write) of all launches of `kernel` in one step, from the committed ncu capture of the default workload."""
-    names = {"pwconv": ["pw::pwconv_tc_kernel"], "dwconv": ["el::dwconv_tile_kernel"], "bias_act": ["el::bias_act_tiled", "el::bias_act_flat"],
+    names = {"pwconv": ["pw::pwconv_tc_kernel"], "dwconv": ["el::dwconv_tile_kernel", "dwtc::dwconv_tc_kernel"], "bias_act": ["el::bias_act_tiled", "el::bias_act_flat"],
              "stem_conv_u8": ["stemtc::stem_tc_kernel"], "wave_merge_bands": ["el::merge_fwd_x2"], "dwt_haar": ["el::dwt_fwd_tiled"],
              "gfl_decode_emit": ["el::gfl_decode_emit_kernel"], "nms_sweep": ["el::nms_sweep"], "upsample2x_cat": ["el::upsample2x_cat_tiled"]}
     try:
-        with open(os.path.join(ROOT, "profiles", "r01e_step_b64_time_dram.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01g_step_b64_time_dram.json")) as f:
             prof = json.load(f)
         # pwconv_tc_kernel also runs the narrow 3x3 convs (el_conv3x3_fwd); the capture cannot tell the two apart
         return sum(prof[n]["dram_bytes"] for n in names.get(kernel, []) if n in prof) or None
@@ -390,7 +390,7 @@ def product_arm(a):
                             "largest_site": {"shape": best["shape"], "MB": best["MB"], "us": best["us"], "achieved": best["gbs"], "frac": best["gbs"] / peak},
                             "note": "achieved = algorithmic bytes of ALL launch sites of this kernel in one step / their summed CUDA-event time "
                                     "(each site timed alone, inputs rotated through > L2); traffic = DRAM bytes of the same launches in one step "
-                                    "from the committed ncu capture (profiles/r01e_step_b64_time_dram.json), null for other configs"}
+                                    "from the committed ncu capture (profiles/r01g_step_b64_time_dram.json), null for other configs"}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         rate, ms, threads = cpu_oracle_rate(a, steps=3, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",

@@ -33,7 +33,7 @@ constexpr int kDwRT = 4;          // output rows per strip = vertical register t
 constexpr int kDwMaxThreads = 256;
 
 struct DwGeom {
-    int CVL, cvl_shift;   // channel vectors per CTA (power of two, <= 8)
+    int CVL, cvl_shift;   // channel vectors per CTA (<= 8); cvl_shift = log2(CVL), or -1 when CVL is not a power of two (C = 48, 80, ...)
     int TW;               // output columns per tile
     int NS;               // thread strips per CTA (threads = CVL * TW * NS)
     int TH;               // output rows per tile (multiple of kDwRT)
@@ -49,6 +49,9 @@ __global__ void __launch_bounds__(kDwMaxThreads) dwconv_tile_kernel(const T* __r
     constexpr int V = Vec16<T>::N, HV = V / 4, P = K / 2, NIN = kDwRT + K - 1;
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int CVL = G.CVL;
+    // (index / CVL, index % CVL): shifts for the usual power-of-two vector counts, a division for e.g. the 80-channel class towers
+    auto div_cvl = [&](int i) { return G.cvl_shift >= 0 ? i >> G.cvl_shift : i / CVL; };
+    auto mod_cvl = [&](int i) { return G.cvl_shift >= 0 ? i & (CVL - 1) : i % CVL; };
     float* s_w = reinterpret_cast<float*>(s_raw);                                   // [tap][HV][cvl][4]
     uint4* s_in = reinterpret_cast<uint4*>(s_raw + (size_t)K * K * CVL * V * 4);    // [row][column][cv]
     const int cbk = (int)blockIdx.z % G.n_cb;
@@ -66,14 +69,14 @@ __global__ void __launch_bounds__(kDwMaxThreads) dwconv_tile_kernel(const T* __r
     pdl_wait();
     {   // ---- stage the input patch: pieces (row r, column p, vector cv), cv fastest = contiguous in global memory and in the patch
         const T* xb = x + n * xs.n + c0;
-        const int per_row = PWf << G.cvl_shift;
+        const int per_row = PWf * CVL;
         for (int r = 0; r < rows_in; ++r) {
             const int iy = ty0 - P + r;
             const bool row_ok = iy >= 0 && iy < H;
             const T* xrow = xb + (int64_t)iy * xs.h;
             const uint32_t drow = dw_smem_addr(s_in + (size_t)r * per_row);
             for (int i = tid; i < per_row; i += nthreads) {
-                const int cv = i & (CVL - 1), ix = tx0 - P + (i >> G.cvl_shift);
+                const int cv = mod_cvl(i), ix = tx0 - P + div_cvl(i);
                 const bool ok = row_ok && ix >= 0 && ix < W;
                 const T* src = ok ? xrow + (int64_t)ix * xs.w + cv * V : xb;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(drow + (uint32_t)i * 16), "l"(src), "r"(ok ? 16u : 0u) : "memory");
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kDwMaxThreads) dwconv_tile_kernel(const T* __r
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    const int cvl = tid & (CVL - 1), rest = tid >> G.cvl_shift;
+    const int cvl = mod_cvl(tid), rest = div_cvl(tid);
     const int xl = rest % G.TW, strip0 = rest / G.TW;
     const int ox = tx0 + xl;
     if (strip0 >= G.NS || ox >= W) return;
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(kDwMaxThreads) dwconv_tile_kernel(const T* __r
 #pragma unroll
     for (int e = 0; e < V; ++e) bv[e] = bias ? __ldg(bias + ch + e) : 0.f;
     const float4* sw4 = reinterpret_cast<const float4*>(s_w);
-    const int row_stride = PWf << G.cvl_shift;  // uint4 units
+    const int row_stride = PWf * CVL;  // uint4 units
     for (int ly0 = strip0 * kDwRT; ly0 < TH; ly0 += G.NS * kDwRT) {
         // accumulators, inputs and taps are kept as fp32 pairs of adjacent channels: one FFMA2 per pair
         f32x2 acc2[kDwRT][V / 2];
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(kDwMaxThreads) dwconv_tile_kernel(const T* __r
             for (int e = 0; e < V / 2; ++e) acc2[r][e] = pack_f32x2(bv[2 * e], bv[2 * e + 1]);
 #pragma unroll 1
         for (int kx = 0; kx < K; ++kx) {
-            const uint4* scol = s_in + (size_t)ly0 * row_stride + ((xl + kx) << G.cvl_shift) + cvl;
+            const uint4* scol = s_in + (size_t)ly0 * row_stride + (xl + kx) * CVL + cvl;
             f32x2 v2[NIN][V / 2];
 #pragma unroll
             for (int j = 0; j < NIN; ++j) {
@@ -369,8 +372,8 @@ static int launch_dw(const void* x, Strides4 xs, const float* w, const float* bi
     const int CV = C / V;
     DwGeom G;
     G.CVL = CV < 8 ? CV : 8;
-    if ((G.CVL & (G.CVL - 1)) || CV % G.CVL) return EL_ERR_UNSUPPORTED;  // 1, 2, 4 or 8 vectors per CTA
-    G.cvl_shift = G.CVL == 1 ? 0 : (G.CVL == 2 ? 1 : (G.CVL == 4 ? 2 : 3));
+    while (CV % G.CVL) --G.CVL;  // largest divisor of CV that is <= 8 (80 channels: 5 vectors per CTA)
+    G.cvl_shift = G.CVL == 1 ? 0 : (G.CVL == 2 ? 1 : (G.CVL == 4 ? 2 : (G.CVL == 8 ? 3 : -1)));
     G.n_cb = CV / G.CVL;
     const int tw_max = kDwMaxThreads / G.CVL;
     const int col_tiles = (int)ceil_div(W, tw_max);

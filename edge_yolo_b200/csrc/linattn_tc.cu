@@ -3,7 +3,10 @@
 // on the 5th-generation tensor cores with fp32 accumulators in tensor memory:
 //   GEMM1  ctx[i][j]  = sum_n softmax_d(K)[n][i] * V[n][j]     M=64 (i), N=64 (j), K = tokens   -> TMEM cols [0,64)
 //   GEMM2  y[n][j]    = sum_i exp(q[n][i]-max_i) * ctx[i][j]/s_i  M=128 tokens, N=64, K=64        -> TMEM cols [64,128)
-// One CTA (4 warps) per (image, head).  Operands are written to shared memory by the CTA's own threads in the
+// One CTA (4 warps) per (image, head) -- or (EL_LINATTN_CLUSTER=1, measured slower at the benchmark shape, see linattn_tc_launch)
+// a CLUSTER of 4 CTAs per (image, head): CTA r takes the chunks r, r+4, ...; the partial ctx (64 x 64 fp32) and the per-channel
+// (max, sum) of q are exchanged through distributed shared memory (mapa + ld.shared::cluster between two barrier.cluster phases), every
+// CTA then normalises the summed ctx itself and runs GEMM2 on its own chunks.  Operands are written to shared memory by the CTA's own threads in the
 // canonical no-swizzle UMMA layouts ("chunk-major": 16-byte chunks of 8 elements, [chunk of the 64-wide dim][token][8]):
 //   softmax(K)^T and V  : MN-major (channels contiguous), K dim = tokens, LBO = 128 B, SBO = 2048 B
 //   P = exp(q - max)    : K-major  (channels = K dim),                   LBO = 2048 B, SBO = 128 B
@@ -36,6 +39,28 @@ constexpr uint32_t kOffCtx = kOffQ + kTileBytes;      // ctx' bf16, 8 KiB
 constexpr uint32_t kOffStat = kOffCtx + kD * kD * 2;  // max[64], sum[64] fp32
 constexpr uint32_t kOffBar = kOffStat + 6 * kD * 4;   // (max, sum, 4 x 64 partials) then 3 mbarriers + tmem address
 constexpr uint32_t kSmemBytes = kOffBar + 64;
+constexpr uint32_t kOffCtxP = (kSmemBytes + 15) & ~15u;        // cluster variant: this CTA's partial ctx, fp32 [64][64]
+constexpr uint32_t kOffGStat = kOffCtxP + kD * kD * 4;          // cluster variant: global max[64], 1 / sum[64]
+constexpr uint32_t kSmemBytesCluster = kOffGStat + 2 * kD * 4;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// address of the same shared-memory location in CTA `rank` of the cluster, and a load through it
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,7 +131,7 @@ template <typename T> __device__ __forceinline__ void load_row(const T* p, bool 
     for (int g = 0; g < 8; ++g) r[g] = valid ? ldg_cached(p + 8 * g) : make_uint4(0, 0, 0, 0);
 }
 
-template <typename T>
+template <typename T, int CS>
 __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__ AttnArgs A) {
     extern __shared__ __align__(1024) unsigned char sm[];
     const uint32_t sbase = smem_addr(sm);
@@ -117,7 +142,8 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + kOffBar + 32);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x / A.heads, head = blockIdx.x % A.heads;
+    const int prob = (int)blockIdx.x / CS, rank = CS > 1 ? (int)cluster_ctarank() : 0;  // 1-D clusters: rank == blockIdx.x % CS
+    const int b = prob / A.heads, head = prob % A.heads;
     const int C = A.heads * kD, N = A.N;
     const T* qkv = reinterpret_cast<const T*>(A.qkv) + (int64_t)b * A.qb;
     const T* gq = qkv + (0 * C + head * kD);
@@ -143,6 +169,7 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
     const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + kD;
 
     const int n_chunks = (N + kChunk - 1) / kChunk;
+    const int n_my = rank < n_chunks ? (n_chunks - rank + CS - 1) / CS : 0;  // this CTA's chunks: rank, rank + CS, ...
     const uint32_t idesc1 = umma_idesc(kFmt, 1, 1, 64, 64);    // both operands MN-major (channels contiguous)
     const uint32_t idesc2 = umma_idesc(kFmt, 0, 0, 128, 64);   // both operands K-major
 
@@ -150,16 +177,17 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
     // The three token rows (K, V, Q: 24 x 16 B per thread) of chunk c+1 are requested while chunk c is being processed.
     uint4 rk[8], rv[8], rq[8];
     {
-        const bool v0 = tid < N;
-        load_row<T>(gk + (int64_t)tid * A.qn, v0, rk);
-        load_row<T>(gv + (int64_t)tid * A.qn, v0, rv);
-        load_row<T>(gq + (int64_t)tid * A.qn, v0, rq);
+        const int n0 = rank * kChunk + tid;
+        const bool v0 = n0 < N;
+        load_row<T>(gk + (int64_t)n0 * A.qn, v0, rk);
+        load_row<T>(gv + (int64_t)n0 * A.qn, v0, rv);
+        load_row<T>(gq + (int64_t)n0 * A.qn, v0, rq);
     }
-    for (int c = 0; c < n_chunks; ++c) {
-        const int buf = c & 1;
+    for (int c = 0; c < n_my; ++c) {  // c counts this CTA's chunks; gc is the chunk's index in the sequence
+        const int buf = c & 1, gc = rank + c * CS;
         unsigned char* sA = sm + (buf ? kOffA1 : kOffA0);
         unsigned char* sB = sm + (buf ? kOffB1 : kOffB0);
-        const int n = c * kChunk + tid;
+        const int n = gc * kChunk + tid;
         const bool valid = n < N;
         if (c >= 2) mbar_wait(bar_g1[buf], ((c >> 1) - 1) & 1);  // the MMAs that read this buffer two chunks ago are done
         float f[kD];
@@ -191,8 +219,8 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
         for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(sB + g * 2048 + tid * 16) = rv[g];
 #pragma unroll
         for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(sm + kOffQ + tid * 128 + ((g ^ (tid & 7)) << 4)) = rq[g];
-        if (c + 1 < n_chunks) {  // prefetch the next chunk's rows; they land while the MMAs and the statistics run
-            const int nn = n + kChunk;
+        if (c + 1 < n_my) {  // prefetch the next chunk's rows; they land while the MMAs and the statistics run
+            const int nn = n + CS * kChunk;
             const bool vn = nn < N;
             load_row<T>(gk + (int64_t)nn * A.qn, vn, rk);
             load_row<T>(gv + (int64_t)nn * A.qn, vn, rv);
@@ -202,7 +230,7 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            const int nvalid = min(kChunk, N - c * kChunk);
+            const int nvalid = min(kChunk, N - gc * kChunk);
             const int ksteps = (nvalid + 15) >> 4;  // 16 tokens per MMA; the tail inside a step is zero-padded
             for (int ks = 0; ks < ksteps; ++ks) {
                 const uint64_t da = umma_desc(smem_addr(sA) + ks * 256, 128, 2048);
@@ -212,7 +240,7 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
             umma_commit(bar_g1[buf]);
         }
         {   // online max / sum of exp over this tile's tokens: thread = (channel, half of the tokens), halves merged through smem
-            const int nvalid = min(kChunk, N - c * kChunk);
+            const int nvalid = min(kChunk, N - gc * kChunk);
             const T* col = reinterpret_cast<const T*>(sm + kOffQ);
             const int ch = tid & 63, hf = tid >> 6, g = ch >> 3, e = ch & 7;
             const int t0 = hf * 64, t1 = min(nvalid, t0 + 64);
@@ -235,13 +263,14 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
         __syncthreads();  // the q tile and the partials are reused by the next chunk
     }
     // all of GEMM1 has landed in TMEM once the last commit fires (commits complete in order)
-    {
-        const int last = n_chunks - 1;
+    if (n_my > 0) {
+        const int last = n_my - 1;
         mbar_wait(bar_g1[last & 1], (last >> 1) & 1);
         tc_fence_after();
     }
-    // ------------------------------------------------------------------ ctx' = diag(1/s) ctx -> shared (B operand of GEMM2, K-major)
-    {
+    const float* s_cmax = s_max;  // per-channel max of q over ALL tokens, used by pass 2
+    if constexpr (CS == 1) {
+        // -------------------------------------------------------------- ctx' = diag(1/s) ctx -> shared (B operand of GEMM2, K-major)
         uint32_t r0[32], r1[32];
         const uint32_t taddr = tmem_d1 + ((uint32_t)(warp * 32) << 16);
         tmem_ld32(taddr, r0);        // columns j = 0..31
@@ -257,28 +286,81 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) dst[(j + 32) * 8] = from_f<T>(__uint_as_float(r1[j]) * inv);
         }
+    } else {
+        // -------------------------------------------------------------- cluster: publish the partial ctx and the local (max, sum)
+        float* s_ctxp = reinterpret_cast<float*>(sm + kOffCtxP);
+        float* s_gmax = reinterpret_cast<float*>(sm + kOffGStat);
+        float* s_ginv = s_gmax + kD;
+        if (n_my > 0) {
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem_d1 + ((uint32_t)(warp * 32) << 16);
+            tmem_ld32(taddr, r0);
+            tmem_ld32(taddr + 32, r1);
+            if (lane < 16) {
+                float* dst = s_ctxp + (warp * 16 + lane) * kD;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[32 + j] = __uint_as_float(r1[j]);
+            }
+        } else {  // no tokens in this CTA (N <= 128 * rank): contributes zeros and (-inf, 0)
+            for (int e = tid; e < kD * kD; e += 128) s_ctxp[e] = 0.f;
+        }
+        cluster_arrive();
+        cluster_wait();  // every CTA's partials are visible cluster-wide
+        const uint32_t a_ctxp = smem_addr(s_ctxp), a_max = smem_addr(s_max), a_sum = smem_addr(s_sum);
+        if (tid < kD) {  // global statistics of channel tid: M = max_r m_r, S = sum_r s_r * exp(m_r - M)
+            float mr[CS], sr[CS], M = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < CS; ++r) {
+                mr[r] = ld_cluster_f32(map_to_rank(a_max + tid * 4, r));
+                sr[r] = ld_cluster_f32(map_to_rank(a_sum + tid * 4, r));
+                M = fmaxf(M, mr[r]);
+            }
+            float S = 0.f;
+#pragma unroll
+            for (int r = 0; r < CS; ++r) S += mr[r] == -INFINITY ? 0.f : sr[r] * __expf(mr[r] - M);
+            s_gmax[tid] = M;
+            s_ginv[tid] = 1.f / S;
+        }
+        __syncthreads();
+        {   // ctx' = diag(1/S) * sum_r ctx_r -> K-major B tile of GEMM2; consecutive threads read consecutive j (coalesced DSMEM rows)
+            uint32_t base[CS];
+#pragma unroll
+            for (int r = 0; r < CS; ++r) base[r] = map_to_rank(a_ctxp, r);
+            T* ctx = reinterpret_cast<T*>(sm + kOffCtx);
+            for (int e = tid; e < kD * kD; e += 128) {
+                const int i = e >> 6, j = e & 63;
+                float v = 0.f;
+#pragma unroll
+                for (int r = 0; r < CS; ++r) v += ld_cluster_f32(base[r] + e * 4);
+                ctx[(i >> 3) * 512 + j * 8 + (i & 7)] = from_f<T>(v * s_ginv[i]);
+            }
+        }
+        cluster_arrive();  // second phase: this CTA no longer reads remote memory; matched by the wait before exit
+        s_cmax = s_gmax;
     }
     tc_fence_before();
     __syncthreads();
 
     // ------------------------------------------------------------------ pass 2: y = exp(q - max) ctx'
     T* gy = reinterpret_cast<T*>(A.y) + (int64_t)b * A.yb + head * kD;
-    load_row<T>(gq + (int64_t)tid * A.qn, tid < N, rq);
-    for (int c = 0; c < n_chunks; ++c) {
+    load_row<T>(gq + (int64_t)(rank * kChunk + tid) * A.qn, rank * kChunk + tid < N, rq);
+    for (int c = 0; c < n_my; ++c) {
         unsigned char* sP = sm + ((c & 1) ? kOffA1 : kOffA0);
-        const int n = c * kChunk + tid;
+        const int n = (rank + c * CS) * kChunk + tid;
         const bool valid = n < N;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             float t8[8];
             unpack<T>(rq[g], t8);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) t8[e] = valid ? __expf(t8[e] - s_max[8 * g + e]) : 0.f;
+            for (int e = 0; e < 8; ++e) t8[e] = valid ? __expf(t8[e] - s_cmax[8 * g + e]) : 0.f;
             uint4 o;
             o.x = pack2<T>(t8[0], t8[1]); o.y = pack2<T>(t8[2], t8[3]); o.z = pack2<T>(t8[4], t8[5]); o.w = pack2<T>(t8[6], t8[7]);
             *reinterpret_cast<uint4*>(sP + g * 2048 + tid * 16) = o;  // row = token, 16 B chunk g of the K dim
         }
-        if (c + 1 < n_chunks) load_row<T>(gq + (int64_t)(n + kChunk) * A.qn, n + kChunk < N, rq);  // next chunk's q rows (L2 hits)
+        if (c + 1 < n_my) load_row<T>(gq + (int64_t)(n + CS * kChunk) * A.qn, n + CS * kChunk < N, rq);  // next chunk's q rows (L2 hits)
         proxy_fence();
         __syncthreads();
         if (tid == 0) {
@@ -317,6 +399,7 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
         __syncthreads();  // D2 has been drained: the next chunk's MMA may overwrite it
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
+    if constexpr (CS > 1) cluster_wait();  // no CTA of the cluster exits while a peer may still read its shared memory
 }
 
 }  // namespace tc
@@ -329,13 +412,36 @@ bool linattn_tc_supported(const AttnArgs& A, int dtype) {
     return aligned16(A.qkv) && aligned16(A.y) && A.qn % 8 == 0 && A.qb % 8 == 0 && A.yn % 8 == 0 && A.yb % 8 == 0;
 }
 
+template <typename T, int CS>
+static void launch_one(const AttnArgs& A, int B, cudaStream_t s) {
+    const uint32_t smem = CS > 1 ? tc::kSmemBytesCluster : tc::kSmemBytes;
+    cudaFuncSetAttribute(tc::linattn_tc_kernel<T, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * A.heads * CS));
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CS > 1 ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, tc::linattn_tc_kernel<T, CS>, A);
+}
+
 int linattn_tc_launch(const AttnArgs& A, int B, int dtype, cudaStream_t s) {
+    // One CTA per (image, head).  EL_LINATTN_CLUSTER=1 selects the 4-CTA cluster variant that splits the tokens: built to fill the GPU when
+    // B * heads < 148 (configs[1]: 128 problems of 4 chunks), parity-tested, but MEASURED SLOWER there (54.1 vs 45.4 us): four times the
+    // CTAs each pay the fixed costs (TMEM allocation, barrier init, two cluster barriers, 64 KB of DSMEM reads for the ctx sum) that
+    // already dominate this latency-bound kernel.
+    static const int mode = [] { const char* v = getenv("EL_LINATTN_CLUSTER"); return v ? atoi(v) : 0; }();
+    const bool cluster = mode != 0;
     if (dtype == EL_BF16) {
-        cudaFuncSetAttribute(tc::linattn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
-        tc::linattn_tc_kernel<__nv_bfloat16><<<B * A.heads, 128, tc::kSmemBytes, s>>>(A);
+        if (cluster) launch_one<__nv_bfloat16, 4>(A, B, s);
+        else launch_one<__nv_bfloat16, 1>(A, B, s);
     } else {
-        cudaFuncSetAttribute(tc::linattn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes);
-        tc::linattn_tc_kernel<__half><<<B * A.heads, 128, tc::kSmemBytes, s>>>(A);
+        if (cluster) launch_one<__half, 4>(A, B, s);
+        else launch_one<__half, 1>(A, B, s);
     }
     note_launches(1);
     return check_launch();

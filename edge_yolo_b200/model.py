@@ -188,9 +188,9 @@ def _dw_eligible(conv: nn.Conv2d, epilogue: bool = False) -> bool:
     C = conv.in_channels
     if not M.USE_DWCONV or not (epilogue or k >= 5 or M.DWCONV_K3):
         return False
-    C8 = C // 8
-    return (C % 8 == 0 and (C8 & (C8 - 1) == 0 or C % 64 == 0) and conv.groups == C == conv.out_channels and C > 1 and conv.kernel_size == (k, k) and k in (3, 5, 7) and conv.stride == (1, 1)
-            and conv.dilation == (1, 1) and conv.padding == (k // 2, k // 2) and C % 8 == 0 and (C <= 64 or C % 64 == 0))
+    # any multiple of 8 channels: the kernel blocks the channel vectors by their largest divisor <= 8 (80-channel class towers: 5)
+    return (C % 8 == 0 and conv.groups == C == conv.out_channels and C > 1 and conv.kernel_size == (k, k) and k in (3, 5, 7) and conv.stride == (1, 1)
+            and conv.dilation == (1, 1) and conv.padding == (k // 2, k // 2))
 
 
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:

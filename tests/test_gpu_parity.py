@@ -487,7 +487,8 @@ def test_stem_conv_u8(dtype, tol, c0, hw):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("k", [3, 5, 7])
-@pytest.mark.parametrize("shape,epi", [((2, 16, 40, 52), False), ((3, 8, 9, 7), True), ((2, 64, 20, 20), True), ((1, 128, 11, 13), False)])
+@pytest.mark.parametrize("shape,epi", [((2, 16, 40, 52), False), ((3, 8, 9, 7), True), ((2, 64, 20, 20), True), ((1, 128, 11, 13), False),
+                                       ((2, 80, 24, 20), True), ((1, 48, 17, 33), False), ((1, 24, 12, 9), True)])  # 10 / 6 / 3 channel vectors: blocked by 5 / 6 / 3
 def test_dwconv(dtype, tol, k, shape, epi):
     """Depthwise k x k conv (+ bias + SiLU) over NHWC views (DSConv.dw / DWConv, nn/modules/conv.py:87-112) vs torch fp64."""
     gen = torch.Generator().manual_seed(k * 100 + shape[1])
