@@ -70,7 +70,10 @@ def wavelet_enhancer_engine_forward(self, b: torch.Tensor) -> torch.Tensor:
     buf = ops.dwt_haar(b)
     LLp = self.f_ll(buf[:B])
     hp = self.f_h(buf[B:])
-    U = ops.wave_merge_bands(LLp, hp[:B], hp[B : 2 * B], hp[2 * B :], self.alpha, H, W)
+    a32 = self.__dict__.get("el_alpha32")  # fp32 copy of alpha for the kernel, cached until alpha is modified (a 16-bit model would
+    if a32 is None or a32[0] != self.alpha._version or a32[1].device != self.alpha.device:  # otherwise launch a cast kernel per call)
+        a32 = self.el_alpha32 = (self.alpha._version, self.alpha.detach().float().contiguous())
+    U = ops.wave_merge_bands(LLp, hp[:B], hp[B : 2 * B], hp[2 * B :], a32[1], H, W)
     gate = self.__dict__.get("el_gate")
     if gate is None or gate[0] != self.gamma._version:  # tanh(gamma) as a host scalar, cached until gamma is modified
         gate = self.el_gate = (self.gamma._version, float(torch.tanh(self.gamma.detach().float())))
