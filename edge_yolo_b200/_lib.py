@@ -56,6 +56,8 @@ _SIGNATURES = {
     "el_qfl_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "el_dfl_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "el_dfl_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "el_box_iou": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "el_match_predictions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "el_ingest_u8": (c_int, [c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_void_p]),
     "el_stem_conv_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_bias_act_fwd": (c_int, [c_void_p, I64P, c_void_p, c_void_p, I64P, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int,

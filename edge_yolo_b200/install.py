@@ -17,6 +17,9 @@ What is replaced (reference path -> ours):
     utils/loss.py        quality_focal_loss, QualityFocalLoss.forward, distribution_focal_loss, DFLoss.__call__
                                                       -> loss.*
                          v8DetectionLoss (also the name bound in nn/tasks.py) -> detection_loss.v8DetectionLoss
+    (metrics=True)
+    utils/metrics.py     box_iou (also the name imported by models/yolo/detect/val.py) -> metrics.box_iou
+    engine/validator.py  BaseValidator.match_predictions (non-scipy branch)           -> metrics.match_predictions
 There is no CPU fallback: after install() these functions need CUDA tensors.
 """
 from __future__ import annotations
@@ -33,7 +36,17 @@ def _swap(obj, name, new):
     setattr(obj, name, new)
 
 
-def install(nms: bool = True, modules: bool = True, losses: bool = True, criterion: bool = True):
+def _validator_match_predictions(self, pred_classes, true_classes, iou, use_scipy=False):
+    """`BaseValidator.match_predictions` (engine/validator.py:222-262); the scipy branch stays the reference's."""
+    from . import metrics
+
+    if use_scipy:
+        orig = next(v for (obj, name), v in _ORIGINALS.items() if name == "match_predictions")
+        return orig(self, pred_classes, true_classes, iou, use_scipy=True)
+    return metrics.match_predictions(pred_classes, true_classes, iou, self.iouv)
+
+
+def install(nms: bool = True, modules: bool = True, losses: bool = True, criterion: bool = True, metrics: bool = False):
     """Patch the imported `ultralytics` package in place.  Returns the list of patched names."""
     from . import _lib, detection_loss as el_det, loss as el_loss, modules as M, nms as el_nms
 
@@ -65,6 +78,16 @@ def install(nms: bool = True, modules: bool = True, losses: bool = True, criteri
         _swap(uloss, "v8DetectionLoss", el_det.v8DetectionLoss)
         _swap(tasks, "v8DetectionLoss", el_det.v8DetectionLoss)
         done += ["utils.loss.v8DetectionLoss", "nn.tasks.v8DetectionLoss"]
+    if metrics:  # validator metrics on the device (opt-in: `val` then needs its predictions and labels on the GPU, which they are)
+        from . import metrics as el_metrics
+
+        umetrics = importlib.import_module("ultralytics.utils.metrics")
+        dval = importlib.import_module("ultralytics.models.yolo.detect.val")
+        validator = importlib.import_module("ultralytics.engine.validator")
+        _swap(umetrics, "box_iou", el_metrics.box_iou)
+        _swap(dval, "box_iou", el_metrics.box_iou)
+        _swap(validator.BaseValidator, "match_predictions", _validator_match_predictions)
+        done += ["utils.metrics.box_iou", "models.yolo.detect.val.box_iou", "engine.validator.BaseValidator.match_predictions"]
     return done
 
 

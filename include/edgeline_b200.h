@@ -242,6 +242,16 @@ int el_conv3x3_fwd(const void* x, const int64_t xs[4], int C, const void* wpk, c
 int el_sppf_pool_fwd(const void* x, const int64_t xs[4], void* out, const int64_t os[4], int B, int C,
                      int H, int W, int dtype, void* stream);
 
+/* ---- 8f-4. validator metrics: box_iou (utils/metrics.py:55-71) and DetectionValidator.match_predictions, non-scipy branch
+ * (engine/validator.py:222-262) --------------------------------------------------------------------------------------------
+ * el_box_iou: box1 (N rows of 4 floats, row pitch stride1 elements, xyxy), box2 (M rows) -> out (N, M) dense fp32,
+ *   inter / (area1 + area2 - inter + eps) in fp32, evaluated left to right like the reference.
+ * el_match_predictions: iou (L labels x D detections, dense row-major, as the validator passes it), pred_cls (D), true_cls (L),
+ *   iouv (T <= 16 thresholds, device) -> correct (D, T) bytes 0/1.  One image per call; no host synchronisation. */
+int el_box_iou(const float* box1, int64_t stride1, const float* box2, int64_t stride2, float* out, int N, int M, float eps, void* stream);
+int el_match_predictions(const float* iou, const float* pred_cls, const float* true_cls, const float* iouv, int L, int D, int T,
+                         uint8_t* correct, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

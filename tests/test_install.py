@@ -78,3 +78,26 @@ def test_module_constructor_signatures_match_reference():
         a, b = inspect.signature(ref_cls.__init__), inspect.signature(mine.__init__)
         assert list(a.parameters) == list(b.parameters), ref_cls.__name__
         assert [p.default for p in a.parameters.values()] == [p.default for p in b.parameters.values()], ref_cls.__name__
+
+
+def test_install_metrics_opt_in_round_trip():
+    """metrics=True additionally rebinds box_iou and BaseValidator.match_predictions with the reference's signatures."""
+    ref_loader.load()
+    import ultralytics.engine.validator as validator
+    import ultralytics.models.yolo.detect.val as dval
+    import ultralytics.utils.metrics as umetrics
+
+    import edge_yolo_b200.install as el
+    from edge_yolo_b200 import metrics as el_metrics
+
+    o_iou, o_match = umetrics.box_iou, validator.BaseValidator.match_predictions
+    assert list(inspect.signature(el_metrics.box_iou).parameters) == list(inspect.signature(o_iou).parameters)
+    names = el.install(metrics=True)
+    try:
+        assert len(names) == 15
+        assert umetrics.box_iou is el_metrics.box_iou and dval.box_iou is el_metrics.box_iou
+        assert list(inspect.signature(validator.BaseValidator.match_predictions).parameters) == list(inspect.signature(o_match).parameters)
+        assert dval.DetectionValidator.match_predictions is validator.BaseValidator.match_predictions
+    finally:
+        el.uninstall()
+    assert umetrics.box_iou is o_iou and validator.BaseValidator.match_predictions is o_match and dval.box_iou is o_iou
