@@ -9,18 +9,70 @@ namespace el {
 constexpr int kQflThreads = 256;
 constexpr int kQflPerThread = 4;
 
+// sigmoid and softplus share one exponential: e = exp(-|x|) in (0, 1];  sigmoid = 1/(1+e) (x >= 0) or e/(1+e);  softplus(-|x|) = log1p(e)
 __device__ __forceinline__ void qfl_terms(float x, float t, float beta, float& p, float& bce, float& diff, float& scale) {
-    p = 1.f / (1.f + expf(-x));
-    bce = fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));  // binary_cross_entropy_with_logits
+    const float e = expf(-fabsf(x));
+    const float inv = 1.f / (1.f + e);
+    p = x >= 0.f ? inv : e * inv;
+    bce = fmaxf(x, 0.f) - x * t + log1pf(e);                // binary_cross_entropy_with_logits
     diff = t > 0.f ? fabsf(t - p) : p;                      // loss.py:57-61
     scale = beta == 2.f ? diff * diff : powf(diff, beta);
 }
 
-template <typename T>
+// four consecutive logits of type T as one 16-byte (fp32) or 8-byte (16-bit) access
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&f)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&f)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void load4<__half>(const __half* p, float (&f)[4]) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const float (&f)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&f)[4]) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, const float (&f)[4]) {
+    __half2 a = __floats2half2_rn(f[0], f[1]), b = __floats2half2_rn(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+// VEC: every pointer is 16-byte aligned -> groups of four elements per thread and iteration (128-bit target / loss accesses), the
+// n % 4 tail goes through the scalar loop.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(kQflThreads) qfl_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ target, int64_t n, float beta,
                                                               float* __restrict__ loss, float* __restrict__ partials) {
     float acc = 0.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    int64_t done = 0;
+    if constexpr (VEC) {
+        const int64_t n4 = n >> 2;
+        for (int64_t q = tid0; q < n4; q += nthr) {
+            float x[4], l[4];
+            load4<T>(pred + 4 * q, x);
+            const float4 t = *reinterpret_cast<const float4*>(target + 4 * q);
+            const float tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float p, bce, diff, scale;
+                qfl_terms(x[k], tt[k], beta, p, bce, diff, scale);
+                l[k] = bce * scale;
+            }
+            if (loss) *reinterpret_cast<float4*>(loss + 4 * q) = make_float4(l[0], l[1], l[2], l[3]);
+            acc += (l[0] + l[1]) + (l[2] + l[3]);
+        }
+        done = n4 << 2;
+    }
+    for (int64_t i = done + tid0; i < n; i += nthr) {
         float p, bce, diff, scale;
         qfl_terms(to_f(pred[i]), target[i], beta, p, bce, diff, scale);
         float l = bce * scale;
@@ -54,21 +106,37 @@ __global__ void __launch_bounds__(256) sum_partials(const float* __restrict__ pa
     }
 }
 
-template <typename T>
+__device__ __forceinline__ float qfl_grad(float x, float t, float beta) {
+    float p, bce, diff, scale;
+    qfl_terms(x, t, beta, p, bce, diff, scale);
+    // d scale / dx: the modulating factor is not detached in the reference (autograd flows through it)
+    float sgn = 1.f;
+    if (t > 0.f) { float d = t - p; sgn = d > 0.f ? -1.f : (d < 0.f ? 1.f : 0.f); }
+    float dpow = beta == 2.f ? 2.f * diff : beta * powf(diff, beta - 1.f);
+    return (p - t) * scale + bce * dpow * sgn * p * (1.f - p);
+}
+
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(kQflThreads) qfl_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ target, int64_t n, float beta,
                                                               const float* __restrict__ gout, const float* __restrict__ gscalar, T* __restrict__ gpred) {
     const float gs = gscalar ? __ldg(gscalar) : 1.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float x = to_f(pred[i]), t = target[i];
-        float p, bce, diff, scale;
-        qfl_terms(x, t, beta, p, bce, diff, scale);
-        // d scale / dx: the modulating factor is not detached in the reference (autograd flows through it)
-        float sgn = 1.f;
-        if (t > 0.f) { float d = t - p; sgn = d > 0.f ? -1.f : (d < 0.f ? 1.f : 0.f); }
-        float dpow = beta == 2.f ? 2.f * diff : beta * powf(diff, beta - 1.f);
-        float g = (p - t) * scale + bce * dpow * sgn * p * (1.f - p);
-        gpred[i] = from_f<T>(g * (gout ? gout[i] : gs));
+    const int64_t tid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    int64_t done = 0;
+    if constexpr (VEC) {
+        const int64_t n4 = n >> 2;
+        for (int64_t q = tid0; q < n4; q += nthr) {
+            float x[4], g[4];
+            load4<T>(pred + 4 * q, x);
+            const float4 t = *reinterpret_cast<const float4*>(target + 4 * q);
+            float4 go = make_float4(gs, gs, gs, gs);
+            if (gout) go = *reinterpret_cast<const float4*>(gout + 4 * q);
+            g[0] = qfl_grad(x[0], t.x, beta) * go.x; g[1] = qfl_grad(x[1], t.y, beta) * go.y;
+            g[2] = qfl_grad(x[2], t.z, beta) * go.z; g[3] = qfl_grad(x[3], t.w, beta) * go.w;
+            store4<T>(gpred + 4 * q, g);
+        }
+        done = n4 << 2;
     }
+    for (int64_t i = done + tid0; i < n; i += nthr) gpred[i] = from_f<T>(qfl_grad(to_f(pred[i]), target[i], beta) * (gout ? gout[i] : gs));
 }
 
 // ------------------------------------------------------------------------------------- DFL
@@ -163,7 +231,11 @@ extern "C" int el_qfl_fwd(const void* pred, const float* target, int64_t n, floa
     if (!pred || !target || n <= 0 || (!loss && !loss_sum) || (loss_sum && !partials)) return EL_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = qfl_grid(n);
-    EL_DISPATCH_DTYPE(dtype, { qfl_fwd_kernel<T><<<grid, kQflThreads, 0, s>>>((const T*)pred, target, n, beta, loss, loss_sum ? partials : nullptr); });
+    const bool vec = aligned16(pred) && aligned16(target) && (!loss || aligned16(loss));
+    EL_DISPATCH_DTYPE(dtype, {
+        if (vec) qfl_fwd_kernel<T, true><<<grid, kQflThreads, 0, s>>>((const T*)pred, target, n, beta, loss, loss_sum ? partials : nullptr);
+        else qfl_fwd_kernel<T, false><<<grid, kQflThreads, 0, s>>>((const T*)pred, target, n, beta, loss, loss_sum ? partials : nullptr);
+    });
     if (loss_sum) sum_partials<<<1, 256, 0, s>>>(partials, grid, loss_sum);
     note_launches(loss_sum ? 2 : 1);
     return check_launch();
@@ -173,7 +245,11 @@ extern "C" int el_qfl_bwd(const void* pred, const float* target, int64_t n, floa
                           void* stream) {
     if (!pred || !target || !gpred || n <= 0 || ((gout == nullptr) == (gscalar == nullptr))) return EL_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    EL_DISPATCH_DTYPE(dtype, { qfl_bwd_kernel<T><<<qfl_grid(n), kQflThreads, 0, s>>>((const T*)pred, target, n, beta, gout, gscalar, (T*)gpred); });
+    const bool vec = aligned16(pred) && aligned16(target) && aligned16(gpred) && (!gout || aligned16(gout));
+    EL_DISPATCH_DTYPE(dtype, {
+        if (vec) qfl_bwd_kernel<T, true><<<qfl_grid(n), kQflThreads, 0, s>>>((const T*)pred, target, n, beta, gout, gscalar, (T*)gpred);
+        else qfl_bwd_kernel<T, false><<<qfl_grid(n), kQflThreads, 0, s>>>((const T*)pred, target, n, beta, gout, gscalar, (T*)gpred);
+    });
     note_launches(1);
     return check_launch();
 }
