@@ -13,6 +13,7 @@ What is replaced (reference path -> ours):
                          _WaveletEnhancer.forward    -> modules.wavelet_enhancer_forward
                          LinearAttention.forward     -> modules.linear_attention_forward
     nn/modules/head.py   GFLHeadv2_uniH.forward      -> modules.gfl_head_forward
+    nn/modules/conv.py   WTConv2d.forward            -> modules.WTConv2d.forward (Haar analysis / synthesis on the DWT kernels)
     utils/ops.py         non_max_suppression         -> nms.non_max_suppression
     utils/loss.py        quality_focal_loss, QualityFocalLoss.forward, distribution_focal_loss, DFLoss.__call__
                                                       -> loss.*
@@ -61,7 +62,10 @@ def install(nms: bool = True, modules: bool = True, losses: bool = True, criteri
         _swap(block._WaveletEnhancer, "forward", M.wavelet_enhancer_forward)
         _swap(block.LinearAttention, "forward", M.linear_attention_forward)
         _swap(head.GFLHeadv2_uniH, "forward", M.gfl_head_forward)
-        done += ["block._PywtDWT2D.forward", "block._WaveletEnhancer.forward", "block.LinearAttention.forward", "head.GFLHeadv2_uniH.forward"]
+        conv = importlib.import_module("ultralytics.nn.modules.conv")
+        _swap(conv.WTConv2d, "forward", M.WTConv2d.forward)
+        done += ["block._PywtDWT2D.forward", "block._WaveletEnhancer.forward", "block.LinearAttention.forward", "head.GFLHeadv2_uniH.forward",
+                 "conv.WTConv2d.forward"]
     if nms:
         _swap(uops, "non_max_suppression", el_nms.non_max_suppression)
         done.append("utils.ops.non_max_suppression")

@@ -464,6 +464,67 @@ class DWConv(Conv):
         super().__init__(c1, c2, k, s, g=math.gcd(c1, c2), d=d, act=act)
 
 
+class _ScaleModule(nn.Module):
+    """conv.py:448-461: a learnable per-channel scale (state-dict key `weight`)."""
+
+    def __init__(self, dims, init_scale=1.0, init_bias=0):
+        super().__init__()
+        self.dims = dims
+        self.weight = nn.Parameter(torch.ones(*dims) * init_scale)
+        self.bias = None
+
+    def forward(self, x):
+        return torch.mul(self.weight, x)
+
+
+class WTConv2d(nn.Module):
+    """conv.py:463-598: depthwise conv + multi-level wavelet branch.  Same constructor, parameter names and state-dict
+    keys (`wt_filter`, `iwt_filter`, `base_conv.*`, `base_scale.weight`, `wavelet_convs.i.weight`, `wavelet_scale.i.weight`).  The
+    analysis / synthesis (the reference's grouped stride-2 conv and transposed conv with a repeated filter bank) run on
+    `el_dwt_haar_fwd` / `el_dwt_haar_bwd` directly in the module's (B, C, 4, h, w) coefficient layout; the depthwise convolutions stay
+    on cuDNN on this API path.  Only the Haar bank (`db1` / `haar`, the only one the reference's yamls use) is implemented."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=5, stride=1, bias=True, wt_levels=1, wt_type="db1"):
+        super().__init__()
+        assert in_channels == out_channels, "WTConv2d needs in_channels == out_channels"
+        if wt_type not in ("db1", "haar"):
+            raise NotImplementedError(f"WTConv2d: only the Haar filter bank (db1) has a kernel, got {wt_type!r}")
+        self.in_channels, self.wt_levels, self.stride, self.dilation = in_channels, wt_levels, stride, 1
+        s = torch.tensor(2.0 ** -0.5, dtype=torch.float32)
+        lo, hi = torch.stack((s, s)), torch.stack((s, -s))  # reversed decomposition taps = reconstruction taps for Haar
+        bank = torch.stack([lo.unsqueeze(0) * lo.unsqueeze(1), lo.unsqueeze(0) * hi.unsqueeze(1),
+                            hi.unsqueeze(0) * lo.unsqueeze(1), hi.unsqueeze(0) * hi.unsqueeze(1)], 0)[:, None].repeat(in_channels, 1, 1, 1)
+        self.wt_filter = nn.Parameter(bank.clone(), requires_grad=False)   # kept for state-dict compatibility; the kernels hold the taps
+        self.iwt_filter = nn.Parameter(bank.clone(), requires_grad=False)
+        pad = autopad(kernel_size, None, 1)
+        self.base_conv = nn.Conv2d(in_channels, in_channels, kernel_size, 1, pad, 1, groups=in_channels, bias=bias)
+        self.base_scale = _ScaleModule([1, in_channels, 1, 1])
+        self.wavelet_convs = nn.ModuleList(
+            [nn.Conv2d(in_channels * 4, in_channels * 4, kernel_size, 1, pad, 1, groups=in_channels * 4, bias=False) for _ in range(wt_levels)])
+        self.wavelet_scale = nn.ModuleList([_ScaleModule([1, in_channels * 4, 1, 1], init_scale=0.1) for _ in range(wt_levels)])
+        self.do_stride = nn.AvgPool2d(kernel_size=1, stride=stride) if stride > 1 else None
+
+    def forward(self, x):
+        lls, highs, shapes = [], [], []
+        cur = x
+        for i in range(self.wt_levels):
+            shapes.append(cur.shape)
+            if cur.shape[2] % 2 or cur.shape[3] % 2:  # odd sizes: zero pad right / bottom (conv.py:556-558)
+                cur = F.pad(cur, (0, cur.shape[3] % 2, 0, cur.shape[2] % 2))
+            coeffs = ops.wavelet_2d_transform(cur.contiguous())              # (B, C, 4, h, w)
+            b, c, _, hh, ww = coeffs.shape
+            cur = coeffs[:, :, 0]                                             # raw LL feeds the next level
+            tag = self.wavelet_scale[i](self.wavelet_convs[i](coeffs.reshape(b, c * 4, hh, ww))).reshape(b, c, 4, hh, ww)
+            lls.append(tag[:, :, 0])
+            highs.append(tag[:, :, 1:4])
+        nxt = 0
+        for i in range(self.wt_levels - 1, -1, -1):
+            ll, hi, shp = lls.pop() + nxt, highs.pop(), shapes.pop()
+            nxt = ops.inverse_2d_wavelet_transform(torch.cat([ll.unsqueeze(2), hi], 2))[:, :, : shp[2], : shp[3]]
+        y = self.base_scale(self.base_conv(x)) + nxt
+        return self.do_stride(y) if self.do_stride is not None else y
+
+
 class DSConv(nn.Module):
     """Depthwise-separable conv with its own BatchNorm (conv.py:87-104); keys `dw`, `pw`, `bn`."""
 

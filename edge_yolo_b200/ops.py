@@ -113,6 +113,72 @@ def idwt_haar(bands: torch.Tensor, H: int, W: int) -> torch.Tensor:
     return _dwt_bwd(bands, like)
 
 
+# ----------------------------------------------------------- DWT / IDWT in WTConv2d's coefficient layout
+# wavelet_2d_transform / inverse_2d_wavelet_transform (nn/modules/conv.py:430-443) keep the coefficients as (B, C, 4, H/2, W/2) with the
+# sub-bands ordered (LL, [[+,+],[-,-]], [[+,-],[+,-]], HH): bands 1 and 2 swapped with respect to `_PywtDWT2D`.  The kernels take
+# arbitrary element strides, so the same two entry points serve this layout: the analysis of the TRANSPOSED image yields exactly the
+# swapped order, and the (band, B, C, h, w) stride table points straight into the 5-D tensor -- no permute / copy kernels.
+def _coeff_view(coeffs: torch.Tensor):
+    """(B, C, 4, h, w) tensor -> stride table {band, n, c, h', w'} of its transposed-image view (h' runs over w)."""
+    sb, sc, s4, sh, sw = coeffs.stride()
+    return (s4, sb, sc, sw, sh)
+
+
+def _dwt_coeffs_fwd(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    B, C, H, W = x.shape
+    coeffs = torch.empty((B, C, 4, H // 2, W // 2), device=x.device, dtype=x.dtype)
+    if coeffs.numel():
+        sn, sc, sh, sw = x.stride()
+        check(_lib.lib().el_dwt_haar_fwd(x.data_ptr(), _i64((sn, sc, sw, sh)), coeffs.data_ptr(), _i64(_coeff_view(coeffs)),
+                                         B, C, W, H, _dt(x), _stream()), "el_dwt_haar_fwd")
+    return coeffs
+
+
+def _dwt_coeffs_bwd(coeffs: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    _need_cuda(coeffs)
+    B, C = coeffs.shape[:2]
+    out = torch.empty((B, C, H, W), device=coeffs.device, dtype=coeffs.dtype)
+    sn, sc, sh, sw = out.stride()
+    check(_lib.lib().el_dwt_haar_bwd(coeffs.data_ptr(), _i64(_coeff_view(coeffs)), out.data_ptr(), _i64((sn, sc, sw, sh)),
+                                     B, C, W, H, _dt(coeffs), _stream()), "el_dwt_haar_bwd")
+    return out
+
+
+class _DWTCoeffs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = x.shape[-2:]
+        return _dwt_coeffs_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _dwt_coeffs_bwd(g.contiguous(), *ctx.hw)  # the synthesis is the adjoint of the analysis
+
+
+class _IDWTCoeffs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coeffs):
+        return _dwt_coeffs_bwd(coeffs, 2 * coeffs.shape[-2], 2 * coeffs.shape[-1])
+
+    @staticmethod
+    def backward(ctx, g):
+        return _dwt_coeffs_fwd(g.contiguous())
+
+
+def wavelet_2d_transform(x: torch.Tensor) -> torch.Tensor:
+    """Haar case of `wavelet_2d_transform` (conv.py:430-435): (B,C,H,W), H and W even -> (B, C, 4, H/2, W/2)."""
+    if x.shape[-1] % 2 or x.shape[-2] % 2:
+        raise EdgelineError("wavelet_2d_transform: even H and W expected (WTConv2d pads odd sizes first)")
+    return _DWTCoeffs.apply(x) if x.requires_grad and torch.is_grad_enabled() else _dwt_coeffs_fwd(x)
+
+
+def inverse_2d_wavelet_transform(coeffs: torch.Tensor) -> torch.Tensor:
+    """Haar case of `inverse_2d_wavelet_transform` (conv.py:438-443): (B, C, 4, h, w) -> (B, C, 2h, 2w)."""
+    coeffs = coeffs.contiguous()
+    return _IDWTCoeffs.apply(coeffs) if coeffs.requires_grad and torch.is_grad_enabled() else _dwt_coeffs_bwd(coeffs, 2 * coeffs.shape[-2], 2 * coeffs.shape[-1])
+
+
 # ---------------------------------------------------------------------------------- merge
 def _merge_fwd(b, bands, alpha):
     _need_cuda(b, alpha, *bands)

@@ -51,6 +51,37 @@ def dwt_haar_adjoint(gLL, gLH, gHL, gHH, H: int, W: int):
     return g
 
 
+def wtconv2d(x, base_w, base_b, base_scale, wave_w, wave_scale, stride: int = 1):
+    """WTConv2d.forward, nn/modules/conv.py:540-598 (db1 = Haar), SURVEY 8f-3.  `wave_w[i]` (4C,1,k,k) / `wave_scale[i]` (1,4C,1,1) per level.
+
+    The module's filter bank (create_2d_wavelet_filter, conv.py:408-428) orders the sub-bands (LL, [[+,+],[-,-]], [[+,-],[+,-]], HH),
+    i.e. bands 1 and 2 swapped with respect to `_PywtDWT2D`; channel index of the depthwise conv = c * 4 + band.  Odd sizes are zero
+    padded at the right / bottom before each analysis and cropped after the synthesis; the synthesis is the adjoint of the analysis.
+    """
+    import torch.nn.functional as F
+
+    k = base_w.shape[-1]
+    lls, highs, shapes = [], [], []
+    cur = x
+    for w, sc in zip(wave_w, wave_scale):
+        shapes.append(cur.shape)
+        if cur.shape[2] % 2 or cur.shape[3] % 2:
+            cur = F.pad(cur, (0, cur.shape[3] % 2, 0, cur.shape[2] % 2))
+        LL, LH, HL, HH = dwt_haar(cur)
+        B, C, h, w_ = LL.shape
+        t = torch.stack((LL, HL, LH, HH), 2).reshape(B, 4 * C, h, w_)
+        t = (F.conv2d(t, w, None, padding=k // 2, groups=4 * C) * sc).reshape(B, C, 4, h, w_)
+        lls.append(t[:, :, 0])
+        highs.append(t[:, :, 1:])
+        cur = LL
+    nxt = 0
+    for _ in range(len(wave_w)):
+        ll, hi, shp = lls.pop() + nxt, highs.pop(), shapes.pop()
+        nxt = dwt_haar_adjoint(ll, hi[:, :, 1], hi[:, :, 0], hi[:, :, 2], 2 * ll.shape[-2], 2 * ll.shape[-1])[:, :, : shp[2], : shp[3]]
+    y = F.conv2d(x, base_w, base_b, padding=k // 2, groups=x.shape[1]) * base_scale + nxt
+    return y[:, :, ::stride, ::stride] if stride > 1 else y
+
+
 # ------------------------------------------------------------------------- a2: merge
 def _bilinear_axis(n_in: int, n_out: int):
     """PyTorch `align_corners=False` source index rule used by F.interpolate (block.py:3681-3683)."""

@@ -26,7 +26,7 @@ _STUBBED = ("matplotlib", "pywt", "thop", "seaborn")
 
 class _Wavelet:
     def __init__(self, name):
-        if name != "haar":
+        if name not in ("haar", "db1"):  # PyWavelets: db1 is the Haar wavelet (WTConv2d's default wt_type, conv.py:487)
             raise ValueError("stub pywt only provides the Haar wavelet")
         s = 1.0 / math.sqrt(2.0)
         self.dec_lo, self.dec_hi = [s, s], [-s, s]

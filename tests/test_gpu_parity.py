@@ -861,3 +861,42 @@ def test_training_step_through_custom_ops():
                 assert cos > 0.998, (k, cos)
             checked += 1
     assert checked >= 20
+
+
+# ------------------------------------------------------------------------------ WTConv2d / IDWT
+@pytest.mark.parametrize("name", ["l1", "odd_l2", "l3_s2_k3"])
+def test_wtconv2d_golden(golden, name):
+    """WTConv2d (multi-level Haar analysis / synthesis on the DWT kernels in the module's coefficient layout) against outputs of the
+    unmodified reference module, loaded through the reference's own state dict."""
+    from edge_yolo_b200 import modules as M
+
+    g = golden("wtconv")
+    sd = {k[len(name) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(f"{name}_sd_")}
+    k, lv, st = (int(v) for v in g[f"{name}_cfg"])
+    x = torch.from_numpy(g[f"{name}_x"])
+    m = M.WTConv2d(x.shape[1], x.shape[1], kernel_size=k, stride=st, wt_levels=lv)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    assert torch.equal(m.wt_filter, sd["wt_filter"]) and torch.equal(m.iwt_filter, sd["iwt_filter"])  # the module's own bank == pywt's db1
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        y = m(x.to(DEV))
+    close(y, g[f"{name}_y"], 1e-5, 1e-5)
+
+
+def test_wavelet_transform_coefficient_layout_roundtrip_and_grad():
+    """wavelet_2d_transform / inverse_2d_wavelet_transform (conv.py:430-443): band order of the module's filter bank, perfect
+    reconstruction, and autograd (the synthesis is the adjoint of the analysis)."""
+    x = torch.randn(3, 6, 10, 14, device=DEV, requires_grad=True)
+    c = ops().wavelet_2d_transform(x)
+    LL, LH, HL, HH = O.dwt_haar(x.detach().cpu())
+    close(c[:, :, 0], LL, 1e-6, 1e-6)
+    close(c[:, :, 1], HL, 1e-6, 1e-6)   # [[+,+],[-,-]]
+    close(c[:, :, 2], LH, 1e-6, 1e-6)   # [[+,-],[+,-]]
+    close(c[:, :, 3], HH, 1e-6, 1e-6)
+    r = ops().inverse_2d_wavelet_transform(c)
+    close(r, x, 1e-5, 1e-6)
+    w = torch.randn_like(r)
+    (r * w).sum().backward()
+    close(x.grad, w, 1e-5, 1e-6)  # d/dx sum(w * IDWT(DWT(x))) = w for an orthonormal transform

@@ -27,7 +27,7 @@ def test_install_and_uninstall_round_trip():
     ref_sig = inspect.signature(uops.non_max_suppression)
     names = el.install()
     try:
-        assert len(names) == 12
+        assert len(names) == 13
         assert tasks.v8DetectionLoss.__module__ == "edge_yolo_b200.detection_loss"
         assert block._WaveletEnhancer.forward is M.wavelet_enhancer_forward
         assert block.LinearAttention.forward is M.linear_attention_forward
@@ -68,11 +68,12 @@ def test_loss_signatures_match_reference():
 def test_module_constructor_signatures_match_reference():
     ref_loader.load()
     import ultralytics.nn.modules.block as block
+    import ultralytics.nn.modules.conv as conv
     import ultralytics.nn.modules.head as head
 
     from edge_yolo_b200 import modules as M
 
-    for ref_cls, mine in ((block.DSC3K2_Wavelet, M.DSC3K2_Wavelet), (block.C2PSA_LinearAttention, M.C2PSA_LinearAttention),
+    for ref_cls, mine in ((conv.WTConv2d, M.WTConv2d), (block.DSC3K2_Wavelet, M.DSC3K2_Wavelet), (block.C2PSA_LinearAttention, M.C2PSA_LinearAttention),
                           (block.LinearAttention, M.LinearAttention), (block._WaveletEnhancer, M._WaveletEnhancer),
                           (head.GFLHeadv2_uniH, M.GFLHeadv2_uniH), (block.DSBottleneck, M.DSBottleneck), (block.DSC3k, M.DSC3k)):
         a, b = inspect.signature(ref_cls.__init__), inspect.signature(mine.__init__)
@@ -94,7 +95,7 @@ def test_install_metrics_opt_in_round_trip():
     assert list(inspect.signature(el_metrics.box_iou).parameters) == list(inspect.signature(o_iou).parameters)
     names = el.install(metrics=True)
     try:
-        assert len(names) == 15
+        assert len(names) == 16
         assert umetrics.box_iou is el_metrics.box_iou and dval.box_iou is el_metrics.box_iou
         assert list(inspect.signature(validator.BaseValidator.match_predictions).parameters) == list(inspect.signature(o_match).parameters)
         assert dval.DetectionValidator.match_predictions is validator.BaseValidator.match_predictions
