@@ -115,6 +115,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// exp(a - b) as one FFMA + MUFU.EX2: ex2(a * log2e - b * log2e).  (__expf(a - b) costs FADD + FMUL + a denormal-range fix-up of three more
+// instructions; with one warp per scheduler every instruction of these 64-element loops is ~5 cycles of latency.)
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
         for (int i = 1; i < kD; ++i) m = fmaxf(m, f[i]);
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < kD; ++i) { f[i] = __expf(f[i] - m); s += f[i]; }
+        for (int i = 0; i < kD; ++i) { f[i] = ex2_approx(fmaf(f[i], kLog2e, -m * kLog2e)); s += f[i]; }
         const float inv = valid ? 1.f / s : 0.f;  // padded tokens contribute exact zeros
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
 #pragma unroll 16
             for (int tt = 0; tt < 64; ++tt) {
                 const int t = t0 + tt;
-                const float v = __expf(to_f(col[t * 64 + ((g ^ (t & 7)) << 3) + e]) - mt);
+                const float v = ex2_approx(fmaf(to_f(col[t * 64 + ((g ^ (t & 7)) << 3) + e]), kLog2e, -mt * kLog2e));
                 acc += t < t1 ? v : 0.f;
             }
             s_pm[128 + hf * 64 + ch] = acc;
@@ -352,6 +361,8 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
         cluster_arrive();  // second phase: this CTA no longer reads remote memory; matched by the wait before exit
         s_cmax = s_gmax;
     }
+    float* s_cml = reinterpret_cast<float*>(sm + kOffStat) + 2 * kD;  // max * log2e per channel (reuses the pass-1 partials)
+    if (tid < kD) s_cml[tid] = s_cmax[tid] * kLog2e;
     tc_fence_before();
     __syncthreads();
 
@@ -367,7 +378,10 @@ __global__ void __launch_bounds__(128) linattn_tc_kernel(const __grid_constant__
             float t8[8];
             unpack<T>(rq[g], t8);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) t8[e] = valid ? __expf(t8[e] - s_cmax[8 * g + e]) : 0.f;
+            for (int e = 0; e < 8; ++e) {
+                const float p = ex2_approx(fmaf(t8[e], kLog2e, -s_cml[8 * g + e]));  // branch-free; rows past N are zeroed by the select
+                t8[e] = valid ? p : 0.f;
+            }
             uint4 o;
             o.x = pack2<T>(t8[0], t8[1]); o.y = pack2<T>(t8[2], t8[3]); o.z = pack2<T>(t8[4], t8[5]); o.w = pack2<T>(t8[6], t8[7]);
             *reinterpret_cast<uint4*>(sP + g * 2048 + tid * 16) = o;  // row = token, 16 B chunk g of the K dim
