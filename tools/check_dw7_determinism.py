@@ -1,3 +1,6 @@
+"""Determinism and view-invariance check of the k = 7 depthwise kernels: 50 repeated launches must be bit-identical, and channel-slice
+input / output views must give the same bits as dense tensors (used while hunting the ld.global.nc / programmatic-dependent-launch hazard,
+DESIGN.md section 5).  python tools/dbg_dw7.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
