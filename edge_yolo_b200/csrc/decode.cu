@@ -132,7 +132,7 @@ __device__ __forceinline__ void side_stats(float (&lg)[kRegMax], float& dist, fl
 }
 
 // DGQP hidden layer for one 64-anchor tile with 256 threads, FMA version: thread = (anchor pair ap, ap+32 ; 8 hidden units).
-// partial z sums go to s_part[8][kTile].
+// partial z sums go to s_part[8][kTile] (the fused kernel's shared-memory map reserves 8 rows for this version, 2 for the MMA version).
 __device__ __forceinline__ void dgqp_hidden_fma(const float* __restrict__ w, const float* __restrict__ s_stat, float (*s_part)[kTile]) {
     constexpr int LD = WL<false>::stat_ld;
     const int ap = threadIdx.x & 31, hg = threadIdx.x >> 5;
@@ -398,7 +398,7 @@ __device__ __forceinline__ TileInfo tile_info(const DecodeParams& P, int t) {
     return ti;
 }
 
-constexpr int kStageCap = 1024;  // staged candidate keys per tile (8 KiB per stage); the rare overflow goes straight to global memory
+constexpr int kStageCap = 512;   // staged candidate keys per tile (4 KiB per stage; a single-label tile emits <= 64); overflow goes straight to global memory
 
 // shared-memory map of the fused kernel (byte offsets), one definition for the host (size) and the device (carve-up)
 struct EmitLayout {
@@ -417,7 +417,7 @@ __host__ __device__ inline EmitLayout emit_layout(int nc, uint32_t esz, int nl) 
     L.w = cur; cur += (uint32_t)nl * L.w_stride * 4;
     L.stat = cur; cur += kTile * WL<MMA>::stat_ld * 4;
     L.dist = cur; cur += 4 * kTile * 4;
-    L.part = cur; cur += 8 * kTile * 4;
+    L.part = cur; cur += (MMA ? 2 : 8) * kTile * 4;  // partial z sums: two hidden halves (MMA) or eight hidden groups (FMA)
     L.bias_ld = (4 * kRegMax + nc + 3) & ~3;
     L.bias = cur; cur += (uint32_t)nl * L.bias_ld * 4;  // per level: box bias (64) | class bias (nc)
     L.bar = cur; cur += 16;
@@ -438,7 +438,7 @@ template <> __device__ __forceinline__ void unpack2<__half>(uint32_t w, float& l
 template <> __device__ __forceinline__ void unpack2<float>(uint32_t w, float& lo, float& hi) { lo = hi = __uint_as_float(w); }  // never used
 
 template <typename T, bool MULTI>
-__global__ void __launch_bounds__(256, 2) gfl_decode_emit_kernel(const __grid_constant__ DecodeParams P, const __grid_constant__ EmitArgs E) {
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) gfl_decode_emit_kernel(const __grid_constant__ DecodeParams P, const __grid_constant__ EmitArgs E) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool kFast = sizeof(T) == 2;
     constexpr int LD = WL<kFast>::stat_ld;
@@ -784,11 +784,15 @@ extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* 
     EmitArgs E{conf, class_keep, (unsigned long long*)(ws + L.keys), L.key_stride, (int*)(ws + L.counts), (float4*)(ws + box_off), B};
     const size_t sm = emit_smem_bytes(nc, esz, nl);
     const int total = B * P.tiles_per_image;
-    const int grid = total < 2 * kSMs ? total : 2 * kSMs;  // persistent: two CTAs per SM
+    // persistent: as many CTAs as stay resident (16-bit maps: 3 per SM -- 56 / 74 registers and 75 KB of shared memory since the DGQP layer
+    // moved to the tensor cores; fp32 maps: 2 per SM)
 #define EL_LAUNCH_EMIT(M)                                                                               \
     do {                                                                                                \
         auto kern = gfl_decode_emit_kernel<T, M>;                                                       \
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);               \
+        int occ = 0;                                                                                    \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, sm) != cudaSuccess || occ < 1) occ = 2; \
+        const int grid = total < occ * kSMs ? total : occ * kSMs;                                       \
         kern<<<grid, 256, sm, st>>>(P, E);                                                              \
     } while (0)
     if (do_emit) {
