@@ -23,7 +23,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC, UNIT = "images/sec (EdgeLine-YOLO-n, 640x640, bf16)", "images/s"
+UNIT = "images/s"
+
+
+def metric(a):
+    """BASELINE.json's metric, named for the configuration actually run (default: configs[1], EdgeLine-YOLO-n at 640x640)."""
+    return f"images/sec (EdgeLine-YOLO-{a.scale}, {a.imgsz}x{a.imgsz}, bf16)"
 
 
 def parse():
@@ -36,6 +41,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--imgsz", type=int, default=640)
     ap.add_argument("--nc", type=int, default=80)
+    ap.add_argument("--conf", type=float, default=0.25, help="NMS confidence threshold (BASELINE configs[2]: 0.001)")
+    ap.add_argument("--iou", type=float, default=0.7)
+    ap.add_argument("--max-det", type=int, default=300)
+    ap.add_argument("--multi-label", action="store_true", help="validator-style NMS: every (anchor, class) pair above --conf is a candidate")
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel roofline pass")
@@ -46,9 +55,15 @@ def parse():
     return ap.parse_args()
 
 
+def nms_settings(a):
+    return dict(conf=a.conf, iou=a.iou, max_det=a.max_det, multi_label=a.multi_label)
+
+
 def workload(a):
+    nms = "predict defaults (conf .25, iou .7, max_det 300)" if (a.conf, a.iou, a.max_det, a.multi_label) == (0.25, 0.7, 300, False) else \
+        f"NMS conf {a.conf:g}, iou {a.iou:g}, max_det {a.max_det}, {'multi_label (validator / stress regime)' if a.multi_label else 'single label'}"
     return {"workload": f"EdgeLine-YOLO-{a.scale} inference, synthetic {a.imgsz}x{a.imgsz}, batch {a.batch}/GPU, nc={a.nc}, "
-                        f"{(a.imgsz // 8) ** 2 + (a.imgsz // 16) ** 2 + (a.imgsz // 32) ** 2} anchors, predict defaults (conf .25, iou .7, max_det 300), "
+                        f"{(a.imgsz // 8) ** 2 + (a.imgsz // 16) ** 2 + (a.imgsz // 32) ** 2} anchors, {nms}, "
                         "random-init weights (wave.gamma=0.5, no bias_init)",
             "batch_per_gpu": a.batch, "imgsz": a.imgsz, "scale": a.scale, "nc": a.nc, "parallelism": f"batch-sharded replicas x{a.gpus}",
             "input": "uint8 HWC batch (what the predictor's preprocess consumes); `value`: resident in HBM, `e2e`: pinned host memory",
@@ -105,10 +120,10 @@ def cpu_oracle_rate(a, steps, warmup):
     model = model_ref.build(a.scale, a.nc, seed=0)
     x = torch.rand(a.cpu_sample, 3, a.imgsz, a.imgsz, generator=torch.Generator().manual_seed(0))
     for _ in range(warmup):
-        model_ref.predict(model, x)
+        model_ref.predict(model, x, **nms_settings(a))
     t0 = time.perf_counter()
     for _ in range(steps):
-        model_ref.predict(model, x)
+        model_ref.predict(model, x, **nms_settings(a))
     dt = time.perf_counter() - t0
     return a.cpu_sample * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
@@ -119,7 +134,7 @@ def reference_arm(a):
         return
     rate, ms, threads = cpu_oracle_rate(a, max(1, a.steps), max(1, min(a.warmup, 2)))
     sample = f"{a.cpu_sample} images per step (bounded sample of the batch-{a.batch} workload), forward + decode + NMS, fp32"
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+    line = {"impl": "reference", "metric": metric(a), "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload(a),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -310,7 +325,7 @@ def product_arm(a):
     torch.backends.cudnn.benchmark = not a.no_cudnn_benchmark
 
     model = build_model(a.scale, a.nc, seed=0, device=dev)
-    pred = Predictor(model, a.batch, a.imgsz, use_graph=not a.no_graph)
+    pred = Predictor(model, a.batch, a.imgsz, use_graph=not a.no_graph, **nms_settings(a))
     gen = torch.Generator().manual_seed(1234 + rank)
     host_u8 = torch.randint(0, 256, (a.batch, a.imgsz, a.imgsz, 3), dtype=torch.uint8, generator=gen).pin_memory()
     pred.predict_u8(host_u8)  # also leaves a real batch in pred.x
@@ -367,7 +382,7 @@ def product_arm(a):
     kept = kept_per_step[-1]
 
     value = world * a.batch * a.steps / (ms_total * 1e-3)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+    line = {"metric": metric(a), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload(a), "clocks": clocks,
             "e2e": {"value": world * a.batch * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": host_u8.numel(),

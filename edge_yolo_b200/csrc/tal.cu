@@ -1,0 +1,227 @@
+// Task-aligned target assignment on the device (the step between decode and the DFL / QFL loss kernels of
+// every training step):
+//   el_tal_assign   ultralytics/utils/tal.py:14-295  TaskAlignedAssigner.forward
+//                     get_pos_mask            :103-119   candidates = anchor centre strictly inside a valid ground truth (:244-261)
+//                     get_box_metrics         :121-148   metric = score[gt class]^alpha * CIoU(gt, pred).clamp(0)^beta   (CIoU: utils/metrics.py:74-134)
+//                     select_topk_candidates  :172-199   the topk anchors of every ground truth by metric
+//                     select_highest_overlaps :263-295   an anchor claimed by several ground truths goes to the one it overlaps most
+//                     get_targets             :201-241   labels / boxes / one-hot scores of the assigned ground truth
+//                     normalisation           :96-101    scores *= max_gt( metric * best_iou_of_gt / (best_metric_of_gt + eps) )
+// The reference materialises ~20 dense (B, n_gt, A) tensors and a 10-iteration scatter_add_ loop; here it is three kernels over one
+// (B, n_gt, A) workspace of metric / overlap / flag planes:
+//   1. tal_metric_topk   one CTA per (image, ground truth): candidates, CIoU, metric, then `topk` rounds of a block-wide arg-max
+//                        (ties -> lower anchor index; torch.topk leaves that order open, the loss does not depend on it: a tie can only
+//                        involve zero metrics, whose target scores are zero)
+//   2. tal_resolve       one thread per (image, anchor): multi-claim resolution, labels / boxes / fg / gt index, per-ground-truth
+//                        maxima of metric and overlap over the final positives (integer atomicMax on non-negative floats: exact and
+//                        order-independent)
+//   3. tal_emit          one thread per (image, anchor, class): the normalised soft one-hot target scores
+// Arithmetic is written with explicit fp32 intrinsics in the reference's evaluation order (no FMA contraction), so the metrics, and
+// with them the selected anchors, are those of the reference's own eager CUDA ops (IEEE division / sqrt, libdevice atanf / powf).
+#include "el_internal.h"
+
+namespace el {
+
+constexpr int kTalThreads = 256;
+constexpr uint8_t kTalPos = 1, kTalTaken = 2, kTalCand = 4;
+
+// x.pow(p) as torch evaluates it for a Python-scalar exponent (ATen pow_tensor_scalar: 0.5 -> sqrt, 1 -> x, 2 -> x*x, 3 -> x*x*x, else pow)
+__device__ __forceinline__ float pow_scalar(float x, float p) {
+    if (p == 1.f) return x;
+    if (p == 0.5f) return sqrtf(x);
+    if (p == 2.f) return __fmul_rn(x, x);
+    if (p == 3.f) return __fmul_rn(__fmul_rn(x, x), x);
+    return powf(x, p);
+}
+
+// CIoU of xyxy boxes, utils/metrics.py:74-134 with xywh=False, CIoU=True, eps=1e-7; a = ground truth, b = prediction (tal.py:170)
+__device__ __forceinline__ float ciou_xyxy(const float4 a, const float4 b) {
+    const float eps = 1e-7f;
+    const float aw = __fsub_rn(a.z, a.x), ah = __fadd_rn(__fsub_rn(a.w, a.y), eps);
+    const float bw = __fsub_rn(b.z, b.x), bh = __fadd_rn(__fsub_rn(b.w, b.y), eps);
+    const float iw = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+    const float ih = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(aw, ah), __fmul_rn(bw, bh)), inter), eps);
+    const float iou = __fdiv_rn(inter, uni);
+    const float cw = __fsub_rn(fmaxf(a.z, b.z), fminf(a.x, b.x));
+    const float ch = __fsub_rn(fmaxf(a.w, b.w), fminf(a.y, b.y));
+    const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(cw, cw), __fmul_rn(ch, ch)), eps);
+    const float dx = __fsub_rn(__fsub_rn(__fadd_rn(b.x, b.z), a.x), a.z);
+    const float dy = __fsub_rn(__fsub_rn(__fadd_rn(b.y, b.w), a.y), a.w);
+    const float rho2 = __fdiv_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), 4.f);
+    const float da = __fsub_rn(atanf(__fdiv_rn(bw, bh)), atanf(__fdiv_rn(aw, ah)));
+    const float v = __fmul_rn(0.40528473456935109f /* 4 / pi^2 */, __fmul_rn(da, da));
+    const float alpha = __fdiv_rn(v, __fadd_rn(__fsub_rn(v, iou), 1.0000001f /* 1 + eps */));
+    return __fsub_rn(iou, __fadd_rn(__fdiv_rn(rho2, c2), __fmul_rn(v, alpha)));
+}
+
+__device__ __forceinline__ int clamp_label(float v, int nc) {
+    const int l = (int)v;  // .long(): truncation
+    return l < 0 ? 0 : (l >= nc ? nc - 1 : l);
+}
+
+// grid (n_gt, B).  metric / overlap / flags: (B, n_gt, A) planes of the workspace; best: (B, n_gt, 2) zeroed here for tal_resolve.
+// The planes are written and re-read by this CTA between barriers: no __restrict__ / non-coherent loads on them.
+__global__ void __launch_bounds__(kTalThreads) tal_metric_topk_kernel(const float* __restrict__ scores, const float* __restrict__ boxes,
+                                                                      const float* __restrict__ anchors, const float* __restrict__ gt_labels,
+                                                                      const float* __restrict__ gt_boxes, const uint8_t* __restrict__ gt_valid,
+                                                                      int A, int nc, int M, int topk, float alpha, float beta, float* metric,
+                                                                      float* overlap, uint8_t* flags, int* best) {
+    const int m = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int64_t g = (int64_t)b * M + m;
+    float* met = metric + g * A;
+    float* ovl = overlap + g * A;
+    uint8_t* flg = flags + g * A;
+    if (tid == 0) best[2 * g] = best[2 * g + 1] = 0;
+    const bool valid = gt_valid[g] != 0;
+    const float4 gt = make_float4(gt_boxes[4 * g], gt_boxes[4 * g + 1], gt_boxes[4 * g + 2], gt_boxes[4 * g + 3]);
+    const int lab = clamp_label(gt_labels[g], nc);
+    for (int a = tid; a < A; a += kTalThreads) {
+        const float ax = anchors[2 * a], ay = anchors[2 * a + 1];
+        // min(anchor - x1y1, x2y2 - anchor) > 1e-9 (tal.py:254-261)
+        const float d = fminf(fminf(__fsub_rn(ax, gt.x), __fsub_rn(ay, gt.y)), fminf(__fsub_rn(gt.z, ax), __fsub_rn(gt.w, ay)));
+        const bool cand = valid && d > 1e-9f;
+        float v = 0.f, u = 0.f;
+        if (cand) {
+            const float* pb = boxes + ((int64_t)b * A + a) * 4;
+            u = fmaxf(ciou_xyxy(gt, make_float4(pb[0], pb[1], pb[2], pb[3])), 0.f);
+            const float s = scores[((int64_t)b * A + a) * nc + lab];
+            v = __fmul_rn(pow_scalar(s, alpha), pow_scalar(u, beta));
+        }
+        met[a] = v;
+        ovl[a] = u;
+        flg[a] = cand ? kTalCand : 0;
+    }
+    if (!valid) return;  // a padded ground truth selects nothing (uniform over the CTA)
+    __shared__ unsigned long long s_key[kTalThreads / 32];
+    __syncthreads();
+    // key = metric bits (non-negative floats order like integers) : ~anchor  ->  max key = largest metric, lowest anchor index
+    for (int r = 0; r < topk; ++r) {
+        unsigned long long key = 0;  // real keys have non-zero low words (A < 2^31)
+        for (int a = tid; a < A; a += kTalThreads) {
+            if (flg[a] & kTalTaken) continue;
+            const unsigned long long k = ((unsigned long long)__float_as_uint(met[a]) << 32) | (0xffffffffu - (unsigned)a);
+            key = k > key ? k : key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if ((tid & 31) == 0) s_key[tid >> 5] = key;
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int w = 1; w < kTalThreads / 32; ++w) key = s_key[w] > key ? s_key[w] : key;
+            if (key) {
+                const unsigned a = 0xffffffffu - (unsigned)(key & 0xffffffffu);
+                const uint8_t f = flg[a];
+                flg[a] = f | kTalTaken | ((f & kTalCand) ? kTalPos : 0);  // in the top k AND inside a valid ground truth (tal.py:112-117)
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// one thread per (image, anchor)
+__global__ void __launch_bounds__(256) tal_resolve_kernel(const float* __restrict__ metric, const float* __restrict__ overlap,
+                                                          const uint8_t* __restrict__ flags, const float* __restrict__ gt_labels,
+                                                          const float* __restrict__ gt_boxes, int B, int A, int nc, int M, int* best,
+                                                          int64_t* __restrict__ labels, float* __restrict__ tboxes, uint8_t* __restrict__ fg,
+                                                          int64_t* __restrict__ gt_idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * A) return;
+    const int b = (int)(i / A), a = (int)(i - (int64_t)b * A);
+    const int64_t base = (int64_t)b * M * A + a;
+    int claims = 0, first = 0, bm = 0;
+    float bi = overlap[base];
+    for (int m = 0; m < M; ++m) {
+        const int64_t o = base + (int64_t)m * A;
+        if (flags[o] & kTalPos) {
+            if (claims == 0) first = m;
+            ++claims;
+        }
+        const float u = overlap[o];
+        if (u > bi) { bi = u; bm = m; }  // argmax over ground truths: first maximum (tal.py:286)
+    }
+    const bool is_fg = claims > 0;
+    const int gi = claims > 1 ? bm : first;  // `first` is 0 for background anchors, like mask_pos.argmax(-2) (tal.py:293)
+    const int64_t g = (int64_t)b * M + gi;
+    labels[i] = clamp_label(gt_labels[g], nc);
+    reinterpret_cast<float4*>(tboxes)[i] = make_float4(gt_boxes[4 * g], gt_boxes[4 * g + 1], gt_boxes[4 * g + 2], gt_boxes[4 * g + 3]);
+    fg[i] = is_fg ? 1 : 0;
+    gt_idx[i] = gi;
+    if (is_fg) {  // pos_align_metrics / pos_overlaps: maxima over the final positives of this ground truth (tal.py:97-98)
+        atomicMax(best + 2 * g, __float_as_int(metric[g * A + a]));
+        atomicMax(best + 2 * g + 1, __float_as_int(overlap[g * A + a]));
+    }
+}
+
+// one thread per (image, anchor, class): target_scores = one_hot(label) * fg * metric * best_overlap / (best_metric + eps)
+__global__ void __launch_bounds__(256) tal_emit_kernel(const float* __restrict__ metric, const int* __restrict__ best, const int64_t* __restrict__ labels,
+                                                       const uint8_t* __restrict__ fg, const int64_t* __restrict__ gt_idx, int64_t total, int A, int nc,
+                                                       int M, float eps, float* __restrict__ tscores) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ba = i / nc;
+        const int c = (int)(i - ba * nc);
+        float out = 0.f;
+        if (fg[ba] && labels[ba] == c) {
+            const int b = (int)(ba / A), a = (int)(ba - (int64_t)b * A);
+            const int64_t g = (int64_t)b * M + gt_idx[ba];
+            out = __fdiv_rn(__fmul_rn(metric[g * A + a], __int_as_float(best[2 * g + 1])), __fadd_rn(__int_as_float(best[2 * g]), eps));
+        }
+        tscores[i] = out;
+    }
+}
+
+struct TalLayout { size_t metric, overlap, flags, best, total; };
+static TalLayout tal_layout(int B, int M, int A) {
+    const size_t n = (size_t)B * M * A;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    TalLayout L;
+    L.metric = 0;
+    L.overlap = up(L.metric + n * 4);
+    L.flags = up(L.overlap + n * 4);
+    L.best = up(L.flags + n);
+    L.total = up(L.best + (size_t)B * M * 2 * 4);
+    return L;
+}
+
+}  // namespace el
+
+using namespace el;
+
+extern "C" int el_tal_workspace_bytes(int B, int M, int A, size_t* bytes) {
+    if (!bytes || B <= 0 || M <= 0 || A <= 0) return EL_ERR_ARG;
+    *bytes = tal_layout(B, M, A).total;
+    return EL_OK;
+}
+
+extern "C" int el_tal_assign(const float* scores, const float* boxes, const float* anchors, const float* gt_labels, const float* gt_boxes,
+                             const uint8_t* gt_valid, int B, int A, int nc, int M, int topk, float alpha, float beta, float eps, void* workspace,
+                             size_t workspace_bytes, int64_t* labels, float* tboxes, float* tscores, uint8_t* fg, int64_t* gt_idx, void* stream) {
+    if (!scores || !boxes || !anchors || !gt_labels || !gt_boxes || !gt_valid || !workspace || !labels || !tboxes || !tscores || !fg || !gt_idx)
+        return EL_ERR_ARG;
+    if (B <= 0 || A <= 0 || nc <= 0 || M <= 0 || topk <= 0) return EL_ERR_ARG;
+    if (B > 65535 || !aligned16(tboxes)) return EL_ERR_UNSUPPORTED;
+    const TalLayout L = tal_layout(B, M, A);
+    if (workspace_bytes < L.total) return EL_ERR_WORKSPACE;
+    if (!aligned16(workspace)) return EL_ERR_ARG;
+    char* ws = static_cast<char*>(workspace);
+    float* metric = reinterpret_cast<float*>(ws + L.metric);
+    float* overlap = reinterpret_cast<float*>(ws + L.overlap);
+    uint8_t* flags = reinterpret_cast<uint8_t*>(ws + L.flags);
+    int* best = reinterpret_cast<int*>(ws + L.best);
+    cudaStream_t st = (cudaStream_t)stream;
+    tal_metric_topk_kernel<<<dim3(M, B), kTalThreads, 0, st>>>(scores, boxes, anchors, gt_labels, gt_boxes, gt_valid, A, nc, M, topk < A ? topk : A,
+                                                              alpha, beta, metric, overlap, flags, best);
+    const int64_t n_ba = (int64_t)B * A;
+    tal_resolve_kernel<<<(unsigned)ceil_div(n_ba, 256), 256, 0, st>>>(metric, overlap, flags, gt_labels, gt_boxes, B, A, nc, M, best, labels, tboxes, fg,
+                                                                      gt_idx);
+    const int64_t total = n_ba * nc;
+    const int64_t blocks = ceil_div(total, 256);
+    tal_emit_kernel<<<(unsigned)(blocks < kSMs * 16 ? blocks : kSMs * 16), 256, 0, st>>>(metric, best, labels, fg, gt_idx, total, A, nc, M, eps, tscores);
+    note_launches(3);
+    return check_launch();
+}

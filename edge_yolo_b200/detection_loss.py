@@ -5,20 +5,27 @@ What runs where:
   * class term          -> BCE-with-logits, the branch the reference really takes with GFLHeadv2_uniH (`head._qualities`
                            stays None in training); `use_qfl=True` switches to `el_qfl_fwd/bwd`, the one-line
                            change the reference documents at loss.py:404-407
-  * target assignment   -> `TaskAlignedAssigner` below: a vectorised torch restatement of utils/tal.py:14-295.  It is the
-                           rank-1 "next" row of SURVEY section 8(f); it has no kernel of its own yet, so it runs as device-side torch
-                           ops (no host synchronisation except the data-dependent `fg_mask.sum()` the reference also has)
+  * target assignment   -> `TaskAlignedAssigner` below (utils/tal.py:14-295, the rank-1 "next" row of SURVEY section 8(f)):
+                           `fused=True` runs `el_tal_assign` (three kernels over one (B, n_gt, A) workspace: metric + top-k,
+                           multi-claim resolution, normalised soft targets); `fused=False` is the same algorithm as ~25 device-side
+                           torch ops (the formulation the kernel was developed against; kept for A/B measurement, CUDA only like
+                           everything else here).  Neither synchronises with the host.
   * CIoU                -> `bbox_ciou` (utils/metrics.py:74-134 with xywh=False, CIoU=True)
 """
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 
 import torch
 import torch.nn.functional as F
 
+from . import _lib
 from .loss import DFLoss, quality_focal_loss
+
+# default of TaskAlignedAssigner(fused=None): the fused kernel path unless EL_TAL_FUSED=0
+_TAL_FUSED_DEFAULT = os.environ.get("EL_TAL_FUSED", "0") != "0"
 
 
 def make_anchors(feats, strides, offset: float = 0.5):
@@ -68,8 +75,33 @@ class TaskAlignedAssigner:
     """Task-aligned target assignment (utils/tal.py:14-295): metric = score^alpha * CIoU^beta, top-k anchors per ground truth
     among those whose centre lies inside it, ties between ground truths resolved by the larger overlap."""
 
-    def __init__(self, topk=13, num_classes=80, alpha=1.0, beta=6.0, eps=1e-9):
+    def __init__(self, topk=13, num_classes=80, alpha=1.0, beta=6.0, eps=1e-9, fused=None):
         self.topk, self.num_classes, self.alpha, self.beta, self.eps = topk, num_classes, alpha, beta, eps
+        self.fused = _TAL_FUSED_DEFAULT if fused is None else bool(fused)
+
+    def _assign_fused(self, scores, boxes, anchors, gt_labels, gt_boxes, gt_valid):
+        """`el_tal_assign`: dense fp32 operands, outputs allocated here, workspace from the caching allocator."""
+        from .ops import _stream, check
+
+        B, A, nc = scores.shape
+        M = gt_boxes.shape[1]
+        dev = scores.device
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()  # noqa: E731
+        sc, bx, an, gl, gb = f32(scores), f32(boxes), f32(anchors), f32(gt_labels.reshape(B, M)), f32(gt_boxes)
+        gv = gt_valid.reshape(B, M).to(torch.uint8).contiguous()
+        L = _lib.lib()
+        nbytes = _lib.c_size_t()
+        check(L.el_tal_workspace_bytes(B, M, A, _lib.ctypes.byref(nbytes)), "el_tal_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        labels = torch.empty((B, A), dtype=torch.int64, device=dev)
+        tboxes = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+        tscores = torch.empty((B, A, nc), dtype=torch.float32, device=dev)
+        fg = torch.empty((B, A), dtype=torch.uint8, device=dev)
+        gt_idx = torch.empty((B, A), dtype=torch.int64, device=dev)
+        check(L.el_tal_assign(sc.data_ptr(), bx.data_ptr(), an.data_ptr(), gl.data_ptr(), gb.data_ptr(), gv.data_ptr(), B, A, nc, M, int(self.topk),
+                              float(self.alpha), float(self.beta), float(self.eps), ws.data_ptr(), ws.numel(), labels.data_ptr(), tboxes.data_ptr(),
+                              tscores.data_ptr(), fg.data_ptr(), gt_idx.data_ptr(), _stream()), "el_tal_assign")
+        return labels, tboxes.to(gt_boxes.dtype), tscores.to(scores.dtype), fg.bool(), gt_idx
 
     @torch.no_grad()
     def __call__(self, scores, boxes, anchors, gt_labels, gt_boxes, gt_valid):
@@ -80,6 +112,8 @@ class TaskAlignedAssigner:
         if M == 0:
             z = torch.zeros_like(scores[..., 0])
             return torch.full_like(z, self.num_classes), torch.zeros_like(boxes), torch.zeros_like(scores), z, z
+        if self.fused and scores.is_cuda:
+            return self._assign_fused(scores, boxes, anchors, gt_labels, gt_boxes, gt_valid)
         valid = gt_valid.bool()                                                   # (B,M,1)
         # anchor centre strictly inside the ground-truth box (tal.py:254-261)
         lt = anchors.view(1, 1, A, 2) - gt_boxes[..., None, :2]
@@ -139,7 +173,7 @@ class v8DetectionLoss:
     """Drop-in for `ultralytics.utils.loss.v8DetectionLoss`: `criterion(preds, batch) -> (loss.sum() * B, loss.detach())`
     with loss = (box, cls, dfl) scaled by the hyper-parameter gains."""
 
-    def __init__(self, model, tal_topk=10, use_qfl: bool = False):
+    def __init__(self, model, tal_topk=10, use_qfl: bool = False, fused_tal=None):
         head = model.model[-1]
         self.head = head
         self.hyp = getattr(model, "args", None) or SimpleNamespace(box=7.5, cls=0.5, dfl=1.5)  # cfg/default.yaml
@@ -149,7 +183,7 @@ class v8DetectionLoss:
         self.no = head.nc + head.reg_max * 4
         self.device = next(model.parameters()).device
         self.use_dfl, self.use_qfl = head.reg_max > 1, use_qfl
-        self.assigner = TaskAlignedAssigner(topk=tal_topk, num_classes=self.nc, alpha=0.5, beta=6.0)
+        self.assigner = TaskAlignedAssigner(topk=tal_topk, num_classes=self.nc, alpha=0.5, beta=6.0, fused=fused_tal)
         self.bbox_loss = BboxLoss(head.reg_max)
         self.proj = torch.arange(head.reg_max, dtype=torch.float, device=self.device)
 

@@ -252,6 +252,20 @@ int el_box_iou(const float* box1, int64_t stride1, const float* box2, int64_t st
 int el_match_predictions(const float* iou, const float* pred_cls, const float* true_cls, const float* iouv, int L, int D, int T,
                          uint8_t* correct, void* stream);
 
+/* ---- 8f-1. task-aligned target assignment: TaskAlignedAssigner.forward, utils/tal.py:14-295 (CIoU: utils/metrics.py:74-134) ----
+ * scores (B,A,nc) class probabilities, boxes (B,A,4) predicted xyxy in pixels, anchors (A,2) cell centres in pixels,
+ * gt_labels (B,M) class ids as floats (what the reference's target tensor holds), gt_boxes (B,M,4) xyxy pixels, gt_valid (B,M)
+ * bytes (mask_gt, loss.py:374); all dense fp32 / uint8.  metric = score[gt class]^alpha * clamp(CIoU, 0)^beta over the anchors whose
+ * centre lies strictly inside a valid ground truth, the `topk` best anchors per ground truth, multi-claims to the larger overlap.
+ * Outputs (dense): labels (B,A) int64, tboxes (B,A,4) fp32 (16-byte aligned), tscores (B,A,nc) fp32 normalised soft one-hot,
+ * fg (B,A) bytes, gt_idx (B,A) int64 -- the reference's return tuple (tal.py:101).  Background anchors carry ground truth 0's
+ * label / box like the reference.  Three kernels over a (B,M,A) workspace; no host synchronisation.  M >= 1 (no targets: the
+ * caller returns the reference's constant tuple, tal.py:76-84). */
+int el_tal_workspace_bytes(int B, int M, int A, size_t* bytes);
+int el_tal_assign(const float* scores, const float* boxes, const float* anchors, const float* gt_labels, const float* gt_boxes,
+                  const uint8_t* gt_valid, int B, int A, int nc, int M, int topk, float alpha, float beta, float eps, void* workspace,
+                  size_t workspace_bytes, int64_t* labels, float* tboxes, float* tscores, uint8_t* fg, int64_t* gt_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,3 +56,27 @@ dg = torch.empty(rows * 4, 16, device=dev)
 go = torch.ones(rows, 1, device=dev)
 report("el_dfl_fwd (5120 fg anchors)", timeit(lambda i: check(L.el_dfl_fwd(pd[i].data_ptr(), td[i].data_ptr(), rows, _dt(pd[i]), dl.data_ptr(), _stream()), "dfl")), rows * 4 * (16 * 4 + 4) + rows * 4)
 report("el_dfl_bwd", timeit(lambda i: check(L.el_dfl_bwd(pd[i].data_ptr(), td[i].data_ptr(), rows, _dt(pd[i]), go.data_ptr(), dg.data_ptr(), _stream()), "dfl")), rows * 4 * (2 * 16 * 4 + 4))
+
+# ---- task-aligned assigner at the same size (B = 64, 8 boxes per image, 8400 anchors, 80 classes): el_tal_assign (three kernels) against
+# the torch-op formulation.  Algorithmic bytes: read scores' gathered column + boxes + anchors per (gt, anchor) candidate at worst, write
+# target scores (B*A*nc*4) + boxes / labels / fg / index (B*A*37): the dense target-score write dominates.
+from edge_yolo_b200.detection_loss import TaskAlignedAssigner, make_anchors  # noqa: E402
+
+B, M, nc = 64, 8, 80
+cpu_g = torch.Generator().manual_seed(1)
+pts, st = make_anchors([torch.empty(1, 1, 640 // s, 640 // s) for s in (8, 16, 32)], (8, 16, 32))
+anchors = (pts * st).to(dev)
+A = anchors.shape[0]
+cases = []
+for _ in range(R):
+    ltrb = torch.rand(B, A, 4, generator=cpu_g) * 6 * st
+    boxes = torch.cat((pts * st - ltrb[..., :2], pts * st + ltrb[..., 2:]), -1).to(dev)
+    scores = torch.sigmoid(torch.randn(B, A, nc, generator=cpu_g) * 2 - 3).to(dev)
+    c, wh = torch.rand(B, M, 2, generator=cpu_g) * 0.8 + 0.1, torch.rand(B, M, 2, generator=cpu_g) * 0.35 + 0.05
+    gt_boxes = (torch.cat((c - wh / 2, c + wh / 2), -1) * 640).to(dev)
+    gt_labels = torch.randint(0, nc, (B, M, 1), generator=cpu_g).float().to(dev)
+    cases.append((scores, boxes, anchors, gt_labels, gt_boxes, torch.ones(B, M, 1, dtype=torch.bool, device=dev)))
+tal_bytes = B * A * (nc * 4 + 37) + B * A * 16 + B * M * A // 8 * (16 + 4)
+fused, eager = TaskAlignedAssigner(10, nc, 0.5, 6.0, fused=True), TaskAlignedAssigner(10, nc, 0.5, 6.0, fused=False)
+report("el_tal_assign (3 kernels)", timeit(lambda i: fused(*cases[i])), tal_bytes)
+report("TAL as device-side torch ops", timeit(lambda i: eager(*cases[i])), tal_bytes)
