@@ -143,3 +143,34 @@ def test_detection_loss_qfl_switch_gpu(golden):
     total.backward()
     assert torch.isfinite(total) and all(torch.isfinite(f.grad).all() for f in feats)
     assert float(items[1]) != float(g["a_items"][1])  # a different class term than BCE
+
+
+def _tal_golden(golden, tag, device, fused, rtol=1e-5, atol=1e-9):
+    """tests/golden/tal.npz: inputs and outputs of the unmodified reference's TaskAlignedAssigner.forward (oracle/gen_golden_tal.py; seeds with
+    >= 0.1 % margin on every discrete decision, so the whole assignment must be reproduced exactly and only the scores carry a tolerance)."""
+    from edge_yolo_b200.detection_loss import TaskAlignedAssigner
+
+    g = golden("tal")
+    B, imgsz, nc, M, topk = (int(v) for v in g[f"{tag}_cfg"])
+    alpha, beta = (float(v) for v in g[f"{tag}_alpha_beta"])
+    args = [torch.from_numpy(g[f"{tag}_{k}"]).to(device) for k in ("scores", "boxes", "anchors", "gt_labels", "gt_boxes", "gt_valid")]
+    labels, tboxes, tscores, fg, gt_idx = TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=alpha, beta=beta, fused=fused)(*args)
+    assert int(g[f"{tag}_out_fg"].sum()) > 0
+    np.testing.assert_array_equal(fg.cpu().numpy(), g[f"{tag}_out_fg"])
+    np.testing.assert_array_equal(gt_idx.cpu().numpy(), g[f"{tag}_out_gt_idx"])
+    np.testing.assert_array_equal(labels.cpu().numpy(), g[f"{tag}_out_labels"])
+    np.testing.assert_array_equal(tboxes.cpu().numpy(), g[f"{tag}_out_tboxes"])
+    np.testing.assert_allclose(tscores.cpu().numpy(), g[f"{tag}_out_tscores"], rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("tag", ["multi", "sparse"])
+def test_tal_torch_formulation_matches_reference_golden(golden, tag):
+    _tal_golden(golden, tag, "cpu", fused=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True], ids=["torch_ops", "fused_kernel"])
+@pytest.mark.parametrize("tag", ["multi", "sparse"])
+def test_tal_matches_reference_golden_gpu(golden, tag, fused):
+    # libdevice powf / atanf against the CPU's: the same tolerance as the loss golden above (the assignment itself is compared exactly)
+    _tal_golden(golden, tag, "cuda", fused=fused, rtol=2e-5, atol=1e-8)
