@@ -45,14 +45,18 @@ def parse():
     ap.add_argument("--iou", type=float, default=0.7)
     ap.add_argument("--max-det", type=int, default=300)
     ap.add_argument("--multi-label", action="store_true", help="validator-style NMS: every (anchor, class) pair above --conf is a candidate")
-    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=None,
+                    help="images per CPU-baseline step (default: 16 for the n model at 640x640 -- the batch at which the host cores are busiest -- else 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel roofline pass")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay (for ncu)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run warm-ups, then ONE eager step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="skip cuDNN autotuning (keeps ncu launch lists short)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.cpu_sample is None:
+        a.cpu_sample = 16 if (a.scale, a.imgsz) == ("n", 640) else 4
+    return a
 
 
 def nms_settings(a):
@@ -407,9 +411,9 @@ def product_arm(a):
                                     "(each site timed alone, inputs rotated through > L2); traffic = DRAM bytes of the same launches in one step "
                                     "from the committed ncu capture (profiles/r01g_step_b64_time_dram.json), null for other configs"}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        rate, ms, threads = cpu_oracle_rate(a, steps=3, warmup=1)
+        rate, ms, threads = cpu_oracle_rate(a, steps=5, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"3 steps x {a.cpu_sample} images (bounded sample of the batch-{a.batch} workload), forward + decode + NMS, fp32"}
+                                "sample": f"5 steps x {a.cpu_sample} images (bounded sample of the batch-{a.batch} workload), forward + decode + NMS, fp32"}
     eld.shutdown()
     if rank == 0:
         _emit(line)
