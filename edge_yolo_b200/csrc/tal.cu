@@ -1,12 +1,12 @@
 // Task-aligned target assignment on the device (the step between decode and the DFL / QFL loss kernels of
 // every training step):
 //   el_tal_assign   ultralytics/utils/tal.py:14-295  TaskAlignedAssigner.forward
-//                     get_pos_mask            :103-119   candidates = anchor centre strictly inside a valid ground truth (:244-261)
-//                     get_box_metrics         :121-148   metric = score[gt class]^alpha * CIoU(gt, pred).clamp(0)^beta   (CIoU: utils/metrics.py:74-134)
-//                     select_topk_candidates  :172-199   the topk anchors of every ground truth by metric
-//                     select_highest_overlaps :263-295   an anchor claimed by several ground truths goes to the one it overlaps most
-//                     get_targets             :201-241   labels / boxes / one-hot scores of the assigned ground truth
-//                     normalisation           :96-101    scores *= max_gt( metric * best_iou_of_gt / (best_metric_of_gt + eps) )
+//                     get_pos_mask            :120-130   candidates = anchor centre strictly inside a valid ground truth (:241-262)
+//                     get_box_metrics         :132-155   metric = score[gt class]^alpha * CIoU(gt, pred).clamp(0)^beta   (CIoU: utils/metrics.py:74-134)
+//                     select_topk_candidates  :157-190   the topk anchors of every ground truth by metric
+//                     select_highest_overlaps :265-295   an anchor claimed by several ground truths goes to the one it overlaps most
+//                     get_targets             :192-238   labels / boxes / one-hot scores of the assigned ground truth
+//                     normalisation           :110-116   scores *= max_gt( metric * best_iou_of_gt / (best_metric_of_gt + eps) )
 // The reference materialises ~20 dense (B, n_gt, A) tensors and a 10-iteration scatter_add_ loop; here it is three kernels over one
 // (B, n_gt, A) workspace of metric / overlap / flag planes:
 //   1. tal_metric_topk   one CTA per (image, ground truth): candidates, CIoU, metric, then `topk` rounds of a block-wide arg-max
@@ -34,7 +34,7 @@ __device__ __forceinline__ float pow_scalar(float x, float p) {
     return powf(x, p);
 }
 
-// CIoU of xyxy boxes, utils/metrics.py:74-134 with xywh=False, CIoU=True, eps=1e-7; a = ground truth, b = prediction (tal.py:170)
+// CIoU of xyxy boxes, utils/metrics.py:74-134 with xywh=False, CIoU=True, eps=1e-7; a = ground truth, b = prediction (iou_calculation, tal.py:153-155)
 __device__ __forceinline__ float ciou_xyxy(const float4 a, const float4 b) {
     const float eps = 1e-7f;
     const float aw = __fsub_rn(a.z, a.x), ah = __fadd_rn(__fsub_rn(a.w, a.y), eps);
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kTalThreads) tal_metric_topk_kernel(const floa
     const int lab = clamp_label(gt_labels[g], nc);
     for (int a = tid; a < A; a += kTalThreads) {
         const float ax = anchors[2 * a], ay = anchors[2 * a + 1];
-        // min(anchor - x1y1, x2y2 - anchor) > 1e-9 (tal.py:254-261)
+        // min(anchor - x1y1, x2y2 - anchor) > 1e-9 (tal.py:258-262)
         const float d = fminf(fminf(__fsub_rn(ax, gt.x), __fsub_rn(ay, gt.y)), fminf(__fsub_rn(gt.z, ax), __fsub_rn(gt.w, ay)));
         const bool cand = valid && d > 1e-9f;
         float v = 0.f, u = 0.f;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kTalThreads) tal_metric_topk_kernel(const floa
             if (key) {
                 const unsigned a = 0xffffffffu - (unsigned)(key & 0xffffffffu);
                 const uint8_t f = flg[a];
-                flg[a] = f | kTalTaken | ((f & kTalCand) ? kTalPos : 0);  // in the top k AND inside a valid ground truth (tal.py:112-117)
+                flg[a] = f | kTalTaken | ((f & kTalCand) ? kTalPos : 0);  // in the top k AND inside a valid ground truth (tal.py:126-128)
                 if (kSmem) s_met[a] = -1.f;
             }
         }
@@ -160,13 +160,13 @@ __global__ void __launch_bounds__(256) tal_resolve_kernel(const float* __restric
         if (u > bi) { bi = u; bm = m; }  // argmax over ground truths: first maximum (tal.py:286)
     }
     const bool is_fg = claims > 0;
-    const int gi = claims > 1 ? bm : first;  // `first` is 0 for background anchors, like mask_pos.argmax(-2) (tal.py:293)
+    const int gi = claims > 1 ? bm : first;  // `first` is 0 for background anchors, like mask_pos.argmax(-2) (tal.py:294)
     const int64_t g = (int64_t)b * M + gi;
     labels[i] = clamp_label(gt_labels[g], nc);
     reinterpret_cast<float4*>(tboxes)[i] = make_float4(gt_boxes[4 * g], gt_boxes[4 * g + 1], gt_boxes[4 * g + 2], gt_boxes[4 * g + 3]);
     fg[i] = is_fg ? 1 : 0;
     gt_idx[i] = gi;
-    if (is_fg) {  // pos_align_metrics / pos_overlaps: maxima over the final positives of this ground truth (tal.py:97-98)
+    if (is_fg) {  // pos_align_metrics / pos_overlaps: maxima over the final positives of this ground truth (tal.py:112-113)
         atomicMax(best + 2 * g, __float_as_int(metric[g * A + a]));
         atomicMax(best + 2 * g + 1, __float_as_int(overlap[g * A + a]));
     }

@@ -116,12 +116,12 @@ class TaskAlignedAssigner:
         if self.fused and scores.is_cuda:
             return self._assign_fused(scores, boxes, anchors, gt_labels, gt_boxes, gt_valid)
         valid = gt_valid.bool()                                                   # (B,M,1)
-        # anchor centre strictly inside the ground-truth box (tal.py:254-261)
+        # anchor centre strictly inside the ground-truth box (tal.py:241-262)
         lt = anchors.view(1, 1, A, 2) - gt_boxes[..., None, :2]
         rb = gt_boxes[..., None, 2:] - anchors.view(1, 1, A, 2)
         inside = torch.cat((lt, rb), -1).amin(-1) > 1e-9                          # (B,M,A)
         cand = inside & valid
-        # per (gt, anchor): class probability of the gt's class and CIoU, only where the anchor is a candidate (tal.py:149-166)
+        # per (gt, anchor): class probability of the gt's class and CIoU, only where the anchor is a candidate (tal.py:132-155)
         lab = gt_labels.squeeze(-1).long().clamp(0, nc - 1)                       # (B,M)
         cls_score = scores.gather(2, lab.unsqueeze(1).expand(B, A, M)).permute(0, 2, 1)   # (B,M,A)
         iou = bbox_ciou(gt_boxes.unsqueeze(2), boxes.unsqueeze(1)).squeeze(-1).clamp_(0)
@@ -129,21 +129,21 @@ class TaskAlignedAssigner:
         iou = torch.where(cand, iou, zero)
         cls_score = torch.where(cand, cls_score, zero.to(cls_score.dtype))
         metric = cls_score.pow(self.alpha) * iou.pow(self.beta)
-        # top-k anchors per ground truth; padded ground truths select nothing (tal.py:172-199)
+        # top-k anchors per ground truth; padded ground truths select nothing (tal.py:157-190, :126-128)
         top = metric.topk(self.topk, dim=-1).indices                              # (B,M,k)
         in_top = torch.zeros_like(metric, dtype=torch.bool).scatter_(2, top, True) & valid
         pos = in_top & inside                                                     # (B,M,A)
-        # an anchor claimed by several ground truths goes to the one it overlaps most (tal.py:282-295)
+        # an anchor claimed by several ground truths goes to the one it overlaps most (tal.py:265-295)
         n_claims = pos.sum(1)                                                     # (B,A)
         best = F.one_hot(iou.argmax(1), M).permute(0, 2, 1).bool()                # (B,M,A)
         pos = torch.where((n_claims > 1).unsqueeze(1), best, pos)
         fg = pos.any(1)
         gt_idx = pos.float().argmax(1)                                            # (B,A); 0 where background
-        # targets (tal.py:201-241)
+        # targets (tal.py:192-238)
         labels = lab.gather(1, gt_idx)
         tboxes = gt_boxes.gather(1, gt_idx.unsqueeze(-1).expand(B, A, 4))
         tscores = F.one_hot(labels, nc).to(scores.dtype) * fg.unsqueeze(-1)
-        # soft labels: metric normalised per ground truth to its best overlap (tal.py:96-101)
+        # soft labels: metric normalised per ground truth to its best overlap (tal.py:110-116)
         posf = pos.to(metric.dtype)
         metric = metric * posf
         best_metric = metric.amax(-1, keepdim=True)

@@ -258,9 +258,9 @@ int el_match_predictions(const float* iou, const float* pred_cls, const float* t
  * bytes (mask_gt, loss.py:374); all dense fp32 / uint8.  metric = score[gt class]^alpha * clamp(CIoU, 0)^beta over the anchors whose
  * centre lies strictly inside a valid ground truth, the `topk` best anchors per ground truth, multi-claims to the larger overlap.
  * Outputs (dense): labels (B,A) int64, tboxes (B,A,4) fp32 (16-byte aligned), tscores (B,A,nc) fp32 normalised soft one-hot,
- * fg (B,A) bytes, gt_idx (B,A) int64 -- the reference's return tuple (tal.py:101).  Background anchors carry ground truth 0's
+ * fg (B,A) bytes, gt_idx (B,A) int64 -- the reference's return tuple (tal.py:118).  Background anchors carry ground truth 0's
  * label / box like the reference.  Three kernels over a (B,M,A) workspace; no host synchronisation.  M >= 1 (no targets: the
- * caller returns the reference's constant tuple, tal.py:76-84). */
+ * caller returns the reference's constant tuple, tal.py:64-71). */
 int el_tal_workspace_bytes(int B, int M, int A, size_t* bytes);
 int el_tal_assign(const float* scores, const float* boxes, const float* anchors, const float* gt_labels, const float* gt_boxes,
                   const uint8_t* gt_valid, int B, int A, int nc, int M, int topk, float alpha, float beta, float eps, void* workspace,

@@ -47,9 +47,9 @@ def make_case(B, imgsz, nc, M, seed):
 
 
 def margins_ok(assigner, args, topk, rel=1e-3):
-    """Decision margins of the reference's own intermediate tensors (get_pos_mask, tal.py:103-119)."""
+    """Decision margins of the reference's own intermediate tensors (get_pos_mask, tal.py:120-130)."""
     scores, boxes, anchors, gt_labels, gt_boxes, valid = args
-    assigner.bs, assigner.n_max_boxes = scores.shape[0], gt_boxes.shape[1]  # what forward() sets before calling get_pos_mask (tal.py:63-64)
+    assigner.bs, assigner.n_max_boxes = scores.shape[0], gt_boxes.shape[1]  # what forward() sets before calling get_pos_mask (tal.py:60-61)
     mask_pos, metric, overlaps = assigner.get_pos_mask(scores, boxes, gt_labels, gt_boxes, anchors, valid)
     srt = metric.sort(-1, descending=True).values
     last_in, first_out = srt[..., topk - 1], srt[..., topk]
