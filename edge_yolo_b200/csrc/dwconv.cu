@@ -2,7 +2,7 @@
 // bias + activation epilogue.  Engine-path replacement for the depthwise halves of the reference's separable blocks:
 //   DSConv.dw  (nn/modules/conv.py:87-104: Conv2d(c, c, k, groups=c, bias=False), k = 3 and 7 in DSBottleneck,
 //               nn/modules/block.py:1467-1503)           -> no epilogue, the result feeds the pointwise conv
-//   DWConv     (nn/modules/conv.py:107-112, the Detect cls tower head.py:66-71) -> folded-BN bias + SiLU epilogue
+//   DWConv     (nn/modules/conv.py:124-130, the Detect cls tower head.py:66-71) -> folded-BN bias + SiLU epilogue
 // HBM-bound by design for k = 3 (every input element read from DRAM once, every output written once); k = 7 is bounded by
 // fp32 FMA issue (49 taps per output) and is written to keep the load/store pipe below it.
 //

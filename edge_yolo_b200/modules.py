@@ -329,7 +329,7 @@ def conv_engine_forward(self, x, out=None, residual=None, out2=None):
 
 
 def dwconv_engine_forward(self, x, out=None, residual=None, out2=None):
-    """DWConv.forward_fuse (conv.py:107-112): depthwise conv + folded-BN bias + activation in one kernel."""
+    """DWConv.forward_fuse (conv.py:124-130): depthwise conv + folded-BN bias + activation in one kernel."""
     if residual is not None or out2 is not None:
         return conv_engine_forward(self, x, out=out, residual=residual, out2=out2)
     return ops.dwconv(x, _dw_on(self, x), self.el_k, bias=_bias_on(self, x), act=self.el_act, out=out)

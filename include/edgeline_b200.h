@@ -205,7 +205,7 @@ int el_upsample2x_cat_fwd(const void* x, const int64_t xs[4], const void* skip, 
                           int dtype, void* stream);
 /* el_dwconv_fwd: depthwise k x k convolution, stride 1, padding k/2 (k in {3,5,7}), NHWC views, optional fused
  * bias + activation: DSConv.dw (nn/modules/conv.py:87-104, no epilogue) and DWConv + folded BatchNorm + SiLU
- * (conv.py:107-112; Detect cls tower head.py:66-71).  w: fp32 (k*k, C) tap-major; bias fp32 (C) or NULL;
+ * (conv.py:124-130; Detect cls tower head.py:66-71).  w: fp32 (k*k, C) tap-major; bias fp32 (C) or NULL;
  * act as el_bias_act_fwd.  C must be a multiple of the 16-byte channel vector and <= 64 or a multiple of 64. */
 int el_dwconv_fwd(const void* x, const int64_t xs[4], const float* w, const float* bias, void* out,
                   const int64_t os[4], int B, int C, int H, int W, int k, int act, int dtype, void* stream);
