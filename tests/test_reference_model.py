@@ -120,3 +120,10 @@ def test_tal_formulation_matches_reference_on_random_cases(seed):
     assert bool(fg_g[hot].all()) and torch.equal(l_g[hot], l_w[hot]) and torch.equal(gi_g[hot], gi_w[hot]) and torch.equal(b_g[hot], b_w[hot])
     bg = ~fg_g & ~fg_w.bool()
     assert torch.equal(l_g[bg], l_w[bg]) and torch.equal(b_g[bg], b_w[bg])
+    # ... and the independent numpy restatement (oracle/tal_ref.py) under the same rule
+    from oracle import tal_ref
+
+    l_o, b_o, s_o, fg_o, gi_o = tal_ref.task_aligned_assign(*[t.numpy() for t in args], topk=topk, alpha=alpha, beta=beta)
+    np.testing.assert_allclose(s_o, s_w.numpy(), rtol=1e-5, atol=1e-9)
+    h = hot.numpy()
+    assert fg_o[h].all() and (l_o[h] == l_w.numpy()[h]).all() and (gi_o[h] == gi_w.numpy()[h]).all() and (b_o[h] == b_w.numpy()[h]).all()
