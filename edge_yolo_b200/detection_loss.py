@@ -113,7 +113,10 @@ class TaskAlignedAssigner:
         if M == 0:
             z = torch.zeros_like(scores[..., 0])
             return torch.full_like(z, self.num_classes), torch.zeros_like(boxes), torch.zeros_like(scores), z, z
-        if self.fused and scores.is_cuda:
+        if self.fused:
+            if not scores.is_cuda:
+                raise _lib.EdgelineError("TaskAlignedAssigner: CUDA tensors expected (el_tal_assign has no CPU fallback; "
+                                         "fused=False selects the torch-op formulation explicitly)")
             return self._assign_fused(scores, boxes, anchors, gt_labels, gt_boxes, gt_valid)
         valid = gt_valid.bool()                                                   # (B,M,1)
         # anchor centre strictly inside the ground-truth box (tal.py:241-262)

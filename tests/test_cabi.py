@@ -63,6 +63,11 @@ def test_no_cpu_fallback():
         ops.linear_attention(torch.randn(1, 192, 4, 4), 1)
     with pytest.raises(EdgelineError):
         ops.nms_batched(torch.rand(1, 6, 10))
+    from edge_yolo_b200.detection_loss import TaskAlignedAssigner
+
+    with pytest.raises(EdgelineError):  # the default assigner is the kernel path: CPU tensors are an error, not a detour through torch ops
+        TaskAlignedAssigner(topk=2, num_classes=3)(torch.rand(1, 4, 3), torch.rand(1, 4, 4), torch.rand(4, 2), torch.zeros(1, 1, 1),
+                                                    torch.rand(1, 1, 4), torch.ones(1, 1, 1, dtype=torch.bool))
 
 
 def test_product_does_not_import_oracle():
