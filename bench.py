@@ -411,9 +411,10 @@ def product_arm(a):
                                     "(each site timed alone, inputs rotated through > L2); traffic = DRAM bytes of the same launches in one step "
                                     "from the committed ncu capture (profiles/r01g_step_b64_time_dram.json), null for other configs"}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        rate, ms, threads = cpu_oracle_rate(a, steps=16, warmup=1)
+        cpu_steps = 16 if (a.scale, a.imgsz) == ("n", 640) else 4  # ~5-10 s of CPU work on the box's host cores either way
+        rate, ms, threads = cpu_oracle_rate(a, steps=cpu_steps, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"16 steps x {a.cpu_sample} images (bounded sample of the batch-{a.batch} workload), forward + decode + NMS, fp32"}
+                                "sample": f"{cpu_steps} steps x {a.cpu_sample} images (bounded sample of the batch-{a.batch} workload), forward + decode + NMS, fp32"}
     eld.shutdown()
     if rank == 0:
         _emit(line)
