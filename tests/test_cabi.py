@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -101,3 +102,37 @@ def test_nms_signature_matches_reference():
     # end-to-end shaped input never touches a kernel (ops.py:224-228)
     out = non_max_suppression(torch.tensor([[[0, 0, 1, 1, 0.9, 1.0], [0, 0, 1, 1, 0.1, 2.0]]]), conf_thres=0.25)
     assert out[0].shape == (1, 6)
+
+
+@pytest.mark.parametrize("N,src_c,M", [(64, [64], 1 << 20), (256, [128, 128], 25600), (80, [16, 48], 6400), (48, [32, 8, 72], 1 << 20)])
+def test_pack_pw_weight_layout(N, src_c, M):
+    """Host-side packing of a 1x1 conv weight into the resident UMMA B operand (ops.pack_pw_weight) against an independent reader of
+    the documented layout: per output-channel tile and K chunk one [n_tile][box] K-major tile, 16-byte chunk j of row r stored at
+    chunk j ^ ((r * row_bytes >> 7) & (row_bytes / 16 - 1)) (the TMA / UMMA 32-, 64- and 128-byte swizzles), tiles padded to 1 KiB."""
+    from edge_yolo_b200 import ops
+
+    K = sum(src_c)
+    w = ((torch.arange(N * K) * 7) % 251 - 125).float().reshape(N, K)      # exactly representable in bf16
+    from edge_yolo_b200 import _lib
+
+    n_tile = _lib.lib().el_pwconv_tile(N, 2 * sum(b for _, _, b in ops._pw_chunks(src_c)), M)
+    assert n_tile > 0 and n_tile % 16 == 0
+    packed = ops.pack_pw_weight(w, src_c, torch.bfloat16, M).float().numpy()
+    got = np.zeros((-(-N // n_tile) * n_tile, K), np.float32)
+    pos = 0
+    for t in range(-(-N // n_tile)):
+        for k0, creal, bw in ops._pw_chunks(src_c):
+            rb = 2 * bw                                                    # row bytes = swizzle span
+            tile = packed[pos : pos + n_tile * bw].reshape(n_tile, bw // 8, 8)
+            for r in range(n_tile):
+                f = ((r * rb) >> 7) & (rb // 16 - 1)
+                for j in range(bw // 8):
+                    c0 = 8 * j
+                    if c0 < creal:
+                        got[t * n_tile + r, k0 + c0 : k0 + c0 + 8] = tile[r, j ^ f]
+                    else:
+                        assert not tile[r, j ^ f].any()                    # channel padding of a narrow last box is zero
+            pos += -(-(n_tile * bw * 2) // 1024) * 512                     # elements: tile bytes rounded up to 1 KiB
+    assert pos == packed.size
+    np.testing.assert_array_equal(got[:N], w.numpy())
+    assert not got[N:].any()                                               # output-channel padding rows are zero
