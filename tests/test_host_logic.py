@@ -1,0 +1,57 @@
+"""Host-side logic that needs no GPU: BatchNorm folding of `EdgeLineYOLO.fuse` (the counterpart of BaseModel.fuse, nn/tasks.py:214-242,
+plus DSConv's BatchNorm) and the K-chunk table of the concat-free 1x1 convolution."""
+import pytest
+import torch
+
+from edge_yolo_b200 import EdgelineError, ops
+from edge_yolo_b200.model import EdgeLineYOLO
+from edge_yolo_b200.modules import Conv, DSConv
+
+
+def _randomise_bn(model, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.3)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.2)
+
+
+@torch.no_grad()
+def test_fuse_folds_batchnorm_exactly_for_conv_and_dsconv():
+    """Every Conv / DWConv / DSConv of the n graph gives the same output (fp32, eval) before and after `fuse(dsconv=True)`; the folded
+    modules keep no BatchNorm and the state-dict keys of the convolutions survive (checkpoint compatibility)."""
+    model = EdgeLineYOLO("n", 80).float().eval()
+    _randomise_bn(model)
+    g = torch.Generator().manual_seed(1)
+    probes = []
+    for name, m in model.named_modules():
+        if isinstance(m, (Conv, DSConv)):
+            c_in = m.conv.in_channels if isinstance(m, Conv) else m.dw.in_channels
+            x = torch.randn(2, c_in, 12, 12, generator=g)
+            probes.append((name, m, x, m(x)))
+    assert len(probes) > 60 and any(isinstance(m, DSConv) for _, m, _, _ in probes)
+    model.fuse(dsconv=True)
+    for name, m, x, want in probes:
+        got = m(x)
+        assert not isinstance(getattr(m, "bn", None), torch.nn.BatchNorm2d), name
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5, msg=lambda s, n=name: f"{n}: {s}")
+    keys = model.state_dict().keys()
+    assert "model.0.conv.weight" in keys and "model.0.conv.bias" in keys and not any(".bn." in k for k in keys if k.startswith("model.0."))
+
+
+def test_pw_chunks_cover_the_concatenated_k_in_order():
+    """`_pw_chunks`: per source 64-channel TMA boxes (16 / 32 for narrow sources), consecutive in the concatenated K, no box crossing a
+    source boundary -- what lets el_pwconv_fwd read `torch.cat([a, b, m1, ...], 1)` without materialising it (block.py:3783-3788)."""
+    for src_c in ([64], [16], [32, 32], [24, 64, 8], [128, 128, 64, 64], [40, 200]):
+        chunks = ops._pw_chunks(src_c)
+        k = 0
+        bounds = [sum(src_c[: i + 1]) for i in range(len(src_c))]
+        for k0, creal, bw in chunks:
+            assert k0 == k and 0 < creal <= bw and bw in (16, 32, 64)
+            assert not any(k0 < b < k0 + creal for b in bounds)            # stays inside one source
+            k += creal
+        assert k == sum(src_c)
+    with pytest.raises(EdgelineError):
+        ops._pw_chunks([20])                                               # sources are multiples of 8 channels (16-byte vectors)
