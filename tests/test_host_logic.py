@@ -55,3 +55,33 @@ def test_pw_chunks_cover_the_concatenated_k_in_order():
         assert k == sum(src_c)
     with pytest.raises(EdgelineError):
         ops._pw_chunks([20])                                               # sources are multiples of 8 channels (16-byte vectors)
+
+
+def test_non_max_suppression_host_branches():
+    """The branches of `non_max_suppression` decided on the host, as in utils/ops.py:215-232: threshold asserts (same messages), tuple
+    inputs, the end-to-end (B, N, 6) early return with its `classes` filter, and the hard errors outside the detection path."""
+    from edge_yolo_b200.nms import non_max_suppression
+
+    with pytest.raises(AssertionError, match="Invalid Confidence threshold 1.5"):
+        non_max_suppression(torch.zeros(1, 6, 4), conf_thres=1.5)
+    with pytest.raises(AssertionError, match="Invalid IoU -0.1"):
+        non_max_suppression(torch.zeros(1, 6, 4), iou_thres=-0.1)
+    g = torch.Generator().manual_seed(0)
+    e2e = torch.rand(2, 50, 6, generator=g)
+    e2e[..., 5] = torch.randint(0, 4, (2, 50), generator=g).float()
+    out = non_max_suppression((e2e, None), conf_thres=0.4, max_det=7)      # tuple: (inference output, loss output)
+    for o, p in zip(out, e2e):
+        assert torch.equal(o, p[p[:, 4] > 0.4][:7])
+    out = non_max_suppression(e2e, conf_thres=0.4, max_det=50, classes=[1, 3])
+    for o, p in zip(out, e2e):
+        keep = p[p[:, 4] > 0.4]
+        assert torch.equal(o, keep[(keep[:, 5] == 1) | (keep[:, 5] == 3)])
+    dense = torch.rand(1, 4 + 3, 20, generator=g)
+    with pytest.raises(NotImplementedError):
+        non_max_suppression(dense, rotated=True)
+    with pytest.raises(NotImplementedError):
+        non_max_suppression(dense, labels=[torch.zeros(1, 5)])
+    with pytest.raises(NotImplementedError):
+        non_max_suppression(dense, nc=2)                                    # 1 mask channel
+    with pytest.raises(EdgelineError):
+        non_max_suppression(dense)                                          # CPU tensor: no fallback
