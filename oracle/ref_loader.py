@@ -1,10 +1,16 @@
 """TEST INFRASTRUCTURE ONLY -- never imported by the product package.
 
-Imports the *unmodified* reference (`/root/reference/ultralytics`) inside the dev
-container so that golden vectors can be generated from it (see `gen_golden.py`).
-The reference cannot travel to the GPU box, so nothing in `-m gpu` tests, `smoke()`
-or `bench.py` may call this module; they use the committed fixtures in
-`tests/golden/` instead.
+Imports the *unmodified* reference `ultralytics` package.  Two locations are searched:
+
+  1. `/root/reference` (the read-only mount of the dev container) -- used to generate the golden
+     vectors (`gen_golden.py`);
+  2. `<repo>/baseline/_ref` -- the same package pip-installed by `__graft_entry__.build()`
+     (`pip install --no-index --no-deps --target baseline/_ref`, byte-identical .py / .yaml files).
+     That directory is git-ignored but ships to the GPU box with the gpurun snapshot, which is what lets
+     the `-m gpu` tests run `install()` behind the real `YOLO(cfg).predict / val / train` next to the
+     uninstalled reference on the same B200, and `bench.py --impl reference` time the unmodified reference.
+
+Nothing in the product package imports this module.
 
 The reference needs three packages that are absent from this image
 (SURVEY.md section 8c): matplotlib (utils/__init__.py:23), pywt (nn/modules/block.py:12,
@@ -20,7 +26,10 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("EDGELINE_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.environ.get("EDGELINE_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+REFERENCE_ROOT = next((p for p in _CANDIDATES if p and os.path.isdir(os.path.join(p, "ultralytics"))), "/root/reference")
+CFG_DIR = os.path.join(REFERENCE_ROOT, "ultralytics", "cfg", "models", "11")
 _STUBBED = ("matplotlib", "pywt", "thop", "seaborn")
 
 
@@ -41,6 +50,8 @@ class _StubLoader(importlib.abc.Loader):
             m.Wavelet = _Wavelet
         if spec.name == "thop":
             m.profile = lambda *a, **k: (0.0, 0.0)
+        if spec.name == "matplotlib.font_manager":  # utils/checks.py:325 (check_font) scans the system fonts before it tries to download
+            m.findSystemFonts = lambda *a, **k: []
         return m
 
     def exec_module(self, module):
@@ -65,6 +76,8 @@ def load():
     os.environ.setdefault("YOLO_CONFIG_DIR", "/tmp/edgeline_yolo_cfg")
     os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))  # ultralytics/__init__.py:7-9 forces 1
     os.makedirs(os.environ["YOLO_CONFIG_DIR"], exist_ok=True)
+    for font in ("Arial.ttf", "Arial.Unicode.ttf"):  # check_det_dataset -> check_font would try to download them (no network); plots stay off
+        open(os.path.join(os.environ["YOLO_CONFIG_DIR"], font), "ab").close()
     sys.dont_write_bytecode = True  # the reference mount is read-only
     if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
         sys.meta_path.append(_StubFinder())
