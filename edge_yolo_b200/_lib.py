@@ -26,7 +26,6 @@ _SIGNATURES = {
     "el_status_string": (c_char_p, [c_int]),
     "el_last_cuda_error": (c_int, []),
     "el_launch_count": (ctypes.c_uint64, []),
-    "el_debug_set_detect_stages": (None, [c_int]),
     "el_dwt_haar_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_dwt_haar_bwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_wave_merge_fwd": (c_int, [c_void_p, I64P, POINTER(c_void_p), I64P, c_void_p, c_void_p, I64P] + [c_int] * 7 + [c_void_p]),
@@ -44,7 +43,7 @@ _SIGNATURES = {
     "el_gfl_detect_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "el_gfl_detect_fwd": (c_int, [c_int, POINTER(c_void_p), I64P, POINTER(c_void_p), I64P, POINTER(c_int32), POINTER(c_float),
                                   POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
-                                  POINTER(c_void_p), c_int, c_int, c_int, c_float, c_double, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_size_t,
+                                  POINTER(c_void_p), c_int, c_int, c_int, c_float, c_double, c_int, c_int, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "el_nms_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
     "el_nms_batched": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_double, c_int, c_int, c_void_p, c_int, c_int, c_float,

@@ -761,8 +761,9 @@ extern "C" int el_gfl_detect_workspace_bytes(int B, int nc, int A, int multi_lab
 extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* box_s, const void* const* cls, const int64_t* cls_s, const int32_t* hw,
                                  const float* stride, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2,
                                  const float* const* box_bias, const float* const* cls_bias, int B, int nc, int dtype, float conf, double iou, int multi_label, int agnostic, const int32_t* class_keep,
-                                 int max_det, int max_nms, float max_wh, void* workspace, size_t workspace_bytes, float* out, int32_t* out_count,
+                                 int max_det, int max_nms, float max_wh, int stages, void* workspace, size_t workspace_bytes, float* out, int32_t* out_count,
                                  int64_t* out_index, void* stream) {
+    if (stages < 1 || stages > 7) return EL_ERR_ARG;
     if (nl <= 0 || nl > kMaxLevels || !box || !cls || !box_s || !cls_s || !hw || !stride || !w1 || !b1 || !w2 || !b2 || B <= 0 || nc <= 0 ||
         !workspace || !out || !out_count || max_det <= 0 || max_nms <= 0)
         return EL_ERR_ARG;
@@ -779,7 +780,7 @@ extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* 
     if (workspace_bytes < box_off + (size_t)B * P.A * sizeof(float4)) return EL_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
-    const bool do_emit = g_detect_stages & 1;
+    const bool do_emit = stages & 1;
     if (do_emit) nms_prepare(L, ws, st);
     EmitArgs E{conf, class_keep, (unsigned long long*)(ws + L.keys), L.key_stride, (int*)(ws + L.counts), (float4*)(ws + box_off), B};
     const size_t sm = emit_smem_bytes(nc, esz, nl);
@@ -804,6 +805,6 @@ extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* 
     }
 #undef EL_LAUNCH_EMIT
     if (int e = check_launch()) return e;
-    return nms_finish(L, ws, BoxSource{(const float*)(ws + box_off), (int64_t)P.A * 4, 4, 1}, B, nc, iou, agnostic, max_det, max_nms, max_wh, out,
+    return nms_finish(L, ws, BoxSource{(const float*)(ws + box_off), (int64_t)P.A * 4, 4, 1}, B, nc, iou, agnostic, max_det, max_nms, max_wh, stages, out,
                       out_count, out_index, st);
 }

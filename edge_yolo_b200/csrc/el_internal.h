@@ -23,16 +23,13 @@ struct BoxSource { const float* base; int64_t sb, sa, sk; };
 
 // zero counters / select state (call before emitting keys)
 void nms_prepare(const NmsLayout& L, void* ws, cudaStream_t s);
-// keys + counts are in the workspace: max_nms cut, sort, greedy sweep
+// keys + counts are in the workspace: max_nms cut + sort (stages bit 1), greedy sweep (stages bit 2)
 int nms_finish(const NmsLayout& L, void* ws, BoxSource src, int B, int nc, double iou, int agnostic, int max_det, int max_nms, float max_wh,
-               float* out, int32_t* out_count, int64_t* out_index, cudaStream_t s);
+               int stages, float* out, int32_t* out_count, int64_t* out_index, cudaStream_t s);
 
 // tensor-core path of el_stem_conv_u8 for 16-bit activations (stem_tc.cu)
 int stem_tc_launch(const uint8_t* src, const float* w, const float* bias, void* dst, Strides4 ds, int B, int C0, int H, int W, int dtype, cudaStream_t st);
 
 constexpr int kMaxDetSmem = 4096;
-
-// measurement aid (el_debug_set_detect_stages): bit0 = candidate emit, bit1 = select + sort, bit2 = sweep
-extern int g_detect_stages;
 
 }  // namespace el

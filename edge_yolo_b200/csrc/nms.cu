@@ -657,12 +657,10 @@ extern "C" int el_nms_workspace_bytes(int B, int nc, int A, int multi_label, int
 
 namespace el {
 
-int g_detect_stages = 7;
-
 void nms_prepare(const NmsLayout& L, void* ws, cudaStream_t s) { cudaMemsetAsync(ws, 0, L.keys, s); }  // counts, select state, histograms
 
 int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc, double iou, int agnostic, int max_det, int max_nms, float max_wh,
-               float* out, int32_t* out_count, int64_t* out_index, cudaStream_t s) {
+               int stages, float* out, int32_t* out_count, int64_t* out_index, cudaStream_t s) {
     char* ws = (char*)workspace;
     int* counts = (int*)(ws + L.counts);
     SelectState* st = (SelectState*)(ws + L.state);
@@ -670,7 +668,7 @@ int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc
     unsigned long long* keys = (unsigned long long*)(ws + L.keys);
     unsigned long long* keys2 = (unsigned long long*)(ws + L.keys2);
     SweepArgs P{};
-    const bool do_sort = g_detect_stages & 2, do_sweep = g_detect_stages & 4;
+    const bool do_sort = stages & 2, do_sweep = stages & 4;
     if (L.select && !do_sort) {
         P.keys = keys2; P.key_stride = L.key2_stride; P.counts = nullptr; P.st = st; P.cap = L.cap2;
     } else if (!do_sort) {
@@ -735,7 +733,7 @@ extern "C" int el_nms_batched(const float* pred, int B, int nc, int A, float con
     else
         nms_emit<false><<<eg, 256, 0, s>>>(pred, nc, A, conf, class_keep, (unsigned long long*)(ws + L.keys), L.key_stride, (int*)(ws + L.counts));
     note_launches(1);
-    return nms_finish(L, ws, BoxSource{pred, (int64_t)(4 + nc) * A, 1, A}, B, nc, iou, agnostic, max_det, max_nms, max_wh, out, out_count, out_index, s);
+    return nms_finish(L, ws, BoxSource{pred, (int64_t)(4 + nc) * A, 1, A}, B, nc, iou, agnostic, max_det, max_nms, max_wh, 7, out, out_count, out_index, s);
 }
 
 extern "C" int el_nms_boxes_workspace_bytes(int n, size_t* bytes) {
@@ -772,5 +770,3 @@ extern "C" int el_nms_boxes(const float* boxes, const float* scores, int n, doub
     note_launches(2);  // keys + sweep
     return check_launch();
 }
-
-extern "C" void el_debug_set_detect_stages(int mask) { el::g_detect_stages = mask & 7; }

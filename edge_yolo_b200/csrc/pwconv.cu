@@ -514,6 +514,28 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
     A.stage_bytes = (uint32_t)pw::kTileM * max_rb;
     A.a_stage_bytes = A.stage_bytes;
     const int n_tiles = (int)ceil_div(N, A.n_tile);
+    if (n_tiles > 1) {
+        // In-place use (a destination aliasing a K source, e.g. the enhancer's `fuse` GEMM writing over b) is only safe with ONE output-channel
+        // tile: the CTA of column tile nt loads ALL K channels of its pixel rows but stores only its own n_tile channels, so with the N axis
+        // split CTA (m, 0) could overwrite channels that CTA (m, 1) has not loaded yet (cross-CTA write-after-read race).  Refuse it.
+        auto aliases = [&](const void* o, int64_t o_pitch, int o_c) {
+            const char* ob0 = (const char*)o;
+            const char* ob1 = ob0 + ((M - 1) * o_pitch + o_c) * 2;
+            for (int i = 0; i < nsrc; ++i) {
+                const char* sb0 = (const char*)src[i];
+                const char* sb1 = sb0 + ((M - 1) * src_pitch[i] + src_c[i]) * 2;
+                if (ob1 <= sb0 || sb1 <= ob0) continue;            // disjoint byte ranges
+                if (o_pitch == src_pitch[i]) {                      // channel slices of one pixel-major buffer: disjoint channel windows are fine
+                    int64_t d = ((ob0 - sb0) / 2) % o_pitch;
+                    if (d < 0) d += o_pitch;
+                    if (d >= src_c[i] && d + o_c <= o_pitch) continue;
+                }
+                return true;
+            }
+            return false;
+        };
+        if (aliases(out, out_pitch, out2 ? split : N) || (out2 && aliases(out2, out2_pitch, N - split))) return EL_ERR_ARG;
+    }
     // store box: up to 64 channels; with two destinations it must not straddle the split
     int ob = 64;
     if (out2) while (split % ob) ob >>= 1;

@@ -28,6 +28,16 @@ from . import ops
 # ------------------------------------------------------------------------------------------
 
 
+def _ver(p: torch.Tensor) -> int:
+    """`p._version`, or -1 for inference tensors (no version counter; they cannot be modified in place outside inference mode, and
+    the caches below also key on the storage pointer).  The reference's validator loads and fuses checkpoints under
+    `torch.inference_mode` (engine/validator.py:108, utils/torch_utils.py:62-72), so its parameters are inference tensors."""
+    try:
+        return p._version
+    except RuntimeError:
+        return -1
+
+
 def dwt_forward(self, x: torch.Tensor):
     """`_PywtDWT2D.forward` (nn/modules/block.py:3619-3642): returns (LL, LH, HL, HH)."""
     if getattr(self, "wave_name", "haar") != "haar":
@@ -59,25 +69,29 @@ def wavelet_enhancer_forward(self, b: torch.Tensor, inplace: bool = False, out2:
 
 
 def wavelet_enhancer_engine_forward(self, b: torch.Tensor) -> torch.Tensor:
-    """`_WaveletEnhancer.forward` (block.py:3685-3710) for the inference engine, in place on b: DWT split -> f_ll (tcgen05 1x1) /
+    """`_WaveletEnhancer.forward` (block.py:3685-3710) for the inference engine (in place on b where that is race-free): DWT split -> f_ll (tcgen05 1x1) /
     shared f_h (cuDNN 3x3) -> bands-only upsample*w kernel -> ONE GEMM for `fuse` that reads [b | upsampled bands] in place
     (no concat of b) and applies bias + SiLU + the gated residual b + tanh(gamma) * y in its epilogue."""
     fuse = self.fuse
-    if not (hasattr(fuse, "el_bias") and b.dtype in (torch.bfloat16, torch.float16) and _pixel_linear(b) and b.shape[1] % 16 == 0
-            and b.shape[2] % 2 == 0 and b.shape[3] % 2 == 0 and _pw_ok(fuse.conv, [b])):
+    B, c, H, W = b.shape
+    n_tiles = _pw_n_tiles(fuse.conv, (c, 2 * c), B * H * W) if c % 16 == 0 else 99  # of the GEMM that really runs: K = [b | 2c upsampled bands]
+    if not (hasattr(fuse, "el_bias") and b.dtype in (torch.bfloat16, torch.float16) and _pixel_linear(b) and c % 16 == 0
+            and H % 2 == 0 and W % 2 == 0 and _pw_ok(fuse.conv, [b]) and n_tiles <= 4):
         return wavelet_enhancer_forward(self, b, inplace=True)
-    B, _, H, W = b.shape
     buf = ops.dwt_haar(b)
     LLp = self.f_ll(buf[:B])
     hp = self.f_h(buf[B:])
     a32 = self.__dict__.get("el_alpha32")  # fp32 copy of alpha for the kernel, cached until alpha is modified (a 16-bit model would
-    if a32 is None or a32[0] != self.alpha._version or a32[1].device != self.alpha.device:  # otherwise launch a cast kernel per call)
-        a32 = self.el_alpha32 = (self.alpha._version, self.alpha.detach().float().contiguous())
+    if a32 is None or a32[0] != (_ver(self.alpha), self.alpha.data_ptr()) or a32[1].device != self.alpha.device:  # otherwise launch a cast kernel per call)
+        a32 = self.el_alpha32 = ((_ver(self.alpha), self.alpha.data_ptr()), self.alpha.detach().float().contiguous())
     U = ops.wave_merge_bands(LLp, hp[:B], hp[B : 2 * B], hp[2 * B :], a32[1], H, W)
     gate = self.__dict__.get("el_gate")
-    if gate is None or gate[0] != self.gamma._version:  # tanh(gamma) as a host scalar, cached until gamma is modified
-        gate = self.el_gate = (self.gamma._version, float(torch.tanh(self.gamma.detach().float())))
-    return pw_apply(fuse.conv, [b, U], _bias_on(fuse, b), fuse.el_act, out=b, residual=b, res_scale=gate[1])
+    if gate is None or gate[0] != (_ver(self.gamma), self.gamma.data_ptr()):  # tanh(gamma) as a host scalar, cached until gamma is modified
+        gate = self.el_gate = ((_ver(self.gamma), self.gamma.data_ptr()), float(torch.tanh(self.gamma.detach().float())))
+    # In place over b only when ONE CTA column owns all output channels of a pixel tile.  With N split over several CTAs, CTA (m, 0) would
+    # store its channels of b while CTA (m, 1) may still be loading all of b as its A operand (el_pwconv_fwd refuses that aliasing).
+    out = b if n_tiles == 1 else torch.empty_like(b)
+    return pw_apply(fuse.conv, [b, U], _bias_on(fuse, b), fuse.el_act, out=out, residual=b, res_scale=gate[1])
 
 
 def linear_attention_forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -87,7 +101,7 @@ def linear_attention_forward(self, x: torch.Tensor) -> torch.Tensor:
 
 def _dgqp_weights(self):
     """fp32 views of the DGQP heads `reg_conf[i]` = Conv2d(20,64,1) ReLU Conv2d(64,1,1) Sigmoid (head.py:847-854)."""
-    key = tuple((p.data_ptr(), p._version, p.dtype, p.device) for seq in self.reg_conf for p in seq.parameters())
+    key = tuple((p.data_ptr(), _ver(p), p.dtype, p.device) for seq in self.reg_conf for p in seq.parameters())
     cache = getattr(self, "_el_dgqp", None)
     if cache is None or cache[0] != key:
         ws = []
@@ -229,14 +243,19 @@ def _pw_ok(conv: nn.Conv2d, srcs, *others) -> bool:
     # the weight block of one output-channel tile stays resident in shared memory (<= 128 KB): very wide K splits N into many tiles,
     # each of which re-reads the activations -- beyond 4 tiles cuDNN is the better choice
     x0 = srcs[0]
-    key = (tuple(t.shape[1] for t in srcs), x0.shape[0] * x0.shape[2] * x0.shape[3])
+    return _pw_n_tiles(conv, tuple(t.shape[1] for t in srcs), x0.shape[0] * x0.shape[2] * x0.shape[3]) <= 4
+
+
+def _pw_n_tiles(conv: nn.Conv2d, src_channels: tuple, M: int) -> int:
+    """Output-channel tiles el_pwconv_fwd uses for this (source split, pixel count): the el_pwconv_tile rule, cached on the conv."""
+    key = (tuple(src_channels), M)
     cache = conv.__dict__.setdefault("el_pw_tiles", {})
     n_tiles = cache.get(key)
     if n_tiles is None:
         row_bytes = sum(2 * bw for _, _, bw in ops._pw_chunks(key[0]))
         n_tile = ops._lib.lib().el_pwconv_tile(conv.out_channels, row_bytes, key[1])
         n_tiles = cache[key] = (-(-conv.out_channels // n_tile) if n_tile > 0 else 99)
-    return n_tiles <= 4
+    return n_tiles
 
 
 USE_CONV3X3 = True  # el_conv3x3_fwd for the dense 3x3 convs of the engine graph
@@ -266,9 +285,13 @@ def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=Non
     cache = conv.__dict__.setdefault("el_wpk", {})
     x0 = srcs[0]
     M = x0.shape[0] * x0.shape[2] * x0.shape[3]
-    key = (tuple(t.shape[1] for t in srcs), x0.dtype, x0.device, M if M < (1 << 16) else 0)  # the tile split depends on M only for small maps
+    # the tile split depends on M only for small maps; weight version + storage pointer: an in-place update or a load_state_dict after
+    # fuse(engine=True) repacks instead of silently using stale tiles
+    key = (tuple(t.shape[1] for t in srcs), x0.dtype, x0.device, M if M < (1 << 16) else 0, _ver(conv.weight), conv.weight.data_ptr())
     wpk = cache.get(key)
     if wpk is None:
+        for k in [k for k in cache if k[:4] == key[:4]]:
+            del cache[k]  # superseded packing of the same site
         wpk = cache[key] = ops.pack_pw_weight(conv.weight, key[0], key[1], M).to(key[2])
     return ops.pwconv(srcs, wpk, conv.out_channels, bias=bias, act=act, residual=residual, out=out, out2=out2, res_scale=res_scale,
                       up_addend=up_addend)
@@ -296,10 +319,12 @@ def upcat_cv1(cv1, uc: UpCat, out, out2):
     conv = cv1.conv
     C1 = x_low.shape[1]
     halves = conv.__dict__.get("el_up_halves")
+    if halves is not None and halves[2] != (_ver(conv.weight), conv.weight.data_ptr()):
+        halves = None  # cv1's weight was modified after the split was cached
     if halves is None:
         lo, sk = nn.Conv2d(C1, conv.out_channels, 1, bias=False), nn.Conv2d(skip.shape[1], conv.out_channels, 1, bias=False)
         lo.weight, sk.weight = nn.Parameter(conv.weight[:, :C1].detach().clone(), False), nn.Parameter(conv.weight[:, C1:].detach().clone(), False)
-        halves = conv.el_up_halves = (lo, sk)
+        halves = conv.el_up_halves = (lo, sk, (_ver(conv.weight), conv.weight.data_ptr()))
     z = pw_apply(halves[0], [x_low], None, ops.ACT_NONE)
     return pw_apply(halves[1], [skip], _bias_on(cv1, skip), cv1.el_act, out=out, out2=out2, up_addend=z)
 

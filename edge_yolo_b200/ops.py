@@ -421,17 +421,11 @@ def gfl_detect(boxes, clss, dgqp, strides, conf_thres=0.25, iou_thres=0.45, mult
         keep = keep.to(dev)
     cols = [_ptrs([w[k] for w in dgqp]) for k in range(4)]
     bb, cb = _bias_tables(bias, nl)
-    if stages != 7:
-        L.el_debug_set_detect_stages(int(stages))
-    try:
-        st = L.el_gfl_detect_fwd(nl, _ptrs(boxes), _i64(bs), _ptrs(clss), _i64(cs), (c_int32 * len(hw))(*hw),
-                                 (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3], bb, cb, B, nc, _dt(boxes[0]),
-                                 float(conf_thres), float(iou_thres), int(bool(multi_label)), int(bool(agnostic)),
-                                 keep.data_ptr() if keep is not None else None, int(max_det), int(max_nms), float(max_wh), ws.data_ptr(),
-                                 need.value, out.data_ptr(), cnt.data_ptr(), None, _stream())
-    finally:
-        if stages != 7:
-            L.el_debug_set_detect_stages(7)
+    st = L.el_gfl_detect_fwd(nl, _ptrs(boxes), _i64(bs), _ptrs(clss), _i64(cs), (c_int32 * len(hw))(*hw),
+                             (c_float * nl)(*[float(s) for s in strides]), cols[0], cols[1], cols[2], cols[3], bb, cb, B, nc, _dt(boxes[0]),
+                             float(conf_thres), float(iou_thres), int(bool(multi_label)), int(bool(agnostic)),
+                             keep.data_ptr() if keep is not None else None, int(max_det), int(max_nms), float(max_wh), int(stages), ws.data_ptr(),
+                             need.value, out.data_ptr(), cnt.data_ptr(), None, _stream())
     if st == 2 and stages != 7:
         raise EdgelineError("gfl_detect: staged execution needs dense NHWC head maps")
     if st == 2:  # EL_ERR_UNSUPPORTED: strided / NCHW / unaligned maps -> two-call path with the same kernels downstream

@@ -46,12 +46,6 @@ int el_last_cuda_error(void);
 /* Number of kernels this library has enqueued so far in the process (measurement aid: bench.py
  * reports the per-step delta as `gpu_launches`). */
 unsigned long long el_launch_count(void);
-/* Stage mask of el_gfl_detect_fwd / el_nms_batched's tail (bit0 decode + candidate emit, bit1 select + sort, bit2 sweep;
- * default 7 = everything): the following calls launch only the selected stages on the caller's workspace.  Used by bench.py to
- * time the stages separately and by the inference engine to capture the chain as separate CUDA graphs (the NMS of batch i
- * overlaps the forward of batch i+1).  Process-global: set, call, restore from one thread. */
-void el_debug_set_detect_stages(int mask);
-
 /* ---- a1. Haar analysis: _PywtDWT2D.forward, nn/modules/block.py:3619-3642 -------------------
  * x (B,C,H,W) -> bands (4,B,C,H/2,W/2) in the order LL,LH,HL,HH; xs = {sn,sc,sh,sw},
  * bs = {sband,sn,sc,sh,sw}.  Odd trailing row/column is dropped (floor), taps are
@@ -126,7 +120,11 @@ int el_gfl_decode_fwd(int nl, const void* const* box, const int64_t* box_s, cons
  * 64-anchor tiles of the NHWC head outputs with bulk TMA copies, decode them in shared memory and write
  * only the xywh boxes (B,A,4) and the candidate keys; results are bit-identical to
  * el_gfl_decode_fwd + el_nms_batched.  Returns EL_ERR_UNSUPPORTED when the maps are not dense NHWC with
- * 16-byte-aligned tile rows (callers then use the two-call path). */
+ * 16-byte-aligned tile rows (callers then use the two-call path).
+ * `stages` selects which part of the chain this call enqueues on the caller's workspace (bit 0 decode + candidate emit,
+ * bit 1 max_nms cut + sort, bit 2 sweep; 7 = everything): the inference engine captures stage 1 and stages 6 as two CUDA
+ * graphs so that the NMS tail of batch i overlaps the forward of batch i+1, and bench.py times the stages separately.
+ * The argument is per call -- the library keeps no mutable state between calls (re-entrant across threads / streams). */
 int el_gfl_detect_workspace_bytes(int B, int nc, int A, int multi_label, int max_nms, size_t* bytes);
 int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* box_s, const void* const* cls,
                       const int64_t* cls_s, const int32_t* hw, const float* stride,
@@ -134,8 +132,8 @@ int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* box_s, cons
                       const float* const* b2, const float* const* box_bias,
                       const float* const* cls_bias, int B, int nc, int dtype, float conf_thres,
                       double iou_thres, int multi_label, int agnostic, const int32_t* class_keep,
-                      int max_det, int max_nms, float max_wh, void* workspace, size_t workspace_bytes,
-                      float* out, int32_t* out_count, int64_t* out_index, void* stream);
+                      int max_det, int max_nms, float max_wh, int stages, void* workspace,
+                      size_t workspace_bytes, float* out, int32_t* out_count, int64_t* out_index, void* stream);
 
 /* ---- a9. batched NMS: non_max_suppression, utils/ops.py:167-316 (detection, nm=0) ------------
  * pred (B,4+nc,A) fp32 contiguous, xywh + scores (the tensor el_gfl_decode_fwd writes).

@@ -86,3 +86,22 @@ def load():
     import ultralytics  # noqa: E402
 
     return ultralytics
+
+
+def model_yaml(scale: str = "n", nc: int | None = None, tmp_dir: str | None = None) -> str:
+    """Path that `YOLO(...)` / `DetectionModel(...)` accept for EdgeLine-YOLO-<scale> (cfg/models/11/yolo11-test.yaml).  With `nc`, a copy of
+    the reference's yaml whose only change is the class count: yaml_model_load strips the scale letter from the file name and opens
+    `yolo11-test.yaml` beside it (nn/tasks.py:1150-1180), so the copy is written under that name into `tmp_dir`."""
+    import re
+
+    if nc is None:
+        return os.path.join(CFG_DIR, f"yolo11{scale}-test.yaml")
+    with open(os.path.join(CFG_DIR, "yolo11-test.yaml")) as f:
+        text = f.read()
+    text, n = re.subn(r"(?m)^nc:\s*\d+", f"nc: {nc}", text, count=1)
+    assert n == 1, "nc line not found in the reference yaml"
+    tmp_dir = tmp_dir or os.path.join(os.environ.get("YOLO_CONFIG_DIR", "/tmp/edgeline_yolo_cfg"), f"nc{nc}")
+    os.makedirs(tmp_dir, exist_ok=True)
+    with open(os.path.join(tmp_dir, "yolo11-test.yaml"), "w") as f:
+        f.write(text)
+    return os.path.join(tmp_dir, f"yolo11{scale}-test.yaml")

@@ -58,6 +58,9 @@ class FakePredictor:
 torch.cuda.Event = FakeEvent
 torch.cuda.is_available = lambda: True
 torch.cuda.set_device = lambda d: None
+_real_device = torch.device
+_real_empty = torch.empty
+torch.empty = lambda *a, **k: _real_empty(*a, **{kk: (vv if kk != 'device' else 'cpu') for kk, vv in k.items()})
 torch.cuda.synchronize = lambda *a, **k: None
 torch.Tensor.pin_memory = lambda self: self
 

@@ -6,7 +6,6 @@ GPU box: baseline/_ref, shipped with the gpurun snapshot).
 from __future__ import annotations
 
 import os
-import re
 
 import torch
 
@@ -21,19 +20,8 @@ def reference():
 
 
 def model_yaml(tmp_dir: str, scale: str = "n", nc: int | None = None) -> str:
-    """Path that `YOLO(...)` accepts for EdgeLine-YOLO-<scale>.  With `nc`, a copy of the reference's yolo11-test.yaml whose
-    only change is the class count (yaml_model_load strips the scale letter and opens `yolo11-test.yaml` beside it, nn/tasks.py:1150-1180)."""
     _, rl = reference()
-    src = os.path.join(rl.CFG_DIR, "yolo11-test.yaml")
-    if nc is None:
-        return os.path.join(rl.CFG_DIR, f"yolo11{scale}-test.yaml")
-    text = open(src).read()
-    text, n = re.subn(r"(?m)^nc:\s*\d+", f"nc: {nc}", text, count=1)
-    assert n == 1, "nc line not found in the reference yaml"
-    os.makedirs(tmp_dir, exist_ok=True)
-    with open(os.path.join(tmp_dir, "yolo11-test.yaml"), "w") as f:
-        f.write(text)
-    return os.path.join(tmp_dir, f"yolo11{scale}-test.yaml")
+    return rl.model_yaml(scale, nc, tmp_dir)
 
 
 def synth_checkpoint_state():

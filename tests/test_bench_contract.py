@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _line(*flags):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_mock_bench.py"), "--steps", "4", "--warmup", "3", "--no-profile",
-                        "--no-cpu-baseline", *flags], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                        "--no-cpu-baseline", "--sustained-seconds", "0.05", *(flags if "--extras" in flags else ("--no-extras", *flags))], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout                                   # exactly ONE JSON line on stdout
@@ -39,3 +39,14 @@ def test_product_arm_names_a_non_default_configuration():
     assert "EdgeLine-YOLO-s" in d["metric"] and "1280x1280" in d["metric"]
     w = d["config"]["workload"]
     assert "conf 0.001" in w and "multi_label" in w and "33600 anchors" in w and d["config"]["batch_per_gpu"] == 32
+
+
+def test_product_arm_extra_inference_configs_ride_in_the_same_line():
+    d = _line("--extras", "c2,c3")
+    x = d["extra_configs"]
+    assert set(x) == {"configs[2]", "configs[3]"}
+    assert "1280x1280" in x["configs[2]"]["metric"] and "EdgeLine-YOLO-s" in x["configs[2]"]["metric"] and x["configs[2]"]["scaling"] == "weak"
+    assert x["configs[3]"]["scaling"] == "strong" and x["configs[3]"]["global_batch"] == 512 and x["configs[3]"]["batch_per_gpu"] == 512
+    assert x["configs[3]"]["e2e"]["h2d_bytes_per_step"] == 512 * 640 * 640 * 3
+    assert d["sustained"]["seconds"] >= 0.05 and d["sustained"]["steps"] >= 4 and d["sustained"]["value"] > 0
+    assert d["e2e"]["h2d_gbs_per_rank"] > 0

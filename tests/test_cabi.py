@@ -54,6 +54,25 @@ def test_argument_validation_without_gpu(lib):
     assert lib.el_qfl_partials(64 * 8400 * 80) >= 148
 
 
+def test_pwconv_refuses_in_place_output_when_n_is_tiled(lib):
+    """el_pwconv_fwd: a destination aliasing a K source is a cross-CTA write-after-read race as soon as the output channels are split over
+    several CTAs: refused with EL_ERR_ARG before any CUDA work; disjoint channel slices of one buffer stay legal (they
+    fail later, on this GPU-less machine, with EL_ERR_CUDA from the tensor-map encode)."""
+    from ctypes import c_int32, c_int64, c_void_p
+
+    M, c = 64 * 20 * 20, 128
+    assert -(-c // lib.el_pwconv_tile(c, 2 * 3 * c, M)) > 1  # the enhancer's fuse GEMM at 20x20, batch 64: two output-channel tiles
+    b, U, w, fresh = 0x10000000, 0x20000000, 0x30000000, 0x40000000
+    call = lambda srcs, pitches, cs, out, out_pitch, N=c: lib.el_pwconv_fwd(
+        len(srcs), (c_void_p * len(srcs))(*srcs), (c_int64 * len(srcs))(*pitches), (c_int32 * len(srcs))(*cs), w, None, b, c, 1.0, 0, 0, out, out_pitch,
+        None, 0, 0, M, N, 1, 2, None)
+    assert call([b, U], [c, 2 * c], [c, 2 * c], b, c) == 1            # out aliases source 0: refused
+    assert call([b, U], [c, 2 * c], [c, 2 * c], fresh, c) != 1        # out of place: passes validation
+    # channel slices of ONE (M, 4c) buffer: source = channels [0, 2c), destination = channels [2c, 3c) -> legal; overlapping windows -> refused
+    assert call([b], [4 * c], [2 * c], b + 2 * (2 * c), 4 * c) != 1
+    assert call([b], [4 * c], [2 * c], b + 2 * c, 4 * c) == 1
+
+
 def test_no_cpu_fallback():
     from edge_yolo_b200 import EdgelineError, ops
 

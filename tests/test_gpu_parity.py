@@ -689,6 +689,87 @@ def test_predictor_matches_api_path():
         assert d.shape == w.shape
 
 
+@pytest.mark.parametrize("scale", ["n", "s"])
+def test_predictor_benchmark_configuration_matches_unpipelined_and_two_call_paths(scale):
+    """The configuration bench.py measures (batch 64, 640x640, two pipelined CUDA graphs, level streams, persistent multi-tile GEMM CTAs)
+    against (a) the same engine run eagerly without graphs and (b) the dense decode + nms_batched two-call path: bit-equal rows and counts
+    over several steps with changing inputs.  Scheduling-dependent faults (in-place GEMM race) only show at this size."""
+    from edge_yolo_b200.engine import Predictor, build_model
+    from edge_yolo_b200.nms import non_max_suppression
+
+    B, S = 64, 640
+    model = build_model(scale, 80, seed=0, device=DEV)
+    pred = Predictor(model, batch=B, imgsz=S, pipeline_nms=True)
+    eager = Predictor(model, batch=B, imgsz=S, use_graph=False)
+    gen = torch.Generator().manual_seed(77)
+    hosts = [torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(3)]
+    got = {}
+    pred.predict_many(hosts + hosts, consume=lambda i, rows, cnt: got.__setitem__(i, (rows.clone(), cnt.clone())))
+    for i, h in enumerate(hosts):
+        rows_e, cnt_e = eager.predict_u8(h)
+        for k in (i, i + 3):  # both buffer sets, with other batches in flight around them
+            rows, cnt = got[k]
+            assert torch.equal(cnt, cnt_e), f"step {k}: counts differ from the eager engine"
+            for b in range(B):
+                n = int(cnt[b])
+                assert rows[b, :n].numpy().tobytes() == rows_e[b, :n].numpy().tobytes(), f"step {k} image {b}"
+    for m in model.modules():
+        if hasattr(m, "el_detect"):
+            m.el_detect = None
+    with torch.no_grad():
+        y, _ = model(None, stem_out=ops().stem_conv_u8(hosts[0].to(DEV), *pred.stem))
+        want = non_max_suppression(y, conf_thres=0.25, iou_thres=0.7, max_det=300)
+    rows, cnt = got[0]
+    assert [int(c) for c in cnt] == [w.shape[0] for w in want]
+    for b in range(B):
+        assert rows[b, : int(cnt[b])].numpy().tobytes() == want[b].cpu().numpy().tobytes()
+
+
+@pytest.mark.parametrize("c,hw", [(128, 20), (256, 20), (64, 40)])
+def test_enhancer_tail_in_place_is_race_free_under_sm_pressure(c, hw):
+    """The engine's enhancer tail (fuse GEMM over [b | upsampled bands] with the gated residual in its epilogue) at the bench batch,
+    while another stream hogs SMs so that the grid's CTAs are NOT all co-resident: equal to the out-of-place call (with the
+    output channels split over several CTAs the old in-place form let one CTA overwrite b while another still loaded it)."""
+    from edge_yolo_b200 import modules as M
+
+    o = ops()
+    B, dtype, cl = 64, torch.bfloat16, torch.channels_last
+    gen = torch.Generator().manual_seed(c + hw)
+    torch.manual_seed(c)
+    enh = M._WaveletEnhancer(c).eval()
+    with torch.no_grad():
+        enh.gamma.fill_(0.5)
+    from edge_yolo_b200.model import EdgeLineYOLO
+
+    holder = torch.nn.Module()
+    holder.model = torch.nn.Sequential(enh)
+    EdgeLineYOLO.fuse(holder, engine=True)  # BatchNorm folding + engine epilogues for this one block
+    holder = holder.to(DEV, dtype).to(memory_format=cl)
+    for m in holder.modules():
+        for k, v in list(vars(m).items()):
+            if k.startswith("el_") and isinstance(v, torch.Tensor):
+                setattr(m, k, v.to(DEV))
+    b0 = torch.randn(B, c, hw, hw, generator=gen).to(DEV, dtype).contiguous(memory_format=cl)
+    with torch.no_grad():
+        want = M.wavelet_enhancer_engine_forward(enh, b0.clone())
+        torch.cuda.synchronize()
+        hog = torch.cuda.Stream()
+        big = torch.randn(8192, 8192, device=DEV, dtype=dtype)
+        for _ in range(5):
+            with torch.cuda.stream(hog):
+                for _ in range(4):
+                    big @ big  # keeps most SMs busy while the enhancer's kernels trickle in
+            got = M.wavelet_enhancer_engine_forward(enh, b0.clone())
+            torch.cuda.synchronize()
+            assert torch.equal(got, want)
+    # and the C ABI refuses the unsafe aliasing outright
+    n_tiles = M._pw_n_tiles(enh.fuse.conv, (c, 2 * c), B * hw * hw)
+    if n_tiles > 1:
+        U = torch.randn(B, 2 * c, hw, hw, device=DEV).to(dtype).contiguous(memory_format=cl)
+        with pytest.raises(Exception):
+            M.pw_apply(enh.fuse.conv, [b0, U], M._bias_on(enh.fuse, b0), enh.fuse.el_act, out=b0, residual=b0, res_scale=0.4)
+
+
 @pytest.mark.parametrize("scale,nc,batch,imgsz,kw", [
     ("n", 80, 3, 352, {}),                                             # ragged 128-pixel tiles at every level, odd batch
     ("n", 10, 1, 224, dict(conf=0.001, multi_label=True)),             # nc not a multiple of 8: the class towers' last conv falls back to cuDNN

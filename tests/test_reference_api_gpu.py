@@ -83,21 +83,36 @@ def test_nms_rows_bit_exact_behind_reference_namespace(api):
             assert g.cpu().numpy().tobytes() == wg.cpu().numpy().tobytes(), f"rows differ from the reference's CUDA path for {kw}"
 
 
+def _match(dets, row):
+    """Row of `dets` (k, 6) of the same class closest to `row`: (max |box delta| in px, |conf delta|) or None."""
+    same = dets[dets[:, 5] == row[5]]
+    if not same.shape[0]:
+        return None
+    d = (same[:, :4] - row[:4]).abs().max(1).values
+    j = int(d.argmin())
+    return float(d[j]), abs(float(same[j, 4] - row[4]))
+
+
 @pytest.mark.parametrize("half", [False, True])
 def test_predict_through_yolo_api(api, half):
     """YOLO.predict (engine/model.py:501) -> BasePredictor.stream_inference (engine/predictor.py:220-300) -> DetectionPredictor.postprocess
-    (models/yolo/detect/predict.py:23-41) -> Results; tensor source (data/loaders.py:516-570).  half=True is the reference's fp16 mode (Q11)."""
+    (models/yolo/detect/predict.py:23-41) -> Results; tensor source (data/loaders.py:516-570).  half=True is the reference's fp16 mode (Q11):
+    the 16-bit contract (2e-2) is stated against the reference's fp32 outputs, and the reference's own fp16 mode is measured beside it."""
     R, tmp = api
     m = R.build_yolo(tmp, trained=True)
     x = _images(8, seed=11)[0]
-    kw = dict(device=0, conf=0.25, iou=0.7, max_det=300, half=half, verbose=False)
-    res_ref = m.predict(x, **kw)
+    kw = dict(device=0, conf=0.25, iou=0.7, max_det=300, verbose=False)
+    res_ref = m.predict(x, half=False, **kw)
+    m.predictor = None  # the predictor caches its AutoBackend; the fp32 / fp16 cast of the model happens at its setup (engine/predictor.py:300-312)
+    res_ref16 = m.predict(x, half=True, **kw) if half else None
+    m.predictor = None
     with R.installed() as inst:
-        res_el = m.predict(x, **kw)
+        res_el = m.predict(x, half=half, **kw)
         assert inst.launches > 0
+    m.predictor = None
     assert len(res_ref) == len(res_el) == 8
-    n_total = 0
-    for a, b in zip(res_el, res_ref):
+    n_total, worst_el, worst_ref16 = 0, [0.0, 0.0], [0.0, 0.0]
+    for i, (a, b) in enumerate(zip(res_el, res_ref)):
         da, db = a.boxes.data.float().cpu(), b.boxes.data.float().cpu()
         n_total += db.shape[0]
         if not half:
@@ -105,16 +120,22 @@ def test_predict_through_yolo_api(api, half):
             assert torch.equal(da[:, 5], db[:, 5]), "classes differ"
             np.testing.assert_allclose(da[:, :4].numpy(), db[:, :4].numpy(), rtol=1e-5, atol=S * 1e-5)
             np.testing.assert_allclose(da[:, 4].numpy(), db[:, 4].numpy(), rtol=0, atol=1e-5)
-        else:  # fp16 model: 2e-2 contract; detections near the confidence threshold may appear / vanish, so match boxes by class + position
-            assert abs(da.shape[0] - db.shape[0]) <= max(1, db.shape[0] // 10)
-            for row in db:
-                if float(row[4]) < 0.35:
-                    continue
-                same = da[da[:, 5] == row[5]]
-                assert same.shape[0], "a confident reference detection has no counterpart"
-                d = (same[:, :4] - row[:4]).abs().max(1).values
-                j = int(d.argmin())
-                assert float(d[j]) < 0.02 * S and abs(float(same[j, 4] - row[4])) < 2e-2
+            continue
+        # fp16 model: detections near the confidence threshold may appear / vanish, so match the confident ones by class + position
+        d16 = res_ref16[i].boxes.data.float().cpu()
+        assert abs(da.shape[0] - db.shape[0]) <= max(1, db.shape[0] // 10)
+        for row in db:
+            if float(row[4]) < 0.35:
+                continue
+            got, ref16 = _match(da, row), _match(d16, row)
+            assert got is not None, "a confident reference detection has no counterpart"
+            worst_el = [max(worst_el[0], got[0]), max(worst_el[1], got[1])]
+            if ref16 is not None:
+                worst_ref16 = [max(worst_ref16[0], ref16[0]), max(worst_ref16[1], ref16[1])]
+    if half:
+        print(f"\nfp16 predict vs the reference's fp32 detections: installed box {worst_el[0]:.3f} px conf {worst_el[1]:.4f}; "
+              f"the reference's own fp16 mode box {worst_ref16[0]:.3f} px conf {worst_ref16[1]:.4f}")
+        assert worst_el[0] < 0.02 * S and worst_el[1] < 2e-2, worst_el
     assert n_total >= 8, "the synthetic checkpoint should detect at least one object per image"
 
 
@@ -168,8 +189,13 @@ def test_train_step_loss_and_gradients_through_model_call(api):
     net.criterion = None
     assert _rel(l_el, l_ref) < 1e-4 and _rel(i_el, i_ref) < 1e-4, (l_el, l_ref, i_el, i_ref)
     assert set(g_el) == set(g_ref)
-    worst = max((_rel(g_el[n], g_ref[n]), n) for n in g_ref if float(g_ref[n].abs().max()) > 0)
-    assert worst[0] < 2e-3, worst  # fp32 sums in another order through ~100 layers of backward
+    # Per-parameter max |delta| relative to that parameter's largest reference gradient, floored at 1e-4 of the largest gradient of the
+    # whole model: several gradients are exactly zero in exact arithmetic (a BatchNorm bias in front of a 1x1 conv + train-mode BatchNorm
+    # is cancelled by the mean subtraction, e.g. model.10.m.0.ffn.1.bn.bias) and hold only rounding noise on either arm.
+    G = max(float(g.abs().max()) for g in g_ref.values())
+    errs = sorted(((float((g_el[n] - g_ref[n]).abs().max()) / (float(g_ref[n].abs().max()) + 1e-4 * G), n) for n in g_ref), reverse=True)
+    print("\nworst gradient deviations:", [(f"{e:.2e}", n) for e, n in errs[:5]])
+    assert errs[0][0] < 2e-3, errs[:5]  # fp32 sums in another order through ~100 layers of backward
 
 
 def test_yolo_train_runs_on_the_installed_kernels(api):
