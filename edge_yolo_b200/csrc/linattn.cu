@@ -153,6 +153,9 @@ constexpr size_t kAttnSimtSmem = (size_t)(3 * kD * kLd + kD * 65 + 2 * kD) * siz
 // tcgen05 path, linattn_tc.cu
 int linattn_tc_launch(const AttnArgs& A, int B, int dtype, cudaStream_t s);
 bool linattn_tc_supported(const AttnArgs& A, int dtype);
+// TMA-fed, chunk-parallel tcgen05 path for N <= 512 tokens, linattn_tma.cu
+int linattn_tma_launch(const AttnArgs& A, int B, int dtype, cudaStream_t s);
+bool linattn_tma_supported(const AttnArgs& A, int dtype);
 
 }  // namespace el
 
@@ -163,6 +166,8 @@ extern "C" int el_linattn_fwd(const void* qkv, const int64_t qs[3], void* y, con
     AttnArgs A{qkv, qs[0], qs[1], qs[2], y, ys[0], ys[1], ys[2], heads, N};
     cudaStream_t s = (cudaStream_t)stream;
     static const bool force_simt = getenv("EL_LINATTN_SIMT") != nullptr;  // A/B switch for tests and profiling
+    static const bool no_tma = getenv("EL_LINATTN_NO_TMA") != nullptr;     // A/B switch: the round-1 tcgen05 kernel for every N
+    if (!force_simt && !no_tma && linattn_tma_supported(A, dtype)) return linattn_tma_launch(A, B, dtype, s);
     if (!force_simt && linattn_tc_supported(A, dtype)) return linattn_tc_launch(A, B, dtype, s);
     const bool ch_fast = A.qc == 1 && A.yc == 1;
     EL_DISPATCH_DTYPE(dtype, {
