@@ -160,10 +160,27 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_tma_kernel(const __grid_c
     constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
 
     pdl_launch_dependents();
-    if (tid == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&A.qkv_map) : "memory");
+    if (warp == 16) {
+        // ------------------------------------------------------------------------------------ TMA producer: the whole problem at once, and first:
+        // this lane initialises the load barriers itself and issues all twelve tile loads before the CTA-wide set-up barrier, so the operand
+        // fetch (the ~3 us HBM phase of this kernel) overlaps the TMEM allocation and the other barriers' initialisation
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&A.qkv_map) : "memory");
+            for (int c = 0; c < kMaxChunks; ++c) { mbar_init(bar_kq + 8 * c, 1); mbar_init(bar_v + 8 * c, 1); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            pdl_wait();  // the qkv GEMM that produced our input has completed from here on
+            for (int c = 0; c < n_chunks; ++c) {  // K and Q first (the compute warps start on them), V is only read by the tensor core
+                mbar_expect_tx(bar_kq + 8 * c, 2 * kTile);
+                tma_load_3d(sbase + kOffK + c * kTile, &A.qkv_map, C + head * kD, c * kChunk, b, bar_kq + 8 * c);
+                tma_load_3d(sbase + kOffQ + c * kTile, &A.qkv_map, head * kD, c * kChunk, b, bar_kq + 8 * c);
+            }
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_expect_tx(bar_v + 8 * c, kTile);
+                tma_load_3d(sbase + kOffV + c * kTile, &A.qkv_map, 2 * C + head * kD, c * kChunk, b, bar_v + 8 * c);
+            }
+        }
+    } else if (tid == 0) {
         for (int c = 0; c < kMaxChunks; ++c) {
-            mbar_init(bar_kq + 8 * c, 1); mbar_init(bar_v + 8 * c, 1);
             mbar_init(bar_kready + 8 * c, 128); mbar_init(bar_pready + 8 * c, 128);
             mbar_init(bar_d2 + 8 * c, 1);
         }
@@ -179,21 +196,10 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_tma_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
     const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + kD;
-    pdl_wait();  // the qkv GEMM that produced our input has completed from here on
+    pdl_wait();  // every thread that stores to global memory orders itself behind the previous grid as well
 
     if (warp == 16) {
-        // ------------------------------------------------------------------------------------ TMA producer: the whole problem at once
-        if (lane == 0) {
-            for (int c = 0; c < n_chunks; ++c) {  // K and Q first (the compute warps start on them), V is only read by the tensor core
-                mbar_expect_tx(bar_kq + 8 * c, 2 * kTile);
-                tma_load_3d(sbase + kOffK + c * kTile, &A.qkv_map, C + head * kD, c * kChunk, b, bar_kq + 8 * c);
-                tma_load_3d(sbase + kOffQ + c * kTile, &A.qkv_map, head * kD, c * kChunk, b, bar_kq + 8 * c);
-            }
-            for (int c = 0; c < n_chunks; ++c) {
-                mbar_expect_tx(bar_v + 8 * c, kTile);
-                tma_load_3d(sbase + kOffV + c * kTile, &A.qkv_map, 2 * C + head * kD, c * kChunk, b, bar_v + 8 * c);
-            }
-        }
+        // (loads already issued above)
     } else if (warp == 17) {
         // ------------------------------------------------------------------------------------ MMA issuer
         if (lane == 0) {

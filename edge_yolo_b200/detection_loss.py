@@ -5,17 +5,16 @@ What runs where:
   * class term          -> BCE-with-logits, the branch the reference really takes with GFLHeadv2_uniH (`head._qualities`
                            stays None in training); `use_qfl=True` switches to `el_qfl_fwd/bwd`, the one-line
                            change the reference documents at loss.py:404-407
-  * target assignment   -> `TaskAlignedAssigner` below (utils/tal.py:14-295, the rank-1 "next" row of SURVEY section 8(f)):
-                           `fused=True` runs `el_tal_assign` (three kernels over one (B, n_gt, A) workspace: metric + top-k,
-                           multi-claim resolution, normalised soft targets; the default); `fused=False` is the same algorithm as ~25
-                           device-side torch ops (the formulation the kernel was developed against, kept for A/B measurement and for
-                           the host-orchestration test on CPU tensors).  Neither synchronises with the host.
+  * target assignment   -> `TaskAlignedAssigner` below (utils/tal.py:14-295, the rank-1 "next" row of SURVEY section 8(f)): `el_tal_assign`,
+                           three kernels over one (B, n_gt, A) workspace (metric + top-k, multi-claim resolution, normalised soft targets), no
+                           host synchronisation.  (The same algorithm as ~25 torch ops -- the formulation the kernel was developed against -- is
+                           test infrastructure and lives with the tests' checker, not in this package.  `v8DetectionLoss.assigner` is a plain attribute, which is how the CPU
+                           host-orchestration test swaps it in.)
   * CIoU                -> `bbox_ciou` (utils/metrics.py:74-134 with xywh=False, CIoU=True)
 """
 from __future__ import annotations
 
 import math
-import os
 from types import SimpleNamespace
 
 import torch
@@ -23,10 +22,6 @@ import torch.nn.functional as F
 
 from . import _lib
 from .loss import DFLoss, quality_focal_loss
-
-# default of TaskAlignedAssigner(fused=None): the fused kernel path (158 us against 1690 us as torch ops at B = 64, 8 boxes per image,
-# 8400 anchors, 80 classes: profiles/r01h_loss_kernels.log) unless EL_TAL_FUSED=0
-_TAL_FUSED_DEFAULT = os.environ.get("EL_TAL_FUSED", "1") != "0"
 
 
 def make_anchors(feats, strides, offset: float = 0.5):
@@ -76,9 +71,8 @@ class TaskAlignedAssigner:
     """Task-aligned target assignment (utils/tal.py:14-295): metric = score^alpha * CIoU^beta, top-k anchors per ground truth
     among those whose centre lies inside it, ties between ground truths resolved by the larger overlap."""
 
-    def __init__(self, topk=13, num_classes=80, alpha=1.0, beta=6.0, eps=1e-9, fused=None):
+    def __init__(self, topk=13, num_classes=80, alpha=1.0, beta=6.0, eps=1e-9):
         self.topk, self.num_classes, self.alpha, self.beta, self.eps = topk, num_classes, alpha, beta, eps
-        self.fused = _TAL_FUSED_DEFAULT if fused is None else bool(fused)
 
     def _assign_fused(self, scores, boxes, anchors, gt_labels, gt_boxes, gt_valid):
         """`el_tal_assign`: dense fp32 operands, outputs allocated here, workspace from the caching allocator."""
@@ -113,46 +107,9 @@ class TaskAlignedAssigner:
         if M == 0:
             z = torch.zeros_like(scores[..., 0])
             return torch.full_like(z, self.num_classes), torch.zeros_like(boxes), torch.zeros_like(scores), z, z
-        if self.fused:
-            if not scores.is_cuda:
-                raise _lib.EdgelineError("TaskAlignedAssigner: CUDA tensors expected (el_tal_assign has no CPU fallback; "
-                                         "fused=False selects the torch-op formulation explicitly)")
-            return self._assign_fused(scores, boxes, anchors, gt_labels, gt_boxes, gt_valid)
-        valid = gt_valid.bool()                                                   # (B,M,1)
-        # anchor centre strictly inside the ground-truth box (tal.py:241-262)
-        lt = anchors.view(1, 1, A, 2) - gt_boxes[..., None, :2]
-        rb = gt_boxes[..., None, 2:] - anchors.view(1, 1, A, 2)
-        inside = torch.cat((lt, rb), -1).amin(-1) > 1e-9                          # (B,M,A)
-        cand = inside & valid
-        # per (gt, anchor): class probability of the gt's class and CIoU, only where the anchor is a candidate (tal.py:132-155)
-        lab = gt_labels.squeeze(-1).long().clamp(0, nc - 1)                       # (B,M)
-        cls_score = scores.gather(2, lab.unsqueeze(1).expand(B, A, M)).permute(0, 2, 1)   # (B,M,A)
-        iou = bbox_ciou(gt_boxes.unsqueeze(2), boxes.unsqueeze(1)).squeeze(-1).clamp_(0)
-        zero = torch.zeros((), dtype=iou.dtype, device=iou.device)
-        iou = torch.where(cand, iou, zero)
-        cls_score = torch.where(cand, cls_score, zero.to(cls_score.dtype))
-        metric = cls_score.pow(self.alpha) * iou.pow(self.beta)
-        # top-k anchors per ground truth; padded ground truths select nothing (tal.py:157-190, :126-128)
-        top = metric.topk(self.topk, dim=-1).indices                              # (B,M,k)
-        in_top = torch.zeros_like(metric, dtype=torch.bool).scatter_(2, top, True) & valid
-        pos = in_top & inside                                                     # (B,M,A)
-        # an anchor claimed by several ground truths goes to the one it overlaps most (tal.py:265-295)
-        n_claims = pos.sum(1)                                                     # (B,A)
-        best = F.one_hot(iou.argmax(1), M).permute(0, 2, 1).bool()                # (B,M,A)
-        pos = torch.where((n_claims > 1).unsqueeze(1), best, pos)
-        fg = pos.any(1)
-        gt_idx = pos.float().argmax(1)                                            # (B,A); 0 where background
-        # targets (tal.py:192-238)
-        labels = lab.gather(1, gt_idx)
-        tboxes = gt_boxes.gather(1, gt_idx.unsqueeze(-1).expand(B, A, 4))
-        tscores = F.one_hot(labels, nc).to(scores.dtype) * fg.unsqueeze(-1)
-        # soft labels: metric normalised per ground truth to its best overlap (tal.py:110-116)
-        posf = pos.to(metric.dtype)
-        metric = metric * posf
-        best_metric = metric.amax(-1, keepdim=True)
-        best_iou = (iou * posf).amax(-1, keepdim=True)
-        norm = (metric * best_iou / (best_metric + self.eps)).amax(1).unsqueeze(-1)
-        return labels, tboxes, tscores * norm, fg, gt_idx
+        if not scores.is_cuda:
+            raise _lib.EdgelineError("TaskAlignedAssigner: CUDA tensors expected (el_tal_assign has no CPU fallback)")
+        return self._assign_fused(scores, boxes, anchors, gt_labels, gt_boxes, gt_valid)
 
 
 class BboxLoss:
@@ -177,7 +134,7 @@ class v8DetectionLoss:
     """Drop-in for `ultralytics.utils.loss.v8DetectionLoss`: `criterion(preds, batch) -> (loss.sum() * B, loss.detach())`
     with loss = (box, cls, dfl) scaled by the hyper-parameter gains."""
 
-    def __init__(self, model, tal_topk=10, use_qfl: bool = False, fused_tal=None):
+    def __init__(self, model, tal_topk=10, use_qfl: bool = False):
         head = model.model[-1]
         self.head = head
         self.hyp = getattr(model, "args", None) or SimpleNamespace(box=7.5, cls=0.5, dfl=1.5)  # cfg/default.yaml
@@ -187,7 +144,7 @@ class v8DetectionLoss:
         self.no = head.nc + head.reg_max * 4
         self.device = next(model.parameters()).device
         self.use_dfl, self.use_qfl = head.reg_max > 1, use_qfl
-        self.assigner = TaskAlignedAssigner(topk=tal_topk, num_classes=self.nc, alpha=0.5, beta=6.0, fused=fused_tal)
+        self.assigner = TaskAlignedAssigner(topk=tal_topk, num_classes=self.nc, alpha=0.5, beta=6.0)
         self.bbox_loss = BboxLoss(head.reg_max)
         self.proj = torch.arange(head.reg_max, dtype=torch.float, device=self.device)
 

@@ -14,6 +14,9 @@ What is replaced (reference path -> ours):
                          LinearAttention.forward     -> modules.linear_attention_forward
     nn/modules/head.py   GFLHeadv2_uniH.forward      -> modules.gfl_head_forward
     nn/modules/conv.py   WTConv2d.forward            -> modules.WTConv2d.forward (Haar analysis / synthesis on the DWT kernels)
+    nn/modules/block.py  HaarDWT2D.forward           -> modules.haar_dwt2d_forward
+                         IHaarDWT2D.__init__/forward -> modules.IHaarDWT2D (the reference's class is broken, Q5: installing REPAIRS it, so that
+                                                        WaveletMixerMultiLevel / C3AW_MLM of the fork become constructible and run on the DWT kernels)
     utils/ops.py         non_max_suppression         -> nms.non_max_suppression
     utils/loss.py        quality_focal_loss, QualityFocalLoss.forward, distribution_focal_loss, DFLoss.__call__
                                                       -> loss.*
@@ -64,8 +67,11 @@ def install(nms: bool = True, modules: bool = True, losses: bool = True, criteri
         _swap(head.GFLHeadv2_uniH, "forward", M.gfl_head_forward)
         conv = importlib.import_module("ultralytics.nn.modules.conv")
         _swap(conv.WTConv2d, "forward", M.WTConv2d.forward)
+        _swap(block.HaarDWT2D, "forward", M.haar_dwt2d_forward)
+        _swap(block.IHaarDWT2D, "__init__", M.ihaar_dwt2d_init)
+        _swap(block.IHaarDWT2D, "forward", M.ihaar_dwt2d_forward)
         done += ["block._PywtDWT2D.forward", "block._WaveletEnhancer.forward", "block.LinearAttention.forward", "head.GFLHeadv2_uniH.forward",
-                 "conv.WTConv2d.forward"]
+                 "conv.WTConv2d.forward", "block.HaarDWT2D.forward", "block.IHaarDWT2D.__init__", "block.IHaarDWT2D.forward"]
     if nms:
         _swap(uops, "non_max_suppression", el_nms.non_max_suppression)
         done.append("utils.ops.non_max_suppression")

@@ -550,6 +550,98 @@ class WTConv2d(nn.Module):
         return self.do_stride(y) if self.do_stride is not None else y
 
 
+def haar_dwt2d_forward(self, x: torch.Tensor):
+    """`HaarDWT2D.forward` (nn/modules/block.py:247-259): (LL, LH, HL, HH) with LH = vertical and HL = horizontal difference, i.e. the
+    second and third band of `el_dwt_haar_fwd` swapped.  The kernel's taps are float32(2^-1/2)^2 = 0.49999997 where this
+    module's are 0.5: 6e-8 relative, inside the 1e-5 contract."""
+    if x.shape[-1] % 2 or x.shape[-2] % 2:
+        raise ValueError("HaarDWT2D needs even H and W (the reference's view(B, C, 4, H // 2, W // 2) fails otherwise)")
+    buf = ops.dwt_haar(x)
+    B = x.shape[0]
+    return buf[:B], buf[2 * B : 3 * B], buf[B : 2 * B], buf[3 * B :]
+
+
+def ihaar_dwt2d_forward(self, LL, LH, HL, HH):
+    """Haar synthesis, the inverse of `HaarDWT2D` (the forward the reference's `IHaarDWT2D`, block.py:2714-2750, was meant to have: that
+    class cannot be constructed in the reference, Q5, and its un-reachable forward feeds a band-major cat into a transposed conv whose
+    groups expect channel-interleaved bands, which mixes channels).
+    The four bands are centre-cropped to their common size like the reference (:2729-2735) and go through `el_dwt_haar_bwd`."""
+    Hm, Wm = min(t.shape[-2] for t in (LL, LH, HL, HH)), min(t.shape[-1] for t in (LL, LH, HL, HH))
+
+    def crop(t):
+        dh, dw = (t.shape[-2] - Hm) // 2, (t.shape[-1] - Wm) // 2
+        return t[..., dh : dh + Hm, dw : dw + Wm]
+
+    fmt = torch.channels_last if ops._channels_last(LL) else torch.contiguous_format
+    bands = torch.cat([crop(LL), crop(HL), crop(LH), crop(HH)], 0).contiguous(memory_format=fmt)  # kernel order: LL, horizontal, vertical, HH
+    return ops.idwt_haar(bands, 2 * Hm, 2 * Wm)
+
+
+_HAAR_2X2 = (("ll", [[0.5, 0.5], [0.5, 0.5]]), ("lh", [[0.5, 0.5], [-0.5, -0.5]]), ("hl", [[0.5, -0.5], [0.5, -0.5]]), ("hh", [[0.5, -0.5], [-0.5, 0.5]]))
+
+
+def ihaar_dwt2d_init(self):
+    """`IHaarDWT2D.__init__` as block.py:2715-2732 defines it before the stray second `__init__(self, dim, num_heads)` (:2755) overrides it:
+    no arguments; buffers `ll`, `lh`, `hl`, `hh`, `recon_ll`, `recon_h`.  A plain function (no zero-argument super()) so that install() can
+    bind it onto the reference's own class."""
+    nn.Module.__init__(self)
+    for name, k in _HAAR_2X2:
+        self.register_buffer(name, torch.tensor(k, dtype=torch.float32))
+    self.register_buffer("recon_ll", torch.tensor([[0.5, 0.5], [0.5, 0.5]], dtype=torch.float32).view(1, 1, 2, 2))
+    self.register_buffer("recon_h", torch.tensor([[0.5, -0.5], [0.5, -0.5]], dtype=torch.float32).view(1, 1, 2, 2))
+
+
+class HaarDWT2D(nn.Module):
+    """block.py:225-259; the four 2 x 2 filters stay registered as buffers (`ll`, `lh`, `hl`, `hh`) for state-dict compatibility."""
+
+    def __init__(self):
+        super().__init__()
+        for name, k in _HAAR_2X2:
+            self.register_buffer(name, torch.tensor(k, dtype=torch.float32))
+
+    forward = haar_dwt2d_forward
+
+
+class IHaarDWT2D(nn.Module):
+    """block.py:2714-2750, as it was meant to be (see ihaar_dwt2d_init / ihaar_dwt2d_forward)."""
+
+    __init__ = ihaar_dwt2d_init
+    forward = ihaar_dwt2d_forward
+
+
+class WaveletMixerMultiLevel(nn.Module):
+    """Two-level Haar mixer, block.py:2600-2660: same constructor, parameter names (`f_ll1`, `f_lh1`, `f_hl1`, `f_hh1`, `f_ll2_head`,
+    `dw_weight`, `f_ll2_tail`, `f_h2`) and forward; both analyses and both syntheses run on the DWT kernels (the reference's own
+    version cannot be built because its `IHaarDWT2D` is broken, Q5).  Needs H and W divisible by 4."""
+
+    def __init__(self, c, use_dilated=True, k=5, d=3):
+        super().__init__()
+        self.dwt, self.idwt = HaarDWT2D(), IHaarDWT2D()
+        self.f_ll1, self.f_lh1, self.f_hl1, self.f_hh1 = Conv(c, c, 1, 1), Conv(c, c, 3, 1), Conv(c, c, 3, 1), Conv(c, c, 3, 1)
+        self.use_dilated, self.k, self.d = use_dilated, k, d
+        self.f_ll2_head = Conv(c, c, 1, 1)
+        self.dw_weight = nn.Parameter(torch.empty(c, 1, k, k))
+        nn.init.kaiming_uniform_(self.dw_weight, a=math.sqrt(5))
+        self.dw_bias = None
+        self.f_ll2_tail = Conv(c, c, 1, 1)
+        self.f_h2 = Conv(c, c, 3, 1)
+
+    def _depthwise_dynamic(self, x):
+        """block.py:2629-2641: the dilation shrinks on small maps so that the dilated kernel never exceeds the input."""
+        d = 1
+        if self.use_dilated:
+            d = min(self.d, max(1, (min(x.shape[-2:]) - 1) // (self.k - 1)))
+        return F.conv2d(x, self.dw_weight, self.dw_bias, stride=1, padding=((self.k - 1) * d) // 2, dilation=d, groups=x.shape[1])
+
+    def forward(self, x):
+        LL1, LH1, HL1, HH1 = self.dwt(x)
+        LL1, LH1, HL1, HH1 = self.f_ll1(LL1), self.f_lh1(LH1), self.f_hl1(HL1), self.f_hh1(HH1)
+        LL2, LH2, HL2, HH2 = self.dwt(LL1)
+        LL2 = self.f_ll2_tail(self._depthwise_dynamic(self.f_ll2_head(LL2)))
+        LH2, HL2, HH2 = self.f_h2(LH2), self.f_h2(HL2), self.f_h2(HH2)
+        return self.idwt(self.idwt(LL2, LH2, HL2, HH2), LH1, HL1, HH1)
+
+
 class DSConv(nn.Module):
     """Depthwise-separable conv with its own BatchNorm (conv.py:87-104); keys `dw`, `pw`, `bn`."""
 

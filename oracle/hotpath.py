@@ -51,6 +51,37 @@ def dwt_haar_adjoint(gLL, gLH, gHL, gHH, H: int, W: int):
     return g
 
 
+def haar_dwt2d(x: torch.Tensor):
+    """`HaarDWT2D.forward`, nn/modules/block.py:225-259: grouped stride-2 conv with exact 0.5 taps; sub-band order
+    LL, LH = [[+,+],[-,-]] (vertical difference), HL = [[+,-],[+,-]] (horizontal difference), HH -- LH / HL swapped with respect to
+    `_PywtDWT2D` (SURVEY Q4).  H and W even (`y.view(B, C, 4, H // 2, W // 2)` fails otherwise)."""
+    a, b = x[..., 0::2, 0::2], x[..., 0::2, 1::2]
+    c, d = x[..., 1::2, 0::2], x[..., 1::2, 1::2]
+    return 0.5 * (a + b + c + d), 0.5 * (a + b - c - d), 0.5 * (a - b + c - d), 0.5 * (a - b - c + d)
+
+
+def ihaar_dwt2d(LL, LH, HL, HH):
+    """The inverse of `haar_dwt2d` (the Haar bank with 0.5 taps is orthogonal, so the synthesis is the transpose of the analysis).
+    PARITY UNPINNED: the reference's `IHaarDWT2D` (block.py:2714-2750) cannot be constructed (Q5: a commented-out class header leaves a
+    foreign `__init__(self, dim, num_heads)` / `forward(self, x)` inside it), and the forward it was meant to have feeds a band-major
+    `cat` into a transposed conv whose groups expect channel-interleaved bands, which mixes channels.  The definition here is the one the
+    module's name and its use in `WaveletMixerMultiLevel` (:2656-2659, reconstruct one level up) require: idwt(dwt(x)) == x.  The centre
+    crop of the four bands to their common size is the reference's (:2729-2735)."""
+    Hm, Wm = min(t.shape[-2] for t in (LL, LH, HL, HH)), min(t.shape[-1] for t in (LL, LH, HL, HH))
+
+    def crop(t):
+        dh, dw = (t.shape[-2] - Hm) // 2, (t.shape[-1] - Wm) // 2
+        return t[..., dh : dh + Hm, dw : dw + Wm]
+
+    LL, LH, HL, HH = crop(LL), crop(LH), crop(HL), crop(HH)
+    x = LL.new_zeros(*LL.shape[:-2], 2 * Hm, 2 * Wm)
+    x[..., 0::2, 0::2] = 0.5 * (LL + LH + HL + HH)
+    x[..., 0::2, 1::2] = 0.5 * (LL + LH - HL - HH)
+    x[..., 1::2, 0::2] = 0.5 * (LL - LH + HL - HH)
+    x[..., 1::2, 1::2] = 0.5 * (LL - LH - HL + HH)
+    return x
+
+
 def wtconv2d(x, base_w, base_b, base_scale, wave_w, wave_scale, stride: int = 1):
     """WTConv2d.forward, nn/modules/conv.py:540-598 (db1 = Haar), SURVEY 8f-3.  `wave_w[i]` (4C,1,k,k) / `wave_scale[i]` (1,4C,1,1) per level.
 

@@ -37,7 +37,11 @@ def _run(golden, tag, device, patch_dfl, fused_tal=False):
 
     g = golden("detection_loss")
     model = _Model(int(g["nc"])).to(device)
-    crit = v8DetectionLoss(model, fused_tal=fused_tal)
+    crit = v8DetectionLoss(model)
+    if not fused_tal:  # the torch-op formulation of the assigner is test infrastructure (oracle/tal_torch.py): swapped in through the plain attribute
+        from oracle.tal_torch import TorchTaskAlignedAssigner
+
+        crit.assigner = TorchTaskAlignedAssigner(topk=crit.assigner.topk, num_classes=crit.nc, alpha=crit.assigner.alpha, beta=crit.assigner.beta)
     if patch_dfl:
         crit.bbox_loss.dfl = _torch_dfl
     feats = [torch.from_numpy(g[f"{tag}_feat{i}"]).to(device).requires_grad_() for i in range(3)]
@@ -100,8 +104,10 @@ def test_tal_fused_kernel_matches_torch_formulation(B, imgsz, nc, M, topk):
     from edge_yolo_b200.detection_loss import TaskAlignedAssigner
 
     args = _tal_case(B, imgsz, nc, M, seed=B * 1000 + M, device="cuda")
-    want = TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=0.5, beta=6.0, fused=False)(*args)
-    got = TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=0.5, beta=6.0, fused=True)(*args)
+    from oracle.tal_torch import TorchTaskAlignedAssigner
+
+    want = TorchTaskAlignedAssigner(topk=topk, num_classes=nc, alpha=0.5, beta=6.0)(*args)
+    got = TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=0.5, beta=6.0)(*args)
     l_w, b_w, s_w, fg_w, gi_w = [t.cpu() for t in want]
     l_g, b_g, s_g, fg_g, gi_g = [t.cpu() for t in got]
     assert s_g.shape == s_w.shape and s_g.dtype == s_w.dtype and fg_g.dtype == torch.bool and l_g.dtype == torch.int64 and gi_g.dtype == torch.int64
@@ -154,7 +160,10 @@ def _tal_golden(golden, tag, device, fused, rtol=1e-5, atol=1e-9):
     B, imgsz, nc, M, topk = (int(v) for v in g[f"{tag}_cfg"])
     alpha, beta = (float(v) for v in g[f"{tag}_alpha_beta"])
     args = [torch.from_numpy(g[f"{tag}_{k}"]).to(device) for k in ("scores", "boxes", "anchors", "gt_labels", "gt_boxes", "gt_valid")]
-    labels, tboxes, tscores, fg, gt_idx = TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=alpha, beta=beta, fused=fused)(*args)
+    from oracle.tal_torch import TorchTaskAlignedAssigner
+
+    cls = TaskAlignedAssigner if fused else TorchTaskAlignedAssigner
+    labels, tboxes, tscores, fg, gt_idx = cls(topk=topk, num_classes=nc, alpha=alpha, beta=beta)(*args)
     assert int(g[f"{tag}_out_fg"].sum()) > 0
     np.testing.assert_array_equal(fg.cpu().numpy(), g[f"{tag}_out_fg"])
     np.testing.assert_array_equal(gt_idx.cpu().numpy(), g[f"{tag}_out_gt_idx"])

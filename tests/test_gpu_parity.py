@@ -101,6 +101,48 @@ def test_dwt_backward_matches_adjoint():
     close(x.grad, want)
 
 
+def test_haar_dwt2d_modules_golden_and_round_trip(golden):
+    """HaarDWT2D on the DWT kernel against the reference's own outputs (band order LL, vertical, horizontal, HH: SURVEY Q4); IHaarDWT2D
+    (unbuildable in the reference, Q5) inverts them; centre crop of unequal bands like block.py:2729-2735."""
+    from edge_yolo_b200 import modules as M
+
+    g = golden("haar")
+    dwt, idwt = M.HaarDWT2D().to(DEV), M.IHaarDWT2D().to(DEV)
+    assert sorted(idwt.state_dict()) == ["hh", "hl", "lh", "ll", "recon_h", "recon_ll"]
+    for tag in "abc":
+        x = T(g[f"{tag}_x"]).to(DEV)
+        bands = dwt(x)
+        close(torch.stack(bands, 0), g[f"{tag}_bands"], 1e-5, 1e-6)
+        close(idwt(*bands), g[f"{tag}_x"], 1e-5, 1e-6)
+        xc = x.contiguous(memory_format=torch.channels_last)
+        close(idwt(*dwt(xc)), g[f"{tag}_x"], 1e-5, 1e-6)
+    LL, LH, HL, HH = [torch.randn(2, 4, 6 + i % 2, 8, device=DEV) for i in range(4)]
+    close(idwt(LL, LH, HL, HH), O.ihaar_dwt2d(LL.cpu(), LH.cpu(), HL.cpu(), HH.cpu()), 1e-5, 1e-6)
+
+
+def test_wavelet_mixer_multilevel_vs_oracle():
+    """WaveletMixerMultiLevel (block.py:2600-2660) with both analyses / syntheses on the DWT kernels against the same module whose dwt / idwt
+    are the CPU oracle's; gradients flow through the kernels' adjoints."""
+    import copy
+    import types
+
+    from edge_yolo_b200 import modules as M
+
+    torch.manual_seed(3)
+    ref = M.WaveletMixerMultiLevel(8).eval()
+    dev = copy.deepcopy(ref).to(DEV)
+    ref.dwt.forward = types.MethodType(lambda self, x: O.haar_dwt2d(x), ref.dwt)
+    ref.idwt.forward = types.MethodType(lambda self, *b: O.ihaar_dwt2d(*b), ref.idwt)
+    x = torch.randn(2, 8, 24, 32, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        close(dev(x.to(DEV)), ref(x), 1e-4, 1e-5)
+    xg = x.to(DEV).requires_grad_()
+    dev(xg).square().sum().backward()
+    xr = x.clone().requires_grad_()
+    ref(xr).square().sum().backward()
+    close(xg.grad, xr.grad, 1e-3, 1e-4)
+
+
 # ---------------------------------------------------------------------------------- merge
 @pytest.mark.parametrize("case", ["even", "odd"])
 def test_merge_and_residual_golden(golden, case):

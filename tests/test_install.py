@@ -27,7 +27,7 @@ def test_install_and_uninstall_round_trip():
     ref_sig = inspect.signature(uops.non_max_suppression)
     names = el.install()
     try:
-        assert len(names) == 13
+        assert len(names) == 16
         assert tasks.v8DetectionLoss.__module__ == "edge_yolo_b200.detection_loss"
         assert block._WaveletEnhancer.forward is M.wavelet_enhancer_forward
         assert block.LinearAttention.forward is M.linear_attention_forward
@@ -95,10 +95,34 @@ def test_install_metrics_opt_in_round_trip():
     assert list(inspect.signature(el_metrics.box_iou).parameters) == list(inspect.signature(o_iou).parameters)
     names = el.install(metrics=True)
     try:
-        assert len(names) == 16
+        assert len(names) == 19
         assert umetrics.box_iou is el_metrics.box_iou and dval.box_iou is el_metrics.box_iou
         assert list(inspect.signature(validator.BaseValidator.match_predictions).parameters) == list(inspect.signature(o_match).parameters)
         assert dval.DetectionValidator.match_predictions is validator.BaseValidator.match_predictions
     finally:
         el.uninstall()
     assert umetrics.box_iou is o_iou and validator.BaseValidator.match_predictions is o_match and dval.box_iou is o_iou
+
+
+def test_install_repairs_the_references_ihaar_dwt2d():
+    """`IHaarDWT2D()` raises TypeError in the reference (a stray __init__(self, dim, num_heads) overrides the real one), which
+    makes WaveletMixerMultiLevel / C3AW_MLM unbuildable.  install() binds the intended constructor and the synthesis forward onto the
+    reference's class; uninstall() restores the (broken) original."""
+    ref_loader.load()
+    import ultralytics.nn.modules.block as block
+
+    import edge_yolo_b200.install as el
+
+    with pytest.raises(TypeError):
+        block.IHaarDWT2D()
+    el.install(nms=False, losses=False, criterion=False)
+    try:
+        m = block.WaveletMixerMultiLevel(8)
+        assert type(m.idwt) is block.IHaarDWT2D and sorted(m.idwt.state_dict()) == ["hh", "hl", "lh", "ll", "recon_h", "recon_ll"]
+        from edge_yolo_b200 import modules as M
+
+        assert sorted(m.state_dict()) == sorted(M.WaveletMixerMultiLevel(8).state_dict())
+    finally:
+        el.uninstall()
+    with pytest.raises(TypeError):
+        block.IHaarDWT2D()

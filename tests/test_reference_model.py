@@ -98,21 +98,21 @@ def test_metric_oracle_matches_reference(seed):
 
 @pytest.mark.parametrize("seed", range(12))
 def test_tal_formulation_matches_reference_on_random_cases(seed):
-    """The assigner the CUDA kernel was developed against (`TaskAlignedAssigner(fused=False)`) versus the live reference's
+    """The assigner the CUDA kernel was developed against (oracle/tal_torch.py) versus the live reference's
     `TaskAlignedAssigner.forward` (utils/tal.py:14-295) on unfiltered random cases -- including ground truths with fewer than `topk`
     positive metrics, where torch.topk's order among zero metrics is open: target scores must agree everywhere, and labels / boxes /
     ground-truth indices wherever an anchor carries a non-zero target (what the loss reads)."""
     ref_loader.load()
     from ultralytics.utils.tal import TaskAlignedAssigner as RefTAL
 
-    from edge_yolo_b200.detection_loss import TaskAlignedAssigner
+    from oracle.tal_torch import TorchTaskAlignedAssigner as TaskAlignedAssigner
     from oracle.gen_golden_tal import make_case
 
     B, imgsz, nc, M, topk = [(3, 128, 80, 12, 10), (3, 256, 4, 16, 13), (2, 320, 10, 6, 10), (4, 192, 3, 2, 13)][seed % 4]
     alpha, beta = ((0.5, 6.0), (1.0, 6.0), (0.5, 2.0))[seed % 3]
     args = make_case(B, imgsz, nc, M, seed=100 + seed)
     want = RefTAL(topk=topk, num_classes=nc, alpha=alpha, beta=beta)(*args)
-    got = TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=alpha, beta=beta, fused=False)(*args)
+    got = TaskAlignedAssigner(topk=topk, num_classes=nc, alpha=alpha, beta=beta)(*args)
     l_w, b_w, s_w, fg_w, gi_w = want
     l_g, b_g, s_g, fg_g, gi_g = got
     np.testing.assert_allclose(s_g.numpy(), s_w.numpy(), rtol=1e-5, atol=1e-9)

@@ -1,56 +1,61 @@
-"""Per-launch summary of an `ncu --set full` report (ncu -i rep --page raw --csv > raw.csv): python tools/ncu_summary.py raw.csv [out.csv]"""
+"""Summarise an .ncu-rep (read here, on the CPU box): per launch the metrics the roofline discussion uses.
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep [--source N]   # --source: top-N source lines by stall samples of the first launch"""
 import csv
+import io
+import subprocess
 import sys
 
-rows = list(csv.reader(open(sys.argv[1])))
-hdr, units = rows[0], rows[1]
-ix = {h: i for i, h in enumerate(hdr)}
-cols = [("Kernel Name", "kernel"), ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__registers_per_thread", "regs"),
-        ("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
-        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
-        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ_pct"), ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_pct"),
-        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu_pct"), ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu_wave_pct"),
-        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu_pct"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pct"),
-        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct")]
-have = [(h, n) for h, n in cols if h in ix]
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_membar_per_warp_active.pct",
+        "smsp__warp_issue_stalled_sleeping_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
+        "smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct",
+        "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct", "smsp__warp_issue_stalled_selected_per_warp_active.pct",
+        "smsp__warp_issue_stalled_tex_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_drain_per_warp_active.pct",
+        "smsp__warp_issue_stalled_imc_miss_per_warp_active.pct", "smsp__warp_issue_stalled_misc_per_warp_active.pct"]
 
 
-def to_bytes(v, unit):
-    v = float(v.replace(",", "")) if v not in ("", "n/a") else 0.0
-    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-
-
-def to_us(v, unit):
-    v = float(v.replace(",", ""))
-    return v * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}.get(unit, 1)
-
-
-out = [",".join(n for _, n in have) + ",dram_MB,GBps_dram"]
-for r in rows[2:]:
-    vals = []
-    rd = wr = us = 0.0
-    for h, n in have:
-        v = r[ix[h]]
-        if n == "kernel":
-            v = '"' + v[:90].replace('"', "'") + '"'
-        elif n == "us":
-            us = to_us(v, units[ix[h]])
-            v = f"{us:.2f}"
-        elif n == "dram_rd":
-            rd = to_bytes(v, units[ix[h]])
-            v = f"{rd / 1e6:.2f}"
-        elif n == "dram_wr":
-            wr = to_bytes(v, units[ix[h]])
-            v = f"{wr / 1e6:.2f}"
-        else:
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr = rows[0]
+    idx = {k: hdr.index(k) for k in KEYS if k in hdr}
+    name_i = hdr.index("Kernel Name")
+    for r in rows[2:]:
+        print("==", r[name_i][:90])
+        for k, i in idx.items():
+            if r[i] not in ("", "0"):
+                print(f"   {k:86s} {r[i]}")
+    if "--source" in sys.argv:
+        n = int(sys.argv[sys.argv.index("--source") + 1])
+        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass" if "--sass" in sys.argv else "cuda"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(src)))
+        hdr = next((r for r in rows if "Source" in r), None)
+        if hdr is None:
+            print("no source page")
+            return
+        si = hdr.index("Source")
+        samp = next((hdr.index(c) for c in hdr if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)"), None)
+        inst = next((hdr.index(c) for c in hdr if c.startswith("Instructions Executed")), None)
+        body = [r for r in rows[rows.index(hdr) + 1:] if len(r) > max(si, samp or 0)]
+        def num(x):
             try:
-                v = f"{float(v.replace(',', '')):.1f}"
+                return float(x.replace(",", ""))
             except ValueError:
-                pass
-        vals.append(v)
-    vals += [f"{(rd + wr) / 1e6:.1f}", f"{(rd + wr) / us / 1e3:.0f}" if us else ""]
-    out.append(",".join(vals))
-text = "\n".join(out) + "\n"
-if len(sys.argv) > 2:
-    open(sys.argv[2], "w").write(text)
-print(text)
+                return 0.0
+        body.sort(key=lambda r: -num(r[samp]))
+        tot = sum(num(r[samp]) for r in body) or 1
+        print(f"-- top {n} source lines by stall samples (total {tot:.0f})")
+        for r in body[:n]:
+            print(f"   {100 * num(r[samp]) / tot:5.1f}%  inst {r[inst] if inst else '':>10s}  {r[si].strip()[:150]}")
+
+
+if __name__ == "__main__":
+    main()

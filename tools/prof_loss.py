@@ -77,6 +77,8 @@ for _ in range(R):
     gt_labels = torch.randint(0, nc, (B, M, 1), generator=cpu_g).float().to(dev)
     cases.append((scores, boxes, anchors, gt_labels, gt_boxes, torch.ones(B, M, 1, dtype=torch.bool, device=dev)))
 tal_bytes = B * A * (nc * 4 + 37) + B * A * 16 + B * M * A // 8 * (16 + 4)
-fused, eager = TaskAlignedAssigner(10, nc, 0.5, 6.0, fused=True), TaskAlignedAssigner(10, nc, 0.5, 6.0, fused=False)
+from oracle.tal_torch import TorchTaskAlignedAssigner  # noqa: E402
+
+fused, eager = TaskAlignedAssigner(10, nc, 0.5, 6.0), TorchTaskAlignedAssigner(10, nc, 0.5, 6.0)
 report("el_tal_assign (3 kernels)", timeit(lambda i: fused(*cases[i])), tal_bytes)
 report("TAL as device-side torch ops", timeit(lambda i: eager(*cases[i])), tal_bytes)
