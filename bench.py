@@ -308,6 +308,7 @@ def profile_kernels(pred, a, iters=10):
             + (up_addend.numel() if up_addend is not None else 0)) * e(srcs[0]),
         "dwconv": lambda _o, x, *r, **k: 2 * x.numel() * e(x),
         "conv3x3": lambda _o, x, wpk, N, **k: (x.numel() + _o.numel()) * e(x),
+        "conv3x3_halo": lambda _o, x, wpk, N, **k: (x.numel() + _o.numel()) * e(x),
         "upsample2x_cat": lambda _o, x, skip: (x.numel() + skip.numel() + _o.numel()) * e(x),
         "sppf_pool": lambda _o, x: 5 * x.numel() * e(x),
         "nms_batched": lambda out, y, *r, **k: y.shape[0] * y.shape[2] * (y.shape[1] - 4) * 4 + out[0].numel() * 4,

@@ -55,6 +55,8 @@ _SIGNATURES = {
     "el_qfl_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "el_dfl_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "el_dfl_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "el_dfl_side_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "el_dfl_side_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "el_box_iou": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_float, c_void_p]),
     "el_match_predictions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "el_tal_workspace_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
@@ -69,6 +71,8 @@ _SIGNATURES = {
                               c_int64, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
     "el_conv3x3_tile": (c_int, [c_int, c_int, c_int64]),
     "el_conv3x3_fwd": (c_int, [c_void_p, I64P, c_int, c_void_p, c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "el_conv3x3_halo_ok": (c_int, [c_int, c_int]),
+    "el_conv3x3_halo_fwd": (c_int, [c_void_p, I64P, c_int, c_void_p, c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_sppf_pool_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_upsample2x_cat_fwd": (c_int, [c_void_p, I64P, c_void_p, I64P, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }

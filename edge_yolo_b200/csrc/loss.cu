@@ -140,10 +140,11 @@ __global__ void __launch_bounds__(kQflThreads) qfl_bwd_kernel(const T* __restric
 }
 
 // ------------------------------------------------------------------------------------- DFL
-// one thread per (row, side): 16 logits; 4 consecutive lanes form a row
+// one thread per (row, side): 16 logits; 4 consecutive lanes form a row.  per_side = 0: DFLoss (mean over the 4 sides of a row, loss.py:209-224);
+// per_side = 1: distribution_focal_loss (one value per side, loss.py:88-137)
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) dfl_kernel(const T* __restrict__ pred, const float* __restrict__ target, int64_t sides, float* __restrict__ loss,
-                                                  const float* __restrict__ gout, T* __restrict__ gpred) {
+                                                  const float* __restrict__ gout, T* __restrict__ gpred, int per_side) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool valid = i < sides;
     float lg[16];
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) dfl_kernel(const T* __restrict__ pred, co
         float lse = m + logf(s);
         l = (lse - xl) * wl + (lse - xr) * wr;  // CE(pred, tl)*wl + CE(pred, tr)*wr
         if (BWD) {
-            float g = __ldg(gout + (i >> 2)) * 0.25f;  // .mean(-1) over the 4 sides
+            float g = per_side ? __ldg(gout + i) : __ldg(gout + (i >> 2)) * 0.25f;  // .mean(-1) over the 4 sides
             float inv = 1.f / s;
             float o[16];
 #pragma unroll
@@ -208,9 +209,13 @@ __global__ void __launch_bounds__(256) dfl_kernel(const T* __restrict__ pred, co
         }
     }
     if (!BWD) {
-        l += __shfl_xor_sync(0xffffffffu, l, 1);
-        l += __shfl_xor_sync(0xffffffffu, l, 2);
-        if (valid && (threadIdx.x & 3) == 0) loss[i >> 2] = l * 0.25f;
+        if (per_side) {
+            if (valid) loss[i] = l;
+        } else {
+            l += __shfl_xor_sync(0xffffffffu, l, 1);
+            l += __shfl_xor_sync(0xffffffffu, l, 2);
+            if (valid && (threadIdx.x & 3) == 0) loss[i >> 2] = l * 0.25f;
+        }
     }
 }
 
@@ -258,7 +263,23 @@ extern "C" int el_dfl_fwd(const void* pred, const float* target, int64_t rows, i
     if (!pred || !target || !loss || rows <= 0 || !aligned16(pred)) return EL_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t sides = rows * 4;
-    EL_DISPATCH_DTYPE(dtype, { dfl_kernel<T, false><<<(unsigned)ceil_div(sides, 256), 256, 0, s>>>((const T*)pred, target, sides, loss, nullptr, nullptr); });
+    EL_DISPATCH_DTYPE(dtype, { dfl_kernel<T, false><<<(unsigned)ceil_div(sides, 256), 256, 0, s>>>((const T*)pred, target, sides, loss, nullptr, nullptr, 0); });
+    note_launches(1);
+    return check_launch();
+}
+
+extern "C" int el_dfl_side_fwd(const void* pred, const float* target, int64_t sides, int dtype, float* loss, void* stream) {
+    if (!pred || !target || !loss || sides <= 0 || !aligned16(pred)) return EL_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    EL_DISPATCH_DTYPE(dtype, { dfl_kernel<T, false><<<(unsigned)ceil_div(sides, 256), 256, 0, s>>>((const T*)pred, target, sides, loss, nullptr, nullptr, 1); });
+    note_launches(1);
+    return check_launch();
+}
+
+extern "C" int el_dfl_side_bwd(const void* pred, const float* target, int64_t sides, int dtype, const float* gout, void* gpred, void* stream) {
+    if (!pred || !target || !gout || !gpred || sides <= 0 || !aligned16(pred) || !aligned16(gpred)) return EL_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    EL_DISPATCH_DTYPE(dtype, { dfl_kernel<T, true><<<(unsigned)ceil_div(sides, 256), 256, 0, s>>>((const T*)pred, target, sides, nullptr, gout, (T*)gpred, 1); });
     note_launches(1);
     return check_launch();
 }
@@ -267,7 +288,7 @@ extern "C" int el_dfl_bwd(const void* pred, const float* target, int64_t rows, i
     if (!pred || !target || !gout || !gpred || rows <= 0 || !aligned16(pred) || !aligned16(gpred)) return EL_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t sides = rows * 4;
-    EL_DISPATCH_DTYPE(dtype, { dfl_kernel<T, true><<<(unsigned)ceil_div(sides, 256), 256, 0, s>>>((const T*)pred, target, sides, nullptr, gout, (T*)gpred); });
+    EL_DISPATCH_DTYPE(dtype, { dfl_kernel<T, true><<<(unsigned)ceil_div(sides, 256), 256, 0, s>>>((const T*)pred, target, sides, nullptr, gout, (T*)gpred, 0); });
     note_launches(1);
     return check_launch();
 }

@@ -32,18 +32,7 @@ def distribution_focal_loss(pred, target, reduction: str = "none"):
     if reg_max != 16:
         raise NotImplementedError("edge_yolo_b200 DFL kernels are compiled for reg_max=16")
     target.clamp_(0, reg_max - 1 - 0.01)
-    flat_t = target.reshape(-1)
-    pad = (-flat_t.numel()) % 4  # the kernel works on groups of 4 sides
-    p = pred.reshape(-1, reg_max)
-    if pad:
-        flat_t = torch.cat((flat_t, flat_t.new_zeros(pad)))
-        p = torch.cat((p, p.new_zeros(pad, reg_max)))
-    # per-side values: feed each side as its own "row" replicated 4x is wasteful; instead use rows of 4 sides and
-    # recover per-side terms from d(mean)/d(side): simpler and exact -> call the row kernel on a (n,4) view and
-    # un-mean with a one-hot trick is not possible, so compute per side with a 4x repeat only for this rarely used API.
-    rep_t = flat_t.view(-1, 1).expand(-1, 4).contiguous()
-    rep_p = p.view(-1, 1, reg_max).expand(-1, 4, reg_max).reshape(-1, reg_max)
-    loss = ops.dfl_loss(rep_p, rep_t).view(-1)[: target.numel()].view_as(target)
+    loss = ops.dfl_side_loss(pred, target)  # el_dfl_side_fwd / _bwd: the DFL row kernel without the mean over a row's 4 sides
     if reduction == "mean":
         return loss.mean()
     if reduction == "sum":

@@ -279,6 +279,22 @@ def _conv3_ok(conv: nn.Conv2d, x: torch.Tensor, out=None) -> bool:
     return 0 < n_tiles <= 3
 
 
+USE_CONV3X3_HALO = True  # el_conv3x3_halo_fwd for the wide (C_in % 64 == 0) stride-1 dense 3x3 convs of the engine graph
+
+
+def _conv3_halo_ok(conv: nn.Conv2d, x: torch.Tensor, out=None) -> bool:
+    """el_conv3x3_halo_fwd applies: dense 3x3, padding 1, stride 1, 16-bit NHWC, C_in a multiple of 64, weights resident."""
+    if not (USE_CONV3X3_HALO and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1) and conv.dilation == (1, 1)
+            and conv.groups == 1 and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and not torch.is_grad_enabled()):
+        return False
+    C, N = x.shape[1], conv.out_channels
+    if C % 64 or N % 8 or x.stride(1) != 1 or any(s % 8 for i, s in enumerate(x.stride()) if i != 1) or x.data_ptr() % 16:
+        return False
+    if out is not None and (out.stride(1) != 1 or any(s % 8 for i, s in enumerate(out.stride()) if i != 1) or out.data_ptr() % 16):
+        return False
+    return ops.conv3x3_halo_ok(C, N)
+
+
 def pw_apply(conv: nn.Conv2d, srcs, bias, act, out=None, residual=None, out2=None, res_scale=1.0, up_addend=None):
     """1x1 conv over the channel concatenation of `srcs` + bias + activation (+ residual) as one tcgen05 GEMM (ops.pwconv).
     Weight tiles are packed once per (conv, source split) and cached on the conv module."""
@@ -340,6 +356,13 @@ def conv_engine_forward(self, x, out=None, residual=None, out2=None):
     if _pw_ok(self.conv, srcs, out, residual, out2):
         return pw_apply(self.conv, srcs, _bias_on(self, srcs[0]), self.el_act, out=out, residual=residual, out2=out2)
     x = srcs[0] if len(srcs) == 1 else torch.cat(srcs, 1)
+    if residual is None and out2 is None and _conv3_halo_ok(self.conv, x, out):
+        cache = self.conv.__dict__.setdefault("el_wpk", {})
+        key = ("3x3halo", x.dtype, x.device, 0, _ver(self.conv.weight), self.conv.weight.data_ptr())
+        wpk = cache.get(key)
+        if wpk is None:
+            wpk = cache[key] = ops.pack_conv3x3_halo_weight(self.conv.weight, x.dtype).to(x.device)
+        return ops.conv3x3_halo(x, wpk, self.conv.out_channels, bias=_bias_on(self, x), act=self.el_act, out=out)
     if residual is None and out2 is None and _conv3_ok(self.conv, x, out):
         cache = self.conv.__dict__.setdefault("el_wpk", {})
         B, C, H, W = x.shape

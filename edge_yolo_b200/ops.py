@@ -104,10 +104,27 @@ def dwt_haar(x: torch.Tensor) -> torch.Tensor:
     return _dwt_fwd(x)
 
 
+class _IDWT(torch.autograd.Function):
+    """Haar synthesis with the analysis as its backward (each is the other's adjoint)."""
+
+    @staticmethod
+    def forward(ctx, bands, H, W):
+        ctx.cl = _channels_last(bands)
+        B = bands.shape[0] // 4
+        return _dwt_bwd(bands, _empty_like_layout(bands, (B, bands.shape[1], H, W)))
+
+    @staticmethod
+    def backward(ctx, g):
+        fmt = torch.channels_last if ctx.cl else torch.contiguous_format
+        return _dwt_fwd(g.contiguous(memory_format=fmt)), None, None
+
+
 def idwt_haar(bands: torch.Tensor, H: int, W: int) -> torch.Tensor:
     """Haar synthesis (adjoint of `dwt_haar`), the single-level case of inverse_2d_wavelet_transform
     (nn/modules/conv.py:438-443).  `bands` is the (4*B, C, H//2, W//2) buffer `dwt_haar` returns."""
     _need_cuda(bands)
+    if bands.requires_grad and torch.is_grad_enabled():
+        return _IDWT.apply(bands, H, W)
     B = bands.shape[0] // 4
     like = _empty_like_layout(bands, (B, bands.shape[1], H, W))
     return _dwt_bwd(bands, like)
@@ -558,6 +575,36 @@ def dfl_loss(pred_dist: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     return _DFL.apply(pred_dist, target)
 
 
+class _DFLSide(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        _need_cuda(pred, target)
+        p = pred.reshape(-1, 16).contiguous()
+        t = target.reshape(-1).float().contiguous()
+        if p.shape[0] != t.shape[0]:
+            raise EdgelineError(f"dfl: expected pred (..., 16) and target (...), got {tuple(pred.shape)} / {tuple(target.shape)}")
+        ctx.save_for_backward(p, t)
+        ctx.pshape = pred.shape
+        loss = torch.empty(t.shape[0], device=p.device, dtype=torch.float32)
+        if t.shape[0]:
+            check(_lib.lib().el_dfl_side_fwd(p.data_ptr(), t.data_ptr(), t.shape[0], _dt(p), loss.data_ptr(), _stream()), "el_dfl_side_fwd")
+        return loss.view(target.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        p, t = ctx.saved_tensors
+        gp = torch.empty_like(p)
+        if t.shape[0]:
+            g = g.reshape(-1).float().contiguous()
+            check(_lib.lib().el_dfl_side_bwd(p.data_ptr(), t.data_ptr(), t.shape[0], _dt(p), g.data_ptr(), gp.data_ptr(), _stream()), "el_dfl_side_bwd")
+        return gp.view(ctx.pshape), None
+
+
+def dfl_side_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """distribution_focal_loss(reduction="none") (utils/loss.py:88-137): pred (..., 16) logits, target (...) in bins -> (...) fp32."""
+    return _DFLSide.apply(pred, target)
+
+
 # --------------------------------------------------------------------------------- ingest
 def ingest_u8(src: torch.Tensor, dtype=torch.bfloat16, channels_last: bool = True, out: torch.Tensor | None = None) -> torch.Tensor:
     """uint8 (B,H,W,3) images -> (B,3,H,W) activations / 255 (the predictor's preprocess, engine/predictor.py:117-135)."""
@@ -755,6 +802,33 @@ def conv3x3(x: torch.Tensor, wpk: torch.Tensor, N: int, bias: torch.Tensor | Non
         raise EdgelineError("conv3x3: bias must be a contiguous fp32 vector of N elements")
     check(_lib.lib().el_conv3x3_fwd(x.data_ptr(), _i64(x.stride()), C, wpk.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
                                     _i64(out.stride()), B, H, W, N, int(stride), int(act), _dt(x), _stream()), "el_conv3x3_fwd")
+    return out
+
+
+def conv3x3_halo_ok(C: int, N: int) -> bool:
+    """el_conv3x3_halo_fwd covers this (C_in, N) site (C_in a multiple of 64, the nine weight tiles resident in shared memory)."""
+    return bool(_lib.lib().el_conv3x3_halo_ok(int(C), int(N)))
+
+
+def pack_conv3x3_halo_weight(weight: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """Conv2d weight (N, C, 3, 3) -> resident UMMA B tiles of el_conv3x3_halo_fwd: [tap = ky*3+kx][64-channel chunk] K-major SW128 tiles of
+    ceil16(N) rows (the packing of a 1x1 conv over nine C-channel sources with one output-channel tile)."""
+    N, C, kh, kw = weight.shape
+    if (kh, kw) != (3, 3) or C % 64:
+        raise EdgelineError("pack_conv3x3_halo_weight: need a (N, C, 3, 3) weight with C a multiple of 64")
+    return pack_pw_weight(weight.detach().permute(0, 2, 3, 1).reshape(N, 9 * C), [C] * 9, dtype, n_tile=-(-N // 16) * 16)
+
+
+def conv3x3_halo(x: torch.Tensor, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, act: int = ACT_NONE, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Dense 3x3 conv (padding 1, stride 1, wide C_in) + bias + activation from ONE haloed TMA tile per K chunk (NHWC 16-bit activations)."""
+    _need_cuda(x, wpk)
+    B, C, H, W = x.shape
+    if out is None:
+        out = torch.empty((B, N, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise EdgelineError("conv3x3_halo: bias must be a contiguous fp32 vector of N elements")
+    check(_lib.lib().el_conv3x3_halo_fwd(x.data_ptr(), _i64(x.stride()), C, wpk.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                                         _i64(out.stride()), B, H, W, N, int(act), _dt(x), _stream()), "el_conv3x3_halo_fwd")
     return out
 
 

@@ -173,6 +173,12 @@ int el_dfl_fwd(const void* pred, const float* target, int64_t rows, int dtype, f
                void* stream);
 int el_dfl_bwd(const void* pred, const float* target, int64_t rows, int dtype, const float* gout,
                void* gpred, void* stream);
+/* Per-side form: distribution_focal_loss(reduction="none"), utils/loss.py:88-137.  pred (sides, 16), target (sides) fp32 -> loss (sides) fp32;
+ * bwd: gpred (sides, 16) = gout[side] * (softmax - wl*d_tl - wr*d_tr).  Same kernel as above without the mean over the 4 sides of a row. */
+int el_dfl_side_fwd(const void* pred, const float* target, int64_t sides, int dtype, float* loss,
+                    void* stream);
+int el_dfl_side_bwd(const void* pred, const float* target, int64_t sides, int dtype, const float* gout,
+                    void* gpred, void* stream);
 
 /* ---- ingest: uint8 HWC images -> normalised NHWC activations (engine/predictor.py:117-135) ----
  * src (B,H,W,3) uint8 -> dst (B,3,H,W) logical with strides ds, value/255 in `dtype`. */
@@ -234,6 +240,14 @@ int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t src_pitch[], 
 int el_conv3x3_tile(int N, int C, int64_t M);
 int el_conv3x3_fwd(const void* x, const int64_t xs[4], int C, const void* wpk, const float* bias, void* out,
                    const int64_t os[4], int B, int H, int W, int N, int stride, int act, int dtype, void* stream);
+/* Wide dense 3x3 conv (stride 1, padding 1, C_in a multiple of 64): Conv.forward_fuse, nn/modules/conv.py:58-60, at the sites where the
+ * tap-shifted form above loses to cuDNN (f_h of _WaveletEnhancer block.py:3668-3673 from c = 64, the Detect box towers head.py:59-63).
+ * One haloed (10 x 16 pixel) TMA box per 64-channel K chunk serves all nine taps through row-shifted UMMA descriptors (conv3x3_halo.cu).
+ * wpk: the (N, 9*C) matrix in (ky, kx, c) order packed as [tap][chunk] K-major SW128 tiles of n_pad = ceil16(N) rows (ops.pack_conv3x3_halo_weight);
+ * x / out NHWC 16-bit with element strides {n, c = 1, h, w}.  el_conv3x3_halo_ok: 1 if the nine weight tiles of a (C, N) site fit shared memory. */
+int el_conv3x3_halo_ok(int C, int N);
+int el_conv3x3_halo_fwd(const void* x, const int64_t xs[4], int C, const void* wpk, const float* bias, void* out,
+                        const int64_t os[4], int B, int H, int W, int N, int act, int dtype, void* stream);
 /* el_sppf_pool_fwd: out (B,4C,H,W) = cat[x, m(x), m(m(x)), m(m(m(x)))], m = MaxPool2d(5,1,2): the pooling
  * pyramid of SPPF (nn/modules/block.py:204-223) as separable 5/9/13 window maxima in shared memory.
  * NHWC views, H*W*64 B of shared memory (maps up to ~56x56), else EL_ERR_UNSUPPORTED. */

@@ -128,6 +128,7 @@ def test_wavelet_mixer_multilevel_vs_oracle():
 
     from edge_yolo_b200 import modules as M
 
+    torch.backends.cudnn.allow_tf32 = False  # the CPU arm is fp32: cuDNN's default TF32 convolutions would differ by 1e-4
     torch.manual_seed(3)
     ref = M.WaveletMixerMultiLevel(8).eval()
     dev = copy.deepcopy(ref).to(DEV)
@@ -393,6 +394,23 @@ def test_dfl_golden(golden):
     close(pred.grad, g["dfl_grad"], 1e-5, 1e-7)
     per_side = distribution_focal_loss(T(g["dfl_pred"]).to(DEV).view(10, 4, 16), T(g["dfl_target"]).to(DEV))
     close(per_side, g["dfl_fn_loss"], 1e-5, 1e-6)
+    # per-side kernel path (el_dfl_side_fwd / _bwd): ragged side count (not a multiple of 4), gradient against autograd of the reference formula
+    gen = torch.Generator().manual_seed(17)
+    p0 = torch.randn(7, 3, 16, generator=gen) * 2
+    t0 = torch.rand(7, 3, generator=gen) * 16 - 0.5
+    w = torch.rand(7, 3, generator=gen)
+    pr = p0.clone().requires_grad_()
+    tc = t0.clamp(0, 14.99)
+    tl = tc.long()
+    lp = torch.log_softmax(pr, -1)
+    want = -(lp.gather(-1, tl.unsqueeze(-1)).squeeze(-1) * ((tl + 1).float() - tc) + lp.gather(-1, (tl + 1).unsqueeze(-1)).squeeze(-1) * (tc - tl.float()))
+    (want * w).sum().backward()
+    pd = p0.to(DEV).requires_grad_()
+    got = distribution_focal_loss(pd, t0.to(DEV))
+    close(got, want.detach(), 1e-5, 1e-6)
+    (got * w.to(DEV)).sum().backward()
+    close(pd.grad, pr.grad, 1e-5, 1e-7)
+    assert float(distribution_focal_loss(p0.to(DEV), t0.to(DEV), reduction="sum")) == pytest.approx(float(want.sum()), rel=1e-5)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
@@ -666,6 +684,34 @@ def test_conv3x3(dtype, C, N, hw, stride, act):
     got = o.conv3x3(x, o.pack_conv3x3_weight(w, dtype, B * Ho * Wo), N, bias=bias, act=act, stride=stride)
     assert got.shape == want.shape
     close(got, want, 2e-2, 2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,C,N,hw,act", [(2, 64, 64, (80, 80), 1), (3, 64, 32, (20, 20), 1), (2, 128, 64, (40, 40), 1), (1, 64, 64, (8, 14), 0), (2, 64, 48, (9, 15), 2),
+                                          (1, 64, 128, (29, 31), 1), (2, 128, 64, (10, 10), 1), (1, 64, 64, (3, 5), 1)])
+def test_conv3x3_halo(dtype, B, C, N, hw, act):
+    """Wide dense 3x3 conv (stride 1, padding 1) from ONE haloed TMA tile per K chunk with row-shifted UMMA descriptors (el_conv3x3_halo_fwd)
+    == Conv.forward_fuse (nn/modules/conv.py:58-60) on the same 16-bit-rounded operands: image borders (zero padding = TMA fill), ragged
+    8 x 14 tiles, several K chunks, N below / above one store box, the three activations."""
+    o = ops()
+    gen = torch.Generator().manual_seed(C + N + hw[0])
+    x = torch.randn(B, C, *hw, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(N, C, 3, 3, generator=gen) * (9 * C) ** -0.5).to(DEV)
+    bias = torch.randn(N, generator=gen).to(DEV)
+    assert o.conv3x3_halo_ok(C, N)
+    want = torch.nn.functional.conv2d(x.float(), w.to(dtype).float(), bias, stride=1, padding=1)
+    want = torch.nn.functional.silu(want) if act == 1 else (want.relu() if act == 2 else want)
+    got = o.conv3x3_halo(x, o.pack_conv3x3_halo_weight(w, dtype), N, bias=bias, act=act)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    close(got, want, 2e-2, 2e-2)
+    # a channel-slice destination (the engine writes into concat-free block buffers) and a second call on another input (ring / barrier phases)
+    buf = torch.zeros(B, N + 16, *hw, device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
+    x2 = torch.flip(x, dims=[0, 2])
+    o.conv3x3_halo(x2, o.pack_conv3x3_halo_weight(w, dtype), N, bias=bias, act=act, out=buf[:, 8 : 8 + N])
+    want2 = torch.nn.functional.conv2d(x2.float(), w.to(dtype).float(), bias, stride=1, padding=1)
+    want2 = torch.nn.functional.silu(want2) if act == 1 else (want2.relu() if act == 2 else want2)
+    close(buf[:, 8 : 8 + N], want2, 2e-2, 2e-2)
+    assert float(buf[:, :8].abs().max()) == 0 and float(buf[:, 8 + N :].abs().max()) == 0
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
