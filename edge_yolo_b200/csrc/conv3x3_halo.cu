@@ -144,7 +144,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     const uint32_t bar_full = bar_acc_empty + 16 * kMaxGroup;           // [kMaxStages]
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;               // [kMaxStages]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + off_bar + 8 + 32 * kMaxGroup + 16 * kMaxStages);
-    const int G = A.group;
 
     const int64_t first = blockIdx.x;
     const int my_tiles = first < A.n_tiles ? (int)((A.n_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
@@ -180,57 +179,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------ TMA producer: one haloed box per K chunk
-        // Tiles are consumed in groups of G: the MMA warp interleaves the MMAs of a group's tiles (see below), so within a group the boxes are
-        // produced chunk-major (chunk c of every tile of the group, then chunk c + 1, ...): the order the consumer waits for them.
         if (lane == 0) {
             int it = 0;
-            for (int g0 = 0; g0 < my_tiles; g0 += G) {
-                const int ng = min(G, my_tiles - g0);
-                for (int c = 0; c < nch; ++c) {
-                    for (int g = 0; g < ng; ++g, ++it) {
-                        const int64_t tile = first + (int64_t)(g0 + g) * gridDim.x;
-                        const int img = (int)(tile / per_img), r = (int)(tile % per_img);
-                        const int y0 = (r / A.tiles_x) * kTH - 1, x0 = (r % A.tiles_x) * kTW - 1;
-                        const int s = it % S, use = it / S;
-                        if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)(use - 1) & 1);
-                        mbar_expect_tx(bar_full + 8 * s, kInRows * 128);
-                        tma_load_4d(sbase + off_ring + (uint32_t)s * stage_bytes, &A.src_map, c * 64, x0, y0, img, bar_full + 8 * s);
-                    }
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int64_t tile = first + (int64_t)tl * gridDim.x;
+                const int img = (int)(tile / per_img), r = (int)(tile % per_img);
+                const int y0 = (r / A.tiles_x) * kTH - 1, x0 = (r % A.tiles_x) * kTW - 1;
+                for (int c = 0; c < nch; ++c, ++it) {
+                    const int s = it % S, use = it / S;
+                    if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)(use - 1) & 1);
+                    mbar_expect_tx(bar_full + 8 * s, kInRows * 128);
+                    tma_load_4d(sbase + off_ring + (uint32_t)s * stage_bytes, &A.src_map, c * 64, x0, y0, img, bar_full + 8 * s);
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------------------------ MMA issuer: 9 taps x 4 K steps per chunk and tile.
-        // A tile's 36 x chunks MMAs all accumulate into ONE TMEM accumulator.  G > 1 interleaves the MMAs of G tiles (independent accumulators);
-        // built to test whether dependent accumulates limit the issue rate -- they do not, the interleaved form is 4x slower (see the host
-        // code), so G = 1 is what runs: two accumulator sets, the epilogue of tile i overlaps the MMAs of tile i + 1.
+        // ------------------------------------------------------------------------------------ MMA issuer: 9 taps x 4 K steps per chunk.
+        // All MMAs of a tile accumulate into ONE TMEM accumulator, back to back.  (A variant that walked tiles in groups with one accumulator
+        // per tile and interleaved their MMAs was built to test whether the dependent-accumulate chain limits the issue rate; it measured
+        // 3.5 - 4x slower -- 193 / 212 us for groups of 1 / 4 against 55 us at 64 -> 64 @ 80 x 80, batch 64 -- and was dropped.)
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(kFmt, 128, n_pad);
             mbar_wait(bar_w, 0);
             int it = 0;
-            for (int g0 = 0; g0 < my_tiles; g0 += G) {
-                const int ng = min(G, my_tiles - g0), grp = g0 / G, set = grp & 1, use = grp >> 1;  // accumulator set and how often it was used
-                if (use > 0)
-                    for (int g = 0; g < ng; ++g) mbar_wait(bar_acc_empty + 8 * (set * kMaxGroup + g), (uint32_t)(use - 1) & 1);
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int b = tl & 1, ub = tl >> 1;
+                if (ub > 0) mbar_wait(bar_acc_empty + 8 * b, (uint32_t)(ub - 1) & 1);
                 tc_fence_after();
-                for (int c = 0; c < nch; ++c, it += ng) {
-                    for (int g = 0; g < ng; ++g) mbar_wait(bar_full + 8 * ((it + g) % S), (uint32_t)((it + g) / S) & 1);
+                const uint32_t d = tmem + (uint32_t)b * n_pad;
+                for (int c = 0; c < nch; ++c, ++it) {
+                    const int s = it % S;
+                    mbar_wait(bar_full + 8 * s, (uint32_t)(it / S) & 1);
                     tc_fence_after();
+                    const uint32_t a_base = sbase + off_ring + (uint32_t)s * stage_bytes;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t shift = (uint32_t)((tap / 3) * kPitch + tap % 3) * 128;
+                        const uint32_t a_tap = a_base + (uint32_t)((tap / 3) * kPitch + tap % 3) * 128;
                         const uint32_t b_tap = sbase + (uint32_t)(tap * nch + c) * A.tile_w_bytes;
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t db = umma_desc_sw128(b_tap + 32 * ks);
-                            for (int g = 0; g < ng; ++g)
-                                umma(tmem + (uint32_t)(set * G + g) * n_pad, umma_desc_sw128(sbase + off_ring + (uint32_t)((it + g) % S) * stage_bytes + shift + 32 * ks), db,
-                                     idesc, (c > 0 || tap > 0 || ks > 0) ? 1u : 0u);
-                        }
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma(d, umma_desc_sw128(a_tap + 32 * ks), umma_desc_sw128(b_tap + 32 * ks), idesc, (c > 0 || tap > 0 || ks > 0) ? 1u : 0u);
                     }
-                    for (int g = 0; g < ng; ++g) umma_commit(bar_empty + 8 * ((it + g) % S));
+                    umma_commit(bar_empty + 8 * s);
                 }
-                for (int g = 0; g < ng; ++g) umma_commit(bar_acc_full + 8 * (set * kMaxGroup + g));
+                umma_commit(bar_acc_full + 8 * b);
             }
         }
     } else {
@@ -243,12 +235,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         const uint32_t swz = ((uint32_t)(row * rbo) >> 7) & (uint32_t)(rbo / 16 - 1);
         int sub = 0;
         for (int tl = 0; tl < my_tiles; ++tl) {
-            const int grp = tl / G, set = grp & 1, g = tl - grp * G;
-            const int b = set * G + g, bb = set * kMaxGroup + g;  // TMEM accumulator / its barrier pair
+            const int b = tl & 1, bb = b;  // double-buffered TMEM accumulator and its barrier pair
             const int64_t tile = first + (int64_t)tl * gridDim.x;
             const int img = (int)(tile / per_img), r = (int)(tile % per_img);
             const int y0 = (r / A.tiles_x) * kTH, x0 = (r % A.tiles_x) * kTW;
-            mbar_wait(bar_acc_full + 8 * bb, (uint32_t)(grp >> 1) & 1);
+            mbar_wait(bar_acc_full + 8 * bb, (uint32_t)(tl >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem + (uint32_t)b * n_pad + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < N; c0 += ob, ++sub) {
@@ -380,17 +371,10 @@ extern "C" int el_conv3x3_halo_fwd(const void* x, const int64_t xs_[4], int C, c
     A.wpk = wpk; A.bias = bias; A.B = B; A.H = H; A.W = W; A.N = N; A.chunks = C / 64; A.act = act;
     A.tiles_x = (int)ceil_div(W, c3::kTW); A.tiles_y = (int)ceil_div(H, c3::kTH);
     A.n_tiles = (int64_t)B * A.tiles_x * A.tiles_y;
-    // tiles in flight per CTA = independent accumulators: as many as the ring (every tile of a group holds a stage per chunk step), TMEM
-    // (group * n_pad columns) and kMaxGroup allow; at least 2 so that the epilogue of one overlaps the MMAs of the other
-    // group = 1: one tile per accumulator set, i.e. plain double buffering.  Interleaving the MMAs of several tiles (group = 4, one accumulator
-    // each) was measured 4x SLOWER (212 vs 55 us at 64 -> 64 @ 80 x 80, batch 64; EL_C3_GROUP re-enables it): consecutive tcgen05.mma
-    // instructions that accumulate into the SAME TMEM tile stream through the tensor core, switching the accumulator between instructions does not.
-    static const int group_env = [] { const char* v = getenv("EL_C3_GROUP"); return v ? atoi(v) : 1; }();
-    A.group = group_env < 1 ? 1 : (group_env > c3::kMaxGroup ? c3::kMaxGroup : group_env);
-    while (A.group > 1 && (A.group > A.stages || 2 * A.group * A.n_pad > 512)) --A.group;  // two sets of `group` accumulators in TMEM
+    A.group = 1;  // two accumulators: the epilogue of tile i overlaps the MMAs of tile i + 1
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * A.group * A.n_pad)) cols <<= 1;
-    if (cols > 512 || A.group < 1) return EL_ERR_UNSUPPORTED;
+    while (cols < (uint32_t)(2 * A.n_pad)) cols <<= 1;
+    if (cols > 512) return EL_ERR_UNSUPPORTED;
     A.tmem_cols = cols;
     if (!c3::make_map4(&A.src_map, x, C, W, H, B, xs_, 64, c3::kPitch, c3::kTH + 2, dtype)) return EL_ERR_CUDA;
     if (!c3::make_map4(&A.out_map, out, N, W, H, B, os_, A.ob, c3::kTW, 1, dtype)) return EL_ERR_CUDA;

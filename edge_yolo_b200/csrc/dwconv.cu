@@ -401,6 +401,10 @@ static int launch_dw(const void* x, Strides4 xs, const float* w, const float* bi
     return EL_OK;
 }
 
+// persistent TMA-pipelined k = 3 kernel, dwconv_tma.cu
+int dwconv3_tma_launch(const void* x, Strides4 xs, const float* w, const float* bias, void* out, Strides4 os, int B, int C, int H, int W, int act,
+                       int dtype, cudaStream_t st);
+
 }  // namespace el
 
 using namespace el;
@@ -427,6 +431,15 @@ extern "C" int el_dwconv_fwd(const void* x, const int64_t xs_[4], const float* w
                 if (rc != EL_OK) return rc;
                 note_launches(1);
                 return check_launch();
+            }
+        }
+        if constexpr (sizeof(T) == 2) {
+            // k = 3, C = 16 / 32 / 64 n: persistent TMA-pipelined streaming kernel (dwconv_tma.cu); EL_DW_TMA=0 keeps the cp.async tile kernel
+            static const bool tma_on = [] { const char* v = getenv("EL_DW_TMA"); return !(v && v[0] == '0'); }();
+            if (k == 3 && tma_on) {
+                rc = dwconv3_tma_launch(x, xs, w, bias, out, os, B, C, H, W, act, dtype, st);
+                if (rc == EL_OK) { note_launches(1); return check_launch(); }
+                if (rc != EL_ERR_UNSUPPORTED) return rc;
             }
         }
         if (k == 3) rc = launch_dw<T, 3>(x, xs, w, bias, out, os, B, C, H, W, act, st);

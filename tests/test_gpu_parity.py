@@ -566,6 +566,29 @@ def test_dwconv(dtype, tol, k, shape, epi):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,act", [((2, 64, 80, 80), 0), ((3, 32, 40, 40), 1), ((2, 16, 160, 160), 0), ((2, 128, 20, 20), 2), ((1, 256, 20, 20), 0),
+                                       ((2, 64, 23, 37), 1), ((1, 32, 7, 61), 0), ((5, 16, 45, 19), 1), ((70, 64, 20, 20), 0)])
+def test_dwconv3_tma_pipeline(dtype, shape, act):
+    """k = 3 depthwise conv on the persistent TMA-pipelined kernel (C = 16 / 32 / 64 n, 16-bit): whole tiles and ragged ones, image borders
+    (TMA zero fill = padding), several channel blocks, more tiles than CTAs (ring / barrier phase wrap), channel-slice source and destination
+    views, the three epilogues; against torch fp64 on the same 16-bit inputs."""
+    o = ops()
+    gen = torch.Generator().manual_seed(shape[1] + shape[2])
+    B, C, H, W = shape
+    full = torch.randn(B, C + 16, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    x = full[:, 16:]
+    w = (torch.randn(C, 1, 3, 3, generator=gen) * 0.3).to(DEV)
+    b = torch.randn(C, generator=gen).to(DEV) if act else None
+    want = torch.nn.functional.conv2d(x.double(), w.double(), b.double() if act else None, padding=1, groups=C)
+    want = torch.nn.functional.silu(want) if act == 1 else (want.relu() if act == 2 else want)
+    out = torch.full((B, C + 8, H, W), 7.0, device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
+    got = o.dwconv(x, o.pack_dw_weight(w), 3, bias=b, act=act, out=out[:, 8:])
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
+    close(got, want.float(), tol, tol)
+    assert float((out[:, :8] - 7.0).abs().max()) == 0.0  # nothing written outside the destination view
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("k", [7])
 @pytest.mark.parametrize("shape,epi", [((2, 32, 33, 47), True), ((1, 64, 80, 80), False), ((2, 16, 160, 160), True), ((3, 48, 32, 32), True)])
 def test_dwconv_tensor_core(dtype, shape, epi, k):
