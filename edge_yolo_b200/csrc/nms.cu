@@ -250,6 +250,14 @@ __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay
     if (!(w > 0.f) || !(h > 0.f)) return false;
     float inter = __fmul_rn(w, h);
     float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
+    // Division-free answer when the quotient is clearly on one side of the threshold: p = thr * uni carries one rounding (2^-24), the
+    // quotient another, so a 2e-6 margin decides exactly as the rounded division would; only the band around the threshold (and
+    // degenerate magnitudes) pays for the IEEE division.  The result is the division's in every case.
+    if (uni > 1e-30f && uni < 1e30f && inter > 1e-30f && thr > 0.f) {
+        const float p = __fmul_rn(thr, uni);
+        if (inter > __fmul_rn(p, 1.000002f)) return true;
+        if (inter < __fmul_rn(p, 0.999998f)) return false;
+    }
     return __fdiv_rn(inter, uni) > thr;
 }
 
@@ -285,9 +293,21 @@ __device__ __forceinline__ Cand load_cand(const SweepArgs& P, const unsigned lon
     return c;
 }
 
+// Greedy sweep of one image's sorted candidates, 1024 per chunk, 32 (one warp) per step.  The serial chain of NMS is
+//   "test the warp's candidates against the keeps of the previous step -> resolve the warp -> publish its keeps";
+// everything else is kept off it (ncu of the first version, 54 steps of ~6600 cycles per image: the resolving warp wrote its output rows
+// to global memory and then fenced once per keep so that other warps could follow the class lists concurrently -- MEMBAR.SC.CTA behind
+// outstanding STGs -- and evaluated an IEEE division per overlapping pair inside its lane-serial loop):
+//   * kept boxes live in shared memory with their class tag; within a chunk a candidate tests the keeps it has not seen yet by INDEX
+//     ([checked, nk), class compare first), so new keeps are only read after the step's barrier: no fences;
+//   * per-class newest-first lists (FROM_PRED) serve only the chunk-start bulk test against everything kept by earlier chunks; the
+//     resolver links its keeps with plain stores, the next reader comes after a barrier;
+//   * every warp precomputes, before its turn, which of its higher lanes each lane suppresses (32 x 32 pair masks, shuffles, the
+//     division-free band test), so resolving a warp is a bit loop over its keeps: ffs / shfl / and;
+//   * output rows are written once, at the end, by all threads (the kept candidates' sorted indices are remembered in shared memory).
 template <bool SMEM_KEPT, bool FROM_PRED>
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant__ SweepArgs P) {
-    extern __shared__ float s_kept[];  // [5][kcap] floats, then (FROM_PRED) next[kcap] and head[nb] ints
+    extern __shared__ float s_kept[];  // SMEM_KEPT: [5][kcap] floats; then (FROM_PRED) next[kcap], kcls[kcap], ki[kcap], head[nb] ints
     __shared__ int s_nk[2];
     __shared__ float s_red[2][kSweepThreads / 32];
     __shared__ int s_bucketed;
@@ -303,7 +323,9 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
     // different classes are disjoint after the offset, so a candidate only has to be tested against kept boxes of its own
     // class -- same result, ~nc times fewer IoU tests.  Otherwise (or class-agnostic) everything goes into one list.
     int* s_next = reinterpret_cast<int*>(s_kept + 5 * (SMEM_KEPT ? kcap : 0));
-    int* s_head = s_next + kcap;
+    int* s_kcls = s_next + kcap;
+    int* s_ki = s_kcls + kcap;
+    int* s_head = s_ki + kcap;
     const int nb = (FROM_PRED && !P.agnostic && P.nc <= kMaxBucketClasses) ? P.nc : 1;
     if (FROM_PRED) {
         float lo = INFINITY, hi = -INFINITY;
@@ -331,70 +353,79 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
     for (int c0 = 0; c0 < n && !done; c0 += kSweepThreads) {
         const int i = c0 + tid;
         const bool valid = i < n;
-        Cand cd{};
+        uint32_t cidx = 0;
         float ox1 = 0.f, oy1 = 0.f, ox2 = 0.f, oy2 = 0.f, area = 0.f;
         int bucket = 0;
         if (valid) {
             if (FROM_PRED) {
-                cd = load_cand(P, kb, b, i);
+                const Cand cd = load_cand(P, kb, b, i);
                 const float off = P.agnostic ? 0.f : __fmul_rn(cd.clsf, P.max_wh);  // ops.py:289
                 ox1 = __fadd_rn(cd.rx1, off); oy1 = __fadd_rn(cd.ry1, off); ox2 = __fadd_rn(cd.rx2, off); oy2 = __fadd_rn(cd.ry2, off);
                 bucket = bucketed ? cd.cls : 0;
             } else {
-                cd.idx = ~(uint32_t)kb[i];
-                const float4 bx = __ldg(reinterpret_cast<const float4*>(P.box) + cd.idx);
+                cidx = ~(uint32_t)kb[i];
+                const float4 bx = __ldg(reinterpret_cast<const float4*>(P.box) + cidx);
                 ox1 = bx.x; oy1 = bx.y; ox2 = bx.z; oy2 = bx.w;
             }
             area = __fmul_rn(__fsub_rn(ox2, ox1), __fsub_rn(oy2, oy1));
         }
         bool alive = valid;
-        int checked = 0;  // candidates of this chunk have not been tested against anything yet
+        // ---- chunk start: everything kept by earlier chunks (stable: nobody appends before the first barrier below)
+        int checked = s_nk[step & 1];
+        if (alive && checked > 0) {
+            if (FROM_PRED) {
+                for (int j = s_head[bucket]; j >= 0; j = s_next[j])
+                    if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
+            } else {
+                for (int j = 0; j < checked; ++j)
+                    if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
+            }
+        }
+        // ---- pair masks of this warp: bit j of `sup` = this lane suppresses lane j > lane (same class list, IoU > thr)
+        unsigned sup = 0;
+        if (__any_sync(0xffffffffu, alive)) {
+#pragma unroll 4
+            for (int j = 1; j < 32; ++j) {
+                const float jx1 = __shfl_sync(0xffffffffu, ox1, j), jy1 = __shfl_sync(0xffffffffu, oy1, j);
+                const float jx2 = __shfl_sync(0xffffffffu, ox2, j), jy2 = __shfl_sync(0xffffffffu, oy2, j);
+                const float jar = __shfl_sync(0xffffffffu, area, j);
+                const int jb = FROM_PRED ? __shfl_sync(0xffffffffu, bucket, j) : 0;
+                const bool jal = __shfl_sync(0xffffffffu, (int)alive, j);
+                if (alive && jal && lane < j && jb == bucket && iou_gt(ox1, oy1, ox2, oy2, area, jx1, jy1, jx2, jy2, jar, P.thr)) sup |= 1u << j;
+            }
+        }
+        if (c0 > 0) __syncthreads();  // every warp has finished walking the class lists before the first resolver of this chunk appends to them
         for (int sub = 0; sub < kSweepThreads / 32; ++sub, ++step) {
             if (c0 + sub * 32 >= n) break;  // no candidates left for the remaining warps (uniform)
             const int nk = s_nk[step & 1];
-            if (warp >= sub && alive) {
-                if (FROM_PRED) {  // newest-first list of this candidate's class; entries below `checked` were tested earlier
-                    for (int j = s_head[bucket]; j >= checked; j = s_next[j]) {
-                        if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
-                    }
-                } else {
-                    for (int j = checked; j < nk; ++j) {
-                        if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
-                    }
+            if (warp >= sub && alive) {  // keeps published since this candidate last looked (all from this chunk)
+                for (int j = checked; j < nk; ++j) {
+                    if (FROM_PRED && s_kcls[j] != bucket) continue;
+                    if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
                 }
             }
             checked = nk;
             if (warp == sub) {
-                // greedy resolution inside the warp: the lowest alive lane is kept, then kills its overlaps
+                // greedy resolution inside the warp from the precomputed masks: the lowest alive lane is kept and kills its overlaps
                 unsigned m = __ballot_sync(0xffffffffu, alive), K = 0;
                 while (m) {
                     const int j = __ffs(m) - 1;
                     K |= 1u << j;
-                    float jx1 = __shfl_sync(0xffffffffu, ox1, j), jy1 = __shfl_sync(0xffffffffu, oy1, j);
-                    float jx2 = __shfl_sync(0xffffffffu, ox2, j), jy2 = __shfl_sync(0xffffffffu, oy2, j);
-                    float jar = __shfl_sync(0xffffffffu, area, j);
-                    if (alive && lane > j && iou_gt(jx1, jy1, jx2, jy2, jar, ox1, oy1, ox2, oy2, area, P.thr)) alive = false;
-                    m = __ballot_sync(0xffffffffu, alive) & ~((2u << j) - 1u);
+                    m &= ~(__shfl_sync(0xffffffffu, sup, j) | (1u << j));
                 }
                 const int rank = nk + __popc(K & ((1u << lane) - 1u));
                 const bool keep = ((K >> lane) & 1u) && rank < P.max_det;
                 if (keep) {
                     kx1[rank] = ox1; ky1[rank] = oy1; kx2[rank] = ox2; ky2[rank] = oy2; kar[rank] = area;
-                    if (FROM_PRED) {
-                        float* o = P.out + ((int64_t)b * P.max_det + rank) * 6;
-                        o[0] = cd.rx1; o[1] = cd.ry1; o[2] = cd.rx2; o[3] = cd.ry2; o[4] = cd.score; o[5] = cd.clsf;
-                        if (P.out_index) P.out_index[(int64_t)b * P.max_det + rank] = (int64_t)cd.idx;
-                    } else {
-                        P.keep[rank] = (int64_t)cd.idx;
-                    }
+                    if (FROM_PRED) { s_kcls[rank] = bucket; s_ki[rank] = i; }
+                    else P.keep[rank] = (int64_t)cidx;
                 }
-                if (FROM_PRED) {  // link the new keeps into their class lists in rank order (lists stay sorted newest-first)
+                if (FROM_PRED) {  // link the new keeps into their class lists in rank order (lists stay newest-first); read at the next chunk start
                     unsigned km = __ballot_sync(0xffffffffu, keep);
                     while (km) {
                         const int j = __ffs(km) - 1;
                         km &= km - 1;
-                        // box data and next pointer are published before the head: warps still in their test loop may already see the entry
-                        if (lane == j) { s_next[rank] = s_head[bucket]; __threadfence_block(); s_head[bucket] = rank; }
+                        if (lane == j) { s_next[rank] = s_head[bucket]; s_head[bucket] = rank; }
                         __syncwarp();
                     }
                 }
@@ -403,11 +434,20 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
                     s_nk[(step + 1) & 1] = nn < P.max_det ? nn : P.max_det;
                 }
             }
-            __syncthreads();  // also publishes global-memory kept entries to the other warps of the CTA
+            __syncthreads();  // publishes the new keeps (shared or global memory) to the other warps of the CTA
             if (s_nk[(step + 1) & 1] >= P.max_det) { done = true; ++step; break; }
         }
     }
-    if (tid == 0) P.out_count[b] = s_nk[step & 1];
+    const int nkf = s_nk[step & 1];
+    if (FROM_PRED) {  // output rows, in rank order, from the remembered sorted indices
+        for (int r = tid; r < nkf; r += kSweepThreads) {
+            const Cand cd = load_cand(P, kb, b, s_ki[r]);
+            float* o = P.out + ((int64_t)b * P.max_det + r) * 6;
+            o[0] = cd.rx1; o[1] = cd.ry1; o[2] = cd.rx2; o[3] = cd.ry2; o[4] = cd.score; o[5] = cd.clsf;
+            if (P.out_index) P.out_index[(int64_t)b * P.max_det + r] = (int64_t)cd.idx;
+        }
+    }
+    if (tid == 0) P.out_count[b] = nkf;
 }
 
 // ---- class-parallel sweep ---------------------------------------------------------------------------
@@ -705,7 +745,7 @@ int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc
         P.handled = handled;
     }
     const int nb = (!agnostic && nc <= kMaxBucketClasses) ? nc : 1;
-    size_t sm = (size_t)6 * max_det * sizeof(float) + (size_t)nb * sizeof(int);
+    size_t sm = (size_t)8 * max_det * sizeof(float) + (size_t)nb * sizeof(int);  // kept boxes [5], next, class tag, sorted index; list heads
     if (sm > 48 * 1024) cudaFuncSetAttribute(nms_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     nms_sweep<true, true><<<B, kSweepThreads, sm, s>>>(P);  // images the class-parallel kernel declined (or all of them)
     note_launches(1);

@@ -5,6 +5,8 @@
 // All kernels are HBM-bound streaming kernels: the fast path walks channel-contiguous (NHWC or
 // NHWC channel-slice) views with 16-byte vectors, one vector per thread per tap; a generic
 // strided kernel (thread order follows the fastest-moving stride) covers NCHW and odd shapes.
+#include <cstdlib>
+
 #include "el_common.cuh"
 
 namespace el {
@@ -619,6 +621,242 @@ __global__ void __launch_bounds__(256) merge_fwd_x2(const T* __restrict__ b, Str
     }
 }
 
+// Exact 2x case, shared-memory staged and software-pipelined (the default for channel-vectorised views).
+// What the profiles of the earlier versions said (round 2, largest site, B = 64, c = 16, 160 x 160):
+//   * merge_fwd_x2 (registers): 18.5 M warp instructions for 205 k warp-level stores -- 90 per store, of which ~30 are the blend; the rest
+//     is per-thread set-up (softplus, 64-bit index products, ten address computations) amortised over eight stores, and the L1 data
+//     pipe is 72 % busy because a 16 B-per-lane load whose lanes alternate between the four band tensors costs 16 wavefronts;
+//   * a first staged version (one CTA = one row chunk: cp.async -> barrier -> blend -> exit) halved the instructions but every CTA of a
+//     wave sat in the same phase: nobody stored while everybody waited for its loads (time = a whole number of ~3.9 us waves).
+// This version: a CTA (channel vector x output column threads) owns a column tile and a RANGE of source rows and streams down it in
+// steps of SR rows through a double buffer: the cp.async loads of step s+2 are in flight while step s is blended and stored, the
+// horizontally blended last row of a step stays in registers (no halo re-read between steps), set-up is paid once per range.
+//   thread (cv, y) stages the fixed slot (band, vector, source column y) of every row (no index arithmetic in the loop); the 4x re-use
+//   of a band pixel is served by LDS.128; 16-bit maps blend with packed fp32x2 arithmetic (horizontal 2 ops / pair, vertical through
+//   the shared difference cur - prev 3 ops / pair).  Tile row layout [band][source column][vector] with a band pitch of S 16-byte units
+//   (S chosen on the host so the 16 B reads of a quarter warp fall into distinct banks).
+//   DRAM reads = band bytes x (cpb/2+2)/(cpb/2) column halo x (RPC+1)/RPC row halo.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ f32x2 mul_f32x2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// 16 bytes of T as packed fp32 pairs (16-bit types: 4 pairs; fp32: 2 pairs)
+template <typename T> struct Pairs { static constexpr int N = Vec16<T>::N / 2; };
+template <typename T> __device__ __forceinline__ void unpack_pairs(uint4 raw, f32x2 (&p)[Pairs<T>::N]) {
+    float f[Vec16<T>::N];
+    unpack<T>(raw, f);
+#pragma unroll
+    for (int i = 0; i < Pairs<T>::N; ++i) p[i] = pack_f32x2(f[2 * i], f[2 * i + 1]);
+}
+template <typename T> __device__ __forceinline__ uint4 pack_pairs(const f32x2 (&p)[Pairs<T>::N]) {
+    float f[Vec16<T>::N];
+#pragma unroll
+    for (int i = 0; i < Pairs<T>::N; ++i) unpack_f32x2(p[i], f[2 * i], f[2 * i + 1]);
+    return pack<T>(f);
+}
+
+// blend state of one thread: the horizontally blended previous source row.  16-bit maps keep it as packed fp32 pairs.
+template <typename T, bool FAST> struct MergeRow;
+template <typename T> struct MergeRow<T, true> {
+    static constexpr int NP = Pairs<T>::N;
+    f32x2 v[NP];
+    __device__ __forceinline__ void hblend(uint4 a0, uint4 a1, float ax, float bx) {
+        const f32x2 ax2 = pack_f32x2(ax, ax), bx2 = pack_f32x2(bx, bx);
+        f32x2 v0[NP], v1[NP];
+        unpack_pairs<T>(a0, v0);
+        unpack_pairs<T>(a1, v1);
+#pragma unroll
+        for (int e = 0; e < NP; ++e) v[e] = fma_f32x2(v1[e], bx2, mul_f32x2(v0[e], ax2));
+    }
+    __device__ __forceinline__ uint4 packed() const { return pack_pairs<T>(v); }
+    // rows 2k+1 = .75 prev + .25 cur and 2k+2 = .25 prev + .75 cur through the shared difference d = cur - prev
+    __device__ __forceinline__ void vblend(const MergeRow& cur, uint4& lo, uint4& hi) const {
+        const f32x2 neg1 = pack_f32x2(-1.f, -1.f), q25 = pack_f32x2(0.25f, 0.25f), nq25 = pack_f32x2(-0.25f, -0.25f);
+        f32x2 r0[NP], r1[NP];
+#pragma unroll
+        for (int e = 0; e < NP; ++e) {
+            const f32x2 d = fma_f32x2(v[e], neg1, cur.v[e]);
+            r0[e] = fma_f32x2(d, q25, v[e]);
+            r1[e] = fma_f32x2(d, nq25, cur.v[e]);
+        }
+        lo = pack_pairs<T>(r0);
+        hi = pack_pairs<T>(r1);
+    }
+};
+template <typename T> struct MergeRow<T, false> {  // fp32 maps: the reference's operation order, scalar IEEE arithmetic
+    static constexpr int V = Vec16<T>::N;
+    float v[V];
+    __device__ __forceinline__ void hblend(uint4 a0, uint4 a1, float ax, float bx) {
+        float v0[V], v1[V];
+        unpack<T>(a0, v0);
+        unpack<T>(a1, v1);
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = ax * v0[e] + bx * v1[e];
+    }
+    __device__ __forceinline__ uint4 packed() const { return pack<T>(v); }
+    __device__ __forceinline__ void vblend(const MergeRow& cur, uint4& lo, uint4& hi) const {
+        float r0[V], r1[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            r0[e] = 0.75f * v[e] + 0.25f * cur.v[e];
+            r1[e] = 0.25f * v[e] + 0.75f * cur.v[e];
+        }
+        lo = pack<T>(r0);
+        hi = pack<T>(r1);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) merge_fwd_x2p(const T* __restrict__ b, Strides4 bs, BandPtrs bands, const float* __restrict__ alpha,
+                                                     T* __restrict__ out, Strides4 os, int c, int CVb, int hv, int hv_shift, int SR, int RPC, int h,
+                                                     int w, int S) {
+    constexpr int V = Vec16<T>::N;
+    constexpr bool kFast = sizeof(T) == 2;  // 16-bit maps: SFU softplus, packed fp32x2 blends
+    extern __shared__ __align__(16) unsigned char merge_smem[];
+    pdl_launch_dependents();
+    const int H = 2 * h, W = 2 * w;
+    const int cv = (int)threadIdx.x, xi = (int)threadIdx.y, cpb = (int)blockDim.y;
+    const int X0 = (int)blockIdx.x * cpb, X = X0 + xi;
+    const int u = max(cv - CVb, 0);
+    const int seg = min(hv_shift >= 0 ? u >> hv_shift : u / hv, 3), vi = u - seg * hv;
+    float wb;
+    {   // softplus(alpha) / (sum + 1e-6), same operation order as band_weights()
+        const int lane = (cv + (int)blockDim.x * xi) & 31;
+        const float a = __ldg(alpha + (lane & 3));
+        const float sp = a > 20.f ? a : (kFast ? __logf(1.f + __expf(a)) : log1pf(expf(a)));
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s += __shfl_sync(0xffffffffu, sp, i);
+        s += 1e-6f;
+        const float spb = __shfl_sync(0xffffffffu, sp, seg);
+        wb = kFast ? __fdividef(spb, s) : spb / s;
+    }
+    const int ka = (int)blockIdx.y * RPC, kb = min(ka + RPC, h);  // source-row intervals [ka, kb) of this CTA: needs rows ka .. kb (clamped)
+    const int y_first = ka == 0 ? 0 : 2 * ka + 1;                 // output rows y_first .. min(2 kb, H - 1)
+    pdl_wait();  // everything above overlapped the producer's tail; activations are read (and `out` is written) only from here on
+    if (cv < CVb) {  // pass-through copy of b (full-concat form only); these threads take no part in the staging
+        if (X < W) {
+            const int y_last = min(2 * kb, H - 1);
+            const T* p = b + (int64_t)blockIdx.z * bs.n + (int64_t)y_first * bs.h + (int64_t)X * bs.w + cv * V;
+            T* q = out + (int64_t)blockIdx.z * os.n + (int64_t)y_first * os.h + (int64_t)X * os.w + cv * V;
+#pragma unroll 4
+            for (int y = y_first; y <= y_last; ++y, p += bs.h, q += os.h) stg_stream(q, ldg_stream(p));
+        }
+        return;  // exited threads do not count at the CTA barrier
+    }
+    const int n_scols = cpb / 2 + 2, sc0 = max(X0 / 2 - 1, 0);
+    const int row_units = 4 * S;
+    uint4* const row0 = reinterpret_cast<uint4*>(merge_smem);      // source row ka
+    uint4* const ring = row0 + row_units;                           // [2][SR] rows: buffer (s & 1) holds rows ka + s SR + 1 .. ka + (s+1) SR
+    // ---- staging: this thread's slot (band seg, vector vi, source column sc0 + xi) of consecutive rows, one running source pointer
+    const bool stager = xi < n_scols;
+    const Strides4 sb = bands.s[seg];
+    const T* src = reinterpret_cast<const T*>(bands.p[seg]) + (int64_t)blockIdx.z * sb.n + (int64_t)ka * sb.h + (int64_t)min(sc0 + xi, w - 1) * sb.w + vi * V;
+    int src_row = ka;                                                // row `src` points at; rows past the bottom edge repeat row h - 1
+    const int slot = seg * S + xi * hv + vi;
+    auto stage_rows = [&](uint4* dst, int n) {                      // next n rows -> dst[0 .. n)
+        if (stager) {
+            for (int r = 0; r < n; ++r, dst += row_units) {
+                cp_async16(dst + slot, src);
+                if (src_row < h - 1) { src += sb.h; ++src_row; }
+            }
+        }
+        cp_async_commit();
+    };
+    const int n_int = kb - ka, n_steps = (n_int + SR - 1) / SR;
+    auto step_rows = [&](int s) { return min(SR, n_int - s * SR); };  // new rows (= intervals) of step s
+    // group 0: row ka + the rows of step 0; group 1: the rows of step 1
+    if (stager) {
+        cp_async16(row0 + slot, src);
+        if (src_row < h - 1) { src += sb.h; ++src_row; }
+    }
+    stage_rows(ring, step_rows(0));
+    if (n_steps > 1) stage_rows(ring + SR * row_units, step_rows(1)); else cp_async_commit();
+
+    const bool active = X < W;
+    // PyTorch's source rule for exact 2x: X = 2m -> (m-1, m) with lambda .75 (X = 0: source 0 alone); X = 2m+1 -> (m, m+1) with lambda .25
+    const int m = X >> 1, odd = X & 1;
+    const int x0 = min(odd ? m : max(m - 1, 0), w - 1), x1 = min(x0 + 1, w - 1);
+    const float lx = odd ? 0.25f : (m == 0 ? 0.f : 0.75f);
+    const float ax = (1.f - lx) * wb, bx = lx * wb;
+    const int rd0 = seg * S + (x0 - sc0) * hv + vi, dx = (x1 - x0) * hv;
+    T* q = out + (int64_t)blockIdx.z * os.n + (int64_t)y_first * os.h + (int64_t)min(X, W - 1) * os.w + cv * V;
+    const int64_t oh = os.h;
+    MergeRow<T, kFast> prev, cur;
+    int k = ka;
+    for (int s = 0; s < n_steps; ++s) {
+        cp_async_wait<1>();   // this thread's copies of step s (and row ka) have landed; step s+1 may still be in flight
+        __syncthreads();      // ... and everybody else's
+        const uint4* buf = ring + (s & 1) * SR * row_units + rd0;
+        if (active) {
+            if (s == 0) {
+                prev.hblend(row0[rd0], row0[rd0 + dx], ax, bx);
+                if (ka == 0) {  // output row 0 = source row 0
+                    stg_stream(q, prev.packed());
+                    q += oh;
+                }
+            }
+            const int n = step_rows(s);
+            for (int i = 0; i < n; ++i, ++k, buf += row_units) {
+                cur.hblend(buf[0], buf[dx], ax, bx);
+                uint4 lo, hi;
+                prev.vblend(cur, lo, hi);
+                stg_stream(q, lo);
+                q += oh;
+                if (k < h - 1) {  // the last interval of the image produces one row
+                    stg_stream(q, hi);
+                    q += oh;
+                }
+                prev = cur;
+            }
+        }
+        __syncthreads();      // buffer (s & 1) is free again
+        if (s + 2 < n_steps) stage_rows(ring + (s & 1) * SR * row_units, step_rows(s + 2)); else cp_async_commit();
+    }
+}
+
+// host-side plan of merge_fwd_x2p: column tile that wastes the fewest lanes, row range that gives every SM several resident CTAs
+struct MergePlan { int cpb, SR, RPC, S; dim3 grid, block; size_t smem; bool ok; };
+static inline MergePlan merge_plan(int CVt, int hv, int W, int h, int B, int force_sr, int force_rpc) {
+    MergePlan p{};
+    double best = -1.0;
+    for (int cpb = (256 / CVt) & ~1; cpb >= 4; cpb -= 2) {  // cpb >= 4: the cpb threads of a channel vector stage the cpb/2 + 2 source columns
+        // useful lanes / launched lanes (ragged last column tile, last warp of the CTA); ties go to the wider tile (less column halo)
+        const int tiles = (int)ceil_div(W, cpb);
+        const double eff = (double)W * CVt / ((double)tiles * ceil_div(cpb * CVt, 32) * 32);
+        if (eff > best + 1e-9) { best = eff; p.cpb = cpb; }
+    }
+    if (best < 0.0) return p;
+    const int n_scols = p.cpb / 2 + 2;
+    p.S = n_scols * hv;
+    const int want = hv >= 8 ? 0 : (hv == 4 ? 4 : 2);  // band pitch mod 8 (16 B units): distinct banks for the lanes of a quarter warp
+    if (hv < 8) while (p.S % 8 != want) ++p.S;
+    const int64_t col_tiles = ceil_div(W, p.cpb);
+    p.SR = force_sr > 0 ? force_sr : 4;
+    auto bytes = [&](int SR) { return (size_t)(2 * SR + 1) * 4 * p.S * 16; };
+    while (p.SR > 1 && bytes(p.SR) > 40 * 1024) p.SR >>= 1;
+    p.smem = bytes(p.SR);
+    if (p.smem > 96 * 1024) return p;
+    // row ranges: ~8 CTAs per SM over the whole grid, at least two pipeline steps per CTA where the map is tall enough
+    int64_t splits = ceil_div((int64_t)kSMs * 8, col_tiles * B);
+    const int64_t max_splits = ceil_div(h, 2 * p.SR);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.RPC = (int)ceil_div(h, splits);  // balanced ranges; the last step of a range may be short
+    if (force_rpc > 0) p.RPC = force_rpc;
+    p.grid = dim3((unsigned)col_tiles, (unsigned)ceil_div(h, p.RPC), (unsigned)B);
+    p.block = dim3((unsigned)CVt, (unsigned)p.cpb, 1);
+    p.ok = true;
+    return p;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) gated_tiled(const T* b, Strides4 bs, const T* __restrict__ y, Strides4 ys, const float* __restrict__ gamma, T* o,
                                                    Strides4 os, T* o2, Strides4 os2, int CV, int cols_per_block, int rows, int H, int W) {
@@ -724,6 +962,10 @@ extern "C" int el_wave_merge_fwd(const void* b, const int64_t bs_[4], const void
         if (!band[i]) return EL_ERR_ARG;
         bp.p[i] = band[i];
         bp.s[i] = s4(band_s + 4 * i);
+        // the stride of a size-1 dimension is arbitrary (PyTorch reports 1 for a (B, C, 1, 1) tensor in either memory format): never stepped
+        if (h == 1) bp.s[i].h = 0;
+        if (w == 1) bp.s[i].w = 0;
+        if (B == 1) bp.s[i].n = 0;
     }
     EL_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec16<T>::N;
@@ -731,7 +973,19 @@ extern "C" int el_wave_merge_fwd(const void* b, const int64_t bs_[4], const void
         for (int i = 0; i < 4; ++i) vec = vec && channel_vectorisable<T>(bp.p[i], bp.s[i], c / 2);
         if (!b && !(vec && co / V <= 256 && B <= 65535)) return EL_ERR_UNSUPPORTED;
         if (vec) {
-            if (co / V <= 256 && B <= 65535 && H == 2 * h && W == 2 * w) {
+            static const int use_smem = [] { const char* e = getenv("EL_MERGE_SMEM"); return e ? atoi(e) : 1; }();
+            static const int force_sr = [] { const char* e = getenv("EL_MERGE_SR"); return e ? atoi(e) : 0; }();    // experiment knobs
+            static const int force_rpc = [] { const char* e = getenv("EL_MERGE_RPC"); return e ? atoi(e) : 0; }();
+            MergePlan mp{};
+            if (use_smem && co / V <= 256 && B <= 65535 && H == 2 * h && W == 2 * w) mp = merge_plan(co / V, (c / 2) / V, W, h, B, force_sr, force_rpc);
+            if (mp.ok) {
+                auto kern = merge_fwd_x2p<T>;
+                if (mp.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mp.smem);
+                const int hvv = (c / 2) / V;
+                int hv_shift = -1;
+                for (int sft = 0; sft < 16; ++sft) if ((1 << sft) == hvv) hv_shift = sft;
+                launch_pdl(kern, mp.grid, mp.block, mp.smem, st, (const T*)b, bs, bp, alpha, (T*)out, os, c, b ? c / V : 0, hvv, hv_shift, mp.SR, mp.RPC, h, w, mp.S);
+            } else if (co / V <= 256 && B <= 65535 && H == 2 * h && W == 2 * w) {
                 int cpb, srows;
                 dim3 g = tile_grid(co / V, W, h, B, cpb, srows, 4, 2);  // rows here = SOURCE rows per thread
                 if (srows == 4) merge_fwd_x2<T, 4><<<g, 256, 0, st>>>((const T*)b, bs, bp, alpha, (T*)out, os, c, co / V, cpb, h, w, c_off);

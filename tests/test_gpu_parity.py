@@ -174,6 +174,28 @@ def test_merge_vs_oracle(dtype, tol, cl, shape):
     close(res, O.gated_residual(b, yy, gamma), tol, tol)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("shape", [(2, 16, 36, 44), (1, 32, 6, 130), (2, 64, 34, 18), (1, 256, 12, 10), (1, 512, 4, 6), (3, 16, 2, 2), (1, 48, 70, 54)])
+def test_merge_x2_staged_shapes(dtype, tol, shape):
+    """Exact-2x sites on the shared-memory staged kernel (merge_fwd_x2s): ragged column tiles, several row chunks per CTA, clamped
+    edges, both output forms; channels_last like the engine.  Oracle = the reference's interpolate + cat formulation."""
+    B, c, H, W = shape
+    gen = torch.Generator().manual_seed(H * 1000 + W)
+    cl = torch.channels_last
+    b = torch.randn(B, c, H, W, generator=gen).to(dtype)
+    bands = [torch.randn(B, c // 2, H // 2, W // 2, generator=gen).to(dtype) for _ in range(4)]
+    alpha = torch.tensor([0.5, -0.3, 1.2, 0.1])
+    ref = O.wave_merge(b.float(), *[t.float() for t in bands], alpha)
+    db = [t.to(DEV).contiguous(memory_format=cl) for t in bands]
+    full = ops().wave_merge(b.to(DEV).contiguous(memory_format=cl), *db, alpha.to(DEV))
+    close(full, ref, tol, tol)
+    if dtype != torch.float32:
+        # the two forms may take different kernels (the tile plan depends on the channel-vector count): same fp32 blend up to the order
+        # of its roundings, so equal to the last 16-bit ulp rather than bit for bit
+        got = ops().wave_merge_bands(*db, alpha.to(DEV), H, W)
+        close(got, full[:, c:], 2.0 ** (-7 if dtype == torch.bfloat16 else -10), 1e-6)
+
+
 def test_merge_backward_vs_autograd_of_oracle():
     gen = torch.Generator().manual_seed(4)
     B, c, H, W = 2, 8, 9, 11
