@@ -81,29 +81,60 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// Sorted (descending) top-4 of 16 values by a merge network: four 4-sorters (5 compare-exchanges each), then three "top half of a
+// bitonic merge" steps (c_i = max(a_i, b_{3-i}) keeps the four largest of two sorted quads as a bitonic sequence, two more exchange
+// levels sort it): 76 min / max instead of the 112 of a running insertion -- the insertion was 14 % of the fused kernel's instructions.
+// min / max are exact, so the result is the same multiset the insertion produced, whatever the input order.
+__device__ __forceinline__ void cex(float& a, float& b) {  // a >= b afterwards
+    const float hi = fmaxf(a, b), lo = fminf(a, b);
+    a = hi; b = lo;
+}
+__device__ __forceinline__ void sort4_desc(float& a, float& b, float& c, float& d) {
+    cex(a, b); cex(c, d); cex(a, c); cex(b, d); cex(b, c);
+}
+__device__ __forceinline__ void merge_top4(float& a0, float& a1, float& a2, float& a3, float b0, float b1, float b2, float b3) {
+    a0 = fmaxf(a0, b3); a1 = fmaxf(a1, b2); a2 = fmaxf(a2, b1); a3 = fmaxf(a3, b0);
+    cex(a0, a2); cex(a1, a3); cex(a0, a1); cex(a2, a3);
+}
+__device__ __forceinline__ void top4_of_16(float (&v)[kRegMax], float& t0, float& t1, float& t2, float& t3) {
+    sort4_desc(v[0], v[1], v[2], v[3]);
+    sort4_desc(v[4], v[5], v[6], v[7]);
+    sort4_desc(v[8], v[9], v[10], v[11]);
+    sort4_desc(v[12], v[13], v[14], v[15]);
+    merge_top4(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    merge_top4(v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+    merge_top4(v[0], v[1], v[2], v[3], v[8], v[9], v[10], v[11]);
+    t0 = v[0]; t1 = v[1]; t2 = v[2]; t3 = v[3];
+}
+
+// `swapped` (16-bit maps of the fused kernel): lg[0..7] holds bins 8..15 and lg[8..15] bins 0..7 -- the two 16-byte halves of a side are
+// read in alternating order to keep the shared-memory reads conflict-free.  The sums run per half in bin order and are combined as
+// (bins 0-7) + (bins 8-15), so the result does not depend on which half came first: the dense kernel (swapped = false) and the fused
+// kernel stay bit-identical.
 template <bool FAST>
-__device__ __forceinline__ void side_stats(float (&lg)[kRegMax], float& dist, float* __restrict__ stat5) {
+__device__ __forceinline__ void side_stats(float (&lg)[kRegMax], float& dist, float* __restrict__ stat5, bool swapped = false) {
     float m = lg[0];
 #pragma unroll
     for (int k = 1; k < kRegMax; ++k) m = fmaxf(m, lg[k]);
-    float t0 = -1.f, t1 = -1.f, t2 = -1.f, t3 = -1.f;  // running top-4, descending
+    float t0, t1, t2, t3;  // top-4, descending
     if constexpr (FAST) {
         // 16-bit maps: exp as one FFMA + MUFU.EX2 per bin; the integral, the top-4 and the mean are taken on the unnormalised
         // exponentials and scaled once (same values up to fp32 rounding, ~45 fewer instructions per side)
         constexpr float kLog2e = 1.4426950408889634f;
         const float ml = m * kLog2e;
-        float s = 0.f, d = 0.f;
+        float sa = 0.f, sb = 0.f, da = 0.f, db = 0.f;  // per loaded half: sum and sum of (bin mod 8) * e
 #pragma unroll
-        for (int k = 0; k < kRegMax; ++k) {
-            const float e = ex2_approx(fmaf(lg[k], kLog2e, -ml));
-            s += e;
-            d = fmaf((float)k, e, d);
-            float v = e;
-            float n0 = fmaxf(t0, v); v = fminf(t0, v); t0 = n0;
-            float n1 = fmaxf(t1, v); v = fminf(t1, v); t1 = n1;
-            float n2 = fmaxf(t2, v); v = fminf(t2, v); t2 = n2;
-            t3 = fmaxf(t3, v);
+        for (int k = 0; k < 8; ++k) {
+            lg[k] = ex2_approx(fmaf(lg[k], kLog2e, -ml));
+            lg[8 + k] = ex2_approx(fmaf(lg[8 + k], kLog2e, -ml));
+            sa += lg[k]; sb += lg[8 + k];
+            da = fmaf((float)k, lg[k], da); db = fmaf((float)k, lg[8 + k], db);
         }
+        const float s_lo = swapped ? sb : sa, s_hi = swapped ? sa : sb;
+        const float d_lo = swapped ? db : da, d_hi = swapped ? da : db;
+        const float s = s_lo + s_hi;
+        const float d = fmaf(8.f, s_hi, d_lo + d_hi);
+        top4_of_16(lg, t0, t1, t2, t3);
         const float inv = rcp_fast(s);
         dist = d * inv;
         stat5[0] = to_tf32(t0 * inv); stat5[1] = to_tf32(t1 * inv); stat5[2] = to_tf32(t2 * inv); stat5[3] = to_tf32(t3 * inv);
@@ -116,15 +147,11 @@ __device__ __forceinline__ void side_stats(float (&lg)[kRegMax], float& dist, fl
         float d = 0.f, psum = 0.f;
 #pragma unroll
         for (int k = 0; k < kRegMax; ++k) {
-            float p = lg[k] * inv;
-            d += (float)k * p;
-            psum += p;
-            float v = p;
-            float n0 = fmaxf(t0, v); v = fminf(t0, v); t0 = n0;
-            float n1 = fmaxf(t1, v); v = fminf(t1, v); t1 = n1;
-            float n2 = fmaxf(t2, v); v = fminf(t2, v); t2 = n2;
-            t3 = fmaxf(t3, v);
+            lg[k] = lg[k] * inv;
+            d += (float)k * lg[k];
+            psum += lg[k];
         }
+        top4_of_16(lg, t0, t1, t2, t3);
         dist = d;
         stat5[0] = t0; stat5[1] = t1; stat5[2] = t2; stat5[3] = t3;
         stat5[4] = psum * (1.f / kRegMax);  // prob.mean(dim=2): == 1/16, carries no information but is reproduced
@@ -422,7 +449,7 @@ __host__ __device__ inline EmitLayout emit_layout(int nc, uint32_t esz, int nl) 
     L.bias = cur; cur += (uint32_t)nl * L.bias_ld * 4;  // per level: box bias (64) | class bias (nc)
     L.bar = cur; cur += 16;
     L.stage[0] = cur; cur += kStageCap * 8; L.stage[1] = cur; cur += kStageCap * 8;
-    L.ctl = cur; cur += 64;
+    L.ctl = cur; cur += 96;  // ten ints of staging state, then (at +48) the TileInfo of the tile staged in each buffer
     L.total = cur;
     return L;
 }
@@ -462,6 +489,9 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) gfl_decode_emit_k
     int* s_fcnt = s_scnt + 4;     // [2] number of staged keys to flush
     int* s_fbase = s_scnt + 6;    // [2] reserved base slot in the image's key list
     int* s_fimg = s_scnt + 8;     // [2] image of the staged tile
+    // tile coordinates of the tile in flight in each stage, written by the issuing thread before it arms the barrier (its arrive releases,
+    // the waiters' try_wait acquires): the other 255 threads read 16 bytes instead of redoing the division and the level search per tile
+    TileInfo* s_tinfo = reinterpret_cast<TileInfo*>(smem_raw + ML.ctl + 48);
     if (tid < 2) { s_scnt[tid] = 0; s_slimit[tid] = INT_MAX; s_fcnt[tid] = 0; }
 
     for (int l = 0; l < P.nl; ++l) {
@@ -480,6 +510,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) gfl_decode_emit_k
     const int total = E.B * P.tiles_per_image;
     auto issue = [&](int t, int stage) {  // one thread: arm the barrier with the byte count, then two bulk copies
         const TileInfo ti = tile_info(P, t);
+        s_tinfo[stage] = ti;
         const DecodeLevel& L = P.lv[ti.l];
         const uint32_t nb = (uint32_t)ti.nvalid * 4 * kRegMax * sizeof(T), ncb = (uint32_t)ti.nvalid * nc * sizeof(T);
         const T* gb = reinterpret_cast<const T*>(L.box) + (int64_t)ti.b * L.bs.n + (int64_t)ti.pix0 * (4 * kRegMax);
@@ -515,24 +546,25 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) gfl_decode_emit_k
     };
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int stage = it & 1;
-        const TileInfo ti = tile_info(P, t);
+        mbar_wait(&bar[stage], (it >> 1) & 1);
+        const TileInfo ti = s_tinfo[stage];
         const DecodeLevel& L = P.lv[ti.l];
         const float* w = s_w + ti.l * ML.w_stride;
         const float* bias_b = s_bias + ti.l * bias_ld;
         const float* bias_c = bias_b + 4 * kRegMax;
-        mbar_wait(&bar[stage], (it >> 1) & 1);
 
         {   // phase 1: thread = (anchor a, side): 16 logits from the staged tile
             const int side = tid & 3, a = tid >> 2;
+            const int hswap = sizeof(T) == 2 ? (lane >> 2) & 1 : 0;  // 1: this thread holds bins 8..15 first
             float lg[kRegMax];
             const T* pv = s_box(stage) + a * (4 * kRegMax) + side * kRegMax;
             if constexpr (sizeof(T) == 2) {
-                const int h = (lane >> 2) & 1;  // alternate the half read first: conflict-free 16 B shared loads
+                // alternate the half read first: conflict-free 16 B shared loads; lg keeps the LOADED order (side_stats un-swaps the sums)
                 float f0[8], f1[8];
-                unpack<T>(*reinterpret_cast<const uint4*>(pv + 8 * h), f0);
-                unpack<T>(*reinterpret_cast<const uint4*>(pv + 8 * (h ^ 1)), f1);
+                unpack<T>(*reinterpret_cast<const uint4*>(pv + 8 * hswap), f0);
+                unpack<T>(*reinterpret_cast<const uint4*>(pv + 8 * (hswap ^ 1)), f1);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { lg[k] = h ? f1[k] : f0[k]; lg[8 + k] = h ? f0[k] : f1[k]; }
+                for (int k = 0; k < 8; ++k) { lg[k] = f0[k]; lg[8 + k] = f1[k]; }
             } else {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
@@ -546,7 +578,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) gfl_decode_emit_k
             const float4* bb4 = reinterpret_cast<const float4*>(bias_b + side * kRegMax);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const float4 bv = bb4[v];
+                const float4 bv = bb4[v ^ (2 * hswap)];  // the bias of the bins this half really holds
                 lg[4 * v] += bv.x; lg[4 * v + 1] += bv.y; lg[4 * v + 2] += bv.z; lg[4 * v + 3] += bv.w;
             }
             if (a >= ti.nvalid) {
@@ -554,7 +586,7 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) gfl_decode_emit_k
                 for (int k = 0; k < kRegMax; ++k) lg[k] = 0.f;
             }
             float dist;
-            side_stats<kFast>(lg, dist, &s_stat[a * LD + side * 5]);
+            side_stats<kFast>(lg, dist, &s_stat[a * LD + side * 5], hswap != 0);
             s_dist[side][a] = dist;
         }
         __syncthreads();

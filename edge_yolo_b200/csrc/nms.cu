@@ -14,6 +14,9 @@
 //                  n x n/64 mask in HBM.
 // IoU arithmetic replicates torchvision's fp32 sequence with round-to-nearest intrinsics (no FMA
 // contraction) so keep decisions are bit-exact against the CPU op.
+#include <cstdio>
+#include <cstdlib>
+
 #include "el_internal.h"
 
 namespace el {
@@ -261,6 +264,20 @@ __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay
     return __fdiv_rn(inter, uni) > thr;
 }
 
+// Branch-free form for unrolled loops: 0 = no, 1 = yes, 2 = inside the band around the threshold (the caller evaluates iou_gt, i.e. the
+// IEEE division, for those).  Same arithmetic as iou_gt up to the division.
+__device__ __forceinline__ int iou_class(float4 a, float aarea, float bx1, float by1, float bx2, float by2, float barea, float thr) {
+    const float w = __fsub_rn(fminf(a.z, bx2), fmaxf(a.x, bx1)), h = __fsub_rn(fminf(a.w, by2), fmaxf(a.y, by1));
+    const float inter = __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
+    const float p = __fmul_rn(thr, uni);
+    const bool ov = (w > 0.f) & (h > 0.f);
+    const bool ranged = (uni > 1e-30f) & (uni < 1e30f) & (inter > 1e-30f) & (thr > 0.f);
+    const bool yes = ov & ranged & (inter > __fmul_rn(p, 1.000002f));
+    const bool no = !ov | (ranged & (inter < __fmul_rn(p, 0.999998f)));
+    return yes ? 1 : (no ? 0 : 2);
+}
+
 struct SweepArgs {
     const unsigned long long* keys; int64_t key_stride;
     const int* counts; const SelectState* st; int cap;
@@ -274,7 +291,7 @@ struct SweepArgs {
     const int* handled;                                  // per image: 1 = already done by nms_sweep_classes (may be NULL)
 };
 
-constexpr int kMaxBucketClasses = 2048;  // per-class kept lists are used up to this many classes
+constexpr int kMaxBucketClasses = 2048;  // class tags are used up to this many classes
 
 // raw (un-offset) xyxy box + class of sorted candidate i; shared by the bounds pre-pass and the sweep
 struct Cand { float rx1, ry1, rx2, ry2, score, clsf; uint32_t idx; int cls; };
@@ -295,37 +312,57 @@ __device__ __forceinline__ Cand load_cand(const SweepArgs& P, const unsigned lon
 
 // Greedy sweep of one image's sorted candidates, 1024 per chunk, 32 (one warp) per step.  The serial chain of NMS is
 //   "test the warp's candidates against the keeps of the previous step -> resolve the warp -> publish its keeps";
-// everything else is kept off it (ncu of the first version, 54 steps of ~6600 cycles per image: the resolving warp wrote its output rows
-// to global memory and then fenced once per keep so that other warps could follow the class lists concurrently -- MEMBAR.SC.CTA behind
-// outstanding STGs -- and evaluated an IEEE division per overlapping pair inside its lane-serial loop):
-//   * kept boxes live in shared memory with their class tag; within a chunk a candidate tests the keeps it has not seen yet by INDEX
-//     ([checked, nk), class compare first), so new keeps are only read after the step's barrier: no fences;
-//   * per-class newest-first lists (FROM_PRED) serve only the chunk-start bulk test against everything kept by earlier chunks; the
-//     resolver links its keeps with plain stores, the next reader comes after a barrier;
-//   * every warp precomputes, before its turn, which of its higher lanes each lane suppresses (32 x 32 pair masks, shuffles, the
-//     division-free band test), so resolving a warp is a bit loop over its keeps: ffs / shfl / and;
+// everything else is kept off it.  History (bench.py regime: 2000 tied candidates per image, one dominant class, 54 steps; clock64
+// traces with -DEL_SWEEP_TRACE): the first version spent ~6600 cycles per step -- the resolving warp wrote its output rows to global
+// memory and fenced once per keep so that other warps could follow per-class linked lists concurrently, and evaluated an IEEE division
+// per overlapping pair inside its lane-serial loop.  Now:
+//   * kept boxes live in shared memory (float4 + area) with a class tag; a candidate tests the keeps it has not seen yet by INDEX
+//     ([checked, nk), rounds of four branch-free IoU classes, class compare first), so new keeps are only read after the step's
+//     barrier: no fences, no lists to link;
+//   * the IEEE division is evaluated only inside a 2e-6 band around the threshold (iou_class / iou_gt), results unchanged;
+//   * every warp precomputes, before its turn, which of its higher lanes each lane suppresses (32 x 32 pair masks), so resolving a
+//     warp is a bit loop over its keeps: ffs / shfl / and;
 //   * output rows are written once, at the end, by all threads (the kept candidates' sorted indices are remembered in shared memory).
+// Also measured and dropped: only the next two resolvers walking (the pre-walk of a large backlog then sits on the barrier: 281 us
+// against 169), and a barrier-free producer / consumer variant (one chain warp with a scheduler of its own, 24 tester warps covering the
+// groups ahead of it, ld.acquire / st.release hand-over: 190 us -- a single warp issues a dependent instruction every ~5 cycles, so the
+// chain's own 14 tests + bit loop per group cost what the contention had cost before).
 template <bool SMEM_KEPT, bool FROM_PRED>
 __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant__ SweepArgs P) {
-    extern __shared__ float s_kept[];  // SMEM_KEPT: [5][kcap] floats; then (FROM_PRED) next[kcap], kcls[kcap], ki[kcap], head[nb] ints
+    extern __shared__ __align__(16) float s_kept[];  // SMEM_KEPT: kept boxes float4[kcap], areas[kcap]; then (FROM_PRED) class tags[kcap], sorted indices[kcap]
     __shared__ int s_nk[2];
     __shared__ float s_red[2][kSweepThreads / 32];
     __shared__ int s_bucketed;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (P.handled && P.handled[b]) return;
+#ifdef EL_SWEEP_TRACE
+    __shared__ long long s_tr[8];
+    if (tid < 8) s_tr[tid] = 0;
+    const long long tr_begin = clock64();
+#define TR_MARK(var) const long long var = clock64()
+#define TR_ADD(k, a, b_) do { if (lane == 0) atomicAdd((unsigned long long*)&s_tr[k], (unsigned long long)((b_) - (a))); } while (0)
+#else
+#define TR_MARK(var)
+#define TR_ADD(k, a, b_)
+#endif
     const int n = seg_count(P.counts, P.st, b, P.cap);
     const int kcap = SMEM_KEPT ? P.max_det : P.cap;
-    float* kx1 = SMEM_KEPT ? s_kept : P.gkept;
-    float *ky1 = kx1 + kcap, *kx2 = ky1 + kcap, *ky2 = kx2 + kcap, *kar = ky2 + kcap;
+    float4* kbox = reinterpret_cast<float4*>(SMEM_KEPT ? s_kept : P.gkept);
+    float* kar = reinterpret_cast<float*>(kbox + kcap);
     const unsigned long long* kb = P.keys + (int64_t)b * P.key_stride;
-    // Per-class kept lists (FROM_PRED only).  The reference separates classes by adding cls*max_wh to the coordinates
-    // (ops.py:289-295); when every candidate coordinate of this image lies in an interval narrower than max_wh, boxes of
-    // different classes are disjoint after the offset, so a candidate only has to be tested against kept boxes of its own
-    // class -- same result, ~nc times fewer IoU tests.  Otherwise (or class-agnostic) everything goes into one list.
-    int* s_next = reinterpret_cast<int*>(s_kept + 5 * (SMEM_KEPT ? kcap : 0));
-    int* s_kcls = s_next + kcap;
+    // one candidate against kept entry j: 0 / 1, the band around the threshold resolved by the exact division
+    auto hits = [&](int j, float ox1, float oy1, float ox2, float oy2, float area) -> bool {
+        const float4 kbx = kbox[j];
+        const float ka = kar[j];
+        const int r = iou_class(kbx, ka, ox1, oy1, ox2, oy2, area, P.thr);
+        return r == 2 ? iou_gt(kbx.x, kbx.y, kbx.z, kbx.w, ka, ox1, oy1, ox2, oy2, area, P.thr) : r == 1;
+    };
+    // Class tags (FROM_PRED only).  The reference separates classes by adding cls*max_wh to the coordinates (ops.py:289-295); when
+    // every candidate coordinate of this image lies in an interval narrower than max_wh, boxes of different classes are disjoint
+    // after the offset, so a candidate only needs the IoU against kept boxes of its own class -- same result, the other pairs cost a
+    // compare.  Otherwise (or class-agnostic) every keep carries tag 0.
+    int* s_kcls = reinterpret_cast<int*>(s_kept + 5 * (SMEM_KEPT ? kcap : 0));
     int* s_ki = s_kcls + kcap;
-    int* s_head = s_ki + kcap;
     const int nb = (FROM_PRED && !P.agnostic && P.nc <= kMaxBucketClasses) ? P.nc : 1;
     if (FROM_PRED) {
         float lo = INFINITY, hi = -INFINITY;
@@ -336,7 +373,6 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
         }
         lo = -warp_max(-lo); hi = warp_max(hi);
         if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
-        for (int i = tid; i < nb; i += kSweepThreads) s_head[i] = -1;
     }
     if (tid == 0) { s_nk[0] = 0; s_nk[1] = 0; }
     __syncthreads();
@@ -370,17 +406,34 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
             area = __fmul_rn(__fsub_rn(ox2, ox1), __fsub_rn(oy2, oy1));
         }
         bool alive = valid;
-        // ---- chunk start: everything kept by earlier chunks (stable: nobody appends before the first barrier below)
-        int checked = s_nk[step & 1];
-        if (alive && checked > 0) {
-            if (FROM_PRED) {
-                for (int j = s_head[bucket]; j >= 0; j = s_next[j])
-                    if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
-            } else {
-                for (int j = 0; j < checked; ++j)
-                    if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
+        TR_MARK(tc0);
+        // walk kept entries [j0, j1) for this thread's candidate: rounds of four branch-free IoU classes (the loads and the tests of a
+        // round overlap; rounds of eight were measured slower: a step publishes ~6 keeps, the padding of the second half is wasted
+        // issue slots for all 32 warps), class compare first
+        auto walk = [&](int j0, int j1) {
+            for (int j = j0; j < j1 && alive; j += 4) {
+                int any1 = 0, any2 = 0;
+                int code[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = min(j + u, j1 - 1);  // the tail repeats the last entry (idempotent)
+                    const int r = iou_class(kbox[jj], kar[jj], ox1, oy1, ox2, oy2, area, P.thr);
+                    code[u] = (FROM_PRED && s_kcls[jj] != bucket) ? 0 : r;
+                    any1 |= code[u] & 1; any2 |= code[u] & 2;
+                }
+                if (any1) alive = false;
+                else if (any2) {  // rare: inside the band around the threshold -> the division decides
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (code[u] == 2 && hits(min(j + u, j1 - 1), ox1, oy1, ox2, oy2, area)) alive = false;
+                }
             }
-        }
+        };
+        // ---- chunk start: everything kept by earlier chunks
+        int checked = s_nk[step & 1];
+        if (alive && checked > 0) walk(0, checked);
+        TR_MARK(tc1);
+        if (warp == 0) TR_ADD(4, tc0, tc1);
         // ---- pair masks of this warp: bit j of `sup` = this lane suppresses lane j > lane (same class list, IoU > thr)
         unsigned sup = 0;
         if (__any_sync(0xffffffffu, alive)) {
@@ -394,17 +447,18 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
                 if (alive && jal && lane < j && jb == bucket && iou_gt(ox1, oy1, ox2, oy2, area, jx1, jy1, jx2, jy2, jar, P.thr)) sup |= 1u << j;
             }
         }
-        if (c0 > 0) __syncthreads();  // every warp has finished walking the class lists before the first resolver of this chunk appends to them
+        TR_MARK(tc2);
+        if (warp == 0) TR_ADD(5, tc1, tc2);
         for (int sub = 0; sub < kSweepThreads / 32; ++sub, ++step) {
             if (c0 + sub * 32 >= n) break;  // no candidates left for the remaining warps (uniform)
             const int nk = s_nk[step & 1];
+            TR_MARK(ts0);
             if (warp >= sub && alive) {  // keeps published since this candidate last looked (all from this chunk)
-                for (int j = checked; j < nk; ++j) {
-                    if (FROM_PRED && s_kcls[j] != bucket) continue;
-                    if (iou_gt(kx1[j], ky1[j], kx2[j], ky2[j], kar[j], ox1, oy1, ox2, oy2, area, P.thr)) { alive = false; break; }
-                }
+                walk(checked, nk);
             }
             checked = nk;
+            TR_MARK(ts1);
+            if (warp == sub) TR_ADD(0, ts0, ts1);
             if (warp == sub) {
                 // greedy resolution inside the warp from the precomputed masks: the lowest alive lane is kept and kills its overlaps
                 unsigned m = __ballot_sync(0xffffffffu, alive), K = 0;
@@ -413,32 +467,37 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
                     K |= 1u << j;
                     m &= ~(__shfl_sync(0xffffffffu, sup, j) | (1u << j));
                 }
+                TR_MARK(ts2);
+                TR_ADD(1, ts1, ts2);
                 const int rank = nk + __popc(K & ((1u << lane) - 1u));
                 const bool keep = ((K >> lane) & 1u) && rank < P.max_det;
                 if (keep) {
-                    kx1[rank] = ox1; ky1[rank] = oy1; kx2[rank] = ox2; ky2[rank] = oy2; kar[rank] = area;
+                    kbox[rank] = make_float4(ox1, oy1, ox2, oy2); kar[rank] = area;
                     if (FROM_PRED) { s_kcls[rank] = bucket; s_ki[rank] = i; }
                     else P.keep[rank] = (int64_t)cidx;
-                }
-                if (FROM_PRED) {  // link the new keeps into their class lists in rank order (lists stay newest-first); read at the next chunk start
-                    unsigned km = __ballot_sync(0xffffffffu, keep);
-                    while (km) {
-                        const int j = __ffs(km) - 1;
-                        km &= km - 1;
-                        if (lane == j) { s_next[rank] = s_head[bucket]; s_head[bucket] = rank; }
-                        __syncwarp();
-                    }
                 }
                 if (lane == 0) {
                     int nn = nk + __popc(K);
                     s_nk[(step + 1) & 1] = nn < P.max_det ? nn : P.max_det;
                 }
+                TR_MARK(ts3);
+                TR_ADD(2, ts2, ts3);
             }
+            TR_MARK(ts4);
             __syncthreads();  // publishes the new keeps (shared or global memory) to the other warps of the CTA
+            TR_MARK(ts5);
+            if (warp == sub) TR_ADD(3, ts4, ts5);
+            if (warp == ((sub + 16) & 31)) TR_ADD(6, ts0, ts5);
             if (s_nk[(step + 1) & 1] >= P.max_det) { done = true; ++step; break; }
         }
     }
     const int nkf = s_nk[step & 1];
+#ifdef EL_SWEEP_TRACE
+    __syncthreads();
+    if (b == 0 && tid == 0)
+        printf("sweep trace image 0: n %d steps %d kept %d | total %lld cyc | resolver: walk %lld resolve %lld publish %lld barrier %lld | chunk: bulk %lld pairmask %lld | other-warp step total %lld\n",
+               n, step, nkf, clock64() - tr_begin, s_tr[0], s_tr[1], s_tr[2], s_tr[3], s_tr[4], s_tr[5], s_tr[6]);
+#endif
     if (FROM_PRED) {  // output rows, in rank order, from the remembered sorted indices
         for (int r = tid; r < nkf; r += kSweepThreads) {
             const Cand cd = load_cand(P, kb, b, s_ki[r]);
@@ -744,8 +803,7 @@ int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc
         note_launches(1);
         P.handled = handled;
     }
-    const int nb = (!agnostic && nc <= kMaxBucketClasses) ? nc : 1;
-    size_t sm = (size_t)8 * max_det * sizeof(float) + (size_t)nb * sizeof(int);  // kept boxes [5], next, class tag, sorted index; list heads
+    size_t sm = (size_t)8 * max_det * sizeof(float);  // kept boxes float4 + area, class tag, sorted index (+ one spare int per keep)
     if (sm > 48 * 1024) cudaFuncSetAttribute(nms_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     nms_sweep<true, true><<<B, kSweepThreads, sm, s>>>(P);  // images the class-parallel kernel declined (or all of them)
     note_launches(1);

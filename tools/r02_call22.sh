@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+cp edge_yolo_b200/libedgeline_b200.so /tmp/lib_backup.so
+cp tools/_trace/libedgeline_b200_trace.so edge_yolo_b200/libedgeline_b200.so
+timeout 200 python tools/prof_detect.py --iters 1 > gpurun_out/c22_trace.log 2>&1
+cp /tmp/lib_backup.so edge_yolo_b200/libedgeline_b200.so
+true
