@@ -58,6 +58,10 @@ _SIGNATURES = {
     "el_dfl_side_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "el_dfl_side_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "el_box_iou": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "el_ap_per_class_workspace_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
+    "el_ap_per_class": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p, c_size_t, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "el_scale_boxes": (c_int, [c_void_p, c_int64, c_int64, c_float, c_float, c_float, c_int, c_int, c_float, c_float, c_void_p]),
     "el_match_predictions": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "el_tal_workspace_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
     "el_tal_assign": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_float] * 3 + [c_void_p, c_size_t] + [c_void_p] * 6),

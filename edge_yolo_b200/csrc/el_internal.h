@@ -32,4 +32,13 @@ int stem_tc_launch(const uint8_t* src, const float* w, const float* bias, void* 
 
 constexpr int kMaxDetSmem = 4096;
 
+__host__ __device__ inline uint32_t pow2ceil(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// descending in-place sort of B key segments (count per segment on the device, pow2 / 16384-multiple padded stride): nms.cu
+void sort_keys_desc(unsigned long long* keys, int64_t stride, const int* counts, int cap, int B, cudaStream_t s);
+
 }  // namespace el

@@ -25,12 +25,6 @@ constexpr int kSortChunk = 16384;  // keys sorted per CTA in shared memory (128 
 constexpr int kSortThreads = 1024;
 constexpr int kSweepThreads = 1024;
 
-__host__ __device__ inline uint32_t pow2ceil(uint32_t v) {
-    uint32_t p = 1;
-    while (p < v) p <<= 1;
-    return p;
-}
-
 // ------------------------------------------------------------------------------- 1. emit
 template <bool MULTI>
 __global__ void __launch_bounds__(256) nms_emit(const float* __restrict__ pred, int nc, int A, float conf, const int32_t* __restrict__ class_keep,
@@ -736,6 +730,8 @@ static void launch_sort(unsigned long long* keys, int64_t stride, const int* cou
         note_launches(1);
     }
 }
+
+void sort_keys_desc(unsigned long long* keys, int64_t stride, const int* counts, int cap, int B, cudaStream_t s) { launch_sort(keys, stride, counts, nullptr, cap, B, s); }
 
 static float threshold_round_down(double thr) {
     float f = (float)thr;

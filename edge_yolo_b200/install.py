@@ -23,7 +23,9 @@ What is replaced (reference path -> ours):
                          v8DetectionLoss (also the name bound in nn/tasks.py) -> detection_loss.v8DetectionLoss
     (metrics=True)
     utils/metrics.py     box_iou (also the name imported by models/yolo/detect/val.py) -> metrics.box_iou
+                         ap_per_class (called by DetMetrics.process, metrics.py:803)   -> metrics.ap_per_class (plot=True: the reference's)
     engine/validator.py  BaseValidator.match_predictions (non-scipy branch)           -> metrics.match_predictions
+    utils/ops.py         scale_boxes (fp32 CUDA tensors; other callers keep the reference's) -> metrics.scale_boxes
 There is no CPU fallback: after install() these functions need CUDA tensors.
 """
 from __future__ import annotations
@@ -48,6 +50,30 @@ def _validator_match_predictions(self, pred_classes, true_classes, iou, use_scip
         orig = next(v for (obj, name), v in _ORIGINALS.items() if name == "match_predictions")
         return orig(self, pred_classes, true_classes, iou, use_scipy=True)
     return metrics.match_predictions(pred_classes, true_classes, iou, self.iouv)
+
+
+def _ap_per_class(tp, conf, pred_cls, target_cls, plot=False, **kw):
+    """`ap_per_class` (utils/metrics.py:537): the curves on the GPU; a plotting request is the reference's own function (matplotlib)."""
+    from . import metrics
+
+    if plot:
+        orig = next(v for (obj, name), v in _ORIGINALS.items() if name == "ap_per_class")
+        return orig(tp, conf, pred_cls, target_cls, plot=True, **kw)
+    return metrics.ap_per_class(tp, conf, pred_cls, target_cls, plot=False, **kw)
+
+
+def _scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None, padding=True, xywh=False):
+    """`scale_boxes` (utils/ops.py:92): the library's kernel for the tensors it is defined for (fp32, CUDA, unit-stride rows -- the
+    predictor's `pred[:, :4]`); numpy arrays and CPU tensors (plotting, dataset utilities) are not this library's inputs and keep
+    the reference's code."""
+    import torch
+
+    from . import metrics
+
+    if isinstance(boxes, torch.Tensor) and boxes.is_cuda and boxes.dtype == torch.float32 and boxes.ndim == 2 and boxes.stride(1) == 1:
+        return metrics.scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=ratio_pad, padding=padding, xywh=xywh)
+    orig = next(v for (obj, name), v in _ORIGINALS.items() if name == "scale_boxes")
+    return orig(img1_shape, boxes, img0_shape, ratio_pad=ratio_pad, padding=padding, xywh=xywh)
 
 
 def install(nms: bool = True, modules: bool = True, losses: bool = True, criterion: bool = True, metrics: bool = False):
@@ -97,7 +123,10 @@ def install(nms: bool = True, modules: bool = True, losses: bool = True, criteri
         _swap(umetrics, "box_iou", el_metrics.box_iou)
         _swap(dval, "box_iou", el_metrics.box_iou)
         _swap(validator.BaseValidator, "match_predictions", _validator_match_predictions)
-        done += ["utils.metrics.box_iou", "models.yolo.detect.val.box_iou", "engine.validator.BaseValidator.match_predictions"]
+        _swap(umetrics, "ap_per_class", _ap_per_class)
+        _swap(uops, "scale_boxes", _scale_boxes)
+        done += ["utils.metrics.box_iou", "models.yolo.detect.val.box_iou", "engine.validator.BaseValidator.match_predictions",
+                 "utils.metrics.ap_per_class", "utils.ops.scale_boxes"]
     return done
 
 

@@ -263,6 +263,22 @@ int el_sppf_pool_fwd(const void* x, const int64_t xs[4], void* out, const int64_
 int el_box_iou(const float* box1, int64_t stride1, const float* box2, int64_t stride2, float* out, int N, int M, float eps, void* stream);
 int el_match_predictions(const float* iou, const float* pred_cls, const float* true_cls, const float* iouv, int L, int D, int T,
                          uint8_t* correct, void* stream);
+/* el_ap_per_class: ap_per_class + compute_ap, utils/metrics.py:505-623, up to the per-class curves (float64 like numpy).
+ *   tp (N, T) bytes 0/1 row-major (T <= 16 IoU thresholds), conf (N), pred_cls (N) class ids as floats -- the concatenated stats of the
+ *   validator (models/yolo/detect/val.py:170-195), device pointers; classes (nc) = np.unique(target_cls) ascending as floats and
+ *   n_labels (nc) its counts, device pointers.  Outputs (device, float64): ap (nc, T), p_curve / r_curve / prec_values (nc, 1000)
+ *   and n_pred (nc) int32 predictions per class; rows of classes without predictions or labels stay zero (metrics.py:571).
+ *   Detections are ordered like np.argsort(-conf, kind="stable").  The O(nc x 1000) tail (F1, smoothing, arg-max, tp / fp
+ *   rounding, metrics.py:602-622) is host work on these arrays.  Workspace from el_ap_per_class_workspace_bytes; N < 2^31.
+ * el_scale_boxes: scale_boxes + clip_boxes, utils/ops.py:92-127 and :319-338, in place on n rows of >= 4 fp32 values (row pitch in
+ *   elements): (x - pad) / gain in IEEE fp32, then clamp x to [0, clip_w] and y to [0, clip_h]; xywh != 0 leaves columns 2, 3
+ *   un-padded as the reference does.  gain / pad are computed by the caller exactly as the reference computes them (host scalars). */
+int el_ap_per_class_workspace_bytes(int64_t N, int T, int nc, size_t* bytes);
+int el_ap_per_class(const uint8_t* tp, const float* conf, const float* pred_cls, int64_t N, int T, const float* classes, const int64_t* n_labels,
+                    int nc, double eps, void* workspace, size_t workspace_bytes, double* ap, double* p_curve, double* r_curve, double* prec_values,
+                    int32_t* n_pred, void* stream);
+int el_scale_boxes(float* boxes, int64_t n, int64_t row_stride, float pad_x, float pad_y, float gain, int padding, int xywh, float clip_w,
+                   float clip_h, void* stream);
 
 /* ---- 8f-1. task-aligned target assignment: TaskAlignedAssigner.forward, utils/tal.py:14-295 (CIoU: utils/metrics.py:74-134) ----
  * scores (B,A,nc) class probabilities, boxes (B,A,4) predicted xyxy in pixels, anchors (A,2) cell centres in pixels,

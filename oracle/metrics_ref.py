@@ -116,3 +116,84 @@ def synthetic_case(seed, n_img=6, nc=5):
         dets.append(det.astype(np.float32))
         labs.append(lab.astype(np.float32))
     return dets, labs
+
+
+def smooth(y: np.ndarray, f: float = 0.05) -> np.ndarray:
+    """Box filter of fraction f, utils/metrics.py:447-452."""
+    nf = round(len(y) * f * 2) // 2 + 1
+    p = np.ones(nf // 2)
+    yp = np.concatenate((p * y[0], y, p * y[-1]), 0)
+    return np.convolve(yp, np.ones(nf) / nf, mode="valid")
+
+
+def ap_per_class(tp: np.ndarray, conf: np.ndarray, pred_cls: np.ndarray, target_cls: np.ndarray, eps: float = 1e-16):
+    """Restatement of `ap_per_class` (utils/metrics.py:537-623, plot=False) with the same 12-tuple.  The only liberty: a STABLE
+    argsort by confidence (the reference's default quicksort leaves the order of exactly tied confidences open)."""
+    order = np.argsort(-conf, kind="stable")
+    tp, conf, pred_cls = tp[order], conf[order], pred_cls[order]
+    classes, nt = np.unique(target_cls, return_counts=True)
+    nc = classes.shape[0]
+    x, prec_values = np.linspace(0, 1, 1000), []
+    ap, p_curve, r_curve = np.zeros((nc, tp.shape[1])), np.zeros((nc, 1000)), np.zeros((nc, 1000))
+    for ci, c in enumerate(classes):
+        sel = pred_cls == c
+        if sel.sum() == 0 or nt[ci] == 0:
+            continue
+        fpc = (1 - tp[sel]).cumsum(0)
+        tpc = tp[sel].cumsum(0)
+        recall = tpc / (nt[ci] + eps)
+        r_curve[ci] = np.interp(-x, -conf[sel], recall[:, 0], left=0)
+        precision = tpc / (tpc + fpc)
+        p_curve[ci] = np.interp(-x, -conf[sel], precision[:, 0], left=1)
+        for j in range(tp.shape[1]):
+            mrec = np.concatenate(([0.0], recall[:, j], [1.0]))
+            mpre = np.concatenate(([1.0], precision[:, j], [0.0]))
+            mpre = np.flip(np.maximum.accumulate(np.flip(mpre)))
+            xs = np.linspace(0, 1, 101)
+            y = np.interp(xs, mrec, mpre)
+            ap[ci, j] = ((y[1:] + y[:-1]) * np.diff(xs) / 2.0).sum()
+            if j == 0:
+                prec_values.append(np.interp(x, mrec, mpre))
+    prec_values = np.array(prec_values)
+    f1_curve = 2 * p_curve * r_curve / (p_curve + r_curve + eps)
+    i = smooth(f1_curve.mean(0), 0.1).argmax()
+    p, r, f1 = p_curve[:, i], r_curve[:, i], f1_curve[:, i]
+    tpo = (r * nt).round()
+    fpo = (tpo / (p + eps) - tpo).round()
+    return tpo, fpo, p, r, f1, ap, classes.astype(int), p_curve, r_curve, f1_curve, x, prec_values
+
+
+def scale_boxes(img1_shape, boxes: np.ndarray, img0_shape, ratio_pad=None, padding=True, xywh=False) -> np.ndarray:
+    """`scale_boxes` + `clip_boxes` (utils/ops.py:92-127, 319-338) on a float32 copy, torch's fp32 arithmetic (subtract, divide, clamp)."""
+    b = np.array(boxes, dtype=np.float32, copy=True)
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1), round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
+    else:
+        gain, pad = ratio_pad[0][0], ratio_pad[1]
+    if padding:
+        b[..., 0] -= np.float32(pad[0])
+        b[..., 1] -= np.float32(pad[1])
+        if not xywh:
+            b[..., 2] -= np.float32(pad[0])
+            b[..., 3] -= np.float32(pad[1])
+    b[..., :4] /= np.float32(gain)
+    b[..., [0, 2]] = b[..., [0, 2]].clip(0, np.float32(img0_shape[1]))
+    b[..., [1, 3]] = b[..., [1, 3]].clip(0, np.float32(img0_shape[0]))
+    return b
+
+
+def ap_case(seed: int, n_det: int = 4000, n_lab: int = 900, nc: int = 7, ties: bool = False):
+    """Seeded validator statistics: confidences in [0, 1), correlated TP flags that fall off with the IoU threshold, a class without
+    predictions and a predicted class without labels; `ties` quantises the confidences (many exact ties)."""
+    rng = np.random.default_rng(seed)
+    conf = rng.random(n_det).astype(np.float32)
+    if ties:
+        conf = (np.round(conf * 50) / 50).astype(np.float32)
+    pred_cls = rng.integers(0, nc + 1, n_det).astype(np.float32)          # class nc has no labels
+    pred_cls[pred_cls == 2] = 3                                             # class 2 has labels but no predictions
+    target_cls = rng.integers(0, nc, n_lab).astype(np.float32)
+    quality = rng.random(n_det) * (0.4 + 0.6 * conf)
+    thr = np.linspace(0.15, 0.75, 10)
+    tp = quality[:, None] > thr[None, :]
+    return tp, conf, pred_cls, target_cls

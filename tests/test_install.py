@@ -91,17 +91,29 @@ def test_install_metrics_opt_in_round_trip():
     import edge_yolo_b200.install as el
     from edge_yolo_b200 import metrics as el_metrics
 
-    o_iou, o_match = umetrics.box_iou, validator.BaseValidator.match_predictions
+    import ultralytics.utils.ops as uops
+
+    o_iou, o_match, o_ap, o_scale = umetrics.box_iou, validator.BaseValidator.match_predictions, umetrics.ap_per_class, uops.scale_boxes
     assert list(inspect.signature(el_metrics.box_iou).parameters) == list(inspect.signature(o_iou).parameters)
+    assert list(inspect.signature(el_metrics.scale_boxes).parameters) == list(inspect.signature(o_scale).parameters)
+    assert list(inspect.signature(el_metrics.ap_per_class).parameters)[:10] == list(inspect.signature(o_ap).parameters)
     names = el.install(metrics=True)
     try:
-        assert len(names) == 19
+        assert len(names) == 21
         assert umetrics.box_iou is el_metrics.box_iou and dval.box_iou is el_metrics.box_iou
+        assert umetrics.ap_per_class is el._ap_per_class and uops.scale_boxes is el._scale_boxes
+        # inputs outside the library's domain keep the reference's code: a CPU tensor goes through the reference's scale_boxes
+        import torch
+
+        cpu_boxes = torch.tensor([[10.0, 20.0, 700.0, 500.0]])
+        want = o_scale((640, 640), cpu_boxes.clone(), (480, 640))
+        assert torch.equal(uops.scale_boxes((640, 640), cpu_boxes.clone(), (480, 640)), want)
         assert list(inspect.signature(validator.BaseValidator.match_predictions).parameters) == list(inspect.signature(o_match).parameters)
         assert dval.DetectionValidator.match_predictions is validator.BaseValidator.match_predictions
     finally:
         el.uninstall()
     assert umetrics.box_iou is o_iou and validator.BaseValidator.match_predictions is o_match and dval.box_iou is o_iou
+    assert umetrics.ap_per_class is o_ap and uops.scale_boxes is o_scale
 
 
 def test_install_repairs_the_references_ihaar_dwt2d():
