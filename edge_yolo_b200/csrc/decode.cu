@@ -800,7 +800,6 @@ extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* 
         !workspace || !out || !out_count || max_det <= 0 || max_nms <= 0)
         return EL_ERR_ARG;
     if (conf < 0.f || conf > 1.f || iou < 0.0 || iou > 1.0) return EL_ERR_ARG;
-    if (max_det > kMaxDetSmem) return EL_ERR_UNSUPPORTED;
     DecodeParams P;
     if (int e = fill_params(P, nl, box, box_s, cls, cls_s, hw, stride, w1, b1, w2, b2, box_bias, cls_bias, nc)) return e;
     if ((int64_t)P.A * nc >= (int64_t)1 << 31) return EL_ERR_UNSUPPORTED;

@@ -340,8 +340,10 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
 #define TR_ADD(k, a, b_)
 #endif
     const int n = seg_count(P.counts, P.st, b, P.cap);
-    const int kcap = SMEM_KEPT ? P.max_det : P.cap;
-    float4* kbox = reinterpret_cast<float4*>(SMEM_KEPT ? s_kept : P.gkept);
+    const int kcap = P.max_det < P.cap ? P.max_det : P.cap;  // keeps never outnumber candidates
+    // !SMEM_KEPT: the kept list lives in global memory (max_det beyond kMaxDetSmem, or el_nms_boxes where every box may be kept); the
+    // batched form gives every image 8 * cap floats of it
+    float4* kbox = reinterpret_cast<float4*>(SMEM_KEPT ? s_kept : P.gkept + (FROM_PRED ? (int64_t)b * 8 * P.cap : 0));
     float* kar = reinterpret_cast<float*>(kbox + kcap);
     const unsigned long long* kb = P.keys + (int64_t)b * P.key_stride;
     // one candidate against kept entry j: 0 / 1, the band around the threshold resolved by the exact division
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(kSweepThreads) nms_sweep(const __grid_constant
     // every candidate coordinate of this image lies in an interval narrower than max_wh, boxes of different classes are disjoint
     // after the offset, so a candidate only needs the IoU against kept boxes of its own class -- same result, the other pairs cost a
     // compare.  Otherwise (or class-agnostic) every keep carries tag 0.
-    int* s_kcls = reinterpret_cast<int*>(s_kept + 5 * (SMEM_KEPT ? kcap : 0));
+    int* s_kcls = reinterpret_cast<int*>(kar + kcap);
     int* s_ki = s_kcls + kcap;
     const int nb = (FROM_PRED && !P.agnostic && P.nc <= kMaxBucketClasses) ? P.nc : 1;
     if (FROM_PRED) {
@@ -698,7 +700,7 @@ NmsLayout nms_layout(int B, int nc, int A, int multi, int max_nms) {
     L.keys2 = off; off = al(off + sizeof(unsigned long long) * L.key2_stride * B);
     const int sweep_cap = L.select ? L.cap2 : L.cap;  // candidates the sweep can see per image
     L.handled = off; off = al(off + sizeof(int) * B);
-    L.gkept = off; off = al(off + sizeof(float) * 5 * (size_t)sweep_cap * B);  // kept boxes of the class-parallel sweep
+    L.gkept = off; off = al(off + sizeof(float) * 8 * (size_t)sweep_cap * B);  // kept boxes of the class-parallel sweep (5 floats per keep); global kept list of nms_sweep for max_det > kMaxDetSmem (8 per keep)
     L.total = off;
     return L;
 }
@@ -799,9 +801,16 @@ int nms_finish(const NmsLayout& L, void* workspace, BoxSource src, int B, int nc
         note_launches(1);
         P.handled = handled;
     }
-    size_t sm = (size_t)8 * max_det * sizeof(float);  // kept boxes float4 + area, class tag, sorted index (+ one spare int per keep)
-    if (sm > 48 * 1024) cudaFuncSetAttribute(nms_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    nms_sweep<true, true><<<B, kSweepThreads, sm, s>>>(P);  // images the class-parallel kernel declined (or all of them)
+    // images the class-parallel kernel declined (or all of them)
+    const int kcap = max_det < P.cap ? max_det : P.cap;
+    if (kcap <= kMaxDetSmem) {
+        size_t sm = (size_t)8 * kcap * sizeof(float);  // kept boxes float4 + area, class tag, sorted index (+ one spare int per keep)
+        if (sm > 48 * 1024) cudaFuncSetAttribute(nms_sweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        nms_sweep<true, true><<<B, kSweepThreads, sm, s>>>(P);
+    } else {  // the reference accepts any max_det (ops.py:167): kept list in the workspace instead of shared memory
+        P.gkept = (float*)(ws + L.gkept);
+        nms_sweep<false, true><<<B, kSweepThreads, 0, s>>>(P);
+    }
     note_launches(1);
     return check_launch();
 }
@@ -814,7 +823,6 @@ extern "C" int el_nms_batched(const float* pred, int B, int nc, int A, float con
     if (!pred || !workspace || !out || !out_count || B <= 0 || nc <= 0 || A <= 0 || max_det <= 0 || max_nms <= 0) return EL_ERR_ARG;
     if (conf < 0.f || conf > 1.f || iou < 0.0 || iou > 1.0) return EL_ERR_ARG;  // ops.py:217-218
     if ((int64_t)A * nc >= (int64_t)1 << 31) return EL_ERR_UNSUPPORTED;
-    if (max_det > kMaxDetSmem) return EL_ERR_UNSUPPORTED;
     const bool multi = multi_label && nc > 1;  // ops.py:239
     const NmsLayout L = nms_layout(B, nc, A, multi, max_nms);
     if (workspace_bytes < L.total) return EL_ERR_WORKSPACE;

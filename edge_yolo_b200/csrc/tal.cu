@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) tal_emit_kernel(const float* __restrict__
             }
             r += dr;
             c += dc;
-            if (c >= nv) { c -= nv; ++r; }
+            while (c >= nv) { c -= nv; ++r; }  // rows wider than the CTA (nc > 256 V) wrap more than once
         }
         __syncthreads();
     }
@@ -254,7 +254,7 @@ extern "C" int el_tal_assign(const float* scores, const float* boxes, const floa
     if (!scores || !boxes || !anchors || !gt_labels || !gt_boxes || !gt_valid || !workspace || !labels || !tboxes || !tscores || !fg || !gt_idx)
         return EL_ERR_ARG;
     if (B <= 0 || A <= 0 || nc <= 0 || M <= 0 || topk <= 0) return EL_ERR_ARG;
-    if (B > 65535 || nc > 256 || !aligned16(tboxes)) return EL_ERR_UNSUPPORTED;
+    if (B > 65535 || nc > (1 << 20) || !aligned16(tboxes)) return EL_ERR_UNSUPPORTED;
     const TalLayout L = tal_layout(B, M, A);
     if (workspace_bytes < L.total) return EL_ERR_WORKSPACE;
     if (!aligned16(workspace)) return EL_ERR_ARG;

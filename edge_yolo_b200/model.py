@@ -176,7 +176,16 @@ class EdgeLineYOLO(nn.Module):
                         and isinstance(nxt, M.DSC3K2_Wavelet) and nxt.f == -1 and isinstance(cat.f, list) and len(cat.f) <= 4):
                     cat.el_lazy = True
                     cat.forward = types.MethodType(M.concat_engine_forward, cat)
+            self.el_engine_fused = True
         return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        """An engine-fused model holds state that no state dict carries (folded-BN biases as fp32 side tensors, packed depthwise
+        filters, the head biases handed to the decode kernel): loading weights into it would silently pair new weights with old
+        biases.  Load the checkpoint first, then `fuse(engine=True)`."""
+        if getattr(self, "el_engine_fused", False):
+            raise RuntimeError("EdgeLineYOLO: load_state_dict after fuse(engine=True) is not supported -- load the checkpoint before fusing")
+        return super().load_state_dict(state_dict, strict=strict, assign=assign)
 
 
 def _dw_eligible(conv: nn.Conv2d, epilogue: bool = False) -> bool:

@@ -96,7 +96,8 @@ def _tal_case(B, imgsz, nc, M, seed, device):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,imgsz,nc,M,topk", [(4, 640, 80, 8, 10), (2, 1280, 10, 5, 13), (3, 160, 3, 1, 10), (3, 128, 80, 12, 10), (3, 256, 4, 16, 13),
-                                             (2, 1600, 2, 3, 10)])   # 52 500 anchors: the metric row does not fit shared memory
+                                             (2, 1600, 2, 3, 10),    # 52 500 anchors: the metric row does not fit shared memory
+                                             (2, 160, 1203, 6, 10), (2, 128, 365, 4, 10)])  # LVIS / Objects365-sized heads: target rows wider than a CTA
 def test_tal_fused_kernel_matches_torch_formulation(B, imgsz, nc, M, topk):
     """`el_tal_assign` (utils/tal.py:14-295 in three kernels) against the torch-op formulation that `test_detection_loss_gpu` pins to the
     reference: identical target scores, and identical labels / boxes / ground-truth indices wherever an anchor carries a non-zero target.

@@ -315,6 +315,8 @@ def _random_pred(gen, B, nc, A, quant=None, img=640.0):
     (2, 10, 33600, dict(conf_thres=0.95, iou_thres=0.7, multi_label=True)),            # 1280^2 anchor count
     (3, 3, 1000, dict(conf_thres=0.001, iou_thres=0.5, multi_label=True, max_det=1000)),
     (2, 4, 3000, dict(conf_thres=0.3, iou_thres=0.45, agnostic=True)),
+    (2, 6, 9000, dict(conf_thres=0.05, iou_thres=0.9, multi_label=True, max_det=20000, max_nms=30000)),  # > 4096 keeps: kept list in the workspace
+    (1, 2, 2500, dict(conf_thres=0.05, iou_thres=0.99, multi_label=True, max_det=100000)),               # max_det beyond the candidate count
 ])
 def test_nms_vs_oracle_bit_exact(B, nc, A, kw):
     from edge_yolo_b200.nms import non_max_suppression

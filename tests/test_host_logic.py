@@ -85,3 +85,17 @@ def test_non_max_suppression_host_branches():
         non_max_suppression(dense, nc=2)                                    # 1 mask channel
     with pytest.raises(EdgelineError):
         non_max_suppression(dense)                                          # CPU tensor: no fallback
+
+
+def test_engine_fused_model_refuses_load_state_dict():
+    """the engine keeps folded biases / packed filters outside the state dict; loading weights after fuse(engine=True) must fail
+    loudly instead of pairing new weights with stale side tensors.  Loading BEFORE fusing is the supported order."""
+    model = EdgeLineYOLO("n", 8).float().eval()
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    model.load_state_dict(state)  # fine: not fused yet
+    try:
+        model.fuse(engine=True)
+    except EdgelineError:
+        pytest.skip("engine fuse needs the CUDA library's weight packing")
+    with pytest.raises(RuntimeError, match="before fusing"):
+        model.load_state_dict(state, strict=False)
