@@ -436,7 +436,8 @@ def step_traffic(kernel):
     """(DRAM bytes read + written by all launches of `kernel` in one step, capture file) from the newest committed ncu capture of the
     default workload (profiles/r*_step_b64_time_dram.json: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`
     over `bench.py --profile-step`).  ncu cannot run inside the timed program, so this is labelled with its source file."""
-    names = {"pwconv": ["pw::pwconv_tc_kernel"], "dwconv": ["el::dwconv_tile_kernel", "dwtc::dwconv_tc_kernel"], "bias_act": ["el::bias_act_tiled", "el::bias_act_flat"],
+    names = {"pwconv": ["pw::pwconv_tc_kernel"], "dwconv": ["el::dwconv_tile_kernel", "dwtc::dwconv_tc_kernel", "dwt::dwconv3_tma_kernel"],
+             "bias_act": ["el::bias_act_tiled", "el::bias_act_flat"], "conv3x3_halo": ["c3::conv3x3_halo_kernel"], "linear_attention": ["ta::linattn_tma_kernel"],
              "stem_conv_u8": ["stemtc::stem_tc_kernel"], "wave_merge_bands": ["el::merge_fwd_x2"], "dwt_haar": ["el::dwt_fwd_tiled"],
              "gfl_decode_emit": ["el::gfl_decode_emit_kernel"], "nms_sweep": ["el::nms_sweep"], "upsample2x_cat": ["el::upsample2x_cat_tiled"]}
     import glob

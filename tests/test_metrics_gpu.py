@@ -98,7 +98,7 @@ def test_ap_per_class_vs_oracle(n_det, n_lab, nc, ties):
     got = metrics.ap_per_class(torch.from_numpy(tp).cuda(), torch.from_numpy(conf).cuda(), torch.from_numpy(pc).cuda(), tc)
     for name, u, v in zip(AP_NAMES, got, want):
         np.testing.assert_allclose(np.asarray(u, dtype=float), np.asarray(v, dtype=float), rtol=1e-9, atol=1e-12, err_msg=name)
-    assert float(np.asarray(want[5]).mean()) > 0.01
+    assert n_lab < 100 or float(np.asarray(want[5]).mean()) > 0.01
 
 
 def test_ap_per_class_empty_inputs():
