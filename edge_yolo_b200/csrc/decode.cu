@@ -14,6 +14,7 @@
 //                            (B, A, 4) and the NMS candidate keys are written (warp-ballot compaction)
 //                            -- 45 % of the dense kernel's HBM traffic.
 #include <climits>
+#include <cstdlib>
 
 #include "el_internal.h"
 
@@ -696,6 +697,274 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 3 : 2) gfl_decode_emit_k
     }
 }
 
+// ---------------------------------------------------------------------------- warp-autonomous fused emit kernel (16-bit maps, single label)
+// gfl_decode_emit_kernel walks 64-anchor tiles with the whole CTA: three CTA barriers per tile, every warp in the same phase at the same
+// time (all in the MUFU-heavy softmax, then all in the min / max network, then all in the class scan), issue slots 59 % busy at 24 warps
+// per SM, and the per-tile bookkeeping (tile coordinates, staging hand-over) runs in all eight warps.  Here a WARP owns a slab of 16
+// anchors from the bulk copy to the candidate keys and synchronises with nobody but itself:
+//   lane 0 issues two 1-D bulk copies (box slab 2 KB, class slab 32 nc bytes) onto the warp's own mbarriers -- the next slab's box copy as
+//   soon as the softmax phase has consumed the current one, its class copy after the class scan;
+//   phase 1  lanes <-> (anchor of 8, side) twice: softmax statistics -> the warp's 16 x 28 TF32 statistics tile, DFL distances;
+//   phase 2  the warp's own m16 tile through the DGQP hidden layer: 24 mma.sync m16n8k8, partial sums kept in the order of the CTA kernel
+//            (hidden units 0-31 and 32-63 separately, then added), so quality and scores are bit-identical to it and to the dense kernel;
+//   phase 3  lanes <-> (anchor of 8, class quarter) twice: logit maximum, windowed scoring, first-max combine; boxes by the quarter-0 lanes;
+//   one atomicAdd per slab reserves the key slots of its <= 16 candidates.
+// With 24 independent warps per SM in different phases the schedulers always find an issuable warp; __syncwarp is the only barrier.
+constexpr int kSlab = 16;
+constexpr int kWarpsPerCta = 12;
+
+struct WarpEmitLayout { uint32_t w, bias, warp0, warp_stride, box, cls, stat, dist, bar, total; int bias_ld, w_stride; };
+__host__ __device__ inline WarpEmitLayout warp_emit_layout(int nc, int nl) {
+    WarpEmitLayout L;
+    L.w_stride = WL<true>::total;
+    L.bias_ld = (4 * kRegMax + nc + 3) & ~3;
+    uint32_t cur = 0;
+    L.w = cur; cur += (uint32_t)nl * L.w_stride * 4;
+    L.bias = cur; cur += (uint32_t)nl * L.bias_ld * 4;
+    cur = (cur + 127u) & ~127u;
+    L.warp0 = cur;
+    uint32_t o = 0;
+    L.box = o; o += kSlab * 4 * kRegMax * 2;
+    L.cls = o; o += ((uint32_t)kSlab * nc * 2 + 127u) & ~127u;
+    L.stat = o; o += kSlab * WL<true>::stat_ld * 4;
+    L.dist = o; o += 4 * kSlab * 4;
+    L.bar = o; o += 16;
+    L.warp_stride = (o + 127u) & ~127u;
+    L.total = L.warp0 + kWarpsPerCta * L.warp_stride;
+    return L;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) gfl_decode_emit_warp_kernel(const __grid_constant__ DecodeParams P, const __grid_constant__ EmitArgs E) {
+    static_assert(sizeof(T) == 2, "16-bit maps only");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int LD = WL<true>::stat_ld;
+    const int nc = P.nc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const WarpEmitLayout ML = warp_emit_layout(nc, P.nl);
+    float* s_w = (float*)(smem_raw + ML.w);
+    float* s_bias = (float*)(smem_raw + ML.bias);
+    unsigned char* wbase = smem_raw + ML.warp0 + warp * ML.warp_stride;
+    T* s_box = (T*)(wbase + ML.box);
+    T* s_cls = (T*)(wbase + ML.cls);
+    float* s_stat = (float*)(wbase + ML.stat);
+    float (*s_dist)[kSlab] = (float (*)[kSlab])(wbase + ML.dist);
+    uint64_t* bar = (uint64_t*)(wbase + ML.bar);  // [0] box slab, [1] class slab
+
+    for (int l = 0; l < P.nl; ++l) {
+        load_level_weights<true>(s_w + l * ML.w_stride, P.lv[l]);
+        for (int i = tid; i < 4 * kRegMax + nc; i += kWarpsPerCta * 32)
+            s_bias[l * ML.bias_ld + i] = i < 4 * kRegMax ? (P.lv[l].bb ? __ldg(P.lv[l].bb + i) : 0.f) : (P.lv[l].cb ? __ldg(P.lv[l].cb + i - 4 * kRegMax) : 0.f);
+    }
+    if (lane < kSlab) *reinterpret_cast<float4*>(&s_stat[lane * LD + kStat]) = make_float4(0.f, 0.f, 0.f, 0.f);  // K padding 20 -> 24, written once
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // slabs of this warp: u = first + k * stride; slab u = quarter (u & 3) of tile (u >> 2)
+    const int total = E.B * P.tiles_per_image * 4;
+    const int stride = gridDim.x * kWarpsPerCta, first = blockIdx.x * kWarpsPerCta + warp;
+    struct Slab { int b, l, pix0, nval; };
+    auto slab_of = [&](int u) {
+        const TileInfo ti = tile_info(P, u >> 2);
+        Slab sl;
+        sl.b = ti.b; sl.l = ti.l; sl.pix0 = ti.pix0 + kSlab * (u & 3);
+        sl.nval = max(min(ti.nvalid - kSlab * (u & 3), kSlab), 0);
+        return sl;
+    };
+    auto issue_box = [&](const Slab& sl) {   // lane 0 only
+        const DecodeLevel& L = P.lv[sl.l];
+        const uint32_t nb = (uint32_t)sl.nval * 4 * kRegMax * sizeof(T);
+        mbar_expect_tx(&bar[0], nb);
+        bulk_g2s(s_box, reinterpret_cast<const T*>(L.box) + (int64_t)sl.b * L.bs.n + (int64_t)sl.pix0 * (4 * kRegMax), nb, &bar[0]);
+    };
+    auto issue_cls = [&](const Slab& sl) {   // lane 0 only
+        const DecodeLevel& L = P.lv[sl.l];
+        const uint32_t ncb = (uint32_t)sl.nval * nc * sizeof(T);
+        mbar_expect_tx(&bar[1], ncb);
+        bulk_g2s(s_cls, reinterpret_cast<const T*>(L.cls) + (int64_t)sl.b * L.cs.n + (int64_t)sl.pix0 * nc, ncb, &bar[1]);
+    };
+    // skip empty slabs (quarters past the end of a ragged tile)
+    auto next_live = [&](int u, Slab& sl) {
+        for (; u < total; u += stride) {
+            sl = slab_of(u);
+            if (sl.nval > 0) return u;
+        }
+        return total;
+    };
+    Slab cur, nxt;
+    int u = next_live(first, cur);
+    if (u < total && lane == 0) { issue_box(cur); issue_cls(cur); }
+    const int g = lane >> 2, t4 = lane & 3;
+    const int hswap = g & 1;  // 1: this lane reads bins 8..15 of a side first (conflict-free 16 B shared loads)
+    const int cq = (nc + 3) >> 2;
+    uint32_t phase = 0;
+    for (; u < total; phase ^= 1) {
+        const int un = next_live(u + stride, nxt);
+        const DecodeLevel& L = P.lv[cur.l];
+        const float* w = s_w + cur.l * ML.w_stride;
+        const float* bias_b = s_bias + cur.l * ML.bias_ld;
+        const float* bias_c = bias_b + 4 * kRegMax;
+        mbar_wait(&bar[0], phase);
+        // ---- phase 1: (anchor g / g + 8, side t4)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int a = g + 8 * i;
+            float lg[kRegMax];
+            const T* pv = s_box + a * (4 * kRegMax) + t4 * kRegMax;
+            float f0[8], f1[8];
+            unpack<T>(*reinterpret_cast<const uint4*>(pv + 8 * hswap), f0);
+            unpack<T>(*reinterpret_cast<const uint4*>(pv + 8 * (hswap ^ 1)), f1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { lg[k] = f0[k]; lg[8 + k] = f1[k]; }
+            const float4* bb4 = reinterpret_cast<const float4*>(bias_b + t4 * kRegMax);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float4 bv = bb4[v ^ (2 * hswap)];
+                lg[4 * v] += bv.x; lg[4 * v + 1] += bv.y; lg[4 * v + 2] += bv.z; lg[4 * v + 3] += bv.w;
+            }
+            if (a >= cur.nval) {
+#pragma unroll
+                for (int k = 0; k < kRegMax; ++k) lg[k] = 0.f;
+            }
+            float dist;
+            side_stats<true>(lg, dist, &s_stat[a * LD + t4 * 5], hswap != 0);
+            s_dist[t4][a] = dist;
+        }
+        __syncwarp();
+        if (lane == 0 && un < total) issue_box(nxt);  // the box slab has been consumed: prefetch the next one behind phases 2 and 3
+        // ---- phase 2: DGQP hidden layer of the warp's own 16-anchor tile; z of anchors g (q0) and g + 8 (q1)
+        float q0, q1;
+        {
+            const uint32_t* S = reinterpret_cast<const uint32_t*>(s_stat) + g * LD + t4;
+            uint32_t a[3][4];
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks) {
+                a[ks][0] = S[8 * ks]; a[ks][1] = S[8 * LD + 8 * ks]; a[ks][2] = S[8 * ks + 4]; a[ks][3] = S[8 * LD + 8 * ks + 4];
+            }
+            const uint2* Wf = reinterpret_cast<const uint2*>(w) + lane;
+            const float2* b1 = reinterpret_cast<const float2*>(w + WL<true>::b1);
+            const float2* w2 = reinterpret_cast<const float2*>(w + WL<true>::w2);
+            float zp[2][2];  // [hidden half][row g / g + 8]: the CTA kernel's two partial sums
+#pragma unroll
+            for (int nh = 0; nh < 2; ++nh) {
+                float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int nt = 4 * nh + j;
+                    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) {
+                        const uint2 bfr = Wf[(nt * 3 + ks) * 32];
+                        mma_tf32(d, a[ks], bfr.x, bfr.y);
+                    }
+                    const float2 bb = b1[4 * nt + t4], ww = w2[4 * nt + t4];
+                    z0 = fmaf(ww.x, fmaxf(d[0] + bb.x, 0.f), z0); z0 = fmaf(ww.y, fmaxf(d[1] + bb.y, 0.f), z0);
+                    z1 = fmaf(ww.x, fmaxf(d[2] + bb.x, 0.f), z1); z1 = fmaf(ww.y, fmaxf(d[3] + bb.y, 0.f), z1);
+                }
+                z0 += __shfl_xor_sync(0xffffffffu, z0, 1); z0 += __shfl_xor_sync(0xffffffffu, z0, 2);
+                z1 += __shfl_xor_sync(0xffffffffu, z1, 1); z1 += __shfl_xor_sync(0xffffffffu, z1, 2);
+                zp[nh][0] = z0; zp[nh][1] = z1;
+            }
+            const float b2 = w[WL<true>::b2];
+            float z = b2; z += zp[0][0] + zp[1][0];
+            q0 = fminf(fmaxf(sigmoidf_<true>(z), 1e-6f), 1.f - 1e-6f);  // clamp(1e-6, 1 - 1e-6), head.py:343
+            z = b2; z += zp[0][1] + zp[1][1];
+            q1 = fminf(fmaxf(sigmoidf_<true>(z), 1e-6f), 1.f - 1e-6f);
+        }
+        mbar_wait(&bar[1], phase);
+        // ---- phase 3: (anchor g / g + 8, class quarter t4)
+        unsigned long long key[2];
+        bool pass[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int a = g + 8 * i, qd = t4;
+            const bool av = a < cur.nval;
+            const float q = i == 0 ? q0 : q1;
+            if (av && qd == 0) {
+                const int pix = cur.pix0 + a, py = pix / L.W, px = pix - py * L.W;
+                E.boxes[(int64_t)cur.b * P.A + L.a_off + pix] = decode_box(px, py, s_dist[0][a], s_dist[1][a], s_dist[2][a], s_dist[3][a], L.stride);
+            }
+            const T* pc = s_cls + a * nc;
+            float best = -INFINITY;
+            int bc = 0;
+            if (nc == 80) {  // COCO-sized head: class maximum on the logits, only logits within 1/64 of it are scored (see gfl_decode_emit_kernel)
+                constexpr int CQ = 20;
+                float xs[CQ];
+                const uint2* pcv = reinterpret_cast<const uint2*>(pc + qd * CQ);
+                const float4* bv4 = reinterpret_cast<const float4*>(bias_c + qd * CQ);
+#pragma unroll
+                for (int v = 0; v < CQ / 4; ++v) {
+                    const uint2 r = pcv[v];
+                    const float4 bb = bv4[v];
+                    unpack2<T>(r.x, xs[4 * v], xs[4 * v + 1]);
+                    unpack2<T>(r.y, xs[4 * v + 2], xs[4 * v + 3]);
+                    xs[4 * v] += bb.x; xs[4 * v + 1] += bb.y; xs[4 * v + 2] += bb.z; xs[4 * v + 3] += bb.w;
+                }
+                float mx = xs[0];
+#pragma unroll
+                for (int j = 1; j < CQ; ++j) mx = fmaxf(mx, xs[j]);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                const float bound = sigmoidf_<true>(mx) * q;
+                if (av && bound * 1.0001f > E.conf) {
+                    const float thr = mx > 8.f ? -INFINITY : mx - 0.015625f;
+#pragma unroll
+                    for (int j = 0; j < CQ; ++j) {
+                        if (xs[j] >= thr) {
+                            const float sc = sigmoidf_<true>(xs[j]) * q;
+                            if (sc > best) { best = sc; bc = qd * CQ + j; }
+                        }
+                    }
+                }
+            } else if (av) {
+                const int c1 = min(nc, (qd + 1) * cq);
+                for (int c = qd * cq; c < c1; ++c) {  // first maximum inside the quarter
+                    const float sc = sigmoidf_<true>(to_f(pc[c]) + bias_c[c]) * q;
+                    if (sc > best) { best = sc; bc = c; }
+                }
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {  // combine the 4 quarters; ties go to the lower class (cls.max(1) first-max rule)
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+            }
+            pass[i] = av && qd == 0 && best > E.conf && (!E.class_keep || E.class_keep[bc]);
+            const uint32_t idx = (uint32_t)(L.a_off + cur.pix0 + a) * (uint32_t)nc + (uint32_t)bc;
+            key[i] = ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)(~idx);
+        }
+        __syncwarp();
+        if (lane == 0 && un < total) issue_cls(nxt);  // the class slab has been consumed
+        {   // one slot reservation per slab; anchors keep their order inside it (any order is fine: the keys are sorted later)
+            const unsigned m0 = __ballot_sync(0xffffffffu, pass[0]), m1 = __ballot_sync(0xffffffffu, pass[1]);
+            const int n0 = __popc(m0), nn = n0 + __popc(m1);
+            if (nn) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(E.counts + cur.b, nn);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                unsigned long long* dst = E.keys + (int64_t)cur.b * E.key_stride + base;
+                const unsigned below = (1u << lane) - 1u;
+                if (pass[0]) dst[__popc(m0 & below)] = key[0];
+                if (pass[1]) dst[n0 + __popc(m1 & below)] = key[1];
+            }
+        }
+        u = un;
+        cur = nxt;
+    }
+}
+
+// can the warp kernel stage this problem?  (emit_supported + 16-byte slab granularity of the class maps)
+static bool warp_emit_supported(const DecodeParams& P) {
+    for (int l = 0; l < P.nl; ++l) {
+        const int rem = (P.lv[l].H * P.lv[l].W) % kSlab;
+        if (rem && ((rem * P.nc * 2) % 16)) return false;
+    }
+    return warp_emit_layout(P.nc, P.nl).total <= 110 * 1024;
+}
+
 static size_t emit_smem_bytes(int nc, size_t esz, int nl) {
     return (esz == 2 ? emit_layout<true>(nc, (uint32_t)esz, nl).total : emit_layout<false>(nc, (uint32_t)esz, nl).total) + 64;
 }
@@ -827,7 +1096,21 @@ extern "C" int el_gfl_detect_fwd(int nl, const void* const* box, const int64_t* 
         const int grid = total < occ * kSMs ? total : occ * kSMs;                                       \
         kern<<<grid, 256, sm, st>>>(P, E);                                                              \
     } while (0)
-    if (do_emit) {
+    static const int use_warp = [] { const char* e = getenv("EL_DECODE_WARP"); return e ? atoi(e) : 1; }();
+    if (do_emit && use_warp && !multi && esz == 2 && warp_emit_supported(P)) {
+        const WarpEmitLayout WLo = warp_emit_layout(nc, nl);
+        const int slabs = total * 4;
+        int grid = (int)ceil_div(slabs, kWarpsPerCta);
+        if (grid > 2 * kSMs) grid = 2 * kSMs;
+        if (dtype == EL_BF16) {
+            cudaFuncSetAttribute(gfl_decode_emit_warp_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WLo.total);
+            gfl_decode_emit_warp_kernel<__nv_bfloat16><<<grid, kWarpsPerCta * 32, WLo.total, st>>>(P, E);
+        } else {
+            cudaFuncSetAttribute(gfl_decode_emit_warp_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WLo.total);
+            gfl_decode_emit_warp_kernel<__half><<<grid, kWarpsPerCta * 32, WLo.total, st>>>(P, E);
+        }
+        note_launches(1);
+    } else if (do_emit) {
         EL_DISPATCH_DTYPE(dtype, {
             if (multi) EL_LAUNCH_EMIT(true);
             else EL_LAUNCH_EMIT(false);
