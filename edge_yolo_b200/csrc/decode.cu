@@ -258,10 +258,21 @@ __device__ __forceinline__ float4 decode_box(int px, int py, float l, float t, f
 template <bool MMA>
 __device__ __forceinline__ void load_level_weights(float* __restrict__ dst, const DecodeLevel& L) {
     if constexpr (MMA) {
-        for (int i = threadIdx.x; i < WL<true>::w1n; i += blockDim.x) {  // i = ((nt * 3 + ks) * 32 + lane) * 2 + j
-            const int j = i & 1, lane = (i >> 1) & 31, f = i >> 6, nt = f / 3, ks = f - 3 * nt;
-            const int k = 8 * ks + (lane & 3) + 4 * j, n = 8 * nt + (lane >> 2);
-            dst[i] = k < kStat ? to_tf32(__ldg(L.w1 + n * kStat + k)) : 0.f;
+        // fragment slot of w1[n][k]: ((nt * 3 + ks) * 32 + lane) * 2 + j with nt = n / 8, ks = k / 8, lane = (n % 8) * 4 + k % 4, j = (k % 8) / 4.
+        // One task = (hidden unit n, four consecutive k): a 16-byte row read (k = 20 .. 23: the zero padding) and four slots two floats apart --
+        // the per-element version (a division and a scalar __ldg per slot) was ~4 % of the fused kernel's instructions and most of the dense kernel's prologue.
+        const bool vec = (reinterpret_cast<uintptr_t>(L.w1) & 15) == 0;
+        for (int task = threadIdx.x; task < kHidden * 6; task += blockDim.x) {
+            const int n = task / 6, q = task - 6 * n;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < 5) {
+                const float* src = L.w1 + n * kStat + 4 * q;
+                if (vec) v = __ldg(reinterpret_cast<const float4*>(src));
+                else v = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+            }
+            const int nt = n >> 3, gq = n & 7, ks = q >> 1, j = q & 1;
+            float* d = dst + ((nt * 3 + ks) * 32 + gq * 4) * 2 + j;
+            d[0] = to_tf32(v.x); d[2] = to_tf32(v.y); d[4] = to_tf32(v.z); d[6] = to_tf32(v.w);
         }
     } else {
         for (int i = threadIdx.x; i < kHidden * kStat; i += blockDim.x) dst[i] = __ldg(L.w1 + i);
