@@ -933,7 +933,7 @@ def test_predictor_shapes(scale, nc, batch, imgsz, kw):
         assert d2.numpy().tobytes() == d.numpy().tobytes()
 
 
-@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
 @pytest.mark.parametrize("nc,sizes,kw", [
     (80, ((80, 80), (40, 40), (20, 20)), dict(conf_thres=0.25, iou_thres=0.7)),
     (80, ((80, 80), (40, 40), (20, 20)), dict(conf_thres=0.6, iou_thres=0.7, multi_label=True)),
