@@ -260,7 +260,9 @@ def test_decode_vs_oracle(dtype, tol, cl, nc, sizes):
     fmt = torch.channels_last if cl else torch.contiguous_format
     y = ops().gfl_decode([b.to(DEV).contiguous(memory_format=fmt) for b in boxes], [c.to(DEV).contiguous(memory_format=fmt) for c in clss],
                          [tuple(t.reshape(-1).contiguous().to(DEV) for t in w) for w in ws], [8.0, 16.0, 32.0])
-    close(y[:, :4], ref[:, :4], max(tol, 1e-5), 1e-3 if dtype == torch.float32 else (0.5 if dtype == torch.bfloat16 else 0.1))
+    # the oracle sees the same 16-bit-rounded maps, so the boxes only carry the kernel's own arithmetic (SFU exp / rcp: ~1e-6 relative):
+    # 0.02 px on coordinates up to 640 (round 1 allowed 0.5 px here)
+    close(y[:, :4], ref[:, :4], 1e-5, 1e-3 if dtype == torch.float32 else 0.02)
     close(y[:, 4:], ref[:, 4:], tol, tol * 1e-2)
 
 
