@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
     __shared__ __align__(1024) unsigned char s_a[128 * 64];      // im2col tile: 128 rows x 32 K, 64-byte swizzle
     __shared__ __align__(1024) unsigned char s_wt[C0 * 64];      // weights: C0 rows x 32 K, same layout
     __shared__ __align__(16) uint32_t s_in[kInRows * kInPitch];  // raw bytes of the input patch
-    __shared__ float s_bias[C0];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -100,12 +99,16 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid < C0) {  // weight row co: K index = (ky*3 + kx)*3 + ci from the caller's (C0, 3, 3, 3) = [co][ci][ky][kx] fp32
-        s_bias[tid] = __ldg(bias + tid);
+        // The accumulator comes out as h = (conv + bias) / 2, the argument of SiLU(x) = h + h * tanh(h): the weights are halved (exact) and
+        // the bias rides in two of the five spare K columns (27, 28: the im2col rows hold 1.0 there) as a 16-bit hi + lo pair (2^-17 relative),
+        // so the epilogue is one MUFU.TANH + one FFMA per channel instead of FADD + FMUL + MUFU + FFMA and reads no bias.
+        const float hb = 0.5f * __ldg(bias + tid);
+        const float hb_hi = to_f(from_f<T>(hb));
         float k32[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
             const int t = k / 3, ci = k - 3 * t;  // t = ky*3 + kx
-            k32[k] = k < 27 ? __ldg(w + tid * 27 + ci * 9 + t) : 0.f;
+            k32[k] = k < 27 ? 0.5f * __ldg(w + tid * 27 + ci * 9 + t) : (k == 27 ? hb_hi : (k == 28 ? hb - hb_hi : 0.f));
         }
         const uint32_t swz = ((uint32_t)tid >> 1) & 3;
 #pragma unroll
@@ -130,10 +133,29 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
 
     // the input patch of tile t+1 is requested (4 words per thread, held in registers) right after tile t's patch has been staged,
     // so its global-memory latency hides behind tile t's im2col build, MMA and epilogue
+    // Tile coordinates (image n, tile row ry, tile column rx) advance by gridDim.x tiles per iteration as a mixed-radix add: the divisions
+    // by the run-time tile counts (t / per_img, r / tiles_x, r % tiles_x, in the prefetch and again in the loop body) were ~100 of the
+    // kernel's 449 instructions per pixel (ncu source page, round 2: I2F.RP / MUFU.RCP / F2I / IABS sequences, issue slots 73 % busy).
+    struct TileC { int n, ry, rx; };
+    const int per_img = tiles_x * tiles_y;
+    TileC cur, step;
+    {
+        const int t0 = blockIdx.x, d = gridDim.x;
+        cur.n = t0 / per_img; const int r0 = t0 - cur.n * per_img; cur.ry = r0 / tiles_x; cur.rx = r0 - cur.ry * tiles_x;
+        step.n = d / per_img; const int rd = d - step.n * per_img; step.ry = rd / tiles_x; step.rx = rd - step.ry * tiles_x;
+    }
+    auto advance = [&](TileC c) {
+        c.rx += step.rx;
+        if (c.rx >= tiles_x) { c.rx -= tiles_x; ++c.ry; }
+        c.ry += step.ry;
+        if (c.ry >= tiles_y) { c.ry -= tiles_y; ++c.n; }
+        c.n += step.n;
+        return c;
+    };
     uint32_t pre[4];
-    auto fetch = [&](int t) {
-        const int per_img = tiles_x * tiles_y, n = t / per_img, r = t - n * per_img;
-        const int oy0 = (r / tiles_x) * kTH, ox0 = (r % tiles_x) * kTW;
+    auto fetch = [&](const TileC& c) {
+        const int n = c.n;
+        const int oy0 = c.ry * kTH, ox0 = c.rx * kTW;
         const uint8_t* img = src + (int64_t)n * H * row_bytes;
         const int iy0 = 2 * oy0 - 1, seg0 = (2 * ox0 - 1) * 3;
         const int w_lo = (seg0 - (seg0 & 3)) >> 2;  // floor(seg0 / 4)
@@ -147,11 +169,12 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
                 pre[k] = __ldg(reinterpret_cast<const uint32_t*>(img + (int64_t)iy * row_bytes + byte0));
         }
     };
-    if ((int)blockIdx.x < total) fetch(blockIdx.x);
+    if ((int)blockIdx.x < total) fetch(cur);
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int per_img = tiles_x * tiles_y, n = t / per_img, r = t - n * per_img;
-        const int oy0 = (r / tiles_x) * kTH, ox0 = (r % tiles_x) * kTW;
+        const int n = cur.n;
+        const int oy0 = cur.ry * kTH, ox0 = cur.rx * kTW;
+        const TileC nxt = advance(cur);
         const int seg0 = (2 * ox0 - 1) * 3;
         // ---- stage the 5 x 387-byte input patch
 #pragma unroll
@@ -160,7 +183,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
             if (i < kInRows * kInWords) s_in[(i / kInWords) * kInPitch + (i % kInWords)] = pre[k];
         }
         __syncthreads();
-        if (t + (int)gridDim.x < total) fetch(t + gridDim.x);
+        if (t + (int)gridDim.x < total) fetch(nxt);
         // ---- im2col row of this thread's pixel: 3 x 9 bytes -> 27 exact 16-bit values (+ 5 zeros)
         {
             const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_in);
@@ -171,8 +194,9 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
 #pragma unroll
                 for (int j = 0; j < 9; ++j) k32[ky * 9 + j] = u8_to_f(p[j]);
             }
+            k32[27] = 1.f; k32[28] = 1.f;  // the bias columns of the weight tile
 #pragma unroll
-            for (int k = 27; k < 32; ++k) k32[k] = 0.f;
+            for (int k = 29; k < 32; ++k) k32[k] = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 o;
@@ -206,7 +230,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
                     float f[V];
 #pragma unroll
                     for (int e = 0; e < V; ++e) {
-                        const float h = 0.5f * (__uint_as_float(v[8 * g + e]) + s_bias[c0 + 8 * g + e]);
+                        const float h = __uint_as_float(v[8 * g + e]);  // (conv + bias) / 2 straight from the accumulator
                         float th;
                         asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
                         f[e] = fmaf(h, th, h);  // SiLU(x) = h + h * tanh(h), h = x / 2
@@ -217,6 +241,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
         }
         tc_fence_before();
         __syncthreads();  // TMEM accumulator, A tile and input patch are reused by the next tile
+        cur = nxt;
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kCols));
 }
