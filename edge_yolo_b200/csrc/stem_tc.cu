@@ -98,24 +98,34 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "n"(kCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (tid < C0) {  // weight row co: K index = (ky*3 + kx)*3 + ci from the caller's (C0, 3, 3, 3) = [co][ci][ky][kx] fp32
-        // The accumulator comes out as h = (conv + bias) / 2, the argument of SiLU(x) = h + h * tanh(h): the weights are halved (exact) and
-        // the bias rides in two of the five spare K columns (27, 28: the im2col rows hold 1.0 there) as a 16-bit hi + lo pair (2^-17 relative),
-        // so the epilogue is one MUFU.TANH + one FFMA per channel instead of FADD + FMUL + MUFU + FFMA and reads no bias.
-        const float hb = 0.5f * __ldg(bias + tid);
-        const float hb_hi = to_f(from_f<T>(hb));
+    if (tid < C0) {
+        // Operand form (round 2): the im2col rows are fp16 values 1024 + v (bit pattern 0x6400 | v: exact, and assembled from the raw bytes by
+        // one PRMT per pair -- no u8 -> float -> 16-bit conversion chain: that chain was ~130 of the kernel's ~290 instructions per pixel), so
+        // both MMA operands are fp16 whatever the activation type T.  K index = 10 * ky + (kx * 3 + ci), slot 10 * ky + 9 is padding (weight
+        // 0), slots 30 / 31 carry the bias: the rows hold 1.0 there and the weight tile holds, as an fp16 hi + lo pair,
+        //     bias' = bias / 2 - 1024 * sum_k W'_k        (W'_k = fp16(W_k / 2): the rounded weights, so the 1024 offsets cancel exactly)
+        // The accumulator is then h = (conv + bias) / 2, the argument of SiLU(x) = h + h * tanh(h): one MUFU.TANH + one FFMA per channel.
         float k32[32];
+        float wsum = 0.f;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const int t = k / 3, ci = k - 3 * t;  // t = ky*3 + kx
-            k32[k] = k < 27 ? 0.5f * __ldg(w + tid * 27 + ci * 9 + t) : (k == 27 ? hb_hi : (k == 28 ? hb - hb_hi : 0.f));
+        for (int k = 0; k < 30; ++k) {
+            const int ky = k / 10, j = k - 10 * ky, kx = j / 3, ci = j - 3 * kx;
+            float v = 0.f;
+            if (j < 9) {
+                v = __half2float(__float2half_rn(0.5f * __ldg(w + tid * 27 + ci * 9 + ky * 3 + kx)));
+                wsum += v;
+            }
+            k32[k] = v;
         }
+        const float hb = 0.5f * __ldg(bias + tid) - 1024.f * wsum;
+        k32[30] = __half2float(__float2half_rn(hb));
+        k32[31] = hb - k32[30];
         const uint32_t swz = ((uint32_t)tid >> 1) & 3;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint4 o;
-            o.x = pack2f<T>(k32[8 * j], k32[8 * j + 1]); o.y = pack2f<T>(k32[8 * j + 2], k32[8 * j + 3]);
-            o.z = pack2f<T>(k32[8 * j + 4], k32[8 * j + 5]); o.w = pack2f<T>(k32[8 * j + 6], k32[8 * j + 7]);
+            o.x = pack2f<__half>(k32[8 * j], k32[8 * j + 1]); o.y = pack2f<__half>(k32[8 * j + 2], k32[8 * j + 3]);
+            o.z = pack2f<__half>(k32[8 * j + 4], k32[8 * j + 5]); o.w = pack2f<__half>(k32[8 * j + 6], k32[8 * j + 7]);
             *reinterpret_cast<uint4*>(s_wt + tid * 64 + ((j ^ swz) << 4)) = o;
         }
     }
@@ -125,7 +135,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t idesc = umma_idesc(kFmt, 128, C0);
+    const uint32_t idesc = umma_idesc(0, 128, C0);  // A and B are fp16 (see the weight prologue), D fp32
     const int py = tid >> 6, px = tid & 63;        // this thread's pixel inside the 64 x 2 patch = GEMM row tid
     const uint32_t a_swz = ((uint32_t)tid >> 1) & 3;
     const int row_bytes = W * 3;
@@ -184,26 +194,27 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const uint8_t* __restrict_
         }
         __syncthreads();
         if (t + (int)gridDim.x < total) fetch(nxt);
-        // ---- im2col row of this thread's pixel: 3 x 9 bytes -> 27 exact 16-bit values (+ 5 zeros)
+        // ---- im2col row of this thread's pixel: 3 x 9 bytes -> fp16 pairs (0x6400 | byte): per image row three aligned words, two funnel
+        //      shifts to the byte the pixel starts at, five PRMTs
         {
-            const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_in);
-            float k32[32];
+            uint32_t pr[16];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-                const uint8_t* p = sb + (2 * py + ky) * (kInPitch * 4) + (seg0 & 3) + 6 * px;
-#pragma unroll
-                for (int j = 0; j < 9; ++j) k32[ky * 9 + j] = u8_to_f(p[j]);
+                const uint32_t boff = (uint32_t)((2 * py + ky) * (kInPitch * 4) + (seg0 & 3) + 6 * px);
+                const uint32_t* pw = s_in + (boff >> 2);
+                const uint32_t sh = (boff & 3) * 8;
+                const uint32_t w0 = pw[0], w1 = pw[1], w2 = pw[2];
+                const uint32_t r0 = __funnelshift_r(w0, w1, sh), r1 = __funnelshift_r(w1, w2, sh), r2 = w2 >> sh;  // bytes 0-3, 4-7, 8
+                pr[5 * ky + 0] = __byte_perm(r0, 0x64646464u, 0x4140);
+                pr[5 * ky + 1] = __byte_perm(r0, 0x64646464u, 0x4342);
+                pr[5 * ky + 2] = __byte_perm(r1, 0x64646464u, 0x4140);
+                pr[5 * ky + 3] = __byte_perm(r1, 0x64646464u, 0x4342);
+                pr[5 * ky + 4] = __byte_perm(r2, 0x64646464u, 0x4440);  // (byte 8, padding slot: weight 0)
             }
-            k32[27] = 1.f; k32[28] = 1.f;  // the bias columns of the weight tile
+            pr[15] = 0x3C003C00u;  // 1.0, 1.0: the two bias columns
 #pragma unroll
-            for (int k = 29; k < 32; ++k) k32[k] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                o.x = pack2f<T>(k32[8 * j], k32[8 * j + 1]); o.y = pack2f<T>(k32[8 * j + 2], k32[8 * j + 3]);
-                o.z = pack2f<T>(k32[8 * j + 4], k32[8 * j + 5]); o.w = pack2f<T>(k32[8 * j + 6], k32[8 * j + 7]);
-                *reinterpret_cast<uint4*>(s_a + tid * 64 + ((j ^ a_swz) << 4)) = o;
-            }
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(s_a + tid * 64 + ((j ^ a_swz) << 4)) = make_uint4(pr[4 * j], pr[4 * j + 1], pr[4 * j + 2], pr[4 * j + 3]);
         }
         proxy_fence();  // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
         __syncthreads();
