@@ -309,6 +309,7 @@ def profile_kernels(pred, a, iters=10):
         "dwconv": lambda _o, x, *r, **k: 2 * x.numel() * e(x),
         "conv3x3": lambda _o, x, wpk, N, **k: (x.numel() + _o.numel()) * e(x),
         "conv3x3_halo": lambda _o, x, wpk, N, **k: (x.numel() + _o.numel()) * e(x),
+        "conv3x3_mma": lambda _o, x, w, **k: (x.numel() + _o.numel()) * e(x),
         "upsample2x_cat": lambda _o, x, skip: (x.numel() + skip.numel() + _o.numel()) * e(x),
         "sppf_pool": lambda _o, x: 5 * x.numel() * e(x),
         "nms_batched": lambda out, y, *r, **k: y.shape[0] * y.shape[2] * (y.shape[1] - 4) * 4 + out[0].numel() * 4,
@@ -437,7 +438,7 @@ def step_traffic(kernel):
     default workload (profiles/r*_step_b64_time_dram.json: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`
     over `bench.py --profile-step`).  ncu cannot run inside the timed program, so this is labelled with its source file."""
     names = {"pwconv": ["pw::pwconv_tc_kernel"], "dwconv": ["el::dwconv_tile_kernel", "dwtc::dwconv_tc_kernel", "dwt::dwconv3_tma_kernel"],
-             "bias_act": ["el::bias_act_tiled", "el::bias_act_flat"], "conv3x3_halo": ["c3::conv3x3_halo_kernel"], "linear_attention": ["ta::linattn_tma_kernel"],
+             "bias_act": ["el::bias_act_tiled", "el::bias_act_flat"], "conv3x3_halo": ["c3::conv3x3_halo_kernel"], "conv3x3_mma": ["c3m::conv3x3_mma_kernel"], "linear_attention": ["ta::linattn_tma_kernel"],
              "stem_conv_u8": ["stemtc::stem_tc_kernel"], "wave_merge_bands": ["el::merge_fwd_x2"], "dwt_haar": ["el::dwt_fwd_tiled"],
              "gfl_decode_emit": ["el::gfl_decode_emit_kernel"], "nms_sweep": ["el::nms_sweep"], "upsample2x_cat": ["el::upsample2x_cat_tiled"]}
     import glob
