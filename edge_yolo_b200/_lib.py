@@ -57,8 +57,8 @@ _SIGNATURES = {
     "el_dfl_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "el_dfl_side_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "el_dfl_side_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
-    "el_conv3x3_mma_ok": (c_int, [c_int, c_int]),
-    "el_conv3x3_mma_fwd": (c_int, [c_void_p, I64P, c_int, c_void_p, c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "el_conv3x3_mma_ok": (c_int, [c_int, c_int, c_int]),
+    "el_conv3x3_mma_fwd": (c_int, [c_void_p, I64P, c_int, c_void_p, c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_box_iou": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_float, c_void_p]),
     "el_ap_per_class_workspace_bytes": (c_int, [c_int64, c_int, c_int, POINTER(c_size_t)]),
     "el_ap_per_class": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p, c_size_t, c_void_p, c_void_p,

@@ -1,5 +1,5 @@
-// Dense 3 x 3 convolution (stride 1, padding 1) with NARROW channel counts (C_in = 16 / 32, N <= 32) for the inference engine:
-//     out[b, y, x, n] = act( sum_{ky,kx,c} X[b, y+ky-1, x+kx-1, c] * W[n, c, ky, kx] + bias[n] )                NHWC 16-bit activations
+// Dense 3 x 3 convolution (stride 1 / 2, padding 1) with NARROW channel counts (C_in = 16 / 32, N <= 64) for the inference engine:
+//     out[b, y, x, n] = act( sum_{ky,kx,c} X[b, s*y+ky-1, s*x+kx-1, c] * W[n, c, ky, kx] + bias[n] )            NHWC 16-bit activations
 // These are the shared high-band convs f_h of _WaveletEnhancer (nn/modules/block.py:3668-3673: Conv(c, c/2, 3)) at the early, large maps:
 // 16 -> 8 on three stacked 80 x 80 bands and 32 -> 16 on 40 x 40 for EdgeLine-n (a 3B-image batch each, `Conv.forward_fuse`
 // nn/modules/conv.py:58-60).  el_conv3x3_fwd runs them as tcgen05 implicit GEMMs with nine tap-shifted TMA boxes per 128-pixel tile; with
@@ -11,7 +11,9 @@
 //   * a warp owns two output rows (two m16 tiles of 16 pixels); per (tap, 16-channel chunk) ONE ldmatrix.x4 -- the A fragment of tap
 //     (ky, kx) is the same staged tile addressed at pixel (y + ky, x + kx) -- and one mma.sync.m16n8k16 per 8 output channels, weights as
 //     B fragments in shared memory (built once per CTA from the plain fp32 (N, C, 3, 3) weight: no host packing);
-//   * epilogue in registers: bias, SiLU / ReLU, 16-bit pack, 4-byte stores (a warp store = 8 pixels x 16 contiguous bytes).
+//   * epilogue in registers: bias, SiLU / ReLU, 16-bit pack, 4-byte stores (a warp store = 8 pixels x 16 contiguous bytes);
+//   * stride 2 (layer 1 of the yaml, Conv(16, 32, 3, 2) on the 320 x 320 stem output): every ldmatrix row has its own address, so the
+//     16 pixels of an m-tile simply sit two staged pixels apart; the staged tile is 33 x 33.
 #include <type_traits>
 
 #include "el_common.cuh"
@@ -20,16 +22,15 @@ namespace el {
 namespace c3m {
 
 constexpr int kTile = 16;            // output tile edge
-constexpr int kHalo = kTile + 2;     // staged tile edge
 constexpr int kThreads = 256;
-constexpr int kMaxN = 32, kMaxC = 32;
+constexpr int kMaxN = 64, kMaxC = 32;
 
 struct Args {
     const void* x; int64_t xn, xh, xw;      // element strides; channels contiguous
     void* out; int64_t on, oh, ow;
     const float* w;                          // (N, C, 3, 3) fp32
     const float* bias;                       // (N) or null
-    int B, H, W, C, N, act, tiles_x, tiles_y;
+    int B, H, W, Ho, Wo, C, N, act, tiles_x, tiles_y;   // H, W: input; Ho, Wo: output
     int64_t n_tiles;
 };
 
@@ -71,9 +72,10 @@ __device__ __forceinline__ float silu_fast(float v) {  // x * sigmoid(x) = h + h
 }
 
 // KC = C / 16 K chunks per tap, NT = N / 8 output-channel tiles
-template <typename T, int KC, int NT>
+template <typename T, int KC, int NT, int S>
 __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_constant__ Args A) {
     constexpr int C = 16 * KC, N = 8 * NT;
+    constexpr int kHalo = (kTile - 1) * S + 3;                    // staged tile edge: 18 (stride 1) / 33 (stride 2)
     constexpr uint32_t kPitch = C * 2 + 16;                       // bytes per staged pixel
     constexpr uint32_t kStage = kHalo * kHalo * kPitch;           // bytes per staged tile
     constexpr int kCpp = C / 8;                                   // 16-byte chunks per pixel
@@ -86,12 +88,32 @@ __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     pdl_launch_dependents();
-    // ---- B fragments of mma.m16n8k16 (k16 x n8, "col"): lane (g = lane / 4, t = lane % 4) holds k = 2t, 2t+1, 2t+8, 2t+9 of column n = g
-    for (int i = tid; i < 9 * KC * NT * 32 * 4; i += kThreads) {
-        const int e = i & 3, ln = (i >> 2) & 31, f = i >> 7;     // f = (tap * KC + kc) * NT + nt
-        const int nt = f % NT, kc = (f / NT) % KC, tap = f / (NT * KC);
-        const int k = 2 * (ln & 3) + (e & 1) + 8 * (e >> 1), n = 8 * nt + (ln >> 2), c = 16 * kc + k;
-        s_wf[i] = from_f<T>(__ldg(A.w + ((int64_t)n * C + c) * 9 + tap));
+    // ---- B fragments of mma.m16n8k16 (k16 x n8, "col"): lane (g = lane / 4, t = lane % 4) holds k = 2t, 2t+1, 2t+8, 2t+9 of column n = g.
+    //      The plain (N, C, 3, 3) weight is read with coalesced, independent 16-byte loads (all of a thread's loads in flight at once) and
+    //      every element scattered to its slot: a per-slot gather (index arithmetic + one dependent scalar load per element, 18 rounds at
+    //      C = 32, N = 16) put ~5 us of pure latency in front of every launch.
+    {
+        constexpr int kW4 = N * C * 9 / 4;                       // float4s of the weight (N * C * 9 is a multiple of 4: C % 16 == 0)
+        constexpr int kPer = (kW4 + kThreads - 1) / kThreads;
+        float4 wv[kPer];
+#pragma unroll
+        for (int r = 0; r < kPer; ++r) {
+            const int q = tid + r * kThreads;
+            wv[r] = q < kW4 ? __ldg(reinterpret_cast<const float4*>(A.w) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < kPer; ++r) {
+            const int q = tid + r * kThreads;
+            if (q < kW4) {
+                const float v4[4] = {wv[r].x, wv[r].y, wv[r].z, wv[r].w};
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                    const int idx = 4 * q + e4, tap = idx % 9, nc = idx / 9, c = nc % C, n = nc / C;   // element W[n][c][tap]
+                    const int k = c & 15, kc = c >> 4, nt = n >> 3, ln = 4 * (n & 7) + ((k & 7) >> 1), e = (k & 1) + 2 * (k >> 3);
+                    s_wf[((((tap * KC + kc) * NT + nt) * 32 + ln) << 2) + e] = from_f<T>(v4[e4]);
+                }
+            }
+        }
     }
     for (int i = tid; i < N; i += kThreads) s_bias[i] = A.bias ? __ldg(A.bias + i) : 0.f;
     pdl_wait();  // the producer of x has completed from here on
@@ -101,7 +123,7 @@ __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_cons
     const int per_img = A.tiles_x * A.tiles_y;
     auto stage_tile = [&](int64_t tile, int buf) {
         const int img = (int)(tile / per_img), r = (int)(tile - (int64_t)img * per_img);
-        const int y0 = (r / A.tiles_x) * kTile - 1, x0 = (r % A.tiles_x) * kTile - 1;
+        const int y0 = (r / A.tiles_x) * kTile * S - 1, x0 = (r % A.tiles_x) * kTile * S - 1;
         const T* base = xp + (int64_t)img * A.xn;
         const uint32_t dst0 = tiles + (uint32_t)buf * kStage;
         for (int i = tid; i < kChunks; i += kThreads) {
@@ -116,8 +138,17 @@ __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_cons
     const int64_t first = blockIdx.x, stride = gridDim.x;
     if (first < A.n_tiles) stage_tile(first, 0); else cp_async_commit();
     // per-lane ldmatrix row: matrix (lane >> 3) = [pixels 0-7 | 8-15] x [k 0-7 | 8-15], row (lane & 7)
-    const uint32_t a_lane = (uint32_t)((lane & 7) + 8 * ((lane >> 3) & 1)) * kPitch + (uint32_t)(lane >> 4) * 16;
+    const uint32_t a_lane = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * S) * kPitch + (uint32_t)(lane >> 4) * 16;
     const int g = lane >> 2, t4 = lane & 3;
+    // up to 36 B fragments (72 registers) stay in registers for the whole kernel: one LDS.64 per MMA otherwise
+    constexpr int kFrags = 9 * KC * NT;
+    constexpr bool kRegB = kFrags <= 36;
+    uint2 bfr[kRegB ? kFrags : 1];
+    if constexpr (kRegB) {
+        __syncthreads();  // the fragments written by the whole CTA above
+#pragma unroll
+        for (int f = 0; f < kFrags; ++f) bfr[f] = *reinterpret_cast<const uint2*>(s_wf + (f * 32 + lane) * 4);
+    }
     int it = 0;
     for (int64_t tile = first; tile < A.n_tiles; tile += stride, ++it) {
         const int buf = it & 1;
@@ -135,26 +166,28 @@ __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_cons
             for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                const uint32_t arow = tbase + (uint32_t)((ly + tap / 3) * kHalo + tap % 3) * kPitch;
+                const uint32_t arow = tbase + (uint32_t)((ly * S + tap / 3) * kHalo + tap % 3) * kPitch;
 #pragma unroll
                 for (int kc = 0; kc < KC; ++kc) {
                     uint32_t a[4];
                     ldmatrix_x4(arow + kc * 32, a);
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
-                        const uint2 bf = *reinterpret_cast<const uint2*>(s_wf + (((tap * KC + kc) * NT + nt) * 32 + lane) * 4);
+                        uint2 bf;
+                        if constexpr (kRegB) bf = bfr[(tap * KC + kc) * NT + nt];
+                        else bf = *reinterpret_cast<const uint2*>(s_wf + (((tap * KC + kc) * NT + nt) * 32 + lane) * 4);
                         mma16816<T>(acc[nt], a, bf.x, bf.y);
                     }
                 }
             }
             // ---- epilogue: d0,d1 = (pixel g, channels 2t, 2t+1), d2,d3 = (pixel g + 8, same channels)
             const int y = y0 + ly;
-            if (y < A.H) {
+            if (y < A.Ho) {
                 T* orow = outp + (int64_t)img * A.on + (int64_t)y * A.oh;
 #pragma unroll
                 for (int hx = 0; hx < 2; ++hx) {
                     const int x = x0 + g + 8 * hx;
-                    if (x < A.W) {
+                    if (x < A.Wo) {
                         T* o = orow + (int64_t)x * A.ow + 2 * t4;
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt) {
@@ -172,16 +205,16 @@ __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_cons
     cp_async_wait<0>();
 }
 
-template <typename T, int KC, int NT>
+template <typename T, int KC, int NT, int S>
 static cudaError_t launch(const Args& A, cudaStream_t st) {
-    constexpr int C = 16 * KC, N = 8 * NT;
+    constexpr int C = 16 * KC, N = 8 * NT, kHalo = (kTile - 1) * S + 3;
     const size_t smem = (size_t)9 * KC * NT * 32 * 4 * 2 + ((N * 4 + 15) & ~15) + 2 * (size_t)kHalo * kHalo * (C * 2 + 16);
-    auto kern = conv3x3_mma_kernel<T, KC, NT>;
+    auto kern = conv3x3_mma_kernel<T, KC, NT, S>;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    int64_t grid = (int64_t)kSMs * 4;
+    int64_t grid = (int64_t)kSMs * (smem > 100 * 1024 ? 2 : 4);
     if (grid > A.n_tiles) grid = A.n_tiles;
     return launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem, st, A);
 }
@@ -191,13 +224,15 @@ static cudaError_t launch(const Args& A, cudaStream_t st) {
 
 using namespace el;
 
-extern "C" int el_conv3x3_mma_ok(int C, int N) { return (C == 16 || C == 32) && N > 0 && N % 8 == 0 && N <= c3m::kMaxN; }
+extern "C" int el_conv3x3_mma_ok(int C, int N, int stride) {
+    return (C == 16 || C == 32) && N > 0 && N % 8 == 0 && N <= c3m::kMaxN && (stride == 1 || stride == 2);
+}
 
 extern "C" int el_conv3x3_mma_fwd(const void* x, const int64_t xs_[4], int C, const float* w, const float* bias, void* out, const int64_t os_[4], int B,
-                                  int H, int W, int N, int act, int dtype, void* stream) {
+                                  int H, int W, int N, int stride, int act, int dtype, void* stream) {
     if (!x || !xs_ || !w || !out || !os_ || B <= 0 || C <= 0 || H <= 0 || W <= 0 || N <= 0 || act < 0 || act > 2) return EL_ERR_ARG;
     if (dtype != EL_BF16 && dtype != EL_F16) return EL_ERR_UNSUPPORTED;
-    if (!el_conv3x3_mma_ok(C, N) || xs_[1] != 1 || os_[1] != 1 || !aligned16(x) || ((uintptr_t)out & 3)) return EL_ERR_UNSUPPORTED;
+    if (!el_conv3x3_mma_ok(C, N, stride) || xs_[1] != 1 || os_[1] != 1 || !aligned16(x) || !aligned16(w) || ((uintptr_t)out & 3)) return EL_ERR_UNSUPPORTED;
     for (int i = 0; i < 4; ++i) {
         if (i != 1 && xs_[i] % 8) return EL_ERR_UNSUPPORTED;   // 16-byte cp.async sources
         if (i != 1 && os_[i] % 2) return EL_ERR_UNSUPPORTED;   // 4-byte stores
@@ -207,20 +242,27 @@ extern "C" int el_conv3x3_mma_fwd(const void* x, const int64_t xs_[4], int C, co
     A.out = out; A.on = os_[0]; A.oh = os_[2]; A.ow = os_[3];
     A.w = w; A.bias = bias;
     A.B = B; A.H = H; A.W = W; A.C = C; A.N = N; A.act = act;
-    A.tiles_x = (int)ceil_div(W, c3m::kTile); A.tiles_y = (int)ceil_div(H, c3m::kTile);
+    A.Ho = (H - 1) / stride + 1; A.Wo = (W - 1) / stride + 1;   // (H + 2 - 3) / s + 1
+    A.tiles_x = (int)ceil_div(A.Wo, c3m::kTile); A.tiles_y = (int)ceil_div(A.Ho, c3m::kTile);
     A.n_tiles = (int64_t)B * A.tiles_x * A.tiles_y;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
-#define EL_C3M(TT)                                                                                               \
-    do {                                                                                                         \
-        const int kc = C / 16, nt = N / 8;                                                                       \
-        if (kc == 1) { if (nt == 1) e = c3m::launch<TT, 1, 1>(A, st); else if (nt == 2) e = c3m::launch<TT, 1, 2>(A, st); \
-                       else if (nt == 3) e = c3m::launch<TT, 1, 3>(A, st); else e = c3m::launch<TT, 1, 4>(A, st); } \
-        else { if (nt == 1) e = c3m::launch<TT, 2, 1>(A, st); else if (nt == 2) e = c3m::launch<TT, 2, 2>(A, st);        \
-               else if (nt == 3) e = c3m::launch<TT, 2, 3>(A, st); else e = c3m::launch<TT, 2, 4>(A, st); }              \
+    const int kc = C / 16, nt = N / 8;
+#define EL_C3M_NT(TT, KK, SS)                                                                                                   \
+    switch (nt) {                                                                                                               \
+        case 1: e = c3m::launch<TT, KK, 1, SS>(A, st); break; case 2: e = c3m::launch<TT, KK, 2, SS>(A, st); break;             \
+        case 3: e = c3m::launch<TT, KK, 3, SS>(A, st); break; case 4: e = c3m::launch<TT, KK, 4, SS>(A, st); break;             \
+        case 5: e = c3m::launch<TT, KK, 5, SS>(A, st); break; case 6: e = c3m::launch<TT, KK, 6, SS>(A, st); break;             \
+        case 7: e = c3m::launch<TT, KK, 7, SS>(A, st); break; default: e = c3m::launch<TT, KK, 8, SS>(A, st); break;            \
+    }
+#define EL_C3M(TT)                                                                  \
+    do {                                                                            \
+        if (kc == 1) { if (stride == 1) { EL_C3M_NT(TT, 1, 1) } else { EL_C3M_NT(TT, 1, 2) } } \
+        else { if (stride == 1) { EL_C3M_NT(TT, 2, 1) } else { EL_C3M_NT(TT, 2, 2) } }         \
     } while (0)
     if (dtype == EL_BF16) EL_C3M(__nv_bfloat16); else EL_C3M(__half);
 #undef EL_C3M
+#undef EL_C3M_NT
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return EL_ERR_CUDA; }
     note_launches(1);
     return check_launch();

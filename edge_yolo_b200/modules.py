@@ -279,15 +279,17 @@ def _conv3_ok(conv: nn.Conv2d, x: torch.Tensor, out=None) -> bool:
     return 0 < n_tiles <= 3
 
 
-USE_CONV3X3_MMA = True  # el_conv3x3_mma_fwd for the narrow (C_in 16 / 32, N <= 32) stride-1 dense 3x3 convs (f_h on the early maps)
+USE_CONV3X3_MMA = True  # el_conv3x3_mma_fwd for the narrow (C_in 16 / 32, N <= 64) dense 3x3 convs, stride 1 / 2 (f_h on the early maps, layer 1)
 
 
 def _conv3_mma_ok(conv: nn.Conv2d, x: torch.Tensor, out=None) -> bool:
-    """el_conv3x3_mma_fwd applies: dense 3x3, padding 1, stride 1, 16-bit NHWC, C_in 16 / 32, N <= 32."""
-    if not (USE_CONV3X3_MMA and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1) and conv.dilation == (1, 1)
+    """el_conv3x3_mma_fwd applies: dense 3x3, padding 1, stride 1 / 2, 16-bit NHWC, C_in 16 / 32, N <= 64."""
+    if not (USE_CONV3X3_MMA and conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride in ((1, 1), (2, 2)) and conv.dilation == (1, 1)
             and conv.groups == 1 and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and not torch.is_grad_enabled()):
         return False
-    if not ops.conv3x3_mma_ok(x.shape[1], conv.out_channels) or x.stride(1) != 1 or any(s % 8 for i, s in enumerate(x.stride()) if i != 1) or x.data_ptr() % 16:
+    if conv.stride != (1, 1):  # measured (B = 64, 16 -> 32 stride 2 at 320 x 320): 117 us against 89 us on el_conv3x3_fwd -- layer 1 stays there
+        return False
+    if not ops.conv3x3_mma_ok(x.shape[1], conv.out_channels, conv.stride[0]) or x.stride(1) != 1 or any(s % 8 for i, s in enumerate(x.stride()) if i != 1) or x.data_ptr() % 16:
         return False
     if out is not None and (out.stride(1) != 1 or any(s % 2 for i, s in enumerate(out.stride()) if i != 1) or out.data_ptr() % 4):
         return False
@@ -382,7 +384,7 @@ def conv_engine_forward(self, x, out=None, residual=None, out2=None):
         w32 = self.conv.__dict__.get("el_w32")
         if w32 is None or w32[0] != (_ver(self.conv.weight), self.conv.weight.data_ptr(), x.device):
             w32 = self.conv.el_w32 = ((_ver(self.conv.weight), self.conv.weight.data_ptr(), x.device), self.conv.weight.detach().float().contiguous().to(x.device))
-        return ops.conv3x3_mma(x, w32[1], bias=_bias_on(self, x), act=self.el_act, out=out)
+        return ops.conv3x3_mma(x, w32[1], bias=_bias_on(self, x), act=self.el_act, stride=self.conv.stride[0], out=out)
     if residual is None and out2 is None and _conv3_ok(self.conv, x, out):
         cache = self.conv.__dict__.setdefault("el_wpk", {})
         B, C, H, W = x.shape

@@ -805,13 +805,14 @@ def conv3x3(x: torch.Tensor, wpk: torch.Tensor, N: int, bias: torch.Tensor | Non
     return out
 
 
-def conv3x3_mma_ok(C: int, N: int) -> bool:
-    """el_conv3x3_mma_fwd covers this (C_in, N) site (C_in 16 / 32, N a multiple of 8 up to 32)."""
-    return bool(_lib.lib().el_conv3x3_mma_ok(int(C), int(N)))
+def conv3x3_mma_ok(C: int, N: int, stride: int = 1) -> bool:
+    """el_conv3x3_mma_fwd covers this site (C_in 16 / 32, N a multiple of 8 up to 64, stride 1 / 2)."""
+    return bool(_lib.lib().el_conv3x3_mma_ok(int(C), int(N), int(stride)))
 
 
-def conv3x3_mma(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, act: int = ACT_NONE, out: torch.Tensor | None = None) -> torch.Tensor:
-    """Dense 3x3 conv (padding 1, stride 1) + bias + activation for narrow channel counts: `weight` is the plain fp32 (N, C, 3, 3) tensor
+def conv3x3_mma(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, act: int = ACT_NONE, stride: int = 1,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """Dense 3x3 conv (padding 1, stride 1 / 2) + bias + activation for narrow channel counts: `weight` is the plain fp32 (N, C, 3, 3) tensor
     (contiguous, on the device); NHWC 16-bit activations; mma.sync from one haloed shared-memory tile (csrc/conv3x3_mma.cu)."""
     _need_cuda(x, weight)
     B, C, H, W = x.shape
@@ -821,9 +822,9 @@ def conv3x3_mma(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise EdgelineError("conv3x3_mma: bias must be a contiguous fp32 vector of N elements")
     if out is None:
-        out = torch.empty((B, N, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        out = torch.empty((B, N, (H - 1) // stride + 1, (W - 1) // stride + 1), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
     check(_lib.lib().el_conv3x3_mma_fwd(x.data_ptr(), _i64(x.stride()), C, weight.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
-                                        _i64(out.stride()), B, H, W, N, int(act), _dt(x), _stream()), "el_conv3x3_mma_fwd")
+                                        _i64(out.stride()), B, H, W, N, int(stride), int(act), _dt(x), _stream()), "el_conv3x3_mma_fwd")
     return out
 
 

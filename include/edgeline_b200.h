@@ -248,15 +248,16 @@ int el_conv3x3_fwd(const void* x, const int64_t xs[4], int C, const void* wpk, c
 int el_conv3x3_halo_ok(int C, int N);
 int el_conv3x3_halo_fwd(const void* x, const int64_t xs[4], int C, const void* wpk, const float* bias, void* out,
                         const int64_t os[4], int B, int H, int W, int N, int act, int dtype, void* stream);
-/* el_conv3x3_mma_fwd: dense 3 x 3 convolution (stride 1, padding 1) + bias + activation for NARROW channel counts (C_in = 16 / 32,
- * N a multiple of 8 up to 32; el_conv3x3_mma_ok): the shared high-band conv f_h of _WaveletEnhancer (nn/modules/block.py:3668-3673,
- * `Conv.forward_fuse` nn/modules/conv.py:58-60) on the large early maps.  One haloed 18 x 18 tile per 16 x 16 output pixels staged by
+/* el_conv3x3_mma_fwd: dense 3 x 3 convolution (stride 1 / 2, padding 1) + bias + activation for NARROW channel counts (C_in = 16 / 32,
+ * N a multiple of 8 up to 64; el_conv3x3_mma_ok): the shared high-band conv f_h of _WaveletEnhancer (nn/modules/block.py:3668-3673,
+ * `Conv.forward_fuse` nn/modules/conv.py:58-60) on the large early maps and the stride-2 layer 1 of the yaml (cfg/models/11/yolo11-test.yaml:22).
+ * One haloed 18 x 18 (stride 2: 33 x 33) tile per 16 x 16 output pixels staged by
  * cp.async, mma.sync.m16n8k16 from ldmatrix fragments of that tile.  x / out NHWC 16-bit views (channels contiguous, x strides in 8s,
  * out strides even); w is the plain fp32 (N, C, 3, 3) weight (fragments are built in the kernel), bias fp32 (N) or NULL;
  * act as el_bias_act_fwd. */
-int el_conv3x3_mma_ok(int C, int N);
+int el_conv3x3_mma_ok(int C, int N, int stride);
 int el_conv3x3_mma_fwd(const void* x, const int64_t xs[4], int C, const float* w, const float* bias, void* out, const int64_t os[4], int B,
-                       int H, int W, int N, int act, int dtype, void* stream);
+                       int H, int W, int N, int stride, int act, int dtype, void* stream);
 /* el_sppf_pool_fwd: out (B,4C,H,W) = cat[x, m(x), m(m(x)), m(m(m(x)))], m = MaxPool2d(5,1,2): the pooling
  * pyramid of SPPF (nn/modules/block.py:204-223) as separable 5/9/13 window maxima in shared memory.
  * NHWC views, H*W*64 B of shared memory (maps up to ~56x56), else EL_ERR_UNSUPPORTED. */

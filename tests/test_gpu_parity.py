@@ -736,9 +736,10 @@ def test_conv3x3(dtype, C, N, hw, stride, act):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("stride", [1, 2])
 @pytest.mark.parametrize("B,C,N,hw,act", [(3, 16, 8, (80, 80), 1), (3, 32, 16, (40, 40), 1), (2, 16, 8, (37, 29), 0), (1, 32, 32, (16, 16), 2), (2, 16, 24, (5, 3), 1),
-                                          (1, 32, 8, (33, 17), 1), (5, 16, 16, (18, 50), 1)])
-def test_conv3x3_mma(dtype, B, C, N, hw, act):
+                                          (1, 32, 8, (33, 17), 1), (5, 16, 16, (18, 50), 1), (2, 16, 32, (96, 64), 1), (1, 32, 64, (34, 70), 1)])
+def test_conv3x3_mma(dtype, B, C, N, hw, act, stride):
     """Narrow dense 3x3 conv (stride 1, padding 1; el_conv3x3_mma_fwd: haloed cp.async tile, ldmatrix + mma.sync) == Conv.forward_fuse
     (nn/modules/conv.py:58-60) on the same 16-bit-rounded operands: image borders (zero fill), ragged 16 x 16 tiles, one / two K chunks,
     one to four output-channel tiles, the three activations, several tiles per persistent CTA (double buffer), a channel-slice destination."""
@@ -748,16 +749,16 @@ def test_conv3x3_mma(dtype, B, C, N, hw, act):
     w = (torch.randn(N, C, 3, 3, generator=gen) * (9 * C) ** -0.5).to(DEV)
     w_r = w.to(dtype).float()  # the kernel rounds the weights to the activation type
     bias = torch.randn(N, generator=gen).to(DEV)
-    assert o.conv3x3_mma_ok(C, N)
+    assert o.conv3x3_mma_ok(C, N, stride)
     fin = lambda t: torch.nn.functional.silu(t) if act == 1 else (t.relu() if act == 2 else t)
-    want = fin(torch.nn.functional.conv2d(x.float(), w_r, bias, stride=1, padding=1))
-    got = o.conv3x3_mma(x, w, bias=bias, act=act)
+    want = fin(torch.nn.functional.conv2d(x.float(), w_r, bias, stride=stride, padding=1))
+    got = o.conv3x3_mma(x, w, bias=bias, act=act, stride=stride)
     assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
     close(got, want, 2e-2, 2e-2)
-    buf = torch.full((B, N + 16, *hw), 7.0, device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
+    buf = torch.full((B, N + 16, *want.shape[2:]), 7.0, device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
     x2 = torch.flip(x, dims=[0, 3])
-    o.conv3x3_mma(x2, w, bias=None, act=act, out=buf[:, 8 : 8 + N])
-    close(buf[:, 8 : 8 + N], fin(torch.nn.functional.conv2d(x2.float(), w_r, None, stride=1, padding=1)), 2e-2, 2e-2)
+    o.conv3x3_mma(x2, w, bias=None, act=act, stride=stride, out=buf[:, 8 : 8 + N])
+    close(buf[:, 8 : 8 + N], fin(torch.nn.functional.conv2d(x2.float(), w_r, None, stride=stride, padding=1)), 2e-2, 2e-2)
     assert float((buf[:, :8] - 7.0).abs().max()) == 0.0 and float((buf[:, 8 + N :] - 7.0).abs().max()) == 0.0  # nothing written outside the view
 
 
