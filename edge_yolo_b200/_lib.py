@@ -57,6 +57,8 @@ _SIGNATURES = {
     "el_dfl_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "el_dfl_side_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "el_dfl_side_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "el_dsconv3_ok": (c_int, [c_int, c_int]),
+    "el_dsconv3_fwd": (c_int, [c_void_p, I64P, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_conv3x3_mma_ok": (c_int, [c_int, c_int, c_int]),
     "el_conv3x3_mma_fwd": (c_int, [c_void_p, I64P, c_int, c_void_p, c_void_p, c_void_p, I64P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "el_box_iou": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_float, c_void_p]),

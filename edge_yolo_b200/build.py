@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libedgeline_b200.so")
-SOURCES = ["core.cu", "wavelet.cu", "linattn.cu", "linattn_tc.cu", "linattn_tma.cu", "linattn_bwd.cu", "decode.cu", "nms.cu", "loss.cu", "epilogue.cu", "dwconv.cu", "dwconv_tma.cu", "pwconv.cu", "conv3x3_halo.cu", "conv3x3_mma.cu", "stem_tc.cu", "metrics.cu", "tal.cu"]
+SOURCES = ["core.cu", "wavelet.cu", "linattn.cu", "linattn_tc.cu", "linattn_tma.cu", "linattn_bwd.cu", "decode.cu", "nms.cu", "loss.cu", "epilogue.cu", "dwconv.cu", "dwconv_tma.cu", "pwconv.cu", "dsconv.cu", "conv3x3_halo.cu", "conv3x3_mma.cu", "stem_tc.cu", "metrics.cu", "tal.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # no --use_fast_math: IEEE division / sqrt are part of the NMS bit-exactness contract
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

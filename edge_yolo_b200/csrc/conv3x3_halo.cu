@@ -83,6 +83,13 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// the same descriptor from its low word ((address & 0x3FFFF) >> 4, plus a byte offset >> 4): the high word is constant
+__device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) { return ((uint64_t)0x40004040u << 32) | lo; }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t umma_idesc(int fmt, int M, int N) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -198,8 +205,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         // All MMAs of a tile accumulate into ONE TMEM accumulator, back to back.  (A variant that walked tiles in groups with one accumulator
         // per tile and interleaved their MMAs was built to test whether the dependent-accumulate chain limits the issue rate; it measured
         // 3.5 - 4x slower -- 193 / 212 us for groups of 1 / 4 against 55 us at 64 -> 64 @ 80 x 80, batch 64 -- and was dropped.)
-        if (lane == 0) {
+        // Issue cost matters here (36 MMAs per chunk): the WHOLE warp walks the loop, so every address below is warp-uniform and lives in the
+        // uniform datapath (UIADD3 on the low descriptor word, no register -> uniform-register moves, no per-thread waterfall around
+        // UTCHMMA -- which is what `if (lane == 0) { loop }` compiles to: ~19 instructions per MMA); one elected lane issues MMAs and commits.
+        {
             const uint32_t idesc = umma_idesc(kFmt, 128, n_pad);
+            const bool leader = elect_one();
+            const uint32_t b_tap_step = ((uint32_t)nch * A.tile_w_bytes) >> 4;
             mbar_wait(bar_w, 0);
             int it = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
@@ -211,18 +223,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
                     const int s = it % S;
                     mbar_wait(bar_full + 8 * s, (uint32_t)(it / S) & 1);
                     tc_fence_after();
-                    const uint32_t a_base = sbase + off_ring + (uint32_t)s * stage_bytes;
+                    const uint32_t a_lo = ((sbase + off_ring + (uint32_t)s * stage_bytes) & 0x3FFFF) >> 4;
+                    const uint32_t b_lo = ((sbase + (uint32_t)c * A.tile_w_bytes) & 0x3FFFF) >> 4;
+                    if (leader) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t a_tap = a_base + (uint32_t)((tap / 3) * kPitch + tap % 3) * 128;
-                        const uint32_t b_tap = sbase + (uint32_t)(tap * nch + c) * A.tile_w_bytes;
+                        for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma(d, umma_desc_sw128(a_tap + 32 * ks), umma_desc_sw128(b_tap + 32 * ks), idesc, (c > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < 4; ++ks)  // tap (ky, kx): the tile rows shifted by ky * 16 + kx; 32 bytes along K per step
+                                umma(d, umma_desc_lo(a_lo + (uint32_t)(((tap / 3) * kPitch + tap % 3) * 128 + 32 * ks) / 16),
+                                     umma_desc_lo(b_lo + (uint32_t)tap * b_tap_step + 2 * ks), idesc, (c > 0 || tap > 0 || ks > 0) ? 1u : 0u);
+                        }
+                        umma_commit(bar_empty + 8 * s);
+                        if (c == nch - 1) umma_commit(bar_acc_full + 8 * b);
                     }
-                    umma_commit(bar_empty + 8 * s);
+                    __syncwarp();
                 }
-                umma_commit(bar_acc_full + 8 * b);
             }
         }
     } else {

@@ -31,9 +31,9 @@ struct Args {
     const float* w;      // [9][C] fp32, tap-major (ops.pack_dw_weight)
     const float* bias;   // [C] or null
     void* out; int64_t osn, osh, osw;
-    int C, H, W, B, act, cvl_shift, NG, TH, tiles_x, tiles_y, n_cb, stages;
+    int C, H, W, B, act, CVL, NG, TH, tiles_x, tiles_y, n_cb, stages;   // CVL: 16-byte channel vectors per channel block (1..8, any value)
     int64_t n_tiles;
-    uint32_t stage_bytes;
+    uint32_t stage_bytes, box_bytes;   // ring pitch (128-byte multiple) and the bytes one box delivers
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv3_tma_kernel(const __grid_c
 
     const int64_t first = blockIdx.x;
     const int my_tiles = first < A.n_tiles ? (int)((A.n_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
-    const int CVL = 1 << A.cvl_shift, CB = CVL * 8;
+    const int CVL = A.CVL, CB = CVL * 8;
 
     pdl_launch_dependents();
     if (tid == 0) {
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv3_tma_kernel(const __grid_c
                 tile_coords(first + (int64_t)tl * gridDim.x, img, cb, ty, tx);
                 const int s = tl % S, use = tl / S;
                 if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)(use - 1) & 1);
-                mbar_expect_tx(bar_full + 8 * s, A.stage_bytes);
+                mbar_expect_tx(bar_full + 8 * s, A.box_bytes);
                 tma_load_4d(sbase + (uint32_t)s * A.stage_bytes, &A.src_map, cb * CB, tx * kTW - 1, ty * A.TH - 1, img, bar_full + 8 * s);
             }
         }
@@ -121,8 +121,9 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv3_tma_kernel(const __grid_c
     }
     // ---------------------------------------------------------------------------------------- compute threads
     constexpr int V = 8;
-    const int cvl = tid & (CVL - 1), rest = tid >> A.cvl_shift;
-    const int xl = rest % kTW, grp = rest / kTW;     // grp < NG by construction (kCompute = CVL * 20 * NG)
+    const int cvl = tid % CVL, rest = tid / CVL;
+    const int xl = rest % kTW, grp = rest / kTW;
+    const bool active = grp < A.NG;                  // CVL * 20 * NG <= kCompute: the threads past the last strip only take part in the barriers
     const int ly0 = grp * kRT;
     const uint32_t row_pitch = (uint32_t)kPW * CVL * 16;    // bytes per patch row
     const uint32_t my_off = (uint32_t)ly0 * row_pitch + (uint32_t)(xl * CVL + cvl) * 16;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv3_tma_kernel(const __grid_c
         mbar_wait(bar_full + 8 * s, (uint32_t)(tl / S) & 1);
         const uint32_t base = sbase + (uint32_t)s * A.stage_bytes + my_off;
         f32x2 acc[kRT][V / 2];
+        if (active) {
         {
             const float4 b0 = *reinterpret_cast<const float4*>(s_b + ch), b1 = *reinterpret_cast<const float4*>(s_b + ch + 4);
 #pragma unroll
@@ -165,9 +167,10 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv3_tma_kernel(const __grid_c
                     for (int e = 0; e < V / 2; ++e) acc[r][e] = fma_f32x2(v[r + ky][e], w2[e], acc[r][e]);
             }
         }
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // this warp has read everything it needs from the stage
-        if (ox < A.W) {
+        if (active && ox < A.W) {
             T* q = outp + (int64_t)img * A.osn + (int64_t)oy0 * A.osh + (int64_t)ox * A.osw + ch;
 #pragma unroll
             for (int r = 0; r < kRT; ++r) {
@@ -204,22 +207,24 @@ static EncodeTiledFn encode_fn() {
 
 }  // namespace dwt
 
-// k = 3, 16-bit, channel-contiguous views, C = 16 / 32 or a multiple of 64: returns EL_ERR_UNSUPPORTED otherwise (the caller falls back to
+// k = 3, 16-bit, channel-contiguous views, C a multiple of 16 (or of 8 with a divisor 2..8 of the vector count): returns EL_ERR_UNSUPPORTED otherwise (the caller falls back to
 // dwconv_tile_kernel).  Launch counting / error collection stay with the caller.
 int dwconv3_tma_launch(const void* x, Strides4 xs, const float* w, const float* bias, void* out, Strides4 os, int B, int C, int H, int W, int act,
                        int dtype, cudaStream_t st) {
     if (dtype != EL_BF16 && dtype != EL_F16) return EL_ERR_UNSUPPORTED;
-    int cvl_shift;
-    if (C == 16) cvl_shift = 1; else if (C == 32) cvl_shift = 2; else if (C % 64 == 0) cvl_shift = 3; else return EL_ERR_UNSUPPORTED;
+    if (C <= 0 || C % 8) return EL_ERR_UNSUPPORTED;
+    int CVL = 1;  // channel block = the largest divisor of the vector count that is <= 8 (80 channels: blocks of 5 vectors)
+    for (int d = 2; d <= 8; ++d) if ((C / 8) % d == 0) CVL = d;
+    if (CVL < 2) return EL_ERR_UNSUPPORTED;
     if (xs.c != 1 || os.c != 1 || xs.n % 8 || xs.h % 8 || xs.w % 8 || os.n % 8 || os.h % 8 || os.w % 8 || !aligned16(x) || !aligned16(out)) return EL_ERR_UNSUPPORTED;
     dwt::EncodeTiledFn fn = dwt::encode_fn();
     if (!fn) return EL_ERR_CUDA;
     dwt::Args A{};
-    const int CVL = 1 << cvl_shift, CB = CVL * 8;
-    A.cvl_shift = cvl_shift; A.NG = dwt::kCompute / (CVL * dwt::kTW); A.TH = A.NG * dwt::kRT;
+    const int CB = CVL * 8;
+    A.CVL = CVL; A.NG = dwt::kCompute / (CVL * dwt::kTW); A.TH = A.NG * dwt::kRT;
     A.n_cb = C / CB;
-    A.stage_bytes = (uint32_t)(A.TH + 2) * dwt::kPW * CVL * 16;  // a multiple of 128 for every CVL (22 * 32 * (TH + 2), TH + 2 even ...) -- checked below
-    if (A.stage_bytes % 128) A.stage_bytes = (A.stage_bytes + 127u) & ~127u;
+    A.box_bytes = (uint32_t)(A.TH + 2) * dwt::kPW * CVL * 16;
+    A.stage_bytes = (A.box_bytes + 127u) & ~127u;
     const size_t fixed = 128 + (size_t)10 * C * 4 + 16 * dwt::kMaxStages + 16;
     int S = (int)(((size_t)200 * 1024 - fixed) / A.stage_bytes);
     if (S > dwt::kMaxStages) S = dwt::kMaxStages;
@@ -233,7 +238,6 @@ int dwconv3_tma_launch(const void* x, Strides4 xs, const float* w, const float* 
     const cuuint64_t strides[3] = {(cuuint64_t)xs.w * 2, (cuuint64_t)xs.h * 2, (cuuint64_t)(B > 1 ? xs.n : (int64_t)H * xs.h) * 2};
     const cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)dwt::kPW, (cuuint32_t)(A.TH + 2), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    if ((uint32_t)(A.TH + 2) * dwt::kPW * CB * 2 != A.stage_bytes) return EL_ERR_UNSUPPORTED;  // the box must fill the stage exactly (expect_tx count)
     if (fn(&A.src_map, dtype == EL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return EL_ERR_CUDA;

@@ -91,6 +91,13 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp; the loops around it stay warp-uniform, so descriptors / coordinates live in uniform registers and the
+// UTMALDG / UTCHMMA issue is not wrapped in a per-thread register -> uniform-register waterfall (what `if (lane == 0) { loop }` compiles to)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -164,17 +171,23 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_tma_kernel(const __grid_c
         // ------------------------------------------------------------------------------------ TMA producer: the whole problem at once, and first:
         // this lane initialises the load barriers itself and issues all twelve tile loads before the CTA-wide set-up barrier, so the operand
         // fetch (the ~3 us HBM phase of this kernel) overlaps the TMEM allocation and the other barriers' initialisation
-        if (lane == 0) {
+        const bool leader = elect_one();
+        if (leader) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&A.qkv_map) : "memory");
             for (int c = 0; c < kMaxChunks; ++c) { mbar_init(bar_kq + 8 * c, 1); mbar_init(bar_v + 8 * c, 1); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            pdl_wait();  // the qkv GEMM that produced our input has completed from here on
-            for (int c = 0; c < n_chunks; ++c) {  // K and Q first (the compute warps start on them), V is only read by the tensor core
+        }
+        __syncwarp();
+        pdl_wait();  // the qkv GEMM that produced our input has completed from here on
+        for (int c = 0; c < n_chunks; ++c) {  // K and Q first (the compute warps start on them), V is only read by the tensor core
+            if (leader) {
                 mbar_expect_tx(bar_kq + 8 * c, 2 * kTile);
                 tma_load_3d(sbase + kOffK + c * kTile, &A.qkv_map, C + head * kD, c * kChunk, b, bar_kq + 8 * c);
                 tma_load_3d(sbase + kOffQ + c * kTile, &A.qkv_map, head * kD, c * kChunk, b, bar_kq + 8 * c);
             }
-            for (int c = 0; c < n_chunks; ++c) {
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            if (leader) {
                 mbar_expect_tx(bar_v + 8 * c, kTile);
                 tma_load_3d(sbase + kOffV + c * kTile, &A.qkv_map, 2 * C + head * kD, c * kChunk, b, bar_v + 8 * c);
             }
@@ -202,7 +215,8 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_tma_kernel(const __grid_c
         // (loads already issued above)
     } else if (warp == 17) {
         // ------------------------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             const uint32_t idesc1 = umma_idesc(kFmt, 1, 1, 64, 64);   // ctx[i][j] += ksm[n][i] v[n][j]: both operands MN-major, K = tokens
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(bar_kready + 8 * c, 0);
@@ -210,20 +224,25 @@ __global__ void __launch_bounds__(kThreads, 1) linattn_tma_kernel(const __grid_c
                 tc_fence_after();
                 const int nvalid = min(kChunk, N - c * kChunk);
                 const int ksteps = (nvalid + 15) >> 4;  // rows past N are zero in V (TMA fill): they add nothing
-                for (int ks = 0; ks < ksteps; ++ks)
-                    umma(tmem_d1, umma_desc_sw128(sbase + kOffK + c * kTile + ks * 2048), umma_desc_sw128(sbase + kOffV + c * kTile + ks * 2048), idesc1,
-                         (c > 0 || ks > 0) ? 1u : 0u);
+                const uint64_t dk = umma_desc_sw128(sbase + kOffK + c * kTile), dv = umma_desc_sw128(sbase + kOffV + c * kTile);
+                if (leader) {
+                    for (int ks = 0; ks < ksteps; ++ks)  // a K step of 16 token rows = +2048 B on the start address (>> 4 in the descriptor)
+                        umma(tmem_d1, dk + (uint64_t)(ks * 128), dv + (uint64_t)(ks * 128), idesc1, (c > 0 || ks > 0) ? 1u : 0u);
+                    if (c == n_chunks - 1) umma_commit(bar_g1);
+                }
+                __syncwarp();
             }
-            umma_commit(bar_g1);
             const uint32_t idesc2 = umma_idesc(kFmt, 0, 1, 128, 64);  // y[n][j] = P_c[n][i] ctx_c[i][j]: A K-major, B MN-major, K = 64 channels
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(bar_pready + 8 * c, 0);
                 tc_fence_after();
+                const uint64_t dq = umma_desc_sw128(sbase + kOffQ + c * kTile), dk = umma_desc_sw128(sbase + kOffK + c * kTile);
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    umma(tmem_d2 + c * kD, umma_desc_sw128(sbase + kOffQ + c * kTile + ks * 32), umma_desc_sw128(sbase + kOffK + c * kTile + ks * 2048), idesc2,
-                         ks > 0 ? 1u : 0u);
-                umma_commit(bar_d2 + 8 * c);
+                    for (int ks = 0; ks < 4; ++ks) umma(tmem_d2 + c * kD, dq + (uint64_t)(ks * 2), dk + (uint64_t)(ks * 128), idesc2, ks > 0 ? 1u : 0u);
+                    umma_commit(bar_d2 + 8 * c);
+                }
+                __syncwarp();
             }
         }
     } else if ((warp >> 2) < n_chunks) {

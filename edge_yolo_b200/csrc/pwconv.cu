@@ -126,6 +126,14 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp.  The producer / MMA loops stay warp-uniform around it, so coordinates and descriptors live in uniform registers
+// and UTMALDG / UTCHMMA are not wrapped in a per-thread register -> uniform-register waterfall (what `if (lane == 0) { loop }` compiles to:
+// ~19 instructions per MMA, measured on the 3x3 halo kernel where 36 MMAs per chunk made the issue thread the bottleneck)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -223,7 +231,8 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             int it = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const int64_t tile = first + (int64_t)tl * gridDim.x;
@@ -241,18 +250,22 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                     const Chunk ck = A.chunk[c];
                     const uint32_t dst = sbase + off_ring + (uint32_t)s * A.stage_bytes;
                     const uint32_t wt_bytes = A.stream_w ? (uint32_t)n_tile * ck.rb : 0u;
-                    mbar_expect_tx(bar_full + 8 * s, (uint32_t)kTileM * ck.rb + wt_bytes);
-                    if (A.stream_w)  // this chunk's weight tile rides in the same stage (L2-resident after the first tile)
-                        bulk_g2s(dst + A.a_stage_bytes, reinterpret_cast<const unsigned char*>(A.wpk) + (size_t)nt * A.w_bytes + ck.w_off, wt_bytes,
-                                 bar_full + 8 * s);
-                    if (A.spatial) tma_load_4d(dst, &A.src_map[0], ck.c0, x0 + ck.src % 3, y0 + ck.src / 3, img, bar_full + 8 * s);
-                    else tma_load_2d(dst, &A.src_map[ck.src], ck.c0, m0, bar_full + 8 * s);
+                    if (leader) {
+                        mbar_expect_tx(bar_full + 8 * s, (uint32_t)kTileM * ck.rb + wt_bytes);
+                        if (A.stream_w)  // this chunk's weight tile rides in the same stage (L2-resident after the first tile)
+                            bulk_g2s(dst + A.a_stage_bytes, reinterpret_cast<const unsigned char*>(A.wpk) + (size_t)nt * A.w_bytes + ck.w_off, wt_bytes,
+                                     bar_full + 8 * s);
+                        if (A.spatial) tma_load_4d(dst, &A.src_map[0], ck.c0, x0 + ck.src % 3, y0 + ck.src / 3, img, bar_full + 8 * s);
+                        else tma_load_2d(dst, &A.src_map[ck.src], ck.c0, m0, bar_full + 8 * s);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = umma_idesc(kFmt, kTileM, n_tile);
             if (!A.stream_w) mbar_wait(bar_w, 0);
             int it = 0;
@@ -268,11 +281,16 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                     const Chunk ck = A.chunk[c];
                     const uint32_t a_base = sbase + off_ring + (uint32_t)s * A.stage_bytes;
                     const uint32_t b_base = A.stream_w ? a_base + A.a_stage_bytes : sbase + ck.w_off;
-                    for (int ks = 0; ks < ck.rb / 32; ++ks)  // one MMA per 16 channels = 32 bytes along K inside the swizzle atom
-                        umma(d, umma_desc_sw(a_base + 32 * ks, ck.rb), umma_desc_sw(b_base + 32 * ks, ck.rb), idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                    umma_commit(bar_empty + 8 * s);
+                    const uint64_t da = umma_desc_sw(a_base, ck.rb), db = umma_desc_sw(b_base, ck.rb);
+                    const int ksteps = ck.rb / 32;
+                    if (leader) {
+                        for (int ks = 0; ks < ksteps; ++ks)  // one MMA per 16 channels = 32 bytes along K inside the swizzle atom (+2 in the descriptor's start field)
+                            umma(d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        umma_commit(bar_empty + 8 * s);
+                        if (c == nch - 1) umma_commit(bar_acc_full + 8 * b);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(bar_acc_full + 8 * b);
             }
         }
     } else {
@@ -304,14 +322,15 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                 const uint32_t stg = sbase + off_stage + (uint32_t)(sub & 1) * staging_bytes;
                 if (et == 0) bulk_wait_read<1>();  // the store that last read this staging buffer (two uses ago) is done with it
                 epi_barrier();
-                for (int j0 = 0; j0 < ob; j0 += 32) {  // two 16-column TMEM loads in flight per wait
+                const int jmax = min(ob, ((n_real - c0) + 15) & ~15);  // the last box of an 80-channel conv holds 16 real columns: skip the other 48
+                for (int j0 = 0; j0 < jmax; j0 += 32) {  // two 16-column TMEM loads in flight per wait
                 uint32_t v[2][16];
                 tmem_ld16_nowait(taddr + c0 + j0, v[0]);
-                if (j0 + 16 < ob) tmem_ld16_nowait(taddr + c0 + j0 + 16, v[1]);
+                if (j0 + 16 < jmax) tmem_ld16_nowait(taddr + c0 + j0 + 16, v[1]);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    if (j0 + jj * 16 >= ob) break;
+                    if (j0 + jj * 16 >= jmax) break;
                     const int j = j0 + jj * 16;
                     float f[16];
                     const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0 + j);

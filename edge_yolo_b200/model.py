@@ -151,6 +151,10 @@ class EdgeLineYOLO(nn.Module):
             for m in self.modules():
                 if type(m) in binds:
                     m.forward = types.MethodType(binds[type(m)], m)
+            for m in self.modules():  # DWConv(k = 3) -> Conv(1x1) pairs (class towers): one fused kernel
+                if (isinstance(m, nn.Sequential) and len(m) == 2 and all(isinstance(t, Conv) and hasattr(t, "el_bias") for t in m)
+                        and hasattr(m[0], "el_dw") and m[0].el_k == 3 and m[1].conv.kernel_size == (1, 1)):
+                    m.forward = types.MethodType(M.dwpw_engine_forward, m)
             head = self.model[-1]
             if isinstance(head, GFLHeadv2_uniH):  # the last 1x1 convs of both towers lose their bias; the decode kernels add it
                 box_b, cls_b = [], []
@@ -197,11 +201,11 @@ def _dw_eligible(conv: nn.Conv2d, epilogue: bool = False) -> bool:
     C = conv.in_channels
     if not M.USE_DWCONV or not (epilogue or k >= 5 or M.DWCONV_K3):
         return False
-    # The kernel takes any multiple of 8 channels (vectors blocked by their largest divisor <= 8), but the engine keeps the sites whose
-    # vector count is not a power of two (the 80-channel class towers: blocks of 5) on PyTorch's depthwise kernel + el_bias_act: measured
-    # over the whole graph that is ~1 % faster (22 559 vs 22 311 img/s) although the two are on par in isolation (109 vs 118 us).
+    # The kernels take any multiple of 8 channels (vectors blocked by their largest divisor <= 8).  Round 1 kept the sites whose vector count
+    # is not a power of two (the 80-channel class towers: blocks of 5) on PyTorch's depthwise kernel + el_bias_act, which was ~1 % faster over
+    # the graph than the cp.async tile kernel; the persistent TMA kernel takes any block width since round 2 (modules.DWCONV_ANY_C).
     C8 = C // 8
-    return (C % 8 == 0 and (C8 & (C8 - 1) == 0 or C % 64 == 0) and conv.groups == C == conv.out_channels and C > 1 and conv.kernel_size == (k, k)
+    return (C % 8 == 0 and (C8 & (C8 - 1) == 0 or C % 64 == 0 or (M.DWCONV_ANY_C and k == 3 and C >= 16)) and conv.groups == C == conv.out_channels and C > 1 and conv.kernel_size == (k, k)
             and k in (3, 5, 7) and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.padding == (k // 2, k // 2))
 
 

@@ -211,6 +211,7 @@ def gfl_head_forward(self, x):
 
 USE_DWCONV = True  # el_dwconv_fwd in the engine graph (model._dw_eligible picks the sites where it wins)
 DWCONV_K3 = True   # also the bare k = 3 depthwise of DSConv (on par with PyTorch in isolation; ours chains with PDL)
+DWCONV_ANY_C = True  # k = 3 depthwise with any multiple of 8 channels >= 16 (the 80-channel class towers) on dwconv3_tma_kernel
 
 
 def _bias_on(self, x):
@@ -405,9 +406,48 @@ def dwconv_engine_forward(self, x, out=None, residual=None, out2=None):
     return ops.dwconv(x, _dw_on(self, x), self.el_k, bias=_bias_on(self, x), act=self.el_act, out=out)
 
 
+USE_DSCONV3 = True  # el_dsconv3_fwd: depthwise 3x3 -> pointwise 1x1 in one kernel (DSConv k = 3; DWConv -> Conv pairs of the class towers)
+DSCONV3_MIN_C = 32  # narrower sites stay on the two-kernel path
+DSCONV3_MAX_HW = int(__import__("os").environ.get("EL_DS3_MAX_HW", 1600))  # maps up to 40 x 40: where one launch instead of two is what pays (tools/prof_dsconv.py)
+
+
+def _ds3_ok(dw: nn.Conv2d, pw: nn.Conv2d, x: torch.Tensor, out=None) -> bool:
+    """el_dsconv3_fwd applies: depthwise 3x3 / stride 1 / padding 1 into a dense 1x1 conv, 16-bit NHWC views, no autograd."""
+    C, N = dw.in_channels, pw.out_channels
+    if not (USE_DSCONV3 and C >= DSCONV3_MIN_C and x.shape[2] * x.shape[3] <= DSCONV3_MAX_HW and dw.kernel_size == (3, 3) and dw.stride == (1, 1) and dw.padding == (1, 1) and dw.dilation == (1, 1)
+            and dw.groups == C == dw.out_channels and pw.kernel_size == (1, 1) and pw.stride == (1, 1) and pw.groups == 1 and pw.padding in ((0, 0), 0)
+            and pw.in_channels == C and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and not torch.is_grad_enabled()):
+        return False
+    for t in (x, out):
+        if t is not None and (t.stride(1) != 1 or any(st % 8 for i, st in enumerate(t.stride()) if i != 1) or t.data_ptr() % 16):
+            return False
+    return ops.dsconv3_ok(C, N)
+
+
+def ds3_apply(dw_packed, pw: nn.Conv2d, x, bias, act, dw_bias=None, dw_act=ops.ACT_NONE, out=None):
+    """Fused depthwise 3x3 -> 1x1 (ops.dsconv3); the pointwise weight tile is packed once per (dtype, device, weight version) and cached on the conv."""
+    key = (x.dtype, x.device, _ver(pw.weight), pw.weight.data_ptr())
+    c = pw.__dict__.get("el_ds3_wpk")
+    if c is None or c[0] != key:
+        c = pw.el_ds3_wpk = (key, ops.pack_dsconv3_weight(pw.weight, x.dtype).to(x.device))
+    return ops.dsconv3(x, dw_packed, c[1], pw.out_channels, bias=bias, act=act, dw_bias=dw_bias, dw_act=dw_act, out=out)
+
+
+def dwpw_engine_forward(self, x):
+    """Sequential(DWConv(x, x, 3), Conv(x, c, 1)) of the class towers (head.py:66-71) as one kernel: depthwise + bias + SiLU feeds the
+    1x1 GEMM from shared memory."""
+    dwm, pwm = self[0], self[1]
+    w = _dw_on(dwm, x)
+    if w is not None and dwm.el_k == 3 and _ds3_ok(dwm.conv, pwm.conv, x):
+        return ds3_apply(w, pwm.conv, x, _bias_on(pwm, x), pwm.el_act, dw_bias=_bias_on(dwm, x), dw_act=dwm.el_act)
+    return pwm(dwm(x))
+
+
 def dsconv_engine_forward(self, x, out=None, residual=None, out2=None):
     """DSConv.forward (conv.py:100-104) with its BatchNorm folded into the pointwise conv."""
     w = _dw_on(self, x)
+    if w is not None and self.el_k == 3 and residual is None and out2 is None and _ds3_ok(self.dw, self.pw, x, out):
+        return ds3_apply(w, self.pw, x, _bias_on(self, x), ops.ACT_SILU, out=out)
     d = ops.dwconv(x, w, self.el_k) if w is not None else self.dw(x)
     if _pw_ok(self.pw, [d], out, residual, out2):
         return pw_apply(self.pw, [d], _bias_on(self, x), ops.ACT_SILU, out=out, residual=residual, out2=out2)

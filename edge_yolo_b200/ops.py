@@ -774,6 +774,38 @@ def pwconv(srcs, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, ac
     return out
 
 
+def dsconv3_ok(C: int, N: int) -> bool:
+    """el_dsconv3_fwd covers this (C_in, N) site (C 16 / 32 or >= 64, N a multiple of 8 up to 256, pointwise weights resident in shared memory)."""
+    return bool(_lib.lib().el_dsconv3_ok(int(C), int(N)))
+
+
+def pack_dsconv3_weight(pw_weight: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """Pointwise weight (N, C[,1,1]) of a depthwise-separable pair -> the resident B operand of el_dsconv3_fwd: the el_pwconv_fwd packing for one
+    source of C channels with a single output-channel tile of ceil16(N) rows."""
+    N, C = pw_weight.shape[0], pw_weight.shape[1]
+    return pack_pw_weight(pw_weight, [C], dtype=dtype, n_tile=-(-N // 16) * 16)
+
+
+def dsconv3(x: torch.Tensor, dw_packed: torch.Tensor, wpk: torch.Tensor, N: int, bias: torch.Tensor | None = None, act: int = ACT_SILU,
+            dw_bias: torch.Tensor | None = None, dw_act: int = ACT_NONE, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Depthwise 3x3 (stride 1, padding 1; + dw_bias + dw_act) -> pointwise 1x1 + bias + act in one kernel (DSConv.forward with k = 3,
+    nn/modules/conv.py:100-104; DWConv -> Conv(1x1) of the class towers, nn/modules/head.py:66-71).  `dw_packed` from pack_dw_weight,
+    `wpk` from pack_dsconv3_weight; NHWC 16-bit activations (channel-slice views allowed)."""
+    _need_cuda(x, dw_packed, wpk)
+    B, C, H, W = x.shape
+    if dw_packed.dtype != torch.float32 or tuple(dw_packed.shape) != (9, C) or not dw_packed.is_contiguous():
+        raise EdgelineError("dsconv3: dw_packed must be contiguous fp32 (9, C)")
+    for name, b, n in (("bias", bias, N), ("dw_bias", dw_bias, C)):
+        if b is not None and (b.dtype != torch.float32 or b.numel() != n or not b.is_contiguous()):
+            raise EdgelineError(f"dsconv3: {name} must be a contiguous fp32 vector of {n} elements")
+    if out is None:
+        out = torch.empty((B, N, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    check(_lib.lib().el_dsconv3_fwd(x.data_ptr(), _i64(x.stride()), C, dw_packed.data_ptr(), dw_bias.data_ptr() if dw_bias is not None else None, int(dw_act),
+                                    wpk.data_ptr(), bias.data_ptr() if bias is not None else None, int(act), out.data_ptr(), _i64(out.stride()),
+                                    B, H, W, N, _dt(x), _stream()), "el_dsconv3_fwd")
+    return out
+
+
 def conv3x3_tiles(N: int, C: int, B: int, H: int, W: int, stride: int = 1):
     """(n_tile, n_tiles) el_conv3x3_fwd uses for this site."""
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1

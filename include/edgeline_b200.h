@@ -210,9 +210,19 @@ int el_upsample2x_cat_fwd(const void* x, const int64_t xs[4], const void* skip, 
 /* el_dwconv_fwd: depthwise k x k convolution, stride 1, padding k/2 (k in {3,5,7}), NHWC views, optional fused
  * bias + activation: DSConv.dw (nn/modules/conv.py:87-104, no epilogue) and DWConv + folded BatchNorm + SiLU
  * (conv.py:124-130; Detect cls tower head.py:66-71).  w: fp32 (k*k, C) tap-major; bias fp32 (C) or NULL;
- * act as el_bias_act_fwd.  C must be a multiple of the 16-byte channel vector and <= 64 or a multiple of 64. */
+ * act as el_bias_act_fwd.  C must be a multiple of the 16-byte channel vector. */
 int el_dwconv_fwd(const void* x, const int64_t xs[4], const float* w, const float* bias, void* out,
                   const int64_t os[4], int B, int C, int H, int W, int k, int act, int dtype, void* stream);
+/* el_dsconv3_fwd: depthwise 3 x 3 (stride 1, padding 1; optional bias + activation) -> pointwise 1 x 1 + bias + activation in ONE kernel:
+ * DSConv.forward with k = 3 (nn/modules/conv.py:100-104: dw -> pw -> BatchNorm -> SiLU; cv1 of DSBottleneck, nn/modules/block.py:1494-1503) and
+ * the DWConv(x, x, 3) -> Conv(x, c, 1) stages of the class towers (nn/modules/head.py:66-71).  The depthwise result is rounded to the
+ * activation type (as el_dwconv_fwd would store it) and written straight into the swizzled A tile of the tcgen05 GEMM; it never reaches HBM.
+ * x / out NHWC 16-bit views (channels contiguous, other strides in 8s); dw_w fp32 (9, C) tap-major, dw_bias fp32 (C) or NULL, dw_act / act
+ * as el_bias_act_fwd; wpk = the el_pwconv_fwd weight packing for ONE source of C channels with a single output-channel tile of
+ * ceil16(N) rows; bias fp32 (N) or NULL.  el_dsconv3_ok: C = 16 / 32 or >= 64 (multiple of 8), N a multiple of 8 up to 256, weights resident. */
+int el_dsconv3_ok(int C, int N);
+int el_dsconv3_fwd(const void* x, const int64_t xs[4], int C, const float* dw_w, const float* dw_bias, int dw_act, const void* wpk,
+                   const float* bias, int act, void* out, const int64_t os[4], int B, int H, int W, int N, int dtype, void* stream);
 /* el_pwconv_fwd: pointwise (1x1) convolution + folded-BatchNorm bias + activation (+ shortcut) as one streaming
  * tcgen05 GEMM over NHWC pixels (Conv(k=1).forward_fuse nn/modules/conv.py:58-60; DSConv.pw + bn + act conv.py:100-104;
  * LinearAttention.qkv / proj block.py:3353-3373).  out[p, n] = res_scale * act(sum_k X[p,k] W[n,k] + bias[n]) (+ res[p,n]);

@@ -593,7 +593,8 @@ def test_dwconv(dtype, tol, k, shape, epi):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape,act", [((2, 64, 80, 80), 0), ((3, 32, 40, 40), 1), ((2, 16, 160, 160), 0), ((2, 128, 20, 20), 2), ((1, 256, 20, 20), 0),
-                                       ((2, 64, 23, 37), 1), ((1, 32, 7, 61), 0), ((5, 16, 45, 19), 1), ((70, 64, 20, 20), 0)])
+                                       ((2, 64, 23, 37), 1), ((1, 32, 7, 61), 0), ((5, 16, 45, 19), 1), ((70, 64, 20, 20), 0),
+                                       ((2, 80, 80, 80), 1), ((3, 48, 40, 40), 0), ((2, 24, 33, 21), 2), ((3, 80, 20, 20), 1)])  # blocks of 5 / 6 / 3 vectors: idle compute threads
 def test_dwconv3_tma_pipeline(dtype, shape, act):
     """k = 3 depthwise conv on the persistent TMA-pipelined kernel (C = 16 / 32 / 64 n, 16-bit): whole tiles and ragged ones, image borders
     (TMA zero fill = padding), several channel blocks, more tiles than CTAs (ring / barrier phase wrap), channel-slice source and destination
@@ -612,6 +613,42 @@ def test_dwconv3_tma_pipeline(dtype, shape, act):
     tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
     close(got, want.float(), tol, tol)
     assert float((out[:, :8] - 7.0).abs().max()) == 0.0  # nothing written outside the destination view
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,N,dw_epi,act", [((2, 64, 40, 40), 64, False, 1), ((3, 64, 20, 20), 64, False, 1), ((2, 64, 80, 80), 80, True, 1), ((2, 80, 40, 40), 80, True, 1),
+                                                ((1, 128, 40, 40), 80, True, 0), ((2, 256, 20, 20), 80, True, 1), ((2, 32, 80, 80), 32, False, 1), ((2, 16, 160, 160), 16, False, 2),
+                                                ((2, 64, 23, 37), 24, False, 1), ((1, 128, 7, 61), 128, True, 1), ((5, 32, 45, 19), 64, False, 1), ((70, 64, 20, 20), 64, False, 1),
+                                                ((1, 128, 26, 20), 256, False, 1), ((2, 72, 13, 21), 40, True, 2)])
+def test_dsconv3_fused(dtype, shape, N, dw_epi, act):
+    """Depthwise 3x3 -> pointwise 1x1 in one kernel (el_dsconv3_fwd: DSConv.forward k = 3, nn/modules/conv.py:100-104; DWConv -> Conv of the class
+    towers, head.py:66-71) against (1) the two-kernel path it replaces (el_dwconv_fwd -> el_pwconv_fwd: same depthwise evaluation order, same
+    16-bit rounding of the intermediate, same GEMM K order) and (2) torch fp64 with the intermediate rounded to the activation type.  Whole and
+    ragged 20 x 6 tiles, image borders (TMA zero fill = padding), one to four K chunks incl. a partial last chunk (80 / 72 channels), 16 / 32-channel
+    chunks (idle depthwise warps), two store boxes per tile (N > 64), more tiles than CTAs (ring / phase wrap), channel-slice source and destination."""
+    o = ops()
+    gen = torch.Generator().manual_seed(shape[1] * 3 + shape[2] + N)
+    B, C, H, W = shape
+    assert o.dsconv3_ok(C, N)
+    full = torch.randn(B, C + 16, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    x = full[:, 16:]
+    wd = (torch.randn(C, 1, 3, 3, generator=gen) * 0.3).to(DEV)
+    bd = torch.randn(C, generator=gen).to(DEV) if dw_epi else None
+    wp = (torch.randn(N, C, generator=gen) * C ** -0.5).to(DEV)
+    bp = torch.randn(N, generator=gen).to(DEV)
+    dw_act = o.ACT_SILU if dw_epi else o.ACT_NONE
+    fin = lambda t, a: torch.nn.functional.silu(t) if a == 1 else (t.relu() if a == 2 else t)
+    d64 = fin(torch.nn.functional.conv2d(x.double(), wd.double(), bd.double() if dw_epi else None, padding=1, groups=C), dw_act).to(dtype).double()
+    want = fin(torch.einsum("bchw,nc->bnhw", d64, wp.to(dtype).double()) + bp.double().view(1, -1, 1, 1), act)
+    out = torch.full((B, N + 8, H, W), 7.0, device=DEV, dtype=dtype).contiguous(memory_format=torch.channels_last)
+    got = o.dsconv3(x, o.pack_dw_weight(wd), o.pack_dsconv3_weight(wp, dtype), N, bias=bp, act=act, dw_bias=bd, dw_act=dw_act, out=out[:, 8:])
+    tol = 3e-2 if dtype == torch.bfloat16 else 6e-3
+    close(got, want.float(), tol, tol)
+    assert float((out[:, :8] - 7.0).abs().max()) == 0.0  # nothing written outside the destination view
+    d = o.dwconv(x, o.pack_dw_weight(wd), 3, bias=bd, act=dw_act)
+    two = o.pwconv([d], o.pack_pw_weight(wp, [C], dtype, M=B * H * W), N, bias=bp, act=act)
+    close(got, two, 1e-2 if dtype == torch.bfloat16 else 2e-3, 1e-2 if dtype == torch.bfloat16 else 2e-3)
+    test_dsconv3_fused.max_diff_vs_two_kernels = max(getattr(test_dsconv3_fused, "max_diff_vs_two_kernels", 0.0), float((got.float() - two.float()).abs().max()))
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
