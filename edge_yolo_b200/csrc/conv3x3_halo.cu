@@ -28,7 +28,8 @@
 namespace el {
 namespace c3 {
 
-constexpr int kThreads = 320;                     // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int kMaxEpi = 4;                        // epilogue groups of four warps (one per TMEM lane quarter), each with its own TMEM accumulator
+constexpr int kThreads = 64 + 128 * kMaxEpi;      // TMA warp, MMA warp, up to 16 epilogue warps (the launch uses 64 + 128 * groups)
 constexpr int kTW = 14, kTH = 8, kPitch = 16;     // output tile, pitch of the M rows
 constexpr int kInRows = (kTH + 2) * kPitch;       // 160 rows of 128 B per K chunk
 constexpr uint32_t kStageBytes = kInRows * 128 + 512;  // + 4 rows: tap (2, 2) reads two rows past the tile for the junk columns of the last row
@@ -39,7 +40,7 @@ struct Args {
     CUtensorMap src_map, out_map;
     const void* wpk;       // [9 taps][C/64 chunks] tiles of n_pad x 128 B (SW128, K-major), each padded to 1 KiB
     const float* bias;
-    int B, H, W, N, n_pad, chunks, act, stages, ob, group;  // group: pixel tiles whose MMAs are interleaved (independent accumulators)
+    int B, H, W, N, n_pad, chunks, act, stages, ob, groups, nstg;  // groups: epilogue groups = TMEM accumulators; nstg: staging tiles per group
     int tiles_x, tiles_y;
     int64_t n_tiles;
     uint32_t w_bytes, tile_w_bytes, tmem_cols;
@@ -137,41 +138,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     unsigned char* sm = sm_raw + (sbase - smem_addr(sm_raw));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = A.stages, N = A.N, n_pad = A.n_pad, nch = A.chunks, ob = A.ob;
-    // shared memory map: [weights][stage ring][2 staging tiles 128 x ob][bias][barriers]
+    // shared memory map: [weights][stage ring][groups x nstg staging tiles 128 x ob][bias][barriers]
+    const int G = A.groups, nstg = A.nstg;
     const uint32_t off_ring = (A.w_bytes + 1023u) & ~1023u;
     const uint32_t stage_bytes = (kStageBytes + 1023u) & ~1023u;
     const uint32_t off_stage = off_ring + (uint32_t)S * stage_bytes;
     const uint32_t staging_bytes = 128u * ob * 2;
-    const uint32_t off_bias = off_stage + 2 * staging_bytes;
+    const uint32_t off_bias = off_stage + (uint32_t)(G * nstg) * staging_bytes;
     const uint32_t off_bar = off_bias + (((uint32_t)(n_pad + 64) * 4 + 127) & ~127u);
     float* s_bias = reinterpret_cast<float*>(sm + off_bias);
     const uint32_t bar_w = sbase + off_bar;
-    const uint32_t bar_acc_full = sbase + off_bar + 8;                  // [2][kMaxGroup]: two sets of accumulators, group j uses set j & 1
-    const uint32_t bar_acc_empty = bar_acc_full + 16 * kMaxGroup;       // [2][kMaxGroup]
-    const uint32_t bar_full = bar_acc_empty + 16 * kMaxGroup;           // [kMaxStages]
+    const uint32_t bar_acc_full = sbase + off_bar + 8;                  // [kMaxEpi] accumulator g complete
+    const uint32_t bar_acc_empty = bar_acc_full + 8 * kMaxEpi;          // [kMaxEpi] accumulator g drained by its epilogue group
+    const uint32_t bar_full = bar_acc_empty + 8 * kMaxEpi;              // [kMaxStages]
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;               // [kMaxStages]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + off_bar + 8 + 32 * kMaxGroup + 16 * kMaxStages);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sm + off_bar + 8 + 16 * kMaxEpi + 16 * kMaxStages);
 
     const int64_t first = blockIdx.x;
     const int my_tiles = first < A.n_tiles ? (int)((A.n_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
     const int per_img = A.tiles_x * A.tiles_y;
     constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+    const int nthreads = blockDim.x;
 
     pdl_launch_dependents();
     if (tid == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&A.src_map) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&A.out_map) : "memory");
         mbar_init(bar_w, 1);
-        for (int b = 0; b < 2 * kMaxGroup; ++b) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, 256); }
+        for (int b = 0; b < kMaxEpi; ++b) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_empty + 8 * b, 128); }
         for (int s = 0; s < S; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(bar_w, A.w_bytes);
         const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(A.wpk);
         for (uint32_t o = 0; o < A.w_bytes; o += 32768) bulk_g2s(sbase + o, wsrc + o, min(32768u, A.w_bytes - o), bar_w);
     }
-    for (int i = tid; i < n_pad + 64; i += kThreads) s_bias[i] = (A.bias && i < N) ? __ldg(A.bias + i) : 0.f;
+    for (int i = tid; i < n_pad + 64; i += nthreads) s_bias[i] = (A.bias && i < N) ? __ldg(A.bias + i) : 0.f;
     // the four rows behind every stage (read by tap (2, 2) for the junk columns of the last tile row) must hold finite numbers
-    for (int i = tid; i < S * 32; i += kThreads)
+    for (int i = tid; i < S * 32; i += nthreads)
         *reinterpret_cast<uint4*>(sm + off_ring + (uint32_t)(i >> 5) * stage_bytes + kInRows * 128 + (i & 31) * 16) = make_uint4(0, 0, 0, 0);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(A.tmem_cols));
@@ -186,25 +189,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
 
     if (warp == 0) {
         // ------------------------------------------------------------------------------------ TMA producer: one haloed box per K chunk
-        if (lane == 0) {
-            int it = 0;
-            for (int tl = 0; tl < my_tiles; ++tl) {
-                const int64_t tile = first + (int64_t)tl * gridDim.x;
-                const int img = (int)(tile / per_img), r = (int)(tile % per_img);
-                const int y0 = (r / A.tiles_x) * kTH - 1, x0 = (r % A.tiles_x) * kTW - 1;
-                for (int c = 0; c < nch; ++c, ++it) {
-                    const int s = it % S, use = it / S;
-                    if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)(use - 1) & 1);
+        const bool leader = elect_one();
+        int s = 0, use = 0;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int64_t tile = first + (int64_t)tl * gridDim.x;
+            const int img = (int)(tile / per_img), r = (int)(tile % per_img);
+            const int y0 = (r / A.tiles_x) * kTH - 1, x0 = (r % A.tiles_x) * kTW - 1;
+            for (int c = 0; c < nch; ++c) {
+                if (use > 0) mbar_wait(bar_empty + 8 * s, (uint32_t)(use - 1) & 1);
+                if (leader) {
                     mbar_expect_tx(bar_full + 8 * s, kInRows * 128);
                     tma_load_4d(sbase + off_ring + (uint32_t)s * stage_bytes, &A.src_map, c * 64, x0, y0, img, bar_full + 8 * s);
                 }
+                __syncwarp();
+                if (++s == S) { s = 0; ++use; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------------------------ MMA issuer: 9 taps x 4 K steps per chunk.
-        // All MMAs of a tile accumulate into ONE TMEM accumulator, back to back.  (A variant that walked tiles in groups with one accumulator
-        // per tile and interleaved their MMAs was built to test whether the dependent-accumulate chain limits the issue rate; it measured
-        // 3.5 - 4x slower -- 193 / 212 us for groups of 1 / 4 against 55 us at 64 -> 64 @ 80 x 80, batch 64 -- and was dropped.)
+        // All MMAs of a tile accumulate into ONE TMEM accumulator, back to back; tile tl uses accumulator tl % G, drained by epilogue group tl % G.
+        // (A variant that interleaved the MMAs of several tiles measured 3.5 - 4x slower and was dropped.)
         // Issue cost matters here (36 MMAs per chunk): the WHOLE warp walks the loop, so every address below is warp-uniform and lives in the
         // uniform datapath (UIADD3 on the low descriptor word, no register -> uniform-register moves, no per-thread waterfall around
         // UTCHMMA -- which is what `if (lane == 0) { loop }` compiles to: ~19 instructions per MMA); one elected lane issues MMAs and commits.
@@ -213,15 +217,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
             const bool leader = elect_one();
             const uint32_t b_tap_step = ((uint32_t)nch * A.tile_w_bytes) >> 4;
             mbar_wait(bar_w, 0);
-            int it = 0;
+            int s = 0, b = 0;
+            uint32_t s_par = 0, ub = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
-                const int b = tl & 1, ub = tl >> 1;
-                if (ub > 0) mbar_wait(bar_acc_empty + 8 * b, (uint32_t)(ub - 1) & 1);
+                if (ub > 0) mbar_wait(bar_acc_empty + 8 * b, (ub - 1) & 1);
                 tc_fence_after();
                 const uint32_t d = tmem + (uint32_t)b * n_pad;
-                for (int c = 0; c < nch; ++c, ++it) {
-                    const int s = it % S;
-                    mbar_wait(bar_full + 8 * s, (uint32_t)(it / S) & 1);
+                for (int c = 0; c < nch; ++c) {
+                    mbar_wait(bar_full + 8 * s, s_par);
                     tc_fence_after();
                     const uint32_t a_lo = ((sbase + off_ring + (uint32_t)s * stage_bytes) & 0x3FFFF) >> 4;
                     const uint32_t b_lo = ((sbase + (uint32_t)c * A.tile_w_bytes) & 0x3FFFF) >> 4;
@@ -237,79 +240,91 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
                         if (c == nch - 1) umma_commit(bar_acc_full + 8 * b);
                     }
                     __syncwarp();
+                    if (++s == S) { s = 0; s_par ^= 1; }
                 }
+                if (++b == G) { b = 0; ++ub; }
             }
         }
     } else {
-        // ------------------------------------------------------------------------------------ epilogue warps
-        // With ~190 KB of resident weights + ring only ONE CTA fits an SM, so nothing overlaps a tile's epilogue except the next tile's loads
-        // and MMAs: eight warps (two per TMEM lane quarter, each taking every second 16-column unit) instead of pwconv's four halve it
-        // (measured: 56.7 -> see profiles/r02_conv3x3_halo.json at 64 -> 64 @ 80 x 80, batch 64).
-        const int q = warp & 3, row = q * 32 + lane, et = tid - 64, half = (warp - 2) >> 2;
+        // ------------------------------------------------------------------------------------ epilogue groups
+        // A tile's epilogue is a latency chain (accumulator wait -> tcgen05.ld -> bias / SiLU -> pack -> staging -> TMA stores), and with resident
+        // weights + ring only ONE CTA fits an SM, so nothing else hides it: ncu of the eight-warp, one-tile-at-a-time form showed the tensor pipe
+        // 31 % active and the epilogue warps 37 % of their time at their barrier (profiles/r02f_ncu_halo_*.txt).  Hence G independent groups of four
+        // warps (one per TMEM lane quarter), group g owning accumulator g and the tiles tl = g (mod G): up to G tiles' epilogues are in flight.
+        const int g = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane, gw = (warp - 2) & 3;
         const int rbo = ob * 2;
         const uint32_t swz = ((uint32_t)(row * rbo) >> 7) & (uint32_t)(rbo / 16 - 1);
+        const bool store_leader = gw == 0 && elect_one();   // issues (and therefore tracks) this group's TMA stores
+        const uint32_t bar_id = 1 + g;
         int sub = 0;
-        for (int tl = 0; tl < my_tiles; ++tl) {
-            const int b = tl & 1, bb = b;  // double-buffered TMEM accumulator and its barrier pair
-            const int64_t tile = first + (int64_t)tl * gridDim.x;
-            const int img = (int)(tile / per_img), r = (int)(tile % per_img);
-            const int y0 = (r / A.tiles_x) * kTH, x0 = (r % A.tiles_x) * kTW;
-            mbar_wait(bar_acc_full + 8 * bb, (uint32_t)(tl >> 1) & 1);
+        uint32_t use = 0;
+        for (int tl = g; tl < my_tiles; tl += G, ++use) {
+            mbar_wait(bar_acc_full + 8 * g, use & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem + (uint32_t)b * n_pad + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem + (uint32_t)g * n_pad + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < N; c0 += ob, ++sub) {
-                const uint32_t stg = sbase + off_stage + (uint32_t)(sub & 1) * staging_bytes;
-                if (et == 0) bulk_wait_read<1>();  // the stores that last read this staging buffer (two uses ago) are done with it
-                epi_barrier();
-                // this warp's 16-column units of the store box: half, half + 2 (ob = 64), or just `half` (ob = 32); ob = 16: unit 0 by half 0
-                uint32_t v[2][16];
-                const int u0 = half, u1 = half + 2, nu = ob / 16;
-                if (u0 < nu) tmem_ld16_nowait(taddr + c0 + 16 * u0, v[0]);
-                if (u1 < nu) tmem_ld16_nowait(taddr + c0 + 16 * u1, v[1]);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t stg = sbase + off_stage + (uint32_t)(g * nstg + (nstg == 2 ? (sub & 1) : 0)) * staging_bytes;
+                // the stores that last read this staging tile must be done with it: one tile per group -> all of the group's earlier stores;
+                // two tiles per group -> all but the latest commit
+                if (store_leader) { if (nstg == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                const int jmax = min(ob, n_pad - c0);
+                for (int j0 = 0; j0 < jmax; j0 += 32) {  // two 16-column TMEM loads in flight per wait
+                    uint32_t v[2][16];
+                    tmem_ld16_nowait(taddr + c0 + j0, v[0]);
+                    if (j0 + 16 < jmax) tmem_ld16_nowait(taddr + c0 + j0 + 16, v[1]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const int u = jj ? u1 : u0;
-                    if (u >= nu) break;
-                    const int j = 16 * u;
-                    float f[16];
-                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0 + j);
+                    for (int jj = 0; jj < 2; ++jj) {
+                        if (j0 + jj * 16 >= jmax) break;
+                        const int j = j0 + jj * 16;
+                        float f[16];
+                        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0 + j);
 #pragma unroll
-                    for (int e4 = 0; e4 < 4; ++e4) {
-                        const float4 bb = b4[e4];
-                        f[4 * e4] = __uint_as_float(v[jj][4 * e4]) + bb.x; f[4 * e4 + 1] = __uint_as_float(v[jj][4 * e4 + 1]) + bb.y;
-                        f[4 * e4 + 2] = __uint_as_float(v[jj][4 * e4 + 2]) + bb.z; f[4 * e4 + 3] = __uint_as_float(v[jj][4 * e4 + 3]) + bb.w;
+                        for (int e4 = 0; e4 < 4; ++e4) {
+                            const float4 bb = b4[e4];
+                            f[4 * e4] = __uint_as_float(v[jj][4 * e4]) + bb.x; f[4 * e4 + 1] = __uint_as_float(v[jj][4 * e4 + 1]) + bb.y;
+                            f[4 * e4 + 2] = __uint_as_float(v[jj][4 * e4 + 2]) + bb.z; f[4 * e4 + 3] = __uint_as_float(v[jj][4 * e4 + 3]) + bb.w;
+                        }
+                        if (ACT == 1) {  // SiLU: x * sigmoid(x) = h + h * tanh(h), h = x / 2
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) { const float h = 0.5f * f[e]; f[e] = fmaf(h, tanh_fast(h), h); }
+                        } else if (ACT == 2) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 o;
+                            o.x = pack2<T>(f[8 * h], f[8 * h + 1]); o.y = pack2<T>(f[8 * h + 2], f[8 * h + 3]);
+                            o.z = pack2<T>(f[8 * h + 4], f[8 * h + 5]); o.w = pack2<T>(f[8 * h + 6], f[8 * h + 7]);
+                            const uint32_t chunk = (uint32_t)(j / 8 + h) ^ swz;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)row * rbo + chunk * 16), "r"(o.x), "r"(o.y),
+                                         "r"(o.z), "r"(o.w)
+                                         : "memory");
+                        }
                     }
-                    if (ACT == 1) {  // SiLU: x * sigmoid(x) = h + h * tanh(h), h = x / 2
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) { const float h = 0.5f * f[e]; f[e] = fmaf(h, tanh_fast(h), h); }
-                    } else if (ACT == 2) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) f[e] = fmaxf(f[e], 0.f);
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint4 o;
-                        o.x = pack2<T>(f[8 * h], f[8 * h + 1]); o.y = pack2<T>(f[8 * h + 2], f[8 * h + 3]);
-                        o.z = pack2<T>(f[8 * h + 4], f[8 * h + 5]); o.w = pack2<T>(f[8 * h + 6], f[8 * h + 7]);
-                        const uint32_t chunk = (uint32_t)(j / 8 + h) ^ swz;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)row * rbo + chunk * 16), "r"(o.x), "r"(o.y),
-                                     "r"(o.z), "r"(o.w)
-                                     : "memory");
-                    }
+                }
+                if (c0 + ob >= N) {  // last box of the tile: the accumulator has been read completely
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_empty + 8 * g);
                 }
                 proxy_fence();
-                epi_barrier();
-                if (et == 0) {  // one store per output row of the tile: 14 of its 16 accumulator rows; rows / columns past the image are clipped
-                    for (int oy = 0; oy < kTH; ++oy)
-                        if (y0 + oy < A.H) tma_store_4d(&A.out_map, c0, x0, y0 + oy, img, stg + (uint32_t)(oy * kPitch) * rbo);
-                    bulk_commit();
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (gw == 0) {  // one store per output row of the tile: 14 of its 16 accumulator rows; rows / columns past the image are clipped
+                    const int64_t tile = first + (int64_t)tl * gridDim.x;
+                    const int img = (int)(tile / per_img), r = (int)(tile % per_img);
+                    const int y0 = (r / A.tiles_x) * kTH, x0 = (r % A.tiles_x) * kTW;
+                    if (store_leader) {
+                        for (int oy = 0; oy < kTH; ++oy)
+                            if (y0 + oy < A.H) tma_store_4d(&A.out_map, c0, x0, y0 + oy, img, stg + (uint32_t)(oy * kPitch) * rbo);
+                        bulk_commit();
+                    }
+                    __syncwarp();
                 }
             }
-            tc_fence_before();
-            mbar_arrive(bar_acc_empty + 8 * bb);
         }
-        if (et == 0) bulk_wait_read<0>();
+        if (store_leader) bulk_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -343,21 +358,36 @@ static bool make_map4(CUtensorMap* map, const void* base, int channels, int W, i
               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// shared-memory plan: returns the ring depth (0 = does not fit) for a site
-static int plan(int C, int N, int& n_pad, int& ob, uint32_t& w_bytes, uint32_t& tile_w_bytes, size_t& smem) {
+// shared-memory / TMEM plan of a site: returns the ring depth (0 = does not fit).  groups = epilogue groups = TMEM accumulators: the most (<= 4)
+// whose staging tiles still leave a ring of three stages, else two (accumulator double buffering, as before).
+static int plan(int C, int N, int& n_pad, int& ob, uint32_t& w_bytes, uint32_t& tile_w_bytes, int& groups, int& nstg, uint32_t& tmem_cols, size_t& smem) {
     n_pad = (int)ceil_div(N, 16) * 16;
     tile_w_bytes = ((uint32_t)n_pad * 128 + 1023u) & ~1023u;
     w_bytes = 9u * (uint32_t)(C / 64) * tile_w_bytes;
     ob = 64;
     while (ob > 16 && ob / 2 >= n_pad) ob >>= 1;
+    const int nstg_max = N > ob ? 2 : 1;   // several store boxes per tile: two staging tiles per group let box i + 1 be packed while box i is stored
     const uint32_t stage_bytes = (kStageBytes + 1023u) & ~1023u;
-    const size_t fixed = 1024 + ((w_bytes + 1023u) & ~1023u) + 2 * (size_t)128 * ob * 2 + (((size_t)(n_pad + 64) * 4 + 127) & ~(size_t)127) + 8 + 32 * kMaxGroup + 16 * kMaxStages + 16;
     const size_t budget = (size_t)227 * 1024;
-    if (fixed + 2 * stage_bytes > budget) return 0;
-    int S = (int)((budget - fixed) / stage_bytes);
-    if (S > kMaxStages) S = kMaxStages;
-    smem = fixed + (size_t)S * stage_bytes;
-    return S;
+    static const int g_max = [] { const char* v = getenv("EL_C3_GROUPS"); const int g = v ? atoi(v) : kMaxEpi; return g < 2 ? 2 : (g > kMaxEpi ? kMaxEpi : g); }();
+    for (int pass = 0; pass < 2; ++pass)   // second pass: one staging tile per group even with several boxes per tile (wide N, large weights)
+    for (int G = g_max; G >= 2; --G) {
+        nstg = pass == 0 ? nstg_max : 1;
+        if (pass == 1 && nstg_max == 1) break;
+        uint32_t cols = 32;
+        while (cols < (uint32_t)(G * n_pad)) cols <<= 1;
+        if (cols > 512) continue;
+        const size_t fixed = 1024 + ((w_bytes + 1023u) & ~1023u) + (size_t)(G * nstg) * 128 * ob * 2 + (((size_t)(n_pad + 64) * 4 + 127) & ~(size_t)127) + 8 +
+                             16 * kMaxEpi + 16 * kMaxStages + 16;
+        if (fixed + 2 * stage_bytes > budget) continue;
+        int S = (int)((budget - fixed) / stage_bytes);
+        if (S < 3 && G > 2) continue;
+        if (S > kMaxStages) S = kMaxStages;
+        groups = G; tmem_cols = cols;
+        smem = fixed + (size_t)S * stage_bytes;
+        return S;
+    }
+    return 0;
 }
 
 }  // namespace c3
@@ -368,8 +398,8 @@ using namespace el;
 /* 1 if el_conv3x3_halo_fwd covers a (C_in, N) site: 16-bit, C_in a multiple of 64, N a multiple of 8 up to 256, nine weight tiles resident. */
 extern "C" int el_conv3x3_halo_ok(int C, int N) {
     if (C < 64 || C % 64 || N <= 0 || N % 8 || N > 256) return 0;
-    int n_pad, ob; uint32_t wb, tb; size_t smem;
-    return c3::plan(C, N, n_pad, ob, wb, tb, smem) >= 2 ? 1 : 0;
+    int n_pad, ob, groups, nstg; uint32_t wb, tb, cols; size_t smem;
+    return c3::plan(C, N, n_pad, ob, wb, tb, groups, nstg, cols, smem) >= 2 ? 1 : 0;
 }
 
 extern "C" int el_conv3x3_halo_fwd(const void* x, const int64_t xs_[4], int C, const void* wpk, const float* bias, void* out, const int64_t os_[4], int B,
@@ -381,16 +411,11 @@ extern "C" int el_conv3x3_halo_fwd(const void* x, const int64_t xs_[4], int C, c
         if (i != 1 && (xs_[i] % 8 || os_[i] % 8)) return EL_ERR_UNSUPPORTED;
     c3::Args A{};
     size_t smem = 0;
-    A.stages = c3::plan(C, N, A.n_pad, A.ob, A.w_bytes, A.tile_w_bytes, smem);
+    A.stages = c3::plan(C, N, A.n_pad, A.ob, A.w_bytes, A.tile_w_bytes, A.groups, A.nstg, A.tmem_cols, smem);
     if (A.stages < 2) return EL_ERR_UNSUPPORTED;
     A.wpk = wpk; A.bias = bias; A.B = B; A.H = H; A.W = W; A.N = N; A.chunks = C / 64; A.act = act;
     A.tiles_x = (int)ceil_div(W, c3::kTW); A.tiles_y = (int)ceil_div(H, c3::kTH);
     A.n_tiles = (int64_t)B * A.tiles_x * A.tiles_y;
-    A.group = 1;  // two accumulators: the epilogue of tile i overlaps the MMAs of tile i + 1
-    uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * A.n_pad)) cols <<= 1;
-    if (cols > 512) return EL_ERR_UNSUPPORTED;
-    A.tmem_cols = cols;
     if (!c3::make_map4(&A.src_map, x, C, W, H, B, xs_, 64, c3::kPitch, c3::kTH + 2, dtype)) return EL_ERR_CUDA;
     if (!c3::make_map4(&A.out_map, out, N, W, H, B, os_, A.ob, c3::kTW, 1, dtype)) return EL_ERR_CUDA;
     int64_t gx = kSMs < A.n_tiles ? kSMs : A.n_tiles;
@@ -399,7 +424,7 @@ extern "C" int el_conv3x3_halo_fwd(const void* x, const int64_t xs_[4], int C, c
 #define EL_C3_LAUNCH(TT, ACT)                                                                                                                  \
     {                                                                                                                                          \
         e = cudaFuncSetAttribute(c3::conv3x3_halo_kernel<TT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                   \
-        if (e == cudaSuccess) e = launch_pdl(c3::conv3x3_halo_kernel<TT, ACT>, dim3((unsigned)gx), dim3(c3::kThreads), smem, st, A);            \
+        if (e == cudaSuccess) e = launch_pdl(c3::conv3x3_halo_kernel<TT, ACT>, dim3((unsigned)gx), dim3(64 + 128 * A.groups), smem, st, A);            \
     }
     if (dtype == EL_BF16) {
         if (act == 0) EL_C3_LAUNCH(__nv_bfloat16, 0) else if (act == 1) EL_C3_LAUNCH(__nv_bfloat16, 1) else EL_C3_LAUNCH(__nv_bfloat16, 2)

@@ -113,19 +113,15 @@ def test_half_mode_through_yolo_api(api):
     per-op fp16 contract is tested in test_gpu_parity.py.  Here: the installed fp16 model must be at least as close to the fp32
     reference as the reference's own fp16 mode is (mean error of the dense decode output), and YOLO.predict(half=True) must run."""
     R, tmp = api
-    # Both arms' fp16 error depends on which algorithms cuDNN picks for the fp16 convolutions, and that is process-global state: the reference's
-    # trainer (utils/torch_utils.py:481-485 init_seeds(deterministic=True), run by earlier tests of the suite) leaves
-    # torch.use_deterministic_algorithms(True) + cudnn.deterministic = True behind, under which the reference's own fp16 error on this checkpoint
-    # moves between 0.37 and 0.64 px and the batched f_h call of the installed enhancer gets a worse algorithm (1.18 px; measured on a B200,
-    # gpurun_out/c46_*.log).  The comparison is made in cuDNN's default mode.
-    det, cdet = torch.are_deterministic_algorithms_enabled(), torch.backends.cudnn.deterministic
-    torch.use_deterministic_algorithms(False)
-    torch.backends.cudnn.deterministic = False
-    request_restore = lambda: (torch.use_deterministic_algorithms(det, warn_only=True), setattr(torch.backends.cudnn, "deterministic", cdet))
+    # Both arms' fp16 error depends on which algorithms cuDNN picks for the fp16 convolutions, and that depends on what the process ran before:
+    # on a B200 the reference's OWN fp16 error on this checkpoint came out as 0.365, 0.466 or 0.638 px depending on which other tests had run
+    # (gpurun_out/c46 / c48 / c49 logs: nine orderings), and after the whole of test_gpu_parity.py the installed arm's batched f_h call got a
+    # worse algorithm (1.18 px) with the library's kernels unchanged (0.368 px in every other ordering).  The dense comparison therefore runs
+    # both arms on PyTorch's native convolution kernels (cuDNN off): what differs between the arms is then only the library's kernels.
     m = R.build_yolo(tmp, trained=True)
     x = _images(8, seed=11)[0]
     net = m.model.to("cuda").eval()
-    with torch.no_grad():
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=False):
         y32, _ = net.float()(x.to("cuda"))
         y16_ref, _ = net.half()(x.to("cuda").half())
         with R.installed() as inst:
@@ -147,7 +143,6 @@ def test_half_mode_through_yolo_api(api):
     n_ref, n_el = sum(len(r.boxes) for r in res_ref16), sum(len(r.boxes) for r in res_el16)
     assert n_el > 0 and abs(n_el - n_ref) <= max(4, n_ref // 4), (n_el, n_ref)
     assert all(r.boxes.data.dtype == torch.float16 or r.boxes.data.dtype == torch.float32 for r in res_el16)
-    request_restore()
 
 
 def test_val_map_through_yolo_api(api):
