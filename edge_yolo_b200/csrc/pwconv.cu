@@ -22,6 +22,7 @@
 // Weights are pre-packed on the host into the same swizzled tiles and stay resident in shared memory (1-D bulk copies,
 // once per CTA).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -30,7 +31,7 @@
 namespace el {
 namespace pw {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // TMA warp, MMA warp, one or two epilogue groups of four warps (the launch uses 64 + 128 * groups)
 constexpr int kTileM = 128;
 constexpr int kMaxChunks = 40;
 constexpr int kMaxSrc = 4;
@@ -56,6 +57,7 @@ struct Args {
     int64_t M;
     int N, n_tile, ob;       // ob: channels per staging / store box (16, 32 or 64)
     int act, stages;
+    int groups;              // epilogue groups: 1 (several CTAs per SM hide each other's epilogue) or 2 (one CTA per SM: group g drains accumulator g, tiles alternate)
     uint32_t w_bytes, stage_bytes, tmem_cols;
     int stream_w;            // 1: weight tiles are not resident: each ring stage holds [A box | weight tile of the chunk] (wide K)
     uint32_t a_stage_bytes;  // stream_w: offset of the weight tile inside a stage
@@ -140,7 +142,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the four epilogue warps
+__device__ __forceinline__ void epi_barrier(int g) {  // the four warps of epilogue group g
+    if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {  // 32 lanes x 32 bit x 16 columns
     asm volatile(
@@ -174,8 +178,10 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 
-template <typename T, int ACT, int RES>  // RES: 0 none, 1 out = res + res_scale * act(.), 2 out = act(. + nearest-2x-upsampled addend)
-__global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_constant__ Args A) {
+// RES: 0 none, 1 out = res + res_scale * act(.), 2 out = act(. + nearest-2x-upsampled addend);  GROUPS: epilogue groups (threads = 64 + 128 * GROUPS).
+// The one-group form must keep four CTAs of 192 threads resident per SM (<= 80 registers): that co-residency is what hides its epilogue.
+template <typename T, int ACT, int RES, int GROUPS>
+__global__ void __launch_bounds__(64 + 128 * GROUPS, GROUPS == 1 ? 4 : 1) pwconv_tc_kernel(const __grid_constant__ Args A) {
     extern __shared__ __align__(1024) unsigned char sm_raw[];
     // dynamic shared memory is only guaranteed 16-byte aligned: round up to the 1024 B the 128-byte swizzle atoms need
     const uint32_t sbase = (smem_addr(sm_raw) + 1023u) & ~1023u;
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
     const uint32_t off_ring = A.stream_w ? 0u : ((A.w_bytes + 1023u) & ~1023u);
     const uint32_t off_stage = off_ring + (uint32_t)S * A.stage_bytes;
     const uint32_t staging_bytes = (uint32_t)kTileM * A.ob * 2;
-    const uint32_t off_bias = off_stage + 2 * staging_bytes;
+    const uint32_t off_bias = off_stage + 2 * (uint32_t)GROUPS * staging_bytes;
     const uint32_t off_bar = off_bias + (((uint32_t)(n_tile + 64) * 4 + 127) & ~127u);  // + 64: the last store box may overhang n_tile
     float* s_bias = reinterpret_cast<float*>(sm + off_bias);
     const uint32_t bar_w = sbase + off_bar;                  // weights landed
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
             for (uint32_t o = 0; o < A.w_bytes; o += 32768) bulk_g2s(sbase + o, wsrc + o, min(32768u, A.w_bytes - o), bar_w);
         }
     }
-    for (int i = tid; i < n_tile + 64; i += kThreads) s_bias[i] = (A.bias && n0 + i < A.N) ? __ldg(A.bias + n0 + i) : 0.f;
+    for (int i = tid; i < n_tile + 64; i += (int)blockDim.x) s_bias[i] = (A.bias && n0 + i < A.N) ? __ldg(A.bias + n0 + i) : 0.f;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(A.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -297,13 +303,15 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
         // ------------------------------------------------------------------------------------ epilogue warps
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;          // pixel row inside the tile
-        const int et = tid - 64;                // 0..127
+        const int g = (warp - 2) >> 2;          // epilogue group: owns accumulator g and the tiles tl = g (mod groups) when there are two
+        constexpr int G = GROUPS;
+        const int et = (tid - 64) & 127;        // 0..127 inside the group
         const int ob = A.ob, rbo = ob * 2;      // staging row bytes = swizzle span of the store box
         const uint32_t swz = ((uint32_t)(row * rbo) >> 7) & (uint32_t)(rbo / 16 - 1);
         const int n_real = min(n_tile, A.N - n0);
         int sub = 0;  // staging buffer use counter
-        for (int tl = 0; tl < my_tiles; ++tl) {
-            const int b = tl & 1;
+        for (int tl = g; tl < my_tiles; tl += G) {
+            const int b = tl & 1;   // one group: accumulators alternate; two groups: b == g
             const int64_t m0 = (first + (int64_t)tl * gridDim.x) * kTileM;
             mbar_wait(bar_acc_full + 8 * b, (uint32_t)(tl >> 1) & 1);
             tc_fence_after();
@@ -319,9 +327,9 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                 rrow = reinterpret_cast<const T*>(A.res) + ((bimg * (A.up_H / 2) + y / 2) * (A.up_W / 2) + x / 2) * A.res_pitch + n0;
             }
             for (int c0 = 0; c0 < n_real; c0 += ob, ++sub) {
-                const uint32_t stg = sbase + off_stage + (uint32_t)(sub & 1) * staging_bytes;
+                const uint32_t stg = sbase + off_stage + (uint32_t)(2 * g + (sub & 1)) * staging_bytes;
                 if (et == 0) bulk_wait_read<1>();  // the store that last read this staging buffer (two uses ago) is done with it
-                epi_barrier();
+                epi_barrier(g);
                 const int jmax = min(ob, ((n_real - c0) + 15) & ~15);  // the last box of an 80-channel conv holds 16 real columns: skip the other 48
                 for (int j0 = 0; j0 < jmax; j0 += 32) {  // two 16-column TMEM loads in flight per wait
                 uint32_t v[2][16];
@@ -379,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) pwconv_tc_kernel(const __grid_consta
                 }
                 }
                 proxy_fence();  // generic-proxy writes of the staging tile -> visible to the TMA store (async proxy)
-                epi_barrier();
+                epi_barrier(g);
                 if (et == 0) {
                     const int n = n0 + c0;
                     if (A.spatial) {
@@ -450,11 +458,15 @@ static inline int box_bytes_for(int channels) { return channels <= 16 ? 32 : (ch
 
 template <typename T>
 static cudaError_t launch(const Args& A, dim3 grid, size_t smem, int res_mode, cudaStream_t st) {
-#define EL_PW_LAUNCH(ACT, RES)                                                                                                          \
-    {                                                                                                                                   \
-        cudaError_t e = cudaFuncSetAttribute(pwconv_tc_kernel<T, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
-        if (e != cudaSuccess) return e;                                                                                                 \
-        return launch_pdl(pwconv_tc_kernel<T, ACT, RES>, grid, dim3(kThreads), smem, st, A);                                            \
+#define EL_PW_LAUNCH_G(ACT, RES, GR)                                                                                                         \
+    {                                                                                                                                        \
+        cudaError_t e = cudaFuncSetAttribute(pwconv_tc_kernel<T, ACT, RES, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);    \
+        if (e != cudaSuccess) return e;                                                                                                      \
+        return launch_pdl(pwconv_tc_kernel<T, ACT, RES, GR>, grid, dim3(64 + 128 * GR), smem, st, A);                                        \
+    }
+#define EL_PW_LAUNCH(ACT, RES)                                                                                                               \
+    {                                                                                                                                        \
+        if (A.groups == 2) EL_PW_LAUNCH_G(ACT, RES, 2) else EL_PW_LAUNCH_G(ACT, RES, 1)                                                      \
     }
 #define EL_PW_BY_ACT(RES)                                                                                                               \
     {                                                                                                                                   \
@@ -463,6 +475,7 @@ static cudaError_t launch(const Args& A, dim3 grid, size_t smem, int res_mode, c
     if (res_mode == 1) EL_PW_BY_ACT(1) else if (res_mode == 2) EL_PW_BY_ACT(2) else EL_PW_BY_ACT(0)
 #undef EL_PW_BY_ACT
 #undef EL_PW_LAUNCH
+#undef EL_PW_LAUNCH_G
 }
 
 }  // namespace pw
@@ -596,6 +609,18 @@ extern "C" int el_pwconv_fwd(int nsrc, const void* const src[], const int64_t sr
         else { fixed = fixed0; S = S0; per_sm = 1; }
     }
     if (S < 2) return EL_ERR_UNSUPPORTED;
+    // One CTA per SM (large resident weights): nothing overlaps a tile's epilogue latency chain but the next tile's loads and MMAs, so a second
+    // epilogue group (four more warps, its own pair of staging tiles, accumulator g for tiles tl = g mod 2) keeps two epilogues in flight --
+    // what made the 3x3 halo kernel 1.25x faster.  EL_PW_GROUPS=1 keeps the single group.
+    A.groups = 1;
+    static const int max_groups = [] { const char* v = getenv("EL_PW_GROUPS"); return v ? atoi(v) : 2; }();
+    if (per_sm == 1 && max_groups >= 2) {
+        const size_t fixed2 = fixed + 2 * (size_t)pw::kTileM * A.ob * 2;
+        const size_t budget = (size_t)227 * 1024 - 1024;
+        if (budget > fixed2 && (budget - fixed2) / A.stage_bytes >= 3 && ceil_div(M, pw::kTileM) * n_tiles >= 2 * kSMs) {
+            A.groups = 2; fixed = fixed2; S = (int)((budget - fixed2) / A.stage_bytes);
+        }
+    }
     if (S > pw::kMaxStages) S = pw::kMaxStages;
     A.stages = S;
     const size_t smem = fixed + (size_t)S * A.stage_bytes;
@@ -670,7 +695,7 @@ extern "C" int el_conv3x3_fwd(const void* x, const int64_t xs_[4], int C, const 
     if (ob < 16) return EL_ERR_UNSUPPORTED;
     A.ob = ob;
     A.wpk = wpk; A.bias = bias; A.res = nullptr; A.res_pitch = 0; A.res_scale = 1.f;
-    A.has_out2 = 0; A.split = N;
+    A.has_out2 = 0; A.split = N; A.groups = 1;
     A.M = M; A.N = N; A.act = act;
     uint32_t cols = 32;
     while (cols < 2u * A.n_tile) cols <<= 1;

@@ -459,12 +459,40 @@ def dsbottleneck_engine_forward(self, x, out=None):
     return self.cv2(self.cv1(x), out=out, residual=x if self.add else None)
 
 
+def _c3_cv12(self, x):
+    """cv1 and cv2 of a C3-style block read the same input: ONE GEMM over the stacked output channels with a split store (one launch
+    less per block on the 20 x 20 / 40 x 40 maps where a launch costs what the GEMM does).  Returns (conv, bias, act) or None."""
+    c1, c2 = self.cv1, self.cv2
+    if not (isinstance(x, torch.Tensor) and hasattr(c1, "el_bias") and hasattr(c2, "el_bias") and c1.el_act == c2.el_act
+            and c1.conv.kernel_size == c2.conv.kernel_size == (1, 1) and c1.conv.out_channels % 16 == 0 and c1.conv.in_channels == c2.conv.in_channels
+            and c1.conv.bias is None and c2.conv.bias is None):
+        return None
+    key = (_ver(c1.conv.weight), c1.conv.weight.data_ptr(), _ver(c2.conv.weight), c2.conv.weight.data_ptr(), x.device)
+    c = self.__dict__.get("el_cv12")
+    if c is None or c[0] != key:
+        conv = nn.Conv2d(c1.conv.in_channels, c1.conv.out_channels + c2.conv.out_channels, 1, bias=False).to(device=x.device, dtype=c1.conv.weight.dtype)
+        with torch.no_grad():
+            conv.weight.copy_(torch.cat([c1.conv.weight, c2.conv.weight], 0))
+        bias = torch.cat([_bias_on(c1, x), _bias_on(c2, x)]).contiguous()
+        c = (key, conv.requires_grad_(False), bias)
+        self.__dict__["el_cv12"] = c  # not a registered submodule: the state dict keeps the reference's keys
+    return c[1], c[2], c1.el_act
+
+
 def dsc3k_engine_forward(self, x, out=None):
-    """C3.forward (block.py:394-396) for DSC3k: cv3 reads both branches in place (concat folded into its K loop)."""
-    cur = self.cv1(x)
+    """C3.forward (block.py:394-396) for DSC3k: cv1 | cv2 as one GEMM with a split store, cv3 reads both branches in place (concat folded
+    into its K loop)."""
+    m12 = _c3_cv12(self, x)
+    if m12 is not None and _pw_ok(m12[0], [x]):
+        B, _, H, W = x.shape
+        cur = torch.empty((B, self.cv1.conv.out_channels, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        other = torch.empty((B, self.cv2.conv.out_channels, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        pw_apply(m12[0], [x], m12[1], m12[2], out=cur, out2=other)
+    else:
+        cur, other = self.cv1(x), self.cv2(x)
     for blk in self.m:
         cur = blk(cur)
-    return self.cv3([cur, self.cv2(x)], out=out)
+    return self.cv3([cur, other], out=out)
 
 
 def dsc3k2_wavelet_engine_forward(self, x):
