@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_cons
     constexpr uint32_t kStage = kHalo * kHalo * kPitch;           // bytes per staged tile
     constexpr int kCpp = C / 8;                                   // 16-byte chunks per pixel
     constexpr int kChunks = kHalo * kHalo * kCpp;
+    constexpr int kNS = S == 1 ? 3 : 2;                           // staged tiles per CTA
     extern __shared__ __align__(16) unsigned char sm[];
     T* s_wf = reinterpret_cast<T*>(sm);                           // B fragments: [tap][kc][nt][lane][4]
     constexpr uint32_t kWfBytes = 9 * KC * NT * 32 * 4 * 2;
@@ -136,7 +137,12 @@ __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_cons
         cp_async_commit();
     };
     const int64_t first = blockIdx.x, stride = gridDim.x;
-    if (first < A.n_tiles) stage_tile(first, 0); else cp_async_commit();
+    // ring of kNS staged tiles, kNS - 1 of them in flight ahead of the one being computed: with one tile of look-ahead the kernel moved
+    // (CTAs per SM) x one tile per memory latency, i.e. ~2 TB/s whatever else was tuned
+#pragma unroll
+    for (int p = 0; p < kNS - 1; ++p) {
+        if (first + p * stride < A.n_tiles) stage_tile(first + p * stride, p); else cp_async_commit();
+    }
     // per-lane ldmatrix row: matrix (lane >> 3) = [pixels 0-7 | 8-15] x [k 0-7 | 8-15], row (lane & 7)
     const uint32_t a_lane = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * S) * kPitch + (uint32_t)(lane >> 4) * 16;
     const int g = lane >> 2, t4 = lane & 3;
@@ -151,9 +157,9 @@ __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_cons
     }
     int it = 0;
     for (int64_t tile = first; tile < A.n_tiles; tile += stride, ++it) {
-        const int buf = it & 1;
-        if (tile + stride < A.n_tiles) stage_tile(tile + stride, buf ^ 1); else cp_async_commit();
-        cp_async_wait<1>();
+        const int buf = it % kNS;
+        if (tile + (kNS - 1) * stride < A.n_tiles) stage_tile(tile + (kNS - 1) * stride, (it + kNS - 1) % kNS); else cp_async_commit();
+        cp_async_wait<kNS - 1>();
         __syncthreads();  // this tile's pixels (every thread's copies) and, first time round, the weight fragments are visible
         const int img = (int)(tile / per_img), r = (int)(tile - (int64_t)img * per_img);
         const int y0 = (r / A.tiles_x) * kTile, x0 = (r % A.tiles_x) * kTile;
@@ -208,13 +214,19 @@ __global__ void __launch_bounds__(kThreads) conv3x3_mma_kernel(const __grid_cons
 template <typename T, int KC, int NT, int S>
 static cudaError_t launch(const Args& A, cudaStream_t st) {
     constexpr int C = 16 * KC, N = 8 * NT, kHalo = (kTile - 1) * S + 3;
-    const size_t smem = (size_t)9 * KC * NT * 32 * 4 * 2 + ((N * 4 + 15) & ~15) + 2 * (size_t)kHalo * kHalo * (C * 2 + 16);
+    const size_t smem = (size_t)9 * KC * NT * 32 * 4 * 2 + ((N * 4 + 15) & ~15) + (size_t)(S == 1 ? 3 : 2) * kHalo * kHalo * (C * 2 + 16);
     auto kern = conv3x3_mma_kernel<T, KC, NT, S>;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    int64_t grid = (int64_t)kSMs * (smem > 100 * 1024 ? 2 : 4);
+    // resident CTAs per SM: by shared memory and by registers (the occupancy query knows both); more CTAs than that would run as a second wave
+    static const int per_sm = [&] {  // one query per instantiation (shared memory is a compile-time constant of it)
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, smem) != cudaSuccess || n < 1) n = 1;
+        return n > 4 ? 4 : n;
+    }();
+    int64_t grid = (int64_t)kSMs * per_sm;
     if (grid > A.n_tiles) grid = A.n_tiles;
     return launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem, st, A);
 }

@@ -30,7 +30,9 @@ namespace ds {
 constexpr int kTW = 20, kTH = 6, kRT = 3;     // output tile (120 of the 128 accumulator rows), rows per depthwise thread
 constexpr int kPW = kTW + 2, kPH = kTH + 2;   // patch = tile + halo
 constexpr int kDwThreads = 320;               // (<= 8 channel vectors) x 20 columns x 2 strips
-constexpr int kThreads = 192 + kDwThreads;    // TMA warp, MMA warp, 4 epilogue warps, 10 depthwise warps
+constexpr int kEpiGroups = 2;                 // epilogue groups of four warps; group g drains accumulator g (tiles alternate)
+constexpr int kEpiThreads = 128 * kEpiGroups;
+constexpr int kThreads = 64 + kEpiThreads + kDwThreads;    // TMA warp, MMA warp, 8 epilogue warps, 10 depthwise warps
 constexpr int kMaxSP = 6, kMaxSA = 4;
 
 struct Args {
@@ -106,7 +108,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the four epilogue warps
+__device__ __forceinline__ void epi_barrier(int g) {  // the four warps of epilogue group g
+    if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -138,6 +142,58 @@ __device__ __forceinline__ float silu_tanh(float v) {  // x * sigmoid(x) = h + h
     return fmaf(h, t, h);
 }
 
+// Depthwise 3 x 3 of RT vertically adjacent outputs of one channel vector (8 channels): (RT + 2) x 3 LDS.128 of the staged patch, 9 * RT * 4 packed
+// fp32x2 FMAs in the evaluation order of dwconv3_tma_kernel (kx outer, ky inner, bias first), optional activation, one rounding to T.
+template <typename T, int RT>
+__device__ __forceinline__ void dw3_strip(uint32_t base, uint32_t row_pitch, uint32_t kx_pitch, const float* s_dw, const float* s_dwb, int Cpad, int ch,
+                                          bool silu, bool relu, uint4 (&o)[RT]) {
+    constexpr int V = 8;
+    f32x2 acc[RT][V / 2];
+    {
+        const float4 b0 = *reinterpret_cast<const float4*>(s_dwb + ch), b1 = *reinterpret_cast<const float4*>(s_dwb + ch + 4);
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            acc[r][0] = pack_f32x2(b0.x, b0.y); acc[r][1] = pack_f32x2(b0.z, b0.w);
+            acc[r][2] = pack_f32x2(b1.x, b1.y); acc[r][3] = pack_f32x2(b1.z, b1.w);
+        }
+    }
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+        f32x2 v[RT + 2][V / 2];
+#pragma unroll
+        for (int j = 0; j < RT + 2; ++j) {
+            float f[V];
+            unpack<T>(lds128(base + (uint32_t)j * row_pitch + (uint32_t)kx * kx_pitch), f);
+#pragma unroll
+            for (int e = 0; e < V / 2; ++e) v[j][e] = pack_f32x2(f[2 * e], f[2 * e + 1]);
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const float4 w0 = *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cpad + ch);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cpad + ch + 4);
+            const f32x2 w2[V / 2] = {pack_f32x2(w0.x, w0.y), pack_f32x2(w0.z, w0.w), pack_f32x2(w1.x, w1.y), pack_f32x2(w1.z, w1.w)};
+#pragma unroll
+            for (int r = 0; r < RT; ++r)
+#pragma unroll
+                for (int e = 0; e < V / 2; ++e) acc[r][e] = fma_f32x2(v[r + ky][e], w2[e], acc[r][e]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        float f[V];
+#pragma unroll
+        for (int e = 0; e < V / 2; ++e) unpack_f32x2(acc[r][e], f[2 * e], f[2 * e + 1]);
+        if (silu) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) f[e] = silu_tanh(f[e]);
+        } else if (relu) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) f[e] = fmaxf(f[e], 0.f);
+        }
+        o[r] = pack<T>(f);
+    }
+}
+
 template <typename T, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) dsconv3_tc_kernel(const __grid_constant__ Args A) {
     extern __shared__ __align__(1024) unsigned char sm_raw[];
@@ -150,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) dsconv3_tc_kernel(const __grid_co
     const uint32_t off_a = (A.w_bytes + 1023u) & ~1023u;
     const uint32_t off_stage = off_a + (uint32_t)SA * A.a_bytes;
     const uint32_t staging_bytes = 128u * ob * 2;
-    const uint32_t off_patch = off_stage + 2 * staging_bytes;
+    const uint32_t off_patch = off_stage + 2 * kEpiGroups * staging_bytes;
     const uint32_t off_dw = off_patch + (uint32_t)SP * A.patch_bytes;
     float* s_dw = reinterpret_cast<float*>(sm + off_dw);   // [9][Cpad], zero past C
     float* s_dwb = s_dw + 9 * Cpad;                        // [Cpad]
@@ -189,6 +245,9 @@ __global__ void __launch_bounds__(kThreads, 1) dsconv3_tc_kernel(const __grid_co
     }
     for (int i = tid; i < Cpad; i += kThreads) s_dwb[i] = (A.dw_bias && i < A.C) ? __ldg(A.dw_bias + i) : 0.f;
     for (int i = tid; i < n_pad + 64; i += kThreads) s_bias[i] = (A.bias && i < A.N) ? __ldg(A.bias + i) : 0.f;
+    // the A tiles start as zeros: the columns a partial last chunk never writes and the rows 120..127 must hold finite numbers
+    for (uint32_t o = (uint32_t)tid * 16; o < (uint32_t)SA * A.a_bytes; o += kThreads * 16) sts128(sbase + off_a + o, make_uint4(0, 0, 0, 0));
+    proxy_fence();
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(A.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -248,13 +307,15 @@ __global__ void __launch_bounds__(kThreads, 1) dsconv3_tc_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + 4 * kEpiGroups) {
         // ------------------------------------------------------------------------------------ epilogue warps
-        const int q = warp & 3, row = q * 32 + lane, et = tid - 64;
+        // two groups of four warps, group g owning accumulator g and the tiles tl = g (mod 2): a tile's epilogue is a latency chain, and with one
+        // CTA per SM only another tile's epilogue can overlap it (the 3x3 halo kernel gained 1.25x from the same split)
+        const int g = (warp - 2) >> 2, q = warp & 3, row = q * 32 + lane, et = (tid - 64) & 127;
         const int rbo = ob * 2;
         const uint32_t swz = ((uint32_t)(row * rbo) >> 7) & (uint32_t)(rbo / 16 - 1);
         int sub = 0;
-        for (int tl = 0; tl < my_tiles; ++tl) {
+        for (int tl = g; tl < my_tiles; tl += kEpiGroups) {
             const int b = tl & 1;
             const int64_t tile = first + (int64_t)tl * gridDim.x;
             const int img = (int)(tile / per_img), r = (int)(tile % per_img);
@@ -263,9 +324,9 @@ __global__ void __launch_bounds__(kThreads, 1) dsconv3_tc_kernel(const __grid_co
             tc_fence_after();
             const uint32_t taddr = tmem + (uint32_t)b * n_pad + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < A.N; c0 += ob, ++sub) {
-                const uint32_t stg = sbase + off_stage + (uint32_t)(sub & 1) * staging_bytes;
+                const uint32_t stg = sbase + off_stage + (uint32_t)(2 * g + (sub & 1)) * staging_bytes;
                 if (et == 0) bulk_wait_read<1>();  // the store that last read this staging buffer (two uses ago) is done with it
-                epi_barrier();
+                epi_barrier(g);
                 const int jmax = min(ob, n_pad - c0);  // the last box of an 80-channel conv holds 16 real columns: skip the other 48
                 for (int j0 = 0; j0 < jmax; j0 += 32) {  // two 16-column TMEM loads in flight per wait
                     uint32_t v[2][16];
@@ -301,95 +362,74 @@ __global__ void __launch_bounds__(kThreads, 1) dsconv3_tc_kernel(const __grid_co
                         }
                     }
                 }
+                if (c0 + ob >= A.N) {  // last box: the accumulator has been read completely
+                    tc_fence_before();
+                    mbar_arrive(bar_acc_empty + 8 * b);
+                }
                 proxy_fence();  // generic-proxy writes of the staging tile -> visible to the TMA store (async proxy)
-                epi_barrier();
+                epi_barrier(g);
                 if (et == 0) {  // rows 0..119 of the staging tile are the 20 x 6 box; rows / columns past the image are clipped
                     tma_store_4d(&A.out_map, c0, x0, y0, img, stg);
                     bulk_commit();
                 }
             }
-            tc_fence_before();
-            mbar_arrive(bar_acc_empty + 8 * b);
         }
         if (et == 0) bulk_wait_read<0>();
     } else {
         // ------------------------------------------------------------------------------------ depthwise producers
         constexpr int V = 8;
-        const int dt = tid - 192;
+        const int dt = tid - (64 + kEpiThreads);
         const int CVL = 1 << A.cvl_shift;
         const int cvl = dt & (CVL - 1), rest = dt >> A.cvl_shift;
         const int xl = rest % kTW, strip = rest / kTW;
         const bool active = strip < kTH / kRT;     // narrow chunks (16 / 32 channels) leave the upper warps without work: they only keep the barrier counts
-        const uint32_t row_pitch = (uint32_t)kPW * CVL * 16;
+        const uint32_t row_pitch = (uint32_t)kPW * CVL * 16, kx_pitch = (uint32_t)CVL * 16;
         const uint32_t my_off = (uint32_t)(strip * kRT) * row_pitch + (uint32_t)(xl * CVL + cvl) * 16;
         const int m0 = strip * kRT * kTW + xl;     // A-tile row of this thread's first output pixel
+        // A partial last chunk (80 channels: 64 + 16) has nv < 8 real channel vectors.  Mapping its work like a full chunk would leave 8 - nv of every
+        // 8 lanes computing zeros for a whole chunk's time; instead thread <-> (vector < nv, column, ONE row), so the chunk costs nv / 8 of a full one
+        // spread over all warps.  Its unwritten A columns keep whatever finite values an earlier chunk (or the zero fill at kernel start) left
+        // there: they meet zero weight columns.
+        const int nv = (A.C - (nch - 1) * CB) / V;              // real vectors of the last chunk (== CVL when C is a multiple of the chunk)
+        const bool tail_remap = nv < CVL;
+        const int t_cv = dt % nv, t_rest = dt / nv, t_xl = t_rest % kTW, t_ly = t_rest / kTW;
+        const bool t_active = t_ly < kTH;
+        const uint32_t t_off = (uint32_t)t_ly * row_pitch + (uint32_t)(t_xl * CVL + t_cv) * 16;
+        const int t_m = t_ly * kTW + t_xl;
         const bool dw_silu = A.dw_act == 1, dw_relu = A.dw_act == 2;
         int s = 0, a = 0;
         uint32_t p_par = 0, a_par = 1;   // parities: patch use, and the A slot's PREVIOUS use (what its empty barrier is waited on)
         bool a_wrapped = false;
         for (int tl = 0; tl < my_tiles; ++tl) {
             for (int c = 0; c < nch; ++c) {
-                const int ch = c * CB + cvl * V;
+                const bool tail = tail_remap && c == nch - 1;
                 mbar_wait(bar_pfull + 8 * s, p_par);
+                const uint32_t pbase = sbase + off_patch + (uint32_t)s * A.patch_bytes;
                 uint4 o[kRT];
-                if (active) {
-                    const uint32_t base = sbase + off_patch + (uint32_t)s * A.patch_bytes + my_off;
-                    f32x2 acc[kRT][V / 2];
-                    {
-                        const float4 b0 = *reinterpret_cast<const float4*>(s_dwb + ch), b1 = *reinterpret_cast<const float4*>(s_dwb + ch + 4);
-#pragma unroll
-                        for (int r = 0; r < kRT; ++r) {
-                            acc[r][0] = pack_f32x2(b0.x, b0.y); acc[r][1] = pack_f32x2(b0.z, b0.w);
-                            acc[r][2] = pack_f32x2(b1.x, b1.y); acc[r][3] = pack_f32x2(b1.z, b1.w);
-                        }
-                    }
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        f32x2 v[kRT + 2][V / 2];
-#pragma unroll
-                        for (int j = 0; j < kRT + 2; ++j) {
-                            float f[V];
-                            unpack<T>(lds128(base + (uint32_t)j * row_pitch + (uint32_t)(kx * CVL) * 16), f);
-#pragma unroll
-                            for (int e = 0; e < V / 2; ++e) v[j][e] = pack_f32x2(f[2 * e], f[2 * e + 1]);
-                        }
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            const float4 w0 = *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cpad + ch);
-                            const float4 w1 = *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cpad + ch + 4);
-                            const f32x2 w2[V / 2] = {pack_f32x2(w0.x, w0.y), pack_f32x2(w0.z, w0.w), pack_f32x2(w1.x, w1.y), pack_f32x2(w1.z, w1.w)};
-#pragma unroll
-                            for (int r = 0; r < kRT; ++r)
-#pragma unroll
-                                for (int e = 0; e < V / 2; ++e) acc[r][e] = fma_f32x2(v[r + ky][e], w2[e], acc[r][e]);
-                        }
-                    }
-#pragma unroll
-                    for (int r = 0; r < kRT; ++r) {
-                        float f[V];
-#pragma unroll
-                        for (int e = 0; e < V / 2; ++e) unpack_f32x2(acc[r][e], f[2 * e], f[2 * e + 1]);
-                        if (dw_silu) {
-#pragma unroll
-                            for (int e = 0; e < V; ++e) f[e] = silu_tanh(f[e]);
-                        } else if (dw_relu) {
-#pragma unroll
-                            for (int e = 0; e < V; ++e) f[e] = fmaxf(f[e], 0.f);
-                        }
-                        o[r] = pack<T>(f);
-                    }
+                if (!tail) {
+                    if (active) dw3_strip<T, kRT>(pbase + my_off, row_pitch, kx_pitch, s_dw, s_dwb, Cpad, c * CB + cvl * V, dw_silu, dw_relu, o);
+                } else if (t_active) {
+                    uint4 o1[1];
+                    dw3_strip<T, 1>(pbase + t_off, row_pitch, kx_pitch, s_dw, s_dwb, Cpad, c * CB + t_cv * V, dw_silu, dw_relu, o1);
+                    o[0] = o1[0];
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_pempty + 8 * s);  // this warp has read everything it needs from the patch
                 if (a_wrapped) mbar_wait(bar_aempty + 8 * a, a_par);
-                if (active) {
-                    const uint32_t a_base = sbase + off_a + (uint32_t)a * A.a_bytes;
+                const uint32_t a_base = sbase + off_a + (uint32_t)a * A.a_bytes;
+                if (!tail) {
+                    if (active) {
 #pragma unroll
-                    for (int r = 0; r < kRT; ++r) {
-                        const uint32_t m = (uint32_t)(m0 + r * kTW);
-                        const uint32_t sw = ((m * (uint32_t)rb) >> 7) & (uint32_t)(rb / 16 - 1);
-                        sts128(a_base + m * (uint32_t)rb + (((uint32_t)cvl ^ sw) << 4), o[r]);
+                        for (int r = 0; r < kRT; ++r) {
+                            const uint32_t m = (uint32_t)(m0 + r * kTW);
+                            const uint32_t sw = ((m * (uint32_t)rb) >> 7) & (uint32_t)(rb / 16 - 1);
+                            sts128(a_base + m * (uint32_t)rb + (((uint32_t)cvl ^ sw) << 4), o[r]);
+                        }
                     }
+                } else if (t_active) {
+                    const uint32_t m = (uint32_t)t_m;
+                    const uint32_t sw = ((m * (uint32_t)rb) >> 7) & (uint32_t)(rb / 16 - 1);
+                    sts128(a_base + m * (uint32_t)rb + (((uint32_t)t_cv ^ sw) << 4), o[0]);
                 }
                 proxy_fence();  // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -455,7 +495,7 @@ static bool plan(int C, int N, Args& A, size_t& smem) {
     while (ob0 > 16 && ob0 / 2 >= A.n_pad) ob0 >>= 1;
     const size_t budget = (size_t)227 * 1024;
     for (int ob = ob0; ob >= 16; ob >>= 1) {
-        const size_t fixed = 1024 + ((A.w_bytes + 1023u) & ~1023u) + 2 * (size_t)128 * ob * 2 + (size_t)(10 * Cpad + A.n_pad + 64) * 4 + 40 + 16 * kMaxSP +
+        const size_t fixed = 1024 + ((A.w_bytes + 1023u) & ~1023u) + 2 * kEpiGroups * (size_t)128 * ob * 2 + (size_t)(10 * Cpad + A.n_pad + 64) * 4 + 40 + 16 * kMaxSP +
                              16 * kMaxSA + 16;
         if (fixed + 2 * (size_t)A.a_bytes + 2 * (size_t)A.patch_bytes > budget) continue;
         size_t used = fixed + 2 * (size_t)A.a_bytes + 2 * (size_t)A.patch_bytes;

@@ -408,13 +408,15 @@ def dwconv_engine_forward(self, x, out=None, residual=None, out2=None):
 
 USE_DSCONV3 = True  # el_dsconv3_fwd: depthwise 3x3 -> pointwise 1x1 in one kernel (DSConv k = 3; DWConv -> Conv pairs of the class towers)
 DSCONV3_MIN_C = 32  # narrower sites stay on the two-kernel path
-DSCONV3_MAX_HW = int(__import__("os").environ.get("EL_DS3_MAX_HW", 1600))  # maps up to 40 x 40: where one launch instead of two is what pays (tools/prof_dsconv.py)
+DSCONV3_MAX_HW = int(__import__("os").environ.get("EL_DS3_MAX_HW", 1600))  # 16 / 32-channel sites: only maps up to 40 x 40, where one launch instead of two is
+# what pays; from 64 channels up the fused kernel wins or ties at every map (tools/prof_dsconv.py, profiles/r02f_prof_dsconv.jsonl)
+DSCONV3_WIDE_C = int(__import__("os").environ.get("EL_DS3_WIDE_C", 64))
 
 
 def _ds3_ok(dw: nn.Conv2d, pw: nn.Conv2d, x: torch.Tensor, out=None) -> bool:
     """el_dsconv3_fwd applies: depthwise 3x3 / stride 1 / padding 1 into a dense 1x1 conv, 16-bit NHWC views, no autograd."""
     C, N = dw.in_channels, pw.out_channels
-    if not (USE_DSCONV3 and C >= DSCONV3_MIN_C and x.shape[2] * x.shape[3] <= DSCONV3_MAX_HW and dw.kernel_size == (3, 3) and dw.stride == (1, 1) and dw.padding == (1, 1) and dw.dilation == (1, 1)
+    if not (USE_DSCONV3 and C >= DSCONV3_MIN_C and (C >= DSCONV3_WIDE_C or x.shape[2] * x.shape[3] <= DSCONV3_MAX_HW) and dw.kernel_size == (3, 3) and dw.stride == (1, 1) and dw.padding == (1, 1) and dw.dilation == (1, 1)
             and dw.groups == C == dw.out_channels and pw.kernel_size == (1, 1) and pw.stride == (1, 1) and pw.groups == 1 and pw.padding in ((0, 0), 0)
             and pw.in_channels == C and x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and not torch.is_grad_enabled()):
         return False
