@@ -44,6 +44,9 @@ class FakePredictor:
     def step_device(self):
         time.sleep(0.001)
 
+    def load_resident(self, src):
+        pass
+
     def drain(self):
         pass
 
