@@ -169,8 +169,9 @@ __device__ __forceinline__ void dw3_strip(uint32_t base, uint32_t row_pitch, uin
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            const float4 w0 = *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cpad + ch);
-            const float4 w1 = *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cpad + ch + 4);
+            // taps are stored [tap][half][vector][4]: the lanes of a warp (8 vectors) read 128 contiguous bytes per half (no bank conflict)
+            const float4 w0 = *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cpad + (ch >> 1));
+            const float4 w1 = *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cpad + (Cpad >> 1) + (ch >> 1));
             const f32x2 w2[V / 2] = {pack_f32x2(w0.x, w0.y), pack_f32x2(w0.z, w0.w), pack_f32x2(w1.x, w1.y), pack_f32x2(w1.z, w1.w)};
 #pragma unroll
             for (int r = 0; r < RT; ++r)
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) dsconv3_tc_kernel(const __grid_co
     const uint32_t staging_bytes = 128u * ob * 2;
     const uint32_t off_patch = off_stage + 2 * kEpiGroups * staging_bytes;
     const uint32_t off_dw = off_patch + (uint32_t)SP * A.patch_bytes;
-    float* s_dw = reinterpret_cast<float*>(sm + off_dw);   // [9][Cpad], zero past C
+    float* s_dw = reinterpret_cast<float*>(sm + off_dw);   // [9][2 halves][Cpad / 8 vectors][4], zero past C
     float* s_dwb = s_dw + 9 * Cpad;                        // [Cpad]
     float* s_bias = s_dwb + Cpad;                          // [n_pad + 64]: the last store box may overhang n_pad
     const uint32_t off_bar = off_dw + (uint32_t)(10 * Cpad + n_pad + 64) * 4;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) dsconv3_tc_kernel(const __grid_co
     }
     for (int i = tid; i < 9 * Cpad; i += kThreads) {
         const int tap = i / Cpad, c = i - tap * Cpad;
-        s_dw[i] = c < A.C ? __ldg(A.dw_w + tap * A.C + c) : 0.f;
+        s_dw[tap * Cpad + ((c >> 2) & 1) * (Cpad >> 1) + (c >> 3) * 4 + (c & 3)] = c < A.C ? __ldg(A.dw_w + tap * A.C + c) : 0.f;
     }
     for (int i = tid; i < Cpad; i += kThreads) s_dwb[i] = (A.dw_bias && i < A.C) ? __ldg(A.dw_bias + i) : 0.f;
     for (int i = tid; i < n_pad + 64; i += kThreads) s_bias[i] = (A.bias && i < A.N) ? __ldg(A.bias + i) : 0.f;
