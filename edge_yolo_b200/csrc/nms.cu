@@ -23,7 +23,7 @@ namespace el {
 
 constexpr int kSortChunk = 16384;  // keys sorted per CTA in shared memory (128 KiB)
 constexpr int kSortThreads = 1024;
-constexpr int kSweepThreads = 1024;
+constexpr int kSweepThreads = 512;    // 16 warps: half an SM's registers, so the forward graph's CTAs co-reside with a sweep CTA (the sweep runs beside the next forward)
 
 // ------------------------------------------------------------------------------- 1. emit
 template <bool MULTI>
