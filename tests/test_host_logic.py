@@ -99,3 +99,49 @@ def test_engine_fused_model_refuses_load_state_dict():
         pytest.skip("engine fuse needs the CUDA library's weight packing")
     with pytest.raises(RuntimeError, match="before fusing"):
         model.load_state_dict(state, strict=False)
+
+
+@torch.no_grad()
+def test_c3_cv12_stacks_the_two_entry_convs_of_dsc3k():
+    """`_c3_cv12` (engine: cv1 and cv2 of DSC3k read the same input, C3.forward block.py:394-396): the merged conv's output channels are
+    cv1's then cv2's, its bias the two folded-BatchNorm biases in the same order, so a split store at cv1's width reproduces both convs;
+    the merged conv is not a registered submodule (state-dict keys unchanged) and is rebuilt when a weight changes."""
+    from edge_yolo_b200 import modules as M
+
+    model = EdgeLineYOLO("n", 80).float().eval()
+    _randomise_bn(model, seed=3)
+    keys_before = set(model.state_dict().keys())
+    model.fuse(engine=True)
+    blocks = [m for m in model.modules() if isinstance(m, M.DSC3k)]
+    assert blocks
+    g = torch.Generator().manual_seed(2)
+    for blk in blocks:
+        x = torch.randn(2, blk.cv1.conv.in_channels, 6, 5, generator=g)
+        conv, bias, act = M._c3_cv12(blk, x)
+        c1 = blk.cv1.conv.out_channels
+        assert conv.out_channels == c1 + blk.cv2.conv.out_channels and bias.numel() == conv.out_channels and act == blk.cv1.el_act
+        y = torch.nn.functional.conv2d(x, conv.weight) + bias.view(1, -1, 1, 1)
+        want1 = torch.nn.functional.conv2d(x, blk.cv1.conv.weight) + blk.cv1.el_bias.view(1, -1, 1, 1)
+        want2 = torch.nn.functional.conv2d(x, blk.cv2.conv.weight) + blk.cv2.el_bias.view(1, -1, 1, 1)
+        torch.testing.assert_close(y[:, :c1], want1)
+        torch.testing.assert_close(y[:, c1:], want2)
+        assert M._c3_cv12(blk, x)[0] is conv                      # cached
+        blk.cv2.conv.weight.mul_(2.0)                             # in-place update -> new version -> repacked
+        conv2, _, _ = M._c3_cv12(blk, x)
+        assert conv2 is not conv
+        torch.testing.assert_close(conv2.weight[c1:], blk.cv2.conv.weight)
+    assert {k for k in model.state_dict().keys() if "el_cv12" in k} == set() and keys_before  # nothing new registered
+
+
+def test_dsconv3_weight_packing_is_the_single_tile_pwconv_packing():
+    """`pack_dsconv3_weight` = `pack_pw_weight` for one source of C channels with ONE output-channel tile of ceil16(N) rows (what
+    el_dsconv3_fwd keeps resident): per 64-channel chunk a tile of ceil16(N) x 128 bytes padded to 1 KiB; 16 / 32-channel inputs one narrow tile."""
+    for C, N in ((64, 64), (80, 80), (256, 80), (32, 32), (16, 8), (72, 40)):
+        w = torch.randn(N, C)
+        wpk = ops.pack_dsconv3_weight(w, torch.bfloat16)
+        n_pad = -(-N // 16) * 16
+        assert torch.equal(wpk, ops.pack_pw_weight(w, [C], torch.bfloat16, n_tile=n_pad))
+        rb = 32 if C <= 16 else (64 if C <= 32 else 128)
+        chunks = -(-C // (rb // 2))
+        tile = -(-(n_pad * rb) // 1024) * 1024
+        assert wpk.numel() * 2 == chunks * tile
