@@ -15,7 +15,8 @@
 //     swizzle is a function of the absolute shared-memory address, so the plain start-address shift (base_offset 0) addresses the rows
 //     TMA wrote -- verified on a B200 for exactly these shifts by tools/exp_umma_row_shift.cu (profiles/r02_exp_umma_row_shift.log);
 //   * weights: per (tap, chunk) one K-major SW128 tile [N][64], all resident in shared memory (9 * C_in * N * 2 B <= 144 KB);
-//   * warp roles as in pwconv.cu: TMA producer, MMA issuer (36 MMAs M128 x N x K16 per chunk), eight epilogue warps (tcgen05.ld, bias,
+//   * warp roles as in pwconv.cu: TMA producer, MMA issuer (36 MMAs M128 x N x K16 per chunk), two to four epilogue GROUPS of four warps, each
+//     with its own TMEM accumulator and staging tile, tiles round-robin (tcgen05.ld, bias,
 //     SiLU / ReLU, 16-bit pack into a swizzled staging tile, one TMA store per output row of the tile: box (channels, 14, 1, 1), clipped at
 //     the image border); double-buffered TMEM accumulators; persistent CTAs; PDL.
 #include <cuda.h>
@@ -108,7 +109,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the eight epilogue warps
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"

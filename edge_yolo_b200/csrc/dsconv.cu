@@ -7,16 +7,19 @@
 // Why: the depthwise output is written to HBM by one kernel and read back by the next (2 * B * C * H * W * e bytes and a launch per site;
 // the 17 k = 3 depthwise launches of EdgeLine-n cost ~0.3 ms of a 2.65 ms step, bench.py `kernels.dwconv`), although the GEMM that consumes it
 // only needs it as its A operand in shared memory.  Here the depthwise result never leaves the SM:
-//   warp 0 (one lane)   TMA producer: per (tile, 64-channel chunk) ONE 4-D box (channels, 22 x, 8 y, 1 image) = the 20 x 6 output tile + halo,
-//                       out-of-image pixels zero-filled by the TMA unit (= the convolution's padding), into a ring of patch stages;
-//   warps 6-15          depthwise producers: thread <-> (channel vector, output column, strip of 3 rows); 15 LDS.128 of the patch feed 27 taps as
+//   warp 0              TMA producer (one elected lane issues; the loop is warp-uniform): per (tile, 64-channel chunk) ONE 4-D box (channels, 22 x, 8 y,
+//                       1 image) = the 20 x 6 output tile + halo, out-of-image pixels zero-filled by the TMA unit (= the convolution's padding), into a
+//                       ring of patch stages;
+//   warps 10-19         depthwise producers: thread <-> (channel vector, output column, strip of 3 rows); 15 LDS.128 of the patch feed 27 taps as
 //                       packed fp32x2 FMAs (same evaluation order as dwconv3_tma_kernel), optional bias + SiLU, one rounding to the activation
 //                       type, and the 16-byte result goes straight into the K-major SWIZZLED A tile of the GEMM (row = pixel ly * 20 + lx,
-//                       chunk cv ^ swizzle(row)): what el_pwconv_fwd would have fetched by TMA; fence.proxy.async + mbarrier hand-over;
-//   warp 1 (one lane)   tcgen05.mma M128 x N x K16 from the A tile and the resident weight tiles, accumulators double buffered in TMEM;
-//   warps 2-5           epilogue as in pwconv.cu (tcgen05.ld, bias, SiLU / ReLU, 16-bit pack into a swizzled staging tile) and ONE 4-D TMA
-//                       store per 64 output channels: box (channels, 20 x, 6 y, 1 image), clipped at the image border.
-// Rows 120..127 of the A tile are never written and never stored (an MMA row only depends on its own A row).
+//                       chunk cv ^ swizzle(row)): what el_pwconv_fwd would have fetched by TMA; fence.proxy.async + mbarrier hand-over.
+//                       A partial last chunk (80 channels = 64 + 16) is mapped (vector, column, ONE row) over all warps;
+//   warp 1              tcgen05.mma M128 x N x K16 (elected lane) from the A tile and the resident weight tiles, accumulators double buffered in TMEM;
+//   warps 2-9           two epilogue groups of four warps (group g drains accumulator g, tiles alternate; as in conv3x3_halo.cu): tcgen05.ld, bias,
+//                       SiLU / ReLU, 16-bit pack into a swizzled staging tile, and ONE 4-D TMA store per 64 output channels: box (channels, 20 x,
+//                       6 y, 1 image), clipped at the image border.
+// Rows 120..127 of the A tile are never written (zero-filled once) and never stored (an MMA row only depends on its own A row).
 // Roofline: HBM, algorithmic bytes B * H * W * (C + N) * e (the depthwise tensor does not exist).
 #include <cuda.h>
 
