@@ -828,6 +828,42 @@ def test_conv3x3_halo(dtype, B, C, N, hw, act):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,src_c,N,hw,opts", [
+    (40, [64, 64, 64], 128, (40, 40), dict(act=1)),              # cv2 at P4 of the batch-64 graph: 48 KB of weights -> one CTA per SM, 500 tiles
+    (64, [128, 128, 128], 256, (20, 20), dict(act=1, res=True)),  # cv2 at P5: two output-channel tiles of 96 KB, shortcut in the epilogue
+    (64, [256], 256, (20, 20), dict(act=1, split=128)),           # cv1 at P5 with chunk(2, 1) destinations
+])
+def test_pwconv_two_epilogue_groups(dtype, B, src_c, N, hw, opts):
+    """The one-CTA-per-SM sites of the batch-64 graph (large resident weights, >= 2 tiles per CTA) run el_pwconv_fwd with TWO epilogue
+    groups (group g drains accumulator g, own staging tiles, tiles alternate): same contract as test_pwconv, at sizes that take that
+    path -- several tiles per persistent CTA, both groups busy, ragged last tile, residual / split-destination epilogues."""
+    o = ops()
+    gen = torch.Generator().manual_seed(sum(src_c) + N + B)
+    H, W = hw
+    cl = torch.channels_last
+    srcs = [torch.randn(B, c, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl) for c in src_c]
+    K = sum(src_c)
+    w = (torch.randn(N, K, generator=gen) * K ** -0.5).to(DEV)
+    bias = torch.randn(N, generator=gen).to(DEV)
+    res = torch.randn(B, N, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl) if opts.get("res") else None
+    want = torch.nn.functional.silu(torch.einsum("bkhw,nk->bnhw", torch.cat([t.float() for t in srcs], 1), w.to(dtype).float()) + bias.view(1, -1, 1, 1))
+    if res is not None:
+        want = res.float() + want
+    wpk = o.pack_pw_weight(w, src_c, dtype, B * H * W)
+    if opts.get("split"):
+        a = torch.empty(B, opts["split"], H, W, device=DEV, dtype=dtype).contiguous(memory_format=cl)
+        b = torch.empty(B, N - opts["split"], H, W, device=DEV, dtype=dtype).contiguous(memory_format=cl)
+        o.pwconv(srcs, wpk, N, bias=bias, act=o.ACT_SILU, out=a, out2=b)
+        got = torch.cat([a, b], 1)
+    else:
+        got = o.pwconv(srcs, wpk, N, bias=bias, act=o.ACT_SILU, residual=res)
+    close(got, want, 2e-2, 2e-2)
+    got2 = o.pwconv(srcs, wpk, N, bias=bias, act=o.ACT_SILU, residual=res) if not opts.get("split") else None  # second launch: barrier phases start over
+    if got2 is not None:
+        assert torch.equal(got, got2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("C1,C2,N,hw,split", [(256, 128, 128, (20, 20), 64), (128, 128, 64, (16, 24), 32), (64, 32, 48, (6, 10), 0)])
 def test_pwconv_upsample_concat(dtype, C1, C2, N, hw, split):
     """nn.Upsample(2, nearest) + Concat + 1x1 Conv + SiLU of the neck (yolo11-test.yaml:34-39, conv.py:58-60) as a low-resolution
