@@ -801,7 +801,8 @@ def test_conv3x3_mma(dtype, B, C, N, hw, act, stride):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("B,C,N,hw,act", [(2, 64, 64, (80, 80), 1), (3, 64, 32, (20, 20), 1), (2, 128, 64, (40, 40), 1), (1, 64, 64, (8, 14), 0), (2, 64, 48, (9, 15), 2),
-                                          (1, 64, 128, (29, 31), 1), (2, 128, 64, (10, 10), 1), (1, 64, 64, (3, 5), 1)])
+                                          (1, 64, 128, (29, 31), 1), (2, 128, 64, (10, 10), 1), (1, 64, 64, (3, 5), 1),
+                                          (24, 64, 64, (80, 80), 1), (40, 128, 64, (40, 40), 1), (30, 64, 128, (40, 40), 2)])  # ~10 / 4 / 3 tiles per CTA: every epilogue group, several rounds
 def test_conv3x3_halo(dtype, B, C, N, hw, act):
     """Wide dense 3x3 conv (stride 1, padding 1) from ONE haloed TMA tile per K chunk with row-shifted UMMA descriptors (el_conv3x3_halo_fwd)
     == Conv.forward_fuse (nn/modules/conv.py:58-60) on the same 16-bit-rounded operands: image borders (zero padding = TMA fill), ragged
