@@ -619,7 +619,8 @@ def test_dwconv3_tma_pipeline(dtype, shape, act):
 @pytest.mark.parametrize("shape,N,dw_epi,act", [((2, 64, 40, 40), 64, False, 1), ((3, 64, 20, 20), 64, False, 1), ((2, 64, 80, 80), 80, True, 1), ((2, 80, 40, 40), 80, True, 1),
                                                 ((1, 128, 40, 40), 80, True, 0), ((2, 256, 20, 20), 80, True, 1), ((2, 32, 80, 80), 32, False, 1), ((2, 16, 160, 160), 16, False, 2),
                                                 ((2, 64, 23, 37), 24, False, 1), ((1, 128, 7, 61), 128, True, 1), ((5, 32, 45, 19), 64, False, 1), ((70, 64, 20, 20), 64, False, 1),
-                                                ((1, 128, 26, 20), 256, False, 1), ((2, 72, 13, 21), 40, True, 2)])
+                                                ((1, 128, 26, 20), 256, False, 1), ((2, 72, 13, 21), 40, True, 2),
+                                                ((16, 64, 80, 80), 80, True, 1), ((20, 80, 40, 40), 80, True, 1)])  # 6 / 2 tiles per CTA: ring wrap, both epilogue groups, partial last chunk
 def test_dsconv3_fused(dtype, shape, N, dw_epi, act):
     """Depthwise 3x3 -> pointwise 1x1 in one kernel (el_dsconv3_fwd: DSConv.forward k = 3, nn/modules/conv.py:100-104; DWConv -> Conv of the class
     towers, head.py:66-71) against (1) the two-kernel path it replaces (el_dwconv_fwd -> el_pwconv_fwd: same depthwise evaluation order, same
