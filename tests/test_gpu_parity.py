@@ -834,6 +834,7 @@ def test_conv3x3_halo(dtype, B, C, N, hw, act):
     (40, [64, 64, 64], 128, (40, 40), dict(act=1)),              # cv2 at P4 of the batch-64 graph: 48 KB of weights -> one CTA per SM, 500 tiles
     (64, [128, 128, 128], 256, (20, 20), dict(act=1, res=True)),  # cv2 at P5: two output-channel tiles of 96 KB, shortcut in the epilogue
     (64, [256], 256, (20, 20), dict(act=1, split=128)),           # cv1 at P5 with chunk(2, 1) destinations
+    (24, [256], 256, (40, 40), dict(act=1, up=True)),             # neck cv1 of the wider scales: low-resolution addend read at (y / 2, x / 2) in the epilogue
 ])
 def test_pwconv_two_epilogue_groups(dtype, B, src_c, N, hw, opts):
     """The one-CTA-per-SM sites of the batch-64 graph (large resident weights, >= 2 tiles per CTA) run el_pwconv_fwd with TWO epilogue
@@ -848,10 +849,18 @@ def test_pwconv_two_epilogue_groups(dtype, B, src_c, N, hw, opts):
     w = (torch.randn(N, K, generator=gen) * K ** -0.5).to(DEV)
     bias = torch.randn(N, generator=gen).to(DEV)
     res = torch.randn(B, N, H, W, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl) if opts.get("res") else None
-    want = torch.nn.functional.silu(torch.einsum("bkhw,nk->bnhw", torch.cat([t.float() for t in srcs], 1), w.to(dtype).float()) + bias.view(1, -1, 1, 1))
+    pre = torch.einsum("bkhw,nk->bnhw", torch.cat([t.float() for t in srcs], 1), w.to(dtype).float()) + bias.view(1, -1, 1, 1)
+    z = torch.randn(B, N, H // 2, W // 2, generator=gen).to(DEV).to(dtype).contiguous(memory_format=cl) if opts.get("up") else None
+    if z is not None:
+        pre = pre + torch.nn.functional.interpolate(z.float(), scale_factor=2, mode="nearest")
+    want = torch.nn.functional.silu(pre)
     if res is not None:
         want = res.float() + want
     wpk = o.pack_pw_weight(w, src_c, dtype, B * H * W)
+    if z is not None:
+        got = o.pwconv(srcs, wpk, N, bias=bias, act=o.ACT_SILU, up_addend=z)
+        close(got, want, 2e-2, 2e-2)
+        return
     if opts.get("split"):
         a = torch.empty(B, opts["split"], H, W, device=DEV, dtype=dtype).contiguous(memory_format=cl)
         b = torch.empty(B, N - opts["split"], H, W, device=DEV, dtype=dtype).contiguous(memory_format=cl)
